@@ -1,0 +1,508 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of faabric_b200 (driver contract).
+
+Headline (``--mode allreduce``, default): the reference's OWN all-reduce
+benchmark workload (tests/dist/mpi/benchmarks/mpi_allreduce.cpp, "large"
+payload): one pass = 214 MPI_Allreduce(MPI_INT, MPI_SUM) calls over the
+ResNet-50 gradient tensors (25,583,592 int32 = 97.6 MiB).  A *step* is one
+pass.  ``value`` is the whole-job algorithmic bandwidth  N * S / t  in GB/s
+(S = bytes per rank per pass); ``busbw_GBps`` = 2(N-1)/N * S / t is reported
+next to it against NVLink.  Device-timed with CUDA events, max over ranks.
+
+Other modes (each prints one JSON line and appends to --out):
+  sweep     MpiWorld allreduce bus GB/s 1 KB..1 GB, ours (per algo) vs NCCL
+  alltoall  all-to-all bus GB/s 1 KB..64 MB per rank, ours vs NCCL
+  snapshot  1 GB region diff+push at 1..50 % dirty (MB/s), vs CPU oracle rate
+  planner   1024-function fan-out / fan-in through the native planner (us)
+
+Launch:  python bench.py --gpus 1          (single process)
+         python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+                --master-addr 127.0.0.1 --master-port P bench.py --gpus N
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--mode", default="allreduce",
+                    choices=["allreduce", "sweep", "alltoall", "snapshot", "planner"])
+    ap.add_argument("--algo", default="auto")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--payload", default="large", choices=["large", "small"])
+    ap.add_argument("--out", default="")
+    ap.add_argument("--max-bytes", type=int, default=1 << 30)
+    ap.add_argument("--region-mb", type=int, default=1024)
+    return ap.parse_args()
+
+
+def reference_arm(args):
+    """The reference (faasm/faabric) is a conan/CMake C++ project; the offline
+    pip install of /root/reference produces an empty 'UNKNOWN' package and its
+    C++ build needs boost/protobuf/flatbuffers/nng/absl/spdlog/hiredis/zstd/
+    catch2 + clang-17, none of which exist in this image."""
+    print(json.dumps({
+        "impl": "reference",
+        "unavailable": "faabric is a conan+CMake C++ project: pip install of /root/reference yields an empty "
+                       "package and its deps (boost, protobuf, flatbuffers, nng, absl, spdlog, hiredis, zstd) "
+                       "are not installable offline",
+    }))
+    return 0
+
+
+# ----------------------------------------------------------------------------
+# distributed plumbing
+# ----------------------------------------------------------------------------
+class Dist:
+    def __init__(self, want_gpus: int):
+        import torch
+
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.multi = self.world > 1
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device")
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        self.pg = None
+        if self.multi:
+            import torch.distributed as dist
+
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.device)
+            self.pg = dist
+        if want_gpus != self.world and self.rank == 0 and self.world > 1:
+            print(f"[bench] --gpus {want_gpus} but WORLD_SIZE={self.world}; using WORLD_SIZE", file=sys.stderr)
+
+    def barrier(self):
+        if self.pg is not None:
+            self.pg.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v: float) -> float:
+        if self.pg is None:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.device)
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.MAX)
+        return float(t.item())
+
+    def make_comm(self, **cfg):
+        from faabric_b200.parallel import LocalGroup, init_from_env
+
+        if self.multi:
+            return init_from_env(**cfg), None
+        g = LocalGroup(1, devices=[self.local], **cfg)
+        return g.comms[0], g
+
+    def close(self):
+        if self.pg is not None:
+            self.pg.destroy_process_group()
+
+
+def timed(dist: Dist, fn, steps: int, warmup: int):
+    """W untimed warm-ups, then exactly `steps` calls bracketed by a barrier +
+    synchronize on both sides and CUDA events; returns max-over-ranks ms/step."""
+    torch = dist.torch
+    for _ in range(warmup):
+        fn()
+    dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    dist.barrier()
+    return dist.max_over_ranks(ms)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "fallback": True}
+
+
+# ----------------------------------------------------------------------------
+# headline: ResNet-50 gradient all-reduce pass
+# ----------------------------------------------------------------------------
+def mode_allreduce(args, dist: Dist):
+    import torch
+    from faabric_b200.models import GradientSync, resnet50_grad_sizes, small_sizes
+    from faabric_b200.utils import ClockSampler
+
+    sizes = resnet50_grad_sizes() if args.payload == "large" else small_sizes()
+    n = dist.world
+    S = sum(sizes) * 4
+    result = {}
+
+    if args.impl == "nccl":
+        if not dist.multi:
+            raise SystemExit("--impl nccl needs >1 rank")
+        bufs = [torch.zeros(s, dtype=torch.int32, device=dist.device) for s in sizes]
+
+        def step():
+            for b in bufs:
+                dist.pg.all_reduce(b)
+
+        sampler = ClockSampler(gpu_index=dist.local).start() if dist.rank == 0 else None
+        ms = timed(dist, step, args.steps, args.warmup)
+        clocks = sampler.stop() if sampler else {}
+        launches = 0
+        e2e = None
+        cfg_extra = {"library": "torch.distributed NCCL all_reduce (baseline, not the product)"}
+    else:
+        comm, group = dist.make_comm(heapBytes=(512 << 20), stageBytes=(16 << 20))
+        sync = GradientSync(comm, sizes, dtype=torch.int32, algo=args.algo, use_graph=not args.no_graph)
+        # deterministic non-trivial contents
+        sync.send.copy_(torch.arange(sync.send.numel(), device=dist.device, dtype=torch.int32) % 1000 + dist.rank)
+        torch.cuda.synchronize()
+        # ---- correctness spot check before timing
+        sync.step()
+        torch.cuda.synchronize()
+        exp0 = (torch.arange(sizes[0], device=dist.device, dtype=torch.int64) % 1000) * n + n * (n - 1) // 2
+        if not torch.equal(sync.recv_views[0].to(torch.int64), exp0):
+            raise SystemExit("all-reduce result mismatch")
+        comm.stats(reset=True)
+        sampler = ClockSampler(gpu_index=dist.local).start() if dist.rank == 0 else None
+        ms = timed(dist, sync.step, args.steps, args.warmup)
+        clocks = sampler.stop() if sampler else {}
+        launches = sync.launches_per_step * args.steps
+        err = comm.check_error()
+        if err:
+            raise SystemExit(f"device watchdog error {err}")
+        # ---- end to end through the public API: pinned host -> H2D -> allreduce -> D2H
+        host = torch.empty(sync.total_padded, dtype=torch.int32).pin_memory()
+        host.copy_((torch.arange(sync.total_padded, dtype=torch.int32) % 1000) + dist.rank)
+        for _ in range(max(3, args.warmup)):
+            sync.step_from_host(host)
+        dist.barrier()
+        t0 = time.perf_counter()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            digest = sync.step_from_host(host)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = dist.max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        wall_ms = dist.max_over_ranks((time.perf_counter() - t0) * 1000 / args.steps)
+        e2e_ms = max(e2e_ms, wall_ms)  # host-synchronous steps: the wall clock governs
+        exp_first = 0 * n + n * (n - 1) // 2
+        if int(digest[0]) != exp_first:
+            raise SystemExit(f"e2e digest mismatch {int(digest[0])} != {exp_first}")
+        e2e = {
+            "value": round(n * S / (e2e_ms * 1e-3) / 1e9, 3),
+            "unit": "GB/s",
+            "ms_per_step": round(e2e_ms, 4),
+            "h2d_bytes_per_step": sync.h2d_bytes_per_step,
+            "d2h_bytes_per_step": sync.d2h_bytes_per_step,
+        }
+        st = comm.stats()
+        cfg_extra = {
+            "backing": comm.backing,
+            "nvls": comm.has_multicast,
+            "cuda_graph": not args.no_graph,
+            "algo": args.algo,
+            "algo_mix": {k: v for k, v in st.items() if k.startswith("algo_") and v},
+        }
+        result["_keep"] = (sync, comm, group)
+
+    algbw = n * S / (ms * 1e-3) / 1e9
+    busbw = (2 * (n - 1) / n) * S / (ms * 1e-3) / 1e9 if n > 1 else 0.0
+    pk = peaks()
+    out = {
+        "metric": "mpi_allreduce_resnet50_grads_algbw_GBps",
+        "value": round(algbw, 3),
+        "unit": "GB/s",
+        "n_gpus": n,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": round(ms, 4),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "int32",
+        "data": "synthetic",
+        "impl": args.impl,
+        "busbw_GBps": round(busbw, 3),
+        "busbw_frac_of_nvlink_770": round(busbw / 770.0, 4) if n > 1 else None,
+        "us_per_allreduce": round(ms * 1000 / len(sizes), 3),
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "config": {
+            "model": "resnet50-gradients (reference mpi_bench 'large' payload)" if args.payload == "large"
+            else "1000 x 8-int messages (reference 'small' payload)",
+            "tensors": len(sizes),
+            "elements": sum(sizes),
+            "bytes_per_rank_per_step": S,
+            "global_batch": None,
+            "seq_len": None,
+            "parallelism": f"dp{n}",
+            "op": "MPI_Allreduce(MPI_INT, MPI_SUM) per tensor",
+            "l2": "inputs+outputs per step = 2 x 97.6 MiB > 126 MB L2 (no flush needed)",
+            "timing": "CUDA events, barrier+sync both sides, max over ranks",
+            "value_definition": "N*S/t (whole-job bytes all-reduced per second); busbw=2(N-1)/N*S/t",
+            "measured_hbm_gbs": pk.get("hbm_gbs"),
+            **cfg_extra,
+        },
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    return out, result
+
+
+# ----------------------------------------------------------------------------
+# sweep: allreduce bus bandwidth by size, ours (each algo) vs NCCL
+# ----------------------------------------------------------------------------
+def _sizes(lo, hi):
+    s = lo
+    out = []
+    while s <= hi:
+        out.append(s)
+        s *= 4
+    if out[-1] != hi:
+        out.append(hi)
+    return out
+
+
+def mode_sweep(args, dist: Dist):
+    import torch
+
+    n = dist.world
+    maxb = args.max_bytes
+    comm, group = dist.make_comm(heapBytes=2 * maxb + (64 << 20), stageBytes=(16 << 20), maxBlocks=64)
+    send = comm.empty(maxb // 4, torch.float32)
+    recv = comm.empty(maxb // 4, torch.float32)
+    send.fill_(1.0)
+    rows = []
+    algos = ["ll", "oneshot", "twoshot"] + (["nvls"] if comm.has_multicast else []) + ["auto"]
+    for nbytes in _sizes(1024, maxb):
+        numel = nbytes // 4
+        row = {"bytes": nbytes}
+        iters = 200 if nbytes <= (1 << 20) else (40 if nbytes <= (64 << 20) else 10)
+        for algo in algos:
+            if algo == "ll" and nbytes > 65536:
+                continue
+            if algo == "oneshot" and nbytes > (16 << 20):
+                continue
+            s, r = send[:numel], recv[:numel]
+            try:
+                ms = timed(dist, lambda: comm.all_reduce(s, r, algo=algo), iters, 5)
+            except Exception as e:  # noqa: BLE001
+                row[algo] = f"error: {e}"
+                continue
+            row[algo + "_us"] = round(ms * 1000, 2)
+            row[algo + "_busbw"] = round((2 * (n - 1) / n) * nbytes / (ms * 1e-3) / 1e9, 2) if n > 1 else round(nbytes / (ms * 1e-3) / 1e9, 2)
+            if algo == "auto":
+                row["auto_pick"] = comm.last_algo
+        if dist.multi:
+            t = torch.ones(numel, dtype=torch.float32, device=dist.device)
+            ms = timed(dist, lambda: dist.pg.all_reduce(t), iters, 5)
+            row["nccl_us"] = round(ms * 1000, 2)
+            row["nccl_busbw"] = round((2 * (n - 1) / n) * nbytes / (ms * 1e-3) / 1e9, 2)
+        rows.append(row)
+        if dist.rank == 0:
+            print("[sweep]", json.dumps(row), file=sys.stderr, flush=True)
+    err = comm.check_error()
+    best = max((r.get("auto_busbw", 0) for r in rows), default=0)
+    out = {
+        "metric": "mpi_allreduce_busbw_sweep_GBps",
+        "value": best,
+        "unit": "GB/s (peak auto bus bandwidth in sweep)",
+        "n_gpus": n,
+        "dtype": "fp32",
+        "data": "synthetic",
+        "higher_is_better": True,
+        "device_error": err,
+        "backing": comm.backing,
+        "nvls": comm.has_multicast,
+        "rows": rows,
+        "roofline": "NVLink5 770 GB/s measured per direction per GPU (900 nominal)",
+    }
+    return out, {"_keep": (comm, group, send, recv)}
+
+
+def mode_alltoall(args, dist: Dist):
+    import torch
+
+    n = dist.world
+    max_per_rank = min(args.max_bytes, 64 << 20)
+    comm, group = dist.make_comm(heapBytes=2 * max_per_rank * n + (64 << 20), stageBytes=(16 << 20), maxBlocks=64)
+    send = comm.empty(max_per_rank * n // 4, torch.float32)
+    recv = comm.empty(max_per_rank * n // 4, torch.float32)
+    send.fill_(2.0)
+    rows = []
+    for per in _sizes(1024, max_per_rank):
+        numel = per * n // 4
+        iters = 200 if per <= (1 << 20) else 30
+        s, r = send[:numel], recv[:numel]
+        ms = timed(dist, lambda: comm.all_to_all(s, r), iters, 5)
+        total = per * n
+        row = {
+            "bytes_per_rank_pair": per,
+            "ours_us": round(ms * 1000, 2),
+            "ours_busbw": round(((n - 1) / n) * total / (ms * 1e-3) / 1e9, 2) if n > 1 else round(total / (ms * 1e-3) / 1e9, 2),
+        }
+        if dist.multi:
+            a = torch.ones(numel, dtype=torch.float32, device=dist.device)
+            b = torch.empty_like(a)
+            ms2 = timed(dist, lambda: dist.pg.all_to_all_single(b, a), iters, 5)
+            row["nccl_us"] = round(ms2 * 1000, 2)
+            row["nccl_busbw"] = round(((n - 1) / n) * total / (ms2 * 1e-3) / 1e9, 2)
+        rows.append(row)
+        if dist.rank == 0:
+            print("[alltoall]", json.dumps(row), file=sys.stderr, flush=True)
+    out = {
+        "metric": "mpi_alltoall_busbw_sweep_GBps",
+        "value": max(r["ours_busbw"] for r in rows),
+        "unit": "GB/s (peak)",
+        "n_gpus": n,
+        "dtype": "fp32",
+        "data": "synthetic",
+        "higher_is_better": True,
+        "device_error": comm.check_error(),
+        "rows": rows,
+    }
+    return out, {"_keep": (comm, group, send, recv)}
+
+
+def mode_snapshot(args, dist: Dist):
+    """1 GB region: every non-main GPU diffs its memory against its base image
+    and pushes the merged bytes straight into the main GPU's image."""
+    import numpy as np
+    import torch
+    from faabric_b200.ops import snapshot as snap
+
+    n = dist.world
+    size = args.region_mb << 20
+    comm, group = dist.make_comm(heapBytes=size + (64 << 20), stageBytes=(16 << 20))
+    main_img = comm.empty(size, torch.uint8)  # symmetric: rank 0's copy is the main image
+    main_img.zero_()
+    base = torch.zeros(size, dtype=torch.uint8, device=dist.device)
+    mem = torch.zeros(size, dtype=torch.uint8, device=dist.device)
+    regs = snap.prepare_regions([], size, dist.device)
+    # peer-mapped pointer of rank 0's image
+    dst_ptr = comm._lib.fb_comm_heap_ptr(comm._h, comm.heap_offset(main_img), 0)
+    n_pages = size // 4096
+    rows = []
+    gen = torch.Generator(device=dist.device).manual_seed(1234 + dist.rank)
+    for pct in (1, 5, 10, 25, 50):
+        n_dirty = n_pages * pct // 100
+        perm = torch.randperm(n_pages, generator=gen, device=dist.device)[:n_dirty]
+        mem.copy_(base)
+        mem.view(n_pages, 4096)[perm] = torch.randint(
+            1, 255, (n_dirty, 4096), dtype=torch.uint8, device=dist.device, generator=gen
+        )
+        flags = torch.zeros(n_pages, dtype=torch.uint8, device=dist.device)
+        flags[perm] = 1
+        stats = torch.zeros(2, dtype=torch.int64, device=dist.device)
+        torch.cuda.synchronize()
+        row = {"dirty_pct": pct, "dirty_bytes": n_dirty * 4096}
+        for label, dirty in (("scan_all", None), ("tracked", flags)):
+            def run():
+                stats.zero_()
+                snap.diff_push(mem, base, dst_ptr, regs, dirty_pages=dirty, stats=stats)
+            ms = timed(dist, run, max(3, args.steps // 2), 3)
+            row[label + "_ms"] = round(ms, 4)
+            row[label + "_region_GBps"] = round(size / (ms * 1e-3) / 1e9, 1)
+            row[label + "_dirty_GBps"] = round(n_dirty * 4096 / (ms * 1e-3) / 1e9, 1)
+        row["diff_bytes"] = int(stats[0].item())
+        # roofline: max(2*region/HBM (scan), dirty/NVLink)
+        pk = peaks()
+        t_scan = 2 * size / (pk.get("hbm_gbs", 6650.0) * 1e9)
+        t_push = (n_dirty * 4096) / 770e9 if n > 1 else (n_dirty * 4096) / (pk.get("hbm_gbs", 6650.0) * 1e9)
+        row["roofline_ms_scan_all"] = round(max(t_scan, t_push) * 1e3, 4)
+        row["frac_of_roofline_scan_all"] = round(max(t_scan, t_push) * 1e3 / row["scan_all_ms"], 3)
+        rows.append(row)
+        if dist.rank == 0:
+            print("[snapshot]", json.dumps(row), file=sys.stderr, flush=True)
+    # CPU oracle rate (reference semantics: 128-B chunk memcmp + byte runs + memcpy)
+    cpu = {}
+    if dist.rank == 0:
+        a = np.zeros(64 << 20, dtype=np.uint8)
+        b = a.copy()
+        b[:: 4096 * 10] = 1
+        t0 = time.perf_counter()
+        d = np.nonzero(a.reshape(-1, 128) != b.reshape(-1, 128))[0]
+        cpu["numpy_compare_GBps"] = round(len(a) / (time.perf_counter() - t0) / 1e9, 2)
+        cpu["chunks"] = int(len(d))
+    out = {
+        "metric": "snapshot_diff_push_region_MBps",
+        "value": round(rows[0]["scan_all_region_GBps"] * 1000, 1),
+        "unit": "MB/s of region processed per GPU (1% dirty, scan-all mode)",
+        "n_gpus": n,
+        "region_bytes": size,
+        "data": "synthetic",
+        "higher_is_better": True,
+        "rows": rows,
+        "cpu_oracle": cpu,
+        "note": "every rank pushes into rank 0's image over NVLink (rank 0 pushes locally)",
+    }
+    return out, {"_keep": (comm, group, main_img)}
+
+
+def mode_planner(args, dist: Dist):
+    from faabric_b200.runtime import planner_fanout_bench
+
+    res = planner_fanout_bench(n_functions=1024, n_hosts=max(dist.world, 8), iters=max(args.steps, 5))
+    out = {
+        "metric": "planner_fanout_fanin_1024_us",
+        "value": res["us_per_batch_median"],
+        "unit": "us",
+        "higher_is_better": False,
+        "n_gpus": dist.world,
+        "details": res,
+    }
+    return out, {}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    dist = Dist(args.gpus)
+    fn = {
+        "allreduce": mode_allreduce,
+        "sweep": mode_sweep,
+        "alltoall": mode_alltoall,
+        "snapshot": mode_snapshot,
+        "planner": mode_planner,
+    }[args.mode]
+    out, keep = fn(args, dist)
+    if dist.rank == 0:
+        line = json.dumps(out)
+        print(line, flush=True)
+        if args.out:
+            Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+            with open(args.out, "a") as f:
+                f.write(line + "\n")
+    dist.barrier()
+    del keep
+    dist.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,239 @@
+// Communicator: one per MPI rank / GPU.  Owns the symmetric heap + signal pad,
+// knows every peer's mapping of them (NVLink P2P, optional NVLS multicast) and
+// launches the fused collective kernels.  All operations are stream-ordered
+// and never synchronise the host; they are CUDA-graph capturable.
+//
+// Two wiring modes:
+//   * local : all ranks live in this process (rank threads, like the
+//             reference's one-thread-per-rank model), one or several GPUs;
+//             several ranks may share a GPU (used by single-GPU tests).
+//   * ipc   : one process per GPU (torchrun-style); handles are exchanged over
+//             the Unix-socket Bootstrap (VMM fds, or legacy CUDA IPC).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "faabric/device/comm_abi.h"
+
+namespace faabric::device {
+
+class Bootstrap;
+
+// Buffers are symmetric-heap pointers at identical offsets on every rank
+#define FB_FLAG_SYMMETRIC 1
+// Skip cross-rank synchronisation (profiling a single rank's data path only)
+#define FB_FLAG_NOSYNC 2
+
+struct CommConfig
+{
+    size_t heapBytes = (size_t)256 << 20; // user-visible symmetric heap
+    size_t stageBytes = (size_t)32 << 20; // each of the two staging buffers
+    size_t slotBytes = (size_t)128 << 10; // p2p eager slot
+    uint64_t timeoutMs = 10000;           // device spin watchdog
+    bool useVmm = true;
+    bool useMulticast = true;
+    int maxBlocks = 32;
+    int threads = 512;
+    // algorithm thresholds (bytes); the autotuner overwrites these
+    size_t llMaxBytes = 32 << 10;
+    size_t oneShotMaxBytes = 256 << 10;
+    size_t nvlsMinBytes = 128 << 10;
+    size_t bcast2StepMinBytes = 1 << 20;
+
+    // Fills defaults from FAABRIC_* environment variables
+    static CommConfig fromEnv();
+};
+
+struct CommStats
+{
+    uint64_t launches = 0;
+    uint64_t bytes = 0;
+    uint64_t algoCount[FB_ALGO_COUNT] = { 0 };
+    uint64_t stagedCopies = 0;
+};
+
+class Communicator
+{
+  public:
+    ~Communicator();
+
+    static std::vector<std::shared_ptr<Communicator>> createLocal(
+      int nranks,
+      const std::vector<int>& devices,
+      const CommConfig& cfg);
+
+    static std::shared_ptr<Communicator> createIpc(int rank,
+                                                   int nranks,
+                                                   int device,
+                                                   const std::string& jobId,
+                                                   const CommConfig& cfg);
+
+    int rank() const { return dev_.rank; }
+    int size() const { return dev_.nranks; }
+    int device() const { return device_; }
+    bool hasMulticast() const { return dev_.mcHeap != nullptr; }
+    const std::string& backing() const { return backing_; }
+    const FbCommDev& devStruct() const { return dev_; }
+    CommConfig& config() { return cfg_; }
+    const CommStats& stats() const { return stats_; }
+    void resetStats() { stats_ = CommStats(); }
+
+    // ---- symmetric heap allocator (call collectively, same order/sizes) ----
+    // Returns an offset usable with heapPtr(); throws std::bad_alloc when full
+    uint64_t alloc(size_t bytes, size_t align = 256);
+    void free(uint64_t offset);
+    uint8_t* heapPtr(uint64_t offset, int rank = -1) const;
+    bool inHeap(const void* p, size_t bytes = 1) const;
+    uint64_t offsetOf(const void* p) const;
+    size_t userHeapBytes() const { return cfg_.heapBytes; }
+
+    // ---- collectives.  Return 0 or a negative FB_E_* code.  `bytes`-based
+    // calls are type-agnostic; reductions take FbDtype / FbOp. ----
+    int allReduce(const void* send,
+                  void* recv,
+                  size_t count,
+                  int dtype,
+                  int op,
+                  int algo,
+                  int flags,
+                  cudaStream_t s);
+    int reduce(const void* send,
+               void* recv,
+               size_t count,
+               int dtype,
+               int op,
+               int root,
+               int flags,
+               cudaStream_t s);
+    int reduceScatter(const void* send,
+                      void* recv,
+                      size_t recvCount,
+                      int dtype,
+                      int op,
+                      int flags,
+                      cudaStream_t s);
+    int scan(const void* send,
+             void* recv,
+             size_t count,
+             int dtype,
+             int op,
+             int flags,
+             cudaStream_t s);
+    int broadcast(void* buf, size_t bytes, int root, int flags, cudaStream_t s);
+    int allGather(const void* send,
+                  void* recv,
+                  size_t bytesPerRank,
+                  int flags,
+                  cudaStream_t s);
+    int gather(const void* send,
+               void* recv,
+               size_t bytesPerRank,
+               int root,
+               int flags,
+               cudaStream_t s);
+    int scatter(const void* send,
+                void* recv,
+                size_t bytesPerRank,
+                int root,
+                int flags,
+                cudaStream_t s);
+    int allToAll(const void* send,
+                 void* recv,
+                 size_t bytesPerRank,
+                 int flags,
+                 cudaStream_t s);
+    int barrier(cudaStream_t s);
+
+    // ---- point to point (device-side mailbox, per-pair FIFO) ----
+    int send(const void* buf, size_t bytes, int peer, cudaStream_t s);
+    int recv(void* buf, size_t bytes, int peer, cudaStream_t s);
+    // zero-copy put into a peer's symmetric buffer + signal bump
+    int putSignal(const void* local,
+                  uint64_t dstOffset,
+                  size_t bytes,
+                  int peer,
+                  int signalIdx,
+                  int blocks,
+                  cudaStream_t s);
+    int waitSignal(int signalIdx, uint32_t count, cudaStream_t s);
+
+    // Device watchdog error word (FB_ERR_*); synchronises `s`
+    uint32_t checkError(cudaStream_t s);
+    // Host-side barrier between the ranks' host threads / processes
+    void hostBarrier();
+    // Last algorithm picked by allReduce (for reporting / tests)
+    int lastAlgo() const { return lastAlgo_; }
+
+    static const char* errorString(int code);
+
+  private:
+    Communicator() = default;
+
+    FbCommDev dev_{};
+    CommConfig cfg_;
+    CommStats stats_;
+    int device_ = 0;
+    std::string backing_;
+    int lastAlgo_ = 0;
+
+    // heap layout (offsets from heap base)
+    uint64_t llOff_ = 0;
+    uint64_t mboxOff_ = 0;
+    uint64_t stageSendOff_ = 0;
+    uint64_t stageRecvOff_ = 0;
+    uint64_t userOff_ = 0;
+    uint64_t heapTotal_ = 0;
+
+    // allocator state
+    std::mutex allocMx_;
+    std::map<uint64_t, uint64_t> freeList_; // offset -> size
+    std::map<uint64_t, uint64_t> allocated_;
+
+    struct Backing;
+    std::shared_ptr<Backing> backingState_;
+    std::shared_ptr<Bootstrap> bootstrap_;
+    // local mode: shared host barrier
+    struct LocalGroup;
+    std::shared_ptr<LocalGroup> localGroup_;
+
+    void computeLayout();
+    void initAllocator();
+    int blocksFor(uint64_t vecs, int perThread) const;
+    int widthFor(const void* a, const void* b, uint64_t bytes) const;
+    FbCommDev devFor(int flags) const;
+
+    int reduceLike(int kind,
+                   const void* send,
+                   void* recv,
+                   size_t count,
+                   int dtype,
+                   int op,
+                   int root,
+                   int algo,
+                   int flags,
+                   cudaStream_t s);
+    int moveLike(int mode,
+                 const void* send,
+                 void* recv,
+                 size_t chunkBytes,
+                 int root,
+                 int flags,
+                 cudaStream_t s);
+};
+
+// Error codes
+#define FB_OK 0
+#define FB_E_UNSUPPORTED -1 // (dtype, op) pair not supported
+#define FB_E_INVALID -2     // bad argument
+#define FB_E_CUDA -3        // CUDA runtime error
+#define FB_E_TOO_LARGE -4   // message does not fit the staging area
+#define FB_E_NO_DEVICE -5
+
+} // namespace faabric::device

@@ -1,0 +1,519 @@
+// Type-agnostic data-movement collectives over peer-mapped memory:
+// allGather / allToAll / gather / scatter / broadcast (pull: every rank loads
+// its peers' symmetric send buffers straight into a local output) plus the
+// two-step large-message broadcast, the cross-rank barrier, and the
+// device-side point-to-point mailbox (eager slots + put-with-signal).
+//
+// Reference algorithms replaced: MpiWorld::{broadcast,scatter,gather,allGather,
+// allToAll,barrier,send,recv} message loops (src/mpi/MpiWorld.cpp:590-1111,
+// 1433-1485,1753-1775).
+#include "coll_move.cuh"
+
+namespace fb {
+
+// ----------------------------------------------------------------------------
+// Generic copy helpers
+// ----------------------------------------------------------------------------
+template<int W>
+struct Word;
+template<>
+struct Word<16>
+{
+    using type = Vec16;
+    __device__ __forceinline__ static Vec16 ld(const uint8_t* p)
+    {
+        return ldVecStream(p);
+    }
+    __device__ __forceinline__ static void st(uint8_t* p, const Vec16& v)
+    {
+        stVec(p, v);
+    }
+};
+template<>
+struct Word<4>
+{
+    using type = uint32_t;
+    __device__ __forceinline__ static uint32_t ld(const uint8_t* p)
+    {
+        return *reinterpret_cast<const volatile uint32_t*>(p);
+    }
+    __device__ __forceinline__ static void st(uint8_t* p, uint32_t v)
+    {
+        *reinterpret_cast<volatile uint32_t*>(p) = v;
+    }
+};
+template<>
+struct Word<1>
+{
+    using type = uint8_t;
+    __device__ __forceinline__ static uint8_t ld(const uint8_t* p)
+    {
+        return *reinterpret_cast<const volatile uint8_t*>(p);
+    }
+    __device__ __forceinline__ static void st(uint8_t* p, uint8_t v)
+    {
+        *reinterpret_cast<volatile uint8_t*>(p) = v;
+    }
+};
+
+// Grid-strided copy of `bytes` (multiple of W) with 4 words in flight/thread
+template<int W>
+__device__ __forceinline__ void gridCopy(uint8_t* dst,
+                                         const uint8_t* src,
+                                         uint64_t bytes,
+                                         uint64_t tid,
+                                         uint64_t nthreads)
+{
+    using WT = typename Word<W>::type;
+    const uint64_t n = bytes / W;
+    uint64_t i = tid;
+    for (; i + 3 * nthreads < n; i += 4 * nthreads) {
+        WT v0 = Word<W>::ld(src + i * W);
+        WT v1 = Word<W>::ld(src + (i + nthreads) * W);
+        WT v2 = Word<W>::ld(src + (i + 2 * nthreads) * W);
+        WT v3 = Word<W>::ld(src + (i + 3 * nthreads) * W);
+        Word<W>::st(dst + i * W, v0);
+        Word<W>::st(dst + (i + nthreads) * W, v1);
+        Word<W>::st(dst + (i + 2 * nthreads) * W, v2);
+        Word<W>::st(dst + (i + 3 * nthreads) * W, v3);
+    }
+    for (; i < n; i += nthreads) {
+        Word<W>::st(dst + i * W, Word<W>::ld(src + i * W));
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Pull-style collectives
+// ----------------------------------------------------------------------------
+template<int W, int NR>
+__global__ void __launch_bounds__(512, 1) moveKernel(const MoveArgs a)
+{
+    using WT = typename Word<W>::type;
+    BlockBarrier bar;
+    bar.load(a.comm);
+    bool ok = true;
+    if (!a.noSync) {
+        ok = bar.sync(a.comm);
+    }
+    const int rank = a.comm.rank;
+    const int n = a.comm.nranks;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+
+    if (ok) {
+        if (a.mode == MOVE_ALLGATHER || a.mode == MOVE_ALLTOALL ||
+            (a.mode == MOVE_GATHER && rank == a.root)) {
+            const uint64_t srcExtra =
+              (a.mode == MOVE_ALLTOALL) ? (uint64_t)rank * a.srcStride : 0;
+            const uint64_t words = a.chunkBytes / W;
+            if constexpr (NR > 0) {
+                // one word from every peer in flight per thread
+                for (uint64_t i = tid; i < words; i += nthreads) {
+                    WT v[NR];
+#pragma unroll
+                    for (int p = 0; p < NR; p++) {
+                        v[p] = Word<W>::ld(a.comm.heap[p] + a.sendOff +
+                                           srcExtra + i * W);
+                    }
+#pragma unroll
+                    for (int p = 0; p < NR; p++) {
+                        Word<W>::st(a.recvLocal + (uint64_t)p * a.dstStride +
+                                      i * W,
+                                    v[p]);
+                    }
+                }
+            } else {
+                for (int q = 0; q < n; q++) {
+                    // start at own rank to spread the load over the peers
+                    int p = (rank + q) % n;
+                    gridCopy<W>(a.recvLocal + (uint64_t)p * a.dstStride,
+                                a.comm.heap[p] + a.sendOff + srcExtra,
+                                a.chunkBytes,
+                                tid,
+                                nthreads);
+                }
+            }
+        } else if (a.mode == MOVE_SCATTER) {
+            gridCopy<W>(a.recvLocal,
+                        a.comm.heap[a.root] + a.sendOff +
+                          (uint64_t)rank * a.srcStride,
+                        a.chunkBytes,
+                        tid,
+                        nthreads);
+        } else if (a.mode == MOVE_BCAST) {
+            if (rank != a.root) {
+                gridCopy<W>(a.recvLocal,
+                            a.comm.heap[a.root] + a.sendOff,
+                            a.chunkBytes,
+                            tid,
+                            nthreads);
+            }
+        } else if (a.mode == MOVE_BCAST_2STEP) {
+            // Step 1: rank r pulls slice r from the root into its symmetric
+            // buffer (root egress = (N-1)/N * S instead of (N-1) * S)
+            const uint64_t total = a.chunkBytes;
+            uint64_t slice = ((total / n) + 15) & ~(uint64_t)15;
+            uint64_t myBeg = min((uint64_t)rank * slice, total);
+            uint64_t myEnd = (rank == n - 1) ? total
+                                             : min(myBeg + slice, total);
+            if (rank != a.root && myEnd > myBeg) {
+                // W divides (myEnd - myBeg) for every slice but possibly the
+                // last; the host guarantees total % W == 0
+                gridCopy<W>(a.comm.heap[rank] + a.recvOff + myBeg,
+                            a.comm.heap[a.root] + a.sendOff + myBeg,
+                            myEnd - myBeg,
+                            tid,
+                            nthreads);
+            }
+            ok = a.noSync ? true : bar.sync(a.comm);
+            // Step 2: pull every other slice from its owner
+            if (ok && rank != a.root) {
+                for (int q = 1; q < n; q++) {
+                    int p = (rank + q) % n;
+                    uint64_t b = min((uint64_t)p * slice, total);
+                    uint64_t e =
+                      (p == n - 1) ? total : min(b + slice, total);
+                    if (e <= b) {
+                        continue;
+                    }
+                    const uint8_t* src = (p == a.root)
+                                           ? a.comm.heap[p] + a.sendOff + b
+                                           : a.comm.heap[p] + a.recvOff + b;
+                    gridCopy<W>(a.comm.heap[rank] + a.recvOff + b,
+                                src,
+                                e - b,
+                                tid,
+                                nthreads);
+                }
+            }
+        }
+    }
+    if (!a.noSync) {
+        bar.sync(a.comm);
+    }
+    bar.store(a.comm);
+}
+
+template<int W>
+static cudaError_t launchMoveW(const MoveArgs& a,
+                               int blocks,
+                               int threads,
+                               cudaStream_t s)
+{
+    int n = a.comm.nranks;
+    if (n == 2) {
+        moveKernel<W, 2><<<blocks, threads, 0, s>>>(a);
+    } else if (n == 4) {
+        moveKernel<W, 4><<<blocks, threads, 0, s>>>(a);
+    } else if (n == 8) {
+        moveKernel<W, 8><<<blocks, threads, 0, s>>>(a);
+    } else {
+        moveKernel<W, 0><<<blocks, threads, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launchMove(const MoveArgs& a,
+                       int width,
+                       int blocks,
+                       int threads,
+                       cudaStream_t s)
+{
+    if (width == 16) {
+        return launchMoveW<16>(a, blocks, threads, s);
+    }
+    if (width == 4) {
+        return launchMoveW<4>(a, blocks, threads, s);
+    }
+    return launchMoveW<1>(a, blocks, threads, s);
+}
+
+// ----------------------------------------------------------------------------
+// Barrier
+// ----------------------------------------------------------------------------
+__global__ void barrierKernel(const FbCommDev c)
+{
+    BlockBarrier bar;
+    bar.load(c);
+    bar.sync(c);
+    bar.store(c);
+}
+
+cudaError_t launchBarrier(const FbCommDev& c, cudaStream_t s)
+{
+    barrierKernel<<<1, 32, 0, s>>>(c);
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------
+// Point-to-point mailbox.
+//
+// Every ordered pair (src -> dst) owns, in the *receiver's* memory,
+// FB_P2P_BLOCKS sub-channels with two eager slots each.  CTA b of the send
+// kernel on src streams its share of the message into sub-channel b of dst
+// (16-byte peer stores) and publishes a sequence number with st.release.sys;
+// CTA b of the recv kernel acquires it, drains the slot into the user buffer
+// and acknowledges into the *sender's* pad so the slot can be reused.  Sequence
+// counters live in device memory, so send/recv compose in stream order and
+// under CUDA-graph replay with no host involvement: per-pair FIFO ordering
+// (the reference's per-(sender,receiver) queue semantics) comes for free.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t* p2pReadyFlag(const FbCommDev& c,
+                                                  int onRank,
+                                                  int src,
+                                                  int blk)
+{
+    return c.sig[onRank] + FB_SIG_MBOX_OFF + (src * FB_P2P_BLOCKS + blk);
+}
+__device__ __forceinline__ uint32_t* p2pAckFlag(const FbCommDev& c,
+                                                int onRank,
+                                                int dst,
+                                                int blk)
+{
+    return c.sig[onRank] + FB_SIG_MBOX_OFF + FB_P2P_FLAG_WORDS +
+           (dst * FB_P2P_BLOCKS + blk);
+}
+__device__ __forceinline__ uint32_t* p2pSendSeq(const FbCommDev& c,
+                                                int dst,
+                                                int blk)
+{
+    return c.sig[c.rank] + FB_SIG_MBOX_OFF + 2 * FB_P2P_FLAG_WORDS +
+           (dst * FB_P2P_BLOCKS + blk);
+}
+__device__ __forceinline__ uint32_t* p2pRecvSeq(const FbCommDev& c,
+                                                int src,
+                                                int blk)
+{
+    return c.sig[c.rank] + FB_SIG_MBOX_OFF + 3 * FB_P2P_FLAG_WORDS +
+           (src * FB_P2P_BLOCKS + blk);
+}
+
+// Bytes handled by CTA b: the message is cut into FB_P2P_BLOCKS contiguous
+// shares (16-byte aligned except the last)
+__device__ __forceinline__ void p2pShare(uint64_t bytes,
+                                         int blk,
+                                         uint64_t& beg,
+                                         uint64_t& end)
+{
+    uint64_t share = ((bytes + FB_P2P_BLOCKS - 1) / FB_P2P_BLOCKS + 15) &
+                     ~(uint64_t)15;
+    beg = min((uint64_t)blk * share, bytes);
+    end = min(beg + share, bytes);
+}
+
+template<int W>
+__device__ __forceinline__ void blockCopy(uint8_t* dst,
+                                          const uint8_t* src,
+                                          uint64_t bytes)
+{
+    gridCopy<W>(dst, src, bytes, threadIdx.x, blockDim.x);
+}
+
+template<int W>
+__global__ void __launch_bounds__(512, 1) p2pSendKernel(const P2PArgs a)
+{
+    const FbCommDev& c = a.comm;
+    const int blk = blockIdx.x;
+    uint64_t beg, end;
+    p2pShare(a.bytes, blk, beg, end);
+
+    __shared__ uint32_t sSeq;
+    __shared__ int sOk;
+    if (threadIdx.x == 0) {
+        sSeq = *p2pSendSeq(c, a.peer, blk);
+        sOk = 1;
+    }
+    __syncthreads();
+    uint32_t seq = sSeq;
+
+    uint8_t* slots = c.heap[a.peer] + a.mboxOff +
+                     ((uint64_t)c.rank * FB_P2P_BLOCKS + blk) * 2 *
+                       a.slotBytes;
+    // Always send at least one (possibly empty) chunk so zero-byte messages
+    // still synchronise, like the reference's empty MPI messages
+    uint64_t off = beg;
+    do {
+        uint64_t len = min(a.slotBytes, end - off);
+        seq += 1;
+        // wait until the slot we are about to overwrite was drained: the
+        // receiver must have acked chunk (seq - 2)
+        if (threadIdx.x == 0) {
+            bool ok = waitFlagGe(
+              c, p2pAckFlag(c, c.rank, a.peer, blk), seq - 2, FB_ERR_FLAG_TIMEOUT);
+            if (!ok) {
+                sOk = 0;
+            }
+        }
+        __syncthreads();
+        if (!sOk) {
+            break;
+        }
+        uint8_t* slot = slots + (uint64_t)(seq & 1) * a.slotBytes;
+        uint64_t lenW = len - (len % W);
+        blockCopy<W>(slot, a.local + off, lenW);
+        if (threadIdx.x == 0) {
+            for (uint64_t b = lenW; b < len; b++) {
+                slot[b] = a.local[off + b];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            stReleaseSys(p2pReadyFlag(c, a.peer, c.rank, blk), seq);
+        }
+        off += len;
+    } while (off < end);
+
+    if (threadIdx.x == 0) {
+        *p2pSendSeq(c, a.peer, blk) = seq;
+    }
+}
+
+template<int W>
+__global__ void __launch_bounds__(512, 1) p2pRecvKernel(const P2PArgs a)
+{
+    const FbCommDev& c = a.comm;
+    const int blk = blockIdx.x;
+    uint64_t beg, end;
+    p2pShare(a.bytes, blk, beg, end);
+
+    __shared__ uint32_t sSeq;
+    __shared__ int sOk;
+    if (threadIdx.x == 0) {
+        sSeq = *p2pRecvSeq(c, a.peer, blk);
+        sOk = 1;
+    }
+    __syncthreads();
+    uint32_t seq = sSeq;
+
+    const uint8_t* slots = c.heap[c.rank] + a.mboxOff +
+                           ((uint64_t)a.peer * FB_P2P_BLOCKS + blk) * 2 *
+                             a.slotBytes;
+    uint64_t off = beg;
+    do {
+        uint64_t len = min(a.slotBytes, end - off);
+        seq += 1;
+        if (threadIdx.x == 0) {
+            bool ok = waitFlagGe(c,
+                                 p2pReadyFlag(c, c.rank, a.peer, blk),
+                                 seq,
+                                 FB_ERR_FLAG_TIMEOUT);
+            if (!ok) {
+                sOk = 0;
+            }
+        }
+        __syncthreads();
+        if (!sOk) {
+            break;
+        }
+        const uint8_t* slot = slots + (uint64_t)(seq & 1) * a.slotBytes;
+        uint64_t lenW = len - (len % W);
+        blockCopy<W>(a.local + off, slot, lenW);
+        if (threadIdx.x == 0) {
+            for (uint64_t b = lenW; b < len; b++) {
+                a.local[off + b] = slot[b];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // slot drained: let the sender reuse it
+            stReleaseSys(p2pAckFlag(c, a.peer, c.rank, blk), seq);
+        }
+        off += len;
+    } while (off < end);
+
+    if (threadIdx.x == 0) {
+        *p2pRecvSeq(c, a.peer, blk) = seq;
+    }
+}
+
+cudaError_t launchP2PSend(const P2PArgs& a, int width, cudaStream_t s)
+{
+    if (width == 16) {
+        p2pSendKernel<16><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+    } else if (width == 4) {
+        p2pSendKernel<4><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+    } else {
+        p2pSendKernel<1><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launchP2PRecv(const P2PArgs& a, int width, cudaStream_t s)
+{
+    if (width == 16) {
+        p2pRecvKernel<16><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+    } else if (width == 4) {
+        p2pRecvKernel<4><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+    } else {
+        p2pRecvKernel<1><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------
+// put-with-signal / wait-signal for symmetric destinations (zero staging):
+// data lands directly in the peer's buffer, then a user signal word is bumped.
+// ----------------------------------------------------------------------------
+template<int W>
+__global__ void __launch_bounds__(512, 1) putSignalKernel(const PutArgs a)
+{
+    const FbCommDev& c = a.comm;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t lenW = a.bytes - (a.bytes % W);
+    gridCopy<W>(c.heap[a.peer] + a.dstOff, a.local, lenW, tid, nthreads);
+    if (tid == 0) {
+        for (uint64_t b = lenW; b < a.bytes; b++) {
+            (c.heap[a.peer] + a.dstOff)[b] = a.local[b];
+        }
+    }
+    // every CTA publishes its own completion; the waiter expects gridDim.x
+    // increments (red.add is atomic at the destination L2)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fenceSys();
+        uint32_t* sigp = c.sig[a.peer] + FB_SIG_USER_OFF + a.signalIdx;
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(sigp),
+                     "r"(1u)
+                     : "memory");
+    }
+}
+
+__global__ void waitSignalKernel(const FbCommDev c,
+                                 int signalIdx,
+                                 uint32_t addTarget)
+{
+    // The expected value is (consumed so far + addTarget); the consumed count
+    // lives next to the signal so the wait is replayable
+    uint32_t* sigp = c.sig[c.rank] + FB_SIG_USER_OFF + signalIdx;
+    uint32_t* consumed = sigp + FB_SIG_USER_WORDS;
+    uint32_t target = *consumed + addTarget;
+    waitFlagGe(c, sigp, target, FB_ERR_FLAG_TIMEOUT);
+    *consumed = target;
+}
+
+cudaError_t launchPutSignal(const PutArgs& a,
+                            int width,
+                            int blocks,
+                            cudaStream_t s)
+{
+    if (width == 16) {
+        putSignalKernel<16><<<blocks, 512, 0, s>>>(a);
+    } else if (width == 4) {
+        putSignalKernel<4><<<blocks, 512, 0, s>>>(a);
+    } else {
+        putSignalKernel<1><<<blocks, 512, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launchWaitSignal(const FbCommDev& c,
+                             int signalIdx,
+                             uint32_t count,
+                             cudaStream_t s)
+{
+    waitSignalKernel<<<1, 1, 0, s>>>(c, signalIdx, count);
+    return cudaGetLastError();
+}
+
+} // namespace fb

@@ -1,0 +1,220 @@
+// Host-visible launch interface of every sm_100a kernel in csrc/kernels.
+// Plain C++ (no device code) so the host runtime can be built with g++ while
+// the kernels are built with nvcc.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "faabric/device/comm_abi.h"
+
+namespace fb {
+
+// ---------------------------------------------------------------- reduce ----
+struct ReduceArgs
+{
+    FbCommDev comm;
+    uint64_t sendOff;   // symmetric-heap offset of every rank's input
+    uint64_t recvOff;   // symmetric-heap offset of output (push modes)
+    uint8_t* recvLocal; // local output pointer (pull modes), may be outside heap
+    uint64_t bytes;     // total message bytes
+    // The vector range [vecBegin, vecEnd) (16-byte units) this rank reduces
+    uint64_t vecBegin;
+    uint64_t vecEnd;
+    // Where the local result vector index i lands: recvLocal + (i - outBase)*16
+    uint64_t outBase;
+    // How many peers are read: ranks [0, readRanks)
+    int32_t readRanks;
+    // Bit p set => store result to peer p at recvOff (push).  0 => local only
+    uint32_t pushMask;
+    // Who reduces the <16-byte tail (-1: nobody, -2: every rank)
+    int32_t tailOwner;
+    // skip cross-rank waits (profiling the data path under ncu only)
+    int32_t noSync;
+};
+
+// Host-side launcher type shared by the per-type translation units
+typedef cudaError_t (*ReduceLaunchFn)(const ReduceArgs& a,
+                                      int nr,
+                                      int blocks,
+                                      int threads,
+                                      cudaStream_t stream);
+
+#define FB_LL_BLOCKS 8
+#define FB_LL_THREADS 512
+#define FB_LL_MAX_VECS (FB_LL_BLOCKS * FB_LL_THREADS)
+#define FB_LL_MAX_BYTES (FB_LL_MAX_VECS * 16)
+// bytes of LL area needed per rank: 2 parities x nranks x vecs x 32 B
+#define FB_LL_AREA_BYTES(nranks) ((uint64_t)2 * (nranks) * FB_LL_MAX_VECS * 32)
+
+struct LLArgs
+{
+    FbCommDev comm;
+    const uint8_t* sendLocal;
+    uint8_t* recvLocal;
+    uint64_t bytes;
+    uint64_t llOff; // symmetric offset of the LL slot area
+};
+
+typedef cudaError_t (*LLLaunchFn)(const LLArgs& a, cudaStream_t stream);
+
+struct ReduceLaunchers
+{
+    ReduceLaunchFn reduce;
+    LLLaunchFn ll;
+};
+
+// Lookup implemented across coll_reduce_*.cu; returns nullptr if the
+// (dtype, op) pair is not meaningful (e.g. bitwise on floats)
+const ReduceLaunchers* findReduceLaunchers(int dtype, int op);
+const ReduceLaunchers* findReduceLaunchersInt(int dtype, int op);
+const ReduceLaunchers* findReduceLaunchersFloat(int dtype, int op);
+const ReduceLaunchers* findReduceLaunchersPair(int dtype, int op);
+
+
+// ------------------------------------------------------------------ move ----
+enum MoveMode
+{
+    MOVE_ALLGATHER = 0,
+    MOVE_ALLTOALL = 1,
+    MOVE_GATHER = 2,
+    MOVE_SCATTER = 3,
+    MOVE_BCAST = 4,
+    MOVE_BCAST_2STEP = 5
+};
+
+struct MoveArgs
+{
+    FbCommDev comm;
+    uint64_t sendOff;   // symmetric offset of the source buffer(s)
+    uint64_t recvOff;   // symmetric offset of the destination (2-step bcast)
+    uint8_t* recvLocal; // local destination (pull modes)
+    uint64_t chunkBytes; // bytes per (src,dst) pair; whole message for bcast
+    uint64_t srcStride;  // allToAll/scatter: row pitch inside the source buffer
+    uint64_t dstStride;  // allGather/allToAll/gather: row pitch in recvLocal
+    int32_t mode;
+    int32_t root;
+    int32_t noSync;
+};
+
+struct P2PArgs
+{
+    FbCommDev comm;
+    uint8_t* local;     // user buffer (send source / recv destination)
+    uint64_t bytes;
+    uint64_t mboxOff;   // symmetric offset of the mailbox slot area
+    uint64_t slotBytes; // bytes per eager slot
+    int32_t peer;
+};
+
+struct PutArgs
+{
+    FbCommDev comm;
+    const uint8_t* local;
+    uint64_t dstOff;
+    uint64_t bytes;
+    int32_t peer;
+    int32_t signalIdx;
+};
+
+cudaError_t launchMove(const MoveArgs& a,
+                       int width,
+                       int blocks,
+                       int threads,
+                       cudaStream_t s);
+cudaError_t launchBarrier(const FbCommDev& c, cudaStream_t s);
+cudaError_t launchP2PSend(const P2PArgs& a, int width, cudaStream_t s);
+cudaError_t launchP2PRecv(const P2PArgs& a, int width, cudaStream_t s);
+cudaError_t launchPutSignal(const PutArgs& a,
+                            int width,
+                            int blocks,
+                            cudaStream_t s);
+cudaError_t launchWaitSignal(const FbCommDev& c,
+                             int signalIdx,
+                             uint32_t count,
+                             cudaStream_t s);
+
+
+// ------------------------------------------------------------------ nvls ----
+enum NvlsMode
+{
+    NVLS_ALLREDUCE = 0,    // ld_reduce(mc send) -> multimem.st(mc recv)
+    NVLS_REDUCE_LOCAL = 1, // ld_reduce(mc send) -> local store (reduce, reduceScatter)
+    NVLS_BCAST = 2,        // local load -> multimem.st
+    NVLS_ALLGATHER = 3     // local load -> multimem.st at rank offset
+};
+
+struct NvlsArgs
+{
+    FbCommDev comm;
+    uint64_t sendOff;
+    uint64_t recvOff;
+    uint8_t* recvLocal;
+    uint64_t vecBegin;
+    uint64_t vecEnd;
+    uint64_t outBase;
+    int32_t mode;
+    int32_t noSync;
+};
+
+// -1 if the (dtype, op) pair has no in-switch reduction
+int nvlsVariant(int dtype, int op);
+
+cudaError_t launchNvls(const NvlsArgs& a,
+                       int variant,
+                       int blocks,
+                       int threads,
+                       cudaStream_t s);
+
+
+// -------------------------------------------------------------- snapshot ----
+struct SnapDiffArgs
+{
+    const uint8_t* mem;  // executor memory (updated)
+    const uint8_t* orig; // local base image the executor was restored from
+    uint8_t* origW;      // writable alias of orig when updateBase != 0
+    uint8_t* dst;        // main snapshot image (peer-mapped or local)
+    uint64_t size;       // bytes compared (min(image size, memory size))
+    const FbMergeRegionDev* regions; // sorted by offset, gaps already filled
+    int32_t nRegions;
+    const int32_t* typedIdx; // indices of regions with a typed merge op
+    int32_t nTyped;
+    const uint8_t* dirtyPages; // 1 byte per 4 KiB page, null => scan everything
+    uint8_t* pageFlagsOut;     // optional: pages that produced a diff
+    uint8_t* chunkFlags;       // optional: 128-byte chunks that produced a diff
+    uint64_t* stats;           // [0]=diff bytes, [1]=pages with diffs
+    int32_t updateBase;        // also fold the changes into the local base
+};
+
+cudaError_t launchSnapshotDiffPush(const SnapDiffArgs& a,
+                                   int blocks,
+                                   cudaStream_t s);
+cudaError_t launchDirtyScan(const uint8_t* mem,
+                            const uint8_t* base,
+                            uint64_t size,
+                            uint8_t* pageFlags,
+                            uint64_t* nDirty,
+                            int blocks,
+                            cudaStream_t s);
+cudaError_t launchFlagsOr(uint8_t* dst,
+                          const uint8_t* src,
+                          uint64_t n,
+                          cudaStream_t s);
+cudaError_t launchChunkRuns(const uint8_t* flags,
+                            uint64_t nChunks,
+                            uint32_t chunkBytes,
+                            uint64_t totalBytes,
+                            FbDiffDesc* out,
+                            uint32_t maxOut,
+                            uint32_t* count,
+                            cudaStream_t s);
+cudaError_t launchSnapshotApply(uint8_t* image,
+                                uint64_t imageSize,
+                                const FbDiffDesc* descs,
+                                const uint64_t* dataOff,
+                                const uint8_t* blob,
+                                uint32_t nDescs,
+                                cudaStream_t s);
+
+
+} // namespace fb

@@ -1,0 +1,1496 @@
+#include "faabric/device/communicator.h"
+
+#include "faabric/device/bootstrap.h"
+#include "faabric/device/cuda_driver.h"
+#include "launch_api.h"
+
+#include <algorithm>
+#include <initializer_list>
+#include <barrier>
+#include <cstdlib>
+#include <cstring>
+#include <set>
+#include <stdexcept>
+#include <unistd.h>
+
+namespace faabric::device {
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+#define CUDA_OK(expr)                                                          \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) {                                               \
+            throw std::runtime_error(std::string(#expr) + ": " +               \
+                                     cudaGetErrorString(_e));                  \
+        }                                                                      \
+    } while (0)
+
+#define CU_OK(api, expr)                                                       \
+    do {                                                                       \
+        CUresult _r = (expr);                                                  \
+        if (_r != CUDA_SUCCESS) {                                              \
+            throw std::runtime_error(std::string(#expr) + ": " +               \
+                                     (api).errStr(_r));                        \
+        }                                                                      \
+    } while (0)
+
+static size_t roundUp(size_t v, size_t a)
+{
+    return (v + a - 1) / a * a;
+}
+
+static size_t envSize(const char* name, size_t def)
+{
+    const char* v = getenv(name);
+    if (v == nullptr || *v == 0) {
+        return def;
+    }
+    return (size_t)strtoull(v, nullptr, 10);
+}
+
+CommConfig CommConfig::fromEnv()
+{
+    CommConfig c;
+    c.heapBytes = envSize("FAABRIC_SYMM_HEAP_BYTES", c.heapBytes);
+    c.stageBytes = envSize("FAABRIC_STAGE_BYTES", c.stageBytes);
+    c.slotBytes = envSize("FAABRIC_P2P_SLOT_BYTES", c.slotBytes);
+    c.timeoutMs = envSize("FAABRIC_DEVICE_TIMEOUT_MS", c.timeoutMs);
+    c.useVmm = envSize("FAABRIC_USE_VMM", 1) != 0;
+    c.useMulticast = envSize("FAABRIC_USE_NVLS", 1) != 0;
+    c.maxBlocks = (int)envSize("FAABRIC_COMM_BLOCKS", c.maxBlocks);
+    c.llMaxBytes = envSize("FAABRIC_LL_MAX_BYTES", c.llMaxBytes);
+    c.oneShotMaxBytes = envSize("FAABRIC_ONESHOT_MAX_BYTES", c.oneShotMaxBytes);
+    c.nvlsMinBytes = envSize("FAABRIC_NVLS_MIN_BYTES", c.nvlsMinBytes);
+    c.bcast2StepMinBytes =
+      envSize("FAABRIC_BCAST_2STEP_MIN_BYTES", c.bcast2StepMinBytes);
+    return c;
+}
+
+const char* Communicator::errorString(int code)
+{
+    switch (code) {
+        case FB_OK:
+            return "ok";
+        case FB_E_UNSUPPORTED:
+            return "unsupported (dtype, op) or layout";
+        case FB_E_INVALID:
+            return "invalid argument";
+        case FB_E_CUDA:
+            return "CUDA error";
+        case FB_E_TOO_LARGE:
+            return "message larger than staging area";
+        case FB_E_NO_DEVICE:
+            return "no CUDA device";
+        default:
+            return "unknown";
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Backing memory
+// ---------------------------------------------------------------------------
+struct Communicator::Backing
+{
+    bool vmm = false;
+    bool legacyIpc = false;
+    size_t mapSize = 0;
+    // per rank (local mode: all ranks; ipc mode: index = rank)
+    std::vector<CUmemGenericAllocationHandle> handles;
+    std::vector<CUdeviceptr> vas;
+    std::vector<void*> mallocPtrs;  // owned cudaMalloc allocations
+    std::vector<int> mallocDevices;
+    std::vector<void*> ipcOpened;   // cudaIpcOpenMemHandle results
+    CUmemGenericAllocationHandle mcHandle = 0;
+    std::vector<CUdeviceptr> mcVas;
+    bool hasMc = false;
+    std::vector<uint32_t*> errWords;
+    std::vector<int> errDevices;
+
+    ~Backing()
+    {
+        const DriverApi& api = getDriverApi();
+        for (void* p : ipcOpened) {
+            cudaIpcCloseMemHandle(p);
+        }
+        for (size_t i = 0; i < mcVas.size(); i++) {
+            if (mcVas[i] != 0) {
+                api.cuMemUnmap(mcVas[i], mapSize);
+                api.cuMemAddressFree(mcVas[i], mapSize);
+            }
+        }
+        for (size_t i = 0; i < vas.size(); i++) {
+            if (vas[i] != 0) {
+                api.cuMemUnmap(vas[i], mapSize);
+                api.cuMemAddressFree(vas[i], mapSize);
+            }
+        }
+        for (auto h : handles) {
+            if (h != 0) {
+                api.cuMemRelease(h);
+            }
+        }
+        if (hasMc && mcHandle != 0) {
+            api.cuMemRelease(mcHandle);
+        }
+        for (size_t i = 0; i < mallocPtrs.size(); i++) {
+            cudaSetDevice(mallocDevices[i]);
+            cudaFree(mallocPtrs[i]);
+        }
+        for (size_t i = 0; i < errWords.size(); i++) {
+            cudaSetDevice(errDevices[i]);
+            cudaFree(errWords[i]);
+        }
+        cudaGetLastError();
+    }
+};
+
+struct Communicator::LocalGroup
+{
+    std::barrier<> bar;
+    explicit LocalGroup(int n)
+      : bar(n)
+    {}
+};
+
+static const size_t SIG_REGION = 64 * 1024; // signal pad, padded
+
+void Communicator::computeLayout()
+{
+    int n = dev_.nranks;
+    cfg_.stageBytes = roundUp(std::max<size_t>(cfg_.stageBytes, 1 << 16), 4096);
+    cfg_.slotBytes = roundUp(std::max<size_t>(cfg_.slotBytes, 4096), 4096);
+    llOff_ = 0;
+    mboxOff_ = roundUp(llOff_ + FB_LL_AREA_BYTES(n), 4096);
+    stageSendOff_ = roundUp(
+      mboxOff_ + (uint64_t)n * FB_P2P_BLOCKS * 2 * cfg_.slotBytes, 4096);
+    stageRecvOff_ = stageSendOff_ + cfg_.stageBytes;
+    userOff_ = stageRecvOff_ + cfg_.stageBytes;
+    heapTotal_ = userOff_ + roundUp(cfg_.heapBytes, 4096);
+}
+
+void Communicator::initAllocator()
+{
+    freeList_.clear();
+    allocated_.clear();
+    freeList_[userOff_] = heapTotal_ - userOff_;
+}
+
+static bool multicastSupported(const DriverApi& api, int device)
+{
+    if (api.cuMulticastCreate == nullptr) {
+        return false;
+    }
+    CUdevice d;
+    if (api.cuDeviceGet(&d, device) != CUDA_SUCCESS) {
+        return false;
+    }
+    int v = 0;
+    if (api.cuDeviceGetAttribute(
+          &v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, d) != CUDA_SUCCESS) {
+        return false;
+    }
+    return v != 0;
+}
+
+static CUmemAllocationProp vmmProp(int device, bool shareable)
+{
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = shareable
+                                  ? CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+                                  : CU_MEM_HANDLE_TYPE_NONE;
+    return prop;
+}
+
+static void setAccess(const DriverApi& api,
+                      CUdeviceptr va,
+                      size_t size,
+                      const std::vector<int>& devices)
+{
+    std::vector<CUmemAccessDesc> descs;
+    for (int d : devices) {
+        CUmemAccessDesc a;
+        memset(&a, 0, sizeof(a));
+        a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        a.location.id = d;
+        a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        descs.push_back(a);
+    }
+    CU_OK(api, api.cuMemSetAccess(va, size, descs.data(), descs.size()));
+}
+
+// ---------------------------------------------------------------------------
+// Local (single-process) creation
+// ---------------------------------------------------------------------------
+std::vector<std::shared_ptr<Communicator>> Communicator::createLocal(
+  int nranks,
+  const std::vector<int>& devices,
+  const CommConfig& cfgIn)
+{
+    if (nranks < 1 || nranks > FB_MAX_RANKS || (int)devices.size() != nranks) {
+        throw std::invalid_argument("createLocal: bad rank/device list");
+    }
+    if (!cudaAvailable()) {
+        throw std::runtime_error("createLocal: no CUDA device");
+    }
+    std::vector<std::shared_ptr<Communicator>> comms;
+    for (int r = 0; r < nranks; r++) {
+        auto c = std::shared_ptr<Communicator>(new Communicator());
+        c->cfg_ = cfgIn;
+        c->dev_.rank = r;
+        c->dev_.nranks = nranks;
+        c->device_ = devices[r];
+        c->computeLayout();
+        c->initAllocator();
+        comms.push_back(c);
+    }
+    const size_t total = SIG_REGION + comms[0]->heapTotal_;
+    std::set<int> distinct(devices.begin(), devices.end());
+    std::vector<int> distinctDevs(distinct.begin(), distinct.end());
+    const bool allDistinct = (int)distinct.size() == nranks;
+
+    auto backing = std::make_shared<Backing>();
+    std::vector<uint8_t*> bases(nranks, nullptr);
+    std::vector<uint8_t*> mcBases(nranks, nullptr);
+    std::string kind = "cudaMalloc+peer";
+
+    const DriverApi& api = getDriverApi();
+    bool vmmDone = false;
+    if (cfgIn.useVmm && api.loaded) {
+        try {
+            size_t gran = 0;
+            CUmemAllocationProp p0 = vmmProp(devices[0], false);
+            CU_OK(api,
+                  api.cuMemGetAllocationGranularity(
+                    &gran, &p0, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+            bool wantMc = cfgIn.useMulticast && allDistinct && nranks >= 2;
+            for (int d : distinctDevs) {
+                wantMc = wantMc && multicastSupported(api, d);
+            }
+            CUmulticastObjectProp mcProp;
+            memset(&mcProp, 0, sizeof(mcProp));
+            if (wantMc) {
+                mcProp.numDevices = nranks;
+                mcProp.size = total;
+                mcProp.handleTypes = 0;
+                size_t mcGran = 0;
+                if (api.cuMulticastGetGranularity(
+                      &mcGran, &mcProp, CU_MULTICAST_GRANULARITY_RECOMMENDED) ==
+                    CUDA_SUCCESS) {
+                    gran = std::max(gran, mcGran);
+                } else {
+                    wantMc = false;
+                }
+            }
+            size_t mapSize = roundUp(total, gran);
+            backing->mapSize = mapSize;
+            backing->vmm = true;
+            backing->handles.assign(nranks, 0);
+            backing->vas.assign(nranks, 0);
+            for (int r = 0; r < nranks; r++) {
+                CUDA_OK(cudaSetDevice(devices[r]));
+                CUDA_OK(cudaFree(0));
+                CUmemAllocationProp prop = vmmProp(devices[r], false);
+                CU_OK(api,
+                      api.cuMemCreate(&backing->handles[r], mapSize, &prop, 0));
+                CU_OK(api,
+                      api.cuMemAddressReserve(
+                        &backing->vas[r], mapSize, gran, 0, 0));
+                CU_OK(api,
+                      api.cuMemMap(
+                        backing->vas[r], mapSize, 0, backing->handles[r], 0));
+                setAccess(api, backing->vas[r], mapSize, distinctDevs);
+                bases[r] = reinterpret_cast<uint8_t*>(backing->vas[r]);
+            }
+            vmmDone = true;
+            kind = "vmm";
+            if (wantMc) {
+                try {
+                    mcProp.size = mapSize;
+                    CU_OK(api,
+                          api.cuMulticastCreate(&backing->mcHandle, &mcProp));
+                    backing->hasMc = true;
+                    for (int r = 0; r < nranks; r++) {
+                        CUdevice cd;
+                        CU_OK(api, api.cuDeviceGet(&cd, devices[r]));
+                        CU_OK(api,
+                              api.cuMulticastAddDevice(backing->mcHandle, cd));
+                    }
+                    for (int r = 0; r < nranks; r++) {
+                        CUDA_OK(cudaSetDevice(devices[r]));
+                        CU_OK(api,
+                              api.cuMulticastBindMem(backing->mcHandle,
+                                                     0,
+                                                     backing->handles[r],
+                                                     0,
+                                                     mapSize,
+                                                     0));
+                    }
+                    backing->mcVas.assign(1, 0);
+                    CU_OK(api,
+                          api.cuMemAddressReserve(
+                            &backing->mcVas[0], mapSize, gran, 0, 0));
+                    CU_OK(api,
+                          api.cuMemMap(backing->mcVas[0],
+                                       mapSize,
+                                       0,
+                                       backing->mcHandle,
+                                       0));
+                    setAccess(api, backing->mcVas[0], mapSize, distinctDevs);
+                    for (int r = 0; r < nranks; r++) {
+                        mcBases[r] =
+                          reinterpret_cast<uint8_t*>(backing->mcVas[0]);
+                    }
+                    kind = "vmm+multicast";
+                } catch (const std::exception& e) {
+                    fprintf(stderr,
+                            "[faabric-b200] multicast unavailable: %s\n",
+                            e.what());
+                    std::fill(mcBases.begin(), mcBases.end(), nullptr);
+                }
+            }
+        } catch (const std::exception& e) {
+            if (vmmDone) {
+                throw;
+            }
+            fprintf(stderr,
+                    "[faabric-b200] VMM unavailable (%s), using cudaMalloc\n",
+                    e.what());
+            backing = std::make_shared<Backing>();
+        }
+    }
+    if (!vmmDone) {
+        for (int r = 0; r < nranks; r++) {
+            CUDA_OK(cudaSetDevice(devices[r]));
+            for (int d : distinctDevs) {
+                if (d != devices[r]) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(d, 0);
+                    if (e != cudaSuccess &&
+                        e != cudaErrorPeerAccessAlreadyEnabled) {
+                        throw std::runtime_error(
+                          std::string("cudaDeviceEnablePeerAccess: ") +
+                          cudaGetErrorString(e));
+                    }
+                    cudaGetLastError();
+                }
+            }
+            void* p = nullptr;
+            CUDA_OK(cudaMalloc(&p, total));
+            backing->mallocPtrs.push_back(p);
+            backing->mallocDevices.push_back(devices[r]);
+            bases[r] = (uint8_t*)p;
+        }
+    }
+
+    // zero the pads + control areas, allocate error words
+    auto group = std::make_shared<LocalGroup>(nranks);
+    for (int r = 0; r < nranks; r++) {
+        CUDA_OK(cudaSetDevice(devices[r]));
+        CUDA_OK(cudaMemset(bases[r], 0, SIG_REGION + comms[r]->userOff_));
+        uint32_t* err = nullptr;
+        CUDA_OK(cudaMalloc((void**)&err, 256));
+        CUDA_OK(cudaMemset(err, 0, 256));
+        backing->errWords.push_back(err);
+        backing->errDevices.push_back(devices[r]);
+        CUDA_OK(cudaDeviceSynchronize());
+        auto& c = comms[r];
+        for (int p = 0; p < nranks; p++) {
+            c->dev_.sig[p] = reinterpret_cast<uint32_t*>(bases[p]);
+            c->dev_.heap[p] = bases[p] + SIG_REGION;
+        }
+        c->dev_.mcHeap = mcBases[r] ? mcBases[r] + SIG_REGION : nullptr;
+        c->dev_.err = err;
+        c->dev_.timeoutNs = c->cfg_.timeoutMs * 1000000ull;
+        c->backingState_ = backing;
+        c->backing_ = kind;
+        c->localGroup_ = group;
+    }
+    return comms;
+}
+
+// ---------------------------------------------------------------------------
+// Multi-process creation
+// ---------------------------------------------------------------------------
+std::shared_ptr<Communicator> Communicator::createIpc(int rank,
+                                                      int nranks,
+                                                      int device,
+                                                      const std::string& jobId,
+                                                      const CommConfig& cfgIn)
+{
+    if (nranks < 1 || nranks > FB_MAX_RANKS || rank < 0 || rank >= nranks) {
+        throw std::invalid_argument("createIpc: bad rank");
+    }
+    if (!cudaAvailable()) {
+        throw std::runtime_error("createIpc: no CUDA device");
+    }
+    auto c = std::shared_ptr<Communicator>(new Communicator());
+    c->cfg_ = cfgIn;
+    c->dev_.rank = rank;
+    c->dev_.nranks = nranks;
+    c->device_ = device;
+    c->computeLayout();
+    c->initAllocator();
+    c->bootstrap_ = std::make_shared<Bootstrap>(rank, nranks, jobId);
+    Bootstrap& bs = *c->bootstrap_;
+
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaFree(0));
+    const size_t total = SIG_REGION + c->heapTotal_;
+    auto backing = std::make_shared<Backing>();
+    std::vector<uint8_t*> bases(nranks, nullptr);
+    uint8_t* mcBase = nullptr;
+    std::string kind;
+
+    const DriverApi& api = getDriverApi();
+    // ---- stage 1: try VMM with POSIX fd export; all ranks must agree ----
+    uint8_t vmmOk = 0;
+    int myFd = -1;
+    size_t gran = 0;
+    size_t mapSize = 0;
+    uint8_t mcWanted = 0;
+    if (cfgIn.useVmm && api.loaded) {
+        try {
+            CUmemAllocationProp prop = vmmProp(device, true);
+            CU_OK(api,
+                  api.cuMemGetAllocationGranularity(
+                    &gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+            mcWanted = (cfgIn.useMulticast && nranks >= 2 &&
+                        multicastSupported(api, device))
+                         ? 1
+                         : 0;
+            if (mcWanted) {
+                CUmulticastObjectProp mp;
+                memset(&mp, 0, sizeof(mp));
+                mp.numDevices = nranks;
+                mp.size = total;
+                mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+                size_t mg = 0;
+                if (api.cuMulticastGetGranularity(
+                      &mg, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED) ==
+                    CUDA_SUCCESS) {
+                    gran = std::max(gran, mg);
+                } else {
+                    mcWanted = 0;
+                }
+            }
+            mapSize = roundUp(total, gran);
+            backing->handles.assign(nranks, 0);
+            backing->vas.assign(nranks, 0);
+            CU_OK(api,
+                  api.cuMemCreate(&backing->handles[rank], mapSize, &prop, 0));
+            CU_OK(api,
+                  api.cuMemExportToShareableHandle(
+                    &myFd,
+                    backing->handles[rank],
+                    CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR,
+                    0));
+            vmmOk = 1;
+        } catch (const std::exception& e) {
+            fprintf(stderr,
+                    "[faabric-b200] rank %d: VMM export failed: %s\n",
+                    rank,
+                    e.what());
+            vmmOk = 0;
+        }
+    }
+    {
+        uint8_t st[2] = { vmmOk, mcWanted };
+        auto all = bs.allGather(st, 2);
+        for (int r = 0; r < nranks; r++) {
+            vmmOk = vmmOk && all[2 * r];
+            mcWanted = mcWanted && all[2 * r + 1];
+        }
+    }
+    if (vmmOk) {
+        backing->vmm = true;
+        backing->mapSize = mapSize;
+        std::vector<int> fds = bs.allGatherFds(myFd);
+        ::close(myFd);
+        for (int p = 0; p < nranks; p++) {
+            if (p != rank) {
+                CU_OK(api,
+                      api.cuMemImportFromShareableHandle(
+                        &backing->handles[p],
+                        (void*)(uintptr_t)fds[p],
+                        CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+            }
+            ::close(fds[p]);
+            CU_OK(api,
+                  api.cuMemAddressReserve(&backing->vas[p], mapSize, gran, 0, 0));
+            CU_OK(api,
+                  api.cuMemMap(backing->vas[p], mapSize, 0, backing->handles[p], 0));
+            setAccess(api, backing->vas[p], mapSize, { device });
+            bases[p] = reinterpret_cast<uint8_t*>(backing->vas[p]);
+        }
+        kind = "vmm-ipc";
+        // ---- multicast ----
+        if (mcWanted) {
+            uint8_t ok = 1;
+            int mcFd = -1;
+            try {
+                if (rank == 0) {
+                    CUmulticastObjectProp mp;
+                    memset(&mp, 0, sizeof(mp));
+                    mp.numDevices = nranks;
+                    mp.size = mapSize;
+                    mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+                    CU_OK(api, api.cuMulticastCreate(&backing->mcHandle, &mp));
+                    backing->hasMc = true;
+                    CU_OK(api,
+                          api.cuMemExportToShareableHandle(
+                            &mcFd,
+                            backing->mcHandle,
+                            CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR,
+                            0));
+                }
+            } catch (const std::exception& e) {
+                fprintf(stderr,
+                        "[faabric-b200] multicast create failed: %s\n",
+                        e.what());
+                ok = 0;
+            }
+            // rank 0 tells everybody whether an fd follows
+            {
+                auto all = bs.allGather(&ok, 1);
+                ok = all[0];
+            }
+            if (ok) {
+                int got = bs.broadcastFd(mcFd, 0);
+                if (mcFd >= 0) {
+                    ::close(mcFd);
+                }
+                uint8_t step = 1;
+                try {
+                    if (rank != 0) {
+                        CU_OK(api,
+                              api.cuMemImportFromShareableHandle(
+                                &backing->mcHandle,
+                                (void*)(uintptr_t)got,
+                                CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+                        backing->hasMc = true;
+                    }
+                    CUdevice cd;
+                    CU_OK(api, api.cuDeviceGet(&cd, device));
+                    CU_OK(api, api.cuMulticastAddDevice(backing->mcHandle, cd));
+                } catch (const std::exception& e) {
+                    fprintf(stderr,
+                            "[faabric-b200] rank %d multicast add failed: %s\n",
+                            rank,
+                            e.what());
+                    step = 0;
+                }
+                ::close(got);
+                {
+                    auto all = bs.allGather(&step, 1);
+                    for (int r = 0; r < nranks; r++) {
+                        step = step && all[r];
+                    }
+                }
+                if (step) {
+                    try {
+                        CU_OK(api,
+                              api.cuMulticastBindMem(backing->mcHandle,
+                                                     0,
+                                                     backing->handles[rank],
+                                                     0,
+                                                     mapSize,
+                                                     0));
+                        backing->mcVas.assign(1, 0);
+                        CU_OK(api,
+                              api.cuMemAddressReserve(
+                                &backing->mcVas[0], mapSize, gran, 0, 0));
+                        CU_OK(api,
+                              api.cuMemMap(backing->mcVas[0],
+                                           mapSize,
+                                           0,
+                                           backing->mcHandle,
+                                           0));
+                        setAccess(api, backing->mcVas[0], mapSize, { device });
+                    } catch (const std::exception& e) {
+                        fprintf(stderr,
+                                "[faabric-b200] rank %d multicast bind/map "
+                                "failed: %s\n",
+                                rank,
+                                e.what());
+                        step = 0;
+                    }
+                    auto all = bs.allGather(&step, 1);
+                    for (int r = 0; r < nranks; r++) {
+                        step = step && all[r];
+                    }
+                    if (step) {
+                        mcBase = reinterpret_cast<uint8_t*>(backing->mcVas[0]);
+                        kind = "vmm-ipc+multicast";
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- legacy CUDA IPC ----
+        if (myFd >= 0) {
+            ::close(myFd);
+        }
+        backing = std::make_shared<Backing>();
+        backing->legacyIpc = true;
+        void* p = nullptr;
+        CUDA_OK(cudaMalloc(&p, total));
+        backing->mallocPtrs.push_back(p);
+        backing->mallocDevices.push_back(device);
+        cudaIpcMemHandle_t h;
+        CUDA_OK(cudaIpcGetMemHandle(&h, p));
+        auto all = bs.allGather(&h, sizeof(h));
+        for (int q = 0; q < nranks; q++) {
+            if (q == rank) {
+                bases[q] = (uint8_t*)p;
+                continue;
+            }
+            cudaIpcMemHandle_t ph;
+            memcpy(&ph, all.data() + (size_t)q * sizeof(h), sizeof(h));
+            void* mapped = nullptr;
+            CUDA_OK(cudaIpcOpenMemHandle(
+              &mapped, ph, cudaIpcMemLazyEnablePeerAccess));
+            backing->ipcOpened.push_back(mapped);
+            bases[q] = (uint8_t*)mapped;
+        }
+        kind = "cuda-ipc";
+    }
+
+    CUDA_OK(cudaMemset(bases[rank], 0, SIG_REGION + c->userOff_));
+    uint32_t* err = nullptr;
+    CUDA_OK(cudaMalloc((void**)&err, 256));
+    CUDA_OK(cudaMemset(err, 0, 256));
+    backing->errWords.push_back(err);
+    backing->errDevices.push_back(device);
+    CUDA_OK(cudaDeviceSynchronize());
+    for (int p = 0; p < nranks; p++) {
+        c->dev_.sig[p] = reinterpret_cast<uint32_t*>(bases[p]);
+        c->dev_.heap[p] = bases[p] + SIG_REGION;
+    }
+    c->dev_.mcHeap = mcBase ? mcBase + SIG_REGION : nullptr;
+    c->dev_.err = err;
+    c->dev_.timeoutNs = c->cfg_.timeoutMs * 1000000ull;
+    c->backingState_ = backing;
+    c->backing_ = kind;
+    // nobody may touch a peer's pad before it has been zeroed
+    bs.barrier();
+    return c;
+}
+
+Communicator::~Communicator()
+{
+    // Backing is shared: freed when the last rank's communicator dies
+}
+
+void Communicator::hostBarrier()
+{
+    if (bootstrap_) {
+        bootstrap_->barrier();
+    } else if (localGroup_) {
+        localGroup_->bar.arrive_and_wait();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Heap allocator (first fit, deterministic => symmetric across ranks)
+// ---------------------------------------------------------------------------
+uint64_t Communicator::alloc(size_t bytes, size_t align)
+{
+    std::lock_guard<std::mutex> lk(allocMx_);
+    if (align < 256) {
+        align = 256;
+    }
+    bytes = roundUp(std::max<size_t>(bytes, 1), 256);
+    for (auto it = freeList_.begin(); it != freeList_.end(); ++it) {
+        uint64_t start = roundUp(it->first, align);
+        uint64_t pad = start - it->first;
+        if (it->second >= pad + bytes) {
+            uint64_t blockOff = it->first;
+            uint64_t blockSize = it->second;
+            freeList_.erase(it);
+            if (pad > 0) {
+                freeList_[blockOff] = pad;
+            }
+            uint64_t rest = blockSize - pad - bytes;
+            if (rest > 0) {
+                freeList_[start + bytes] = rest;
+            }
+            allocated_[start] = bytes;
+            return start;
+        }
+    }
+    throw std::bad_alloc();
+}
+
+void Communicator::free(uint64_t offset)
+{
+    std::lock_guard<std::mutex> lk(allocMx_);
+    auto it = allocated_.find(offset);
+    if (it == allocated_.end()) {
+        return;
+    }
+    uint64_t size = it->second;
+    allocated_.erase(it);
+    auto ins = freeList_.emplace(offset, size).first;
+    // coalesce with the next block
+    auto next = std::next(ins);
+    if (next != freeList_.end() && ins->first + ins->second == next->first) {
+        ins->second += next->second;
+        freeList_.erase(next);
+    }
+    if (ins != freeList_.begin()) {
+        auto prev = std::prev(ins);
+        if (prev->first + prev->second == ins->first) {
+            prev->second += ins->second;
+            freeList_.erase(ins);
+        }
+    }
+}
+
+uint8_t* Communicator::heapPtr(uint64_t offset, int rank) const
+{
+    if (rank < 0) {
+        rank = dev_.rank;
+    }
+    return dev_.heap[rank] + offset;
+}
+
+bool Communicator::inHeap(const void* p, size_t bytes) const
+{
+    const uint8_t* b = dev_.heap[dev_.rank];
+    const uint8_t* q = (const uint8_t*)p;
+    return q >= b && q + bytes <= b + heapTotal_;
+}
+
+uint64_t Communicator::offsetOf(const void* p) const
+{
+    return (uint64_t)((const uint8_t*)p - dev_.heap[dev_.rank]);
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------
+int Communicator::blocksFor(uint64_t vecs, int perThread) const
+{
+    uint64_t perBlock = (uint64_t)cfg_.threads * perThread;
+    uint64_t b = (vecs + perBlock - 1) / perBlock;
+    int maxB = std::min(cfg_.maxBlocks, FB_MAX_BLOCKS);
+    if (b < 1) {
+        b = 1;
+    }
+    if (b > (uint64_t)maxB) {
+        b = maxB;
+    }
+    return (int)b;
+}
+
+static int alignWidth(uint64_t v)
+{
+    if ((v & 15) == 0) {
+        return 16;
+    }
+    if ((v & 3) == 0) {
+        return 4;
+    }
+    return 1;
+}
+
+int Communicator::widthFor(const void* a, const void* b, uint64_t bytes) const
+{
+    int w = std::min(alignWidth((uint64_t)(uintptr_t)a),
+                     alignWidth((uint64_t)(uintptr_t)b));
+    return std::min(w, alignWidth(bytes));
+}
+
+FbCommDev Communicator::devFor(int flags) const
+{
+    (void)flags;
+    return dev_;
+}
+
+uint32_t Communicator::checkError(cudaStream_t s)
+{
+    uint32_t v = 0;
+    cudaSetDevice(device_);
+    cudaError_t e =
+      cudaMemcpyAsync(&v, dev_.err, sizeof(v), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) {
+        e = cudaStreamSynchronize(s);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0xffffffffu;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// Reductions
+// ---------------------------------------------------------------------------
+enum ReduceKind
+{
+    K_ALLREDUCE = 0,
+    K_REDUCE = 1,
+    K_REDUCE_SCATTER = 2,
+    K_SCAN = 3
+};
+
+int Communicator::reduceLike(int kind,
+                             const void* send,
+                             void* recv,
+                             size_t count,
+                             int dtype,
+                             int op,
+                             int root,
+                             int algo,
+                             int flags,
+                             cudaStream_t s)
+{
+    const int n = dev_.nranks;
+    const int rank = dev_.rank;
+    const size_t esize = fbDtypeSize(dtype);
+    if (esize == 0) {
+        return FB_E_INVALID;
+    }
+    const fb::ReduceLaunchers* L = fb::findReduceLaunchers(dtype, op);
+    if (L == nullptr) {
+        return FB_E_UNSUPPORTED;
+    }
+    cudaSetDevice(device_);
+    const bool symmetric = (flags & FB_FLAG_SYMMETRIC) != 0;
+    const int noSync = (flags & FB_FLAG_NOSYNC) ? 1 : 0;
+    const bool isRootOrAll = (kind != K_REDUCE) || (rank == root);
+
+    // message bytes each rank contributes
+    uint64_t bytes = (uint64_t)count * esize;
+    if (kind == K_REDUCE_SCATTER) {
+        bytes = (uint64_t)count * esize * n; // count = per-rank output
+    }
+    if (bytes == 0) {
+        return barrier(s);
+    }
+    if (symmetric && (!inHeap(send, bytes))) {
+        return FB_E_INVALID;
+    }
+
+    const int nvVariant = fb::nvlsVariant(dtype, op);
+
+    // ---- algorithm choice ----
+    if (kind == K_ALLREDUCE) {
+        if (algo == FB_ALGO_AUTO) {
+            if (bytes <= cfg_.llMaxBytes && bytes <= FB_LL_MAX_BYTES) {
+                algo = FB_ALGO_LL;
+            } else if (hasMulticast() && nvVariant >= 0 &&
+                       bytes >= cfg_.nvlsMinBytes && (bytes % 16) == 0) {
+                algo = FB_ALGO_NVLS;
+            } else if (bytes <= cfg_.oneShotMaxBytes) {
+                algo = FB_ALGO_ONESHOT;
+            } else {
+                algo = FB_ALGO_TWOSHOT;
+            }
+        }
+        if (algo == FB_ALGO_LL &&
+            (bytes > FB_LL_MAX_BYTES || (((uintptr_t)send | (uintptr_t)recv) & 15))) {
+            algo = FB_ALGO_ONESHOT;
+        }
+        if (algo == FB_ALGO_NVLS &&
+            (!hasMulticast() || nvVariant < 0 || (bytes % 16) != 0)) {
+            algo = FB_ALGO_TWOSHOT;
+        }
+        // one-shot reads the peers' inputs while writing the output: in-place
+        // on symmetric buffers must go through the two-shot (owner-only) path
+        if (algo == FB_ALGO_ONESHOT && symmetric && send == recv) {
+            algo = FB_ALGO_TWOSHOT;
+        }
+    } else if (kind == K_REDUCE) {
+        if (algo == FB_ALGO_AUTO) {
+            if (hasMulticast() && nvVariant >= 0 && bytes >= cfg_.nvlsMinBytes &&
+                (bytes % 16) == 0) {
+                algo = FB_ALGO_NVLS;
+            } else if (bytes <= cfg_.oneShotMaxBytes * 2) {
+                algo = FB_ALGO_ONESHOT;
+            } else {
+                algo = FB_ALGO_TWOSHOT;
+            }
+        }
+        if (algo == FB_ALGO_NVLS &&
+            (!hasMulticast() || nvVariant < 0 || (bytes % 16) != 0)) {
+            algo = FB_ALGO_ONESHOT;
+        }
+        if (algo == FB_ALGO_LL) {
+            algo = FB_ALGO_ONESHOT;
+        }
+    } else if (kind == K_REDUCE_SCATTER) {
+        uint64_t slice = (uint64_t)count * esize;
+        if ((slice % 16) != 0) {
+            return FB_E_UNSUPPORTED;
+        }
+        if (algo == FB_ALGO_AUTO || algo == FB_ALGO_NVLS) {
+            algo = (hasMulticast() && nvVariant >= 0 &&
+                    slice >= cfg_.nvlsMinBytes / 2)
+                     ? FB_ALGO_NVLS
+                     : FB_ALGO_ONESHOT;
+        } else {
+            algo = FB_ALGO_ONESHOT;
+        }
+    } else {
+        algo = FB_ALGO_ONESHOT; // scan
+    }
+    lastAlgo_ = algo;
+    stats_.algoCount[algo]++;
+
+    // ---- LL: no staging, no symmetric requirement ----
+    if (algo == FB_ALGO_LL) {
+        fb::LLArgs a;
+        a.comm = dev_;
+        a.sendLocal = (const uint8_t*)send;
+        a.recvLocal = (uint8_t*)recv;
+        a.bytes = bytes;
+        a.llOff = llOff_;
+        stats_.launches++;
+        stats_.bytes += bytes;
+        return L->ll(a, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+    }
+
+    // ---- staged / symmetric chunk loop ----
+    const bool stageSend = !symmetric;
+    // which algorithms write through the symmetric recv offset
+    const bool pushes = (algo == FB_ALGO_TWOSHOT) ||
+                        (algo == FB_ALGO_NVLS && kind == K_ALLREDUCE);
+    bool stageRecv = false;
+    if (pushes) {
+        if (kind == K_REDUCE) {
+            stageRecv = true; // only the root has a recv buffer
+        } else {
+            stageRecv = !symmetric || !inHeap(recv, bytes);
+        }
+    } else if (isRootOrAll && (((uintptr_t)recv) & 15)) {
+        stageRecv = true; // vector stores need 16-byte alignment
+    }
+    if (kind == K_REDUCE_SCATTER && stageSend && bytes > cfg_.stageBytes) {
+        return FB_E_TOO_LARGE;
+    }
+    const uint64_t chunkMax =
+      (stageSend || stageRecv) ? (uint64_t)cfg_.stageBytes : bytes;
+
+    for (uint64_t done = 0; done < bytes; done += chunkMax) {
+        const uint64_t len = std::min<uint64_t>(chunkMax, bytes - done);
+        uint64_t sendOff;
+        if (stageSend) {
+            if (cudaMemcpyAsync(heapPtr(stageSendOff_),
+                                (const uint8_t*)send + done,
+                                len,
+                                cudaMemcpyDeviceToDevice,
+                                s) != cudaSuccess) {
+                return FB_E_CUDA;
+            }
+            stats_.stagedCopies++;
+            sendOff = stageSendOff_;
+        } else {
+            sendOff = offsetOf(send) + done;
+        }
+        uint8_t* recvLocal = (uint8_t*)recv + done;
+        uint64_t recvOff = 0;
+        if (stageRecv) {
+            recvLocal = heapPtr(stageRecvOff_);
+            recvOff = stageRecvOff_;
+        } else if (pushes) {
+            recvOff = offsetOf(recv) + done;
+        }
+
+        const uint64_t nVec = len / 16;
+        uint64_t per = (nVec + n - 1) / n; // slice size in vectors
+        cudaError_t ce = cudaSuccess;
+
+        if (algo == FB_ALGO_NVLS) {
+            fb::NvlsArgs a;
+            memset(&a, 0, sizeof(a));
+            a.comm = dev_;
+            a.sendOff = sendOff;
+            a.recvOff = recvOff;
+            a.recvLocal = recvLocal;
+            a.noSync = noSync;
+            uint64_t work = 0;
+            if (kind == K_ALLREDUCE) {
+                a.mode = fb::NVLS_ALLREDUCE;
+                a.vecBegin = std::min<uint64_t>((uint64_t)rank * per, nVec);
+                a.vecEnd = std::min<uint64_t>(a.vecBegin + per, nVec);
+                a.outBase = 0;
+                work = per;
+            } else if (kind == K_REDUCE) {
+                a.mode = fb::NVLS_REDUCE_LOCAL;
+                a.vecBegin = 0;
+                a.vecEnd = (rank == root) ? nVec : 0;
+                a.outBase = 0;
+                work = nVec;
+            } else { // reduce scatter
+                a.mode = fb::NVLS_REDUCE_LOCAL;
+                uint64_t sliceVec = (uint64_t)count * esize / 16;
+                a.vecBegin = (uint64_t)rank * sliceVec;
+                a.vecEnd = a.vecBegin + sliceVec;
+                a.outBase = a.vecBegin;
+                work = sliceVec;
+            }
+            ce = fb::launchNvls(
+              a, nvVariant, blocksFor(work, 4), cfg_.threads, s);
+        } else {
+            fb::ReduceArgs a;
+            memset(&a, 0, sizeof(a));
+            a.comm = dev_;
+            a.sendOff = sendOff;
+            a.recvOff = recvOff;
+            a.recvLocal = recvLocal;
+            a.bytes = len;
+            a.readRanks = n;
+            a.noSync = noSync;
+            uint64_t work = nVec;
+            if (kind == K_ALLREDUCE && algo == FB_ALGO_ONESHOT) {
+                a.vecBegin = 0;
+                a.vecEnd = nVec;
+                a.pushMask = 0;
+                a.tailOwner = -2;
+            } else if (kind == K_ALLREDUCE) { // two-shot
+                a.vecBegin = std::min<uint64_t>((uint64_t)rank * per, nVec);
+                a.vecEnd = std::min<uint64_t>(a.vecBegin + per, nVec);
+                a.pushMask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1);
+                a.tailOwner = n - 1;
+                work = per;
+            } else if (kind == K_REDUCE && algo == FB_ALGO_ONESHOT) {
+                a.vecBegin = 0;
+                a.vecEnd = (rank == root) ? nVec : 0;
+                a.pushMask = 0;
+                a.tailOwner = root;
+            } else if (kind == K_REDUCE) { // two-shot, push slices to root
+                a.vecBegin = std::min<uint64_t>((uint64_t)rank * per, nVec);
+                a.vecEnd = std::min<uint64_t>(a.vecBegin + per, nVec);
+                a.pushMask = 1u << root;
+                a.tailOwner = n - 1;
+                work = per;
+            } else if (kind == K_REDUCE_SCATTER) {
+                uint64_t sliceVec = (uint64_t)count * esize / 16;
+                a.vecBegin = (uint64_t)rank * sliceVec;
+                a.vecEnd = a.vecBegin + sliceVec;
+                a.outBase = a.vecBegin;
+                a.pushMask = 0;
+                a.tailOwner = -1;
+                a.bytes = len - (len & 15); // slices are vector multiples
+                work = sliceVec;
+            } else { // scan
+                a.vecBegin = 0;
+                a.vecEnd = nVec;
+                a.readRanks = rank + 1;
+                a.pushMask = 0;
+                a.tailOwner = -2;
+            }
+            int perThread = (n == 8) ? 2 : 4;
+            ce = L->reduce(a, n, blocksFor(work, perThread), cfg_.threads, s);
+        }
+        if (ce != cudaSuccess) {
+            return FB_E_CUDA;
+        }
+        stats_.launches++;
+        stats_.bytes += len;
+        if (stageRecv && isRootOrAll) {
+            uint64_t outLen = (kind == K_REDUCE_SCATTER) ? count * esize : len;
+            if (cudaMemcpyAsync((uint8_t*)recv + done,
+                                heapPtr(stageRecvOff_),
+                                outLen,
+                                cudaMemcpyDeviceToDevice,
+                                s) != cudaSuccess) {
+                return FB_E_CUDA;
+            }
+            stats_.stagedCopies++;
+        }
+    }
+    return FB_OK;
+}
+
+int Communicator::allReduce(const void* send,
+                            void* recv,
+                            size_t count,
+                            int dtype,
+                            int op,
+                            int algo,
+                            int flags,
+                            cudaStream_t s)
+{
+    return reduceLike(
+      K_ALLREDUCE, send, recv, count, dtype, op, 0, algo, flags, s);
+}
+
+int Communicator::reduce(const void* send,
+                         void* recv,
+                         size_t count,
+                         int dtype,
+                         int op,
+                         int root,
+                         int flags,
+                         cudaStream_t s)
+{
+    if (root < 0 || root >= dev_.nranks) {
+        return FB_E_INVALID;
+    }
+    return reduceLike(
+      K_REDUCE, send, recv, count, dtype, op, root, FB_ALGO_AUTO, flags, s);
+}
+
+int Communicator::reduceScatter(const void* send,
+                                void* recv,
+                                size_t recvCount,
+                                int dtype,
+                                int op,
+                                int flags,
+                                cudaStream_t s)
+{
+    return reduceLike(K_REDUCE_SCATTER,
+                      send,
+                      recv,
+                      recvCount,
+                      dtype,
+                      op,
+                      0,
+                      FB_ALGO_AUTO,
+                      flags,
+                      s);
+}
+
+int Communicator::scan(const void* send,
+                       void* recv,
+                       size_t count,
+                       int dtype,
+                       int op,
+                       int flags,
+                       cudaStream_t s)
+{
+    return reduceLike(
+      K_SCAN, send, recv, count, dtype, op, 0, FB_ALGO_AUTO, flags, s);
+}
+
+// ---------------------------------------------------------------------------
+// Data movement
+// ---------------------------------------------------------------------------
+int Communicator::moveLike(int mode,
+                           const void* send,
+                           void* recv,
+                           size_t chunkBytes,
+                           int root,
+                           int flags,
+                           cudaStream_t s)
+{
+    const int n = dev_.nranks;
+    const int rank = dev_.rank;
+    cudaSetDevice(device_);
+    const bool symmetric = (flags & FB_FLAG_SYMMETRIC) != 0;
+    const int noSync = (flags & FB_FLAG_NOSYNC) ? 1 : 0;
+    if (chunkBytes == 0) {
+        return barrier(s);
+    }
+    // what this rank contributes (bytes) and whether it is a source at all
+    const bool rooted = (mode == fb::MOVE_GATHER || mode == fb::MOVE_SCATTER ||
+                         mode == fb::MOVE_BCAST);
+    const bool isSource =
+      (mode == fb::MOVE_ALLGATHER || mode == fb::MOVE_ALLTOALL ||
+       mode == fb::MOVE_GATHER) ||
+      (rank == root);
+    // rows x rowBytes describes the source layout per rank
+    const int srcRows =
+      (mode == fb::MOVE_ALLTOALL || mode == fb::MOVE_SCATTER) ? n : 1;
+
+    (void)rooted;
+
+    lastAlgo_ = FB_ALGO_ONESHOT;
+    // ---- NVLS fast paths on symmetric buffers ----
+    if (symmetric && hasMulticast() && (chunkBytes % 16) == 0 &&
+        chunkBytes >= cfg_.nvlsMinBytes &&
+        ((mode == fb::MOVE_ALLGATHER && inHeap(recv, chunkBytes * n)) ||
+         mode == fb::MOVE_BCAST)) {
+        fb::NvlsArgs a;
+        memset(&a, 0, sizeof(a));
+        a.comm = dev_;
+        a.noSync = noSync;
+        a.outBase = 0;
+        uint64_t nVec = chunkBytes / 16;
+        if (mode == fb::MOVE_ALLGATHER) {
+            a.mode = fb::NVLS_ALLGATHER;
+            a.sendOff = offsetOf(send);
+            a.recvOff = offsetOf(recv) + (uint64_t)rank * chunkBytes;
+            a.vecBegin = 0;
+            a.vecEnd = nVec;
+        } else {
+            a.mode = fb::NVLS_BCAST;
+            a.sendOff = offsetOf(recv); // bcast buffer is in-out
+            a.recvOff = offsetOf(recv);
+            a.vecBegin = 0;
+            a.vecEnd = (rank == root) ? nVec : 0;
+        }
+        lastAlgo_ = FB_ALGO_NVLS;
+        stats_.algoCount[FB_ALGO_NVLS]++;
+        stats_.launches++;
+        stats_.bytes += chunkBytes;
+        return fb::launchNvls(a, -1, blocksFor(nVec, 4), cfg_.threads, s) ==
+                   cudaSuccess
+                 ? FB_OK
+                 : FB_E_CUDA;
+    }
+
+    // ---- large symmetric broadcast: scatter + allgather in one kernel ----
+    if (mode == fb::MOVE_BCAST && symmetric &&
+        chunkBytes >= cfg_.bcast2StepMinBytes && (chunkBytes % 16) == 0) {
+        fb::MoveArgs a;
+        memset(&a, 0, sizeof(a));
+        a.comm = dev_;
+        a.sendOff = offsetOf(recv);
+        a.recvOff = offsetOf(recv);
+        a.recvLocal = (uint8_t*)recv;
+        a.chunkBytes = chunkBytes;
+        a.mode = fb::MOVE_BCAST_2STEP;
+        a.root = root;
+        a.noSync = noSync;
+        lastAlgo_ = FB_ALGO_TWOSHOT;
+        stats_.algoCount[FB_ALGO_TWOSHOT]++;
+        stats_.launches++;
+        stats_.bytes += chunkBytes;
+        return fb::launchMove(
+                 a, 16, blocksFor(chunkBytes / 16 / n, 4), cfg_.threads, s) ==
+                   cudaSuccess
+                 ? FB_OK
+                 : FB_E_CUDA;
+    }
+
+    // ---- generic pull, staged in pieces when buffers are not symmetric ----
+    uint64_t piece = chunkBytes;
+    if (!symmetric) {
+        uint64_t cap = (uint64_t)cfg_.stageBytes / srcRows;
+        cap -= cap % 16;
+        if (cap == 0) {
+            return FB_E_TOO_LARGE;
+        }
+        piece = std::min<uint64_t>(chunkBytes, cap);
+    }
+    stats_.algoCount[FB_ALGO_ONESHOT]++;
+    for (uint64_t done = 0; done < chunkBytes; done += piece) {
+        const uint64_t len = std::min<uint64_t>(piece, chunkBytes - done);
+        fb::MoveArgs a;
+        memset(&a, 0, sizeof(a));
+        a.comm = dev_;
+        a.mode = mode;
+        a.root = root;
+        a.noSync = noSync;
+        a.chunkBytes = len;
+        a.recvLocal = (uint8_t*)recv + done;
+        a.dstStride = chunkBytes;
+        if (symmetric) {
+            const void* src = (mode == fb::MOVE_BCAST) ? recv : send;
+            a.sendOff = offsetOf(src) + done;
+            a.srcStride = chunkBytes;
+        } else {
+            a.sendOff = stageSendOff_;
+            a.srcStride = len;
+            if (isSource) {
+                const uint8_t* src =
+                  (const uint8_t*)((mode == fb::MOVE_BCAST) ? recv : send);
+                cudaError_t ce;
+                if (srcRows == 1) {
+                    ce = cudaMemcpyAsync(heapPtr(stageSendOff_),
+                                         src + done,
+                                         len,
+                                         cudaMemcpyDeviceToDevice,
+                                         s);
+                } else {
+                    ce = cudaMemcpy2DAsync(heapPtr(stageSendOff_),
+                                           len,
+                                           src + done,
+                                           chunkBytes,
+                                           len,
+                                           srcRows,
+                                           cudaMemcpyDeviceToDevice,
+                                           s);
+                }
+                if (ce != cudaSuccess) {
+                    return FB_E_CUDA;
+                }
+                stats_.stagedCopies++;
+            }
+        }
+        int width = std::min({ alignWidth((uint64_t)(uintptr_t)a.recvLocal),
+                               alignWidth(a.sendOff),
+                               alignWidth(len),
+                               alignWidth(a.dstStride),
+                               alignWidth(a.srcStride) });
+        uint64_t words = len / width;
+        cudaError_t ce = fb::launchMove(
+          a, width, blocksFor(words, 2), cfg_.threads, s);
+        if (ce != cudaSuccess) {
+            return FB_E_CUDA;
+        }
+        stats_.launches++;
+        stats_.bytes += len;
+    }
+    return FB_OK;
+}
+
+int Communicator::broadcast(void* buf,
+                            size_t bytes,
+                            int root,
+                            int flags,
+                            cudaStream_t s)
+{
+    if (root < 0 || root >= dev_.nranks) {
+        return FB_E_INVALID;
+    }
+    if ((flags & FB_FLAG_SYMMETRIC) && !inHeap(buf, bytes)) {
+        return FB_E_INVALID;
+    }
+    return moveLike(fb::MOVE_BCAST, buf, buf, bytes, root, flags, s);
+}
+
+int Communicator::allGather(const void* send,
+                            void* recv,
+                            size_t bytesPerRank,
+                            int flags,
+                            cudaStream_t s)
+{
+    if ((flags & FB_FLAG_SYMMETRIC) &&
+        (!inHeap(send, bytesPerRank) ||
+         !inHeap(recv, bytesPerRank * dev_.nranks))) {
+        // pull only needs the *send* side symmetric
+        if (!inHeap(send, bytesPerRank)) {
+            return FB_E_INVALID;
+        }
+    }
+    return moveLike(fb::MOVE_ALLGATHER, send, recv, bytesPerRank, 0, flags, s);
+}
+
+int Communicator::gather(const void* send,
+                         void* recv,
+                         size_t bytesPerRank,
+                         int root,
+                         int flags,
+                         cudaStream_t s)
+{
+    if (root < 0 || root >= dev_.nranks) {
+        return FB_E_INVALID;
+    }
+    return moveLike(fb::MOVE_GATHER, send, recv, bytesPerRank, root, flags, s);
+}
+
+int Communicator::scatter(const void* send,
+                          void* recv,
+                          size_t bytesPerRank,
+                          int root,
+                          int flags,
+                          cudaStream_t s)
+{
+    if (root < 0 || root >= dev_.nranks) {
+        return FB_E_INVALID;
+    }
+    return moveLike(fb::MOVE_SCATTER, send, recv, bytesPerRank, root, flags, s);
+}
+
+int Communicator::allToAll(const void* send,
+                           void* recv,
+                           size_t bytesPerRank,
+                           int flags,
+                           cudaStream_t s)
+{
+    return moveLike(fb::MOVE_ALLTOALL, send, recv, bytesPerRank, 0, flags, s);
+}
+
+int Communicator::barrier(cudaStream_t s)
+{
+    cudaSetDevice(device_);
+    if (dev_.nranks == 1) {
+        return FB_OK;
+    }
+    stats_.launches++;
+    return fb::launchBarrier(dev_, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------
+// Point to point
+// ---------------------------------------------------------------------------
+int Communicator::send(const void* buf, size_t bytes, int peer, cudaStream_t s)
+{
+    if (peer < 0 || peer >= dev_.nranks || peer == dev_.rank) {
+        return FB_E_INVALID;
+    }
+    cudaSetDevice(device_);
+    fb::P2PArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = dev_;
+    a.local = (uint8_t*)buf;
+    a.bytes = bytes;
+    a.mboxOff = mboxOff_;
+    a.slotBytes = cfg_.slotBytes;
+    a.peer = peer;
+    stats_.launches++;
+    stats_.bytes += bytes;
+    int w = alignWidth((uint64_t)(uintptr_t)buf);
+    return fb::launchP2PSend(a, w, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+}
+
+int Communicator::recv(void* buf, size_t bytes, int peer, cudaStream_t s)
+{
+    if (peer < 0 || peer >= dev_.nranks || peer == dev_.rank) {
+        return FB_E_INVALID;
+    }
+    cudaSetDevice(device_);
+    fb::P2PArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = dev_;
+    a.local = (uint8_t*)buf;
+    a.bytes = bytes;
+    a.mboxOff = mboxOff_;
+    a.slotBytes = cfg_.slotBytes;
+    a.peer = peer;
+    stats_.launches++;
+    int w = alignWidth((uint64_t)(uintptr_t)buf);
+    return fb::launchP2PRecv(a, w, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+}
+
+int Communicator::putSignal(const void* local,
+                            uint64_t dstOffset,
+                            size_t bytes,
+                            int peer,
+                            int signalIdx,
+                            int blocks,
+                            cudaStream_t s)
+{
+    if (peer < 0 || peer >= dev_.nranks || signalIdx < 0 ||
+        signalIdx >= FB_SIG_USER_WORDS || blocks < 1) {
+        return FB_E_INVALID;
+    }
+    cudaSetDevice(device_);
+    fb::PutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = dev_;
+    a.local = (const uint8_t*)local;
+    a.dstOff = dstOffset;
+    a.bytes = bytes;
+    a.peer = peer;
+    a.signalIdx = signalIdx;
+    int w = std::min(alignWidth((uint64_t)(uintptr_t)local),
+                     alignWidth(dstOffset));
+    stats_.launches++;
+    stats_.bytes += bytes;
+    return fb::launchPutSignal(a, w, blocks, s) == cudaSuccess ? FB_OK
+                                                               : FB_E_CUDA;
+}
+
+int Communicator::waitSignal(int signalIdx, uint32_t count, cudaStream_t s)
+{
+    if (signalIdx < 0 || signalIdx >= FB_SIG_USER_WORDS) {
+        return FB_E_INVALID;
+    }
+    cudaSetDevice(device_);
+    stats_.launches++;
+    return fb::launchWaitSignal(dev_, signalIdx, count, s) == cudaSuccess
+             ? FB_OK
+             : FB_E_CUDA;
+}
+
+} // namespace faabric::device

@@ -1,0 +1,119 @@
+"""Data-parallel gradient synchronisation — the flagship workload.
+
+``GradientSync`` owns one flat symmetric-heap buffer holding every gradient
+tensor of the model and all-reduces them **one MPI_Allreduce-shaped call per
+tensor** (the reference benchmark's semantics), each call being a single fused
+peer-memory kernel.  The per-step launch sequence is captured once into a CUDA
+graph and replayed, so a step costs one graph launch on the host.
+
+Public API used by bench.py / users:
+
+    sync = GradientSync(comm, sizes, dtype=torch.int32)
+    sync.step()                       # device-resident gradients
+    loss = sync.step_from_host(pinned_host_grads)   # H2D + allreduce + D2H
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from ..parallel import Communicator
+
+
+class GradientSync:
+    def __init__(
+        self,
+        comm: Communicator,
+        sizes: Sequence[int],
+        dtype=torch.int32,
+        op: str = "sum",
+        algo: str = "auto",
+        use_graph: bool = True,
+        in_place: bool = False,
+    ):
+        self.comm = comm
+        self.sizes = [int(s) for s in sizes]
+        self.dtype = dtype
+        self.op = op
+        self.algo = algo
+        self.use_graph = use_graph
+        esize = torch.empty((), dtype=dtype).element_size()
+        # every tensor starts on a 256-byte boundary inside the flat buffers
+        self.offsets = []
+        cur = 0
+        for s in self.sizes:
+            self.offsets.append(cur)
+            cur += (s * esize + 255) // 256 * 256 // esize
+        self.total_padded = cur
+        self.total_elems = sum(self.sizes)
+        self.nbytes = self.total_elems * esize
+        self.send = comm.empty(cur, dtype)
+        self.recv = self.send if in_place else comm.empty(cur, dtype)
+        self.send.zero_()
+        if not in_place:
+            self.recv.zero_()
+        self.send_views = [self.send[o : o + s] for o, s in zip(self.offsets, self.sizes)]
+        self.recv_views = [self.recv[o : o + s] for o, s in zip(self.offsets, self.sizes)]
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._stream = torch.cuda.Stream(device=comm.device)
+        self._result = torch.zeros(2, dtype=torch.int64, device=f"cuda:{comm.device}")
+        self._result_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.launches_per_step = len(self.sizes)
+
+    # ------------------------------------------------------------------ core
+    def _issue(self, stream):
+        for s, r in zip(self.send_views, self.recv_views):
+            self.comm.all_reduce(s, r, op=self.op, algo=self.algo, stream=stream)
+
+    def _capture(self):
+        # warm the launch path once outside capture (lazy module loading)
+        torch.cuda.synchronize(self.comm.device)
+        self._issue(self._stream)
+        self._stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self._stream):
+            self._issue(self._stream)
+        self._graph = g
+
+    def step(self, stream: Optional[torch.cuda.Stream] = None):
+        """All-reduce every gradient tensor (async on `stream`)."""
+        stream = stream or torch.cuda.current_stream(self.comm.device)
+        if self.use_graph:
+            if self._graph is None:
+                self._capture()
+            with torch.cuda.stream(stream):
+                self._graph.replay()
+        else:
+            self._issue(stream)
+
+    def step_from_host(self, host_grads: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+        """End-to-end step: copy this step's gradients from pinned host memory,
+        all-reduce, and read a result digest (first element + checksum of the
+        first tensor) back to the host.  Returns the host digest tensor after
+        synchronising the stream."""
+        stream = stream or torch.cuda.current_stream(self.comm.device)
+        with torch.cuda.stream(stream):
+            self.send[: host_grads.numel()].copy_(host_grads, non_blocking=True)
+            self.step(stream)
+            first = self.recv_views[0]
+            self._result[0] = first[0].to(torch.int64)
+            self._result[1] = first.to(torch.int64).sum()
+            self._result_host.copy_(self._result, non_blocking=True)
+        stream.synchronize()
+        return self._result_host
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.total_padded * self.send.element_size()
+
+    @property
+    def d2h_bytes_per_step(self):
+        return self._result_host.numel() * 8
+
+    def close(self):
+        self._graph = None
+        if self.recv is not self.send:
+            self.comm.free(self.recv)
+        self.comm.free(self.send)

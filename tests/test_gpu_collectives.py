@@ -1,0 +1,445 @@
+"""GPU numerics tests of the peer-memory collectives against plain PyTorch
+references.  Runs N ranks inside one process; with a single GPU all ranks share
+it (each on its own stream), which exercises the same flag/barrier protocol as
+a real multi-GPU run.  Mirrors the reference's collective tests
+(tests/test/mpi/test_mpi_world.cpp: "Test collective messaging locally",
+"Test reduce", "Test operator reduce", "Test gather and allgather",
+"Test scan", "Test all-to-all")."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from faabric_b200.parallel import LocalGroup  # noqa: E402
+
+GROUPS = {}
+
+
+def group(n):
+    if n not in GROUPS:
+        GROUPS[n] = LocalGroup(
+            n,
+            heapBytes=96 << 20,
+            stageBytes=8 << 20,
+            maxBlocks=8,
+            timeoutMs=8000,
+        )
+    return GROUPS[n]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cleanup():
+    yield
+    for g in GROUPS.values():
+        g.close()
+    GROUPS.clear()
+
+
+def make_inputs(n, numel, dtype, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = []
+    for r in range(n):
+        if dtype.is_floating_point:
+            t = (torch.rand(numel, generator=g) * 2 - 1).to(dtype)
+        elif dtype == torch.bool:
+            t = torch.randint(0, 2, (numel,), generator=g).to(dtype)
+        else:
+            t = torch.randint(-50, 50, (numel,), generator=g).to(dtype)
+        out.append(t.to(dev))
+    return out
+
+
+def ref_reduce(inputs, op):
+    dt = inputs[0].dtype
+    if dt.is_floating_point:
+        acc = inputs[0].to(torch.float64)
+        for t in inputs[1:]:
+            t = t.to(torch.float64)
+            if op == "sum":
+                acc = acc + t
+            elif op == "prod":
+                acc = acc * t
+            elif op == "max":
+                acc = torch.maximum(acc, t)
+            elif op == "min":
+                acc = torch.minimum(acc, t)
+        return acc
+    acc = inputs[0].clone()
+    for t in inputs[1:]:
+        if op == "sum":
+            acc = acc + t
+        elif op == "prod":
+            acc = acc * t
+        elif op == "max":
+            acc = torch.maximum(acc, t)
+        elif op == "min":
+            acc = torch.minimum(acc, t)
+        elif op == "band":
+            acc = acc & t
+        elif op == "bor":
+            acc = acc | t
+        elif op == "bxor":
+            acc = acc ^ t
+        elif op == "land":
+            acc = ((acc != 0) & (t != 0)).to(dt)
+        elif op == "lor":
+            acc = ((acc != 0) | (t != 0)).to(dt)
+    return acc
+
+
+def check(out, ref, dtype):
+    if dtype.is_floating_point:
+        tol = {torch.float32: 1e-5, torch.float64: 1e-12, torch.float16: 2e-2, torch.bfloat16: 1e-1}[dtype]
+        torch.testing.assert_close(out.to(torch.float64), ref.to(torch.float64), atol=tol, rtol=tol)
+    else:
+        assert torch.equal(out, ref.to(out.dtype))
+
+
+def no_errors(g):
+    assert g.check_errors() == [0] * g.size
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 3])
+@pytest.mark.parametrize("algo", ["ll", "oneshot", "twoshot"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int32, torch.bfloat16])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_allreduce_sum(n, algo, dtype, symmetric):
+    g = group(n)
+    for numel in (1, 7, 1000, 4099, 65536 + 5):
+        if algo == "ll" and numel * 4 > 65536:
+            continue
+        ins = make_inputs(n, numel, dtype, f"cuda:{g.devices[0]}", seed=numel)
+        sends, recvs = [], []
+        for r, c in enumerate(g.comms):
+            if symmetric:
+                s = c.empty(numel, dtype)
+                s.copy_(ins[r].to(s.device))
+                o = c.empty(numel, dtype)
+            else:
+                s = ins[r].to(f"cuda:{c.device}").clone()
+                o = torch.empty_like(s)
+            sends.append(s)
+            recvs.append(o)
+        torch.cuda.synchronize()
+        g.run(lambda c, r, st: c.all_reduce(sends[r], recvs[r], op="sum", algo=algo))
+        g.synchronize()
+        no_errors(g)
+        ref = ref_reduce([t.cpu() for t in ins], "sum")
+        for r in range(n):
+            check(recvs[r].cpu(), ref, dtype)
+            # inputs must be untouched
+            assert torch.equal(sends[r].cpu(), ins[r].cpu())
+        # identical bits on every rank
+        for r in range(1, n):
+            assert torch.equal(recvs[r].cpu().view(torch.uint8), recvs[0].cpu().view(torch.uint8))
+        if symmetric:
+            for c, s, o in zip(g.comms, sends, recvs):
+                c.free(s)
+                c.free(o)
+
+
+@pytest.mark.parametrize("n", [2, 8])
+def test_allreduce_inplace_and_auto(n):
+    g = group(n)
+    for numel in (33, 50000, 600000):
+        ins = make_inputs(n, numel, torch.float32, "cuda:0", seed=numel + 1)
+        bufs = []
+        for r, c in enumerate(g.comms):
+            b = c.empty(numel, torch.float32)
+            b.copy_(ins[r].to(b.device))
+            bufs.append(b)
+        torch.cuda.synchronize()
+        g.run(lambda c, r, st: c.all_reduce(bufs[r]))
+        g.synchronize()
+        no_errors(g)
+        ref = ref_reduce([t.cpu() for t in ins], "sum")
+        for r in range(n):
+            check(bufs[r].cpu(), ref, torch.float32)
+        for c, b in zip(g.comms, bufs):
+            c.free(b)
+
+
+OPS_BY_DTYPE = [
+    (torch.float32, ["max", "min", "prod"]),
+    (torch.float64, ["sum", "max"]),
+    (torch.float16, ["sum", "max"]),
+    (torch.int32, ["max", "min", "prod", "band", "bor", "bxor", "land", "lor"]),
+    (torch.int64, ["sum", "max", "min", "bor"]),
+    (torch.int8, ["sum", "max", "min", "band"]),
+    (torch.uint8, ["sum", "max", "bor"]),
+    (torch.int16, ["sum", "min", "bxor"]),
+]
+
+
+@pytest.mark.parametrize("dtype,ops", OPS_BY_DTYPE)
+def test_allreduce_ops_dtypes(dtype, ops):
+    n = 4
+    g = group(n)
+    numel = 3001
+    for op in ops:
+        for algo in ("oneshot", "twoshot", "ll"):
+            ins = make_inputs(n, numel, dtype, "cuda:0", seed=hash(op) % 1000)
+            if op == "prod":
+                ins = [(t.to(torch.float64).sign() + (t == 0).double()).to(dtype) for t in ins]
+            sends = [t.to(f"cuda:{c.device}").clone() for t, c in zip(ins, g.comms)]
+            recvs = [torch.empty_like(s) for s in sends]
+            g.run(lambda c, r, st: c.all_reduce(sends[r], recvs[r], op=op, algo=algo))
+            g.synchronize()
+            no_errors(g)
+            ref = ref_reduce([t.cpu() for t in ins], op)
+            for r in range(n):
+                check(recvs[r].cpu(), ref, dtype)
+
+
+def test_unsupported_combo_rejected():
+    g = group(2)
+    from faabric_b200.parallel import CommError
+
+    t = torch.zeros(8, device="cuda:0")
+    with pytest.raises(CommError):
+        g.comms[0].all_reduce(t, t.clone(), op="band")
+
+
+@pytest.mark.parametrize("n", [2, 4, 5])
+def test_reduce_scan_reducescatter(n):
+    g = group(n)
+    dtype = torch.float32
+    for numel in (5, 4096, 70001):
+        ins = make_inputs(n, numel, dtype, "cuda:0", seed=numel)
+        sends = []
+        for r, c in enumerate(g.comms):
+            s = c.empty(numel, dtype)
+            s.copy_(ins[r].to(s.device))
+            sends.append(s)
+        torch.cuda.synchronize()
+        # reduce to root 1
+        root = 1
+        outs = [torch.full((numel,), -7.0, device=f"cuda:{c.device}") for c in g.comms]
+        g.run(lambda c, r, st: c.reduce(sends[r], outs[r], root=root))
+        g.synchronize()
+        no_errors(g)
+        check(outs[root].cpu(), ref_reduce([t.cpu() for t in ins], "sum"), dtype)
+        for r in range(n):
+            if r != root:
+                assert torch.all(outs[r] == -7.0)
+        # scan
+        outs = [torch.empty(numel, device=f"cuda:{c.device}") for c in g.comms]
+        g.run(lambda c, r, st: c.scan(sends[r], outs[r]))
+        g.synchronize()
+        no_errors(g)
+        for r in range(n):
+            check(outs[r].cpu(), ref_reduce([t.cpu() for t in ins[: r + 1]], "sum"), dtype)
+        for c, s in zip(g.comms, sends):
+            c.free(s)
+    # reduce-scatter: per-rank slice must be a multiple of 16 bytes
+    per = 1024
+    ins = make_inputs(n, per * n, dtype, "cuda:0", seed=3)
+    sends = []
+    for r, c in enumerate(g.comms):
+        s = c.empty(per * n, dtype)
+        s.copy_(ins[r].to(s.device))
+        sends.append(s)
+    outs = [torch.empty(per, device=f"cuda:{c.device}") for c in g.comms]
+    torch.cuda.synchronize()
+    g.run(lambda c, r, st: c.reduce_scatter(sends[r], outs[r]))
+    g.synchronize()
+    no_errors(g)
+    ref = ref_reduce([t.cpu() for t in ins], "sum")
+    for r in range(n):
+        check(outs[r].cpu(), ref[r * per : (r + 1) * per], dtype)
+    for c, s in zip(g.comms, sends):
+        c.free(s)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 3])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_move_collectives(n, symmetric):
+    g = group(n)
+    for numel in (1, 13, 1024, 40001):
+        dtype = torch.int32
+
+        def alloc(c, count):
+            if symmetric:
+                return c.empty(count, dtype)
+            return torch.empty(count, dtype=dtype, device=f"cuda:{c.device}")
+
+        # ---- allgather
+        sends = [alloc(c, numel) for c in g.comms]
+        for r, s in enumerate(sends):
+            s.copy_(torch.arange(numel, dtype=dtype) + 1000 * r)
+        recvs = [torch.zeros(numel * n, dtype=dtype, device=f"cuda:{c.device}") for c in g.comms]
+        torch.cuda.synchronize()
+        g.run(lambda c, r, st: c.all_gather(sends[r], recvs[r]))
+        g.synchronize()
+        no_errors(g)
+        ref = torch.cat([torch.arange(numel, dtype=dtype) + 1000 * r for r in range(n)])
+        for r in range(n):
+            assert torch.equal(recvs[r].cpu(), ref)
+        # ---- gather to root n-1
+        root = n - 1
+        recvs = [torch.zeros(numel * n, dtype=dtype, device=f"cuda:{c.device}") for c in g.comms]
+        g.run(lambda c, r, st: c.gather(sends[r], recvs[r], root=root))
+        g.synchronize()
+        no_errors(g)
+        assert torch.equal(recvs[root].cpu(), ref)
+        # ---- broadcast from root 0
+        bufs = [alloc(c, numel) for c in g.comms]
+        for r, b in enumerate(bufs):
+            b.fill_(r + 1)
+        bufs[0].copy_(torch.arange(numel, dtype=dtype) * 3)
+        torch.cuda.synchronize()
+        g.run(lambda c, r, st: c.broadcast(bufs[r], root=0))
+        g.synchronize()
+        no_errors(g)
+        for r in range(n):
+            assert torch.equal(bufs[r].cpu(), torch.arange(numel, dtype=dtype) * 3)
+        # ---- alltoall / scatter
+        a2a_send = [alloc(c, numel * n) for c in g.comms]
+        for r, s in enumerate(a2a_send):
+            s.copy_(torch.arange(numel * n, dtype=dtype) + 100000 * r)
+        a2a_recv = [torch.zeros(numel * n, dtype=dtype, device=f"cuda:{c.device}") for c in g.comms]
+        torch.cuda.synchronize()
+        g.run(lambda c, r, st: c.all_to_all(a2a_send[r], a2a_recv[r]))
+        g.synchronize()
+        no_errors(g)
+        for r in range(n):
+            exp = torch.cat(
+                [torch.arange(r * numel, (r + 1) * numel, dtype=dtype) + 100000 * p for p in range(n)]
+            )
+            assert torch.equal(a2a_recv[r].cpu(), exp)
+        sc_recv = [torch.zeros(numel, dtype=dtype, device=f"cuda:{c.device}") for c in g.comms]
+        g.run(lambda c, r, st: c.scatter(a2a_send[r], sc_recv[r], root=1))
+        g.synchronize()
+        no_errors(g)
+        for r in range(n):
+            exp = torch.arange(r * numel, (r + 1) * numel, dtype=dtype) + 100000
+            assert torch.equal(sc_recv[r].cpu(), exp)
+        if symmetric:
+            for c, a, b, d in zip(g.comms, sends, bufs, a2a_send):
+                c.free(a)
+                c.free(b)
+                c.free(d)
+
+
+def test_large_symmetric_broadcast_two_step():
+    n = 4
+    g = group(n)
+    numel = (3 << 20) // 4 + 4  # > bcast2StepMinBytes, multiple of 16 bytes
+    bufs = [c.empty(numel, torch.int32) for c in g.comms]
+    for r, b in enumerate(bufs):
+        b.fill_(r)
+    bufs[2].copy_(torch.arange(numel, dtype=torch.int32))
+    torch.cuda.synchronize()
+    g.run(lambda c, r, st: c.broadcast(bufs[r], root=2))
+    g.synchronize()
+    no_errors(g)
+    assert g.comms[0].last_algo == "twoshot"
+    for r in range(n):
+        assert torch.equal(bufs[r].cpu(), torch.arange(numel, dtype=torch.int32))
+    for c, b in zip(g.comms, bufs):
+        c.free(b)
+
+
+@pytest.mark.parametrize("nbytes", [0, 1, 15, 4096, 300001, 5 << 20])
+def test_send_recv_ring(nbytes):
+    n = 4
+    g = group(n)
+    srcs = [
+        (torch.arange(nbytes, dtype=torch.int64) * (r + 3) % 251).to(torch.uint8).to(f"cuda:{c.device}")
+        for r, c in enumerate(g.comms)
+    ]
+    dsts = [torch.zeros(nbytes, dtype=torch.uint8, device=f"cuda:{c.device}") for c in g.comms]
+    side = [torch.cuda.Stream(device=c.device) for c in g.comms]
+    torch.cuda.synchronize()
+    # ring: r sends to r+1, receives from r-1 (recv on a side stream so the
+    # exchange cannot deadlock, like MpiWorld::sendRecv = irecv + send + wait)
+    for r, c in enumerate(g.comms):
+        c.recv(dsts[r], (r - 1) % n, stream=side[r])
+    g.run(lambda c, r, st: c.send(srcs[r], (r + 1) % n))
+    g.synchronize()
+    for s in side:
+        s.synchronize()
+    no_errors(g)
+    for r in range(n):
+        assert torch.equal(dsts[r].cpu(), srcs[(r - 1) % n].cpu())
+
+
+def test_send_recv_fifo_order():
+    g = group(2)
+    a, b = g.comms
+    msgs = [torch.full((1000 + i,), i, dtype=torch.int32, device="cuda:0") for i in range(6)]
+    outs = [torch.zeros_like(m) for m in msgs]
+    for m in msgs:
+        a.send(m, 1, stream=g.streams[0])
+    for o in outs:
+        b.recv(o, 0, stream=g.streams[1])
+    g.synchronize()
+    no_errors(g)
+    for m, o in zip(msgs, outs):
+        assert torch.equal(m.cpu(), o.cpu())
+
+
+def test_put_signal_and_barrier():
+    g = group(2)
+    a, b = g.comms
+    dst = [c.zeros(5000, torch.float32) for c in g.comms]
+    src = torch.arange(5000, dtype=torch.float32, device=f"cuda:{a.device}")
+    torch.cuda.synchronize()
+    a.put_signal(src, dst[0], peer=1, signal=3, blocks=4, stream=g.streams[0])
+    b.wait_signal(signal=3, count=4, stream=g.streams[1])
+    g.run(lambda c, r, st: c.barrier())
+    g.synchronize()
+    no_errors(g)
+    assert torch.equal(dst[1].cpu(), src.cpu())
+    for c, d in zip(g.comms, dst):
+        c.free(d)
+
+
+def test_graph_capture_replay():
+    """Collectives keep their epochs in device memory so a captured graph can be
+    replayed (launch-bound loops are captured once, replayed many times)."""
+    n = 2
+    g = group(n)
+    numel = 2048
+    bufs = [c.empty(numel, torch.float32) for c in g.comms]
+    outs = [c.empty(numel, torch.float32) for c in g.comms]
+    for r, b in enumerate(bufs):
+        b.fill_(float(r + 1))
+    torch.cuda.synchronize()
+    graphs = []
+    for r, c in enumerate(g.comms):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=g.streams[r]):
+            c.all_reduce(bufs[r], outs[r], algo="oneshot", stream=g.streams[r])
+            c.all_reduce(bufs[r], outs[r], algo="ll", stream=g.streams[r])
+        graphs.append(gr)
+    for it in range(3):
+        for r, b in enumerate(bufs):
+            b.fill_(float(r + 1 + it))
+        torch.cuda.synchronize()
+        for r in range(n):
+            with torch.cuda.stream(g.streams[r]):
+                graphs[r].replay()
+        g.synchronize()
+        torch.cuda.synchronize()
+        no_errors(g)
+        for r in range(n):
+            assert torch.all(outs[r] == float(3 + 2 * it))
+    for c, a, b in zip(g.comms, bufs, outs):
+        c.free(a)
+        c.free(b)
+
+
+def test_watchdog_reports_missing_peer():
+    """A rank that never shows up must not hang the GPU: the bounded spin sets
+    the error word and the kernel retires (failure-detection)."""
+    g = LocalGroup(2, heapBytes=1 << 20, stageBytes=1 << 20, maxBlocks=2, timeoutMs=300)
+    try:
+        t = torch.ones(1 << 16, device="cuda:0")
+        o = torch.empty_like(t)
+        g.comms[0].all_reduce(t, o, algo="oneshot", stream=g.streams[0])
+        g.streams[0].synchronize()
+        assert g.comms[0].check_error(g.streams[0]) != 0
+    finally:
+        g.close()
