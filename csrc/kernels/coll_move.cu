@@ -516,4 +516,30 @@ cudaError_t launchWaitSignal(const FbCommDev& c,
     return cudaGetLastError();
 }
 
+cudaError_t preloadMoveKernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+#define FB_PRELOAD(k)                                                          \
+    if (e == cudaSuccess) {                                                    \
+        e = cudaFuncGetAttributes(&a, k);                                      \
+    }
+#define FB_PRELOAD_W(W)                                                        \
+    FB_PRELOAD((moveKernel<W, 0>))                                             \
+    FB_PRELOAD((moveKernel<W, 2>))                                             \
+    FB_PRELOAD((moveKernel<W, 4>))                                             \
+    FB_PRELOAD((moveKernel<W, 8>))                                             \
+    FB_PRELOAD((p2pSendKernel<W>))                                             \
+    FB_PRELOAD((p2pRecvKernel<W>))                                             \
+    FB_PRELOAD((putSignalKernel<W>))
+    FB_PRELOAD_W(16)
+    FB_PRELOAD_W(4)
+    FB_PRELOAD_W(1)
+    FB_PRELOAD(barrierKernel)
+    FB_PRELOAD(waitSignalKernel)
+#undef FB_PRELOAD_W
+#undef FB_PRELOAD
+    return e;
+}
+
 } // namespace fb

@@ -296,4 +296,38 @@ cudaError_t launchNvls(const NvlsArgs& a,
     return cudaGetLastError();
 }
 
+#define NVLS_PRELOAD(V)                                                        \
+    if (e == cudaSuccess) {                                                    \
+        e = cudaFuncGetAttributes(&a, nvlsKernel<V>);                          \
+    }
+
+cudaError_t preloadNvlsKernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+    NVLS_PRELOAD(MM_ADD_F32)
+    NVLS_PRELOAD(MM_ADD_F16)
+    NVLS_PRELOAD(MM_MIN_F16)
+    NVLS_PRELOAD(MM_MAX_F16)
+    NVLS_PRELOAD(MM_ADD_BF16)
+    NVLS_PRELOAD(MM_MIN_BF16)
+    NVLS_PRELOAD(MM_MAX_BF16)
+    NVLS_PRELOAD(MM_ADD_U32)
+    NVLS_PRELOAD(MM_MIN_U32)
+    NVLS_PRELOAD(MM_MAX_U32)
+    NVLS_PRELOAD(MM_MIN_S32)
+    NVLS_PRELOAD(MM_MAX_S32)
+    NVLS_PRELOAD(MM_ADD_U64)
+    NVLS_PRELOAD(MM_MIN_U64)
+    NVLS_PRELOAD(MM_MAX_U64)
+    NVLS_PRELOAD(MM_MIN_S64)
+    NVLS_PRELOAD(MM_MAX_S64)
+    NVLS_PRELOAD(MM_ADD_F64)
+    NVLS_PRELOAD(MM_AND_B32)
+    NVLS_PRELOAD(MM_OR_B32)
+    NVLS_PRELOAD(MM_XOR_B32)
+    NVLS_PRELOAD(MM_COPY)
+    return e;
+}
+
 } // namespace fb

@@ -348,9 +348,32 @@ cudaError_t launchLL(const LLArgs& a, cudaStream_t stream)
 }
 
 template<typename VR>
+cudaError_t preloadReduce()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+#define FB_PRELOAD(k)                                                          \
+    if (e == cudaSuccess) {                                                    \
+        e = cudaFuncGetAttributes(&a, k);                                      \
+    }
+    FB_PRELOAD((reduceKernel<VR, 0>))
+    FB_PRELOAD((reduceKernel<VR, 2>))
+    FB_PRELOAD((reduceKernel<VR, 4>))
+    FB_PRELOAD((reduceKernel<VR, 8>))
+    FB_PRELOAD((llAllReduceKernel<VR, 0>))
+    FB_PRELOAD((llAllReduceKernel<VR, 2>))
+    FB_PRELOAD((llAllReduceKernel<VR, 4>))
+    FB_PRELOAD((llAllReduceKernel<VR, 8>))
+#undef FB_PRELOAD
+    return e;
+}
+
+template<typename VR>
 const ReduceLaunchers* launchersFor()
 {
-    static const ReduceLaunchers l = { &launchReduce<VR>, &launchLL<VR> };
+    static const ReduceLaunchers l = { &launchReduce<VR>,
+                                       &launchLL<VR>,
+                                       &preloadReduce<VR> };
     return &l;
 }
 

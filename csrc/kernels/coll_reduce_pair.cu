@@ -49,4 +49,27 @@ const ReduceLaunchers* findReduceLaunchers(int dtype, int op)
     return findReduceLaunchersPair(dtype, op);
 }
 
+cudaError_t preloadAllKernels()
+{
+    cudaError_t e = cudaSuccess;
+    for (int dt = 0; dt < FB_DTYPE_COUNT && e == cudaSuccess; dt++) {
+        for (int op = 0; op < FB_OP_COUNT && e == cudaSuccess; op++) {
+            const ReduceLaunchers* l = findReduceLaunchers(dt, op);
+            if (l != nullptr) {
+                e = l->preload();
+            }
+        }
+    }
+    if (e == cudaSuccess) {
+        e = preloadMoveKernels();
+    }
+    if (e == cudaSuccess) {
+        e = preloadNvlsKernels();
+    }
+    if (e == cudaSuccess) {
+        e = preloadSnapshotKernels();
+    }
+    return e;
+}
+
 } // namespace fb

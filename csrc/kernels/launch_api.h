@@ -62,6 +62,10 @@ struct ReduceLaunchers
 {
     ReduceLaunchFn reduce;
     LLLaunchFn ll;
+    // Forces the CUDA module/function load of every variant (lazy loading may
+    // otherwise synchronise the context while a peer rank's kernel is spinning
+    // on this one => deadlock until the watchdog fires)
+    cudaError_t (*preload)();
 };
 
 // Lookup implemented across coll_reduce_*.cu; returns nullptr if the
@@ -216,5 +220,11 @@ cudaError_t launchSnapshotApply(uint8_t* image,
                                 uint32_t nDescs,
                                 cudaStream_t s);
 
+
+// Preload every kernel of the library on the current device (see above)
+cudaError_t preloadAllKernels();
+cudaError_t preloadMoveKernels();
+cudaError_t preloadNvlsKernels();
+cudaError_t preloadSnapshotKernels();
 
 } // namespace fb

@@ -729,4 +729,23 @@ cudaError_t launchSnapshotApply(uint8_t* image,
     return cudaGetLastError();
 }
 
+cudaError_t preloadSnapshotKernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, snapshotDiffPushKernel);
+    if (e == cudaSuccess) {
+        e = cudaFuncGetAttributes(&a, dirtyScanKernel);
+    }
+    if (e == cudaSuccess) {
+        e = cudaFuncGetAttributes(&a, flagsOrKernel);
+    }
+    if (e == cudaSuccess) {
+        e = cudaFuncGetAttributes(&a, chunkRunsKernel);
+    }
+    if (e == cudaSuccess) {
+        e = cudaFuncGetAttributes(&a, snapshotApplyKernel);
+    }
+    return e;
+}
+
 } // namespace fb

@@ -387,6 +387,14 @@ std::vector<std::shared_ptr<Communicator>> Communicator::createLocal(
         }
     }
 
+    // Load every kernel now: with lazy module loading the first launch of a
+    // kernel may synchronise the context, which deadlocks against a rank
+    // whose kernel is already spinning on this rank's flags
+    for (int d : distinctDevs) {
+        CUDA_OK(cudaSetDevice(d));
+        CUDA_OK(fb::preloadAllKernels());
+    }
+
     // zero the pads + control areas, allocate error words
     auto group = std::make_shared<LocalGroup>(nranks);
     for (int r = 0; r < nranks; r++) {
@@ -660,6 +668,7 @@ std::shared_ptr<Communicator> Communicator::createIpc(int rank,
         kind = "cuda-ipc";
     }
 
+    CUDA_OK(fb::preloadAllKernels());
     CUDA_OK(cudaMemset(bases[rank], 0, SIG_REGION + c->userOff_));
     uint32_t* err = nullptr;
     CUDA_OK(cudaMalloc((void**)&err, 256));
