@@ -43,6 +43,8 @@ def parse():
                     choices=["allreduce", "sweep", "alltoall", "snapshot", "planner"])
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--channels", type=int, default=4)
+    ap.add_argument("--tuning", default="", help="JSON tuning table (default: profiles/tuning_N<gpus>.json)")
     ap.add_argument("--payload", default="large", choices=["large", "small"])
     ap.add_argument("--out", default="")
     ap.add_argument("--max-bytes", type=int, default=1 << 30)
@@ -134,6 +136,20 @@ def timed(dist: Dist, fn, steps: int, warmup: int):
     return dist.max_over_ranks(ms)
 
 
+def load_tuning(comm, args, dist):
+    """Apply the measured algorithm table for this world size, if present."""
+    path = Path(args.tuning) if args.tuning else ROOT / "profiles" / f"tuning_N{dist.world}.json"
+    if not path.exists():
+        return None
+    try:
+        t = json.loads(path.read_text())
+        comm.set_allreduce_table([(e["max_bytes"], e["algo"]) for e in t["allreduce"]])
+        return str(path)
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] tuning file {path} ignored: {e}", file=sys.stderr)
+        return None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -174,7 +190,9 @@ def mode_allreduce(args, dist: Dist):
         cfg_extra = {"library": "torch.distributed NCCL all_reduce (baseline, not the product)"}
     else:
         comm, group = dist.make_comm(heapBytes=(512 << 20), stageBytes=(16 << 20))
-        sync = GradientSync(comm, sizes, dtype=torch.int32, algo=args.algo, use_graph=not args.no_graph)
+        load_tuning(comm, args, dist)
+        sync = GradientSync(comm, sizes, dtype=torch.int32, algo=args.algo, use_graph=not args.no_graph,
+                            channels=args.channels)
         # deterministic non-trivial contents
         sync.send.copy_(torch.arange(sync.send.numel(), device=dist.device, dtype=torch.int32) % 1000 + dist.rank)
         torch.cuda.synchronize()
@@ -224,6 +242,7 @@ def mode_allreduce(args, dist: Dist):
             "backing": comm.backing,
             "nvls": comm.has_multicast,
             "cuda_graph": not args.no_graph,
+            "channels": args.channels,
             "algo": args.algo,
             "algo_mix": {k: v for k, v in st.items() if k.startswith("algo_") and v},
         }
@@ -326,6 +345,22 @@ def mode_sweep(args, dist: Dist):
         if dist.rank == 0:
             print("[sweep]", json.dumps(row), file=sys.stderr, flush=True)
     err = comm.check_error()
+    # measured selection table: fastest algorithm per size bucket
+    table = []
+    for r in rows:
+        cands = {a: r[a + "_us"] for a in ("ll", "oneshot", "twoshot", "nvls") if (a + "_us") in r}
+        if cands:
+            table.append({"max_bytes": r["bytes"], "algo": min(cands, key=cands.get), "us": min(cands.values())})
+    merged = []
+    for e in table:
+        if merged and merged[-1]["algo"] == e["algo"]:
+            merged[-1]["max_bytes"] = e["max_bytes"]
+        else:
+            merged.append(dict(e))
+    if dist.rank == 0:
+        tp = Path("gpurun_out") / f"tuning_N{n}.json"
+        tp.parent.mkdir(exist_ok=True)
+        tp.write_text(json.dumps({"n_gpus": n, "allreduce": merged, "source": "bench.py --mode sweep"}, indent=1))
     best = max((r.get("auto_busbw", 0) for r in rows), default=0)
     out = {
         "metric": "mpi_allreduce_busbw_sweep_GBps",
@@ -339,6 +374,7 @@ def mode_sweep(args, dist: Dist):
         "backing": comm.backing,
         "nvls": comm.has_multicast,
         "rows": rows,
+        "tuning_table": merged,
         "roofline": "NVLink5 770 GB/s measured per direction per GPU (900 nominal)",
     }
     return out, {"_keep": (comm, group, send, recv)}

@@ -38,6 +38,8 @@ struct FbConfigC
     int32_t useMulticast;
     int32_t maxBlocks;
     int32_t threads;
+    int32_t channels;
+    int32_t reserved;
     uint64_t llMaxBytes;
     uint64_t oneShotMaxBytes;
     uint64_t nvlsMinBytes;
@@ -65,6 +67,8 @@ void fb_default_config(FbConfigC* out)
     out->useMulticast = c.useMulticast;
     out->maxBlocks = c.maxBlocks;
     out->threads = c.threads;
+    out->channels = c.channels;
+    out->reserved = 0;
     out->llMaxBytes = c.llMaxBytes;
     out->oneShotMaxBytes = c.oneShotMaxBytes;
     out->nvlsMinBytes = c.nvlsMinBytes;
@@ -85,6 +89,7 @@ static CommConfig fromC(const FbConfigC* in)
     c.useMulticast = in->useMulticast != 0;
     c.maxBlocks = in->maxBlocks;
     c.threads = in->threads;
+    c.channels = in->channels;
     c.llMaxBytes = in->llMaxBytes;
     c.oneShotMaxBytes = in->oneShotMaxBytes;
     c.nvlsMinBytes = in->nvlsMinBytes;
@@ -199,6 +204,17 @@ int fb_comm_configure(void* h, int key, uint64_t value)
         default:
             return FB_E_INVALID;
     }
+    return FB_OK;
+}
+
+int fb_comm_set_allreduce_table(void* h,
+                                int n,
+                                const uint64_t* maxBytes,
+                                const int* algos)
+{
+    std::vector<uint64_t> mb(maxBytes, maxBytes + n);
+    std::vector<int> al(algos, algos + n);
+    COMM(h)->setAllReduceTable(mb, al);
     return FB_OK;
 }
 

@@ -38,8 +38,9 @@ extern "C" {
 #define FB_SIG_USER_OFF (FB_SIG_MBOX_OFF + 4 * FB_P2P_FLAG_WORDS)
 // user signals (put-with-signal): value words then consumed-count words
 #define FB_SIG_USER_WORDS 256
-// per-CTA epoch words of the LL all-reduce
+// per-CTA epoch words of the LL all-reduce (FB_LL_BLOCKS words per channel)
 #define FB_SIG_LL_EPOCH_OFF (FB_SIG_USER_OFF + 2 * FB_SIG_USER_WORDS)
+#define FB_MAX_CHANNELS 8
 #define FB_SIG_TOTAL_WORDS 4096
 #define FB_SIG_BYTES (FB_SIG_TOTAL_WORDS * 4)
 
@@ -60,6 +61,12 @@ typedef struct FbCommDev {
     uint32_t* err;
     // watchdog for device-side spins, nanoseconds of %globaltimer
     uint64_t timeoutNs;
+    // Channel support: independent collectives may run concurrently (separate
+    // streams / graph branches) when each uses its own slice of the barrier
+    // flag slots.  blockBase = channel * blocksPerChannel.
+    int32_t blockBase;
+    // first LL epoch word of this channel (relative to FB_SIG_LL_EPOCH_OFF)
+    int32_t llEpochBase;
 } FbCommDev;
 
 // ---- element types understood by the reduce kernels ----

@@ -30,6 +30,12 @@ class Bootstrap;
 #define FB_FLAG_SYMMETRIC 1
 // Skip cross-rank synchronisation (profiling a single rank's data path only)
 #define FB_FLAG_NOSYNC 2
+// Channel id in bits 8..11: independent collectives issued on different
+// channels (and different streams) may execute concurrently.  Every rank must
+// use the same channel for the same logical collective.  Channels > 0 require
+// symmetric buffers (the staging area is not replicated per channel).
+#define FB_FLAG_CHANNEL(c) (((c) & 0xf) << 8)
+#define FB_FLAG_GET_CHANNEL(f) (((f) >> 8) & 0xf)
 
 struct CommConfig
 {
@@ -41,6 +47,7 @@ struct CommConfig
     bool useMulticast = true;
     int maxBlocks = 32;
     int threads = 512;
+    int channels = 4; // concurrent collective lanes (1..FB_MAX_CHANNELS)
     // algorithm thresholds (bytes); the autotuner overwrites these
     size_t llMaxBytes = 32 << 10;
     size_t oneShotMaxBytes = 256 << 10;
@@ -171,6 +178,13 @@ class Communicator
     // Last algorithm picked by allReduce (for reporting / tests)
     int lastAlgo() const { return lastAlgo_; }
 
+    // Measured selection table for allReduce: message sizes up to maxBytes[i]
+    // use algos[i] (entries sorted ascending; the last entry covers the rest).
+    // Written by the autotuner; empty => built-in thresholds.
+    void setAllReduceTable(const std::vector<uint64_t>& maxBytes,
+                           const std::vector<int>& algos);
+    int pickAllReduceAlgo(uint64_t bytes, bool nvlsOk) const;
+
     static const char* errorString(int code);
 
   private:
@@ -182,6 +196,7 @@ class Communicator
     int device_ = 0;
     std::string backing_;
     int lastAlgo_ = 0;
+    std::vector<std::pair<uint64_t, int>> allReduceTable_;
 
     // heap layout (offsets from heap base)
     uint64_t llOff_ = 0;

@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(FB_LL_THREADS, 1) llAllReduceKernel(
 {
     const FbCommDev& c = a.comm;
     const int n = (NR > 0) ? NR : c.nranks;
-    uint32_t* epochWord = c.sig[c.rank] + FB_SIG_LL_EPOCH_OFF + blockIdx.x;
+    uint32_t* epochWord =
+      c.sig[c.rank] + FB_SIG_LL_EPOCH_OFF + c.llEpochBase + blockIdx.x;
     uint32_t epoch = *epochWord + 1;
     if (epoch == 0) {
         epoch = 1; // 0 is the "empty slot" value

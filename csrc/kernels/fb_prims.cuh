@@ -111,13 +111,13 @@ struct BlockBarrier
     {
         // Plain read: only this CTA index on this rank ever writes the word,
         // and the previous writer was an earlier kernel on the same stream.
-        epoch = c.sig[c.rank][FB_SIG_EPOCH_OFF + blockIdx.x];
+        epoch = c.sig[c.rank][FB_SIG_EPOCH_OFF + c.blockBase + blockIdx.x];
     }
 
     __device__ __forceinline__ void store(const FbCommDev& c)
     {
         if (threadIdx.x == 0) {
-            c.sig[c.rank][FB_SIG_EPOCH_OFF + blockIdx.x] = epoch;
+            c.sig[c.rank][FB_SIG_EPOCH_OFF + c.blockBase + blockIdx.x] = epoch;
         }
     }
 
@@ -128,11 +128,11 @@ struct BlockBarrier
         bool ok = true;
         if (threadIdx.x < (unsigned)c.nranks) {
             int peer = threadIdx.x;
-            uint32_t* remote =
-              c.sig[peer] + (size_t)blockIdx.x * FB_MAX_RANKS + c.rank;
+            const size_t slot = (size_t)(c.blockBase + blockIdx.x);
+            uint32_t* remote = c.sig[peer] + slot * FB_MAX_RANKS + c.rank;
             stReleaseSys(remote, epoch);
             const uint32_t* mine =
-              c.sig[c.rank] + (size_t)blockIdx.x * FB_MAX_RANKS + peer;
+              c.sig[c.rank] + slot * FB_MAX_RANKS + peer;
             ok = waitFlagGe(c, mine, epoch, FB_ERR_BARRIER_TIMEOUT);
         }
         // __syncthreads_and also makes the acquire cumulative for the CTA

@@ -60,6 +60,7 @@ CommConfig CommConfig::fromEnv()
     c.useVmm = envSize("FAABRIC_USE_VMM", 1) != 0;
     c.useMulticast = envSize("FAABRIC_USE_NVLS", 1) != 0;
     c.maxBlocks = (int)envSize("FAABRIC_COMM_BLOCKS", c.maxBlocks);
+    c.channels = (int)envSize("FAABRIC_COMM_CHANNELS", c.channels);
     c.llMaxBytes = envSize("FAABRIC_LL_MAX_BYTES", c.llMaxBytes);
     c.oneShotMaxBytes = envSize("FAABRIC_ONESHOT_MAX_BYTES", c.oneShotMaxBytes);
     c.nvlsMinBytes = envSize("FAABRIC_NVLS_MIN_BYTES", c.nvlsMinBytes);
@@ -161,8 +162,10 @@ void Communicator::computeLayout()
     int n = dev_.nranks;
     cfg_.stageBytes = roundUp(std::max<size_t>(cfg_.stageBytes, 1 << 16), 4096);
     cfg_.slotBytes = roundUp(std::max<size_t>(cfg_.slotBytes, 4096), 4096);
+    cfg_.channels = std::clamp(cfg_.channels, 1, FB_MAX_CHANNELS);
     llOff_ = 0;
-    mboxOff_ = roundUp(llOff_ + FB_LL_AREA_BYTES(n), 4096);
+    mboxOff_ = roundUp(
+      llOff_ + (uint64_t)cfg_.channels * FB_LL_AREA_BYTES(n), 4096);
     stageSendOff_ = roundUp(
       mboxOff_ + (uint64_t)n * FB_P2P_BLOCKS * 2 * cfg_.slotBytes, 4096);
     stageRecvOff_ = stageSendOff_ + cfg_.stageBytes;
@@ -787,7 +790,7 @@ int Communicator::blocksFor(uint64_t vecs, int perThread) const
 {
     uint64_t perBlock = (uint64_t)cfg_.threads * perThread;
     uint64_t b = (vecs + perBlock - 1) / perBlock;
-    int maxB = std::min(cfg_.maxBlocks, FB_MAX_BLOCKS);
+    int maxB = std::min(cfg_.maxBlocks, FB_MAX_BLOCKS / cfg_.channels);
     if (b < 1) {
         b = 1;
     }
@@ -817,8 +820,53 @@ int Communicator::widthFor(const void* a, const void* b, uint64_t bytes) const
 
 FbCommDev Communicator::devFor(int flags) const
 {
-    (void)flags;
-    return dev_;
+    FbCommDev d = dev_;
+    int ch = FB_FLAG_GET_CHANNEL(flags);
+    if (ch >= cfg_.channels) {
+        ch = ch % cfg_.channels;
+    }
+    d.blockBase = ch * (FB_MAX_BLOCKS / cfg_.channels);
+    d.llEpochBase = ch * FB_LL_BLOCKS;
+    return d;
+}
+
+void Communicator::setAllReduceTable(const std::vector<uint64_t>& maxBytes,
+                                     const std::vector<int>& algos)
+{
+    allReduceTable_.clear();
+    for (size_t i = 0; i < maxBytes.size() && i < algos.size(); i++) {
+        allReduceTable_.emplace_back(maxBytes[i], algos[i]);
+    }
+    std::sort(allReduceTable_.begin(), allReduceTable_.end());
+}
+
+int Communicator::pickAllReduceAlgo(uint64_t bytes, bool nvlsOk) const
+{
+    if (!allReduceTable_.empty()) {
+        int algo = allReduceTable_.back().second;
+        for (const auto& [maxB, a] : allReduceTable_) {
+            if (bytes <= maxB) {
+                algo = a;
+                break;
+            }
+        }
+        if (algo == FB_ALGO_NVLS && !nvlsOk) {
+            algo = bytes <= cfg_.oneShotMaxBytes ? FB_ALGO_ONESHOT
+                                                 : FB_ALGO_TWOSHOT;
+        }
+        return algo;
+    }
+    if (bytes <= cfg_.llMaxBytes && bytes <= FB_LL_MAX_BYTES) {
+        return FB_ALGO_LL;
+    }
+    // in-switch reduction only pays off beyond a pair of GPUs
+    if (nvlsOk && dev_.nranks >= 4 && bytes >= cfg_.nvlsMinBytes) {
+        return FB_ALGO_NVLS;
+    }
+    if (bytes <= cfg_.oneShotMaxBytes) {
+        return FB_ALGO_ONESHOT;
+    }
+    return FB_ALGO_TWOSHOT;
 }
 
 uint32_t Communicator::checkError(cudaStream_t s)
@@ -891,16 +939,8 @@ int Communicator::reduceLike(int kind,
     // ---- algorithm choice ----
     if (kind == K_ALLREDUCE) {
         if (algo == FB_ALGO_AUTO) {
-            if (bytes <= cfg_.llMaxBytes && bytes <= FB_LL_MAX_BYTES) {
-                algo = FB_ALGO_LL;
-            } else if (hasMulticast() && nvVariant >= 0 &&
-                       bytes >= cfg_.nvlsMinBytes && (bytes % 16) == 0) {
-                algo = FB_ALGO_NVLS;
-            } else if (bytes <= cfg_.oneShotMaxBytes) {
-                algo = FB_ALGO_ONESHOT;
-            } else {
-                algo = FB_ALGO_TWOSHOT;
-            }
+            algo = pickAllReduceAlgo(
+              bytes, hasMulticast() && nvVariant >= 0 && (bytes % 16) == 0);
         }
         if (algo == FB_ALGO_LL &&
             (bytes > FB_LL_MAX_BYTES || (((uintptr_t)send | (uintptr_t)recv) & 15))) {
@@ -955,11 +995,12 @@ int Communicator::reduceLike(int kind,
     // ---- LL: no staging, no symmetric requirement ----
     if (algo == FB_ALGO_LL) {
         fb::LLArgs a;
-        a.comm = dev_;
+        a.comm = devFor(flags);
         a.sendLocal = (const uint8_t*)send;
         a.recvLocal = (uint8_t*)recv;
         a.bytes = bytes;
-        a.llOff = llOff_;
+        a.llOff = llOff_ + (uint64_t)(a.comm.llEpochBase / FB_LL_BLOCKS) *
+                             FB_LL_AREA_BYTES(n);
         stats_.launches++;
         stats_.bytes += bytes;
         return L->ll(a, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
@@ -967,6 +1008,7 @@ int Communicator::reduceLike(int kind,
 
     // ---- staged / symmetric chunk loop ----
     const bool stageSend = !symmetric;
+    const FbCommDev chanDev = devFor(flags);
     // which algorithms write through the symmetric recv offset
     const bool pushes = (algo == FB_ALGO_TWOSHOT) ||
                         (algo == FB_ALGO_NVLS && kind == K_ALLREDUCE);
@@ -982,6 +1024,9 @@ int Communicator::reduceLike(int kind,
     }
     if (kind == K_REDUCE_SCATTER && stageSend && bytes > cfg_.stageBytes) {
         return FB_E_TOO_LARGE;
+    }
+    if ((stageSend || stageRecv) && chanDev.blockBase != 0) {
+        return FB_E_INVALID; // staging buffers exist once, on channel 0 only
     }
     const uint64_t chunkMax =
       (stageSend || stageRecv) ? (uint64_t)cfg_.stageBytes : bytes;
@@ -1018,7 +1063,7 @@ int Communicator::reduceLike(int kind,
         if (algo == FB_ALGO_NVLS) {
             fb::NvlsArgs a;
             memset(&a, 0, sizeof(a));
-            a.comm = dev_;
+            a.comm = chanDev;
             a.sendOff = sendOff;
             a.recvOff = recvOff;
             a.recvLocal = recvLocal;
@@ -1049,7 +1094,7 @@ int Communicator::reduceLike(int kind,
         } else {
             fb::ReduceArgs a;
             memset(&a, 0, sizeof(a));
-            a.comm = dev_;
+            a.comm = chanDev;
             a.sendOff = sendOff;
             a.recvOff = recvOff;
             a.recvLocal = recvLocal;
@@ -1219,7 +1264,7 @@ int Communicator::moveLike(int mode,
          mode == fb::MOVE_BCAST)) {
         fb::NvlsArgs a;
         memset(&a, 0, sizeof(a));
-        a.comm = dev_;
+        a.comm = devFor(flags);
         a.noSync = noSync;
         a.outBase = 0;
         uint64_t nVec = chunkBytes / 16;
@@ -1251,7 +1296,7 @@ int Communicator::moveLike(int mode,
         chunkBytes >= cfg_.bcast2StepMinBytes && (chunkBytes % 16) == 0) {
         fb::MoveArgs a;
         memset(&a, 0, sizeof(a));
-        a.comm = dev_;
+        a.comm = devFor(flags);
         a.sendOff = offsetOf(recv);
         a.recvOff = offsetOf(recv);
         a.recvLocal = (uint8_t*)recv;
@@ -1285,7 +1330,10 @@ int Communicator::moveLike(int mode,
         const uint64_t len = std::min<uint64_t>(piece, chunkBytes - done);
         fb::MoveArgs a;
         memset(&a, 0, sizeof(a));
-        a.comm = dev_;
+        a.comm = devFor(flags);
+        if (!symmetric && a.comm.blockBase != 0) {
+            return FB_E_INVALID;
+        }
         a.mode = mode;
         a.root = root;
         a.noSync = noSync;

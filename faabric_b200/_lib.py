@@ -25,6 +25,8 @@ class FbConfig(C.Structure):
         ("useMulticast", C.c_int32),
         ("maxBlocks", C.c_int32),
         ("threads", C.c_int32),
+        ("channels", C.c_int32),
+        ("reserved", C.c_int32),
         ("llMaxBytes", C.c_uint64),
         ("oneShotMaxBytes", C.c_uint64),
         ("nvlsMinBytes", C.c_uint64),
@@ -83,6 +85,7 @@ def load():
         _sig(lib, f"fb_comm_{n}", i32, [vp])
     _sig(lib, "fb_comm_backing", C.c_char_p, [vp])
     _sig(lib, "fb_comm_configure", i32, [vp, i32, u64])
+    _sig(lib, "fb_comm_set_allreduce_table", i32, [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_int)])
     _sig(lib, "fb_comm_stats", None, [vp, C.POINTER(C.c_uint64), i32])
     _sig(lib, "fb_comm_alloc", C.c_int64, [vp, u64])
     _sig(lib, "fb_comm_free", None, [vp, u64])

@@ -32,6 +32,7 @@ class GradientSync:
         algo: str = "auto",
         use_graph: bool = True,
         in_place: bool = False,
+        channels: int = 4,
     ):
         self.comm = comm
         self.sizes = [int(s) for s in sizes]
@@ -58,14 +59,38 @@ class GradientSync:
         self.recv_views = [self.recv[o : o + s] for o, s in zip(self.offsets, self.sizes)]
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._stream = torch.cuda.Stream(device=comm.device)
+        # independent tensors are all-reduced concurrently on `channels` lanes
+        # (each lane = its own stream + its own slice of the barrier flags)
+        self.channels = max(1, int(channels))
+        self._lanes = [torch.cuda.Stream(device=comm.device) for _ in range(self.channels - 1)]
+        self._fork = torch.cuda.Event()
+        self._joins = [torch.cuda.Event() for _ in self._lanes]
         self._result = torch.zeros(2, dtype=torch.int64, device=f"cuda:{comm.device}")
         self._result_host = torch.zeros(2, dtype=torch.int64).pin_memory()
         self.launches_per_step = len(self.sizes)
 
     # ------------------------------------------------------------------ core
     def _issue(self, stream):
-        for s, r in zip(self.send_views, self.recv_views):
-            self.comm.all_reduce(s, r, op=self.op, algo=self.algo, stream=stream)
+        if self.channels == 1:
+            for s, r in zip(self.send_views, self.recv_views):
+                self.comm.all_reduce(s, r, op=self.op, algo=self.algo, stream=stream)
+            return
+        # fork: lane streams wait for everything already queued on `stream`
+        self._fork.record(stream)
+        for lane in self._lanes:
+            lane.wait_event(self._fork)
+        # biggest tensors first, round-robin over the lanes
+        order = sorted(range(len(self.sizes)), key=lambda i: -self.sizes[i])
+        for k, i in enumerate(order):
+            ch = k % self.channels
+            st = stream if ch == 0 else self._lanes[ch - 1]
+            self.comm.all_reduce(
+                self.send_views[i], self.recv_views[i], op=self.op, algo=self.algo, stream=st, channel=ch
+            )
+        # join
+        for lane, ev in zip(self._lanes, self._joins):
+            ev.record(lane)
+            stream.wait_event(ev)
 
     def _capture(self):
         # warm the launch path once outside capture (lazy module loading)

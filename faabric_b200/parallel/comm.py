@@ -178,6 +178,13 @@ class Communicator:
         base = self._lib.fb_comm_heap_ptr(self._h, 0, -1)
         return t.data_ptr() - base
 
+    def set_allreduce_table(self, table):
+        """table: [(max_bytes, algo_name), ...] measured by the autotuner."""
+        n = len(table)
+        mb = (C.c_uint64 * n)(*[int(t[0]) for t in table])
+        al = (C.c_int * n)(*[ALGOS[t[1]] for t in table])
+        self._check(self._lib.fb_comm_set_allreduce_table(self._h, n, mb, al), "set table")
+
     def configure(self, **kw):
         keys = {
             "llMaxBytes": 0,
@@ -209,11 +216,12 @@ class Communicator:
         self._lib.fb_comm_host_barrier(self._h)
 
     # ------------------------------------------------------------ collectives
-    def all_reduce(self, send, recv=None, op="sum", algo="auto", stream=None, flags=None):
+    def all_reduce(self, send, recv=None, op="sum", algo="auto", stream=None, flags=None, channel=0):
         recv = send if recv is None else recv
         # only the source needs to be symmetric; the native side stages the
         # destination when a push algorithm needs it
         f = self._sym(send) if flags is None else flags
+        f |= (channel & 0xF) << 8
         rc = self._lib.fb_allreduce(
             self._h,
             C.c_void_p(send.data_ptr()),

@@ -368,8 +368,8 @@ def test_send_recv_ring(nbytes):
 def test_send_recv_fifo_order():
     g = group(2)
     a, b = g.comms
-    msgs = [torch.full((1000 + i,), i, dtype=torch.int32, device="cuda:0") for i in range(6)]
-    outs = [torch.zeros_like(m) for m in msgs]
+    msgs = [torch.full((1000 + i,), i, dtype=torch.int32, device=f"cuda:{a.device}") for i in range(6)]
+    outs = [torch.zeros(1000 + i, dtype=torch.int32, device=f"cuda:{b.device}") for i in range(6)]
     for m in msgs:
         a.send(m, 1, stream=g.streams[0])
     for o in outs:
@@ -394,6 +394,35 @@ def test_put_signal_and_barrier():
     assert torch.equal(dst[1].cpu(), src.cpu())
     for c, d in zip(g.comms, dst):
         c.free(d)
+
+
+def test_channels_run_concurrently():
+    """Independent all-reduces on different channels/streams use disjoint flag
+    slots, so they may overlap and complete in any order."""
+    n = 4
+    g = group(n)
+    sizes = [100, 5000, 70000, 300000, 9, 2048, 40000, 1]
+    nch = 4
+    lanes = [[torch.cuda.Stream(device=c.device) for _ in range(nch)] for c in g.comms]
+    sends = [[c.empty(s, torch.int32) for s in sizes] for c in g.comms]
+    recvs = [[c.empty(s, torch.int32) for s in sizes] for c in g.comms]
+    for r in range(n):
+        for t in sends[r]:
+            t.fill_(r + 1)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for r, c in enumerate(g.comms):
+            for i in range(len(sizes)):
+                ch = i % nch
+                c.all_reduce(sends[r][i], recvs[r][i], stream=lanes[r][ch], channel=ch)
+    torch.cuda.synchronize()
+    no_errors(g)
+    for r in range(n):
+        for t in recvs[r]:
+            assert bool((t == n * (n + 1) // 2).all())
+    for r, c in enumerate(g.comms):
+        for t in sends[r] + recvs[r]:
+            c.free(t)
 
 
 def test_graph_capture_replay():
