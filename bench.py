@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--channels", type=int, default=4)
+    ap.add_argument("--blocks", type=int, default=64, help="max CTAs per collective kernel (sweep modes)")
     ap.add_argument("--tuning", default="", help="JSON tuning table (default: profiles/tuning_N<gpus>.json)")
     ap.add_argument("--payload", default="large", choices=["large", "small"])
     ap.add_argument("--out", default="")
@@ -189,7 +190,7 @@ def mode_allreduce(args, dist: Dist):
         e2e = None
         cfg_extra = {"library": "torch.distributed NCCL all_reduce (baseline, not the product)"}
     else:
-        comm, group = dist.make_comm(heapBytes=(512 << 20), stageBytes=(16 << 20))
+        comm, group = dist.make_comm(heapBytes=(512 << 20), stageBytes=(16 << 20), channels=args.channels)
         load_tuning(comm, args, dist)
         sync = GradientSync(comm, sizes, dtype=torch.int32, algo=args.algo, use_graph=not args.no_graph,
                             channels=args.channels)
@@ -311,7 +312,7 @@ def mode_sweep(args, dist: Dist):
 
     n = dist.world
     maxb = args.max_bytes
-    comm, group = dist.make_comm(heapBytes=2 * maxb + (64 << 20), stageBytes=(16 << 20), maxBlocks=64)
+    comm, group = dist.make_comm(heapBytes=2 * maxb + (64 << 20), stageBytes=(16 << 20), maxBlocks=args.blocks, channels=1)
     send = comm.empty(maxb // 4, torch.float32)
     recv = comm.empty(maxb // 4, torch.float32)
     send.fill_(1.0)
@@ -385,7 +386,7 @@ def mode_alltoall(args, dist: Dist):
 
     n = dist.world
     max_per_rank = min(args.max_bytes, 64 << 20)
-    comm, group = dist.make_comm(heapBytes=2 * max_per_rank * n + (64 << 20), stageBytes=(16 << 20), maxBlocks=64)
+    comm, group = dist.make_comm(heapBytes=2 * max_per_rank * n + (64 << 20), stageBytes=(16 << 20), maxBlocks=args.blocks, channels=1)
     send = comm.empty(max_per_rank * n // 4, torch.float32)
     recv = comm.empty(max_per_rank * n // 4, torch.float32)
     send.fill_(2.0)

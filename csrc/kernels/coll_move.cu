@@ -67,15 +67,17 @@ __device__ __forceinline__ void gridCopy(uint8_t* dst,
     using WT = typename Word<W>::type;
     const uint64_t n = bytes / W;
     uint64_t i = tid;
-    for (; i + 3 * nthreads < n; i += 4 * nthreads) {
-        WT v0 = Word<W>::ld(src + i * W);
-        WT v1 = Word<W>::ld(src + (i + nthreads) * W);
-        WT v2 = Word<W>::ld(src + (i + 2 * nthreads) * W);
-        WT v3 = Word<W>::ld(src + (i + 3 * nthreads) * W);
-        Word<W>::st(dst + i * W, v0);
-        Word<W>::st(dst + (i + nthreads) * W, v1);
-        Word<W>::st(dst + (i + 2 * nthreads) * W, v2);
-        Word<W>::st(dst + (i + 3 * nthreads) * W, v3);
+    constexpr int U = 8;
+    for (; i + (U - 1) * nthreads < n; i += U * nthreads) {
+        WT v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            v[u] = Word<W>::ld(src + (i + u * nthreads) * W);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            Word<W>::st(dst + (i + u * nthreads) * W, v[u]);
+        }
     }
     for (; i < n; i += nthreads) {
         Word<W>::st(dst + i * W, Word<W>::ld(src + i * W));
@@ -107,8 +109,33 @@ __global__ void __launch_bounds__(512, 1) moveKernel(const MoveArgs a)
               (a.mode == MOVE_ALLTOALL) ? (uint64_t)rank * a.srcStride : 0;
             const uint64_t words = a.chunkBytes / W;
             if constexpr (NR > 0) {
-                // one word from every peer in flight per thread
-                for (uint64_t i = tid; i < words; i += nthreads) {
+                // NR x U words in flight per thread (NVLink latency ~2-3 us:
+                // bandwidth needs ~16 outstanding 16-byte loads per thread)
+                constexpr int U = (NR <= 2) ? 8 : ((NR <= 4) ? 4 : 2);
+                uint64_t i = tid;
+                for (; i + (U - 1) * nthreads < words; i += U * nthreads) {
+                    WT v[U][NR];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+#pragma unroll
+                        for (int p = 0; p < NR; p++) {
+                            v[u][p] =
+                              Word<W>::ld(a.comm.heap[p] + a.sendOff + srcExtra +
+                                          (i + u * nthreads) * W);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+#pragma unroll
+                        for (int p = 0; p < NR; p++) {
+                            Word<W>::st(a.recvLocal +
+                                          (uint64_t)p * a.dstStride +
+                                          (i + u * nthreads) * W,
+                                        v[u][p]);
+                        }
+                    }
+                }
+                for (; i < words; i += nthreads) {
                     WT v[NR];
 #pragma unroll
                     for (int p = 0; p < NR; p++) {
