@@ -1,0 +1,104 @@
+// A received (or to-be-sent) transport message: 16-byte header + payload.
+// Header layout matches the reference (transport/Message.h:11-21): code u8,
+// size u64, sequence number i32, 3 bytes padding.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <span>
+#include <string>
+#include <vector>
+
+namespace faabric::transport {
+
+#define NO_HEADER 0
+#define HEADER_MSG_SIZE 16
+#define SHUTDOWN_HEADER 220
+static const std::vector<uint8_t> shutdownPayload = { 0, 0, 1, 1 };
+
+#define NO_SEQUENCE_NUM -1
+
+enum class MessageResponseCode
+{
+    SUCCESS,
+    TERM,
+    TIMEOUT,
+    ERROR
+};
+
+class Message final
+{
+  public:
+    Message() = default;
+
+    // Empty message signalling an outcome (e.g. TIMEOUT)
+    explicit Message(MessageResponseCode failCodeIn)
+      : failCode(failCodeIn)
+    {}
+
+    Message(uint8_t codeIn, int seqIn, std::vector<uint8_t>&& payloadIn)
+      : code(codeIn)
+      , sequenceNum(seqIn)
+      , payload(std::move(payloadIn))
+    {}
+
+    Message(uint8_t codeIn, int seqIn, const uint8_t* data, size_t size)
+      : code(codeIn)
+      , sequenceNum(seqIn)
+      , payload(data, data + size)
+    {}
+
+    Message(Message&& other) = default;
+
+    Message& operator=(Message&& other) = default;
+
+    Message(const Message&) = delete;
+
+    Message& operator=(const Message&) = delete;
+
+    MessageResponseCode getResponseCode() const { return failCode; }
+
+    std::vector<uint8_t> dataCopy() const { return payload; }
+
+    std::span<const uint8_t> udata() const
+    {
+        return std::span<const uint8_t>(payload.data(), payload.size());
+    }
+
+    std::span<const char> data() const
+    {
+        return std::span<const char>((const char*)payload.data(), payload.size());
+    }
+
+    std::vector<uint8_t>& buffer() { return payload; }
+
+    size_t size() const { return payload.size(); }
+
+    uint8_t getMessageCode() const { return code; }
+
+    int getSequenceNum() const { return sequenceNum; }
+
+    // Serialised header
+    static void writeHeader(uint8_t* out, uint8_t code, uint64_t size, int32_t seq)
+    {
+        memset(out, 0, HEADER_MSG_SIZE);
+        out[0] = code;
+        memcpy(out + 1, &size, sizeof(uint64_t));
+        memcpy(out + 1 + sizeof(uint64_t), &seq, sizeof(int32_t));
+    }
+
+    static void readHeader(const uint8_t* in, uint8_t& code, uint64_t& size, int32_t& seq)
+    {
+        code = in[0];
+        memcpy(&size, in + 1, sizeof(uint64_t));
+        memcpy(&seq, in + 1 + sizeof(uint64_t), sizeof(int32_t));
+    }
+
+  private:
+    uint8_t code = NO_HEADER;
+    int sequenceNum = NO_SEQUENCE_NUM;
+    std::vector<uint8_t> payload;
+    MessageResponseCode failCode = MessageResponseCode::SUCCESS;
+};
+
+}
