@@ -1,0 +1,104 @@
+#pragma once
+
+#include <faabric/batch-scheduler/SchedulingDecision.h>
+#include <faabric/planner/PlannerApi.h>
+#include <faabric/proto/faabric.pb.h>
+#include <faabric/snapshot/SnapshotRegistry.h>
+#include <faabric/transport/MessageEndpointClient.h>
+#include <faabric/util/PeriodicBackgroundThread.h>
+
+#include <future>
+#include <shared_mutex>
+
+namespace faabric::planner {
+
+// Re-registers this host with the planner every timeout/2
+class KeepAliveThread : public faabric::util::PeriodicBackgroundThread
+{
+  public:
+    void doWork() override;
+
+    void setRequest(std::shared_ptr<RegisterHostRequest> thisHostReqIn);
+
+    // Protects the request (it may be swapped while the thread runs)
+    std::shared_mutex keepAliveThreadMx;
+
+  private:
+    std::shared_ptr<RegisterHostRequest> thisHostReq = nullptr;
+};
+
+// Local cache of results the planner pushed to us / promises we wait on
+struct PlannerCache
+{
+    std::unordered_map<uint32_t, std::promise<std::shared_ptr<faabric::Message>>>
+      plannerResults;
+
+    // Snapshots already pushed to the planner, by key
+    std::set<std::string> pushedSnapshots;
+};
+
+class PlannerClient final : public faabric::transport::MessageEndpointClient
+{
+  public:
+    PlannerClient();
+
+    explicit PlannerClient(const std::string& plannerIp);
+
+    // ------
+    // Util
+    // ------
+    void ping();
+
+    void clearCache();
+
+    // ------
+    // Host membership calls
+    // ------
+    std::vector<Host> getAvailableHosts();
+
+    // Returns the keep-alive timeout (seconds)
+    int registerHost(std::shared_ptr<RegisterHostRequest> req);
+
+    void removeHost(std::shared_ptr<RemoveHostRequest> req);
+
+    // ------
+    // Scheduling calls
+    // ------
+    void setMessageResult(std::shared_ptr<faabric::Message> msg);
+
+    // Called by the FunctionCallServer when the planner notifies a result
+    void setMessageResultLocally(std::shared_ptr<faabric::Message> msg);
+
+    faabric::Message getMessageResult(int appId, int msgId, int timeoutMs);
+
+    faabric::Message getMessageResult(const faabric::Message& msg,
+                                      int timeoutMs);
+
+    std::shared_ptr<faabric::BatchExecuteRequestStatus> getBatchResults(
+      std::shared_ptr<faabric::BatchExecuteRequest> req);
+
+    faabric::batch_scheduler::SchedulingDecision callFunctions(
+      std::shared_ptr<faabric::BatchExecuteRequest> req);
+
+    faabric::batch_scheduler::SchedulingDecision getSchedulingDecision(
+      std::shared_ptr<faabric::BatchExecuteRequest> req);
+
+    int getNumMigrations();
+
+    void preloadSchedulingDecision(
+      std::shared_ptr<faabric::batch_scheduler::SchedulingDecision> preloadDec);
+
+  private:
+    std::mutex plannerCacheMx;
+    PlannerCache cache;
+
+    faabric::snapshot::SnapshotRegistry& snapshotRegistry;
+
+    faabric::Message doGetMessageResult(
+      std::shared_ptr<faabric::Message> msgPtr,
+      int timeoutMs);
+};
+
+PlannerClient& getPlannerClient();
+
+}

@@ -1,0 +1,583 @@
+#include <faabric/batch-scheduler/BatchScheduler.h>
+#include <faabric/executor/Executor.h>
+#include <faabric/executor/ExecutorContext.h>
+#include <faabric/executor/ExecutorFactory.h>
+#include <faabric/mpi/MpiWorldRegistry.h>
+#include <faabric/planner/PlannerClient.h>
+#include <faabric/scheduler/Scheduler.h>
+#include <faabric/snapshot/SnapshotClient.h>
+#include <faabric/transport/PointToPointBroker.h>
+#include <faabric/transport/common.h>
+#include <faabric/util/clock.h>
+#include <faabric/util/config.h>
+#include <faabric/util/environment.h>
+#include <faabric/util/func.h>
+#include <faabric/util/gids.h>
+#include <faabric/util/logging.h>
+#include <faabric/util/memory.h>
+#include <faabric/util/network.h>
+#include <faabric/util/timing.h>
+
+#include <cuda_runtime.h>
+
+namespace faabric::executor {
+
+// ---------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------
+static thread_local std::shared_ptr<ExecutorContext> tlsContext = nullptr;
+
+ExecutorContext::ExecutorContext(Executor* executorIn,
+                                 std::shared_ptr<faabric::BatchExecuteRequest> reqIn,
+                                 int msgIdxIn)
+  : executor(executorIn)
+  , req(std::move(reqIn))
+  , msgIdx(msgIdxIn)
+{}
+
+bool ExecutorContext::isSet()
+{
+    return tlsContext != nullptr;
+}
+
+void ExecutorContext::set(Executor* executorIn,
+                          std::shared_ptr<faabric::BatchExecuteRequest> reqIn,
+                          int msgIdxIn)
+{
+    tlsContext = std::make_shared<ExecutorContext>(executorIn, std::move(reqIn), msgIdxIn);
+}
+
+void ExecutorContext::unset()
+{
+    tlsContext = nullptr;
+}
+
+std::shared_ptr<ExecutorContext> ExecutorContext::get()
+{
+    if (tlsContext == nullptr) {
+        SPDLOG_ERROR("No executor context set");
+        throw ExecutorContextException("No executor context set");
+    }
+    return tlsContext;
+}
+
+// ---------------------------------------------------------------------------
+// Factory
+// ---------------------------------------------------------------------------
+static std::shared_ptr<ExecutorFactory> activeFactory;
+static std::mutex factoryMx;
+
+void ExecutorFactory::flushHost()
+{
+    SPDLOG_WARN("Using default flush method");
+}
+
+void setExecutorFactory(std::shared_ptr<ExecutorFactory> fac)
+{
+    std::lock_guard<std::mutex> lk(factoryMx);
+    activeFactory = std::move(fac);
+}
+
+std::shared_ptr<ExecutorFactory> getExecutorFactory()
+{
+    std::lock_guard<std::mutex> lk(factoryMx);
+    if (activeFactory == nullptr) {
+        throw std::runtime_error("No executor factory set");
+    }
+    return activeFactory;
+}
+
+// ---------------------------------------------------------------------------
+// Executor
+// ---------------------------------------------------------------------------
+static std::atomic<int> executorCounter{ 0 };
+
+Executor::Executor(faabric::Message& msg)
+  : boundMessage(msg)
+  , reg(faabric::snapshot::getSnapshotRegistry())
+  , tracker(faabric::util::getDirtyTracker())
+  , threadPoolSize(faabric::util::getUsableCores())
+  , threadPoolThreads(threadPoolSize)
+  , threadTaskQueues(threadPoolSize)
+{
+    faabric::util::SystemConfig& conf = faabric::util::getSystemConfig();
+    // Unique id: host, function, counter
+    id = conf.endpointHost + "_" + std::to_string(faabric::util::generateGid());
+    lastExec = faabric::util::getGlobalClock().now();
+    for (uint32_t i = 0; i < threadPoolSize; i++) {
+        availablePoolThreads.insert((int)i);
+    }
+    // GPU binding: "gpuN" host aliases pin to that GPU, otherwise round-robin
+    int nGpus = faabric::util::getUsableGpus();
+    if (nGpus > 0) {
+        int alias = faabric::util::gpuIndexFromHostName(msg.executedhost());
+        gpuIdx = alias >= 0 ? alias % nGpus : faabric::util::gpuForRank(executorCounter.fetch_add(1));
+        int prev = -1;
+        cudaGetDevice(&prev);
+        if (cudaSetDevice(gpuIdx) == cudaSuccess) {
+            cudaStream_t s = nullptr;
+            if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) {
+                computeStream = s;
+            }
+        }
+        cudaGetLastError();
+        if (prev >= 0) {
+            cudaSetDevice(prev);
+        }
+    }
+    setUpThreadPool();
+}
+
+Executor::~Executor()
+{
+    if (!_isShutdown) {
+        SPDLOG_DEBUG("Destructing executor {} without shutting down first", id);
+        shutdown();
+    }
+    if (computeStream != nullptr) {
+        cudaStreamDestroy((cudaStream_t)computeStream);
+        cudaGetLastError();
+    }
+}
+
+void Executor::setUpThreadPool() {}
+
+void Executor::shutdown()
+{
+    if (_isShutdown.exchange(true)) {
+        return;
+    }
+    // Poison every started pool thread, then join
+    std::vector<std::shared_ptr<std::jthread>> toJoin;
+    {
+        std::lock_guard<std::mutex> lk(threadsMutex);
+        for (uint32_t i = 0; i < threadPoolThreads.size(); i++) {
+            if (threadPoolThreads[i] != nullptr) {
+                threadTaskQueues[i].enqueue(ExecutorTask(POOL_SHUTDOWN, nullptr));
+                toJoin.push_back(threadPoolThreads[i]);
+            }
+        }
+    }
+    for (auto& t : toJoin) {
+        if (t->joinable() && t->get_id() != std::this_thread::get_id()) {
+            t->join();
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(threadsMutex);
+        for (auto& t : threadPoolThreads) {
+            t = nullptr;
+        }
+    }
+}
+
+void Executor::joinThreadPool()
+{
+    shutdown();
+}
+
+bool Executor::tryClaim()
+{
+    bool expected = false;
+    return claimed.compare_exchange_strong(expected, true);
+}
+
+void Executor::claim()
+{
+    if (!tryClaim()) {
+        throw std::runtime_error("Executor already claimed");
+    }
+}
+
+void Executor::releaseClaim()
+{
+    claimed.store(false);
+}
+
+bool Executor::isExecuting()
+{
+    return claimed.load();
+}
+
+long Executor::getMillisSinceLastExec()
+{
+    auto now = faabric::util::getGlobalClock().now();
+    return faabric::util::getGlobalClock().timeDiff(now, lastExec);
+}
+
+// ---- hooks (defaults) ----
+void Executor::reset(faabric::Message& msg) {}
+
+int32_t Executor::executeTask(int threadPoolIdx,
+                              int msgIdx,
+                              std::shared_ptr<faabric::BatchExecuteRequest> req)
+{
+    return 0;
+}
+
+std::span<uint8_t> Executor::getMemoryView()
+{
+    SPDLOG_WARN("Executor for {} has not implemented memory view method", faabric::util::funcToString(boundMessage, false));
+    return {};
+}
+
+void Executor::setMemorySize(size_t newSize)
+{
+    SPDLOG_WARN("Executor has not implemented set memory size method");
+}
+
+size_t Executor::getMaxMemorySize()
+{
+    SPDLOG_WARN("Executor has not implemented max memory size method");
+    return 0;
+}
+
+void Executor::restore(const std::string& snapshotKey)
+{
+    std::span<uint8_t> memView = getMemoryView();
+    if (memView.empty()) {
+        SPDLOG_WARN("Not restoring {}: empty memory view", snapshotKey);
+        return;
+    }
+    auto snap = reg.getSnapshot(snapshotKey);
+    // Grow executor memory if the image is bigger, then CoW-map it in
+    if (snap->getSize() > memView.size()) {
+        setMemorySize(snap->getSize());
+        memView = getMemoryView();
+    }
+    snap->mapToMemory({ memView.data(), snap->getSize() });
+}
+
+// ---- chained messages ----
+void Executor::addChainedMessage(const faabric::Message& msg)
+{
+    std::lock_guard<std::mutex> lk(chainedMx);
+    auto ber = std::make_shared<faabric::BatchExecuteRequest>();
+    *ber->add_messages() = msg;
+    chainedMessages[msg.id()] = ber;
+}
+
+const faabric::Message& Executor::getChainedMessage(int messageId)
+{
+    std::lock_guard<std::mutex> lk(chainedMx);
+    auto it = chainedMessages.find(messageId);
+    if (it == chainedMessages.end()) {
+        SPDLOG_ERROR("Message {} does not have chained message {}", boundMessage.id(), messageId);
+        throw ChainedCallException("Message does not have chained message " + std::to_string(messageId));
+    }
+    return it->second->messages(0);
+}
+
+std::set<unsigned int> Executor::getChainedMessageIds()
+{
+    std::lock_guard<std::mutex> lk(chainedMx);
+    std::set<unsigned int> ids;
+    for (const auto& [mid, ber] : chainedMessages) {
+        ids.insert((unsigned int)mid);
+    }
+    return ids;
+}
+
+// ---- snapshots ----
+std::shared_ptr<faabric::util::SnapshotData> Executor::getMainThreadSnapshot(
+  faabric::Message& msg,
+  bool createIfNotExists)
+{
+    std::string key = faabric::util::getMainThreadSnapshotKey(msg);
+    bool exists = false;
+    {
+        std::shared_lock<std::shared_mutex> lock(threadExecutionMutex);
+        exists = reg.snapshotExists(key);
+    }
+    if (!exists && createIfNotExists) {
+        std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
+        if (!reg.snapshotExists(key)) {
+            SPDLOG_DEBUG("Creating main thread snapshot: {} for {}", key, faabric::util::funcToString(msg, false));
+            std::span<uint8_t> mem = getMemoryView();
+            auto snap = std::make_shared<faabric::util::SnapshotData>(
+              std::span<const uint8_t>(mem.data(), mem.size()), getMaxMemorySize());
+            reg.registerSnapshot(key, snap);
+        }
+    } else if (!exists) {
+        SPDLOG_ERROR("No main thread snapshot {}", key);
+        throw std::runtime_error("No main thread snapshot");
+    }
+    return reg.getSnapshot(key);
+}
+
+void Executor::deleteMainThreadSnapshot(const faabric::Message& msg)
+{
+    std::string key = faabric::util::getMainThreadSnapshotKey(msg);
+    std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
+    if (reg.snapshotExists(key)) {
+        reg.deleteSnapshot(key);
+    }
+}
+
+std::vector<faabric::util::SnapshotDiff> Executor::mergeDirtyRegions(
+  const faabric::Message& msg,
+  const std::vector<char>& extraDirtyPages)
+{
+    std::string key = faabric::util::getMainThreadSnapshotKey(msg);
+    auto snap = reg.getSnapshot(key);
+    std::span<uint8_t> memView = getMemoryView();
+    tracker->stopTracking(memView);
+
+    // Union of: pages dirtied by each thread, process-wide pages, caller extras
+    faabric::util::mergeManyDirtyPages(dirtyRegions, threadLocalDirtyRegions);
+    std::vector<char> global = tracker->getDirtyPages(memView);
+    faabric::util::mergeDirtyPages(dirtyRegions, global);
+    if (!extraDirtyPages.empty()) {
+        faabric::util::mergeDirtyPages(dirtyRegions, extraDirtyPages);
+    }
+    // Whatever the app did not declare a merge op for is merged bytewise/xor
+    snap->fillGapsWithBytewiseRegions();
+    std::vector<faabric::util::SnapshotDiff> diffs = snap->diffWithDirtyRegions(memView, dirtyRegions);
+    dirtyRegions.clear();
+    threadLocalDirtyRegions.clear();
+    return diffs;
+}
+
+// ---------------------------------------------------------------------------
+// Running tasks
+// ---------------------------------------------------------------------------
+void Executor::executeTasks(std::vector<int> msgIdxs,
+                            std::shared_ptr<faabric::BatchExecuteRequest> req)
+{
+    const int nMessages = (int)msgIdxs.size();
+    lastExec = faabric::util::getGlobalClock().now();
+    faabric::Message& first = *req->mutable_messages(msgIdxs.at(0));
+    const bool isThreads = req->type() == faabric::BatchExecuteRequest::THREADS;
+    const bool isSingleHost = req->singlehost();
+    const std::string funcStr = faabric::util::funcToString(first, false);
+    SPDLOG_TRACE("{} executing {}/{} tasks of {} (single-host={})", id, nMessages, req->messages_size(), funcStr, isSingleHost);
+
+    if (isThreads && !isSingleHost) {
+        // Remote threads start from the main thread's snapshot and track what
+        // they change so it can be diffed and sent back
+        std::string key = faabric::util::getMainThreadSnapshotKey(first);
+        SPDLOG_DEBUG("Restoring {} from snapshot {} before executing {} threads", funcStr, key, nMessages);
+        std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
+        bool isMain = first.mainhost() == faabric::transport::getThisHostAddress() || first.mainhost().empty();
+        if (!isMain) {
+            restore(key);
+        }
+        std::span<uint8_t> memView = getMemoryView();
+        tracker->clearAll();
+        tracker->startTracking(memView);
+        threadLocalDirtyRegions.clear();
+        dirtyRegions.clear();
+    } else if (!isThreads && !first.snapshotkey().empty()) {
+        // A function resuming from a snapshot (migration / thaw)
+        restore(first.snapshotkey());
+    }
+
+    batchCounter.fetch_add(nMessages, std::memory_order_release);
+    if (isThreads) {
+        threadBatchCounter.fetch_add(nMessages, std::memory_order_release);
+    }
+
+    for (int msgIdx : msgIdxs) {
+        const faabric::Message& msg = req->messages(msgIdx);
+        int poolIdx;
+        if (isThreads) {
+            // Threads with the same app idx always share a pool thread
+            poolIdx = msg.appidx() % (int)threadPoolSize;
+        } else {
+            std::lock_guard<std::mutex> lk(threadsMutex);
+            if (availablePoolThreads.empty()) {
+                SPDLOG_ERROR("No available thread pool threads (size: {})", threadPoolSize);
+                throw std::runtime_error("No available thread pool threads!");
+            }
+            poolIdx = *availablePoolThreads.begin();
+            availablePoolThreads.erase(availablePoolThreads.begin());
+        }
+        threadTaskQueues[poolIdx].enqueue(ExecutorTask(msgIdx, req));
+        std::lock_guard<std::mutex> lk(threadsMutex);
+        if (threadPoolThreads[poolIdx] == nullptr) {
+            threadPoolThreads[poolIdx] = std::make_shared<std::jthread>(
+              [this, poolIdx](std::stop_token st) { threadPoolThread(st, poolIdx); });
+        }
+    }
+}
+
+std::vector<std::pair<uint32_t, int32_t>> Executor::executeThreads(
+  std::shared_ptr<faabric::BatchExecuteRequest> req,
+  const std::vector<faabric::util::SnapshotMergeRegion>& mergeRegions)
+{
+    SPDLOG_DEBUG("Executor {} executing {} threads", id, req->messages_size());
+    faabric::Message& msg = *req->mutable_messages(0);
+    std::string key = faabric::util::getMainThreadSnapshotKey(msg);
+    bool existed = reg.snapshotExists(key);
+    auto snap = getMainThreadSnapshot(msg, true);
+    std::span<uint8_t> memView = getMemoryView();
+
+    if (existed) {
+        // Bring the snapshot up to date with what the main thread did since
+        tracker->stopTracking(memView);
+        tracker->stopThreadLocalTracking(memView);
+        std::vector<char> dirty = tracker->getBothDirtyPages(memView);
+        snap->clearMergeRegions();
+        snap->fillGapsWithBytewiseRegions();
+        auto updates = snap->diffWithDirtyRegions(memView, dirty);
+        if (!updates.empty()) {
+            snap->applyDiffs(updates);
+        }
+        snap->clearMergeRegions();
+    }
+    for (const auto& r : mergeRegions) {
+        snap->addMergeRegion(r.offset, r.length, r.dataType, r.operation);
+    }
+
+    req->set_type(faabric::BatchExecuteRequest::THREADS);
+    auto decision = faabric::planner::getPlannerClient().callFunctions(req);
+    if ((int)decision.appId == NOT_ENOUGH_SLOTS) {
+        throw std::runtime_error("Not enough slots to execute threads");
+    }
+    auto results = faabric::scheduler::getScheduler().awaitThreadResults(req);
+
+    // Fold the threads' diffs into the snapshot and refresh our memory from it
+    int nWritten = snap->writeQueuedDiffs();
+    SPDLOG_DEBUG("Merged {} thread diffs into {}", nWritten, key);
+    if (nWritten > 0 || !decision.isSingleHost()) {
+        std::span<uint8_t> view = getMemoryView();
+        snap->mapToMemory({ view.data(), std::min(view.size(), snap->getSize()) });
+    }
+    tracker->startTracking(getMemoryView());
+    tracker->startThreadLocalTracking(getMemoryView());
+    return results;
+}
+
+void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
+{
+    SPDLOG_DEBUG("Thread pool thread {}:{} starting up", id, threadPoolIdx);
+    auto& sch = faabric::scheduler::getScheduler();
+    faabric::transport::PointToPointBroker& broker = faabric::transport::getPointToPointBroker();
+    const auto& conf = faabric::util::getSystemConfig();
+    faabric::util::bindThreadToGpu(gpuIdx);
+
+    while (!st.stop_requested()) {
+        ExecutorTask task;
+        try {
+            task = threadTaskQueues[threadPoolIdx].dequeue(conf.boundTimeout);
+        } catch (const faabric::util::QueueTimeoutException&) {
+            // Nothing to do for a while: keep waiting, the reaper decides
+            // when the whole executor goes away
+            continue;
+        }
+        if (task.messageIndex == POOL_SHUTDOWN) {
+            SPDLOG_DEBUG("Killing thread pool thread {}:{}", id, threadPoolIdx);
+            break;
+        }
+        auto req = task.req;
+        faabric::Message& msg = *req->mutable_messages(task.messageIndex);
+        const bool isThreads = req->type() == faabric::BatchExecuteRequest::THREADS;
+        const bool isMigration = req->type() == faabric::BatchExecuteRequest::MIGRATION;
+        const bool doDirtyTracking = isThreads && !req->singlehost();
+        if (doDirtyTracking) {
+            tracker->startThreadLocalTracking(getMemoryView());
+        }
+
+        ExecutorContext::set(this, req, task.messageIndex);
+        int32_t returnValue = 0;
+        bool migrated = false;
+        bool frozen = false;
+        try {
+            if (isMigration) {
+                // Everyone in the new group lines up before the app carries on
+                broker.postMigrationHook(msg.groupid(), msg.groupidx());
+            }
+            returnValue = executeTask(threadPoolIdx, task.messageIndex, req);
+        } catch (const faabric::util::FunctionMigratedException& ex) {
+            SPDLOG_DEBUG("Task {} migrated, shutting down executor {}", msg.id(), id);
+            returnValue = MIGRATED_FUNCTION_RETURN_VALUE;
+            migrated = true;
+        } catch (const faabric::util::FunctionFrozenException& ex) {
+            SPDLOG_DEBUG("Task {} frozen, shutting down executor {}", msg.id(), id);
+            returnValue = FROZEN_FUNCTION_RETURN_VALUE;
+            frozen = true;
+        } catch (const std::exception& ex) {
+            returnValue = 1;
+            std::string err = "Task " + std::to_string(msg.id()) + " threw exception. What: " + ex.what();
+            SPDLOG_ERROR("{}", err);
+            msg.set_outputdata(err);
+        }
+        if ((migrated || frozen || returnValue == 1) && msg.ismpi()) {
+            // The rank is gone from this host: drop our view of its world
+            auto& worlds = faabric::mpi::getMpiWorldRegistry();
+            if (worlds.worldExists(msg.mpiworldid())) {
+                bool mustClear = worlds.getWorld(msg.mpiworldid()).destroy();
+                if (mustClear) {
+                    worlds.clearWorld(msg.mpiworldid());
+                }
+            }
+        }
+        ExecutorContext::unset();
+        msg.set_returnvalue(returnValue);
+
+        if (doDirtyTracking) {
+            tracker->stopThreadLocalTracking(getMemoryView());
+            std::vector<char> mine = tracker->getThreadLocalDirtyPages(getMemoryView());
+            std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
+            threadLocalDirtyRegions.push_back(std::move(mine));
+        }
+
+        // Counters decide who tidies up
+        int oldThreadCount = isThreads ? threadBatchCounter.fetch_sub(1, std::memory_order_acq_rel) : 0;
+        bool isLastThreadInBatch = isThreads && oldThreadCount == 1;
+        int oldBatchCount = batchCounter.fetch_sub(1, std::memory_order_acq_rel);
+        bool isLastInBatch = oldBatchCount == 1;
+
+        // The last thread diffs this host's memory against the snapshot
+        std::vector<faabric::util::SnapshotDiff> diffs;
+        if (isLastThreadInBatch && doDirtyTracking) {
+            try {
+                std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
+                diffs = mergeDirtyRegions(msg);
+            } catch (const std::exception& ex) {
+                SPDLOG_ERROR("Failed merging dirty regions for {}: {}", msg.id(), ex.what());
+            }
+        }
+
+        // Release resources BEFORE publishing the result: once the result is
+        // out the caller may immediately schedule onto this executor again
+        if (isLastInBatch) {
+            if (!isThreads) {
+                try {
+                    reset(msg);
+                } catch (const std::exception& ex) {
+                    SPDLOG_ERROR("Error resetting executor {}: {}", id, ex.what());
+                }
+            }
+            lastExec = faabric::util::getGlobalClock().now();
+            releaseClaim();
+        }
+        if (!isThreads) {
+            std::lock_guard<std::mutex> lk(threadsMutex);
+            availablePoolThreads.insert(threadPoolIdx);
+        }
+
+        msg.set_finishtimestamp(faabric::util::getGlobalClock().epochMillis());
+        if (isThreads) {
+            bool mainIsHere = msg.mainhost().empty() || msg.mainhost() == faabric::transport::getThisHostAddress();
+            if (!diffs.empty() || isLastThreadInBatch) {
+                std::string key = faabric::util::getMainThreadSnapshotKey(msg);
+                if (mainIsHere) {
+                    if (!diffs.empty()) {
+                        reg.getSnapshot(key)->queueDiffs(diffs);
+                    }
+                } else if (!diffs.empty()) {
+                    faabric::snapshot::getSnapshotClient(msg.mainhost())
+                      ->pushThreadResult(msg.appid(), msg.id(), returnValue, key, diffs);
+                }
+            }
+        }
+        auto result = std::make_shared<faabric::Message>(msg);
+        faabric::planner::getPlannerClient().setMessageResult(result);
+    }
+    // Thread-local caches die with the thread
+    sch.resetThreadLocalCache();
+    broker.resetThreadLocalCache();
+}
+
+} // namespace faabric::executor

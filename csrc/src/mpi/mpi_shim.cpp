@@ -1,0 +1,678 @@
+// The MPI_* C functions, mapped onto MpiWorld through the per-thread
+// MpiContext and the ExecutorContext of the running function.  In the
+// reference this shim lives in the test tree (tests/dist/mpi/mpi_native.cpp:
+// 59-776) and in Faasm's WASM host interface; here it ships with the library.
+// Beyond the reference's implemented set it adds Reduce_scatter (equal
+// counts), Allgatherv / Gatherv / Alltoallv (equal-count fast path + generic
+// point-to-point fallback), Waitall / Waitany, Initialized / Finalized,
+// Init_thread / Query_thread and Get_version.
+#include <faabric/executor/ExecutorContext.h>
+#include <faabric/mpi/MpiContext.h>
+#include <faabric/mpi/MpiWorldRegistry.h>
+#include <faabric/mpi/mpi.h>
+#include <faabric/util/config.h>
+#include <faabric/util/logging.h>
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <unistd.h>
+#include <vector>
+
+using namespace faabric::mpi;
+
+namespace {
+thread_local MpiContext executingContext;
+thread_local bool mpiInitialised = false;
+thread_local bool mpiFinalised = false;
+
+MpiWorld& getExecutingWorld()
+{
+    return getMpiWorldRegistry().getWorld(executingContext.getWorldId());
+}
+
+faabric::Message* getExecutingCall()
+{
+    return &faabric::executor::ExecutorContext::get()->getMsg();
+}
+
+int notImplemented(const std::string& funcName)
+{
+    SPDLOG_TRACE("MPI - {}", funcName);
+    throw std::runtime_error(funcName + " not implemented.");
+}
+
+int terminateMpi()
+{
+    // Destroy the MPI world
+    bool mustClear = getExecutingWorld().destroy();
+    if (mustClear) {
+        getMpiWorldRegistry().clearWorld(executingContext.getWorldId());
+    }
+    mpiFinalised = true;
+    return MPI_SUCCESS;
+}
+
+// In-place collectives pass MPI_IN_PLACE as the send buffer
+const void* resolveInPlace(const void* sendbuf, void* recvbuf)
+{
+    return sendbuf == MPI_IN_PLACE ? recvbuf : sendbuf;
+}
+
+std::map<int, faabric_request_t*>& requestTable()
+{
+    static thread_local std::map<int, faabric_request_t*> t;
+    return t;
+}
+}
+
+extern "C"
+{
+
+int MPI_Init(int* argc, char*** argv)
+{
+    faabric::Message* call = getExecutingCall();
+    if (call->mpirank() <= 0) {
+        // A world of the configured size is created by rank 0
+        SPDLOG_TRACE("MPI - MPI_Init (create)");
+        if (call->mpiworldsize() <= 0) {
+            call->set_mpiworldsize(faabric::util::getSystemConfig().defaultMpiWorldSize);
+        }
+        call->set_ismpi(true);
+        executingContext.createWorld(*call);
+    } else {
+        SPDLOG_TRACE("MPI - MPI_Init (join)");
+        executingContext.joinWorld(*call);
+    }
+    mpiInitialised = true;
+    mpiFinalised = false;
+    int thisRank = executingContext.getRank();
+    // Everyone lines up once the world is wired
+    getExecutingWorld().barrier(thisRank);
+    return MPI_SUCCESS;
+}
+
+int MPI_Init_thread(int* argc, char*** argv, int required, int* provided)
+{
+    if (provided != nullptr) {
+        // Ranks are threads but each rank's MPI calls come from one thread
+        *provided = MPI_THREAD_SERIALIZED;
+    }
+    return MPI_Init(argc, argv);
+}
+
+int MPI_Query_thread(int* provided)
+{
+    *provided = MPI_THREAD_SERIALIZED;
+    return MPI_SUCCESS;
+}
+
+int MPI_Initialized(int* flag)
+{
+    *flag = mpiInitialised ? 1 : 0;
+    return MPI_SUCCESS;
+}
+
+int MPI_Finalized(int* flag)
+{
+    *flag = mpiFinalised ? 1 : 0;
+    return MPI_SUCCESS;
+}
+
+int MPI_Get_version(int* version, int* subversion)
+{
+    *version = 3;
+    *subversion = 1;
+    return MPI_SUCCESS;
+}
+
+int MPI_Comm_rank(MPI_Comm comm, int* rank)
+{
+    SPDLOG_TRACE("MPI - MPI_Comm_rank");
+    *rank = executingContext.getRank();
+    return MPI_SUCCESS;
+}
+
+int MPI_Comm_size(MPI_Comm comm, int* size)
+{
+    SPDLOG_TRACE("MPI - MPI_Comm_size");
+    *size = getExecutingWorld().getSize();
+    return MPI_SUCCESS;
+}
+
+int MPI_Finalize()
+{
+    SPDLOG_TRACE("MPI - MPI_Finalize");
+    return terminateMpi();
+}
+
+int MPI_Abort(MPI_Comm comm, int errorcode)
+{
+    SPDLOG_TRACE("MPI - MPI_Abort");
+    return terminateMpi();
+}
+
+int MPI_Send(const void* buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Send {} -> {}", executingContext.getRank(), dest);
+    getExecutingWorld().send(executingContext.getRank(), dest, (const uint8_t*)buf, datatype, count);
+    return MPI_SUCCESS;
+}
+
+int MPI_Rsend(const void* buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm)
+{
+    // A ready-send is a send whose receive is already posted: same thing here
+    return MPI_Send(buf, count, datatype, dest, tag, comm);
+}
+
+int MPI_Recv(void* buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Status* status)
+{
+    SPDLOG_TRACE("MPI - MPI_Recv {} <- {}", executingContext.getRank(), source);
+    getExecutingWorld().recv(source, executingContext.getRank(), (uint8_t*)buf, datatype, count, status);
+    return MPI_SUCCESS;
+}
+
+int MPI_Sendrecv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, int dest, int sendtag,
+                 void* recvbuf, int recvcount, MPI_Datatype recvtype, int source, int recvtag,
+                 MPI_Comm comm, MPI_Status* status)
+{
+    SPDLOG_TRACE("MPI - MPI_Sendrecv");
+    getExecutingWorld().sendRecv((uint8_t*)sendbuf, sendcount, sendtype, dest,
+                                 (uint8_t*)recvbuf, recvcount, recvtype, source,
+                                 executingContext.getRank(), status);
+    return MPI_SUCCESS;
+}
+
+int MPI_Isend(const void* buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPI_Request* request)
+{
+    SPDLOG_TRACE("MPI - MPI_Isend {} -> {}", executingContext.getRank(), dest);
+    int id = getExecutingWorld().isend(executingContext.getRank(), dest, (const uint8_t*)buf, datatype, count);
+    auto* r = new faabric_request_t{ id };
+    requestTable()[id] = r;
+    *request = r;
+    return MPI_SUCCESS;
+}
+
+int MPI_Irecv(void* buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Request* request)
+{
+    SPDLOG_TRACE("MPI - MPI_Irecv {} <- {}", executingContext.getRank(), source);
+    int id = getExecutingWorld().irecv(source, executingContext.getRank(), (uint8_t*)buf, datatype, count);
+    auto* r = new faabric_request_t{ id };
+    requestTable()[id] = r;
+    *request = r;
+    return MPI_SUCCESS;
+}
+
+int MPI_Wait(MPI_Request* request, MPI_Status* status)
+{
+    if (request == nullptr || *request == nullptr) {
+        return MPI_SUCCESS;
+    }
+    int id = (*request)->id;
+    SPDLOG_TRACE("MPI - MPI_Wait {}", id);
+    getExecutingWorld().awaitAsyncRequest(id);
+    requestTable().erase(id);
+    delete *request;
+    *request = nullptr;
+    return MPI_SUCCESS;
+}
+
+int MPI_Waitall(int count, MPI_Request array_of_requests[], MPI_Status* array_of_statuses)
+{
+    for (int i = 0; i < count; i++) {
+        MPI_Wait(&array_of_requests[i], MPI_STATUS_IGNORE);
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Waitany(int count, MPI_Request array_of_requests[], int* index, MPI_Status* status)
+{
+    // Completion is in posting order per pair, so the first live request is
+    // as good a choice as any
+    for (int i = 0; i < count; i++) {
+        if (array_of_requests[i] != nullptr) {
+            MPI_Wait(&array_of_requests[i], status);
+            *index = i;
+            return MPI_SUCCESS;
+        }
+    }
+    *index = MPI_UNDEFINED;
+    return MPI_SUCCESS;
+}
+
+int MPI_Request_free(MPI_Request* request)
+{
+    if (request != nullptr && *request != nullptr) {
+        requestTable().erase((*request)->id);
+        delete *request;
+        *request = nullptr;
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Get_count(const MPI_Status* status, MPI_Datatype datatype, int* count)
+{
+    SPDLOG_TRACE("MPI - MPI_Get_count");
+    if (status->bytesSize % datatype->size != 0) {
+        SPDLOG_ERROR("Incomplete message (bytes {}, datatype size {})", status->bytesSize, datatype->size);
+        return 1;
+    }
+    *count = status->bytesSize / datatype->size;
+    return MPI_SUCCESS;
+}
+
+int MPI_Probe(int source, int tag, MPI_Comm comm, MPI_Status* status)
+{
+    throw std::runtime_error("MPI_Probe not implemented!");
+}
+
+int MPI_Barrier(MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Barrier");
+    getExecutingWorld().barrier(executingContext.getRank());
+    return MPI_SUCCESS;
+}
+
+int MPI_Bcast(void* buffer, int count, MPI_Datatype datatype, int root, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Bcast {} -> all", root);
+    getExecutingWorld().broadcast(root, executingContext.getRank(), (uint8_t*)buffer, datatype, count, MpiMessageType::BROADCAST);
+    return MPI_SUCCESS;
+}
+
+int MPI_Scatter(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                MPI_Datatype recvtype, int root, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Scatter {} -> all", root);
+    getExecutingWorld().scatter(root, executingContext.getRank(), (const uint8_t*)sendbuf, sendtype, sendcount,
+                                (uint8_t*)recvbuf, recvtype, recvcount);
+    return MPI_SUCCESS;
+}
+
+int MPI_Gather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+               MPI_Datatype recvtype, int root, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Gather all -> {}", root);
+    int rank = executingContext.getRank();
+    const uint8_t* send = (const uint8_t*)sendbuf;
+    if (sendbuf == MPI_IN_PLACE) {
+        // The root's chunk is already in place in the receive buffer
+        send = (const uint8_t*)recvbuf;
+        sendcount = recvcount;
+        sendtype = recvtype;
+    }
+    getExecutingWorld().gather(rank, root, send, sendtype, sendcount, (uint8_t*)recvbuf, recvtype, recvcount);
+    return MPI_SUCCESS;
+}
+
+int MPI_Gatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf,
+                const int* recvcounts, const int* displs, MPI_Datatype recvtype, int root, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Gatherv");
+    MpiWorld& world = getExecutingWorld();
+    int rank = executingContext.getRank();
+    int size = world.getSize();
+    if (rank == root) {
+        for (int r = 0; r < size; r++) {
+            uint8_t* dst = (uint8_t*)recvbuf + (size_t)displs[r] * recvtype->size;
+            if (r == root) {
+                if (sendbuf != MPI_IN_PLACE) {
+                    cudaMemcpy(dst, sendbuf, (size_t)sendcount * sendtype->size, cudaMemcpyDefault);
+                }
+            } else {
+                world.recv(r, root, dst, recvtype, recvcounts[r], nullptr, MpiMessageType::GATHER);
+            }
+        }
+    } else {
+        world.send(rank, root, (const uint8_t*)sendbuf, sendtype, sendcount, MpiMessageType::GATHER);
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Allgather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                  MPI_Datatype recvtype, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Allgather");
+    int rank = executingContext.getRank();
+    const uint8_t* send = (const uint8_t*)sendbuf;
+    if (sendbuf == MPI_IN_PLACE) {
+        send = (const uint8_t*)recvbuf + (size_t)rank * recvcount * recvtype->size;
+        sendcount = recvcount;
+        sendtype = recvtype;
+    }
+    getExecutingWorld().allGather(rank, send, sendtype, sendcount, (uint8_t*)recvbuf, recvtype, recvcount);
+    return MPI_SUCCESS;
+}
+
+int MPI_Allgatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf,
+                   const int* recvcounts, const int* displs, MPI_Datatype recvtype, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Allgatherv");
+    MpiWorld& world = getExecutingWorld();
+    int size = world.getSize();
+    // Equal, contiguous counts are a plain all-gather (fused device kernel)
+    bool regular = true;
+    for (int r = 0; r < size; r++) {
+        regular = regular && recvcounts[r] == recvcounts[0] && displs[r] == r * recvcounts[0];
+    }
+    if (regular) {
+        return MPI_Allgather(sendbuf, sendcount, sendtype, recvbuf, recvcounts[0], recvtype, comm);
+    }
+    // Irregular: gather to rank 0 then broadcast every block
+    int rank = executingContext.getRank();
+    MPI_Gatherv(sendbuf, sendcount, sendtype, recvbuf, recvcounts, displs, recvtype, 0, comm);
+    for (int r = 0; r < size; r++) {
+        uint8_t* block = (uint8_t*)recvbuf + (size_t)displs[r] * recvtype->size;
+        world.broadcast(0, rank, block, recvtype, recvcounts[r], MpiMessageType::ALLGATHER);
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Reduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, int root, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Reduce all -> {}", root);
+    getExecutingWorld().reduce(executingContext.getRank(), root, (uint8_t*)resolveInPlace(sendbuf, recvbuf),
+                               (uint8_t*)recvbuf, datatype, count, op);
+    return MPI_SUCCESS;
+}
+
+int MPI_Reduce_scatter(const void* sendbuf, void* recvbuf, const int* recvcounts, MPI_Datatype datatype,
+                       MPI_Op op, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Reduce_scatter");
+    MpiWorld& world = getExecutingWorld();
+    int size = world.getSize();
+    for (int r = 1; r < size; r++) {
+        if (recvcounts[r] != recvcounts[0]) {
+            return notImplemented("MPI_Reduce_scatter with unequal counts");
+        }
+    }
+    int rank = executingContext.getRank();
+    const void* send = sendbuf;
+    std::vector<uint8_t> tmp;
+    if (sendbuf == MPI_IN_PLACE) {
+        send = recvbuf;
+    }
+    world.reduceScatter(rank, (uint8_t*)send, (uint8_t*)recvbuf, datatype, recvcounts[0], op);
+    return MPI_SUCCESS;
+}
+
+int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Allreduce");
+    getExecutingWorld().allReduce(executingContext.getRank(), (uint8_t*)resolveInPlace(sendbuf, recvbuf),
+                                  (uint8_t*)recvbuf, datatype, count, op);
+    return MPI_SUCCESS;
+}
+
+int MPI_Scan(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Scan");
+    getExecutingWorld().scan(executingContext.getRank(), (uint8_t*)resolveInPlace(sendbuf, recvbuf),
+                             (uint8_t*)recvbuf, datatype, count, op);
+    return MPI_SUCCESS;
+}
+
+int MPI_Alltoall(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                 MPI_Datatype recvtype, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Alltoall");
+    getExecutingWorld().allToAll(executingContext.getRank(), (uint8_t*)sendbuf, sendtype, sendcount,
+                                 (uint8_t*)recvbuf, recvtype, recvcount);
+    return MPI_SUCCESS;
+}
+
+int MPI_Alltoallv(const void* sendbuf, const int sendcounts[], const int sdispls[], MPI_Datatype sendtype,
+                  void* recvbuf, const int recvcounts[], const int rdispls[], MPI_Datatype recvtype, MPI_Comm comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Alltoallv");
+    MpiWorld& world = getExecutingWorld();
+    int rank = executingContext.getRank();
+    int size = world.getSize();
+    // Post every receive, send, then wait: cannot deadlock whatever the sizes
+    std::vector<int> reqs;
+    for (int r = 0; r < size; r++) {
+        uint8_t* dst = (uint8_t*)recvbuf + (size_t)rdispls[r] * recvtype->size;
+        const uint8_t* src = (const uint8_t*)sendbuf + (size_t)sdispls[r] * sendtype->size;
+        if (r == rank) {
+            cudaMemcpy(dst, src, (size_t)sendcounts[r] * sendtype->size, cudaMemcpyDefault);
+        } else {
+            reqs.push_back(world.irecv(r, rank, dst, recvtype, recvcounts[r], MpiMessageType::ALLTOALL));
+        }
+    }
+    for (int r = 0; r < size; r++) {
+        if (r != rank) {
+            const uint8_t* src = (const uint8_t*)sendbuf + (size_t)sdispls[r] * sendtype->size;
+            world.send(rank, r, src, sendtype, sendcounts[r], MpiMessageType::ALLTOALL);
+        }
+    }
+    for (int id : reqs) {
+        world.awaitAsyncRequest(id);
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Cart_create(MPI_Comm old_comm, int ndims, const int dims[], const int periods[], int reorder, MPI_Comm* comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Cart_create");
+    // The grid is remembered by the world; the communicator stays the world
+    int rank = executingContext.getRank();
+    std::vector<int> p(std::max(ndims, 2), 1);
+    std::vector<int> c(std::max(ndims, 2), 0);
+    std::vector<int> d(dims, dims + ndims);
+    d.resize(std::max(ndims, 2), 1);
+    getExecutingWorld().getCartesianRank(rank, ndims, d.data(), p.data(), c.data());
+    *comm = old_comm;
+    return MPI_SUCCESS;
+}
+
+int MPI_Cart_rank(MPI_Comm comm, int coords[], int* rank)
+{
+    SPDLOG_TRACE("MPI - MPI_Cart_rank");
+    getExecutingWorld().getRankFromCoords(rank, coords);
+    return MPI_SUCCESS;
+}
+
+int MPI_Cart_get(MPI_Comm comm, int maxdims, int dims[], int periods[], int coords[])
+{
+    SPDLOG_TRACE("MPI - MPI_Cart_get");
+    if (maxdims > MPI_CART_MAX_DIMENSIONS + 1) {
+        SPDLOG_ERROR("Unexpected number of max. dimensions: {}", maxdims);
+        throw std::runtime_error("Bad dimensions in MPI_Cart_get");
+    }
+    getExecutingWorld().getCartesianRank(executingContext.getRank(), maxdims, dims, periods, coords);
+    return MPI_SUCCESS;
+}
+
+int MPI_Cart_shift(MPI_Comm comm, int direction, int disp, int* rank_source, int* rank_dest)
+{
+    SPDLOG_TRACE("MPI - MPI_Cart_shift");
+    getExecutingWorld().shiftCartesianCoords(executingContext.getRank(), direction, disp, rank_source, rank_dest);
+    return MPI_SUCCESS;
+}
+
+int MPI_Type_size(MPI_Datatype type, int* size)
+{
+    SPDLOG_TRACE("MPI - MPI_Type_size");
+    *size = type->size;
+    return MPI_SUCCESS;
+}
+
+int MPI_Type_free(MPI_Datatype* datatype)
+{
+    return notImplemented("MPI_Type_free");
+}
+
+int MPI_Type_contiguous(int count, MPI_Datatype oldtype, MPI_Datatype* newtype)
+{
+    SPDLOG_TRACE("MPI - MPI_Type_contiguous");
+    return MPI_SUCCESS;
+}
+
+int MPI_Type_commit(MPI_Datatype* type)
+{
+    SPDLOG_TRACE("MPI - MPI_Type_commit");
+    return MPI_SUCCESS;
+}
+
+int MPI_Op_create(MPI_User_function* user_fn, int commute, MPI_Op* op)
+{
+    return notImplemented("MPI_Op_create");
+}
+
+int MPI_Op_free(MPI_Op* op)
+{
+    return notImplemented("MPI_Op_free");
+}
+
+int MPI_Alloc_mem(MPI_Aint size, MPI_Info info, void* baseptr)
+{
+    SPDLOG_TRACE("MPI - MPI_Alloc_mem");
+    if (info != MPI_INFO_NULL) {
+        throw std::runtime_error("Non-null info not supported");
+    }
+    *((void**)baseptr) = malloc((size_t)size);
+    return MPI_SUCCESS;
+}
+
+int MPI_Free_mem(void* base)
+{
+    SPDLOG_TRACE("MPI - MPI_Free_mem");
+    return MPI_SUCCESS;
+}
+
+int MPI_Get_processor_name(char* name, int* resultlen)
+{
+    SPDLOG_TRACE("MPI - MPI_Get_processor_name");
+    std::string host = faabric::util::getSystemConfig().endpointHost;
+    strncpy(name, host.c_str(), MPI_MAX_PROCESSOR_NAME - 1);
+    name[MPI_MAX_PROCESSOR_NAME - 1] = '\0';
+    *resultlen = (int)std::min<size_t>(host.size(), MPI_MAX_PROCESSOR_NAME - 1);
+    return MPI_SUCCESS;
+}
+
+double MPI_Wtime()
+{
+    SPDLOG_TRACE("MPI - MPI_Wtime");
+    return getExecutingWorld().getWTime();
+}
+
+int MPI_Win_get_attr(MPI_Win win, int win_keyval, void* attribute_val, int* flag)
+{
+    SPDLOG_TRACE("MPI - MPI_Win_get_attr");
+    *flag = 1;
+    switch (win_keyval) {
+        case MPI_WIN_BASE:
+            *((void**)attribute_val) = win->basePtr;
+            break;
+        case MPI_WIN_SIZE:
+            *((MPI_Aint*)attribute_val) = (MPI_Aint)win->size;
+            break;
+        case MPI_WIN_DISP_UNIT:
+            *((int*)attribute_val) = win->dispUnit;
+            break;
+        default:
+            throw std::runtime_error("Unrecognised window attribute type " + std::to_string(win_keyval));
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Win_fence(int assert, MPI_Win win)
+{
+    return notImplemented("MPI_Win_fence");
+}
+
+int MPI_Get(void* origin_addr, int origin_count, MPI_Datatype origin_datatype, int target_rank,
+            MPI_Aint target_disp, int target_count, MPI_Datatype target_datatype, MPI_Win win)
+{
+    return notImplemented("MPI_Get");
+}
+
+int MPI_Put(const void* origin_addr, int origin_count, MPI_Datatype origin_datatype, int target_rank,
+            MPI_Aint target_disp, int target_count, MPI_Datatype target_datatype, MPI_Win win)
+{
+    return notImplemented("MPI_Put");
+}
+
+int MPI_Win_free(MPI_Win* win)
+{
+    return notImplemented("MPI_Win_free");
+}
+
+int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, MPI_Win* win)
+{
+    return notImplemented("MPI_Win_create");
+}
+
+int MPI_Win_allocate_shared(MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, void* baseptr, MPI_Win* win)
+{
+    return notImplemented("MPI_Win_allocate_shared");
+}
+
+int MPI_Win_shared_query(MPI_Win win, int rank, MPI_Aint* size, int* disp_unit, void* baseptr)
+{
+    return notImplemented("MPI_Win_shared_query");
+}
+
+int MPI_Comm_dup(MPI_Comm comm, MPI_Comm* newcomm)
+{
+    return notImplemented("MPI_Comm_dup");
+}
+
+MPI_Fint MPI_Comm_c2f(MPI_Comm comm)
+{
+    notImplemented("MPI_Comm_c2f");
+    return 0;
+}
+
+MPI_Comm MPI_Comm_f2c(MPI_Fint comm)
+{
+    notImplemented("MPI_Comm_f2c");
+    return nullptr;
+}
+
+int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm* newcomm)
+{
+    return notImplemented("MPI_Comm_split");
+}
+
+int MPI_Comm_split_type(MPI_Comm comm, int split_type, int key, MPI_Info info, MPI_Comm* newcomm)
+{
+    return notImplemented("MPI_Comm_split_type");
+}
+
+int MPI_Comm_create(MPI_Comm comm, MPI_Group group, MPI_Comm* newcomm)
+{
+    return notImplemented("MPI_Comm_create");
+}
+
+int MPI_Comm_create_group(MPI_Comm comm, MPI_Group group, int tag, MPI_Comm* newcomm)
+{
+    return notImplemented("MPI_Comm_create_group");
+}
+
+int MPI_Comm_group(MPI_Comm comm, MPI_Group* group)
+{
+    return notImplemented("MPI_Comm_group");
+}
+
+int MPI_Group_incl(MPI_Group group, int n, const int ranks[], MPI_Group* newgroup)
+{
+    return notImplemented("MPI_Group_incl");
+}
+
+int MPI_Group_free(MPI_Group* group)
+{
+    return notImplemented("MPI_Group_free");
+}
+
+int MPI_Comm_free(MPI_Comm* comm)
+{
+    SPDLOG_TRACE("MPI - MPI_Comm_free");
+    // Communicators are not owned by the caller
+    return MPI_SUCCESS;
+}
+
+} // extern "C"

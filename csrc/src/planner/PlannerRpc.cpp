@@ -1,0 +1,477 @@
+// PlannerClient / KeepAliveThread / PlannerServer
+#include <faabric/batch-scheduler/BatchScheduler.h>
+#include <faabric/planner/PlannerClient.h>
+#include <faabric/planner/PlannerServer.h>
+#include <faabric/snapshot/SnapshotClient.h>
+#include <faabric/transport/common.h>
+#include <faabric/util/batch.h>
+#include <faabric/util/config.h>
+#include <faabric/util/func.h>
+#include <faabric/util/logging.h>
+#include <faabric/util/network.h>
+#include <faabric/util/ptp.h>
+#include <faabric/util/testing.h>
+
+namespace faabric::planner {
+
+// ---------------------------------------------------------------------------
+// Keep-alive
+// ---------------------------------------------------------------------------
+void KeepAliveThread::doWork()
+{
+    std::shared_ptr<RegisterHostRequest> req;
+    {
+        std::shared_lock<std::shared_mutex> lock(keepAliveThreadMx);
+        req = thisHostReq;
+    }
+    if (req != nullptr) {
+        getPlannerClient().registerHost(req);
+    }
+}
+
+void KeepAliveThread::setRequest(std::shared_ptr<RegisterHostRequest> thisHostReqIn)
+{
+    std::unique_lock<std::shared_mutex> lock(keepAliveThreadMx);
+    thisHostReq = std::move(thisHostReqIn);
+    // Keep-alives must never reset the slot accounting
+    thisHostReq->set_overwrite(false);
+}
+
+// ---------------------------------------------------------------------------
+// Client
+// ---------------------------------------------------------------------------
+static std::string resolvePlannerHost()
+{
+    auto& conf = faabric::util::getSystemConfig();
+    // "planner" is the compose service name in the reference deployment; on a
+    // single box fall back to this machine when it does not resolve
+    std::string ip = faabric::util::getIPFromHostname(conf.plannerHost);
+    if (ip.empty()) {
+        return conf.endpointHost;
+    }
+    return ip;
+}
+
+PlannerClient::PlannerClient()
+  : PlannerClient(resolvePlannerHost())
+{}
+
+PlannerClient::PlannerClient(const std::string& plannerIp)
+  : faabric::transport::MessageEndpointClient(plannerIp, PLANNER_ASYNC_PORT, PLANNER_SYNC_PORT)
+  , snapshotRegistry(faabric::snapshot::getSnapshotRegistry())
+{}
+
+PlannerClient& getPlannerClient()
+{
+    // One client per thread: connections are not shared across threads
+    static thread_local PlannerClient client;
+    return client;
+}
+
+// The result cache must be shared by all threads of the process (results are
+// delivered by FunctionCallServer threads, awaited by executor threads)
+static std::mutex sharedCacheMx;
+static PlannerCache sharedCache;
+
+void PlannerClient::ping()
+{
+    EmptyRequest req;
+    PingResponse resp;
+    syncSend(PlannerCalls::Ping, &req, &resp);
+    // Sanity: the planner must answer with a populated config
+    if (resp.config().ip().empty() && resp.config().hosttimeout() == 0) {
+        SPDLOG_WARN("Planner ping returned an empty config");
+    }
+}
+
+void PlannerClient::clearCache()
+{
+    std::lock_guard<std::mutex> lk(sharedCacheMx);
+    sharedCache.plannerResults.clear();
+    sharedCache.pushedSnapshots.clear();
+}
+
+std::vector<Host> PlannerClient::getAvailableHosts()
+{
+    EmptyRequest req;
+    AvailableHostsResponse resp;
+    syncSend(PlannerCalls::GetAvailableHosts, &req, &resp);
+    std::vector<Host> hosts;
+    for (int i = 0; i < resp.hosts_size(); i++) {
+        hosts.push_back(resp.hosts(i));
+    }
+    return hosts;
+}
+
+int PlannerClient::registerHost(std::shared_ptr<RegisterHostRequest> req)
+{
+    RegisterHostResponse resp;
+    syncSend(PlannerCalls::RegisterHost, req.get(), &resp);
+    if (resp.status().status() != ResponseStatus::OK) {
+        throw std::runtime_error("Error registering host with planner!");
+    }
+    // Sanity check
+    if (resp.config().hosttimeout() <= 0) {
+        throw std::runtime_error("Planner returned a non-positive keep-alive timeout");
+    }
+    return resp.config().hosttimeout();
+}
+
+void PlannerClient::removeHost(std::shared_ptr<RemoveHostRequest> req)
+{
+    RemoveHostResponse resp;
+    syncSend(PlannerCalls::RemoveHost, req.get(), &resp);
+}
+
+void PlannerClient::setMessageResult(std::shared_ptr<faabric::Message> msg)
+{
+    asyncSend(PlannerCalls::SetMessageResult, msg.get());
+}
+
+void PlannerClient::setMessageResultLocally(std::shared_ptr<faabric::Message> msg)
+{
+    std::lock_guard<std::mutex> lk(sharedCacheMx);
+    // May arrive before anyone waits: the promise holds it until then
+    auto& promise = sharedCache.plannerResults[(uint32_t)msg->id()];
+    try {
+        promise.set_value(msg);
+    } catch (const std::future_error&) {
+        SPDLOG_DEBUG("Result for message {} delivered twice", msg->id());
+    }
+}
+
+faabric::Message PlannerClient::getMessageResult(int appId, int msgId, int timeoutMs)
+{
+    auto msgPtr = std::make_shared<faabric::Message>();
+    msgPtr->set_appid(appId);
+    msgPtr->set_id(msgId);
+    return doGetMessageResult(msgPtr, timeoutMs);
+}
+
+faabric::Message PlannerClient::getMessageResult(const faabric::Message& msg, int timeoutMs)
+{
+    return doGetMessageResult(std::make_shared<faabric::Message>(msg), timeoutMs);
+}
+
+faabric::Message PlannerClient::doGetMessageResult(std::shared_ptr<faabric::Message> msgPtr, int timeoutMs)
+{
+    int msgId = msgPtr->id();
+    auto& conf = faabric::util::getSystemConfig();
+    // Tell the planner where to call back
+    msgPtr->set_mainhost(faabric::transport::getThisHostAddress());
+    (void)conf;
+
+    faabric::Message resp;
+    // Ask once.  If the result is not there the planner registers us as a
+    // waiter and pushes the result to our FunctionCallServer
+    std::future<std::shared_ptr<faabric::Message>> fut;
+    {
+        std::lock_guard<std::mutex> lk(sharedCacheMx);
+        auto it = sharedCache.plannerResults.find((uint32_t)msgId);
+        if (it == sharedCache.plannerResults.end()) {
+            it = sharedCache.plannerResults.emplace((uint32_t)msgId, std::promise<std::shared_ptr<faabric::Message>>()).first;
+        }
+        try {
+            fut = it->second.get_future();
+        } catch (const std::future_error&) {
+            // Somebody else is already waiting on this id: poll the planner
+            // instead of sharing the future
+        }
+    }
+    syncSend(PlannerCalls::GetMessageResult, msgPtr.get(), &resp);
+    bool ready = resp.id() == msgId && (resp.type() != faabric::Message::EMPTY);
+    if (ready) {
+        std::lock_guard<std::mutex> lk(sharedCacheMx);
+        sharedCache.plannerResults.erase((uint32_t)msgId);
+        return resp;
+    }
+    if (timeoutMs <= 0) {
+        // Non-blocking probe
+        faabric::Message empty;
+        empty.set_type(faabric::Message::EMPTY);
+        return empty;
+    }
+    if (fut.valid()) {
+        if (fut.wait_for(std::chrono::milliseconds(timeoutMs)) != std::future_status::ready) {
+            std::lock_guard<std::mutex> lk(sharedCacheMx);
+            sharedCache.plannerResults.erase((uint32_t)msgId);
+            SPDLOG_WARN("Timed out waiting for message result promise {}", msgId);
+            faabric::Message empty;
+            empty.set_type(faabric::Message::EMPTY);
+            return empty;
+        }
+        faabric::Message out = *fut.get();
+        std::lock_guard<std::mutex> lk(sharedCacheMx);
+        sharedCache.plannerResults.erase((uint32_t)msgId);
+        return out;
+    }
+    // Fallback: poll
+    auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeoutMs);
+    while (std::chrono::steady_clock::now() < deadline) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        syncSend(PlannerCalls::GetMessageResult, msgPtr.get(), &resp);
+        if (resp.id() == msgId && resp.type() != faabric::Message::EMPTY) {
+            return resp;
+        }
+    }
+    faabric::Message empty;
+    empty.set_type(faabric::Message::EMPTY);
+    return empty;
+}
+
+std::shared_ptr<faabric::BatchExecuteRequestStatus> PlannerClient::getBatchResults(
+  std::shared_ptr<faabric::BatchExecuteRequest> req)
+{
+    auto status = std::make_shared<faabric::BatchExecuteRequestStatus>();
+    syncSend(PlannerCalls::GetBatchResults, req.get(), status.get());
+    return status;
+}
+
+faabric::batch_scheduler::SchedulingDecision PlannerClient::callFunctions(
+  std::shared_ptr<faabric::BatchExecuteRequest> req)
+{
+    // THREADS requests: the planner distributes the main thread snapshot, so it
+    // must have it (full image the first time, tracked changes after that)
+    bool isThreads = req->type() == faabric::BatchExecuteRequest::THREADS;
+    if (isThreads && req->messages_size() > 0) {
+        std::string mainHost = faabric::transport::getThisHostAddress();
+        for (int i = 0; i < req->messages_size(); i++) {
+            req->mutable_messages(i)->set_mainhost(mainHost);
+        }
+        if (!req->singlehosthint()) {
+            std::string key = faabric::util::getMainThreadSnapshotKey(req->messages(0));
+            auto snap = snapshotRegistry.getSnapshot(key);
+            bool firstPush;
+            {
+                std::lock_guard<std::mutex> lk(sharedCacheMx);
+                firstPush = sharedCache.pushedSnapshots.insert(key).second;
+            }
+            auto snapClient = faabric::snapshot::getSnapshotClient(host);
+            if (firstPush) {
+                snapClient->pushSnapshot(key, snap);
+            } else {
+                auto diffs = snap->getTrackedChanges();
+                snapClient->pushSnapshotUpdate(key, snap, diffs);
+            }
+            // Whatever the planner now has, we no longer need to track
+            snap->clearTrackedChanges();
+        }
+    }
+
+    faabric::PointToPointMappings resp;
+    syncSend(PlannerCalls::CallBatch, req.get(), &resp);
+    auto decision = faabric::batch_scheduler::SchedulingDecision::fromPointToPointMappings(resp);
+    // The planner assigns the group id when it commits the decision: mirror it
+    // into the caller's copy of the request
+    if (req->messages_size() > 0 && decision.groupId > 0 && decision.groupId != req->groupid()) {
+        req->set_groupid(decision.groupId);
+        for (int i = 0; i < req->messages_size(); i++) {
+            req->mutable_messages(i)->set_groupid(decision.groupId);
+        }
+    }
+    return decision;
+}
+
+faabric::batch_scheduler::SchedulingDecision PlannerClient::getSchedulingDecision(
+  std::shared_ptr<faabric::BatchExecuteRequest> req)
+{
+    faabric::PointToPointMappings resp;
+    syncSend(PlannerCalls::GetSchedulingDecision, req.get(), &resp);
+    return faabric::batch_scheduler::SchedulingDecision::fromPointToPointMappings(resp);
+}
+
+int PlannerClient::getNumMigrations()
+{
+    EmptyRequest req;
+    NumMigrationsResponse resp;
+    syncSend(PlannerCalls::GetNumMigrations, &req, &resp);
+    return resp.nummigrations();
+}
+
+void PlannerClient::preloadSchedulingDecision(
+  std::shared_ptr<faabric::batch_scheduler::SchedulingDecision> preloadDec)
+{
+    faabric::PointToPointMappings mappings = faabric::util::ptpMappingsFromSchedulingDecision(preloadDec);
+    EmptyResponse resp;
+    syncSend(PlannerCalls::PreloadSchedulingDecision, &mappings, &resp);
+}
+
+// ---------------------------------------------------------------------------
+// Server
+// ---------------------------------------------------------------------------
+PlannerServer::PlannerServer()
+  : faabric::transport::MessageEndpointServer(PLANNER_ASYNC_PORT,
+                                              PLANNER_SYNC_PORT,
+                                              PLANNER_INPROC_LABEL,
+                                              getPlanner().getConfig().numthreadshttpserver())
+  , planner(getPlanner())
+{}
+
+void PlannerServer::doAsyncRecv(transport::Message& message)
+{
+    uint8_t header = message.getMessageCode();
+    if (header == PlannerCalls::SetMessageResult) {
+        recvSetMessageResult(message.udata());
+        return;
+    }
+    // Bad requests must not take the planner down: log and carry on
+    SPDLOG_ERROR("Unrecognised async planner call header: {}", (int)header);
+}
+
+std::string PlannerServer::doSyncRecv(transport::Message& message)
+{
+    uint8_t header = message.getMessageCode();
+    switch (header) {
+        case PlannerCalls::Ping:
+            return recvPing();
+        case PlannerCalls::GetAvailableHosts:
+            return recvGetAvailableHosts();
+        case PlannerCalls::RegisterHost:
+            return recvRegisterHost(message.udata());
+        case PlannerCalls::RemoveHost:
+            return recvRemoveHost(message.udata());
+        case PlannerCalls::GetMessageResult:
+            return recvGetMessageResult(message.udata());
+        case PlannerCalls::GetBatchResults:
+            return recvGetBatchResults(message.udata());
+        case PlannerCalls::GetSchedulingDecision:
+            return recvGetSchedulingDecision(message.udata());
+        case PlannerCalls::GetNumMigrations:
+            return recvGetNumMigrations(message.udata());
+        case PlannerCalls::PreloadSchedulingDecision:
+            return recvPreloadSchedulingDecision(message.udata());
+        case PlannerCalls::CallBatch:
+            return recvCallBatch(message.udata());
+        default:
+            SPDLOG_ERROR("Unrecognised sync planner call header: {}", (int)header);
+            return EmptyResponse().SerializeAsString();
+    }
+}
+
+template<typename T>
+static bool parseInto(std::span<const uint8_t> buffer, T& msg)
+{
+    return msg.ParseFromArray(buffer.data(), (int)buffer.size());
+}
+
+void PlannerServer::recvSetMessageResult(std::span<const uint8_t> buffer)
+{
+    auto msg = std::make_shared<faabric::Message>();
+    if (!parseInto(buffer, *msg)) {
+        SPDLOG_ERROR("Planner could not parse message result");
+        return;
+    }
+    planner.setMessageResult(msg);
+}
+
+std::string PlannerServer::recvPing()
+{
+    PingResponse resp;
+    *resp.mutable_config() = planner.getConfig();
+    return resp.SerializeAsString();
+}
+
+std::string PlannerServer::recvGetAvailableHosts()
+{
+    AvailableHostsResponse resp;
+    for (const auto& h : planner.getAvailableHosts()) {
+        *resp.add_hosts() = *h;
+    }
+    return resp.SerializeAsString();
+}
+
+std::string PlannerServer::recvRegisterHost(std::span<const uint8_t> buffer)
+{
+    RegisterHostRequest req;
+    RegisterHostResponse resp;
+    bool ok = parseInto(buffer, req) && planner.registerHost(req.host(), req.overwrite());
+    if (!ok) {
+        SPDLOG_ERROR("Planner failed to register host {}", req.host().ip());
+    }
+    *resp.mutable_config() = planner.getConfig();
+    resp.mutable_status()->set_status(ok ? ResponseStatus::OK : ResponseStatus::ERROR);
+    return resp.SerializeAsString();
+}
+
+std::string PlannerServer::recvRemoveHost(std::span<const uint8_t> buffer)
+{
+    RemoveHostRequest req;
+    if (parseInto(buffer, req)) {
+        planner.removeHost(req.host());
+    }
+    RemoveHostResponse resp;
+    resp.mutable_status()->set_status(ResponseStatus::OK);
+    return resp.SerializeAsString();
+}
+
+std::string PlannerServer::recvGetMessageResult(std::span<const uint8_t> buffer)
+{
+    auto msg = std::make_shared<faabric::Message>();
+    parseInto(buffer, *msg);
+    auto result = planner.getMessageResult(msg);
+    if (result == nullptr) {
+        faabric::Message empty;
+        empty.set_appid(msg->appid());
+        empty.set_id(msg->id());
+        empty.set_type(faabric::Message::EMPTY);
+        return empty.SerializeAsString();
+    }
+    return result->SerializeAsString();
+}
+
+std::string PlannerServer::recvGetBatchResults(std::span<const uint8_t> buffer)
+{
+    auto req = std::make_shared<faabric::BatchExecuteRequest>();
+    parseInto(buffer, *req);
+    auto status = planner.getBatchResults(req->appid());
+    if (status == nullptr) {
+        // Unknown app: empty status, not finished
+        status = faabric::util::batchExecStatusFactory(req->appid());
+        status->set_appid(0);
+    }
+    return status->SerializeAsString();
+}
+
+std::string PlannerServer::recvGetSchedulingDecision(std::span<const uint8_t> buffer)
+{
+    auto req = std::make_shared<faabric::BatchExecuteRequest>();
+    parseInto(buffer, *req);
+    auto decision = planner.getSchedulingDecision(req);
+    faabric::PointToPointMappings mappings;
+    if (decision != nullptr) {
+        mappings = faabric::util::ptpMappingsFromSchedulingDecision(decision);
+    }
+    return mappings.SerializeAsString();
+}
+
+std::string PlannerServer::recvGetNumMigrations(std::span<const uint8_t> buffer)
+{
+    NumMigrationsResponse resp;
+    resp.set_nummigrations(planner.getNumMigrations());
+    return resp.SerializeAsString();
+}
+
+std::string PlannerServer::recvPreloadSchedulingDecision(std::span<const uint8_t> buffer)
+{
+    faabric::PointToPointMappings mappings;
+    parseInto(buffer, mappings);
+    auto decision = std::make_shared<faabric::batch_scheduler::SchedulingDecision>(
+      faabric::batch_scheduler::SchedulingDecision::fromPointToPointMappings(mappings));
+    planner.preloadSchedulingDecision((int)decision->appId, decision);
+    return EmptyResponse().SerializeAsString();
+}
+
+std::string PlannerServer::recvCallBatch(std::span<const uint8_t> buffer)
+{
+    auto req = std::make_shared<faabric::BatchExecuteRequest>();
+    if (!parseInto(buffer, *req)) {
+        SPDLOG_ERROR("Planner could not parse batch execute request");
+        faabric::batch_scheduler::SchedulingDecision bad(NOT_ENOUGH_SLOTS_DECISION);
+        auto badPtr = std::make_shared<faabric::batch_scheduler::SchedulingDecision>(bad);
+        return faabric::util::ptpMappingsFromSchedulingDecision(badPtr).SerializeAsString();
+    }
+    auto decision = planner.callBatch(req);
+    return faabric::util::ptpMappingsFromSchedulingDecision(decision).SerializeAsString();
+}
+
+} // namespace faabric::planner

@@ -1,0 +1,456 @@
+#include <faabric/batch-scheduler/BatchScheduler.h>
+#include <faabric/executor/Executor.h>
+#include <faabric/executor/ExecutorFactory.h>
+#include <faabric/scheduler/FunctionCallClient.h>
+#include <faabric/scheduler/Scheduler.h>
+#include <faabric/transport/common.h>
+#include <faabric/util/batch.h>
+#include <faabric/util/environment.h>
+#include <faabric/util/func.h>
+#include <faabric/util/logging.h>
+#include <faabric/util/testing.h>
+
+namespace faabric::scheduler {
+
+Scheduler& getScheduler()
+{
+    static Scheduler sch;
+    return sch;
+}
+
+Scheduler::Scheduler()
+  : thisHost(faabric::transport::getThisHostAddress())
+  , conf(faabric::util::getSystemConfig())
+  , reg(faabric::snapshot::getSnapshotRegistry())
+  , broker(faabric::transport::getPointToPointBroker())
+{
+    // Idle executors are reaped periodically
+    if (conf.reaperIntervalSeconds > 0) {
+        reaperThread.start(conf.reaperIntervalSeconds);
+    }
+}
+
+Scheduler::~Scheduler()
+{
+    if (!_isShutdown) {
+        SPDLOG_DEBUG("Destructing scheduler without shutting down first");
+    }
+    reaperThread.stop();
+    keepAliveThread.stop();
+}
+
+std::string Scheduler::getThisHost()
+{
+    return thisHost;
+}
+
+// ---------------------------------------------------------------------------
+// Membership
+// ---------------------------------------------------------------------------
+void Scheduler::addHostToGlobalSet(
+  const std::string& hostIp,
+  std::shared_ptr<faabric::HostResources> overwriteResources)
+{
+    auto req = std::make_shared<faabric::planner::RegisterHostRequest>();
+    req->mutable_host()->set_ip(hostIp);
+    req->set_overwrite(false);
+    if (overwriteResources != nullptr) {
+        req->mutable_host()->set_slots(overwriteResources->slots());
+        req->mutable_host()->set_usedslots(overwriteResources->usedslots());
+        req->set_overwrite(true);
+    } else if (hostIp == thisHost) {
+        // Execution slots: CPU cores, or slots-per-GPU x GPUs on a GPU box
+        int gpus = faabric::util::getUsableGpus();
+        int slots = gpus > 0 ? gpus * conf.slotsPerGpu : (int)faabric::util::getUsableCores();
+        req->mutable_host()->set_slots(slots);
+        req->mutable_host()->set_usedslots(0);
+    }
+    int plannerTimeout = faabric::planner::getPlannerClient().registerHost(req);
+    // Keep-alive only for ourselves, at half the planner's timeout
+    if (hostIp == thisHost && !faabric::util::isTestMode()) {
+        keepAliveThread.setRequest(req);
+        keepAliveThread.startMs(std::max(100, plannerTimeout * 1000 / 2));
+    }
+}
+
+void Scheduler::addHostToGlobalSet()
+{
+    addHostToGlobalSet(thisHost);
+}
+
+void Scheduler::removeHostFromGlobalSet(const std::string& hostIp)
+{
+    auto req = std::make_shared<faabric::planner::RemoveHostRequest>();
+    bool isThisHost = hostIp == thisHost && keepAliveThread.getIntervalSeconds() >= 0;
+    if (isThisHost) {
+        keepAliveThread.stop();
+    }
+    req->mutable_host()->set_ip(hostIp);
+    faabric::planner::getPlannerClient().removeHost(req);
+}
+
+void Scheduler::setThisHostResources(faabric::HostResources& res)
+{
+    addHostToGlobalSet(thisHost, std::make_shared<faabric::HostResources>(res));
+    conf.overrideCpuCount = res.slots();
+}
+
+// ---------------------------------------------------------------------------
+// Lifecycle
+// ---------------------------------------------------------------------------
+void Scheduler::resetThreadLocalCache()
+{
+    clearFunctionCallClients();
+    faabric::snapshot::clearSnapshotClients();
+}
+
+void Scheduler::reset()
+{
+    SPDLOG_DEBUG("Resetting scheduler");
+    resetThreadLocalCache();
+    // Shut the executors down outside the lock: their threads may call back
+    std::vector<std::shared_ptr<faabric::executor::Executor>> toStop;
+    {
+        std::unique_lock<std::shared_mutex> lock(mx);
+        for (auto& [key, vec] : executors) {
+            for (auto& e : vec) {
+                toStop.push_back(e);
+            }
+        }
+        executors.clear();
+    }
+    for (auto& e : toStop) {
+        e->shutdown();
+    }
+    {
+        std::lock_guard<std::mutex> lk(threadResultsMx);
+        threadResults.clear();
+        threadFutures.clear();
+        threadResultMessages.clear();
+    }
+    {
+        std::unique_lock<std::shared_mutex> lock(mx);
+        recordedMessages.clear();
+    }
+    faabric::planner::getPlannerClient().clearCache();
+    _isShutdown = false;
+}
+
+void Scheduler::shutdown()
+{
+    reset();
+    reaperThread.stop();
+    try {
+        removeHostFromGlobalSet(thisHost);
+    } catch (const std::exception& e) {
+        SPDLOG_DEBUG("Could not deregister host on shutdown: {}", e.what());
+    }
+    _isShutdown = true;
+}
+
+void SchedulerReaperThread::doWork()
+{
+    getScheduler().reapStaleExecutors();
+}
+
+int Scheduler::reapStaleExecutors()
+{
+    std::unique_lock<std::shared_mutex> lock(mx);
+    if (executors.empty()) {
+        return 0;
+    }
+    int reaped = 0;
+    std::vector<std::shared_ptr<faabric::executor::Executor>> toStop;
+    for (auto it = executors.begin(); it != executors.end();) {
+        auto& vec = it->second;
+        for (auto e = vec.begin(); e != vec.end();) {
+            long idle = (*e)->getMillisSinceLastExec();
+            if (idle < conf.boundTimeout || (*e)->isExecuting()) {
+                ++e;
+                continue;
+            }
+            // Only reap what we can claim (not mid-way through being claimed)
+            if (!(*e)->tryClaim()) {
+                ++e;
+                continue;
+            }
+            SPDLOG_DEBUG("Reaping stale executor {} ({}ms idle)", (*e)->id, idle);
+            toStop.push_back(*e);
+            e = vec.erase(e);
+            reaped++;
+        }
+        if (vec.empty()) {
+            it = executors.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    lock.unlock();
+    for (auto& e : toStop) {
+        e->shutdown();
+    }
+    return reaped;
+}
+
+long Scheduler::getFunctionExecutorCount(const faabric::Message& msg)
+{
+    std::shared_lock<std::shared_mutex> lock(mx);
+    long n = 0;
+    std::string prefix = faabric::util::funcToString(msg, false);
+    for (const auto& [key, vec] : executors) {
+        if (key == prefix || key.rfind(prefix + ":", 0) == 0) {
+            n += (long)vec.size();
+        }
+    }
+    return n;
+}
+
+void Scheduler::flushLocally()
+{
+    SPDLOG_INFO("Flushing host {}", thisHost);
+    reset();
+    faabric::executor::getExecutorFactory()->flushHost();
+}
+
+// ---------------------------------------------------------------------------
+// Execution
+// ---------------------------------------------------------------------------
+static std::string executorKey(const faabric::Message& msg)
+{
+    // Executors are warm per (user/function, app)
+    return faabric::util::funcToString(msg, false) + ":" + std::to_string(msg.appid());
+}
+
+std::shared_ptr<faabric::executor::Executor> Scheduler::claimExecutor(
+  faabric::Message& msg,
+  std::unique_lock<std::shared_mutex>& schedulerLock)
+{
+    std::string key = executorKey(msg);
+    auto& vec = executors[key];
+    for (auto& e : vec) {
+        if (e->tryClaim()) {
+            SPDLOG_DEBUG("Reusing warm executor {} for {}", e->id, key);
+            return e;
+        }
+    }
+    // Creating an executor can be slow (memory set-up): do it unlocked
+    SPDLOG_DEBUG("Scaling {} from {} -> {}", key, vec.size(), vec.size() + 1);
+    schedulerLock.unlock();
+    std::shared_ptr<faabric::executor::Executor> e;
+    try {
+        e = faabric::executor::getExecutorFactory()->createExecutor(msg);
+    } catch (...) {
+        schedulerLock.lock();
+        throw;
+    }
+    schedulerLock.lock();
+    e->claim();
+    executors[key].push_back(e);
+    return e;
+}
+
+void Scheduler::executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req)
+{
+    std::unique_lock<std::shared_mutex> lock(mx);
+    bool isThreads = req->type() == faabric::BatchExecuteRequest::THREADS;
+    int n = req->messages_size();
+    if (n == 0) {
+        return;
+    }
+    if (faabric::util::isTestMode()) {
+        for (int i = 0; i < n; i++) {
+            recordedMessages.push_back(req->messages(i));
+        }
+    }
+    if (isThreads) {
+        // All threads of a batch share one executor (and its memory)
+        faabric::Message& first = *req->mutable_messages(0);
+        std::shared_ptr<faabric::executor::Executor> e;
+        try {
+            e = claimExecutor(first, lock);
+        } catch (const std::exception& ex) {
+            SPDLOG_ERROR("Failed to claim executor for {}: {}", faabric::util::funcToString(first, false), ex.what());
+            lock.unlock();
+            for (int i = 0; i < n; i++) {
+                auto m = std::make_shared<faabric::Message>(req->messages(i));
+                m->set_returnvalue(1);
+                m->set_outputdata(std::string("Failed to claim executor: ") + ex.what());
+                faabric::planner::getPlannerClient().setMessageResult(m);
+            }
+            return;
+        }
+        lock.unlock();
+        std::vector<int> idxs(n);
+        for (int i = 0; i < n; i++) {
+            idxs[i] = i;
+        }
+        e->executeTasks(idxs, req);
+        return;
+    }
+    // One executor per message
+    std::vector<std::pair<std::shared_ptr<faabric::executor::Executor>, int>> launches;
+    std::vector<int> failed;
+    std::string failure;
+    for (int i = 0; i < n; i++) {
+        faabric::Message& m = *req->mutable_messages(i);
+        try {
+            launches.emplace_back(claimExecutor(m, lock), i);
+        } catch (const std::exception& ex) {
+            failure = ex.what();
+            failed.push_back(i);
+        }
+    }
+    lock.unlock();
+    for (auto& [e, idx] : launches) {
+        e->executeTasks({ idx }, req);
+    }
+    for (int idx : failed) {
+        auto m = std::make_shared<faabric::Message>(req->messages(idx));
+        m->set_returnvalue(1);
+        m->set_outputdata("Failed to claim executor: " + failure);
+        faabric::planner::getPlannerClient().setMessageResult(m);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Thread results
+// ---------------------------------------------------------------------------
+void Scheduler::setThreadResultLocally(uint32_t appId,
+                                       uint32_t msgId,
+                                       int32_t returnValue,
+                                       faabric::transport::Message& message)
+{
+    std::lock_guard<std::mutex> lk(threadResultsMx);
+    // Diffs attached to the result point into the transport message: keep it
+    threadResultMessages.insert_or_assign(msgId, std::move(message));
+    auto it = threadResults.find(msgId);
+    if (it == threadResults.end()) {
+        it = threadResults.emplace(msgId, std::promise<int32_t>()).first;
+        threadFutures.emplace(msgId, it->second.get_future().share());
+    }
+    try {
+        it->second.set_value(returnValue);
+    } catch (const std::future_error&) {
+        SPDLOG_WARN("Thread result for {} set twice", msgId);
+    }
+}
+
+std::vector<std::pair<uint32_t, int32_t>> Scheduler::awaitThreadResults(
+  std::shared_ptr<faabric::BatchExecuteRequest> req,
+  int timeoutMs)
+{
+    std::vector<std::pair<uint32_t, int32_t>> results;
+    results.reserve(req->messages_size());
+    for (int i = 0; i < req->messages_size(); i++) {
+        uint32_t msgId = (uint32_t)req->messages(i).id();
+        // Prefer a result that was pushed to us directly (remote threads)
+        std::shared_future<int32_t> fut;
+        bool local = false;
+        {
+            std::lock_guard<std::mutex> lk(threadResultsMx);
+            auto it = threadFutures.find(msgId);
+            if (it != threadFutures.end()) {
+                fut = it->second;
+                local = true;
+            }
+        }
+        if (local && fut.wait_for(std::chrono::milliseconds(0)) == std::future_status::ready) {
+            results.emplace_back(msgId, fut.get());
+            continue;
+        }
+        faabric::Message res = faabric::planner::getPlannerClient().getMessageResult(
+          req->appid(), (int)msgId, timeoutMs);
+        results.emplace_back(msgId, res.returnvalue());
+    }
+    return results;
+}
+
+size_t Scheduler::getCachedMessageCount()
+{
+    std::lock_guard<std::mutex> lk(threadResultsMx);
+    return threadResultMessages.size();
+}
+
+std::vector<faabric::Message> Scheduler::getRecordedMessages()
+{
+    std::shared_lock<std::shared_mutex> lock(mx);
+    return recordedMessages;
+}
+
+void Scheduler::clearRecordedMessages()
+{
+    std::unique_lock<std::shared_mutex> lock(mx);
+    recordedMessages.clear();
+}
+
+// ---------------------------------------------------------------------------
+// Migration
+// ---------------------------------------------------------------------------
+std::shared_ptr<faabric::PendingMigration> Scheduler::checkForMigrationOpportunities(
+  faabric::Message& msg,
+  int overwriteNewGroupId)
+{
+    int appId = msg.appid();
+    int groupId = msg.groupid();
+    int groupIdx = msg.groupidx();
+    SPDLOG_DEBUG("Message {}:{}:{} checking for migration opportunities", appId, groupId, groupIdx);
+
+    int newGroupId = 0;
+    if (groupIdx == 0) {
+        // Idx 0 asks the planner on behalf of the group, then tells the rest
+        auto req = std::make_shared<faabric::BatchExecuteRequest>();
+        req->set_appid(appId);
+        req->set_groupid(groupId);
+        req->set_user(msg.user());
+        req->set_function(msg.function());
+        req->set_type(faabric::BatchExecuteRequest::MIGRATION);
+        *req->add_messages() = msg;
+        auto decision = faabric::planner::getPlannerClient().callFunctions(req);
+        if ((int)decision.appId == DO_NOT_MIGRATE || (int)decision.appId == NOT_ENOUGH_SLOTS) {
+            newGroupId = groupId;
+        } else if ((int)decision.appId == MUST_FREEZE) {
+            newGroupId = MUST_FREEZE;
+        } else {
+            newGroupId = decision.groupId;
+        }
+        if (overwriteNewGroupId != 0) {
+            newGroupId = overwriteNewGroupId;
+        }
+        std::vector<uint8_t> bytes(sizeof(int));
+        memcpy(bytes.data(), &newGroupId, sizeof(int));
+        auto idxs = broker.getIdxsRegisteredForGroup(groupId);
+        for (int idx : idxs) {
+            if (idx != 0) {
+                broker.sendMessage(groupId, 0, idx, bytes.data(), bytes.size());
+            }
+        }
+    } else if (overwriteNewGroupId == 0) {
+        std::vector<uint8_t> bytes = broker.recvMessage(groupId, 0, groupIdx);
+        memcpy(&newGroupId, bytes.data(), sizeof(int));
+    } else {
+        newGroupId = overwriteNewGroupId;
+    }
+
+    if (newGroupId == MUST_FREEZE) {
+        // Signalled through a pending migration to "nowhere"
+        auto frozen = std::make_shared<faabric::PendingMigration>();
+        frozen->set_appid(MUST_FREEZE);
+        return frozen;
+    }
+    if (newGroupId == groupId) {
+        return nullptr; // nothing to do
+    }
+    // The planner pushed the new mappings before answering idx 0
+    msg.set_groupid(newGroupId);
+    broker.waitForMappingsOnThisHost(newGroupId);
+    std::string newHost = broker.getHostForReceiver(newGroupId, groupIdx);
+    auto migration = std::make_shared<faabric::PendingMigration>();
+    migration->set_appid(appId);
+    migration->set_groupid(newGroupId);
+    migration->set_groupidx(groupIdx);
+    migration->set_srchost(msg.executedhost().empty() ? thisHost : msg.executedhost());
+    migration->set_dsthost(newHost);
+    return migration;
+}
+
+} // namespace faabric::scheduler

@@ -1,0 +1,638 @@
+// SnapshotRegistry, SnapshotClient, SnapshotServer, DeviceSnapshot
+#include <faabric/scheduler/Scheduler.h>
+#include <faabric/snapshot/DeviceSnapshot.h>
+#include <faabric/snapshot/SnapshotClient.h>
+#include <faabric/snapshot/SnapshotRegistry.h>
+#include <faabric/snapshot/SnapshotServer.h>
+#include <faabric/transport/common.h>
+#include <faabric/util/config.h>
+#include <faabric/util/dirty.h>
+#include <faabric/util/logging.h>
+#include <faabric/util/testing.h>
+
+#include "launch_api.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace faabric::snapshot {
+
+using faabric::util::SnapshotData;
+using faabric::util::SnapshotDataType;
+using faabric::util::SnapshotDiff;
+using faabric::util::SnapshotMergeOperation;
+using faabric::util::SnapshotMergeRegion;
+
+// ---------------------------------------------------------------------------
+// Registry
+// ---------------------------------------------------------------------------
+SnapshotRegistry& getSnapshotRegistry()
+{
+    static SnapshotRegistry reg;
+    return reg;
+}
+
+std::shared_ptr<SnapshotData> SnapshotRegistry::getSnapshot(const std::string& key)
+{
+    if (key.empty()) {
+        SPDLOG_ERROR("Attempting to get snapshot with empty key");
+        throw std::runtime_error("Getting snapshot with empty key");
+    }
+    std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+    auto it = snapshotMap.find(key);
+    if (it == snapshotMap.end()) {
+        SPDLOG_ERROR("Snapshot for {} does not exist", key);
+        throw std::runtime_error("Snapshot doesn't exist");
+    }
+    return it->second;
+}
+
+bool SnapshotRegistry::snapshotExists(const std::string& key)
+{
+    std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+    return snapshotMap.find(key) != snapshotMap.end();
+}
+
+void SnapshotRegistry::registerSnapshot(const std::string& key, std::shared_ptr<SnapshotData> data)
+{
+    std::unique_lock<std::shared_mutex> lock(snapshotsMx);
+    SPDLOG_TRACE("Registering snapshot {} size {}", key, data->getSize());
+    snapshotMap.insert_or_assign(key, std::move(data));
+}
+
+void SnapshotRegistry::deleteSnapshot(const std::string& key)
+{
+    std::unique_lock<std::shared_mutex> lock(snapshotsMx);
+    snapshotMap.erase(key);
+}
+
+size_t SnapshotRegistry::getSnapshotCount()
+{
+    std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+    return snapshotMap.size();
+}
+
+std::shared_ptr<DeviceSnapshot> SnapshotRegistry::getDeviceSnapshot(const std::string& key)
+{
+    std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+    auto it = deviceMap.find(key);
+    if (it == deviceMap.end()) {
+        SPDLOG_ERROR("Device snapshot for {} does not exist", key);
+        throw std::runtime_error("Device snapshot doesn't exist");
+    }
+    return it->second;
+}
+
+bool SnapshotRegistry::deviceSnapshotExists(const std::string& key)
+{
+    std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+    return deviceMap.find(key) != deviceMap.end();
+}
+
+void SnapshotRegistry::registerDeviceSnapshot(const std::string& key, std::shared_ptr<DeviceSnapshot> data)
+{
+    std::unique_lock<std::shared_mutex> lock(snapshotsMx);
+    deviceMap.insert_or_assign(key, std::move(data));
+}
+
+void SnapshotRegistry::deleteDeviceSnapshot(const std::string& key)
+{
+    std::unique_lock<std::shared_mutex> lock(snapshotsMx);
+    deviceMap.erase(key);
+}
+
+void SnapshotRegistry::clear()
+{
+    std::unique_lock<std::shared_mutex> lock(snapshotsMx);
+    snapshotMap.clear();
+    deviceMap.clear();
+}
+
+// ---------------------------------------------------------------------------
+// Client (+ mock capture)
+// ---------------------------------------------------------------------------
+static std::mutex mockMutex;
+static std::vector<std::pair<std::string, std::shared_ptr<SnapshotData>>> snapshotPushes;
+static std::vector<std::pair<std::string, std::shared_ptr<MockSnapshotUpdate>>> snapshotDiffPushes;
+static std::vector<std::pair<std::string, std::string>> snapshotDeletes;
+static std::vector<std::pair<std::string, std::tuple<int, int, std::string, int>>> threadResults;
+
+std::vector<std::pair<std::string, std::shared_ptr<SnapshotData>>> getSnapshotPushes()
+{
+    std::lock_guard<std::mutex> lk(mockMutex);
+    return snapshotPushes;
+}
+
+std::vector<std::pair<std::string, std::shared_ptr<MockSnapshotUpdate>>> getSnapshotDiffPushes()
+{
+    std::lock_guard<std::mutex> lk(mockMutex);
+    return snapshotDiffPushes;
+}
+
+std::vector<std::pair<std::string, std::string>> getSnapshotDeletes()
+{
+    std::lock_guard<std::mutex> lk(mockMutex);
+    return snapshotDeletes;
+}
+
+std::vector<std::pair<std::string, std::tuple<int, int, std::string, int>>> getThreadResults()
+{
+    std::lock_guard<std::mutex> lk(mockMutex);
+    return threadResults;
+}
+
+void clearMockSnapshotRequests()
+{
+    std::lock_guard<std::mutex> lk(mockMutex);
+    snapshotPushes.clear();
+    snapshotDiffPushes.clear();
+    snapshotDeletes.clear();
+    threadResults.clear();
+}
+
+static thread_local std::unordered_map<std::string, std::shared_ptr<SnapshotClient>> tlsSnapClients;
+
+std::shared_ptr<SnapshotClient> getSnapshotClient(const std::string& host)
+{
+    auto it = tlsSnapClients.find(host);
+    if (it != tlsSnapClients.end()) {
+        return it->second;
+    }
+    auto c = std::make_shared<SnapshotClient>(host);
+    tlsSnapClients[host] = c;
+    return c;
+}
+
+void clearSnapshotClients()
+{
+    tlsSnapClients.clear();
+}
+
+SnapshotClient::SnapshotClient(const std::string& hostIn)
+  : faabric::transport::MessageEndpointClient(hostIn, SNAPSHOT_ASYNC_PORT, SNAPSHOT_SYNC_PORT)
+{}
+
+static void fillRegions(faabric::proto::RepeatedField<faabric::SnapshotMergeRegionRequest>* out,
+                        const std::vector<SnapshotMergeRegion>& regions)
+{
+    for (const auto& r : regions) {
+        auto* m = out->Add();
+        m->set_offset(r.offset);
+        m->set_length(r.length);
+        m->set_datatype((int)r.dataType);
+        m->set_mergeop((int)r.operation);
+    }
+}
+
+static void fillDiffs(faabric::proto::RepeatedField<faabric::SnapshotDiffRequest>* out,
+                      const std::vector<SnapshotDiff>& diffs)
+{
+    for (const auto& d : diffs) {
+        auto* m = out->Add();
+        m->set_offset(d.getOffset());
+        m->set_datatype((int)d.getDataType());
+        m->set_mergeop((int)d.getOperation());
+        m->set_data(d.getData().data(), d.getData().size());
+    }
+}
+
+void SnapshotClient::pushSnapshot(const std::string& key, std::shared_ptr<SnapshotData> data)
+{
+    if (data->getSize() == 0) {
+        SPDLOG_ERROR("Cannot push snapshot {} with zero size to {}", key, host);
+        throw std::runtime_error("Pushing snapshot with zero size");
+    }
+    SPDLOG_DEBUG("Pushing snapshot {} to {} ({} bytes)", key, host, data->getSize());
+    if (faabric::util::isMockMode()) {
+        std::lock_guard<std::mutex> lk(mockMutex);
+        snapshotPushes.emplace_back(host, data);
+        return;
+    }
+    faabric::SnapshotPushRequest req;
+    req.set_key(key);
+    req.set_maxsize(data->getMaxSize());
+    req.set_contents(data->getDataPtr(), data->getSize());
+    fillRegions(req.mutable_mergeregions(), data->getMergeRegions());
+    faabric::EmptyResponse resp;
+    syncSend(SnapshotCalls::PushSnapshot, &req, &resp);
+}
+
+void SnapshotClient::pushSnapshotUpdate(std::string snapshotKey,
+                                        const std::shared_ptr<SnapshotData>& data,
+                                        const std::vector<SnapshotDiff>& diffs)
+{
+    SPDLOG_DEBUG("Pushing update to snapshot {} to {} ({} diffs)", snapshotKey, host, diffs.size());
+    if (faabric::util::isMockMode()) {
+        auto upd = std::make_shared<MockSnapshotUpdate>();
+        for (const auto& d : diffs) {
+            upd->diffData.push_back(d.getDataCopy());
+            upd->diffs.emplace_back(d.getDataType(), d.getOperation(), d.getOffset(), upd->diffData.back());
+        }
+        upd->mergeRegions = data->getMergeRegions();
+        std::lock_guard<std::mutex> lk(mockMutex);
+        snapshotDiffPushes.emplace_back(host, upd);
+        return;
+    }
+    faabric::SnapshotUpdateRequest req;
+    req.set_key(snapshotKey);
+    fillRegions(req.mutable_mergeregions(), data->getMergeRegions());
+    fillDiffs(req.mutable_diffs(), diffs);
+    faabric::EmptyResponse resp;
+    syncSend(SnapshotCalls::PushSnapshotUpdate, &req, &resp);
+}
+
+void SnapshotClient::deleteSnapshot(const std::string& key)
+{
+    if (faabric::util::isMockMode()) {
+        std::lock_guard<std::mutex> lk(mockMutex);
+        snapshotDeletes.emplace_back(host, key);
+        return;
+    }
+    faabric::SnapshotDeleteRequest req;
+    req.set_key(key);
+    asyncSend(SnapshotCalls::DeleteSnapshot, &req);
+}
+
+void SnapshotClient::pushThreadResult(uint32_t appId,
+                                      uint32_t messageId,
+                                      int returnValue,
+                                      const std::string& key,
+                                      const std::vector<SnapshotDiff>& diffs)
+{
+    if (faabric::util::isMockMode()) {
+        std::lock_guard<std::mutex> lk(mockMutex);
+        threadResults.emplace_back(host, std::make_tuple((int)messageId, returnValue, key, (int)diffs.size()));
+        return;
+    }
+    SPDLOG_DEBUG("Sending thread result for {} to {} (plus {} snapshot diffs)", messageId, host, diffs.size());
+    faabric::ThreadResultRequest req;
+    req.set_appid((int32_t)appId);
+    req.set_messageid((int32_t)messageId);
+    req.set_returnvalue(returnValue);
+    req.set_key(key);
+    fillDiffs(req.mutable_diffs(), diffs);
+    faabric::EmptyResponse resp;
+    syncSend(SnapshotCalls::ThreadResult, &req, &resp);
+}
+
+// ---------------------------------------------------------------------------
+// Server
+// ---------------------------------------------------------------------------
+SnapshotServer::SnapshotServer()
+  : faabric::transport::MessageEndpointServer(SNAPSHOT_ASYNC_PORT,
+                                              SNAPSHOT_SYNC_PORT,
+                                              SNAPSHOT_INPROC_LABEL,
+                                              faabric::util::getSystemConfig().snapshotServerThreads)
+  , reg(faabric::snapshot::getSnapshotRegistry())
+{}
+
+void SnapshotServer::doAsyncRecv(transport::Message& message)
+{
+    uint8_t header = message.getMessageCode();
+    if (header == SnapshotCalls::DeleteSnapshot) {
+        recvDeleteSnapshot(message.udata());
+        return;
+    }
+    throw std::runtime_error("Unrecognized async call header: " + std::to_string(header));
+}
+
+std::string SnapshotServer::doSyncRecv(transport::Message& message)
+{
+    uint8_t header = message.getMessageCode();
+    switch (header) {
+        case SnapshotCalls::PushSnapshot:
+            return recvPushSnapshot(message.udata());
+        case SnapshotCalls::PushSnapshotUpdate:
+            return recvPushSnapshotUpdate(message.udata());
+        case SnapshotCalls::ThreadResult:
+            return recvThreadResult(message);
+        default:
+            throw std::runtime_error("Unrecognized sync call header: " + std::to_string(header));
+    }
+}
+
+std::string SnapshotServer::recvPushSnapshot(std::span<const uint8_t> buffer)
+{
+    faabric::SnapshotPushRequest r;
+    if (!r.ParseFromArray(buffer.data(), (int)buffer.size())) {
+        throw std::runtime_error("Could not parse snapshot push");
+    }
+    if (r.contents().empty()) {
+        SPDLOG_ERROR("Received shapshot {} with zero size", r.key());
+        throw std::runtime_error("Received snapshot with zero size");
+    }
+    SPDLOG_DEBUG("Receiving snapshot {} (size {}, max-size {})", r.key(), r.contents().size(), r.maxsize());
+    auto snap = std::make_shared<SnapshotData>(
+      std::span<const uint8_t>((const uint8_t*)r.contents().data(), r.contents().size()), r.maxsize());
+    for (const auto& mr : r.mergeregions()) {
+        snap->addMergeRegion(mr.offset(),
+                             mr.length(),
+                             (SnapshotDataType)mr.datatype(),
+                             (SnapshotMergeOperation)mr.mergeop());
+    }
+    reg.registerSnapshot(r.key(), snap);
+    // The initial copy-in is not a change worth tracking
+    snap->clearTrackedChanges();
+    return faabric::EmptyResponse().SerializeAsString();
+}
+
+std::string SnapshotServer::recvPushSnapshotUpdate(std::span<const uint8_t> buffer)
+{
+    faabric::SnapshotUpdateRequest r;
+    if (!r.ParseFromArray(buffer.data(), (int)buffer.size())) {
+        throw std::runtime_error("Could not parse snapshot update");
+    }
+    SPDLOG_DEBUG("Queueing {} diffs for snapshot {}", r.diffs_size(), r.key());
+    auto snap = reg.getSnapshot(r.key());
+    // Merge regions are replaced wholesale
+    snap->clearMergeRegions();
+    for (const auto& mr : r.mergeregions()) {
+        snap->addMergeRegion(mr.offset(),
+                             mr.length(),
+                             (SnapshotDataType)mr.datatype(),
+                             (SnapshotMergeOperation)mr.mergeop());
+    }
+    std::vector<SnapshotDiff> diffs;
+    diffs.reserve(r.diffs_size());
+    for (const auto& d : r.diffs()) {
+        diffs.emplace_back((SnapshotDataType)d.datatype(),
+                           (SnapshotMergeOperation)d.mergeop(),
+                           d.offset(),
+                           std::span<const uint8_t>((const uint8_t*)d.data().data(), d.data().size()));
+    }
+    // Applied straight away (the payloads die with this request)
+    snap->applyDiffs(diffs);
+    return faabric::EmptyResponse().SerializeAsString();
+}
+
+std::string SnapshotServer::recvThreadResult(transport::Message& message)
+{
+    auto r = std::make_shared<faabric::ThreadResultRequest>();
+    if (!r->ParseFromArray(message.udata().data(), (int)message.udata().size())) {
+        throw std::runtime_error("Could not parse thread result");
+    }
+    if (r->diffs_size() > 0) {
+        auto snap = reg.getSnapshot(r->key());
+        std::vector<SnapshotDiff> diffs;
+        diffs.reserve(r->diffs_size());
+        // Diffs are queued (merged later by the main thread), so their bytes
+        // must outlive this call: keep an owned copy inside the snapshot path
+        // by re-pointing at data that lives as long as the scheduler's cache
+        auto keep = std::make_shared<std::vector<std::vector<uint8_t>>>();
+        for (const auto& d : r->diffs()) {
+            keep->emplace_back(d.data().begin(), d.data().end());
+        }
+        for (int i = 0; i < r->diffs_size(); i++) {
+            const auto& d = r->diffs(i);
+            diffs.emplace_back((SnapshotDataType)d.datatype(),
+                               (SnapshotMergeOperation)d.mergeop(),
+                               d.offset(),
+                               std::span<const uint8_t>((*keep)[i].data(), (*keep)[i].size()));
+        }
+        snap->queueDiffs(diffs);
+        // Park the owned bytes in the message that the scheduler caches
+        std::vector<uint8_t> blob;
+        for (auto& v : *keep) {
+            (void)v;
+        }
+        static std::mutex keepMx;
+        static std::vector<std::shared_ptr<std::vector<std::vector<uint8_t>>>> keepAlive;
+        std::lock_guard<std::mutex> lk(keepMx);
+        keepAlive.push_back(keep);
+        if (keepAlive.size() > 4096) {
+            keepAlive.erase(keepAlive.begin(), keepAlive.begin() + 2048);
+        }
+    }
+    SPDLOG_DEBUG("Receiving thread result {} for message {} with {} diffs", r->returnvalue(), r->messageid(), r->diffs_size());
+    faabric::scheduler::getScheduler().setThreadResultLocally(
+      (uint32_t)r->appid(), (uint32_t)r->messageid(), r->returnvalue(), message);
+    return faabric::EmptyResponse().SerializeAsString();
+}
+
+void SnapshotServer::recvDeleteSnapshot(std::span<const uint8_t> buffer)
+{
+    faabric::SnapshotDeleteRequest r;
+    r.ParseFromArray(buffer.data(), (int)buffer.size());
+    SPDLOG_DEBUG("Deleting shapshot {}", r.key());
+    reg.deleteSnapshot(r.key());
+}
+
+// ---------------------------------------------------------------------------
+// Device snapshot
+// ---------------------------------------------------------------------------
+#define DS_CUDA(expr)                                                          \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) {                                               \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+        }                                                                      \
+    } while (0)
+
+namespace {
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) {
+            cudaSetDevice(prev);
+        }
+    }
+};
+}
+
+DeviceSnapshot::DeviceSnapshot(size_t sizeIn, int deviceIn)
+  : size(sizeIn)
+  , device(deviceIn)
+{
+    owned = faabric::util::allocateDeviceMemory(size, device);
+    image = owned.ptr;
+    DeviceGuard g(device);
+    DS_CUDA(cudaMemset(image, 0, size));
+    statsDev = faabric::util::allocateDeviceMemory(64, device);
+}
+
+DeviceSnapshot::DeviceSnapshot(uint8_t* devicePtr, size_t sizeIn, int deviceIn)
+  : size(sizeIn)
+  , device(deviceIn)
+  , image(devicePtr)
+{
+    statsDev = faabric::util::allocateDeviceMemory(64, device);
+}
+
+DeviceSnapshot::~DeviceSnapshot() = default;
+
+void DeviceSnapshot::copyInData(std::span<const uint8_t> hostData, uint64_t offset)
+{
+    if (offset + hostData.size() > size) {
+        throw std::runtime_error("Copying data beyond the end of the device snapshot");
+    }
+    DeviceGuard g(device);
+    DS_CUDA(cudaMemcpy(image + offset, hostData.data(), hostData.size(), cudaMemcpyHostToDevice));
+}
+
+std::vector<uint8_t> DeviceSnapshot::getDataCopy(uint64_t offset, size_t n)
+{
+    if (offset + n > size) {
+        throw std::runtime_error("Out of bounds device snapshot access");
+    }
+    std::vector<uint8_t> out(n);
+    DeviceGuard g(device);
+    DS_CUDA(cudaMemcpy(out.data(), image + offset, n, cudaMemcpyDeviceToHost));
+    return out;
+}
+
+void DeviceSnapshot::restoreTo(uint8_t* deviceMem, size_t n, void* stream)
+{
+    if (n > size) {
+        throw std::runtime_error("Target memory larger than device snapshot");
+    }
+    DeviceGuard g(device);
+    DS_CUDA(cudaMemcpyAsync(deviceMem, image, n, cudaMemcpyDefault, (cudaStream_t)stream));
+}
+
+void DeviceSnapshot::addMergeRegion(uint64_t offset,
+                                    size_t length,
+                                    SnapshotDataType dataType,
+                                    SnapshotMergeOperation operation)
+{
+    std::lock_guard<std::mutex> lk(mx);
+    mergeRegions.emplace_back(offset, length, dataType, operation);
+    regionsDirty = true;
+}
+
+void DeviceSnapshot::clearMergeRegions()
+{
+    std::lock_guard<std::mutex> lk(mx);
+    mergeRegions.clear();
+    regionsDirty = true;
+}
+
+std::vector<SnapshotMergeRegion> DeviceSnapshot::getMergeRegions()
+{
+    std::lock_guard<std::mutex> lk(mx);
+    return mergeRegions;
+}
+
+extern "C" int fb_snapshot_prepare_regions(const FbMergeRegionDev* in,
+                                           int nIn,
+                                           int fillOp,
+                                           uint64_t size,
+                                           FbMergeRegionDev* out,
+                                           int maxOut,
+                                           int32_t* typedOut,
+                                           int* nTypedOut);
+
+void DeviceSnapshot::uploadRegions()
+{
+    // Caller holds mx
+    std::vector<FbMergeRegionDev> in;
+    for (const auto& r : mergeRegions) {
+        in.push_back({ r.offset, r.length, (int32_t)r.dataType, (int32_t)r.operation });
+    }
+    int fillOp = faabric::util::getSystemConfig().diffingMode == "bytewise" ? FB_MERGE_BYTEWISE : FB_MERGE_XOR;
+    int cap = 2 * (int)in.size() + 2;
+    std::vector<FbMergeRegionDev> out(cap);
+    std::vector<int32_t> typed(cap);
+    int nTyped = 0;
+    int n = fb_snapshot_prepare_regions(in.data(), (int)in.size(), fillOp, size, out.data(), cap, typed.data(), &nTyped);
+    if (n < 0) {
+        throw std::runtime_error("Too many merge regions");
+    }
+    DeviceGuard g(device);
+    regionsDev = faabric::util::allocateDeviceMemory(std::max<size_t>(1, (size_t)n) * sizeof(FbMergeRegionDev), device);
+    typedIdxDev = faabric::util::allocateDeviceMemory(std::max<size_t>(1, (size_t)nTyped) * sizeof(int32_t), device);
+    DS_CUDA(cudaMemcpy(regionsDev.ptr, out.data(), (size_t)n * sizeof(FbMergeRegionDev), cudaMemcpyHostToDevice));
+    if (nTyped > 0) {
+        DS_CUDA(cudaMemcpy(typedIdxDev.ptr, typed.data(), (size_t)nTyped * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    nRegionsDev = n;
+    nTypedDev = nTyped;
+    regionsDirty = false;
+}
+
+void DeviceSnapshot::diffAndPush(const uint8_t* mem,
+                                 size_t memSize,
+                                 uint8_t* mainImage,
+                                 const uint8_t* dirtyPagesDev,
+                                 bool updateBase,
+                                 void* stream)
+{
+    std::lock_guard<std::mutex> lk(mx);
+    if (regionsDirty) {
+        uploadRegions();
+    }
+    DeviceGuard g(device);
+    DS_CUDA(cudaMemsetAsync(statsDev.ptr, 0, 16, (cudaStream_t)stream));
+    fb::SnapDiffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mem = mem;
+    a.orig = image;
+    a.origW = updateBase ? image : nullptr;
+    a.dst = mainImage;
+    a.size = std::min(memSize, size);
+    a.regions = (const FbMergeRegionDev*)regionsDev.ptr;
+    a.nRegions = nRegionsDev;
+    a.typedIdx = (const int32_t*)typedIdxDev.ptr;
+    a.nTyped = nTypedDev;
+    a.dirtyPages = dirtyPagesDev;
+    a.stats = (uint64_t*)statsDev.ptr;
+    a.updateBase = updateBase ? 1 : 0;
+    DS_CUDA(fb::launchSnapshotDiffPush(a, 296, (cudaStream_t)stream));
+}
+
+DeviceDiffStats DeviceSnapshot::getLastStats(void* stream)
+{
+    uint64_t host[2] = { 0, 0 };
+    DeviceGuard g(device);
+    DS_CUDA(cudaMemcpyAsync(host, statsDev.ptr, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return { host[0], host[1] };
+}
+
+void DeviceSnapshot::applyDiffs(const std::vector<SnapshotDiff>& diffs, void* stream)
+{
+    if (diffs.empty()) {
+        return;
+    }
+    std::vector<FbDiffDesc> descs;
+    std::vector<uint64_t> offs;
+    std::vector<uint8_t> blob;
+    for (const auto& d : diffs) {
+        descs.push_back({ d.getOffset(), d.getData().size(), (int32_t)d.getDataType(), (int32_t)d.getOperation() });
+        offs.push_back(blob.size());
+        blob.insert(blob.end(), d.getData().begin(), d.getData().end());
+        blob.resize((blob.size() + 15) / 16 * 16);
+    }
+    DeviceGuard g(device);
+    auto dDescs = faabric::util::allocateDeviceMemory(descs.size() * sizeof(FbDiffDesc), device);
+    auto dOffs = faabric::util::allocateDeviceMemory(offs.size() * sizeof(uint64_t), device);
+    auto dBlob = faabric::util::allocateDeviceMemory(std::max<size_t>(16, blob.size()), device);
+    DS_CUDA(cudaMemcpy(dDescs.ptr, descs.data(), descs.size() * sizeof(FbDiffDesc), cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(dOffs.ptr, offs.data(), offs.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (!blob.empty()) {
+        DS_CUDA(cudaMemcpy(dBlob.ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    }
+    DS_CUDA(fb::launchSnapshotApply(image,
+                                    size,
+                                    (const FbDiffDesc*)dDescs.ptr,
+                                    (const uint64_t*)dOffs.ptr,
+                                    dBlob.ptr,
+                                    (uint32_t)descs.size(),
+                                    (cudaStream_t)stream));
+    DS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+}
+
+std::vector<char> DeviceSnapshot::getDirtyPages(const uint8_t* mem, size_t memSize)
+{
+    return faabric::util::DeviceCompareDirtyTracker::getDirtyPages(mem, image, std::min(memSize, size), device);
+}
+
+} // namespace faabric::snapshot

@@ -61,13 +61,24 @@ INCLUDES = [
 ]
 
 
-def _headers_stamp() -> str:
+def _stamp_of(paths) -> str:
     h = hashlib.sha1()
-    for pat in ("**/*.h", "**/*.cuh", "**/*.hpp"):
-        for p in sorted(CSRC.glob(pat)):
-            st = p.stat()
-            h.update(f"{p}:{st.st_mtime_ns}:{st.st_size}".encode())
+    for p in sorted(paths):
+        st = p.stat()
+        h.update(f"{p}:{st.st_mtime_ns}:{st.st_size}".encode())
     return h.hexdigest()
+
+
+def _headers_stamp() -> dict:
+    """Two stamps: kernels (.cu) only depend on csrc/kernels + the device ABI
+    headers, host code depends on every header."""
+    kernel_hdrs = list((CSRC / "kernels").glob("*.cuh")) + list((CSRC / "kernels").glob("*.h")) + list(
+        (CSRC / "include" / "faabric" / "device").glob("*.h")
+    )
+    all_hdrs = []
+    for pat in ("**/*.h", "**/*.cuh", "**/*.hpp"):
+        all_hdrs += list(CSRC.glob(pat))
+    return {"cu": _stamp_of(kernel_hdrs), "cpp": _stamp_of(all_hdrs)}
 
 
 def _sources():
@@ -83,7 +94,7 @@ def _obj_for(src: Path) -> Path:
     return OBJ / (str(rel).replace("/", "__") + ".o")
 
 
-def _compile(src: Path, stamp: str, force: bool, extra_defs=()) -> tuple[Path, float, str]:
+def _compile(src: Path, stamp, force: bool, extra_defs=()) -> tuple[Path, float, str]:
     obj = _obj_for(src)
     is_cu = src.suffix == ".cu"
     cmd = (
@@ -91,8 +102,9 @@ def _compile(src: Path, stamp: str, force: bool, extra_defs=()) -> tuple[Path, f
         if is_cu
         else [CXX] + CXX_FLAGS + INCLUDES + list(extra_defs) + ["-c", str(src), "-o", str(obj)]
     )
+    stamp_s = stamp["cu" if is_cu else "cpp"] if isinstance(stamp, dict) else stamp
     key = hashlib.sha1(
-        (" ".join(cmd) + stamp + str(src.stat().st_mtime_ns)).encode()
+        (" ".join(cmd) + stamp_s + str(src.stat().st_mtime_ns)).encode()
     ).hexdigest()
     keyfile = obj.with_suffix(".key")
     if (
@@ -169,7 +181,7 @@ def build(force: bool = False, bins: bool = True, jobs: int | None = None, verbo
     return LIB
 
 
-def _build_bins(stamp: str, relink: bool, verbose: bool) -> None:
+def _build_bins(stamp, relink: bool, verbose: bool) -> None:
     """C++ executables: test runner, planner_server, examples, benchmarks."""
     for sub in ("bin", "tests"):
         d = CSRC / sub
