@@ -73,6 +73,9 @@ class Executor
     virtual size_t getMaxMemorySize();
 
     // ---- GPU binding ----
+    // App this executor is currently working for (0 when idle)
+    int getCurrentAppId() const { return currentAppId.load(); }
+
     int getGpuIdx() const { return gpuIdx; }
 
     // Compute stream of this executor (cudaStream_t); nullptr without a GPU
@@ -128,6 +131,7 @@ class Executor
     std::atomic<bool> _isShutdown = false;
 
     std::atomic<int> batchCounter = 0;
+    std::atomic<int> currentAppId = 0;
 
     std::atomic<int> threadBatchCounter = 0;
 

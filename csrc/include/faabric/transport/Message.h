@@ -14,6 +14,8 @@ namespace faabric::transport {
 #define NO_HEADER 0
 #define HEADER_MSG_SIZE 16
 #define SHUTDOWN_HEADER 220
+// Sync response carrying the text of an exception thrown by the handler
+#define ERROR_HEADER 221
 static const std::vector<uint8_t> shutdownPayload = { 0, 0, 1, 1 };
 
 #define NO_SEQUENCE_NUM -1

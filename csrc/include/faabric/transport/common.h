@@ -43,6 +43,13 @@ struct HostAddress
 
 HostAddress parseHostAddress(const std::string& host);
 
+// Virtual host names (e.g. one per GPU of this box) served by another address
+void registerHostAlias(const std::string& alias, const std::string& realAddress);
+
+void clearHostAliases();
+
+std::string resolveHostAlias(const std::string& host);
+
 std::string makeHostAddress(const std::string& ip, int portOffset);
 
 // Address other workers use to reach this worker

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <deque>
 #include <span>
 #include <string>
 #include <vector>
@@ -209,6 +210,7 @@ class SnapshotData
     MemoryRegion data = nullptr;
 
     std::vector<SnapshotDiff> queuedDiffs;
+    std::deque<std::vector<uint8_t>> queuedDiffData;
 
     // offset -> end (exclusive)
     std::vector<std::pair<uint64_t, uint64_t>> trackedChanges;

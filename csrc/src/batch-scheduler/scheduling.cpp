@@ -19,14 +19,8 @@ SchedulingDecision::SchedulingDecision(uint32_t appIdIn, int32_t groupIdIn)
 
 bool SchedulingDecision::isSingleHost() const
 {
-    // An empty decision is trivially on one host
-    if (hosts.empty()) {
-        return true;
-    }
-    const std::string& thisHost = faabric::util::getSystemConfig().endpointHost;
-    return std::all_of(hosts.begin(), hosts.end(), [&](const std::string& h) {
-        return h == thisHost;
-    });
+    // All messages on the same host (an empty decision trivially so)
+    return std::set<std::string>(hosts.begin(), hosts.end()).size() <= 1;
 }
 
 void SchedulingDecision::addMessage(const std::string& host,

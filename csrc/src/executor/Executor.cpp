@@ -372,6 +372,7 @@ void Executor::executeTasks(std::vector<int> msgIdxs,
         restore(first.snapshotkey());
     }
 
+    currentAppId.store(first.appid());
     batchCounter.fetch_add(nMessages, std::memory_order_release);
     if (isThreads) {
         threadBatchCounter.fetch_add(nMessages, std::memory_order_release);
@@ -550,6 +551,7 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
                 }
             }
             lastExec = faabric::util::getGlobalClock().now();
+            currentAppId.store(0);
             releaseClaim();
         }
         if (!isThreads) {

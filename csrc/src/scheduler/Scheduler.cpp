@@ -217,8 +217,8 @@ void Scheduler::flushLocally()
 // ---------------------------------------------------------------------------
 static std::string executorKey(const faabric::Message& msg)
 {
-    // Executors are warm per (user/function, app)
-    return faabric::util::funcToString(msg, false) + ":" + std::to_string(msg.appid());
+    // Executors are warm per user/function and reused across apps
+    return faabric::util::funcToString(msg, false);
 }
 
 std::shared_ptr<faabric::executor::Executor> Scheduler::claimExecutor(
@@ -263,11 +263,23 @@ void Scheduler::executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req)
         }
     }
     if (isThreads) {
-        // All threads of a batch share one executor (and its memory)
+        // All threads of a batch share one executor (and its memory).  On the
+        // main host that is the executor already running the app's main
+        // function; elsewhere a fresh one is claimed and restored from the
+        // main thread's snapshot.
         faabric::Message& first = *req->mutable_messages(0);
         std::shared_ptr<faabric::executor::Executor> e;
         try {
-            e = claimExecutor(first, lock);
+            auto& candidates = executors[executorKey(first)];
+            for (auto& c : candidates) {
+                if (c->isExecuting() && c->getCurrentAppId() == first.appid()) {
+                    e = c;
+                    break;
+                }
+            }
+            if (e == nullptr) {
+                e = claimExecutor(first, lock);
+            }
         } catch (const std::exception& ex) {
             SPDLOG_ERROR("Failed to claim executor for {}: {}", faabric::util::funcToString(first, false), ex.what());
             lock.unlock();

@@ -377,33 +377,14 @@ std::string SnapshotServer::recvThreadResult(transport::Message& message)
         auto snap = reg.getSnapshot(r->key());
         std::vector<SnapshotDiff> diffs;
         diffs.reserve(r->diffs_size());
-        // Diffs are queued (merged later by the main thread), so their bytes
-        // must outlive this call: keep an owned copy inside the snapshot path
-        // by re-pointing at data that lives as long as the scheduler's cache
-        auto keep = std::make_shared<std::vector<std::vector<uint8_t>>>();
         for (const auto& d : r->diffs()) {
-            keep->emplace_back(d.data().begin(), d.data().end());
-        }
-        for (int i = 0; i < r->diffs_size(); i++) {
-            const auto& d = r->diffs(i);
             diffs.emplace_back((SnapshotDataType)d.datatype(),
                                (SnapshotMergeOperation)d.mergeop(),
                                d.offset(),
-                               std::span<const uint8_t>((*keep)[i].data(), (*keep)[i].size()));
+                               std::span<const uint8_t>((const uint8_t*)d.data().data(), d.data().size()));
         }
+        // Queued (merged later by the main thread); the queue copies the bytes
         snap->queueDiffs(diffs);
-        // Park the owned bytes in the message that the scheduler caches
-        std::vector<uint8_t> blob;
-        for (auto& v : *keep) {
-            (void)v;
-        }
-        static std::mutex keepMx;
-        static std::vector<std::shared_ptr<std::vector<std::vector<uint8_t>>>> keepAlive;
-        std::lock_guard<std::mutex> lk(keepMx);
-        keepAlive.push_back(keep);
-        if (keepAlive.size() > 4096) {
-            keepAlive.erase(keepAlive.begin(), keepAlive.begin() + 2048);
-        }
     }
     SPDLOG_DEBUG("Receiving thread result {} for message {} with {} diffs", r->returnvalue(), r->messageid(), r->diffs_size());
     faabric::scheduler::getScheduler().setThreadResultLocally(

@@ -1,3 +1,4 @@
+#include <algorithm>
 #include <faabric/transport/MessageEndpoint.h>
 #include <faabric/transport/MessageEndpointClient.h>
 #include <faabric/transport/MessageEndpointServer.h>
@@ -26,9 +27,35 @@ namespace faabric::transport {
 // ---------------------------------------------------------------------------
 // Addresses
 // ---------------------------------------------------------------------------
-HostAddress parseHostAddress(const std::string& host)
+// Virtual hosts: one worker process exposes each of its GPUs to the planner as
+// a separate "host" (gpu0..gpuN-1); the alias table routes them to the
+// process that really serves them.
+static std::shared_mutex aliasMx;
+static std::unordered_map<std::string, std::string> hostAliases;
+
+void registerHostAlias(const std::string& alias, const std::string& realAddress)
+{
+    std::unique_lock<std::shared_mutex> lk(aliasMx);
+    hostAliases[alias] = realAddress;
+}
+
+void clearHostAliases()
+{
+    std::unique_lock<std::shared_mutex> lk(aliasMx);
+    hostAliases.clear();
+}
+
+std::string resolveHostAlias(const std::string& host)
+{
+    std::shared_lock<std::shared_mutex> lk(aliasMx);
+    auto it = hostAliases.find(host);
+    return it == hostAliases.end() ? host : it->second;
+}
+
+HostAddress parseHostAddress(const std::string& hostIn)
 {
     HostAddress a;
+    std::string host = resolveHostAlias(hostIn);
     size_t colon = host.rfind(':');
     if (colon != std::string::npos &&
         faabric::util::stringIsInt(host.substr(colon + 1))) {
@@ -220,7 +247,11 @@ int SendMessageEndpoint::connectedFd()
             target = LOCALHOST;
         }
         auto s = std::make_unique<tcp::SendSocket>(target, port);
-        s->dial();
+        // Keep retrying while a peer may still be booting, but never for
+        // longer than this endpoint's own timeout
+        const int sleepMs = 100;
+        int retries = std::clamp(timeoutMs / sleepMs, 1, 60);
+        s->dial(retries, sleepMs);
         sock = std::move(s);
     }
     return sock->getFd();
@@ -301,6 +332,10 @@ Message SyncSendMessageEndpoint::sendAwaitResponse(uint8_t header,
     if (res.getResponseCode() != MessageResponseCode::SUCCESS) {
         dropConnection();
         throw std::runtime_error("Connection closed awaiting response from " + getAddress());
+    }
+    if (res.getMessageCode() == ERROR_HEADER) {
+        throw std::runtime_error("Remote handler on " + getAddress() + " failed: " +
+                                 std::string((const char*)res.udata().data(), res.size()));
     }
     return res;
 }
@@ -612,7 +647,12 @@ void MessageEndpointServerHandler::start(int timeoutMs)
                     if (!async && item->fd >= 0) {
                         // Always answer, or the client hangs until timeout
                         try {
-                            sendFrame(item->fd, NO_HEADER, nullptr, 0, NO_SEQUENCE_NUM);
+                            std::string what = e.what();
+                            sendFrame(item->fd,
+                                      ERROR_HEADER,
+                                      (const uint8_t*)what.data(),
+                                      what.size(),
+                                      NO_SEQUENCE_NUM);
                         } catch (...) {
                         }
                     }

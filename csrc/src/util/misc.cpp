@@ -259,6 +259,10 @@ int safeCopyToBuffer(const std::vector<uint8_t>& dataIn,
                      uint8_t* buffer,
                      int bufferLen)
 {
+    // A non-positive buffer length is a size query
+    if (bufferLen <= 0) {
+        return (int)dataIn.size();
+    }
     return safeCopyToBuffer(dataIn.data(), (int)dataIn.size(), buffer, bufferLen);
 }
 
@@ -275,7 +279,7 @@ int safeCopyToBuffer(const uint8_t* dataIn,
     if (n > 0) {
         memcpy(buffer, dataIn, (size_t)n);
     }
-    return dataLen;
+    return std::max(n, 0);
 }
 
 std::string byteArrayToHexString(const uint8_t* data, int dataSize)

@@ -501,8 +501,12 @@ size_t SnapshotData::getQueuedDiffsCount()
 
 void SnapshotData::queueDiffs(const std::vector<SnapshotDiff>& diffs)
 {
+    // The queue owns its payloads: callers (RPC handlers) may free theirs
     FullLock lock(snapMx);
-    queuedDiffs.insert(queuedDiffs.end(), diffs.begin(), diffs.end());
+    for (const auto& d : diffs) {
+        queuedDiffData.emplace_back(d.getData().begin(), d.getData().end());
+        queuedDiffs.emplace_back(d.getDataType(), d.getOperation(), d.getOffset(), queuedDiffData.back());
+    }
 }
 
 void SnapshotData::applyDiffs(const std::vector<SnapshotDiff>& diffs)
@@ -572,6 +576,7 @@ int SnapshotData::writeQueuedDiffs()
         applyDiffLocked(d);
     }
     queuedDiffs.clear();
+    queuedDiffData.clear();
     PROF_END(WriteQueuedDiffs)
     return n;
 }

@@ -1,0 +1,365 @@
+// Transport layer tests (strategy: reference tests/test/transport/*.cpp)
+#include "harness.h"
+
+#include <faabric/proto/faabric.pb.h>
+#include <faabric/transport/MessageEndpointClient.h>
+#include <faabric/transport/MessageEndpointServer.h>
+#include <faabric/transport/PointToPointBroker.h>
+#include <faabric/transport/PointToPointClient.h>
+#include <faabric/transport/PointToPointServer.h>
+#include <faabric/transport/common.h>
+#include <faabric/util/config.h>
+#include <faabric/util/gids.h>
+#include <faabric/util/network.h>
+#include <faabric/util/testing.h>
+
+#include <atomic>
+#include <thread>
+
+using namespace faabric::transport;
+
+namespace {
+const int TEST_ASYNC_PORT = 9711;
+const int TEST_SYNC_PORT = 9712;
+// Any 127/8 address is loopback but is not recognised as "this host", so it
+// forces the TCP path instead of the in-process fast path
+const char* TCP_HOST = "127.0.0.2";
+
+class EchoServer final : public MessageEndpointServer
+{
+  public:
+    EchoServer()
+      : MessageEndpointServer(TEST_ASYNC_PORT, TEST_SYNC_PORT, "test-echo", 3)
+    {}
+
+    std::atomic<int> asyncCount{ 0 };
+    std::atomic<uint64_t> asyncBytes{ 0 };
+    std::mutex mx;
+    std::vector<int> asyncCodes;
+    std::atomic<int> delayMs{ 0 };
+
+  protected:
+    void doAsyncRecv(Message& message) override
+    {
+        {
+            std::lock_guard<std::mutex> lk(mx);
+            asyncCodes.push_back(message.getMessageCode());
+        }
+        asyncBytes += message.size();
+        asyncCount++;
+    }
+
+    std::string doSyncRecv(Message& message) override
+    {
+        if (delayMs > 0) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(delayMs.load()));
+        }
+        if (message.getMessageCode() == 66) {
+            throw std::runtime_error("handler failure");
+        }
+        faabric::StatePart resp;
+        resp.set_key(std::string((const char*)message.udata().data(), message.size()));
+        resp.set_offset(message.getMessageCode());
+        return resp.SerializeAsString();
+    }
+};
+
+void exerciseEcho(const std::string& host)
+{
+    EchoServer server;
+    server.start();
+    {
+        MessageEndpointClient cli(host, TEST_ASYNC_PORT, TEST_SYNC_PORT);
+        // Sync round trip
+        std::string body = "hello there";
+        faabric::StatePart resp;
+        cli.syncSend(12, (const uint8_t*)body.data(), body.size(), &resp);
+        REQUIRE_EQ(resp.key(), body);
+        REQUIRE_EQ(resp.offset(), 12u);
+
+        // Async with a latch to await handling
+        server.setRequestLatch();
+        cli.asyncSend(5, (const uint8_t*)body.data(), body.size());
+        server.awaitRequestLatch();
+        REQUIRE_EQ(server.asyncCount.load(), 1);
+
+        // Large payload (16 MiB) both ways
+        std::vector<uint8_t> big((size_t)16 << 20);
+        for (size_t i = 0; i < big.size(); i += 4096) {
+            big[i] = (uint8_t)(i >> 12);
+        }
+        Message raw = cli.syncSendRaw(9, big.data(), big.size());
+        faabric::StatePart bigResp;
+        REQUIRE(bigResp.ParseFromArray(raw.udata().data(), (int)raw.size()));
+        REQUIRE_EQ(bigResp.key().size(), big.size());
+        REQUIRE_EQ((uint8_t)bigResp.key()[8192], (uint8_t)2);
+
+        // A handler exception surfaces as an error on the client and the
+        // connection stays usable
+        REQUIRE_THROWS(cli.syncSend(66, (const uint8_t*)body.data(), body.size(), &resp));
+        cli.syncSend(13, (const uint8_t*)body.data(), body.size(), &resp);
+        REQUIRE_EQ(resp.offset(), 13u);
+    }
+
+    // Many clients from many threads; per-client async ordering is preserved
+    std::vector<std::thread> ts;
+    std::atomic<int> ok{ 0 };
+    int before = server.asyncCount.load();
+    for (int t = 0; t < 6; t++) {
+        ts.emplace_back([&, t] {
+            MessageEndpointClient cli(host, TEST_ASYNC_PORT, TEST_SYNC_PORT);
+            for (int i = 0; i < 200; i++) {
+                std::string b = "t" + std::to_string(t) + "-" + std::to_string(i);
+                faabric::StatePart r;
+                cli.syncSend(1 + (i % 50), (const uint8_t*)b.data(), b.size(), &r);
+                if (r.key() == b) {
+                    ok++;
+                }
+                cli.asyncSend(100 + t, (const uint8_t*)b.data(), b.size());
+            }
+        });
+    }
+    for (auto& t : ts) {
+        t.join();
+    }
+    REQUIRE_EQ(ok.load(), 1200);
+    for (int i = 0; i < 500 && server.asyncCount.load() < before + 1200; i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+    REQUIRE_EQ(server.asyncCount.load(), before + 1200);
+    server.stop();
+    REQUIRE(!server.isStarted());
+    // Restartable
+    server.start();
+    {
+        MessageEndpointClient cli(host, TEST_ASYNC_PORT, TEST_SYNC_PORT);
+        faabric::StatePart r;
+        std::string b = "again";
+        cli.syncSend(3, (const uint8_t*)b.data(), b.size(), &r);
+        REQUIRE_EQ(r.key(), b);
+    }
+    server.stop();
+}
+}
+
+TEST_CASE("message endpoints over the in-process fast path", "[transport]")
+{
+    exerciseEcho(LOCALHOST);
+}
+
+TEST_CASE("message endpoints over TCP", "[transport]")
+{
+    exerciseEcho(TCP_HOST);
+}
+
+TEST_CASE("sync send times out on a slow server, fails without one", "[transport]")
+{
+    {
+        MessageEndpointClient cli(TCP_HOST, TEST_ASYNC_PORT, TEST_SYNC_PORT, 300);
+        faabric::StatePart r;
+        std::string b = "x";
+        REQUIRE_THROWS(cli.syncSend(1, (const uint8_t*)b.data(), b.size(), &r));
+    }
+    EchoServer server;
+    server.start();
+    server.delayMs = 600;
+    {
+        MessageEndpointClient cli(TCP_HOST, TEST_ASYNC_PORT, TEST_SYNC_PORT, 150);
+        faabric::StatePart r;
+        std::string b = "x";
+        REQUIRE_THROWS(cli.syncSend(1, (const uint8_t*)b.data(), b.size(), &r));
+    }
+    server.delayMs = 0;
+    server.stop();
+}
+
+TEST_CASE("host address parsing with port offsets", "[transport]")
+{
+    auto a = parseHostAddress("10.0.0.5");
+    REQUIRE_EQ(a.ip, std::string("10.0.0.5"));
+    REQUIRE_EQ(a.portOffset, 0);
+    auto b = parseHostAddress("10.0.0.5:300");
+    REQUIRE_EQ(b.ip, std::string("10.0.0.5"));
+    REQUIRE_EQ(b.portOffset, 300);
+    REQUIRE_EQ(makeHostAddress("h", 0), std::string("h"));
+    REQUIRE_EQ(makeHostAddress("h", 20), std::string("h:20"));
+}
+
+// ---------------------------------------------------------------------------
+// Point-to-point
+// ---------------------------------------------------------------------------
+namespace {
+struct PtpFixture
+{
+    PointToPointBroker& broker = getPointToPointBroker();
+    PointToPointServer server;
+    std::string thisHost = faabric::util::getSystemConfig().endpointHost;
+
+    PtpFixture()
+    {
+        broker.clear();
+        server.start();
+    }
+
+    ~PtpFixture()
+    {
+        server.stop();
+        broker.clear();
+        faabric::util::setMockMode(false);
+    }
+
+    faabric::batch_scheduler::SchedulingDecision localDecision(int appId, int groupId, int n)
+    {
+        faabric::batch_scheduler::SchedulingDecision d(appId, groupId);
+        for (int i = 0; i < n; i++) {
+            d.addMessage(thisHost, faabric::util::generateGid(), i, i);
+        }
+        return d;
+    }
+};
+}
+
+TEST_CASE("ptp: mappings, send/recv and ordering", "[transport][ptp]")
+{
+    PtpFixture f;
+    int appId = 111, groupId = 222;
+    auto decision = f.localDecision(appId, groupId, 4);
+    f.broker.setAndSendMappingsFromSchedulingDecision(decision);
+    f.broker.waitForMappingsOnThisHost(groupId);
+    REQUIRE_EQ(f.broker.getIdxsRegisteredForGroup(groupId).size(), 4u);
+    REQUIRE_EQ(f.broker.getHostForReceiver(groupId, 3), f.thisHost);
+    REQUIRE(PointToPointGroup::groupExists(groupId));
+    REQUIRE_THROWS(f.broker.getHostForReceiver(groupId, 9));
+
+    std::vector<uint8_t> a = { 1, 2, 3 }, b = { 4, 5 };
+    f.broker.sendMessage(groupId, 0, 1, a.data(), a.size());
+    f.broker.sendMessage(groupId, 0, 1, b.data(), b.size());
+    f.broker.sendMessage(groupId, 2, 1, b.data(), b.size());
+    REQUIRE(f.broker.recvMessage(groupId, 0, 1) == a);
+    REQUIRE(f.broker.recvMessage(groupId, 2, 1) == b);
+    REQUIRE(f.broker.recvMessage(groupId, 0, 1) == b);
+
+    // Ordered delivery: deliver out of order, receive in order
+    std::vector<uint8_t> m0 = { 0 }, m1 = { 1 }, m2 = { 2 };
+    f.broker.deliverLocally(groupId, 3, 0, m2.data(), 1, 2);
+    f.broker.deliverLocally(groupId, 3, 0, m0.data(), 1, 0);
+    f.broker.deliverLocally(groupId, 3, 0, m1.data(), 1, 1);
+    REQUIRE(f.broker.recvMessage(groupId, 3, 0, true) == m0);
+    REQUIRE(f.broker.recvMessage(groupId, 3, 0, true) == m1);
+    REQUIRE(f.broker.recvMessage(groupId, 3, 0, true) == m2);
+
+    // Cross-thread stream
+    std::thread sender([&] {
+        for (int i = 0; i < 500; i++) {
+            f.broker.sendMessage(groupId, 1, 2, (const uint8_t*)&i, sizeof(int), true);
+        }
+        f.broker.resetThreadLocalCache();
+    });
+    for (int i = 0; i < 500; i++) {
+        auto m = f.broker.recvMessage(groupId, 1, 2, true);
+        REQUIRE_EQ(*(int*)m.data(), i);
+    }
+    sender.join();
+    f.broker.clearGroup(groupId);
+    REQUIRE_EQ(f.broker.getIdxsRegisteredForGroup(groupId).size(), 0u);
+}
+
+TEST_CASE("ptp: remote hosts get their mappings (mocked)", "[transport][ptp]")
+{
+    PtpFixture f;
+    faabric::util::setMockMode(true);
+    clearSentMessages();
+    int appId = 5, groupId = 6;
+    faabric::batch_scheduler::SchedulingDecision d(appId, groupId);
+    d.addMessage(f.thisHost, 1, 0, 0);
+    d.addMessage("hostB", 2, 1, 1);
+    d.addMessage("hostC", 3, 2, 2);
+    d.addMessage("hostB", 4, 3, 3);
+    f.broker.setAndSendMappingsFromSchedulingDecision(d);
+    auto sent = getSentMappings();
+    REQUIRE_EQ(sent.size(), 2u);
+    std::set<std::string> hosts;
+    for (auto& [host, mappings] : sent) {
+        hosts.insert(host);
+        REQUIRE_EQ(mappings.appid(), appId);
+        REQUIRE_EQ(mappings.groupid(), groupId);
+        REQUIRE_EQ(mappings.mappings_size(), 4);
+    }
+    REQUIRE(hosts == (std::set<std::string>{ "hostB", "hostC" }));
+    REQUIRE_EQ(f.broker.getHostForReceiver(groupId, 2), std::string("hostC"));
+
+    // Remote send is routed through the client
+    std::vector<uint8_t> payload = { 9, 9 };
+    f.broker.sendMessage(groupId, 0, 2, payload.data(), payload.size());
+    auto msgs = getSentPointToPointMessages();
+    REQUIRE_EQ(msgs.size(), 1u);
+    REQUIRE_EQ(msgs[0].first, std::string("hostC"));
+    REQUIRE_EQ(msgs[0].second.recvidx(), 2);
+
+    // Migration updates one mapping
+    f.broker.updateHostForIdx(groupId, 2, "hostD");
+    REQUIRE_EQ(f.broker.getHostForReceiver(groupId, 2), std::string("hostD"));
+    clearSentMessages();
+}
+
+TEST_CASE("ptp: group locks, barrier and notify", "[transport][ptp]")
+{
+    PtpFixture f;
+    int appId = 31, groupId = 32, n = 6;
+    auto decision = f.localDecision(appId, groupId, n);
+    f.broker.setAndSendMappingsFromSchedulingDecision(decision);
+    auto group = PointToPointGroup::getGroup(groupId);
+
+    // Mutual exclusion
+    int counter = 0;
+    std::atomic<int> barrierPhase{ 0 };
+    std::vector<std::thread> ts;
+    std::atomic<bool> failed{ false };
+    for (int i = 0; i < n; i++) {
+        ts.emplace_back([&, i] {
+            try {
+                for (int r = 0; r < 50; r++) {
+                    group->lock(i, false);
+                    int v = counter;
+                    std::this_thread::yield();
+                    counter = v + 1;
+                    group->unlock(i, false);
+                }
+                for (int r = 0; r < 5; r++) {
+                    barrierPhase++;
+                    group->barrier(i);
+                    if (barrierPhase.load() < (r + 1) * n) {
+                        failed = true;
+                    }
+                    group->barrier(i);
+                }
+                if (i != POINT_TO_POINT_MAIN_IDX) {
+                    group->notify(i);
+                }
+            } catch (std::exception& e) {
+                printf("ptp thread %d failed: %s\n", i, e.what());
+                failed = true;
+            }
+            f.broker.resetThreadLocalCache();
+        });
+    }
+    // Main awaits everyone's notification
+    group->notify(POINT_TO_POINT_MAIN_IDX);
+    for (auto& t : ts) {
+        t.join();
+    }
+    REQUIRE(!failed.load());
+    REQUIRE_EQ(counter, n * 50);
+
+    // Recursive lock
+    group->lock(2, true);
+    group->lock(2, true);
+    REQUIRE_EQ(group->getLockOwner(true), 2);
+    group->unlock(2, true);
+    group->unlock(2, true);
+    REQUIRE_EQ(group->getLockOwner(true), NO_LOCK_OWNER_IDX);
+
+    REQUIRE(group->localTryLock());
+    REQUIRE(!group->localTryLock());
+    group->localUnlock();
+}
