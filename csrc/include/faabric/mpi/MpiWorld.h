@@ -85,6 +85,9 @@ class MpiWorld
                           int* periods,
                           int* coords);
 
+    // False if no grid has been set up yet
+    bool getCartesianDims(int* dims2) const;
+
     void getRankFromCoords(int* rank, int* coords);
 
     void shiftCartesianCoords(int rank,
@@ -265,6 +268,8 @@ class MpiWorld
     std::mutex worldMx;
     int groupId = -1;
     std::vector<std::string> hostForRank;
+    // As scheduled (may be a per-GPU alias of this host)
+    std::vector<std::string> virtualHostForRank;
     std::vector<int> portForRank;
     std::map<std::string, std::set<int>> ranksForHost;
     // lowest rank on each host acts as its leader in two-level collectives

@@ -3,6 +3,7 @@
 #include <faabric/mpi/MpiWorld.h>
 #include <faabric/planner/PlannerClient.h>
 #include <faabric/transport/common.h>
+#include <faabric/util/network.h>
 #include <faabric/util/batch.h>
 #include <faabric/util/config.h>
 #include <faabric/util/environment.h>
@@ -54,6 +55,8 @@ struct RankState
     std::map<int, AsyncRequest> requests;
     // sendRank -> request ids of outstanding irecvs, in posting order
     std::map<int, std::deque<int>> pendingIrecvs;
+    // sendRank -> messages taken off the wire by a probe, not yet received
+    std::map<int, std::deque<MpiMessage>> probed;
 
     void reset()
     {
@@ -66,6 +69,7 @@ struct RankState
         sendSockets.clear();
         requests.clear();
         pendingIrecvs.clear();
+        probed.clear();
         nextRequestId = 1;
     }
 };
@@ -333,6 +337,7 @@ void MpiWorld::initLocalRemoteLeaders()
 {
     std::lock_guard<std::mutex> lk(worldMx);
     hostForRank.assign(size, "");
+    virtualHostForRank.assign(size, "");
     portForRank.assign(size, 0);
     ranksForHost.clear();
     leaderForHost.clear();
@@ -345,8 +350,12 @@ void MpiWorld::initLocalRemoteLeaders()
             continue;
         }
         std::string host = broker.getHostForReceiver(groupId, rank);
-        // In tests all ranks are "local" even though they are registered under
-        // the real address
+        // Virtual per-GPU hosts served by this very process are local ranks;
+        // the virtual name still picks the rank's GPU
+        virtualHostForRank[rank] = host;
+        if (host != thisHost && faabric::transport::resolveHostAlias(host) == thisHost) {
+            host = thisHost;
+        }
         hostForRank[rank] = host;
         portForRank[rank] = broker.getMpiPortForReceiver(groupId, rank);
         ranksForHost[host].insert(rank);
@@ -614,6 +623,11 @@ int MpiWorld::isend(int sendRank,
 
 MpiMessage MpiWorld::internalRecv(int sendRank, int recvRank)
 {
+    if (auto it = tls.probed.find(sendRank); it != tls.probed.end() && !it->second.empty()) {
+        MpiMessage m = it->second.front();
+        it->second.pop_front();
+        return m;
+    }
     if (getHostForRank(sendRank) == thisHost || thisHost == getHostForRank(recvRank)) {
         if (getHostForRank(sendRank) == thisHost) {
             return getLocalQueue(sendRank, recvRank)
@@ -769,8 +783,24 @@ void MpiWorld::sendRecv(uint8_t* sendBuffer,
 
 void MpiWorld::probe(int sendRank, int recvRank, MPI_Status* status)
 {
-    // Peeking a multi-producer ring is not supported (the reference throws too)
-    throw std::runtime_error("Probe not supported");
+    // (The reference leaves this unimplemented.)  The next message of the
+    // pair is taken off the queue / wire and parked until the matching recv.
+    checkRanksRange(sendRank, recvRank);
+    if (!tls.pendingIrecvs[sendRank].empty()) {
+        drainPendingFor(sendRank, recvRank, -1);
+    }
+    auto& parked = tls.probed[sendRank];
+    if (parked.empty()) {
+        MpiMessage m = internalRecv(sendRank, recvRank);
+        parked.push_back(m);
+    }
+    const MpiMessage& next = parked.front();
+    if (status != nullptr) {
+        status->MPI_SOURCE = next.sendRank;
+        status->MPI_ERROR = MPI_SUCCESS;
+        status->MPI_TAG = -1;
+        status->bytesSize = (int)payloadSize(next);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -820,7 +850,9 @@ void MpiWorld::ensureDeviceComms()
         if (allLocal) {
             std::vector<int> devices(size);
             for (int r = 0; r < size; r++) {
-                devices[r] = faabric::util::gpuForRank(r);
+                int fromHost = faabric::util::gpuIndexFromHostName(virtualHostForRank[r]);
+                devices[r] = fromHost >= 0 ? fromHost % std::max(1, faabric::device::cudaDeviceCountSafe())
+                                           : faabric::util::gpuForRank(r);
             }
             deviceComms = faabric::device::Communicator::createLocal(size, devices, cfg);
             SPDLOG_INFO("MPI world {}: device communicators up ({} ranks, backing {})", id, size, deviceComms[0]->backing());
@@ -1715,6 +1747,16 @@ void MpiWorld::getCartesianRank(int rank, int maxDims, const int* dims, int* per
         coords[i] = 0;
         periods[i] = 1;
     }
+}
+
+bool MpiWorld::getCartesianDims(int* dims2) const
+{
+    if (cartDims[0] <= 0 || cartDims[1] <= 0) {
+        return false;
+    }
+    dims2[0] = cartDims[0];
+    dims2[1] = cartDims[1];
+    return true;
 }
 
 void MpiWorld::getRankFromCoords(int* rank, int* coords)

@@ -61,6 +61,19 @@ const void* resolveInPlace(const void* sendbuf, void* recvbuf)
     return sendbuf == MPI_IN_PLACE ? recvbuf : sendbuf;
 }
 
+// Host<->host copies must not depend on a CUDA device being present
+static void copyAny(void* dst, const void* src, size_t bytes)
+{
+    if (bytes == 0 || dst == src) {
+        return;
+    }
+    if (MpiWorld::isDevicePointer(dst) || MpiWorld::isDevicePointer(src)) {
+        cudaMemcpy(dst, src, bytes, cudaMemcpyDefault);
+    } else {
+        memcpy(dst, src, bytes);
+    }
+}
+
 std::map<int, faabric_request_t*>& requestTable()
 {
     static thread_local std::map<int, faabric_request_t*> t;
@@ -265,7 +278,9 @@ int MPI_Get_count(const MPI_Status* status, MPI_Datatype datatype, int* count)
 
 int MPI_Probe(int source, int tag, MPI_Comm comm, MPI_Status* status)
 {
-    throw std::runtime_error("MPI_Probe not implemented!");
+    SPDLOG_TRACE("MPI - MPI_Probe");
+    getExecutingWorld().probe(source, executingContext.getRank(), status);
+    return MPI_SUCCESS;
 }
 
 int MPI_Barrier(MPI_Comm comm)
@@ -319,7 +334,7 @@ int MPI_Gatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void*
             uint8_t* dst = (uint8_t*)recvbuf + (size_t)displs[r] * recvtype->size;
             if (r == root) {
                 if (sendbuf != MPI_IN_PLACE) {
-                    cudaMemcpy(dst, sendbuf, (size_t)sendcount * sendtype->size, cudaMemcpyDefault);
+                    copyAny(dst, sendbuf, (size_t)sendcount * sendtype->size);
                 }
             } else {
                 world.recv(r, root, dst, recvtype, recvcounts[r], nullptr, MpiMessageType::GATHER);
@@ -437,7 +452,7 @@ int MPI_Alltoallv(const void* sendbuf, const int sendcounts[], const int sdispls
         uint8_t* dst = (uint8_t*)recvbuf + (size_t)rdispls[r] * recvtype->size;
         const uint8_t* src = (const uint8_t*)sendbuf + (size_t)sdispls[r] * sendtype->size;
         if (r == rank) {
-            cudaMemcpy(dst, src, (size_t)sendcounts[r] * sendtype->size, cudaMemcpyDefault);
+            copyAny(dst, src, (size_t)sendcounts[r] * sendtype->size);
         } else {
             reqs.push_back(world.irecv(r, rank, dst, recvtype, recvcounts[r], MpiMessageType::ALLTOALL));
         }
@@ -482,7 +497,19 @@ int MPI_Cart_get(MPI_Comm comm, int maxdims, int dims[], int periods[], int coor
         SPDLOG_ERROR("Unexpected number of max. dimensions: {}", maxdims);
         throw std::runtime_error("Bad dimensions in MPI_Cart_get");
     }
-    getExecutingWorld().getCartesianRank(executingContext.getRank(), maxdims, dims, periods, coords);
+    // The grid set by MPI_Cart_create is authoritative; before that the caller's
+    // dims are taken as input (what the reference does)
+    auto& world = getExecutingWorld();
+    std::vector<int> d(std::max(maxdims, 2), 1);
+    std::vector<int> p(std::max(maxdims, 2), 1);
+    std::vector<int> c(std::max(maxdims, 2), 0);
+    if (!world.getCartesianDims(d.data())) {
+        std::copy(dims, dims + maxdims, d.begin());
+    }
+    world.getCartesianRank(executingContext.getRank(), maxdims, d.data(), p.data(), c.data());
+    std::copy(d.begin(), d.begin() + maxdims, dims);
+    std::copy(p.begin(), p.begin() + maxdims, periods);
+    std::copy(c.begin(), c.begin() + maxdims, coords);
     return MPI_SUCCESS;
 }
 

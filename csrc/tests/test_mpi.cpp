@@ -1,0 +1,334 @@
+// MPI tests: every rank runs as a real function scheduled by the planner and
+// talks through the C API (strategy: reference tests/test/mpi/*.cpp and the
+// dist-test functions in tests/dist/mpi/examples).
+#include "fixtures.h"
+
+#include <faabric/mpi/MpiWorldRegistry.h>
+#include <faabric/mpi/mpi.h>
+
+#include <numeric>
+
+using namespace tests;
+
+namespace {
+typedef std::function<int(int rank, int size)> RankBody;
+
+#define CHECK_RANK(cond)                                                       \
+    do {                                                                       \
+        if (!(cond)) {                                                         \
+            printf("         rank %d: check failed at line %d: %s\n", rank, __LINE__, #cond); \
+            return 1;                                                          \
+        }                                                                      \
+    } while (0)
+
+// Runs `body` on `worldSize` ranks spread over `nHosts` virtual hosts
+void runMpi(const std::string& name, int worldSize, int nHosts, const RankBody& body)
+{
+    // ceil(worldSize / nHosts) slots per host so the world spans all hosts
+    int perHost = (worldSize + nHosts - 1) / nHosts;
+    ClusterFixture f(nHosts == 1 ? worldSize : 0, nHosts == 1 ? 0 : nHosts, perHost);
+    registerTestFunction("mpi", name, [&](auto*, int, int, auto) {
+        MPI_Init(nullptr, nullptr);
+        int rank = -1, size = -1;
+        MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+        MPI_Comm_size(MPI_COMM_WORLD, &size);
+        int rc = body(rank, size);
+        MPI_Finalize();
+        return rc;
+    });
+    auto req = faabric::util::batchExecFactory("mpi", name, 1);
+    auto& msg = *req->mutable_messages(0);
+    msg.set_ismpi(true);
+    msg.set_mpiworldsize(worldSize);
+    auto decision = f.plannerCli.callFunctions(req);
+    REQUIRE_EQ(decision.nFunctions, 1);
+    auto status = f.awaitBatch(req, 30000);
+    REQUIRE_EQ(status->messageresults_size(), worldSize);
+    std::set<int> ranks;
+    std::set<std::string> hosts;
+    for (auto& m : status->messageresults()) {
+        if (m.returnvalue() != 0) {
+            fbtest::fail(__FILE__, __LINE__, name + ": rank " + std::to_string(m.mpirank()) + " failed: " + m.outputdata());
+        }
+        ranks.insert(m.mpirank());
+        hosts.insert(m.executedhost());
+    }
+    REQUIRE_EQ((int)ranks.size(), worldSize);
+    REQUIRE_EQ((int)hosts.size(), nHosts);
+    faabric::mpi::getMpiWorldRegistry().clear();
+}
+
+int bodyPointToPoint(int rank, int size)
+{
+    MPI_Status status{};
+    // Ring with blocking send/recv (even/odd ordering)
+    int right = (rank + 1) % size, left = (rank + size - 1) % size;
+    int token = rank * 10, got = -1;
+    if (rank % 2 == 0) {
+        MPI_Send(&token, 1, MPI_INT, right, 0, MPI_COMM_WORLD);
+        MPI_Recv(&got, 1, MPI_INT, left, 0, MPI_COMM_WORLD, &status);
+    } else {
+        MPI_Recv(&got, 1, MPI_INT, left, 0, MPI_COMM_WORLD, &status);
+        MPI_Send(&token, 1, MPI_INT, right, 0, MPI_COMM_WORLD);
+    }
+    CHECK_RANK(got == left * 10);
+    CHECK_RANK(status.MPI_SOURCE == left);
+    int count = 0;
+    MPI_Get_count(&status, MPI_INT, &count);
+    CHECK_RANK(count == 1);
+
+    // Sendrecv ring with bigger payloads
+    std::vector<double> out(1000, rank + 0.5), in(1000, -1);
+    MPI_Sendrecv(out.data(), 1000, MPI_DOUBLE, right, 0, in.data(), 1000, MPI_DOUBLE, left, 0, MPI_COMM_WORLD, &status);
+    CHECK_RANK(in[0] == left + 0.5 && in[999] == left + 0.5);
+
+    // Non-blocking all-pairs exchange
+    std::vector<int> sendVals(size), recvVals(size, -1);
+    std::vector<MPI_Request> reqs;
+    for (int r = 0; r < size; r++) {
+        if (r == rank) {
+            continue;
+        }
+        sendVals[r] = rank * 100 + r;
+        MPI_Request rq;
+        MPI_Irecv(&recvVals[r], 1, MPI_INT, r, 0, MPI_COMM_WORLD, &rq);
+        reqs.push_back(rq);
+    }
+    for (int r = 0; r < size; r++) {
+        if (r == rank) {
+            continue;
+        }
+        MPI_Request rq;
+        MPI_Isend(&sendVals[r], 1, MPI_INT, r, 0, MPI_COMM_WORLD, &rq);
+        reqs.push_back(rq);
+    }
+    MPI_Waitall((int)reqs.size(), reqs.data(), MPI_STATUSES_IGNORE);
+    for (int r = 0; r < size; r++) {
+        if (r != rank) {
+            CHECK_RANK(recvVals[r] == r * 100 + rank);
+        }
+    }
+
+    // Probe reports the pending message's size
+    if (rank == 0) {
+        std::vector<long> big(77, 5);
+        MPI_Send(big.data(), 77, MPI_LONG, 1, 0, MPI_COMM_WORLD);
+    } else if (rank == 1) {
+        MPI_Probe(0, 0, MPI_COMM_WORLD, &status);
+        MPI_Get_count(&status, MPI_LONG, &count);
+        CHECK_RANK(count == 77);
+        std::vector<long> big(77, 0);
+        MPI_Recv(big.data(), 77, MPI_LONG, 0, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+        CHECK_RANK(big[76] == 5);
+    }
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+
+int bodyCollectives(int rank, int size)
+{
+    // Broadcast from a non-zero root
+    int root = size - 1;
+    std::vector<int> bc(300, rank == root ? 7 : 0);
+    MPI_Bcast(bc.data(), 300, MPI_INT, root, MPI_COMM_WORLD);
+    CHECK_RANK(bc[0] == 7 && bc[299] == 7);
+
+    // Scatter / gather
+    const int per = 4;
+    std::vector<int> all(per * size), mine(per, -1);
+    if (rank == 1) {
+        std::iota(all.begin(), all.end(), 0);
+    }
+    MPI_Scatter(all.data(), per, MPI_INT, mine.data(), per, MPI_INT, 1, MPI_COMM_WORLD);
+    for (int i = 0; i < per; i++) {
+        CHECK_RANK(mine[i] == rank * per + i);
+        mine[i] *= 2;
+    }
+    std::vector<int> gathered(per * size, -1);
+    MPI_Gather(mine.data(), per, MPI_INT, gathered.data(), per, MPI_INT, 0, MPI_COMM_WORLD);
+    if (rank == 0) {
+        for (int i = 0; i < per * size; i++) {
+            CHECK_RANK(gathered[i] == 2 * i);
+        }
+    }
+
+    // Allgather
+    std::vector<int> ag(2 * size, -1);
+    int pair[2] = { rank, rank * rank };
+    MPI_Allgather(pair, 2, MPI_INT, ag.data(), 2, MPI_INT, MPI_COMM_WORLD);
+    for (int r = 0; r < size; r++) {
+        CHECK_RANK(ag[2 * r] == r && ag[2 * r + 1] == r * r);
+    }
+
+    // Reduce + Allreduce over several types and ops
+    {
+        std::vector<int> v(50, rank + 1), res(50, 0);
+        MPI_Reduce(v.data(), res.data(), 50, MPI_INT, MPI_SUM, 2 % size, MPI_COMM_WORLD);
+        if (rank == 2 % size) {
+            CHECK_RANK(res[49] == size * (size + 1) / 2);
+        }
+        MPI_Allreduce(v.data(), res.data(), 50, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
+        CHECK_RANK(res[0] == size);
+        MPI_Allreduce(v.data(), res.data(), 50, MPI_INT, MPI_MIN, MPI_COMM_WORLD);
+        CHECK_RANK(res[0] == 1);
+        // In place
+        MPI_Allreduce(MPI_IN_PLACE, v.data(), 50, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        CHECK_RANK(v[10] == size * (size + 1) / 2);
+    }
+    {
+        std::vector<double> v(33, 0.5 * (rank + 1)), res(33, 0);
+        MPI_Allreduce(v.data(), res.data(), 33, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+        CHECK_RANK(std::fabs(res[32] - 0.25 * size * (size + 1)) < 1e-9);
+        std::vector<long long> lv(5, 2), lres(5, 0);
+        MPI_Allreduce(lv.data(), lres.data(), 5, MPI_LONG_LONG, MPI_PROD, MPI_COMM_WORLD);
+        CHECK_RANK(lres[0] == (1LL << size));
+        std::vector<float> fv(9, (float)rank), fres(9, 0);
+        MPI_Allreduce(fv.data(), fres.data(), 9, MPI_FLOAT, MPI_MAX, MPI_COMM_WORLD);
+        CHECK_RANK(fres[8] == (float)(size - 1));
+    }
+
+    // Scan (inclusive prefix sum)
+    int sv = rank + 1, sres = 0;
+    MPI_Scan(&sv, &sres, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+    CHECK_RANK(sres == (rank + 1) * (rank + 2) / 2);
+
+    // Alltoall
+    std::vector<int> a2aSend(2 * size), a2aRecv(2 * size, -1);
+    for (int r = 0; r < size; r++) {
+        a2aSend[2 * r] = rank * 1000 + r;
+        a2aSend[2 * r + 1] = -(rank * 1000 + r);
+    }
+    MPI_Alltoall(a2aSend.data(), 2, MPI_INT, a2aRecv.data(), 2, MPI_INT, MPI_COMM_WORLD);
+    for (int r = 0; r < size; r++) {
+        CHECK_RANK(a2aRecv[2 * r] == r * 1000 + rank);
+        CHECK_RANK(a2aRecv[2 * r + 1] == -(r * 1000 + rank));
+    }
+
+    // Reduce_scatter
+    std::vector<int> rsIn(3 * size), rsOut(3, 0), counts(size, 3);
+    for (int i = 0; i < 3 * size; i++) {
+        rsIn[i] = i + rank;
+    }
+    MPI_Reduce_scatter(rsIn.data(), rsOut.data(), counts.data(), MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+    for (int i = 0; i < 3; i++) {
+        int idx = rank * 3 + i;
+        CHECK_RANK(rsOut[i] == idx * size + size * (size - 1) / 2);
+    }
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+
+int bodyMisc(int rank, int size)
+{
+    int flag = 0;
+    MPI_Initialized(&flag);
+    CHECK_RANK(flag == 1);
+    int tsize = 0;
+    MPI_Type_size(MPI_DOUBLE, &tsize);
+    CHECK_RANK(tsize == 8);
+    MPI_Type_size(MPI_LONG_LONG, &tsize);
+    CHECK_RANK(tsize == 8);
+    MPI_Type_size(MPI_CHAR, &tsize);
+    CHECK_RANK(tsize == 1);
+    double t0 = MPI_Wtime();
+    CHECK_RANK(t0 >= 0);
+    char name[MPI_MAX_PROCESSOR_NAME];
+    int len = 0;
+    MPI_Get_processor_name(name, &len);
+    CHECK_RANK(len > 0);
+
+    // 2D periodic cartesian grid
+    int side = 1;
+    while ((side + 1) * (side + 1) <= size) {
+        side++;
+    }
+    if (side * side == size) {
+        int dims[2] = { side, side }, periods[2] = { 1, 1 };
+        MPI_Comm cart;
+        CHECK_RANK(MPI_Cart_create(MPI_COMM_WORLD, 2, dims, periods, 0, &cart) == MPI_SUCCESS);
+        int coords[2], gotDims[2], gotPeriods[2];
+        MPI_Cart_get(cart, 2, gotDims, gotPeriods, coords);
+        CHECK_RANK(coords[0] == rank / side && coords[1] == rank % side);
+        int back = -1;
+        MPI_Cart_rank(cart, coords, &back);
+        CHECK_RANK(back == rank);
+        int src = -1, dst = -1;
+        MPI_Cart_shift(cart, 1, 1, &src, &dst);
+        CHECK_RANK(dst == (rank / side) * side + (rank % side + 1) % side);
+        CHECK_RANK(src == (rank / side) * side + (rank % side + side - 1) % side);
+        MPI_Cart_shift(cart, 0, 1, &src, &dst);
+        CHECK_RANK(dst == ((rank / side + 1) % side) * side + rank % side);
+    }
+
+    // User-allocated memory and gatherv
+    int* mem = nullptr;
+    MPI_Alloc_mem(64 * sizeof(int), MPI_INFO_NULL, &mem);
+    CHECK_RANK(mem != nullptr);
+    mem[63] = rank;
+    std::vector<int> recvCounts(size), displs(size);
+    int total = 0;
+    for (int r = 0; r < size; r++) {
+        recvCounts[r] = r + 1;
+        displs[r] = total;
+        total += r + 1;
+    }
+    std::vector<int> mineV(rank + 1, rank), allV(total, -1);
+    MPI_Allgatherv(mineV.data(), rank + 1, MPI_INT, allV.data(), recvCounts.data(), displs.data(), MPI_INT, MPI_COMM_WORLD);
+    for (int r = 0; r < size; r++) {
+        for (int i = 0; i < r + 1; i++) {
+            CHECK_RANK(allV[displs[r] + i] == r);
+        }
+    }
+    MPI_Free_mem(mem);
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+
+// The BASELINE workloads: ping-pong and a burst of int32 all-reduces
+int bodyPingPongAndAllreduce(int rank, int size)
+{
+    std::vector<uint8_t> buf(8192, (uint8_t)rank);
+    for (int i = 0; i < 200; i++) {
+        if (rank == 0) {
+            MPI_Send(buf.data(), 8192, MPI_BYTE, 1, 0, MPI_COMM_WORLD);
+            MPI_Recv(buf.data(), 8192, MPI_BYTE, 1, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+        } else if (rank == 1) {
+            MPI_Recv(buf.data(), 8192, MPI_BYTE, 0, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+            MPI_Send(buf.data(), 8192, MPI_BYTE, 0, 0, MPI_COMM_WORLD);
+        }
+    }
+    std::vector<int> grad(100000, rank + 1), sum(100000, 0);
+    for (int i = 0; i < 20; i++) {
+        MPI_Allreduce(grad.data(), sum.data(), 100000, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        CHECK_RANK(sum[0] == size * (size + 1) / 2 && sum[99999] == sum[0]);
+    }
+    return 0;
+}
+}
+
+TEST_CASE("mpi: point-to-point on one host", "[mpi]")
+{
+    runMpi("p2p-local", 4, 1, bodyPointToPoint);
+}
+
+TEST_CASE("mpi: collectives on one host", "[mpi]")
+{
+    runMpi("coll-local", 5, 1, bodyCollectives);
+}
+
+TEST_CASE("mpi: misc API (cartesian, types, alloc, gatherv)", "[mpi]")
+{
+    runMpi("misc-local", 4, 1, bodyMisc);
+}
+
+TEST_CASE("mpi: ranks on several virtual GPU hosts of one worker", "[mpi]")
+{
+    runMpi("coll-gpuhosts", 8, 4, bodyCollectives);
+    runMpi("p2p-gpuhosts", 6, 3, bodyPointToPoint);
+}
+
+TEST_CASE("mpi: ping-pong and all-reduce bursts", "[mpi][bench]")
+{
+    runMpi("pingpong", 2, 1, bodyPingPongAndAllreduce);
+    runMpi("allreduce8", 8, 1, bodyPingPongAndAllreduce);
+}
