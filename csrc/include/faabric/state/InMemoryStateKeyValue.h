@@ -68,6 +68,8 @@ class InMemoryStateKeyValue final : public StateKeyValue
     std::mutex appendedMx;
     std::vector<AppendedInMemoryState> appendedData;
 
+    size_t sizeFromRemote() override;
+
     void pullFromRemote() override;
 
     void pullChunkFromRemote(long offset, size_t length) override;

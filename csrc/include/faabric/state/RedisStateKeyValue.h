@@ -23,6 +23,8 @@ class RedisStateKeyValue final : public StateKeyValue
   private:
     const std::string joinedKey;
 
+    size_t sizeFromRemote() override;
+
     void pullFromRemote() override;
 
     void pullChunkFromRemote(long offset, size_t length) override;

@@ -165,6 +165,10 @@ class StateKeyValue
     void zeroDirtyMask();
 
     // ---- backend hooks ----
+    // Size of the authoritative copy (0 if unknown); lets a size-less replica
+    // configure itself on first use
+    virtual size_t sizeFromRemote() { return 0; }
+
     virtual void pullFromRemote() = 0;
 
     virtual void pullChunkFromRemote(long offset, size_t length) = 0;

@@ -203,6 +203,13 @@ void StateKeyValue::configureSize()
 void StateKeyValue::checkSizeConfigured()
 {
     if (valueSize <= 0) {
+        // Created without a size: ask whoever holds the value
+        size_t remote = sizeFromRemote();
+        if (remote > 0) {
+            valueSize = remote;
+            configureSize();
+            return;
+        }
         throw StateKeyValueException(std::string("State value size not set for ") + user + "/" + key);
     }
 }
@@ -290,6 +297,8 @@ void StateKeyValue::invalidateDeviceRange(long offset, long len)
 
 void StateKeyValue::doPull(bool lazy)
 {
+    // Resolve the size first: a size-less replica learns it here
+    checkSizeConfigured();
     doPullChunk(lazy, 0, valueSize);
 }
 
@@ -800,6 +809,15 @@ AppendedInMemoryState& InMemoryStateKeyValue::getAppendedValue(uint idx)
     return appendedData.at(idx);
 }
 
+size_t InMemoryStateKeyValue::sizeFromRemote()
+{
+    if (status == InMemoryStateKeyStatus::MASTER) {
+        return 0;
+    }
+    StateClient client(user, key, mainIP);
+    return client.stateSize();
+}
+
 void InMemoryStateKeyValue::pullFromRemote()
 {
     if (status == InMemoryStateKeyStatus::MASTER) {
@@ -916,6 +934,11 @@ void RedisStateKeyValue::clearAll(bool global)
     if (global) {
         faabric::redis::Redis::getState().flushAll();
     }
+}
+
+size_t RedisStateKeyValue::sizeFromRemote()
+{
+    return faabric::redis::Redis::getState().strlen(joinedKey);
 }
 
 void RedisStateKeyValue::pullFromRemote()

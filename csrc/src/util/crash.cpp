@@ -31,22 +31,39 @@ static void crashHandler(int sig) noexcept
     }
 }
 
+static void installHandler(int s)
+{
+    struct sigaction sa{};
+    sa.sa_handler = crashHandler;
+    sigemptyset(&sa.sa_mask);
+    // Run on the alternate stack so stack overflows still get a trace
+    sa.sa_flags = SA_ONSTACK;
+    if (::sigaction(s, &sa, nullptr) != 0) {
+        SPDLOG_WARN("Could not install crash handler for signal {}", s);
+    }
+}
+
 void setUpCrashHandler(int sig)
 {
-    // SIGSEGV is deliberately absent: the segfault dirty tracker owns it
-    int signals[] = { SIGABRT, SIGILL, SIGFPE };
+    // The segfault dirty tracker installs itself over SIGSEGV later and
+    // falls back to this handler for faults outside tracked memory
+    int signals[] = { SIGSEGV, SIGABRT, SIGILL, SIGFPE, SIGBUS };
     if (sig >= 0) {
         if (sig == TEST_SIGNAL) {
             crashHandler(sig);
             return;
         }
-        ::signal(sig, crashHandler);
+        installHandler(sig);
         return;
     }
+    static thread_local char altStack[64 * 1024];
+    stack_t ss{};
+    ss.ss_sp = altStack;
+    ss.ss_size = sizeof(altStack);
+    ss.ss_flags = 0;
+    ::sigaltstack(&ss, nullptr);
     for (int s : signals) {
-        if (::signal(s, crashHandler) == SIG_ERR) {
-            SPDLOG_WARN("Could not install crash handler for signal {}", s);
-        }
+        installHandler(s);
     }
 }
 

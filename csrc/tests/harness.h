@@ -85,8 +85,8 @@ long& assertionCount();
 #define REQUIRE_EQ(a, b)                                                       \
     do {                                                                       \
         fbtest::assertionCount()++;                                            \
-        auto&& _a = (a);                                                       \
-        auto&& _b = (b);                                                       \
+        auto _a = (a);                                                         \
+        auto _b = (b);                                                         \
         if (!(_a == _b)) {                                                     \
             fbtest::fail(__FILE__, __LINE__, "REQUIRE_EQ(" #a ", " #b ") failed: " + fbtest::show(_a) + " != " + fbtest::show(_b)); \
         }                                                                      \

@@ -1,0 +1,331 @@
+// State, Redis emulation and snapshot service tests (strategy: reference
+// tests/test/state/*.cpp, tests/test/redis/test_redis.cpp,
+// tests/test/snapshot/*.cpp)
+#include "fixtures.h"
+
+#include <faabric/redis/Redis.h>
+#include <faabric/snapshot/SnapshotClient.h>
+#include <faabric/snapshot/SnapshotRegistry.h>
+#include <faabric/state/InMemoryStateKeyValue.h>
+#include <faabric/state/InMemoryStateRegistry.h>
+#include <faabric/state/RedisStateKeyValue.h>
+#include <faabric/state/State.h>
+#include <faabric/state/StateClient.h>
+#include <faabric/state/StateServer.h>
+#include <faabric/util/bytes.h>
+#include <faabric/util/memory.h>
+
+#include <thread>
+
+using namespace faabric::state;
+
+TEST_CASE("redis emulation: strings, counters, ranges", "[redis]")
+{
+    auto& r = faabric::redis::Redis::getQueue();
+    r.flushAll();
+    r.ping();
+    r.set("k", { 1, 2, 3, 4 });
+    REQUIRE(r.get("k") == (std::vector<uint8_t>{ 1, 2, 3, 4 }));
+    REQUIRE_EQ(r.strlen("k"), 4u);
+    uint8_t buf[4] = { 0 };
+    r.get("k", buf, 4);
+    REQUIRE_EQ(buf[3], 4);
+    r.del("k");
+    REQUIRE(r.get("k").empty());
+
+    REQUIRE_EQ(r.incr("ctr"), 1);
+    REQUIRE_EQ(r.incrByLong("ctr", 10), 11);
+    REQUIRE_EQ(r.decr("ctr"), 10);
+    REQUIRE_EQ(r.decrByLong("ctr", 4), 6);
+    REQUIRE_EQ(r.getCounter("ctr"), 6);
+    r.setLong("lng", 123456789012L);
+    REQUIRE_EQ(r.getLong("lng"), 123456789012L);
+
+    std::vector<uint8_t> base(10, 0);
+    r.set("rng", base);
+    uint8_t patch[3] = { 7, 8, 9 };
+    r.setRange("rng", 4, patch, 3);
+    uint8_t out[5];
+    r.getRange("rng", out, 5, 3, 7);
+    REQUIRE_EQ(out[0], 0);
+    REQUIRE_EQ(out[1], 7);
+    REQUIRE_EQ(out[3], 9);
+    r.setRangePipeline("rng", 0, patch, 3);
+    r.flushPipeline(1);
+    REQUIRE_EQ(r.get("rng")[2], 9);
+}
+
+TEST_CASE("redis emulation: sets, lists, queues, locks", "[redis]")
+{
+    auto& r = faabric::redis::Redis::getQueue();
+    r.flushAll();
+    r.sadd("s1", "a");
+    r.sadd("s1", "b");
+    r.sadd("s1", "b");
+    r.sadd("s2", "b");
+    r.sadd("s2", "c");
+    REQUIRE_EQ(r.scard("s1"), 2);
+    REQUIRE(r.sismember("s1", "a"));
+    REQUIRE(!r.sismember("s1", "c"));
+    REQUIRE(r.sdiff("s1", "s2") == (std::set<std::string>{ "a" }));
+    REQUIRE(r.sinter("s1", "s2") == (std::set<std::string>{ "b" }));
+    REQUIRE(r.smembers("s2").count(r.srandmember("s2")) == 1);
+    r.srem("s1", "a");
+    REQUIRE_EQ(r.scard("s1"), 1);
+
+    r.enqueue("q", "first");
+    r.enqueue("q", "second");
+    REQUIRE_EQ(r.listLength("q"), 2);
+    REQUIRE_EQ(r.dequeue("q"), std::string("first"));
+    REQUIRE_EQ(r.dequeue("q"), std::string("second"));
+    REQUIRE_THROWS(r.dequeue("q", 30));
+    // Blocking dequeue woken by another thread
+    std::thread producer([&] {
+        std::this_thread::sleep_for(std::chrono::milliseconds(30));
+        faabric::redis::Redis::getQueue().enqueueBytes("bq", { 5, 6 });
+    });
+    auto bytes = r.dequeueBytes("bq", 2000);
+    producer.join();
+    REQUIRE(bytes == (std::vector<uint8_t>{ 5, 6 }));
+    // Longs are stored the way a redis client formats them (decimal)
+    char vals[16] = { 0 };
+    r.rpushLong("longs", 10);
+    r.rpushLong("longs", 20);
+    r.lpushLong("longs", 5);
+    r.dequeueMultiple("longs", (uint8_t*)vals, sizeof(vals), 3);
+    REQUIRE_EQ(std::string(vals), std::string("51020"));
+    REQUIRE_EQ(r.listLength("longs"), 3);
+
+    // Locks
+    uint32_t id = r.acquireLock("lockme", 5);
+    REQUIRE(id > 0);
+    REQUIRE_EQ(r.acquireLock("lockme", 5), 0u);
+    r.releaseLock("lockme", id + 1); // wrong owner: no-op
+    REQUIRE_EQ(r.acquireLock("lockme", 5), 0u);
+    r.releaseLock("lockme", id);
+    uint32_t id2 = r.acquireLock("lockme", 5);
+    REQUIRE(id2 > 0);
+    r.releaseLock("lockme", id2);
+    REQUIRE(r.setnxex("once", 1, 1));
+    REQUIRE(!r.setnxex("once", 2, 1));
+    r.expire("once", 0);
+    std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    REQUIRE(r.setnxex("once", 3, 1));
+    // Queue and state roles are separate stores
+    REQUIRE(faabric::redis::Redis::getState().get("once").empty());
+}
+
+namespace {
+struct StateFixture
+{
+    State& mainState = getGlobalState();
+    StateServer server;
+    // A second host's view of the state
+    State remoteState;
+
+    StateFixture()
+      : server(getGlobalState())
+      , remoteState("otherhost")
+    {
+        faabric::util::getSystemConfig().reset();
+        mainState.forceClearAll(true);
+        getInMemoryStateRegistry().clear();
+        faabric::redis::Redis::getState().flushAll();
+        server.start();
+    }
+
+    ~StateFixture()
+    {
+        server.stop();
+        mainState.forceClearAll(true);
+        remoteState.forceClearAll(false);
+        getInMemoryStateRegistry().clear();
+        faabric::util::getSystemConfig().reset();
+    }
+};
+}
+
+TEST_CASE("state: in-memory main and remote replicas", "[state]")
+{
+    StateFixture f;
+    size_t size = 3 * STATE_STREAMING_CHUNK_SIZE + 123;
+    std::vector<uint8_t> values(size);
+    for (size_t i = 0; i < size; i++) {
+        values[i] = (uint8_t)(i * 31);
+    }
+    auto mainKv = f.mainState.getKV("demo", "big", size);
+    mainKv->set(values.data());
+    mainKv->pushFull();
+    REQUIRE_EQ(f.mainState.getKVCount(), 1u);
+    REQUIRE_EQ(f.mainState.getStateSize("demo", "big"), size);
+
+    // The other host learns the size and pulls through the state server
+    REQUIRE_EQ(f.remoteState.getStateSize("demo", "big"), size);
+    auto remoteKv = f.remoteState.getKV("demo", "big");
+    // Size-less replicas configure themselves on first use
+    std::vector<uint8_t> pulled(size, 0);
+    remoteKv->get(pulled.data());
+    REQUIRE_EQ(remoteKv->size(), size);
+    REQUIRE(pulled == values);
+
+    // Chunked lazy pull only brings what is asked for
+    auto remoteChunkKv = State("thirdhost").getKV("demo", "big");
+    std::vector<uint8_t> part(100);
+    remoteChunkKv->getChunk(STATE_STREAMING_CHUNK_SIZE + 10, part.data(), 100);
+    REQUIRE_EQ(part[0], values[STATE_STREAMING_CHUNK_SIZE + 10]);
+
+    // Remote partial update reaches main
+    std::vector<uint8_t> patch(64, 0xee);
+    remoteKv->setChunk(2 * STATE_STREAMING_CHUNK_SIZE + 5, patch.data(), patch.size());
+    remoteKv->pushPartial();
+    std::vector<uint8_t> check(64);
+    mainKv->getChunk(2 * STATE_STREAMING_CHUNK_SIZE + 5, check.data(), 64);
+    REQUIRE(check == patch);
+    // ...and untouched bytes stay
+    REQUIRE_EQ(*mainKv->getChunk(3, 1), values[3]);
+
+    // Appends accumulate on main from any host
+    std::vector<uint8_t> a = { 1, 1, 1 }, b = { 2, 2, 2 };
+    auto mainApp = f.mainState.getKV("demo", "log", 3);
+    mainApp->append(a.data(), 3);
+    auto remoteApp = f.remoteState.getKV("demo", "log", 3);
+    remoteApp->append(b.data(), 3);
+    std::vector<uint8_t> appended(6);
+    remoteApp->getAppended(appended.data(), 6, 2);
+    REQUIRE(appended == (std::vector<uint8_t>{ 1, 1, 1, 2, 2, 2 }));
+    remoteApp->clearAppended();
+    REQUIRE_THROWS(mainApp->getAppended(appended.data(), 6, 2));
+
+    // Deletion
+    f.remoteState.deleteKV("demo", "big");
+    REQUIRE_EQ(f.mainState.getKVCount(), 1u);
+}
+
+TEST_CASE("state: shared-memory mapping and locks", "[state]")
+{
+    StateFixture f;
+    size_t size = 2 * faabric::util::HOST_PAGE_SIZE;
+    auto kv = f.mainState.getKV("demo", "mapped", size);
+    std::vector<uint8_t> init(size, 3);
+    kv->set(init.data());
+    auto region = faabric::util::allocatePrivateMemory(size);
+    kv->mapSharedMemory(region.get(), 0, 2);
+    REQUIRE_EQ(region[10], 3);
+    region[10] = 9; // writes through to the KV
+    REQUIRE_EQ(*kv->getChunk(10, 1), 9);
+    kv->unmapSharedMemory(region.get());
+
+    // Write lock excludes readers
+    kv->lockWrite();
+    std::atomic<bool> got{ false };
+    std::thread reader([&] {
+        kv->lockRead();
+        got = true;
+        kv->unlockRead();
+    });
+    std::this_thread::sleep_for(std::chrono::milliseconds(30));
+    REQUIRE(!got.load());
+    kv->unlockWrite();
+    reader.join();
+    REQUIRE(got.load());
+    // A size-less KV nobody has created fails on first use
+    auto ghost = f.mainState.getKV("demo", "nosize");
+    REQUIRE_THROWS(ghost->get());
+}
+
+TEST_CASE("state: redis-backed mode", "[state][redis]")
+{
+    StateFixture f;
+    faabric::util::getSystemConfig().stateMode = "redis";
+    State a("hostA"), b("hostB");
+    std::vector<uint8_t> v = { 9, 8, 7, 6, 5 };
+    auto kvA = a.getKV("demo", "r", v.size());
+    kvA->set(v.data());
+    kvA->pushFull();
+    REQUIRE_EQ(b.getStateSize("demo", "r"), v.size());
+    auto kvB = b.getKV("demo", "r", v.size());
+    std::vector<uint8_t> got(v.size());
+    kvB->get(got.data());
+    REQUIRE(got == v);
+    uint8_t patch[2] = { 1, 2 };
+    kvB->setChunk(1, patch, 2);
+    kvB->pushPartial();
+    kvA->pull();
+    kvA->get(got.data());
+    REQUIRE(got == (std::vector<uint8_t>{ 9, 1, 2, 6, 5 }));
+    a.deleteKV("demo", "r");
+    REQUIRE_EQ(State("hostC").getStateSize("demo", "r"), 0u);
+}
+
+TEST_CASE("snapshots: push, update, thread results, delete over RPC", "[snapshot]")
+{
+    tests::ClusterFixture f(2);
+    auto& reg = faabric::snapshot::getSnapshotRegistry();
+    size_t size = 4 * faabric::util::HOST_PAGE_SIZE;
+    auto snap = std::make_shared<faabric::util::SnapshotData>(size);
+    std::vector<uint8_t> content(size, 1);
+    snap->copyInData(content);
+    snap->addMergeRegion(64, sizeof(int), faabric::util::SnapshotDataType::Int, faabric::util::SnapshotMergeOperation::Sum);
+
+    // The client talks to this very host: the server registers a copy
+    faabric::snapshot::SnapshotClient cli(f.conf.endpointHost);
+    cli.pushSnapshot("snapA", snap);
+    REQUIRE(reg.snapshotExists("snapA"));
+    auto received = reg.getSnapshot("snapA");
+    REQUIRE(received.get() != snap.get());
+    REQUIRE_EQ(received->getSize(), size);
+    REQUIRE_EQ(received->getMergeRegions().size(), 1u);
+    REQUIRE_EQ(*received->getDataPtr(100), 1);
+    REQUIRE_EQ(received->getTrackedChanges().size(), 0u);
+
+    // Updates are applied immediately and replace the merge regions
+    std::vector<uint8_t> bytes(16, 0x7f);
+    int delta = 5;
+    std::vector<faabric::util::SnapshotDiff> diffs;
+    diffs.emplace_back(faabric::util::SnapshotDataType::Raw, faabric::util::SnapshotMergeOperation::Bytewise, 1000, bytes);
+    diffs.emplace_back(faabric::util::SnapshotDataType::Int,
+                       faabric::util::SnapshotMergeOperation::Sum,
+                       64,
+                       std::span<const uint8_t>((const uint8_t*)&delta, sizeof(int)));
+    snap->clearMergeRegions();
+    cli.pushSnapshotUpdate("snapA", snap, diffs);
+    REQUIRE_EQ(*received->getDataPtr(1000), 0x7f);
+    REQUIRE_EQ(faabric::util::unalignedRead<int>(received->getDataPtr(64)), 0x01010101 + 5);
+    REQUIRE_EQ(received->getMergeRegions().size(), 0u);
+
+    // Thread results queue their diffs and resolve the waiting future
+    auto threadReq = faabric::util::batchExecFactory("demo", "thr", 1);
+    uint32_t msgId = threadReq->messages(0).id();
+    std::vector<faabric::util::SnapshotDiff> threadDiffs;
+    threadDiffs.emplace_back(faabric::util::SnapshotDataType::Raw, faabric::util::SnapshotMergeOperation::Bytewise, 2000, bytes);
+    cli.pushThreadResult(threadReq->appid(), msgId, 42, "snapA", threadDiffs);
+    REQUIRE_EQ(received->getQueuedDiffsCount(), 1u);
+    auto results = f.sch.awaitThreadResults(threadReq, 2000);
+    REQUIRE_EQ(results.size(), 1u);
+    REQUIRE_EQ(results[0].first, msgId);
+    REQUIRE_EQ(results[0].second, 42);
+    REQUIRE_EQ(received->writeQueuedDiffs(), 1);
+    REQUIRE_EQ(*received->getDataPtr(2000), 0x7f);
+
+    cli.deleteSnapshot("snapA");
+    for (int i = 0; i < 200 && reg.snapshotExists("snapA"); i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    REQUIRE(!reg.snapshotExists("snapA"));
+    REQUIRE_THROWS(reg.getSnapshot("snapA"));
+    REQUIRE_THROWS(reg.getSnapshot(""));
+
+    // Mock mode records instead of sending
+    faabric::util::setMockMode(true);
+    faabric::snapshot::clearMockSnapshotRequests();
+    faabric::snapshot::SnapshotClient mockCli("elsewhere");
+    mockCli.pushSnapshot("snapB", snap);
+    mockCli.pushSnapshotUpdate("snapB", snap, diffs);
+    mockCli.deleteSnapshot("snapB");
+    REQUIRE_EQ(faabric::snapshot::getSnapshotPushes().size(), 1u);
+    REQUIRE_EQ(faabric::snapshot::getSnapshotDiffPushes().size(), 1u);
+    REQUIRE_EQ(faabric::snapshot::getSnapshotDiffPushes()[0].second->diffs.size(), 2u);
+    REQUIRE_EQ(faabric::snapshot::getSnapshotDeletes().size(), 1u);
+    faabric::snapshot::clearMockSnapshotRequests();
+    faabric::util::setMockMode(false);
+}
