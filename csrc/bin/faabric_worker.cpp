@@ -1,0 +1,370 @@
+// General purpose worker: embeds the runtime with a table of built-in
+// functions (a demo set plus the MPI example programs used by the
+// distributed tests and the CPU baseline benchmarks).
+//
+// Plays the role of the reference's tests/dist/server.cpp + DistTestExecutor,
+// and of the tests/dist/mpi/examples/*.cpp programs.
+#include <faabric/endpoint/FaabricEndpoint.h>
+#include <faabric/endpoint/FaabricEndpointHandler.h>
+#include <faabric/executor/ExecutorFactory.h>
+#include <faabric/mpi/mpi.h>
+#include <faabric/planner/PlannerClient.h>
+#include <faabric/runner/FaabricMain.h>
+#include <faabric/scheduler/Scheduler.h>
+#include <faabric/util/batch.h>
+#include <faabric/util/config.h>
+#include <faabric/util/logging.h>
+
+#include <chrono>
+#include <cmath>
+#include <functional>
+#include <map>
+#include <numeric>
+#include <thread>
+
+using namespace faabric::executor;
+
+typedef std::function<int(faabric::Message&)> WorkerFunction;
+
+static std::map<std::string, WorkerFunction>& functions()
+{
+    static std::map<std::string, WorkerFunction> t;
+    return t;
+}
+
+#define EXPECT(cond)                                                           \
+    do {                                                                       \
+        if (!(cond)) {                                                         \
+            SPDLOG_ERROR("rank {}: check failed at line {}: {}", rank, __LINE__, #cond); \
+            return 1;                                                          \
+        }                                                                      \
+    } while (0)
+
+// Wraps an MPI program body with Init / Finalize
+static void mpiFunction(const std::string& name, std::function<int(int, int, faabric::Message&)> body)
+{
+    functions()["mpi/" + name] = [body](faabric::Message& msg) {
+        MPI_Init(nullptr, nullptr);
+        int rank = 0, size = 0;
+        MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+        MPI_Comm_size(MPI_COMM_WORLD, &size);
+        int rc = body(rank, size, msg);
+        MPI_Finalize();
+        return rc;
+    };
+}
+
+static void registerFunctions()
+{
+    functions()["demo/echo"] = [](faabric::Message& msg) {
+        msg.set_outputdata(msg.inputdata());
+        return 0;
+    };
+    functions()["demo/hello"] = [](faabric::Message& msg) {
+        msg.set_outputdata("hello from " + faabric::scheduler::getScheduler().getThisHost());
+        return 0;
+    };
+    functions()["demo/sleep"] = [](faabric::Message& msg) {
+        int ms = msg.inputdata().empty() ? 100 : std::stoi(msg.inputdata());
+        std::this_thread::sleep_for(std::chrono::milliseconds(ms));
+        return 0;
+    };
+    functions()["demo/error"] = [](faabric::Message& msg) {
+        msg.set_outputdata("deliberate failure");
+        return 1;
+    };
+    functions()["demo/noop"] = [](faabric::Message&) { return 0; };
+
+    mpiFunction("helloworld", [](int rank, int size, faabric::Message& msg) {
+        char name[MPI_MAX_PROCESSOR_NAME];
+        int len = 0;
+        MPI_Get_processor_name(name, &len);
+        msg.set_outputdata("rank " + std::to_string(rank) + "/" + std::to_string(size) + " on " + name);
+        return 0;
+    });
+
+    mpiFunction("allreduce", [](int rank, int size, faabric::Message&) {
+        std::vector<int> v(1000, rank + 1), out(1000, 0);
+        MPI_Allreduce(v.data(), out.data(), 1000, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        EXPECT(out[0] == size * (size + 1) / 2 && out[999] == out[0]);
+        std::vector<double> d(17, rank), dout(17, 0);
+        MPI_Allreduce(d.data(), dout.data(), 17, MPI_DOUBLE, MPI_MAX, MPI_COMM_WORLD);
+        EXPECT(dout[5] == size - 1);
+        MPI_Allreduce(MPI_IN_PLACE, v.data(), 1000, MPI_INT, MPI_MIN, MPI_COMM_WORLD);
+        EXPECT(v[0] == 1);
+        return 0;
+    });
+
+    mpiFunction("allgather", [](int rank, int size, faabric::Message&) {
+        std::vector<int> mine = { rank, rank * 2 }, all(2 * size, -1);
+        MPI_Allgather(mine.data(), 2, MPI_INT, all.data(), 2, MPI_INT, MPI_COMM_WORLD);
+        for (int r = 0; r < size; r++) {
+            EXPECT(all[2 * r] == r && all[2 * r + 1] == 2 * r);
+        }
+        return 0;
+    });
+
+    mpiFunction("alltoall", [](int rank, int size, faabric::Message&) {
+        std::vector<int> s(size), r(size, -1);
+        for (int i = 0; i < size; i++) {
+            s[i] = rank * 100 + i;
+        }
+        MPI_Alltoall(s.data(), 1, MPI_INT, r.data(), 1, MPI_INT, MPI_COMM_WORLD);
+        for (int i = 0; i < size; i++) {
+            EXPECT(r[i] == i * 100 + rank);
+        }
+        return 0;
+    });
+
+    mpiFunction("bcast", [](int rank, int size, faabric::Message&) {
+        int root = size > 2 ? 2 : 0;
+        std::vector<long> v(500, rank == root ? 42 : -1);
+        MPI_Bcast(v.data(), 500, MPI_LONG, root, MPI_COMM_WORLD);
+        EXPECT(v[0] == 42 && v[499] == 42);
+        return 0;
+    });
+
+    mpiFunction("barrier", [](int rank, int size, faabric::Message&) {
+        for (int i = 0; i < 20; i++) {
+            MPI_Barrier(MPI_COMM_WORLD);
+        }
+        return 0;
+    });
+
+    mpiFunction("gather-scatter", [](int rank, int size, faabric::Message&) {
+        const int per = 3;
+        std::vector<int> all(per * size), mine(per, -1);
+        if (rank == 0) {
+            std::iota(all.begin(), all.end(), 0);
+        }
+        MPI_Scatter(all.data(), per, MPI_INT, mine.data(), per, MPI_INT, 0, MPI_COMM_WORLD);
+        for (int i = 0; i < per; i++) {
+            EXPECT(mine[i] == rank * per + i);
+            mine[i] += 1000;
+        }
+        int root = size - 1;
+        std::vector<int> back(per * size, -1);
+        MPI_Gather(mine.data(), per, MPI_INT, back.data(), per, MPI_INT, root, MPI_COMM_WORLD);
+        if (rank == root) {
+            for (int i = 0; i < per * size; i++) {
+                EXPECT(back[i] == 1000 + i);
+            }
+        }
+        return 0;
+    });
+
+    mpiFunction("reduce-scan", [](int rank, int size, faabric::Message&) {
+        int v = rank + 1, out = 0;
+        MPI_Reduce(&v, &out, 1, MPI_INT, MPI_SUM, 0, MPI_COMM_WORLD);
+        if (rank == 0) {
+            EXPECT(out == size * (size + 1) / 2);
+        }
+        MPI_Scan(&v, &out, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        EXPECT(out == (rank + 1) * (rank + 2) / 2);
+        return 0;
+    });
+
+    mpiFunction("sendrecv", [](int rank, int size, faabric::Message&) {
+        int right = (rank + 1) % size, left = (rank + size - 1) % size;
+        std::vector<double> out(2048, rank), in(2048, -1);
+        MPI_Status st{};
+        MPI_Sendrecv(out.data(), 2048, MPI_DOUBLE, right, 0, in.data(), 2048, MPI_DOUBLE, left, 0, MPI_COMM_WORLD, &st);
+        EXPECT(in[0] == left && in[2047] == left);
+        EXPECT(st.MPI_SOURCE == left);
+        return 0;
+    });
+
+    mpiFunction("isendrecv", [](int rank, int size, faabric::Message&) {
+        std::vector<int> sendVals(size), recvVals(size, -1);
+        std::vector<MPI_Request> reqs;
+        for (int r = 0; r < size; r++) {
+            if (r == rank) {
+                continue;
+            }
+            MPI_Request rq;
+            MPI_Irecv(&recvVals[r], 1, MPI_INT, r, 0, MPI_COMM_WORLD, &rq);
+            reqs.push_back(rq);
+        }
+        for (int r = 0; r < size; r++) {
+            if (r == rank) {
+                continue;
+            }
+            sendVals[r] = rank * 1000 + r;
+            MPI_Request rq;
+            MPI_Isend(&sendVals[r], 1, MPI_INT, r, 0, MPI_COMM_WORLD, &rq);
+            reqs.push_back(rq);
+        }
+        MPI_Waitall((int)reqs.size(), reqs.data(), MPI_STATUSES_IGNORE);
+        for (int r = 0; r < size; r++) {
+            if (r != rank) {
+                EXPECT(recvVals[r] == r * 1000 + rank);
+            }
+        }
+        return 0;
+    });
+
+    // Messages between a pair keep their order even when received out of
+    // posting order
+    mpiFunction("order", [](int rank, int size, faabric::Message&) {
+        if (rank == 0) {
+            for (int i = 0; i < 50; i++) {
+                MPI_Send(&i, 1, MPI_INT, size - 1, 0, MPI_COMM_WORLD);
+            }
+        } else if (rank == size - 1) {
+            std::vector<int> got(50, -1);
+            std::vector<MPI_Request> reqs(50);
+            for (int i = 0; i < 50; i++) {
+                MPI_Irecv(&got[i], 1, MPI_INT, 0, 0, MPI_COMM_WORLD, &reqs[i]);
+            }
+            for (int i = 49; i >= 0; i--) {
+                MPI_Wait(&reqs[i], MPI_STATUS_IGNORE);
+            }
+            for (int i = 0; i < 50; i++) {
+                EXPECT(got[i] == i);
+            }
+        }
+        MPI_Barrier(MPI_COMM_WORLD);
+        return 0;
+    });
+
+    mpiFunction("status-probe", [](int rank, int size, faabric::Message&) {
+        if (rank == 0) {
+            std::vector<int> v(33, 7);
+            MPI_Send(v.data(), 33, MPI_INT, 1, 0, MPI_COMM_WORLD);
+        } else if (rank == 1) {
+            MPI_Status st{};
+            MPI_Probe(0, 0, MPI_COMM_WORLD, &st);
+            int count = 0;
+            MPI_Get_count(&st, MPI_INT, &count);
+            EXPECT(count == 33);
+            std::vector<int> v(64, 0);
+            MPI_Recv(v.data(), 64, MPI_INT, 0, 0, MPI_COMM_WORLD, &st);
+            MPI_Get_count(&st, MPI_INT, &count);
+            EXPECT(count == 33 && v[32] == 7 && v[33] == 0);
+        }
+        return 0;
+    });
+
+    mpiFunction("cart", [](int rank, int size, faabric::Message&) {
+        int side = (int)std::lround(std::sqrt((double)size));
+        if (side * side != size) {
+            return 0;
+        }
+        int dims[2] = { side, side }, periods[2] = { 1, 1 }, coords[2];
+        MPI_Comm cart;
+        MPI_Cart_create(MPI_COMM_WORLD, 2, dims, periods, 0, &cart);
+        MPI_Cart_get(cart, 2, dims, periods, coords);
+        EXPECT(coords[0] == rank / side && coords[1] == rank % side);
+        int src, dst;
+        MPI_Cart_shift(cart, 1, 1, &src, &dst);
+        int token = rank, got = -1;
+        MPI_Sendrecv(&token, 1, MPI_INT, dst, 0, &got, 1, MPI_INT, src, 0, cart, MPI_STATUS_IGNORE);
+        EXPECT(got == src);
+        return 0;
+    });
+
+    // ---- CPU baselines ----
+    // Ping-pong between ranks 0 and 1; reports the mean round-trip in us
+    mpiFunction("bench-pingpong", [](int rank, int size, faabric::Message& msg) {
+        int bytes = msg.inputdata().empty() ? 8 : std::stoi(msg.inputdata());
+        const int iters = 2000, warmup = 200;
+        std::vector<uint8_t> buf((size_t)bytes, 1);
+        std::chrono::steady_clock::time_point t0;
+        for (int i = 0; i < iters + warmup; i++) {
+            if (i == warmup) {
+                t0 = std::chrono::steady_clock::now();
+            }
+            if (rank == 0) {
+                MPI_Send(buf.data(), bytes, MPI_BYTE, 1, 0, MPI_COMM_WORLD);
+                MPI_Recv(buf.data(), bytes, MPI_BYTE, 1, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+            } else if (rank == 1) {
+                MPI_Recv(buf.data(), bytes, MPI_BYTE, 0, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+                MPI_Send(buf.data(), bytes, MPI_BYTE, 0, 0, MPI_COMM_WORLD);
+            }
+        }
+        double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / iters;
+        if (rank == 0) {
+            msg.set_outputdata("{\"bytes\": " + std::to_string(bytes) + ", \"rtt_us\": " + std::to_string(us) + "}");
+        }
+        return 0;
+    });
+
+    // The headline: one "step" of ResNet-50 gradient sync = one int32
+    // MPI_Allreduce per parameter tensor, on host memory (reference CPU path)
+    mpiFunction("bench-allreduce", [](int rank, int size, faabric::Message& msg) {
+        // "count[,steps]" in elements; default: a 25.6M-element model in 214
+        // tensors is driven from Python, this is the single-size kernel
+        size_t count = 1 << 20;
+        int steps = 20;
+        if (!msg.inputdata().empty()) {
+            auto comma = msg.inputdata().find(',');
+            count = std::stoul(msg.inputdata().substr(0, comma));
+            if (comma != std::string::npos) {
+                steps = std::stoi(msg.inputdata().substr(comma + 1));
+            }
+        }
+        std::vector<int> v(count, rank + 1), out(count, 0);
+        MPI_Allreduce(v.data(), out.data(), (int)count, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        MPI_Barrier(MPI_COMM_WORLD);
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < steps; i++) {
+            MPI_Allreduce(v.data(), out.data(), (int)count, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        }
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / steps;
+        EXPECT(out[count - 1] == size * (size + 1) / 2);
+        if (rank == 0) {
+            double gbps = (double)count * 4 / (ms * 1e-3) / 1e9;
+            msg.set_outputdata("{\"count\": " + std::to_string(count) + ", \"ms\": " + std::to_string(ms) +
+                               ", \"algbw_GBps\": " + std::to_string(gbps) + "}");
+        }
+        return 0;
+    });
+}
+
+class WorkerExecutor : public Executor
+{
+  public:
+    explicit WorkerExecutor(faabric::Message& msg)
+      : Executor(msg)
+    {}
+
+    int32_t executeTask(int threadPoolIdx, int msgIdx, std::shared_ptr<faabric::BatchExecuteRequest> req) override
+    {
+        auto& msg = *req->mutable_messages(msgIdx);
+        auto it = functions().find(msg.user() + "/" + msg.function());
+        if (it == functions().end()) {
+            msg.set_outputdata("Unknown function " + msg.user() + "/" + msg.function());
+            return 1;
+        }
+        return it->second(msg);
+    }
+};
+
+class WorkerExecutorFactory : public ExecutorFactory
+{
+  protected:
+    std::shared_ptr<Executor> createExecutor(faabric::Message& msg) override
+    {
+        return std::make_shared<WorkerExecutor>(msg);
+    }
+};
+
+int main()
+{
+    faabric::util::initLogging();
+    registerFunctions();
+    auto& conf = faabric::util::getSystemConfig();
+    SPDLOG_INFO("Starting worker {} (port offset {}), planner at {}", conf.endpointHost, conf.portOffset, conf.plannerHost);
+
+    faabric::runner::FaabricMain m(std::make_shared<WorkerExecutorFactory>());
+    m.startBackground();
+
+    // Port 0: workers take no HTTP requests, the endpoint only gives us
+    // signal-driven shutdown
+    faabric::endpoint::FaabricEndpoint endpoint(0, 1, std::make_shared<faabric::endpoint::FaabricEndpointHandler>());
+    endpoint.start(faabric::endpoint::EndpointMode::SIGNAL);
+
+    SPDLOG_INFO("Shutting down worker");
+    m.shutdown();
+    return 0;
+}

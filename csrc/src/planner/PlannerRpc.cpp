@@ -4,6 +4,7 @@
 #include <faabric/planner/PlannerServer.h>
 #include <faabric/snapshot/SnapshotClient.h>
 #include <faabric/transport/common.h>
+#include <faabric/util/string_tools.h>
 #include <faabric/util/batch.h>
 #include <faabric/util/config.h>
 #include <faabric/util/func.h>
@@ -45,11 +46,19 @@ static std::string resolvePlannerHost()
     auto& conf = faabric::util::getSystemConfig();
     // "planner" is the compose service name in the reference deployment; on a
     // single box fall back to this machine when it does not resolve
-    std::string ip = faabric::util::getIPFromHostname(conf.plannerHost);
-    if (ip.empty()) {
-        return conf.endpointHost;
+    // PLANNER_HOST may carry a port offset ("host:offset")
+    std::string name = conf.plannerHost;
+    std::string suffix;
+    size_t colon = name.rfind(':');
+    if (colon != std::string::npos && faabric::util::stringIsInt(name.substr(colon + 1))) {
+        suffix = name.substr(colon);
+        name = name.substr(0, colon);
     }
-    return ip;
+    std::string ip = faabric::util::getIPFromHostname(name);
+    if (ip.empty()) {
+        ip = conf.endpointHost;
+    }
+    return ip + suffix;
 }
 
 PlannerClient::PlannerClient()

@@ -69,7 +69,11 @@ static void fillMessage(faabric::Message& msg,
     msg.set_user(user);
     msg.set_function(function);
     setMessageId(msg);
-    msg.set_mainhost(getSystemConfig().endpointHost);
+    // Same form as transport::getThisHostAddress(): several workers may share
+    // one IP and differ by port offset
+    const auto& conf = getSystemConfig();
+    msg.set_mainhost(conf.portOffset == 0 ? conf.endpointHost
+                                          : conf.endpointHost + ":" + std::to_string(conf.portOffset));
 }
 
 std::shared_ptr<faabric::Message> messageFactoryShared(
@@ -172,7 +176,8 @@ void updateBatchExecAppId(std::shared_ptr<faabric::BatchExecuteRequest> ber,
     for (int i = 0; i < ber->messages_size(); i++) {
         ber->mutable_messages(i)->set_appid(newAppId);
     }
-    if (!isBatchExecRequestValid(ber)) {
+    // (An empty request under construction is fine)
+    if (ber->messages_size() > 0 && !isBatchExecRequestValid(ber)) {
         throw std::runtime_error("Invalid BER after updating app id");
     }
 }
@@ -184,7 +189,7 @@ void updateBatchExecGroupId(std::shared_ptr<faabric::BatchExecuteRequest> ber,
     for (int i = 0; i < ber->messages_size(); i++) {
         ber->mutable_messages(i)->set_groupid(newGroupId);
     }
-    if (!isBatchExecRequestValid(ber)) {
+    if (ber->messages_size() > 0 && !isBatchExecRequestValid(ber)) {
         throw std::runtime_error("Invalid BER after updating group id");
     }
 }

@@ -378,3 +378,55 @@ TEST_CASE("planner: HTTP endpoint", "[planner][endpoint]")
     REQUIRE_EQ(s16, 200);
     endpoint.stop();
 }
+
+TEST_CASE("executor: threads share the main function's memory", "[executor][threads]")
+{
+    ClusterFixture f(8);
+    const int nThreads = 4;
+    // Each thread writes its own slot and adds into a shared Sum region
+    registerTestFunction("demo", "threaded", [&](auto* exec, int, int idx, auto req) {
+        auto& m = *req->mutable_messages(idx);
+        auto mem = exec->getMemoryView();
+        if (req->type() == faabric::BatchExecuteRequest::THREADS) {
+            int t = m.appidx();
+            mem[1024 + t] = (uint8_t)(10 + t);
+            // Same process: plain atomic add on the shared word
+            __atomic_fetch_add((int*)(mem.data() + 64), t + 1, __ATOMIC_RELAXED);
+            return t;
+        }
+        // Main thread
+        *(int*)(mem.data() + 64) = 100;
+        auto threads = faabric::util::batchExecFactory("demo", "threaded", nThreads);
+        faabric::util::updateBatchExecAppId(threads, m.appid());
+        for (int i = 0; i < nThreads; i++) {
+            threads->mutable_messages(i)->set_appidx(i + 1);
+            threads->mutable_messages(i)->set_groupidx(i + 1);
+        }
+        threads->set_singlehost(true);
+        std::vector<faabric::util::SnapshotMergeRegion> regions = { { 64,
+                                                                    sizeof(int),
+                                                                    faabric::util::SnapshotDataType::Int,
+                                                                    faabric::util::SnapshotMergeOperation::Sum } };
+        auto results = exec->executeThreads(threads, regions);
+        if ((int)results.size() != nThreads) {
+            return 1;
+        }
+        for (auto& [id, rv] : results) {
+            if (rv < 1 || rv > nThreads) {
+                return 2;
+            }
+        }
+        // 100 + (2+3+4+5): app idxs are 1..4 and each adds idx+1
+        int sum = *(int*)(mem.data() + 64);
+        m.set_outputdata(std::to_string(sum) + ":" + std::to_string(mem[1024 + 1]) + std::to_string(mem[1024 + 4]));
+        return 0;
+    });
+    auto req = faabric::util::batchExecFactory("demo", "threaded", 1);
+    f.plannerCli.callFunctions(req);
+    auto res = f.awaitResult(req->messages(0));
+    REQUIRE_EQ(res.returnvalue(), 0);
+    REQUIRE_EQ(res.outputdata(), std::string("114:1114"));
+    // Everything ran in ONE executor
+    REQUIRE_EQ(f.sch.getFunctionExecutorCount(req->messages(0)), 1);
+    f.awaitBatch(req);
+}

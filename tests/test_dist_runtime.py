@@ -1,0 +1,131 @@
+"""Distributed tests of the native runtime: planner + 2 worker PROCESSES on this
+box (strategy: the reference's tests/dist suite, which does the same over a
+docker-compose cluster).  CPU only."""
+
+import base64
+import json
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from faabric_b200 import build as fb_build
+from faabric_b200.runtime import LocalCluster, PlannerError
+
+ROOT = Path(__file__).resolve().parents[1]
+BIN = ROOT / "build" / "bin"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    fb_build.build(verbose=False)
+
+
+@pytest.fixture(scope="module")
+def cluster(tmp_path_factory):
+    logs = tmp_path_factory.mktemp("cluster-logs")
+    c = LocalCluster(n_workers=2, slots_per_worker=2, log_dir=logs)
+    c.start()
+    yield c
+    c.stop()
+    for f in sorted(logs.glob("*.log")):
+        tail = f.read_text()[-1500:]
+        print(f"---- {f.name} ----\n{tail}")
+
+
+def _results(status):
+    return sorted(status.get("messageResults", []), key=lambda m: m.get("mpiRank", 0))
+
+
+def test_cpp_unit_suite():
+    """The in-tree C++ test runner (util, schedulers, transport, planner,
+    executor, state, redis, snapshots, MPI)."""
+    r = subprocess.run([str(BIN / "faabric_tests")], capture_output=True, text=True, timeout=900)
+    tail = "\n".join(r.stdout.splitlines()[-40:])
+    assert r.returncode == 0, tail
+    assert " 0 failed" in r.stdout.splitlines()[-1], tail
+
+
+def test_hosts_register_and_functions_spread(cluster):
+    hosts = cluster.client.available_hosts()
+    assert sorted(h["ip"] for h in hosts) == sorted(cluster.worker_hosts())
+    assert all(h["slots"] == 2 for h in hosts)
+    st = cluster.client.invoke("demo", "hello", count=4)
+    outs = [m["output_data"] for m in st["messageResults"]]
+    assert len(outs) == 4
+    # 4 functions over 2x2 slots: both workers took part
+    assert {o.split()[-1] for o in outs} == set(cluster.worker_hosts())
+    assert all(m.get("returnValue", 0) == 0 for m in st["messageResults"])
+    assert all(h.get("usedSlots", 0) == 0 for h in cluster.client.available_hosts())
+
+
+def test_echo_and_errors(cluster):
+    st = cluster.client.invoke("demo", "echo", input_data="ping")
+    assert st["messageResults"][0]["output_data"] == "ping"
+    st = cluster.client.invoke("demo", "error")
+    assert st["messageResults"][0]["returnValue"] == 1
+    st = cluster.client.invoke("demo", "nope")
+    assert "Unknown function" in st["messageResults"][0]["output_data"]
+    with pytest.raises(PlannerError) as e:
+        cluster.client.invoke("demo", "echo", count=50)
+    assert e.value.status == 500 and "No available hosts" in e.value.body
+
+
+MPI_FUNCTIONS = [
+    "helloworld",
+    "allreduce",
+    "allgather",
+    "alltoall",
+    "bcast",
+    "barrier",
+    "gather-scatter",
+    "reduce-scan",
+    "sendrecv",
+    "isendrecv",
+    "order",
+    "status-probe",
+    "cart",
+]
+
+
+@pytest.mark.parametrize("fn", MPI_FUNCTIONS)
+def test_mpi_across_two_workers(cluster, fn):
+    """World of 4 ranks, 2 per worker process: local queues inside a worker,
+    TCP between the workers."""
+    st = cluster.client.invoke("mpi", fn, mpi_world_size=4, timeout=60)
+    res = _results(st)
+    assert len(res) == 4, res
+    assert [m.get("mpiRank", 0) for m in res] == [0, 1, 2, 3]
+    assert all(m.get("returnValue", 0) == 0 for m in res), res
+    assert {m["executedHost"] for m in res} == set(cluster.worker_hosts())
+
+
+def test_mpi_benchmarks_report(cluster):
+    st = cluster.client.invoke("mpi", "bench-pingpong", mpi_world_size=2, input_data="64", timeout=120)
+    out = json.loads(_results(st)[0]["output_data"])
+    assert out["bytes"] == 64 and out["rtt_us"] > 0
+    st = cluster.client.invoke("mpi", "bench-allreduce", mpi_world_size=4, input_data="65536,5", timeout=120)
+    out = json.loads(_results(st)[0]["output_data"])
+    assert out["count"] == 65536 and out["algbw_GBps"] > 0
+
+
+def test_exec_graph_and_policy(cluster):
+    batch = cluster.client.make_batch("demo", "echo", input_data="g", record_exec_graph=True)
+    cluster.client.execute_batch(batch)
+    cluster.client.wait_for_batch(batch["appId"])
+    graph = cluster.client.exec_graph(batch["appId"], batch["messages"][0]["id"])
+    assert graph["root"]["msg"]["id"] == batch["messages"][0]["id"]
+    assert cluster.client.get_policy() == "bin-pack"
+    cluster.client.set_policy("compact")
+    assert cluster.client.get_policy() == "compact"
+    cluster.client.set_policy("bin-pack")
+    assert cluster.client.in_flight_apps().get("apps", []) == []
+
+
+def test_is_app_migratable_tool(tmp_path):
+    csv = tmp_path / "occ.csv"
+    csv.write_text("WorkerIp,Slots\nfoo,7,7,-1,-1\nbar,7,7,-1,-1\n")
+    assert subprocess.run([str(BIN / "is_app_migratable"), "bin-pack", "7", str(csv)], capture_output=True).returncode == 0
+    csv.write_text("WorkerIp,Slots\nfoo,7,7,7,7\nbar,-1,-1,-1,-1\n")
+    assert subprocess.run([str(BIN / "is_app_migratable"), "compact", "7", str(csv)], capture_output=True).returncode == 1
+    assert subprocess.run([str(BIN / "example_check")], capture_output=True).returncode == 0
