@@ -37,7 +37,7 @@ class ChainedCallException : public faabric::util::FaabricException
     {}
 };
 
-class Executor
+class Executor : public std::enable_shared_from_this<Executor>
 {
   public:
     std::string id;

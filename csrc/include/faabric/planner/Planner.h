@@ -3,6 +3,7 @@
 // src/planner/Planner.cpp).  Hosts are GPU workers of the box.
 #pragma once
 
+#include <condition_variable>
 #include <faabric/batch-scheduler/SchedulingDecision.h>
 #include <faabric/planner/PlannerState.h>
 #include <faabric/proto/faabric.pb.h>
@@ -75,6 +76,10 @@ class Planner
 
     faabric::batch_scheduler::InFlightReqs getInFlightReqs();
 
+    // Blocks until the app has no message in flight (false on timeout).
+    // For callers living in the planner's process.
+    bool waitForAppToFinish(int32_t appId, int timeoutMs);
+
     int getNumMigrations();
 
     std::set<std::string> getNextEvictedHostIps();
@@ -90,6 +95,9 @@ class Planner
 
   private:
     std::shared_mutex plannerMx;
+    std::condition_variable_any appFinishedCv;
+
+    void compactInFlightLocked();
 
     PlannerState state;
     PlannerConfig config;

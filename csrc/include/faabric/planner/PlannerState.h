@@ -7,6 +7,7 @@
 #include <map>
 #include <memory>
 #include <set>
+#include <unordered_set>
 #include <string>
 #include <vector>
 
@@ -30,6 +31,11 @@ struct PlannerState
 
     // In-flight apps: request (messages still running) + current placement
     faabric::batch_scheduler::InFlightReqs inFlightReqs;
+
+    // Messages that have finished but are still physically present in
+    // inFlightReqs: results are recorded in O(1) and the request/decision
+    // vectors are compacted in one pass before anybody reads them
+    std::map<int, std::unordered_set<int>> finishedInFlight;
 
     // Placements fixed ahead of time (MPI / OpenMP two-step creation, tests)
     std::map<int, std::shared_ptr<batch_scheduler::SchedulingDecision>>

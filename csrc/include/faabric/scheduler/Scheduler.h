@@ -104,6 +104,9 @@ class Scheduler
     // Idle-executor reaping, returns how many were reaped
     int reapStaleExecutors();
 
+    // Called by an executor when it becomes claimable again
+    void notifyExecutorIdle(const std::string& funcKey, std::weak_ptr<faabric::executor::Executor> executor);
+
     static const int DEFAULT_THREAD_RESULT_TIMEOUT_MS = 20000;
 
   private:
@@ -121,6 +124,10 @@ class Scheduler
       executors;
 
     // ---- Threads ----
+    // Recently released executors per function (hints: entries may be stale)
+    std::mutex idleMx;
+    std::unordered_map<std::string, std::vector<std::weak_ptr<faabric::executor::Executor>>> idleExecutors;
+
     faabric::snapshot::SnapshotRegistry& reg;
 
     std::unordered_map<uint32_t, std::promise<int32_t>> threadResults;

@@ -192,6 +192,9 @@ void Executor::claim()
 void Executor::releaseClaim()
 {
     claimed.store(false);
+    // Tell the scheduler so the next claim does not have to search for us
+    faabric::scheduler::getScheduler().notifyExecutorIdle(faabric::util::funcToString(boundMessage, false),
+                                                          weak_from_this());
 }
 
 bool Executor::isExecuting()

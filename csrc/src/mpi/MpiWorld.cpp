@@ -813,7 +813,9 @@ void* MpiWorld::streamForRank(int rank)
         deviceStreams.resize(size, nullptr);
     }
     if (deviceStreams[rank] == nullptr) {
-        int dev = faabric::util::gpuForRank(rank);
+        // Same GPU as the rank's communicator when there is one
+        int dev = (rank < (int)deviceComms.size() && deviceComms[rank] != nullptr) ? deviceComms[rank]->device()
+                                                                                   : faabric::util::gpuForRank(rank);
         if (dev >= 0) {
             cudaSetDevice(dev);
             cudaStream_t s = nullptr;

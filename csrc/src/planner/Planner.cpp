@@ -219,6 +219,8 @@ void Planner::flushSchedulingState()
     state.policy = "bin-pack";
     faabric::batch_scheduler::resetBatchScheduler("bin-pack");
     state.inFlightReqs.clear();
+    state.finishedInFlight.clear();
+    appFinishedCv.notify_all();
     state.appResults.clear();
     state.appResultWaiters.clear();
     state.preloadedSchedulingDecisions.clear();
@@ -368,20 +370,22 @@ void Planner::setMessageResult(std::shared_ptr<faabric::Message> msg)
         if (inFlight != state.inFlightReqs.end()) {
             auto& req = inFlight->second.first;
             auto& decision = inFlight->second.second;
-            auto* msgs = req->mutable_messages();
-            auto it = std::find_if(msgs->begin(), msgs->end(), [&](const faabric::Message& m) {
-                return m.id() == msgId;
-            });
-            if (it != msgs->end()) {
-                msgs->erase(it);
-                int port = decision->removeMessage(msgId);
+            auto& done = state.finishedInFlight[appId];
+            // Ids are plain ints: a linear look-up is cheap, moving Message
+            // objects around for every result is not
+            const auto& ids = decision->messageIds;
+            auto pos = std::find(ids.begin(), ids.end(), msgId);
+            if (pos != ids.end() && done.insert(msgId).second) {
+                int port = decision->mpiPorts.at((size_t)(pos - ids.begin()));
                 if (hostIt != state.hostMap.end()) {
                     releaseHostMpiPort(hostIt->second, port);
                 }
-                if (req->messages_size() == 0) {
+                if ((int)done.size() == req->messages_size()) {
                     SPDLOG_DEBUG("Planner removing app {} from in-flight", appId);
                     state.inFlightReqs.erase(inFlight);
+                    state.finishedInFlight.erase(appId);
                     state.preloadedSchedulingDecisions.erase(appId);
+                    appFinishedCv.notify_all();
                 }
             }
         }
@@ -506,17 +510,61 @@ std::shared_ptr<faabric::BatchExecuteRequestStatus> Planner::getBatchResults(
     return status;
 }
 
+void Planner::compactInFlightLocked()
+{
+    for (auto& [appId, done] : state.finishedInFlight) {
+        auto it = state.inFlightReqs.find(appId);
+        if (it == state.inFlightReqs.end() || done.empty()) {
+            continue;
+        }
+        auto& req = it->second.first;
+        auto oldDecision = it->second.second;
+        auto newDecision = std::make_shared<SchedulingDecision>(oldDecision->appId, oldDecision->groupId);
+        newDecision->returnHost = oldDecision->returnHost;
+        faabric::proto::RepeatedField<faabric::Message> kept;
+        for (int i = 0; i < req->messages_size(); i++) {
+            if (done.count(req->messages(i).id()) == 0) {
+                *kept.Add() = std::move(*req->mutable_messages(i));
+            }
+        }
+        for (int i = 0; i < oldDecision->nFunctions; i++) {
+            if (done.count(oldDecision->messageIds[i]) == 0) {
+                newDecision->addMessageInPosition(newDecision->nFunctions,
+                                                  oldDecision->hosts[i],
+                                                  oldDecision->messageIds[i],
+                                                  oldDecision->appIdxs[i],
+                                                  oldDecision->groupIdxs[i],
+                                                  oldDecision->mpiPorts[i]);
+            }
+        }
+        *req->mutable_messages() = std::move(kept);
+        // Holders of the old decision object keep a consistent (stale) view
+        it->second.second = newDecision;
+    }
+    state.finishedInFlight.clear();
+}
+
+bool Planner::waitForAppToFinish(int32_t appId, int timeoutMs)
+{
+    std::shared_lock<std::shared_mutex> lock(plannerMx);
+    return appFinishedCv.wait_for(lock, std::chrono::milliseconds(timeoutMs), [&] {
+        return state.inFlightReqs.find(appId) == state.inFlightReqs.end();
+    });
+}
+
 std::shared_ptr<SchedulingDecision> Planner::getSchedulingDecision(
   std::shared_ptr<BatchExecuteRequest> req)
 {
-    std::shared_lock<std::shared_mutex> lock(plannerMx);
+    std::unique_lock<std::shared_mutex> lock(plannerMx);
+    compactInFlightLocked();
     auto it = state.inFlightReqs.find(req->appid());
     return it == state.inFlightReqs.end() ? nullptr : it->second.second;
 }
 
 faabric::batch_scheduler::InFlightReqs Planner::getInFlightReqs()
 {
-    std::shared_lock<std::shared_mutex> lock(plannerMx);
+    std::unique_lock<std::shared_mutex> lock(plannerMx);
+    compactInFlightLocked();
     faabric::batch_scheduler::InFlightReqs copy;
     for (const auto& [appId, pair] : state.inFlightReqs) {
         copy[appId] = std::make_pair(std::make_shared<BatchExecuteRequest>(*pair.first),
@@ -567,6 +615,7 @@ std::shared_ptr<SchedulingDecision> Planner::callBatch(
     DecisionType type;
     {
         std::unique_lock<std::shared_mutex> lock(plannerMx);
+        compactInFlightLocked();
         auto scheduler = faabric::batch_scheduler::getBatchScheduler();
         type = scheduler->getDecisionType(state.inFlightReqs, req);
         auto hostMapCopy = toSchedulerHostMap(state.hostMap, state.nextEvictedHostIps);
@@ -800,11 +849,14 @@ std::shared_ptr<SchedulingDecision> Planner::callBatch(
         // A migration is carried out by the app itself at its next migration
         // point; everything else is dispatched now.  Dispatch happens under
         // the lock so results cannot overtake the in-flight bookkeeping.
+        // The in-flight table keeps mutating `decision` as results arrive, so
+        // the caller gets its own snapshot taken before anything can finish
+        auto returned = std::make_shared<batch_scheduler::SchedulingDecision>(*decision);
         if (type != DecisionType::DIST_CHANGE) {
             dispatchSchedulingDecision(req, decision);
         }
+        return returned;
     }
-    return decision;
 }
 
 void Planner::dispatchSchedulingDecision(

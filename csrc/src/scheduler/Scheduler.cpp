@@ -119,6 +119,10 @@ void Scheduler::reset()
         }
         executors.clear();
     }
+    {
+        std::lock_guard<std::mutex> lk(idleMx);
+        idleExecutors.clear();
+    }
     for (auto& e : toStop) {
         e->shutdown();
     }
@@ -151,6 +155,12 @@ void Scheduler::shutdown()
 void SchedulerReaperThread::doWork()
 {
     getScheduler().reapStaleExecutors();
+}
+
+void Scheduler::notifyExecutorIdle(const std::string& funcKey, std::weak_ptr<faabric::executor::Executor> executor)
+{
+    std::lock_guard<std::mutex> lk(idleMx);
+    idleExecutors[funcKey].push_back(std::move(executor));
 }
 
 int Scheduler::reapStaleExecutors()
@@ -226,6 +236,23 @@ std::shared_ptr<faabric::executor::Executor> Scheduler::claimExecutor(
   std::unique_lock<std::shared_mutex>& schedulerLock)
 {
     std::string key = executorKey(msg);
+    // Fast path: somebody told us they are idle
+    for (;;) {
+        std::shared_ptr<faabric::executor::Executor> candidate;
+        {
+            std::lock_guard<std::mutex> lk(idleMx);
+            auto it = idleExecutors.find(key);
+            if (it == idleExecutors.end() || it->second.empty()) {
+                break;
+            }
+            candidate = it->second.back().lock();
+            it->second.pop_back();
+        }
+        if (candidate != nullptr && !candidate->isShutdown() && candidate->tryClaim()) {
+            SPDLOG_DEBUG("Reusing warm executor {} for {}", candidate->id, key);
+            return candidate;
+        }
+    }
     auto& vec = executors[key];
     for (auto& e : vec) {
         if (e->tryClaim()) {

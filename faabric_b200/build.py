@@ -209,6 +209,10 @@ def _build_bins(stamp, relink: bool, verbose: bool) -> None:
                         "-lfaabric_b200",
                         f"-Wl,-rpath,{LIBDIR}",
                         "-Wl,-rpath,$ORIGIN/../../faabric_b200/lib",
+                        # the GPU tests allocate device buffers themselves
+                        f"-L{CUDA_HOME / 'lib64'}",
+                        "-lcudart_static",
+                        "-lrt",
                         "-lpthread",
                         "-ldl",
                     ]
