@@ -289,6 +289,49 @@ static void registerFunctions()
         return 0;
     });
 
+    // Headline workload on the HOST path (the reference's design: per-tensor
+    // MPI_Allreduce = reduce to rank 0 + broadcast over in-memory queues).
+    // Input: "steps;warmup;n1,n2,..." element counts of every tensor.
+    mpiFunction("bench-allreduce-list", [](int rank, int size, faabric::Message& msg) {
+        const std::string& in = msg.inputdata();
+        size_t s1 = in.find(';'), s2 = in.find(';', s1 + 1);
+        int steps = std::stoi(in.substr(0, s1));
+        int warmup = std::stoi(in.substr(s1 + 1, s2 - s1 - 1));
+        std::vector<size_t> counts;
+        size_t pos = s2 + 1;
+        while (pos < in.size()) {
+            size_t comma = in.find(',', pos);
+            counts.push_back(std::stoul(in.substr(pos, comma - pos)));
+            if (comma == std::string::npos) {
+                break;
+            }
+            pos = comma + 1;
+        }
+        size_t total = std::accumulate(counts.begin(), counts.end(), (size_t)0);
+        std::vector<int> grads(total, rank + 1), out(total, 0);
+        std::chrono::steady_clock::time_point t0;
+        for (int it = 0; it < warmup + steps; it++) {
+            if (it == warmup) {
+                MPI_Barrier(MPI_COMM_WORLD);
+                t0 = std::chrono::steady_clock::now();
+            }
+            size_t off = 0;
+            for (size_t c : counts) {
+                MPI_Allreduce(grads.data() + off, out.data() + off, (int)c, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+                off += c;
+            }
+        }
+        MPI_Barrier(MPI_COMM_WORLD);
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / steps;
+        EXPECT(out[0] == size * (size + 1) / 2 && out[total - 1] == out[0]);
+        if (rank == 0) {
+            double gbps = (double)total * 4 / (ms * 1e-3) / 1e9;
+            msg.set_outputdata("{\"tensors\": " + std::to_string(counts.size()) + ", \"elements\": " + std::to_string(total) +
+                               ", \"ms_per_step\": " + std::to_string(ms) + ", \"algbw_GBps\": " + std::to_string(gbps) + "}");
+        }
+        return 0;
+    });
+
     // The headline: one "step" of ResNet-50 gradient sync = one int32
     // MPI_Allreduce per parameter tensor, on host memory (reference CPU path)
     mpiFunction("bench-allreduce", [](int rank, int size, faabric::Message& msg) {

@@ -239,9 +239,14 @@ class FixedCapacityQueue
                 throw QueueTimeoutException("Timeout waiting for enqueue");
             }
             UniqueLock lock(mx);
+            blockedProducers.fetch_add(1, std::memory_order_acq_rel);
             notFull.wait_for(lock, std::chrono::microseconds(200));
+            blockedProducers.fetch_sub(1, std::memory_order_acq_rel);
         }
-        if (sleepers.load(std::memory_order_acquire) > 0) {
+        // seq_cst pairing with the consumer: it registers as a sleeper
+        // (under mx) BEFORE its final emptiness check
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+        if (sleepers.load(std::memory_order_seq_cst) > 0) {
             UniqueLock lock(mx);
             notEmpty.notify_one();
         }
@@ -252,7 +257,7 @@ class FixedCapacityQueue
         T v;
         if (ring.tryPop(v)) {
             *res = std::move(v);
-            notFull.notify_one();
+            wakeProducer();
         }
     }
 
@@ -262,28 +267,38 @@ class FixedCapacityQueue
             throw std::runtime_error("Dequeue timeout must be positive");
         }
         T v;
-        for (int i = 0; i < 2000; i++) {
+        // Phase 1: spin for a few tens of microseconds - a peer in the
+        // middle of a ping-pong answers within that time
+        auto start = std::chrono::steady_clock::now();
+        for (int i = 0;; i++) {
             if (ring.tryPop(v)) {
-                notFull.notify_one();
+                wakeProducer();
                 return v;
             }
             FAABRIC_CPU_PAUSE();
+            if ((i & 127) == 127 &&
+                std::chrono::steady_clock::now() - start > std::chrono::microseconds(SPIN_BEFORE_SLEEP_US)) {
+                break;
+            }
         }
-        auto deadline = std::chrono::steady_clock::now() +
-                        std::chrono::milliseconds(timeoutMs);
-        sleepers.fetch_add(1, std::memory_order_acq_rel);
+        // Phase 2: sleep.  The emptiness check and the wait happen under the
+        // same mutex the producer takes to notify, so no wake-up is lost
+        auto deadline = start + std::chrono::milliseconds(timeoutMs);
+        UniqueLock lock(mx);
+        sleepers.fetch_add(1, std::memory_order_seq_cst);
+        std::atomic_thread_fence(std::memory_order_seq_cst);
         while (true) {
             if (ring.tryPop(v)) {
                 sleepers.fetch_sub(1, std::memory_order_acq_rel);
-                notFull.notify_one();
+                lock.unlock();
+                wakeProducer();
                 return v;
             }
             if (std::chrono::steady_clock::now() > deadline) {
                 sleepers.fetch_sub(1, std::memory_order_acq_rel);
                 throw QueueTimeoutException("Timeout waiting for dequeue");
             }
-            UniqueLock lock(mx);
-            notEmpty.wait_for(lock, std::chrono::microseconds(500));
+            notEmpty.wait_for(lock, std::chrono::milliseconds(50));
         }
     }
 
@@ -299,11 +314,22 @@ class FixedCapacityQueue
     void reset() { drain(); }
 
   private:
+    static constexpr int SPIN_BEFORE_SLEEP_US = 50;
+
     BoundedRing<T> ring;
     std::mutex mx;
     std::condition_variable notEmpty;
     std::condition_variable notFull;
     std::atomic<int> sleepers{ 0 };
+    std::atomic<int> blockedProducers{ 0 };
+
+    void wakeProducer()
+    {
+        if (blockedProducers.load(std::memory_order_acquire) > 0) {
+            UniqueLock lock(mx);
+            notFull.notify_one();
+        }
+    }
 };
 
 // Busy-waiting bounded queue for pinned rank threads

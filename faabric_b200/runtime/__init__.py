@@ -9,5 +9,14 @@
 
 from .client import PlannerHttpClient, HttpMessageType, PlannerError
 from .cluster import LocalCluster
+from .benchmarks import planner_fanout_bench, cpu_pingpong_bench, cpu_allreduce_bench
 
-__all__ = ["PlannerHttpClient", "HttpMessageType", "PlannerError", "LocalCluster"]
+__all__ = [
+    "PlannerHttpClient",
+    "HttpMessageType",
+    "PlannerError",
+    "LocalCluster",
+    "planner_fanout_bench",
+    "cpu_pingpong_bench",
+    "cpu_allreduce_bench",
+]

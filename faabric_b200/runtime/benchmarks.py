@@ -1,0 +1,63 @@
+"""CPU-side benchmarks of the native runtime (BASELINE.md configs 1 and 5, and
+the `refcpu` comparator: the reference's host-path design run on this box)."""
+
+from __future__ import annotations
+
+import json
+import subprocess
+
+from .cluster import BINDIR, LocalCluster
+
+
+def planner_fanout_bench(n_functions: int = 1024, n_hosts: int = 8, iters: int = 20, warmup: int = 3) -> dict:
+    """Batch-schedule `n_functions` no-ops over `n_hosts` (virtual GPU) hosts,
+    fan-out + fan-in, planner and worker in one process."""
+    exe = BINDIR / "planner_bench"
+    if not exe.exists():
+        from .. import build as _build
+
+        _build.build(verbose=False)
+    r = subprocess.run(
+        [str(exe), "--functions", str(n_functions), "--hosts", str(n_hosts), "--iters", str(iters), "--warmup", str(warmup)],
+        capture_output=True,
+        text=True,
+        timeout=600,
+    )
+    if r.returncode != 0:
+        raise RuntimeError(f"planner_bench failed: {r.stdout[-500:]} {r.stderr[-500:]}")
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    res["us_per_batch_median"] = res["e2e_us_median"]
+    return res
+
+
+def _first_output(status: dict) -> dict:
+    for m in sorted(status["messageResults"], key=lambda m: m.get("mpiRank", 0)):
+        if m.get("output_data"):
+            return json.loads(m["output_data"])
+    raise RuntimeError(f"no output in {status}")
+
+
+def cpu_pingpong_bench(sizes=(8, 1024, 65536), n_workers: int = 1) -> list[dict]:
+    """MPI ping-pong between two ranks on host memory.  n_workers=1: both ranks
+    in one worker (in-memory queues); 2: one rank per worker process (TCP)."""
+    out = []
+    with LocalCluster(n_workers=n_workers, slots_per_worker=2 // n_workers, log_level="warn") as c:
+        for s in sizes:
+            st = c.client.invoke("mpi", "bench-pingpong", mpi_world_size=2, input_data=str(s), timeout=300)
+            res = _first_output(st)
+            res["transport"] = "local-queue" if n_workers == 1 else "tcp"
+            out.append(res)
+    return out
+
+
+def cpu_allreduce_bench(counts: list[int], world_size: int, steps: int = 3, warmup: int = 1) -> dict:
+    """The headline workload (one MPI_Allreduce per gradient tensor) on the
+    host path: reduce-to-root + broadcast over in-memory queues, malloc+memcpy
+    per hop - the design the reference ships."""
+    payload = f"{steps};{warmup};" + ",".join(str(int(c)) for c in counts)
+    with LocalCluster(n_workers=1, slots_per_worker=world_size, log_level="warn") as c:
+        st = c.client.invoke("mpi", "bench-allreduce-list", mpi_world_size=world_size, input_data=payload, timeout=1800)
+        bad = [m for m in st["messageResults"] if m.get("returnValue", 0) != 0]
+        if bad:
+            raise RuntimeError(f"refcpu ranks failed: {bad[:2]}")
+        return _first_output(st)
