@@ -38,9 +38,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu"])
     ap.add_argument("--mode", default="allreduce",
-                    choices=["allreduce", "sweep", "alltoall", "snapshot", "planner"])
+                    choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "pingpong"])
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--channels", type=int, default=4)
@@ -64,6 +64,59 @@ def reference_arm(args):
                        "package and its deps (boost, protobuf, flatbuffers, nng, absl, spdlog, hiredis, zstd) "
                        "are not installable offline",
     }))
+    return 0
+
+
+def refcpu_arm(args):
+    """`refcpu`: the reference's OWN design - per-tensor MPI_Allreduce as
+    reduce-to-rank-0 + broadcast over in-memory queues with malloc+memcpy per
+    hop - run through this repo's native host path (C++, no GPU involved).
+    World size = --gpus (min 2), ranks are executor threads of one worker."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from faabric_b200.models import resnet50_grad_sizes, small_sizes
+    from faabric_b200.runtime import cpu_allreduce_bench
+
+    sizes = resnet50_grad_sizes() if args.payload == "large" else small_sizes()
+    n = max(args.gpus, 2)
+    res = cpu_allreduce_bench(sizes, n, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)))
+    S = sum(sizes) * 4
+    print(json.dumps({
+        "metric": "mpi_allreduce_resnet50_grads_algbw_GBps",
+        "impl": "refcpu",
+        "value": round(S / (res["ms_per_step"] * 1e-3) / 1e9, 4),
+        "unit": "GB/s",
+        "n_gpus": 0,
+        "world_size": n,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": round(res["ms_per_step"], 3),
+        "higher_is_better": True,
+        "dtype": "int32",
+        "data": "synthetic",
+        "config": {"model": "resnet50-gradients", "tensors": len(sizes), "bytes": S,
+                   "path": "host memory, reduce-to-root + broadcast over in-memory queues"},
+    }), flush=True)
+    return 0
+
+
+def mode_pingpong(args):
+    """BASELINE config 1: MPI ping-pong, world_size=2, CPU only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from faabric_b200.runtime import cpu_pingpong_bench
+
+    local = cpu_pingpong_bench(sizes=(8, 1024, 65536), n_workers=1)
+    tcp = cpu_pingpong_bench(sizes=(8, 1024, 65536), n_workers=2)
+    print(json.dumps({
+        "metric": "mpi_pingpong_rtt_us_8B",
+        "value": local[0]["rtt_us"],
+        "unit": "us",
+        "higher_is_better": False,
+        "n_gpus": 0,
+        "world_size": 2,
+        "details": {"same_worker_queue": local, "two_workers_tcp": tcp},
+    }), flush=True)
     return 0
 
 
@@ -503,13 +556,13 @@ def mode_snapshot(args, dist: Dist):
 def mode_planner(args, dist: Dist):
     from faabric_b200.runtime import planner_fanout_bench
 
-    res = planner_fanout_bench(n_functions=1024, n_hosts=max(dist.world, 8), iters=max(args.steps, 5))
+    res = planner_fanout_bench(n_functions=1024, n_hosts=8, iters=max(args.steps, 5), warmup=max(args.warmup, 2))
     out = {
         "metric": "planner_fanout_fanin_1024_us",
         "value": res["us_per_batch_median"],
         "unit": "us",
         "higher_is_better": False,
-        "n_gpus": dist.world,
+        "n_gpus": 0,
         "details": res,
     }
     return out, {}
@@ -519,6 +572,16 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.impl == "refcpu":
+        return refcpu_arm(args)
+    if args.mode == "pingpong":
+        return mode_pingpong(args)
+    if args.mode == "planner":
+        # CPU only: no process group / GPU needed
+        if int(os.environ.get("RANK", "0")) == 0:
+            out, _ = mode_planner(args, None)
+            print(json.dumps(out), flush=True)
+        return 0
     dist = Dist(args.gpus)
     fn = {
         "allreduce": mode_allreduce,

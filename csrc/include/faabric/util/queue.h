@@ -5,6 +5,7 @@
 //  TokenPool             pool of integer tokens
 #pragma once
 
+#include <thread>
 #include <faabric/util/exception.h>
 #include <faabric/util/locks.h>
 
@@ -276,9 +277,13 @@ class FixedCapacityQueue
                 return v;
             }
             FAABRIC_CPU_PAUSE();
-            if ((i & 127) == 127 &&
-                std::chrono::steady_clock::now() - start > std::chrono::microseconds(SPIN_BEFORE_SLEEP_US)) {
-                break;
+            if ((i & 31) == 31) {
+                // The producer may have been woken onto OUR core (wake-affine
+                // placement): give it a chance instead of starving it
+                std::this_thread::yield();
+                if (std::chrono::steady_clock::now() - start > std::chrono::microseconds(SPIN_BEFORE_SLEEP_US)) {
+                    break;
+                }
             }
         }
         // Phase 2: sleep.  The emptiness check and the wait happen under the
