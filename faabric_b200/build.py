@@ -53,6 +53,10 @@ CXX_FLAGS = [
     "-Wno-unused-function",
     "-pthread",
 ]
+# FAABRIC_B200_SANITISE=address|thread|undefined instruments the HOST code
+_SAN = os.environ.get("FAABRIC_B200_SANITISE", "")
+if _SAN:
+    CXX_FLAGS += [f"-fsanitize={_SAN}", "-O1"]
 INCLUDES = [
     f"-I{CSRC / 'include'}",
     f"-I{CSRC / 'kernels'}",
@@ -164,6 +168,7 @@ def build(force: bool = False, bins: bool = True, jobs: int | None = None, verbo
                 "-Wl,--no-undefined",
                 "-Wl,--export-dynamic",
             ]
+            + ([f"-fsanitize={_SAN}"] if _SAN else [])
         )
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -216,6 +221,7 @@ def _build_bins(stamp, relink: bool, verbose: bool) -> None:
                         "-lpthread",
                         "-ldl",
                     ]
+                    + ([f"-fsanitize={_SAN}"] if _SAN else [])
                 )
                 r = subprocess.run(cmd, capture_output=True, text=True)
                 if r.returncode != 0:

@@ -1,0 +1,102 @@
+"""Developer CLI (the reference ships `invoke` tasks: tasks/dev.py, tasks/tests.py).
+
+  python -m faabric_b200.cli build [--force]
+  python -m faabric_b200.cli test [--gpu] [--cpp FILTER]
+  python -m faabric_b200.cli bench [bench.py args…]
+  python -m faabric_b200.cli cluster [--workers N] [--slots S]   # planner + workers until Ctrl-C
+  python -m faabric_b200.cli invoke USER FUNCTION [--count N] [--mpi SIZE] [--input DATA] --port P
+  python -m faabric_b200.cli sanitise {address,thread,undefined}   # rebuild host code with a sanitizer, run the C++ suite
+  python -m faabric_b200.cli sass KERNEL_REGEX                     # dump SASS of matching kernels
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _run(cmd, **kw):
+    print("+", " ".join(str(c) for c in cmd), flush=True)
+    return subprocess.call(cmd, **kw)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="faabric_b200.cli")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    b = sub.add_parser("build")
+    b.add_argument("--force", action="store_true")
+    t = sub.add_parser("test")
+    t.add_argument("--gpu", action="store_true")
+    t.add_argument("--cpp", default=None, help="run only the C++ suite with this name filter")
+    be = sub.add_parser("bench")
+    be.add_argument("rest", nargs=argparse.REMAINDER)
+    c = sub.add_parser("cluster")
+    c.add_argument("--workers", type=int, default=2)
+    c.add_argument("--slots", type=int, default=4)
+    i = sub.add_parser("invoke")
+    i.add_argument("user")
+    i.add_argument("function")
+    i.add_argument("--count", type=int, default=1)
+    i.add_argument("--mpi", type=int, default=0)
+    i.add_argument("--input", default=None)
+    i.add_argument("--host", default="127.0.0.1")
+    i.add_argument("--port", type=int, default=8080)
+    s = sub.add_parser("sanitise")
+    s.add_argument("kind", choices=["address", "thread", "undefined"])
+    sa = sub.add_parser("sass")
+    sa.add_argument("regex")
+    a = ap.parse_args(argv)
+
+    if a.cmd == "build":
+        from . import build as _b
+
+        _b.build(force=a.force)
+        return 0
+    if a.cmd == "test":
+        if a.cpp is not None:
+            return _run([str(ROOT / "build" / "bin" / "faabric_tests"), a.cpp])
+        marker = "gpu" if a.gpu else "not gpu"
+        return _run([sys.executable, "-m", "pytest", "tests", "-x", "-q", "-m", marker], cwd=ROOT)
+    if a.cmd == "bench":
+        return _run([sys.executable, str(ROOT / "bench.py")] + a.rest, cwd=ROOT)
+    if a.cmd == "cluster":
+        from .runtime import LocalCluster
+
+        with LocalCluster(n_workers=a.workers, slots_per_worker=a.slots, log_dir=ROOT / "build" / "cluster-logs") as cl:
+            print(f"planner HTTP on 127.0.0.1:{cl.http_port}; workers: {cl.worker_hosts()} (Ctrl-C to stop)", flush=True)
+            try:
+                while True:
+                    time.sleep(1)
+            except KeyboardInterrupt:
+                pass
+        return 0
+    if a.cmd == "invoke":
+        from .runtime import PlannerHttpClient
+
+        cli = PlannerHttpClient(a.host, a.port)
+        st = cli.invoke(a.user, a.function, a.count, input_data=a.input, mpi_world_size=a.mpi)
+        print(json.dumps(st, indent=1))
+        return 0
+    if a.cmd == "sanitise":
+        # Host code only (device code has compute-sanitizer): separate object dir
+        env = dict(os.environ)
+        env["FAABRIC_B200_SANITISE"] = a.kind
+        rc = _run([sys.executable, "-m", "faabric_b200.build", "--force"], cwd=ROOT, env=env)
+        if rc != 0:
+            return rc
+        return _run([str(ROOT / "build" / "bin" / "faabric_tests")], env=env)
+    if a.cmd == "sass":
+        lib = ROOT / "faabric_b200" / "lib" / "libfaabric_b200.so"
+        return _run(["bash", "-c", f"cuobjdump -sass {lib} | grep -E -A400 'Function : .*({a.regex})' | head -n 600"])
+    return 1
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
