@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-device"])
     ap.add_argument("--mode", default="allreduce",
                     choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "pingpong"])
     ap.add_argument("--algo", default="auto")
@@ -75,15 +75,17 @@ def refcpu_arm(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     from faabric_b200.models import resnet50_grad_sizes, small_sizes
-    from faabric_b200.runtime import cpu_allreduce_bench
+    from faabric_b200.runtime import mpi_allreduce_bench
 
     sizes = resnet50_grad_sizes() if args.payload == "large" else small_sizes()
     n = max(args.gpus, 2)
-    res = cpu_allreduce_bench(sizes, n, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)))
+    device = args.impl == "mpi-device"
+    res = mpi_allreduce_bench(sizes, n, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)),
+                              memory="device" if device else "host")
     S = sum(sizes) * 4
     print(json.dumps({
         "metric": "mpi_allreduce_resnet50_grads_algbw_GBps",
-        "impl": "refcpu",
+        "impl": args.impl,
         "value": round(S / (res["ms_per_step"] * 1e-3) / 1e9, 4),
         "unit": "GB/s",
         "n_gpus": 0,
@@ -95,7 +97,8 @@ def refcpu_arm(args):
         "dtype": "int32",
         "data": "synthetic",
         "config": {"model": "resnet50-gradients", "tensors": len(sizes), "bytes": S,
-                   "path": "host memory, reduce-to-root + broadcast over in-memory queues"},
+                   "path": "MPI C API, device buffers, one fused kernel per call, host-synchronous" if device
+                   else "host memory, reduce-to-root + broadcast over in-memory queues"},
     }), flush=True)
     return 0
 
@@ -572,7 +575,7 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
-    if args.impl == "refcpu":
+    if args.impl in ("refcpu", "mpi-device"):
         return refcpu_arm(args)
     if args.mode == "pingpong":
         return mode_pingpong(args)

@@ -7,6 +7,8 @@
 #include <faabric/endpoint/FaabricEndpoint.h>
 #include <faabric/endpoint/FaabricEndpointHandler.h>
 #include <faabric/executor/ExecutorFactory.h>
+#include <faabric/mpi/MpiWorld.h>
+#include <faabric/mpi/MpiWorldRegistry.h>
 #include <faabric/mpi/mpi.h>
 #include <faabric/planner/PlannerClient.h>
 #include <faabric/runner/FaabricMain.h>
@@ -14,6 +16,8 @@
 #include <faabric/util/batch.h>
 #include <faabric/util/config.h>
 #include <faabric/util/logging.h>
+
+#include <cuda_runtime.h>
 
 #include <chrono>
 #include <cmath>
@@ -289,16 +293,19 @@ static void registerFunctions()
         return 0;
     });
 
-    // Headline workload on the HOST path (the reference's design: per-tensor
-    // MPI_Allreduce = reduce to rank 0 + broadcast over in-memory queues).
-    // Input: "steps;warmup;n1,n2,..." element counts of every tensor.
+    // Headline workload through the MPI C API: one MPI_Allreduce per tensor.
+    // Input: "steps;warmup;host|device;n1,n2,..." (element counts).
+    //  host   = the reference's design (reduce to rank 0 + broadcast over
+    //           in-memory queues, malloc+memcpy per hop)
+    //  device = buffers in HBM, every call is one fused P2P/NVLS kernel
     mpiFunction("bench-allreduce-list", [](int rank, int size, faabric::Message& msg) {
         const std::string& in = msg.inputdata();
-        size_t s1 = in.find(';'), s2 = in.find(';', s1 + 1);
+        size_t s1 = in.find(';'), s2 = in.find(';', s1 + 1), s3 = in.find(';', s2 + 1);
         int steps = std::stoi(in.substr(0, s1));
         int warmup = std::stoi(in.substr(s1 + 1, s2 - s1 - 1));
+        bool onDevice = in.substr(s2 + 1, s3 - s2 - 1) == "device";
         std::vector<size_t> counts;
-        size_t pos = s2 + 1;
+        size_t pos = s3 + 1;
         while (pos < in.size()) {
             size_t comma = in.find(',', pos);
             counts.push_back(std::stoul(in.substr(pos, comma - pos)));
@@ -308,7 +315,23 @@ static void registerFunctions()
             pos = comma + 1;
         }
         size_t total = std::accumulate(counts.begin(), counts.end(), (size_t)0);
-        std::vector<int> grads(total, rank + 1), out(total, 0);
+        std::vector<int> hostGrads(total, rank + 1), hostOut(total, 0);
+        int* grads = hostGrads.data();
+        int* out = hostOut.data();
+        if (onDevice) {
+            auto& world = faabric::mpi::getMpiWorldRegistry().getWorld(msg.mpiworldid());
+            auto comm = world.getDeviceComm(rank);
+            if (comm == nullptr) {
+                msg.set_outputdata("no device communicator for rank " + std::to_string(rank));
+                return 1;
+            }
+            cudaSetDevice(comm->device());
+            if (cudaMalloc(&grads, total * sizeof(int)) != cudaSuccess || cudaMalloc(&out, total * sizeof(int)) != cudaSuccess) {
+                msg.set_outputdata("cudaMalloc failed");
+                return 1;
+            }
+            cudaMemcpy(grads, hostGrads.data(), total * sizeof(int), cudaMemcpyHostToDevice);
+        }
         std::chrono::steady_clock::time_point t0;
         for (int it = 0; it < warmup + steps; it++) {
             if (it == warmup) {
@@ -317,17 +340,23 @@ static void registerFunctions()
             }
             size_t off = 0;
             for (size_t c : counts) {
-                MPI_Allreduce(grads.data() + off, out.data() + off, (int)c, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+                MPI_Allreduce(grads + off, out + off, (int)c, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
                 off += c;
             }
         }
         MPI_Barrier(MPI_COMM_WORLD);
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / steps;
-        EXPECT(out[0] == size * (size + 1) / 2 && out[total - 1] == out[0]);
+        if (onDevice) {
+            cudaMemcpy(hostOut.data(), out, total * sizeof(int), cudaMemcpyDeviceToHost);
+            cudaFree(grads);
+            cudaFree(out);
+        }
+        EXPECT(hostOut[0] == size * (size + 1) / 2 && hostOut[total - 1] == hostOut[0]);
         if (rank == 0) {
             double gbps = (double)total * 4 / (ms * 1e-3) / 1e9;
             msg.set_outputdata("{\"tensors\": " + std::to_string(counts.size()) + ", \"elements\": " + std::to_string(total) +
-                               ", \"ms_per_step\": " + std::to_string(ms) + ", \"algbw_GBps\": " + std::to_string(gbps) + "}");
+                               ", \"memory\": \"" + (onDevice ? "device" : "host") + "\", \"ms_per_step\": " + std::to_string(ms) +
+                               ", \"algbw_GBps\": " + std::to_string(gbps) + "}");
         }
         return 0;
     });

@@ -309,6 +309,22 @@ class MpiWorld
     std::vector<void*> deviceStreams; // cudaStream_t per rank
     std::atomic<uint64_t> deviceCollectives = 0;
     void ensureDeviceComms();
+
+    // Eager device sends park their payload in the SENDER's symmetric heap;
+    // the receiver pulls it over NVLink through its mapping of that heap and
+    // hands the block back.  One arena per rank, carved out at wiring time.
+    struct StagingArena
+    {
+        std::mutex mx;
+        uint64_t base = 0;
+        uint64_t size = 0;
+        std::map<uint64_t, uint64_t> freeBlocks; // offset -> size
+        std::map<uint64_t, uint64_t> usedBlocks;
+    };
+    std::vector<std::unique_ptr<StagingArena>> stagingArenas;
+    uint8_t* stageAlloc(int rank, size_t bytes);
+    void stageFree(int ownerRank, const void* ownerPtr);
+    const uint8_t* peerViewOfStaged(int ownerRank, int viewerRank, const void* ownerPtr);
     void* streamForRank(int rank);
     // Returns true if the collective ran on the device path
     bool tryDeviceAllReduce(int rank, uint8_t* send, uint8_t* recv, faabric_datatype_t* dt, int count, faabric_op_t* op);

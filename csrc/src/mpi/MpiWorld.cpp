@@ -562,16 +562,28 @@ void MpiWorld::send(int sendRank,
     if (isLocal && !faabric::util::isMockMode()) {
         // Eager copy so the caller may reuse its buffer as soon as we return
         if (bytes > 0 && onDevice) {
-            // Stay on the device: the receiver pulls it with a peer copy
-            void* staged = nullptr;
-            cudaStream_t s = (cudaStream_t)streamForRank(sendRank);
-            if (cudaMallocAsync(&staged, bytes, s) != cudaSuccess ||
-                cudaMemcpyAsync(staged, buffer, bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
-                cudaStreamSynchronize(s) != cudaSuccess) {
-                cudaGetLastError();
-                throw std::runtime_error("Device staging for MPI send failed");
+            // Stay on the device when the ranks are wired: park the payload
+            // in our symmetric heap, the receiver pulls it over NVLink
+            uint8_t* staged = getDeviceComm(sendRank) != nullptr ? stageAlloc(sendRank, bytes) : nullptr;
+            if (staged != nullptr) {
+                cudaStream_t s = (cudaStream_t)streamForRank(sendRank);
+                cudaSetDevice(deviceComms[sendRank]->device());
+                if (cudaMemcpyAsync(staged, buffer, bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+                    cudaStreamSynchronize(s) != cudaSuccess) {
+                    cudaGetLastError();
+                    stageFree(sendRank, staged);
+                    throw std::runtime_error("Device staging for MPI send failed");
+                }
+                msg.buffer = staged;
+            } else {
+                // Arena full or no peer wiring: bounce through host memory
+                msg.buffer = malloc(bytes);
+                if (cudaMemcpy(msg.buffer, buffer, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                    cudaGetLastError();
+                    free(msg.buffer);
+                    throw std::runtime_error("Device to host copy for MPI send failed");
+                }
             }
-            msg.buffer = staged;
         } else if (bytes > 0) {
             msg.buffer = malloc(bytes);
             memcpy(msg.buffer, buffer, bytes);
@@ -646,8 +658,12 @@ void MpiWorld::doRecv(MpiMessage& msg,
 {
     if (msg.messageType != messageType) {
         SPDLOG_ERROR("Message types mismatched on {}->{} (expected={}, got={})", msg.sendRank, msg.recvRank, (int)messageType, (int)msg.messageType);
-        if (msg.buffer != nullptr && !isDevicePointer(msg.buffer)) {
-            free(msg.buffer);
+        if (msg.buffer != nullptr) {
+            if (isDevicePointer(msg.buffer)) {
+                stageFree(msg.sendRank, msg.buffer);
+            } else {
+                free(msg.buffer);
+            }
         }
         throw std::runtime_error("Mismatched MPI message types");
     }
@@ -659,15 +675,26 @@ void MpiWorld::doRecv(MpiMessage& msg,
     if (bytes > 0 && msg.buffer != nullptr) {
         const bool srcDev = isDevicePointer(msg.buffer);
         const bool dstDev = isDevicePointer(buffer);
-        if (srcDev || dstDev) {
+        if (srcDev) {
+            // Parked in the sender's heap: read it through OUR mapping
+            const uint8_t* src = peerViewOfStaged(msg.sendRank, msg.recvRank, msg.buffer);
             cudaStream_t s = (cudaStream_t)streamForRank(msg.recvRank);
-            cudaMemcpyAsync(buffer, msg.buffer, bytes, cudaMemcpyDefault, s);
-            if (srcDev) {
-                cudaFreeAsync(msg.buffer, s);
+            cudaSetDevice(deviceComms[msg.recvRank]->device());
+            cudaError_t e = cudaMemcpyAsync(buffer, src, bytes, cudaMemcpyDefault, s);
+            if (e == cudaSuccess) {
+                e = cudaStreamSynchronize(s);
             }
-            cudaStreamSynchronize(s);
-            if (!srcDev) {
-                free(msg.buffer);
+            stageFree(msg.sendRank, msg.buffer);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                throw std::runtime_error(std::string("Peer copy for MPI recv failed: ") + cudaGetErrorString(e));
+            }
+        } else if (dstDev) {
+            cudaError_t e = cudaMemcpy(buffer, msg.buffer, bytes, cudaMemcpyHostToDevice);
+            free(msg.buffer);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                throw std::runtime_error("Host to device copy for MPI recv failed");
             }
         } else {
             memcpy(buffer, msg.buffer, bytes);
@@ -858,6 +885,16 @@ void MpiWorld::ensureDeviceComms()
             }
             deviceComms = faabric::device::Communicator::createLocal(size, devices, cfg);
             SPDLOG_INFO("MPI world {}: device communicators up ({} ranks, backing {})", id, size, deviceComms[0]->backing());
+            // Same allocation on every rank => same offset in every heap
+            size_t arenaBytes = std::min<size_t>((size_t)64 << 20, cfg.heapBytes / 4);
+            stagingArenas.clear();
+            for (int r = 0; r < size; r++) {
+                auto arena = std::make_unique<StagingArena>();
+                arena->base = deviceComms[r]->alloc(arenaBytes);
+                arena->size = arenaBytes;
+                arena->freeBlocks[0] = arenaBytes;
+                stagingArenas.push_back(std::move(arena));
+            }
         } else if (allDistinctHosts && tls.rank >= 0) {
             // One rank per worker process: wire peer memory across processes
             deviceComms.assign(size, nullptr);
@@ -868,6 +905,64 @@ void MpiWorld::ensureDeviceComms()
         SPDLOG_WARN("MPI world {}: no device communicators ({})", id, e.what());
         deviceComms.clear();
     }
+}
+
+uint8_t* MpiWorld::stageAlloc(int rank, size_t bytes)
+{
+    if (rank < 0 || rank >= (int)stagingArenas.size() || rank >= (int)deviceComms.size() || deviceComms[rank] == nullptr) {
+        return nullptr;
+    }
+    StagingArena& a = *stagingArenas[rank];
+    uint64_t need = (bytes + 255) & ~(uint64_t)255;
+    std::lock_guard<std::mutex> lk(a.mx);
+    for (auto it = a.freeBlocks.begin(); it != a.freeBlocks.end(); ++it) {
+        if (it->second < need) {
+            continue;
+        }
+        uint64_t off = it->first;
+        uint64_t rest = it->second - need;
+        a.freeBlocks.erase(it);
+        if (rest > 0) {
+            a.freeBlocks[off + need] = rest;
+        }
+        a.usedBlocks[off] = need;
+        return deviceComms[rank]->heapPtr(a.base + off);
+    }
+    return nullptr;
+}
+
+void MpiWorld::stageFree(int ownerRank, const void* ownerPtr)
+{
+    StagingArena& a = *stagingArenas.at(ownerRank);
+    uint64_t off = deviceComms[ownerRank]->offsetOf(ownerPtr) - a.base;
+    std::lock_guard<std::mutex> lk(a.mx);
+    auto used = a.usedBlocks.find(off);
+    if (used == a.usedBlocks.end()) {
+        SPDLOG_ERROR("Freeing unknown staging block of rank {}", ownerRank);
+        return;
+    }
+    uint64_t len = used->second;
+    a.usedBlocks.erase(used);
+    // Coalesce with the neighbours
+    auto next = a.freeBlocks.lower_bound(off);
+    if (next != a.freeBlocks.end() && off + len == next->first) {
+        len += next->second;
+        next = a.freeBlocks.erase(next);
+    }
+    if (next != a.freeBlocks.begin()) {
+        auto prev = std::prev(next);
+        if (prev->first + prev->second == off) {
+            prev->second += len;
+            return;
+        }
+    }
+    a.freeBlocks[off] = len;
+}
+
+const uint8_t* MpiWorld::peerViewOfStaged(int ownerRank, int viewerRank, const void* ownerPtr)
+{
+    uint64_t off = deviceComms[ownerRank]->offsetOf(ownerPtr);
+    return deviceComms[viewerRank]->heapPtr(off, ownerRank);
 }
 
 std::shared_ptr<faabric::device::Communicator> MpiWorld::getDeviceComm(int rank)

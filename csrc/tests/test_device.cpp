@@ -244,7 +244,12 @@ TEST_CASE("gpu: device snapshot diff+merge+push matches the host implementation"
     auto got = devMain.getDataCopy(0, size);
     size_t mismatches = 0;
     for (size_t i = 0; i < size; i++) {
-        mismatches += got[i] != expected[i];
+        if (got[i] != expected[i]) {
+            if (mismatches < 8) {
+                printf("         mismatch at %zu: device %d host %d (base %d updated %d)\n", i, got[i], expected[i], base[i], updated[i]);
+            }
+            mismatches++;
+        }
     }
     REQUIRE_EQ(mismatches, 0u);
     REQUIRE(stats.diffBytes > 0);

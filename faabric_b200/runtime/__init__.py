@@ -9,7 +9,7 @@
 
 from .client import PlannerHttpClient, HttpMessageType, PlannerError
 from .cluster import LocalCluster
-from .benchmarks import planner_fanout_bench, cpu_pingpong_bench, cpu_allreduce_bench
+from .benchmarks import planner_fanout_bench, cpu_pingpong_bench, cpu_allreduce_bench, mpi_allreduce_bench
 
 __all__ = [
     "PlannerHttpClient",
@@ -19,4 +19,5 @@ __all__ = [
     "planner_fanout_bench",
     "cpu_pingpong_bench",
     "cpu_allreduce_bench",
+    "mpi_allreduce_bench",
 ]

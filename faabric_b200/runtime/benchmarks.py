@@ -50,14 +50,20 @@ def cpu_pingpong_bench(sizes=(8, 1024, 65536), n_workers: int = 1) -> list[dict]
     return out
 
 
-def cpu_allreduce_bench(counts: list[int], world_size: int, steps: int = 3, warmup: int = 1) -> dict:
-    """The headline workload (one MPI_Allreduce per gradient tensor) on the
-    host path: reduce-to-root + broadcast over in-memory queues, malloc+memcpy
-    per hop - the design the reference ships."""
-    payload = f"{steps};{warmup};" + ",".join(str(int(c)) for c in counts)
+def mpi_allreduce_bench(counts: list[int], world_size: int, steps: int = 3, warmup: int = 1, memory: str = "host") -> dict:
+    """The headline workload (one MPI_Allreduce per gradient tensor) through
+    the MPI C API of a worker process.  memory="host": reduce-to-root +
+    broadcast over in-memory queues, malloc+memcpy per hop - the design the
+    reference ships.  memory="device": buffers in HBM, each call one fused
+    P2P/NVLS kernel (needs GPUs)."""
+    payload = f"{steps};{warmup};{memory};" + ",".join(str(int(c)) for c in counts)
     with LocalCluster(n_workers=1, slots_per_worker=world_size, log_level="warn") as c:
         st = c.client.invoke("mpi", "bench-allreduce-list", mpi_world_size=world_size, input_data=payload, timeout=1800)
         bad = [m for m in st["messageResults"] if m.get("returnValue", 0) != 0]
         if bad:
             raise RuntimeError(f"refcpu ranks failed: {bad[:2]}")
         return _first_output(st)
+
+
+def cpu_allreduce_bench(counts: list[int], world_size: int, steps: int = 3, warmup: int = 1) -> dict:
+    return mpi_allreduce_bench(counts, world_size, steps, warmup, memory="host")
