@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-device"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-device", "mpi-symmetric", "mpi-symmetric-nb"])
     ap.add_argument("--mode", default="allreduce",
                     choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "pingpong"])
     ap.add_argument("--algo", default="auto")
@@ -79,9 +79,9 @@ def refcpu_arm(args):
 
     sizes = resnet50_grad_sizes() if args.payload == "large" else small_sizes()
     n = max(args.gpus, 2)
-    device = args.impl == "mpi-device"
+    device = args.impl.startswith("mpi-")
     res = mpi_allreduce_bench(sizes, n, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)),
-                              memory="device" if device else "host")
+                              memory=args.impl[4:] if device else "host")
     S = sum(sizes) * 4
     print(json.dumps({
         "metric": "mpi_allreduce_resnet50_grads_algbw_GBps",
@@ -97,7 +97,7 @@ def refcpu_arm(args):
         "dtype": "int32",
         "data": "synthetic",
         "config": {"model": "resnet50-gradients", "tensors": len(sizes), "bytes": S,
-                   "path": "MPI C API, device buffers, one fused kernel per call, host-synchronous" if device
+                   "path": f"MPI C API ({args.impl[4:]} memory), one fused kernel per MPI call" if device
                    else "host memory, reduce-to-root + broadcast over in-memory queues"},
     }), flush=True)
     return 0
@@ -575,7 +575,7 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
-    if args.impl in ("refcpu", "mpi-device"):
+    if args.impl == "refcpu" or args.impl.startswith("mpi-"):
         return refcpu_arm(args)
     if args.mode == "pingpong":
         return mode_pingpong(args)

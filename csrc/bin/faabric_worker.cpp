@@ -303,7 +303,12 @@ static void registerFunctions()
         size_t s1 = in.find(';'), s2 = in.find(';', s1 + 1), s3 = in.find(';', s2 + 1);
         int steps = std::stoi(in.substr(0, s1));
         int warmup = std::stoi(in.substr(s1 + 1, s2 - s1 - 1));
-        bool onDevice = in.substr(s2 + 1, s3 - s2 - 1) == "device";
+        // host | device (cudaMalloc) | symmetric (MPI_Alloc_mem in the
+        // symmetric heap) | symmetric-nb (same + MPI_Iallreduce/Waitall)
+        std::string memory = in.substr(s2 + 1, s3 - s2 - 1);
+        bool onDevice = memory != "host";
+        bool symmetric = memory.rfind("symmetric", 0) == 0;
+        bool nonBlocking = memory == "symmetric-nb";
         std::vector<size_t> counts;
         size_t pos = s3 + 1;
         while (pos < in.size()) {
@@ -326,12 +331,20 @@ static void registerFunctions()
                 return 1;
             }
             cudaSetDevice(comm->device());
-            if (cudaMalloc(&grads, total * sizeof(int)) != cudaSuccess || cudaMalloc(&out, total * sizeof(int)) != cudaSuccess) {
-                msg.set_outputdata("cudaMalloc failed");
+            bool ok;
+            if (symmetric) {
+                ok = MPI_Alloc_mem(total * sizeof(int), MPI_INFO_FAABRIC_DEVICE, &grads) == MPI_SUCCESS &&
+                     MPI_Alloc_mem(total * sizeof(int), MPI_INFO_FAABRIC_DEVICE, &out) == MPI_SUCCESS;
+            } else {
+                ok = cudaMalloc(&grads, total * sizeof(int)) == cudaSuccess && cudaMalloc(&out, total * sizeof(int)) == cudaSuccess;
+            }
+            if (!ok) {
+                msg.set_outputdata("device allocation failed (FAABRIC_SYMM_HEAP_BYTES too small?)");
                 return 1;
             }
             cudaMemcpy(grads, hostGrads.data(), total * sizeof(int), cudaMemcpyHostToDevice);
         }
+        std::vector<MPI_Request> reqs(counts.size());
         std::chrono::steady_clock::time_point t0;
         for (int it = 0; it < warmup + steps; it++) {
             if (it == warmup) {
@@ -339,23 +352,35 @@ static void registerFunctions()
                 t0 = std::chrono::steady_clock::now();
             }
             size_t off = 0;
-            for (size_t c : counts) {
-                MPI_Allreduce(grads + off, out + off, (int)c, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
-                off += c;
+            for (size_t i = 0; i < counts.size(); i++) {
+                if (nonBlocking) {
+                    MPI_Iallreduce(grads + off, out + off, (int)counts[i], MPI_INT, MPI_SUM, MPI_COMM_WORLD, &reqs[i]);
+                } else {
+                    MPI_Allreduce(grads + off, out + off, (int)counts[i], MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+                }
+                off += counts[i];
+            }
+            if (nonBlocking) {
+                MPI_Waitall((int)reqs.size(), reqs.data(), MPI_STATUSES_IGNORE);
             }
         }
         MPI_Barrier(MPI_COMM_WORLD);
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / steps;
         if (onDevice) {
             cudaMemcpy(hostOut.data(), out, total * sizeof(int), cudaMemcpyDeviceToHost);
-            cudaFree(grads);
-            cudaFree(out);
+            if (symmetric) {
+                MPI_Free_mem(grads);
+                MPI_Free_mem(out);
+            } else {
+                cudaFree(grads);
+                cudaFree(out);
+            }
         }
         EXPECT(hostOut[0] == size * (size + 1) / 2 && hostOut[total - 1] == hostOut[0]);
         if (rank == 0) {
             double gbps = (double)total * 4 / (ms * 1e-3) / 1e9;
             msg.set_outputdata("{\"tensors\": " + std::to_string(counts.size()) + ", \"elements\": " + std::to_string(total) +
-                               ", \"memory\": \"" + (onDevice ? "device" : "host") + "\", \"ms_per_step\": " + std::to_string(ms) +
+                               ", \"memory\": \"" + memory + "\", \"ms_per_step\": " + std::to_string(ms) +
                                ", \"algbw_GBps\": " + std::to_string(gbps) + "}");
         }
         return 0;

@@ -173,6 +173,8 @@ class Communicator
 
     // Device watchdog error word (FB_ERR_*); synchronises `s`
     uint32_t checkError(cudaStream_t s);
+    // Same word without synchronising (caller has already waited for `s`)
+    uint32_t peekError() const;
     // Host-side barrier between the ranks' host threads / processes
     void hostBarrier();
     // Last algorithm picked by allReduce (for reporting / tests)

@@ -191,6 +191,22 @@ class MpiWorld
                    faabric_op_t* operation);
 
     // Element-wise resultBuffer = op(inBuffer, resultBuffer) on the host
+    // Non-blocking all-reduce (MPI-3 MPI_Iallreduce; not in the reference).
+    // On device buffers it is stream-ordered: successive calls pipeline on
+    // the communicator's channels, MPI_Wait drains the stream.
+    int iAllReduce(int rank,
+                   uint8_t* sendBuffer,
+                   uint8_t* recvBuffer,
+                   faabric_datatype_t* datatype,
+                   int count,
+                   faabric_op_t* operation);
+
+    // Symmetric-heap allocation for MPI_Alloc_mem (collective: every rank
+    // must allocate the same sizes in the same order)
+    void* deviceAlloc(int rank, size_t bytes);
+
+    bool deviceFree(int rank, void* ptr);
+
     void op_reduce(faabric_op_t* operation,
                    faabric_datatype_t* datatype,
                    int count,
@@ -325,7 +341,7 @@ class MpiWorld
     uint8_t* stageAlloc(int rank, size_t bytes);
     void stageFree(int ownerRank, const void* ownerPtr);
     const uint8_t* peerViewOfStaged(int ownerRank, int viewerRank, const void* ownerPtr);
-    void* streamForRank(int rank);
+    void* streamForRank(int rank, int channel = 0);
     // Returns true if the collective ran on the device path
     bool tryDeviceAllReduce(int rank, uint8_t* send, uint8_t* recv, faabric_datatype_t* dt, int count, faabric_op_t* op);
 };

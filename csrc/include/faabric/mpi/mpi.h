@@ -16,6 +16,7 @@ extern "C"
 
 #define MPI_SUCCESS 0
 #define MPI_ERR_OTHER 1
+#define MPI_ERR_NO_MEM 2
 #define MPI_MAX_OBJECT_NAME 128
 
     /* ---- opaque-ish handle structs ---- */
@@ -150,8 +151,13 @@ extern "C"
 #define MPI_IN_PLACE (void*)FAABRIC_IN_PLACE
 
 #define FAABRIC_INFO_NULL 1
+#define FAABRIC_INFO_DEVICE 2
     extern struct faabric_info_t faabric_info_null;
+    extern struct faabric_info_t faabric_info_device;
 #define MPI_INFO_NULL &faabric_info_null
+// Extension: MPI_Alloc_mem with this info allocates from the rank's symmetric
+// heap in GPU memory (collective across the world)
+#define MPI_INFO_FAABRIC_DEVICE &faabric_info_device
 
 #define MPI_ANY_SOURCE -1
 #define MPI_UNDEFINED -1
@@ -307,6 +313,7 @@ extern "C"
     int MPI_Op_free(MPI_Op* op);
 
     int MPI_Alloc_mem(MPI_Aint size, MPI_Info info, void* baseptr);
+    int MPI_Iallreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm, MPI_Request* request);
     int MPI_Free_mem(void* base);
     int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, MPI_Win* win);
     int MPI_Win_allocate_shared(MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, void* baseptr, MPI_Win* win);

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(FB_LL_THREADS, 1) llAllReduceKernel(
                         t0 = now;
                     } else if (now - t0 > c.timeoutNs) {
                         if (c.err != nullptr) {
-                            atomicMax(c.err, FB_ERR_FLAG_TIMEOUT);
+                            stRelaxedSys(c.err, FB_ERR_FLAG_TIMEOUT);
                         }
                         ok = false;
                         break;

@@ -82,7 +82,7 @@ __device__ __forceinline__ bool waitFlagGe(const FbCommDev& c,
         if ((++spins & 0x3ff) == 0) {
             if (globalTimerNs() - t0 > c.timeoutNs) {
                 if (c.err != nullptr) {
-                    atomicMax(c.err, errCode);
+                    stRelaxedSys(c.err, errCode); // host-mapped word: plain store, no PCIe atomic
                 }
                 return false;
             }

@@ -141,7 +141,7 @@ struct Communicator::Backing
         }
         for (size_t i = 0; i < errWords.size(); i++) {
             cudaSetDevice(errDevices[i]);
-            cudaFree(errWords[i]);
+            cudaFreeHost(errWords[i]);
         }
         cudaGetLastError();
     }
@@ -403,9 +403,11 @@ std::vector<std::shared_ptr<Communicator>> Communicator::createLocal(
     for (int r = 0; r < nranks; r++) {
         CUDA_OK(cudaSetDevice(devices[r]));
         CUDA_OK(cudaMemset(bases[r], 0, SIG_REGION + comms[r]->userOff_));
+        // Watchdog error word: pinned host memory the kernels can write, so
+        // the host reads it after a stream sync without a device round trip
         uint32_t* err = nullptr;
-        CUDA_OK(cudaMalloc((void**)&err, 256));
-        CUDA_OK(cudaMemset(err, 0, 256));
+        CUDA_OK(cudaHostAlloc((void**)&err, 256, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(err, 0, 256);
         backing->errWords.push_back(err);
         backing->errDevices.push_back(devices[r]);
         CUDA_OK(cudaDeviceSynchronize());
@@ -674,8 +676,8 @@ std::shared_ptr<Communicator> Communicator::createIpc(int rank,
     CUDA_OK(fb::preloadAllKernels());
     CUDA_OK(cudaMemset(bases[rank], 0, SIG_REGION + c->userOff_));
     uint32_t* err = nullptr;
-    CUDA_OK(cudaMalloc((void**)&err, 256));
-    CUDA_OK(cudaMemset(err, 0, 256));
+    CUDA_OK(cudaHostAlloc((void**)&err, 256, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(err, 0, 256);
     backing->errWords.push_back(err);
     backing->errDevices.push_back(device);
     CUDA_OK(cudaDeviceSynchronize());
@@ -871,18 +873,18 @@ int Communicator::pickAllReduceAlgo(uint64_t bytes, bool nvlsOk) const
 
 uint32_t Communicator::checkError(cudaStream_t s)
 {
-    uint32_t v = 0;
     cudaSetDevice(device_);
-    cudaError_t e =
-      cudaMemcpyAsync(&v, dev_.err, sizeof(v), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) {
-        e = cudaStreamSynchronize(s);
-    }
-    if (e != cudaSuccess) {
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
         cudaGetLastError();
         return 0xffffffffu;
     }
-    return v;
+    return peekError();
+}
+
+uint32_t Communicator::peekError() const
+{
+    // The word lives in mapped host memory: a plain (volatile) load
+    return *reinterpret_cast<volatile uint32_t*>(dev_.err);
 }
 
 // ---------------------------------------------------------------------------

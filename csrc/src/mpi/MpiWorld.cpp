@@ -36,6 +36,10 @@ struct AsyncRequest
     faabric_datatype_t* dataType = nullptr;
     int count = 0;
     MpiMessageType messageType = MpiMessageType::NORMAL;
+    // Stream-ordered device collective: complete when `stream` drains
+    bool isDeviceCollective = false;
+    void* stream = nullptr;
+    std::shared_ptr<faabric::device::Communicator> comm;
 };
 
 struct RankState
@@ -57,6 +61,9 @@ struct RankState
     std::map<int, std::deque<int>> pendingIrecvs;
     // sendRank -> messages taken off the wire by a probe, not yet received
     std::map<int, std::deque<MpiMessage>> probed;
+    // Non-blocking device collectives rotate over the communicator's
+    // channels (every rank issues the same sequence => same channel)
+    uint64_t deviceCollectiveSeq = 0;
 
     void reset()
     {
@@ -70,6 +77,7 @@ struct RankState
         requests.clear();
         pendingIrecvs.clear();
         probed.clear();
+        deviceCollectiveSeq = 0;
         nextRequestId = 1;
     }
 };
@@ -777,6 +785,19 @@ void MpiWorld::awaitAsyncRequest(int requestId)
         // Already satisfied while draining for an earlier wait
         return;
     }
+    if (it->second.isDeviceCollective) {
+        AsyncRequest req = it->second;
+        tls.requests.erase(it);
+        cudaSetDevice(req.comm->device());
+        if (cudaStreamSynchronize((cudaStream_t)req.stream) != cudaSuccess) {
+            cudaGetLastError();
+            throw std::runtime_error("Device collective failed at synchronisation");
+        }
+        if (req.comm->peekError() != 0) {
+            throw std::runtime_error("Device collective watchdog fired (peer missing?)");
+        }
+        return;
+    }
     if (it->second.isSend) {
         tls.requests.erase(it);
         return;
@@ -833,13 +854,15 @@ void MpiWorld::probe(int sendRank, int recvRank, MPI_Status* status)
 // ---------------------------------------------------------------------------
 // Device path plumbing
 // ---------------------------------------------------------------------------
-void* MpiWorld::streamForRank(int rank)
+void* MpiWorld::streamForRank(int rank, int channel)
 {
     std::lock_guard<std::mutex> lk(deviceMx);
-    if ((int)deviceStreams.size() < size) {
-        deviceStreams.resize(size, nullptr);
+    const int perRank = FB_MAX_CHANNELS;
+    if ((int)deviceStreams.size() < size * perRank) {
+        deviceStreams.resize((size_t)size * perRank, nullptr);
     }
-    if (deviceStreams[rank] == nullptr) {
+    size_t idx = (size_t)rank * perRank + (size_t)(channel % perRank);
+    if (deviceStreams[idx] == nullptr) {
         // Same GPU as the rank's communicator when there is one
         int dev = (rank < (int)deviceComms.size() && deviceComms[rank] != nullptr) ? deviceComms[rank]->device()
                                                                                    : faabric::util::gpuForRank(rank);
@@ -847,13 +870,13 @@ void* MpiWorld::streamForRank(int rank)
             cudaSetDevice(dev);
             cudaStream_t s = nullptr;
             if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) {
-                deviceStreams[rank] = s;
+                deviceStreams[idx] = s;
             } else {
                 cudaGetLastError();
             }
         }
     }
-    return deviceStreams[rank];
+    return deviceStreams[idx];
 }
 
 void MpiWorld::ensureDeviceComms()
@@ -994,7 +1017,7 @@ static bool runDevice(std::shared_ptr<faabric::device::Communicator> comm,
     if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
         throw std::runtime_error("Device collective failed at synchronisation");
     }
-    uint32_t err = comm->checkError((cudaStream_t)stream);
+    uint32_t err = comm->peekError();
     if (err != 0) {
         throw std::runtime_error("Device collective watchdog fired (peer missing?)");
     }
@@ -1021,6 +1044,76 @@ bool MpiWorld::tryDeviceAllReduce(int rank, uint8_t* send, uint8_t* recv, faabri
         deviceCollectives.fetch_add(1);
     }
     return ran;
+}
+
+int MpiWorld::iAllReduce(int rank, uint8_t* send, uint8_t* recv, faabric_datatype_t* dt, int count, faabric_op_t* op)
+{
+    checkRanksRange(0, rank);
+    const size_t bytes = (size_t)count * dt->size;
+    int requestId = tls.nextRequestId++;
+    AsyncRequest r;
+    r.isSend = true; // nothing to drain on wait unless it becomes a device op
+    r.sendRank = rank;
+    r.recvRank = rank;
+    int fdt = fbDtypeFor(dt);
+    int fop = fbOpFor(op);
+    auto comm = (bytes > 0 && fdt >= 0 && fop >= 0 && isDevicePointer(send)) ? getDeviceComm(rank) : nullptr;
+    if (comm != nullptr) {
+        // Symmetric buffers may use any channel; others go through the single
+        // staging area on channel 0
+        const bool symmetric = comm->inHeap(send, bytes) && comm->inHeap(recv, bytes);
+        int nChannels = std::max(1, comm->config().channels);
+        int channel = symmetric ? (int)(tls.deviceCollectiveSeq++ % (uint64_t)nChannels) : 0;
+        cudaStream_t s = (cudaStream_t)streamForRank(rank, channel);
+        cudaSetDevice(comm->device());
+        int flags = (symmetric ? FB_FLAG_SYMMETRIC : 0) | FB_FLAG_CHANNEL(channel);
+        int rc = comm->allReduce(send, recv, (size_t)count, fdt, fop, FB_ALGO_AUTO, flags, s);
+        if (rc == FB_OK) {
+            deviceCollectives.fetch_add(1);
+            r.isDeviceCollective = true;
+            r.stream = s;
+            r.comm = comm;
+            tls.requests[requestId] = r;
+            return requestId;
+        }
+        if (rc != FB_E_UNSUPPORTED && rc != FB_E_TOO_LARGE) {
+            throw std::runtime_error(std::string("Device collective failed: ") + faabric::device::Communicator::errorString(rc));
+        }
+    }
+    // Host path (or unsupported on the device): complete it now
+    allReduce(rank, send, recv, dt, count, op);
+    tls.requests[requestId] = r;
+    return requestId;
+}
+
+void* MpiWorld::deviceAlloc(int rank, size_t bytes)
+{
+    auto comm = getDeviceComm(rank);
+    if (comm == nullptr) {
+        return nullptr;
+    }
+    try {
+        return comm->heapPtr(comm->alloc(bytes));
+    } catch (const std::bad_alloc&) {
+        return nullptr;
+    }
+}
+
+bool MpiWorld::deviceFree(int rank, void* ptr)
+{
+    std::shared_ptr<faabric::device::Communicator> comm;
+    {
+        std::lock_guard<std::mutex> lk(deviceMx);
+        if (rank < 0 || rank >= (int)deviceComms.size()) {
+            return false;
+        }
+        comm = deviceComms[rank];
+    }
+    if (comm == nullptr || !comm->inHeap(ptr)) {
+        return false;
+    }
+    comm->free(comm->offsetOf(ptr));
+    return true;
 }
 
 // Stages device buffers through pinned host memory for the host algorithms

@@ -557,6 +557,16 @@ int MPI_Op_free(MPI_Op* op)
 int MPI_Alloc_mem(MPI_Aint size, MPI_Info info, void* baseptr)
 {
     SPDLOG_TRACE("MPI - MPI_Alloc_mem");
+    if (info == MPI_INFO_FAABRIC_DEVICE) {
+        // "Special memory" in the MPI sense: the rank's symmetric heap in HBM,
+        // mapped into every peer, so collectives on it need no staging
+        void* p = getExecutingWorld().deviceAlloc(executingContext.getRank(), (size_t)size);
+        if (p == nullptr) {
+            return MPI_ERR_NO_MEM;
+        }
+        *((void**)baseptr) = p;
+        return MPI_SUCCESS;
+    }
     if (info != MPI_INFO_NULL) {
         throw std::runtime_error("Non-null info not supported");
     }
@@ -567,6 +577,29 @@ int MPI_Alloc_mem(MPI_Aint size, MPI_Info info, void* baseptr)
 int MPI_Free_mem(void* base)
 {
     SPDLOG_TRACE("MPI - MPI_Free_mem");
+    if (base == nullptr) {
+        return MPI_SUCCESS;
+    }
+    if (MpiWorld::isDevicePointer(base)) {
+        getExecutingWorld().deviceFree(executingContext.getRank(), base);
+    } else {
+        free(base);
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Iallreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm, MPI_Request* request)
+{
+    SPDLOG_TRACE("MPI - MPI_Iallreduce");
+    int id = getExecutingWorld().iAllReduce(executingContext.getRank(),
+                                            (uint8_t*)resolveInPlace(sendbuf, recvbuf),
+                                            (uint8_t*)recvbuf,
+                                            datatype,
+                                            count,
+                                            op);
+    auto* r = new faabric_request_t{ id };
+    requestTable()[id] = r;
+    *request = r;
     return MPI_SUCCESS;
 }
 

@@ -78,7 +78,7 @@ void SystemConfig::initialise()
     allreduceAlgo = getEnvVar("FAABRIC_ALLREDUCE_ALGO", "auto");
     useNvls = getSystemConfIntParam("FAABRIC_USE_NVLS", "1");
     commStreams = getSystemConfIntParam("FAABRIC_COMM_STREAMS", "2");
-    symmHeapBytes = getSystemConfLongParam("FAABRIC_SYMM_HEAP_BYTES", "268435456");
+    symmHeapBytes = getSystemConfLongParam("FAABRIC_SYMM_HEAP_BYTES", "1073741824");
     slotsPerGpu = getSystemConfIntParam("FAABRIC_SLOTS_PER_GPU", "8");
     portOffset = getSystemConfIntParam("FAABRIC_PORT_OFFSET", "0");
 }

@@ -188,6 +188,7 @@ TEST_CASE("gpu: MPI collectives on device buffers, one rank per GPU (or 4 sharin
 TEST_CASE("gpu: device snapshot diff+merge+push matches the host implementation", "[gpu][snapshot]")
 {
     NEED_GPU();
+    cudaSetDevice(0);
     using namespace faabric::util;
     getSystemConfig().diffingMode = "bytewise";
     const size_t size = 64 * HOST_PAGE_SIZE;
@@ -226,7 +227,10 @@ TEST_CASE("gpu: device snapshot diff+merge+push matches the host implementation"
     SnapshotData hostSnap(std::span<const uint8_t>(base.data(), size));
     addRegions(hostSnap);
     hostSnap.fillGapsWithBytewiseRegions();
-    auto diffs = hostSnap.diffWithDirtyRegions(std::span<uint8_t>(updated.data(), size), std::vector<char>(64, 1));
+    // NB the host diff rewrites typed values in the memory it is given with
+    // their deltas (reference semantics), so it works on a scratch copy
+    std::vector<uint8_t> hostScratch = updated;
+    auto diffs = hostSnap.diffWithDirtyRegions(std::span<uint8_t>(hostScratch.data(), size), std::vector<char>(64, 1));
     SnapshotData hostMain(std::span<const uint8_t>(mainStart.data(), size));
     hostMain.applyDiffs(diffs);
     auto expected = hostMain.getDataCopy();
@@ -277,6 +281,7 @@ TEST_CASE("gpu: device snapshot diff+merge+push matches the host implementation"
 TEST_CASE("gpu: state values have a coherent device copy", "[gpu][state]")
 {
     NEED_GPU();
+    cudaSetDevice(0);
     auto& state = faabric::state::getGlobalState();
     state.forceClearAll(true);
     size_t size = 3 * STATE_STREAMING_CHUNK_SIZE + 100;
@@ -305,4 +310,79 @@ TEST_CASE("gpu: state values have a coherent device copy", "[gpu][state]")
     REQUIRE_EQ(check[5], 7);
     REQUIRE_EQ(check[6], 4);
     state.forceClearAll(true);
+}
+
+namespace {
+int symmetricNonBlockingBody(int rank, int size)
+{
+    auto& world = faabric::mpi::getMpiWorldRegistry().getWorld(faabric::executor::ExecutorContext::get()->getMsg().mpiworldid());
+    auto comm = world.getDeviceComm(rank);
+    CHECK_RANK(comm != nullptr);
+    cudaSetDevice(comm->device());
+    // MPI_Alloc_mem(MPI_INFO_FAABRIC_DEVICE): symmetric heap, no staging
+    const int nTensors = 40;
+    const size_t per = 5000;
+    int *send = nullptr, *recv = nullptr;
+    CHECK_RANK(MPI_Alloc_mem(nTensors * per * sizeof(int), MPI_INFO_FAABRIC_DEVICE, &send) == MPI_SUCCESS);
+    CHECK_RANK(MPI_Alloc_mem(nTensors * per * sizeof(int), MPI_INFO_FAABRIC_DEVICE, &recv) == MPI_SUCCESS);
+    CHECK_RANK(comm->inHeap(send, nTensors * per * sizeof(int)));
+    std::vector<int> init(nTensors * per);
+    for (size_t i = 0; i < init.size(); i++) {
+        init[i] = (int)(i / per) + rank;
+    }
+    cudaMemcpy(send, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice);
+    // A burst of non-blocking all-reduces pipelines over the channels
+    std::vector<MPI_Request> reqs(nTensors);
+    for (int round = 0; round < 3; round++) {
+        for (int t = 0; t < nTensors; t++) {
+            MPI_Iallreduce(send + t * per, recv + t * per, (int)per, MPI_INT, MPI_SUM, MPI_COMM_WORLD, &reqs[t]);
+        }
+        MPI_Waitall(nTensors, reqs.data(), MPI_STATUSES_IGNORE);
+        std::vector<int> out(nTensors * per);
+        cudaMemcpy(out.data(), recv, out.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        for (int t = 0; t < nTensors; t++) {
+            int expected = t * size + size * (size - 1) / 2;
+            CHECK_RANK(out[t * per] == expected && out[(t + 1) * per - 1] == expected);
+        }
+    }
+    // Blocking calls on symmetric memory still work, as do host buffers
+    MPI_Allreduce(send, recv, (int)per, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
+    int hostVal = rank, hostMax = -1;
+    MPI_Request hostReq;
+    MPI_Iallreduce(&hostVal, &hostMax, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD, &hostReq);
+    MPI_Wait(&hostReq, MPI_STATUS_IGNORE);
+    CHECK_RANK(hostMax == size - 1);
+    MPI_Free_mem(send);
+    MPI_Free_mem(recv);
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+}
+
+TEST_CASE("gpu: MPI_Iallreduce bursts on MPI_Alloc_mem device memory", "[gpu][mpi]")
+{
+    NEED_GPU();
+    int worldSize = std::max(2, faabric::device::cudaDeviceCountSafe());
+    ClusterFixture f(worldSize);
+    registerTestFunction("mpi", "device-iallreduce", [&](auto*, int, int, auto) {
+        MPI_Init(nullptr, nullptr);
+        int rank = -1, size = -1;
+        MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+        MPI_Comm_size(MPI_COMM_WORLD, &size);
+        int rc = symmetricNonBlockingBody(rank, size);
+        MPI_Finalize();
+        return rc;
+    });
+    auto req = faabric::util::batchExecFactory("mpi", "device-iallreduce", 1);
+    req->mutable_messages(0)->set_ismpi(true);
+    req->mutable_messages(0)->set_mpiworldsize(worldSize);
+    f.plannerCli.callFunctions(req);
+    auto status = f.awaitBatch(req, 120000);
+    REQUIRE_EQ(status->messageresults_size(), worldSize);
+    for (auto& m : status->messageresults()) {
+        if (m.returnvalue() != 0) {
+            fbtest::fail(__FILE__, __LINE__, "rank " + std::to_string(m.mpirank()) + " failed: " + m.outputdata());
+        }
+    }
+    faabric::mpi::getMpiWorldRegistry().clear();
 }
