@@ -87,7 +87,13 @@ extern "C"
 int MPI_Init(int* argc, char*** argv)
 {
     faabric::Message* call = getExecutingCall();
-    if (call->mpirank() <= 0) {
+    // A function resuming after a migration / thaw re-enters an existing
+    // world: even rank 0 joins, and nobody waits for it at a start-up barrier
+    auto ctx = faabric::executor::ExecutorContext::get();
+    const bool resuming = ctx->getBatchRequest() != nullptr &&
+                          ctx->getBatchRequest()->type() == faabric::BatchExecuteRequest::MIGRATION &&
+                          call->mpiworldid() > 0;
+    if (call->mpirank() <= 0 && !resuming) {
         // A world of the configured size is created by rank 0
         SPDLOG_TRACE("MPI - MPI_Init (create)");
         if (call->mpiworldsize() <= 0) {
@@ -101,9 +107,10 @@ int MPI_Init(int* argc, char*** argv)
     }
     mpiInitialised = true;
     mpiFinalised = false;
-    int thisRank = executingContext.getRank();
-    // Everyone lines up once the world is wired
-    getExecutingWorld().barrier(thisRank);
+    if (!resuming) {
+        // Everyone lines up once the world is wired
+        getExecutingWorld().barrier(executingContext.getRank());
+    }
     return MPI_SUCCESS;
 }
 

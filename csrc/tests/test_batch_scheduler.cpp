@@ -237,6 +237,8 @@ TEST_CASE("spot: dist-change (eviction) decisions", "[batch-scheduler]")
     runScenarios(
       "spot",
       {
+        { "new apps avoid the tainted VM", NEW_REQ, { "gpu0", "gpu1", "idle" }, { 2, 2, 0 }, { 0, 0, 0 }, 1, {}, { "gpu0" }, "gpu1" },
+        { "new apps avoid the tainted VM (no room)", NEW_REQ, { "gpu0", "gpu1" }, { 2, 2 }, { 1, 0 }, 2, {}, NES, "gpu1" },
         { "no tainted VMs", DIST, { "foo" }, { 4 }, { 2 }, 2, { "foo", "foo" }, DNM },
         { "no tainted VMs (multi)", DIST, { "foo", "bar" }, { 4, 2 }, { 4, 1 }, 5, { "foo", "foo", "foo", "foo", "bar" }, DNM },
         { "ignores chances to free hosts", DIST, { "foo", "bar", "baz" }, { 4, 4, 4 }, { 2, 2, 4 }, 4, { "baz", "baz", "baz", "baz" }, DNM },

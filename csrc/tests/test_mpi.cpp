@@ -332,3 +332,173 @@ TEST_CASE("mpi: ping-pong and all-reduce bursts", "[mpi][bench]")
     runMpi("pingpong", 2, 1, bodyPingPongAndAllreduce);
     runMpi("allreduce8", 8, 1, bodyPingPongAndAllreduce);
 }
+
+// ---------------------------------------------------------------------------
+// Migration (strategy: reference tests/dist/mpi/test_mpi_functions.cpp
+// "Test triggering an MPI migration", tests/test/planner migration tests)
+// ---------------------------------------------------------------------------
+#include <faabric/mpi/migration.h>
+
+namespace {
+std::atomic<int> migratedExecutions{ 0 };
+// Lets a test change the cluster while the ranks wait just before their
+// migration point
+std::atomic<bool> holdBeforeMigrationPoint{ false };
+std::atomic<int> ranksWaitingAtGate{ 0 };
+
+// Ranks iterate; halfway through they hit a migration point.  Ranks that move
+// re-enter the function with the loop index as input and carry on.
+int migrationBody(faabric::Message& msg, faabric::executor::Executor* exec)
+{
+    const int nLoops = 6, checkAt = 3;
+    int start = msg.inputdata().empty() ? 0 : std::stoi(msg.inputdata());
+    if (start > 0) {
+        migratedExecutions++;
+    }
+    MPI_Init(nullptr, nullptr);
+    int rank = -1, size = -1;
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+    MPI_Comm_size(MPI_COMM_WORLD, &size);
+    // Something in memory that must survive the move
+    auto mem = exec->getMemoryView();
+    if (start == 0) {
+        *(int*)(mem.data() + 128) = 1000 + rank;
+    } else if (*(int*)(mem.data() + 128) != 1000 + rank) {
+        printf("         rank %d: memory not restored after migration (%d)\n", rank, *(int*)(mem.data() + 128));
+        return 1;
+    }
+    for (int i = start; i < nLoops; i++) {
+        if (i == checkAt && start == 0) {
+            ranksWaitingAtGate++;
+            while (holdBeforeMigrationPoint.load()) {
+                std::this_thread::sleep_for(std::chrono::milliseconds(1));
+            }
+            MPI_Barrier(MPI_COMM_WORLD);
+            faabric::mpi::mpiMigrationPoint(i);
+        }
+        int v = rank + i, sum = 0;
+        MPI_Allreduce(&v, &sum, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        if (sum != size * (size - 1) / 2 + i * size) {
+            printf("         rank %d: bad all-reduce at loop %d: %d\n", rank, i, sum);
+            return 1;
+        }
+    }
+    MPI_Barrier(MPI_COMM_WORLD);
+    MPI_Finalize();
+    return 0;
+}
+}
+
+TEST_CASE("mpi: an app is migrated onto fewer hosts at a migration point", "[mpi][migration]")
+{
+    // Two (virtual) hosts with 4 slots each; the world starts 2 + 2 and the
+    // bin-pack policy consolidates it onto one host at the migration point
+    ClusterFixture f(0, 2, 4);
+    migratedExecutions = 0;
+    registerTestFunction("mpi", "migrate", [&](auto* exec, int, int idx, auto req) {
+        return migrationBody(*req->mutable_messages(idx), exec);
+    });
+    auto req = faabric::util::batchExecFactory("mpi", "migrate", 1);
+    auto& msg = *req->mutable_messages(0);
+    msg.set_ismpi(true);
+    msg.set_mpiworldsize(4);
+    msg.set_recordexecgraph(true);
+
+    // Pin the initial layout: ranks 0,1 on gpu0 and 2,3 on gpu1
+    auto preload = std::make_shared<faabric::batch_scheduler::SchedulingDecision>(req->appid(), 0);
+    std::vector<std::string> initial = { "gpu0", "gpu0", "gpu1", "gpu1" };
+    for (int r = 0; r < 4; r++) {
+        preload->addMessage(initial[r], 0, r, r);
+    }
+    f.plannerCli.preloadSchedulingDecision(preload);
+
+    f.plannerCli.callFunctions(req);
+    auto status = f.awaitBatch(req, 60000);
+    REQUIRE_EQ(f.planner.getNumMigrations(), 1);
+    // 4 ranks + the re-executions of those that moved
+    std::map<int, std::string> finalHost;
+    for (auto& m : status->messageresults()) {
+        if (m.returnvalue() != 0) {
+            fbtest::fail(__FILE__, __LINE__, "rank " + std::to_string(m.mpirank()) + " failed: " + m.outputdata());
+        }
+        finalHost[m.mpirank()] = m.executedhost();
+    }
+    REQUIRE_EQ(finalHost.size(), 4u);
+    std::set<std::string> hosts;
+    for (auto& [r, h] : finalHost) {
+        hosts.insert(h);
+    }
+    REQUIRE_EQ(hosts.size(), 1u);
+    REQUIRE_EQ(migratedExecutions.load(), 2);
+    // Slots are all free again
+    for (auto& h : f.plannerCli.getAvailableHosts()) {
+        REQUIRE_EQ(h.usedslots(), 0);
+    }
+    faabric::mpi::getMpiWorldRegistry().clear();
+}
+
+TEST_CASE("mpi: spot eviction freezes an app, it thaws when capacity returns", "[mpi][migration]")
+{
+    ClusterFixture f(0, 2, 2);
+    f.planner.setPolicy("spot");
+    migratedExecutions = 0;
+    registerTestFunction("mpi", "freeze", [&](auto* exec, int, int idx, auto req) {
+        return migrationBody(*req->mutable_messages(idx), exec);
+    });
+    auto req = faabric::util::batchExecFactory("mpi", "freeze", 1);
+    auto& msg = *req->mutable_messages(0);
+    msg.set_ismpi(true);
+    msg.set_mpiworldsize(4);
+    holdBeforeMigrationPoint = true;
+    ranksWaitingAtGate = 0;
+    f.plannerCli.callFunctions(req);
+    for (int i = 0; i < 5000 && ranksWaitingAtGate.load() < 4; i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    }
+    REQUIRE_EQ(ranksWaitingAtGate.load(), 4);
+    // gpu1 is going away and nothing else has room: the app must freeze
+    f.planner.setNextEvictedVm({ "gpu1" });
+    holdBeforeMigrationPoint = false;
+
+    // Wait until all four ranks have reported FROZEN
+    bool frozen = false;
+    for (int i = 0; i < 2000 && !frozen; i++) {
+        auto evicted = f.planner.getEvictedReqs();
+        auto it = evicted.find(req->appid());
+        if (it != evicted.end() && it->second->messages_size() == 4) {
+            frozen = true;
+            for (auto& m : it->second->messages()) {
+                frozen = frozen && m.returnvalue() == FROZEN_FUNCTION_RETURN_VALUE;
+            }
+        }
+        if (!frozen) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(5));
+        }
+    }
+    REQUIRE(frozen);
+    REQUIRE_EQ(f.planner.getInFlightReqs().size(), 0u);
+    for (auto& h : f.plannerCli.getAvailableHosts()) {
+        REQUIRE_EQ(h.usedslots(), 0);
+    }
+    // Polling while there is no capacity keeps it frozen
+    auto status = f.plannerCli.getBatchResults(req);
+    REQUIRE(status != nullptr);
+    REQUIRE(!status->finished());
+    REQUIRE_EQ(f.planner.getEvictedReqs().size(), 1u);
+
+    // The eviction passes: the next poll thaws the app and it runs to the end
+    f.planner.setNextEvictedVm({});
+    status = f.awaitBatch(req, 60000);
+    REQUIRE_EQ(f.planner.getEvictedReqs().size(), 0u);
+    std::set<int> ranks;
+    for (auto& m : status->messageresults()) {
+        if (m.returnvalue() != 0) {
+            fbtest::fail(__FILE__, __LINE__, "rank " + std::to_string(m.mpirank()) + " failed: " + m.outputdata());
+        }
+        ranks.insert(m.mpirank());
+    }
+    REQUIRE_EQ(ranks.size(), 4u);
+    REQUIRE_EQ(migratedExecutions.load(), 4);
+    f.planner.setPolicy("bin-pack");
+    faabric::mpi::getMpiWorldRegistry().clear();
+}
