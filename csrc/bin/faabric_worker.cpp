@@ -9,6 +9,8 @@
 #include <faabric/executor/ExecutorFactory.h>
 #include <faabric/mpi/MpiWorld.h>
 #include <faabric/mpi/MpiWorldRegistry.h>
+#include <faabric/executor/ExecutorContext.h>
+#include <faabric/mpi/migration.h>
 #include <faabric/mpi/mpi.h>
 #include <faabric/planner/PlannerClient.h>
 #include <faabric/runner/FaabricMain.h>
@@ -16,6 +18,7 @@
 #include <faabric/util/batch.h>
 #include <faabric/util/config.h>
 #include <faabric/util/logging.h>
+#include <faabric/util/memory.h>
 
 #include <cuda_runtime.h>
 
@@ -267,6 +270,35 @@ static void registerFunctions()
         return 0;
     });
 
+    // Iterates with an all-reduce per loop; halfway through every rank hits a
+    // migration point.  Ranks that are moved resume from the loop index they
+    // carried over, with their memory restored from the snapshot.
+    mpiFunction("migrate", [](int rank, int size, faabric::Message& msg) {
+        const int nLoops = 6, checkAt = 3;
+        int start = msg.inputdata().empty() ? 0 : std::stoi(msg.inputdata());
+        auto mem = ExecutorContext::get()->getExecutor()->getMemoryView();
+        int* cell = (int*)(mem.data() + 256);
+        if (start == 0) {
+            *cell = 4000 + rank;
+        } else {
+            EXPECT(*cell == 4000 + rank);
+        }
+        for (int i = start; i < nLoops; i++) {
+            if (i == checkAt && start == 0) {
+                // Give the test time to change the cluster under us
+                std::this_thread::sleep_for(std::chrono::milliseconds(300));
+                MPI_Barrier(MPI_COMM_WORLD);
+                faabric::mpi::mpiMigrationPoint(i);
+            }
+            int v = rank + i, sum = 0;
+            MPI_Allreduce(&v, &sum, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+            EXPECT(sum == size * (size - 1) / 2 + i * size);
+        }
+        MPI_Barrier(MPI_COMM_WORLD);
+        msg.set_outputdata(start == 0 ? "stayed" : "resumed at " + std::to_string(start));
+        return 0;
+    });
+
     // ---- CPU baselines ----
     // Ping-pong between ranks 0 and 1; reports the mean round-trip in us
     mpiFunction("bench-pingpong", [](int rank, int size, faabric::Message& msg) {
@@ -423,7 +455,10 @@ class WorkerExecutor : public Executor
   public:
     explicit WorkerExecutor(faabric::Message& msg)
       : Executor(msg)
-    {}
+    {
+        // A small linear memory so functions can be snapshotted / migrated
+        memory = faabric::util::allocatePrivateMemory(MEMORY_BYTES);
+    }
 
     int32_t executeTask(int threadPoolIdx, int msgIdx, std::shared_ptr<faabric::BatchExecuteRequest> req) override
     {
@@ -435,6 +470,20 @@ class WorkerExecutor : public Executor
         }
         return it->second(msg);
     }
+
+    std::span<uint8_t> getMemoryView() override { return { memory.get(), MEMORY_BYTES }; }
+
+    size_t getMaxMemorySize() override { return MEMORY_BYTES; }
+
+    void restore(const std::string& snapshotKey) override
+    {
+        auto snap = reg.getSnapshot(snapshotKey);
+        snap->mapToMemory({ memory.get(), std::min(MEMORY_BYTES, snap->getSize()) });
+    }
+
+  private:
+    static constexpr size_t MEMORY_BYTES = 64 * 4096;
+    faabric::util::MemoryRegion memory;
 };
 
 class WorkerExecutorFactory : public ExecutorFactory

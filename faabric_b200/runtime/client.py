@@ -130,6 +130,16 @@ class PlannerHttpClient:
             msgs.append(m)
         return {"appId": app_id, "user": user, "function": function, "messages": msgs}
 
+    def preload_decision(self, batch: dict, hosts: list[str]) -> str:
+        """Pin the placement of an app before it is scheduled: hosts[i] is the
+        host of group idx i (MPI rank i)."""
+        msgs = [
+            {"id": 0, "appId": batch["appId"], "appIdx": i, "groupIdx": i, "executedHost": h}
+            for i, h in enumerate(hosts)
+        ]
+        payload = {"appId": batch["appId"], "messages": msgs}
+        return self._ok(HttpMessageType.PRELOAD_SCHEDULING_DECISION, json.dumps(payload))
+
     def execute_batch(self, batch: dict) -> dict:
         return json.loads(self._ok(HttpMessageType.EXECUTE_BATCH, json.dumps(batch)))
 

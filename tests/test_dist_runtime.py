@@ -109,6 +109,25 @@ def test_mpi_benchmarks_report(cluster):
     assert out["count"] == 65536 and out["algbw_GBps"] > 0
 
 
+def test_mpi_migration_between_worker_processes(tmp_path):
+    """Ranks start 2 + 2 on two workers; at the migration point bin-pack
+    consolidates them on one worker: two ranks snapshot their memory, push it
+    to the other PROCESS and resume there."""
+    with LocalCluster(n_workers=2, slots_per_worker=4, log_dir=tmp_path) as c:
+        a, b = c.worker_hosts()
+        batch = c.client.make_batch("mpi", "migrate", mpi_world_size=4)
+        c.client.preload_decision(batch, [a, a, b, b])
+        c.client.execute_batch(batch)
+        st = c.client.wait_for_batch(batch["appId"], timeout=60)
+        res = _results(st)
+        assert len(res) == 4, res
+        assert all(m.get("returnValue", 0) == 0 for m in res), res
+        assert len({m["executedHost"] for m in res}) == 1, res
+        assert sorted(m["output_data"] for m in res) == ["resumed at 3", "resumed at 3", "stayed", "stayed"]
+        assert c.client.in_flight_apps().get("numMigrations", 0) == 1
+        assert all(h.get("usedSlots", 0) == 0 for h in c.client.available_hosts())
+
+
 def test_exec_graph_and_policy(cluster):
     batch = cluster.client.make_batch("demo", "echo", input_data="g", record_exec_graph=True)
     cluster.client.execute_batch(batch)
