@@ -19,6 +19,7 @@
 #include <faabric/util/config.h>
 #include <faabric/util/logging.h>
 #include <faabric/util/memory.h>
+#include <faabric/util/snapshot.h>
 
 #include <cuda_runtime.h>
 
@@ -81,6 +82,54 @@ static void registerFunctions()
         return 1;
     };
     functions()["demo/noop"] = [](faabric::Message&) { return 0; };
+
+    // Fork-join over THREADS: the main function spawns N threads that may land
+    // on other workers; they start from its snapshot, write their own slot and
+    // add into a Sum-merged word; the diffs are merged back into main memory.
+    functions()["demo/threads"] = [](faabric::Message& msg) {
+        auto ctx = ExecutorContext::get();
+        auto* exec = ctx->getExecutor();
+        auto mem = exec->getMemoryView();
+        int* sumCell = (int*)(mem.data() + 64);
+        if (ctx->getBatchRequest()->type() == faabric::BatchExecuteRequest::THREADS) {
+            int t = msg.appidx();
+            mem[8192 + t] = (uint8_t)(10 + t);
+            __atomic_fetch_add(sumCell, t + 1, __ATOMIC_RELAXED);
+            msg.set_outputdata("thread " + std::to_string(t) + " on " + faabric::scheduler::getScheduler().getThisHost());
+            return t;
+        }
+        int nThreads = msg.inputdata().empty() ? 4 : std::stoi(msg.inputdata());
+        *sumCell = 100;
+        auto threads = faabric::util::batchExecFactory(msg.user(), msg.function(), nThreads);
+        faabric::util::updateBatchExecAppId(threads, msg.appid());
+        for (int i = 0; i < nThreads; i++) {
+            threads->mutable_messages(i)->set_appidx(i + 1);
+            threads->mutable_messages(i)->set_groupidx(i + 1);
+        }
+        std::vector<faabric::util::SnapshotMergeRegion> regions = {
+            { 64, sizeof(int), faabric::util::SnapshotDataType::Int, faabric::util::SnapshotMergeOperation::Sum }
+        };
+        auto results = exec->executeThreads(threads, regions);
+        int expectedSum = 100;
+        std::string hosts;
+        for (int i = 0; i < nThreads; i++) {
+            expectedSum += i + 2;
+            if (results.at(i).second != i + 1) {
+                msg.set_outputdata("thread " + std::to_string(i + 1) + " returned " + std::to_string(results.at(i).second));
+                return 1;
+            }
+            if (mem[8192 + i + 1] != 10 + i + 1) {
+                msg.set_outputdata("slot of thread " + std::to_string(i + 1) + " not merged");
+                return 1;
+            }
+        }
+        if (*sumCell != expectedSum) {
+            msg.set_outputdata("sum is " + std::to_string(*sumCell) + ", expected " + std::to_string(expectedSum));
+            return 1;
+        }
+        msg.set_outputdata("merged sum " + std::to_string(*sumCell));
+        return 0;
+    };
 
     mpiFunction("helloworld", [](int rank, int size, faabric::Message& msg) {
         char name[MPI_MAX_PROCESSOR_NAME];

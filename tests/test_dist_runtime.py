@@ -128,6 +128,20 @@ def test_mpi_migration_between_worker_processes(tmp_path):
         assert all(h.get("usedSlots", 0) == 0 for h in c.client.available_hosts())
 
 
+def test_threads_fork_join_across_workers(tmp_path):
+    """THREADS batch spanning two worker processes: remote threads restore the
+    main thread's snapshot, their dirty pages come back as diffs and are merged
+    (bytewise slots + an int Sum region)."""
+    with LocalCluster(n_workers=2, slots_per_worker=3, log_dir=tmp_path) as c:
+        st = c.client.invoke("demo", "threads", input_data="4", timeout=60)
+        res = st["messageResults"]
+        main = [m for m in res if m.get("output_data", "").startswith("merged")]
+        assert len(main) == 1, res
+        assert main[0]["output_data"] == "merged sum 114" and main[0].get("returnValue", 0) == 0
+        thread_hosts = {m["output_data"].split()[-1] for m in res if m.get("output_data", "").startswith("thread")}
+        assert thread_hosts == set(c.worker_hosts()), res
+
+
 def test_exec_graph_and_policy(cluster):
     batch = cluster.client.make_batch("demo", "echo", input_data="g", record_exec_graph=True)
     cluster.client.execute_batch(batch)
