@@ -1,4 +1,5 @@
 #include "faabric/device/communicator.h"
+#include "faabric/device/nvtx.h"
 
 #include "faabric/device/bootstrap.h"
 #include "faabric/device/cuda_driver.h"
@@ -1174,6 +1175,7 @@ int Communicator::allReduce(const void* send,
                             int flags,
                             cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::allReduce");
     return reduceLike(
       K_ALLREDUCE, send, recv, count, dtype, op, 0, algo, flags, s);
 }
@@ -1187,6 +1189,7 @@ int Communicator::reduce(const void* send,
                          int flags,
                          cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::reduce");
     if (root < 0 || root >= dev_.nranks) {
         return FB_E_INVALID;
     }
@@ -1202,6 +1205,7 @@ int Communicator::reduceScatter(const void* send,
                                 int flags,
                                 cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::reduceScatter");
     return reduceLike(K_REDUCE_SCATTER,
                       send,
                       recv,
@@ -1222,6 +1226,7 @@ int Communicator::scan(const void* send,
                        int flags,
                        cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::scan");
     return reduceLike(
       K_SCAN, send, recv, count, dtype, op, 0, FB_ALGO_AUTO, flags, s);
 }
@@ -1398,6 +1403,7 @@ int Communicator::broadcast(void* buf,
                             int flags,
                             cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::broadcast");
     if (root < 0 || root >= dev_.nranks) {
         return FB_E_INVALID;
     }
@@ -1413,6 +1419,7 @@ int Communicator::allGather(const void* send,
                             int flags,
                             cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::allGather");
     if ((flags & FB_FLAG_SYMMETRIC) &&
         (!inHeap(send, bytesPerRank) ||
          !inHeap(recv, bytesPerRank * dev_.nranks))) {
@@ -1431,6 +1438,7 @@ int Communicator::gather(const void* send,
                          int flags,
                          cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::gather");
     if (root < 0 || root >= dev_.nranks) {
         return FB_E_INVALID;
     }
@@ -1444,6 +1452,7 @@ int Communicator::scatter(const void* send,
                           int flags,
                           cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::scatter");
     if (root < 0 || root >= dev_.nranks) {
         return FB_E_INVALID;
     }
@@ -1456,11 +1465,13 @@ int Communicator::allToAll(const void* send,
                            int flags,
                            cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::allToAll");
     return moveLike(fb::MOVE_ALLTOALL, send, recv, bytesPerRank, 0, flags, s);
 }
 
 int Communicator::barrier(cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::barrier");
     cudaSetDevice(device_);
     if (dev_.nranks == 1) {
         return FB_OK;
@@ -1474,6 +1485,7 @@ int Communicator::barrier(cudaStream_t s)
 // ---------------------------------------------------------------------------
 int Communicator::send(const void* buf, size_t bytes, int peer, cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::send");
     if (peer < 0 || peer >= dev_.nranks || peer == dev_.rank) {
         return FB_E_INVALID;
     }
@@ -1494,6 +1506,7 @@ int Communicator::send(const void* buf, size_t bytes, int peer, cudaStream_t s)
 
 int Communicator::recv(void* buf, size_t bytes, int peer, cudaStream_t s)
 {
+    NvtxRange nvtxRange("fb::recv");
     if (peer < 0 || peer >= dev_.nranks || peer == dev_.rank) {
         return FB_E_INVALID;
     }

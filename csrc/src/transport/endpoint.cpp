@@ -4,6 +4,7 @@
 #include <faabric/transport/MessageEndpointServer.h>
 #include <faabric/transport/common.h>
 #include <faabric/util/config.h>
+#include <faabric/util/fault.h>
 #include <faabric/util/logging.h>
 #include <faabric/util/network.h>
 #include <faabric/util/string_tools.h>
@@ -16,6 +17,7 @@
 #include <netinet/in.h>
 #include <poll.h>
 #include <shared_mutex>
+#include <thread>
 #include <sys/epoll.h>
 #include <sys/eventfd.h>
 #include <sys/socket.h>
@@ -262,6 +264,30 @@ void SendMessageEndpoint::dropConnection()
     sock.reset();
 }
 
+// Returns true when the message must be dropped
+static bool injectFault(int port, uint8_t header, const std::string& address)
+{
+    auto& faults = faabric::util::FaultInjector::get();
+    if (!faults.armed()) {
+        return false;
+    }
+    auto rule = faults.match(port, header);
+    if (!rule.has_value()) {
+        return false;
+    }
+    switch (rule->action) {
+        case faabric::util::FaultAction::DROP:
+            SPDLOG_WARN("Fault injection: dropping message {} to {}", (int)header, address);
+            return true;
+        case faabric::util::FaultAction::DELAY:
+            std::this_thread::sleep_for(std::chrono::milliseconds(rule->delayMs));
+            return false;
+        case faabric::util::FaultAction::ERROR:
+            throw std::runtime_error("Fault injection: send of message " + std::to_string((int)header) + " to " + address + " failed");
+    }
+    return false;
+}
+
 AsyncSendMessageEndpoint::AsyncSendMessageEndpoint(const std::string& hostIn,
                                                    int portIn,
                                                    int timeoutMs)
@@ -273,6 +299,9 @@ void AsyncSendMessageEndpoint::send(uint8_t header,
                                     size_t dataSize,
                                     int sequenceNum)
 {
+    if (injectFault(port, header, getAddress())) {
+        return;
+    }
     if (MessageEndpointServer* local = findLocalServer(false)) {
         local->getAsyncHandler()->deliverLocal(
           Message(header, sequenceNum, data, dataSize));
@@ -304,6 +333,11 @@ Message SyncSendMessageEndpoint::sendAwaitResponse(uint8_t header,
                                                    const uint8_t* data,
                                                    size_t dataSize)
 {
+    if (injectFault(port, header, getAddress())) {
+        // The request is lost: what the caller sees is a timeout
+        std::this_thread::sleep_for(std::chrono::milliseconds(std::min(timeoutMs, 200)));
+        throw MessageTimeoutException("Timed out waiting for response from " + getAddress() + " (injected drop)");
+    }
     if (MessageEndpointServer* local = findLocalServer(true)) {
         // Direct call on the caller's thread: no serialisation hop
         Message req(header, NO_SEQUENCE_NUM, data, dataSize);

@@ -363,3 +363,50 @@ TEST_CASE("ptp: group locks, barrier and notify", "[transport][ptp]")
     REQUIRE(!group->localTryLock());
     group->localUnlock();
 }
+
+#include <faabric/util/fault.h>
+
+TEST_CASE("fault injection: drop, delay and fail RPCs", "[transport][fault]")
+{
+    auto& faults = faabric::util::FaultInjector::get();
+    faults.clear();
+    EchoServer server;
+    server.start();
+    MessageEndpointClient cli(LOCALHOST, TEST_ASYNC_PORT, TEST_SYNC_PORT, 2000);
+    std::string body = "payload";
+
+    // Drop the next two async messages with code 5, let others through
+    faults.addRulesFromString("drop:port=" + std::to_string(TEST_ASYNC_PORT) + ",header=5,count=2");
+    REQUIRE(faults.armed());
+    for (int i = 0; i < 3; i++) {
+        cli.asyncSend(5, (const uint8_t*)body.data(), body.size());
+    }
+    cli.asyncSend(6, (const uint8_t*)body.data(), body.size());
+    for (int i = 0; i < 200 && server.asyncCount.load() < 2; i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    REQUIRE_EQ(server.asyncCount.load(), 2);
+    REQUIRE(!faults.armed());
+    REQUIRE_EQ(faults.firedCount() >= 2, true);
+
+    // Delay a sync call
+    faults.addRule({ faabric::util::FaultAction::DELAY, TEST_SYNC_PORT, -1, 80, 1 });
+    faabric::StatePart resp;
+    auto t0 = std::chrono::steady_clock::now();
+    cli.syncSend(9, (const uint8_t*)body.data(), body.size(), &resp);
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    REQUIRE(ms >= 75);
+    REQUIRE_EQ(resp.key(), body);
+
+    // A dropped sync request looks like a timeout, an "error" rule throws
+    faults.addRule({ faabric::util::FaultAction::DROP, TEST_SYNC_PORT, 9, 0, 1 });
+    REQUIRE_THROWS(cli.syncSend(9, (const uint8_t*)body.data(), body.size(), &resp));
+    faults.addRule({ faabric::util::FaultAction::ERROR, -1, 11, 0, 1 });
+    REQUIRE_THROWS(cli.asyncSend(11, (const uint8_t*)body.data(), body.size()));
+    // Back to normal
+    cli.syncSend(9, (const uint8_t*)body.data(), body.size(), &resp);
+    REQUIRE_EQ(resp.key(), body);
+    faults.clear();
+    server.stop();
+}

@@ -33,6 +33,7 @@ class GradientSync:
         use_graph: bool = True,
         in_place: bool = False,
         channels: int = 4,
+        bucket_bytes: int = 0,
     ):
         self.comm = comm
         self.sizes = [int(s) for s in sizes]
@@ -67,12 +68,30 @@ class GradientSync:
         self._joins = [torch.cuda.Event() for _ in self._lanes]
         self._result = torch.zeros(2, dtype=torch.int64, device=f"cuda:{comm.device}")
         self._result_host = torch.zeros(2, dtype=torch.int64).pin_memory()
-        self.launches_per_step = len(self.sizes)
+        # Optional DDP-style bucketing: neighbouring tensors of the flat buffer
+        # are all-reduced together (one kernel per bucket, padding included).
+        # bucket_bytes == 0 keeps the reference semantics: one call per tensor.
+        self.bucket_bytes = int(bucket_bytes)
+        if self.bucket_bytes > 0:
+            spans = []
+            start = 0
+            end = 0
+            for o, sz in zip(self.offsets, self.sizes):
+                pad_end = o + (sz * esize + 255) // 256 * 256 // esize
+                if end > start and (pad_end - start) * esize > self.bucket_bytes:
+                    spans.append((start, end))
+                    start = o
+                end = pad_end
+            spans.append((start, end))
+            self._jobs = [(self.send[a:b], self.recv[a:b], b - a) for a, b in spans]
+        else:
+            self._jobs = [(s, r, n) for s, r, n in zip(self.send_views, self.recv_views, self.sizes)]
+        self.launches_per_step = len(self._jobs)
 
     # ------------------------------------------------------------------ core
     def _issue(self, stream):
         if self.channels == 1:
-            for s, r in zip(self.send_views, self.recv_views):
+            for s, r, _ in self._jobs:
                 self.comm.all_reduce(s, r, op=self.op, algo=self.algo, stream=stream)
             return
         # fork: lane streams wait for everything already queued on `stream`
@@ -80,13 +99,11 @@ class GradientSync:
         for lane in self._lanes:
             lane.wait_event(self._fork)
         # biggest tensors first, round-robin over the lanes
-        order = sorted(range(len(self.sizes)), key=lambda i: -self.sizes[i])
+        order = sorted(range(len(self._jobs)), key=lambda i: -self._jobs[i][2])
         for k, i in enumerate(order):
             ch = k % self.channels
             st = stream if ch == 0 else self._lanes[ch - 1]
-            self.comm.all_reduce(
-                self.send_views[i], self.recv_views[i], op=self.op, algo=self.algo, stream=st, channel=ch
-            )
+            self.comm.all_reduce(self._jobs[i][0], self._jobs[i][1], op=self.op, algo=self.algo, stream=st, channel=ch)
         # join
         for lane, ev in zip(self._lanes, self._joins):
             ev.record(lane)
