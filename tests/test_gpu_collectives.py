@@ -472,3 +472,69 @@ def test_watchdog_reports_missing_peer():
         assert g.comms[0].check_error(g.streams[0]) != 0
     finally:
         g.close()
+
+
+def test_stress_random_skew_and_sizes():
+    """Flag-ordering stress: back-to-back collectives of random kinds, sizes
+    and algorithms while every rank starts each one at a random time offset
+    (device-side sleep), without host synchronisation inside a batch."""
+    import random
+
+    n = 4
+    g = group(n)
+    rng = random.Random(1234)
+    dev = [c.device for c in g.comms]
+    max_elems = 1 << 18
+    sends = [c.empty(max_elems, torch.int32) for c in g.comms]
+    recvs = [[c.empty(max_elems, torch.int32) for _ in range(6)] for c in g.comms]
+    gathers = [c.empty(max_elems, torch.int32) for c in g.comms]
+    try:
+        for it in range(30):
+            base = [torch.randint(-1000, 1000, (max_elems,), dtype=torch.int32) for _ in range(n)]
+            for r in range(n):
+                sends[r].copy_(base[r].to(f"cuda:{dev[r]}"))
+            g.synchronize()
+            torch.cuda.synchronize()
+            plan = []
+            for k in range(6):
+                kind = rng.choice(["allreduce", "allreduce", "allreduce", "allgather", "bcast"])
+                numel = rng.choice([1, 7, 256, 1000, 4096, 33333, 1 << 16, 1 << 18])
+                algo = rng.choice(["auto", "ll", "oneshot", "twoshot"])
+                if algo == "ll" and numel * 4 > 32 * 1024:
+                    algo = "auto"
+                plan.append((kind, numel, algo, rng.randrange(n)))
+            for k, (kind, numel, algo, root) in enumerate(plan):
+                skew = [rng.randrange(0, 400_000) for _ in range(n)]
+
+                def issue(c, r, st, kind=kind, numel=numel, algo=algo, root=root, k=k, skew=skew):
+                    torch.cuda._sleep(skew[r])
+                    if kind == "allreduce":
+                        c.all_reduce(sends[r][:numel], recvs[r][k][:numel], op="sum", algo=algo)
+                    elif kind == "allgather":
+                        per = max(1, numel // n)
+                        c.all_gather(sends[r][:per], gathers[r][: per * n])
+                        recvs[r][k][: per * n].copy_(gathers[r][: per * n])
+                    else:
+                        recvs[r][k][:numel].copy_(sends[r][:numel])
+                        c.broadcast(recvs[r][k][:numel], root=root)
+
+                g.run(issue)
+            g.synchronize()
+            assert g.check_errors() == [0] * n
+            for k, (kind, numel, algo, root) in enumerate(plan):
+                if kind == "allreduce":
+                    exp = sum(b[:numel].to(torch.int64) for b in base).to(torch.int32)
+                elif kind == "allgather":
+                    per = max(1, numel // n)
+                    exp = torch.cat([b[:per] for b in base])
+                else:
+                    exp = base[root][:numel]
+                for r in range(n):
+                    got = recvs[r][k][: exp.numel()].cpu()
+                    assert torch.equal(got, exp), f"iteration {it} op {k} {kind} numel {numel} algo {algo} rank {r}"
+    finally:
+        for r, c in enumerate(g.comms):
+            c.free(sends[r])
+            c.free(gathers[r])
+            for t in recvs[r]:
+                c.free(t)
