@@ -440,8 +440,13 @@ class LocalGroup:
         the per-rank kernels overlap on the device(s))."""
         out = []
         for r, c in enumerate(self.comms):
-            with torch.cuda.device(c.device), torch.cuda.stream(self.streams[r]):
-                out.append(fn(c, r, self.streams[r]))
+            with torch.cuda.device(c.device):
+                # Rank streams are non-blocking: order them after whatever the
+                # caller has queued on the device's current stream (e.g. the
+                # copies that filled the input buffers)
+                self.streams[r].wait_stream(torch.cuda.current_stream(c.device))
+                with torch.cuda.stream(self.streams[r]):
+                    out.append(fn(c, r, self.streams[r]))
         return out
 
     def synchronize(self):
