@@ -270,6 +270,9 @@ def mode_allreduce(args, dist: Dist):
         if err:
             raise SystemExit(f"device watchdog error {err}")
         # ---- end to end through the public API: pinned host -> H2D -> allreduce -> D2H
+        # pinned staging memory on the GPU's own NUMA node (first touch)
+        from faabric_b200.utils import bind_process_near_gpu
+        numa_cpus = bind_process_near_gpu(dist.local) if dist.multi else []
         host = torch.empty(sync.total_padded, dtype=torch.int32).pin_memory()
         host.copy_((torch.arange(sync.total_padded, dtype=torch.int32) % 1000) + dist.rank)
         for _ in range(max(3, args.warmup)):
@@ -295,6 +298,8 @@ def mode_allreduce(args, dist: Dist):
             "ms_per_step": round(e2e_ms, 4),
             "h2d_bytes_per_step": sync.h2d_bytes_per_step,
             "d2h_bytes_per_step": sync.d2h_bytes_per_step,
+            "h2d_pipeline_chunks": 4,
+            "numa_bound_cpus": len(numa_cpus),
         }
         # ---- secondary: DDP-style bucketing (not the headline: fewer, larger calls)
         bucketed = None

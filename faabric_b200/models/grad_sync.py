@@ -87,11 +87,14 @@ class GradientSync:
         else:
             self._jobs = [(s, r, n) for s, r, n in zip(self.send_views, self.recv_views, self.sizes)]
         self.launches_per_step = len(self._jobs)
+        self._chunks = None
+        self._chunk_graphs = []
 
     # ------------------------------------------------------------------ core
-    def _issue(self, stream):
+    def _issue(self, stream, jobs=None):
+        jobs = self._jobs if jobs is None else jobs
         if self.channels == 1:
-            for s, r, _ in self._jobs:
+            for s, r, _ in jobs:
                 self.comm.all_reduce(s, r, op=self.op, algo=self.algo, stream=stream)
             return
         # fork: lane streams wait for everything already queued on `stream`
@@ -99,11 +102,11 @@ class GradientSync:
         for lane in self._lanes:
             lane.wait_event(self._fork)
         # biggest tensors first, round-robin over the lanes
-        order = sorted(range(len(self._jobs)), key=lambda i: -self._jobs[i][2])
+        order = sorted(range(len(jobs)), key=lambda i: -jobs[i][2])
         for k, i in enumerate(order):
             ch = k % self.channels
             st = stream if ch == 0 else self._lanes[ch - 1]
-            self.comm.all_reduce(self._jobs[i][0], self._jobs[i][1], op=self.op, algo=self.algo, stream=st, channel=ch)
+            self.comm.all_reduce(jobs[i][0], jobs[i][1], op=self.op, algo=self.algo, stream=st, channel=ch)
         # join
         for lane, ev in zip(self._lanes, self._joins):
             ev.record(lane)
@@ -130,15 +133,75 @@ class GradientSync:
         else:
             self._issue(stream)
 
-    def step_from_host(self, host_grads: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+    def _pipeline_chunks(self, k: int):
+        """Split the jobs (in buffer order) into k contiguous chunks of similar
+        byte size: [(elem_begin, elem_end, jobs)]."""
+        spans = []
+        for (s, r, n) in self._jobs:
+            begin = s.data_ptr() - self.send.data_ptr()
+            spans.append((begin // self.send.element_size(), s, r, n))
+        spans.sort(key=lambda t: t[0])
+        total = self.total_padded
+        chunks = []
+        cur = []
+        cur_begin = 0
+        for idx, (begin, s, r, n) in enumerate(spans):
+            cur.append((s, r, n))
+            nxt = spans[idx + 1][0] if idx + 1 < len(spans) else total
+            if len(chunks) < k - 1 and nxt - cur_begin >= total / k:
+                chunks.append((cur_begin, nxt, cur))
+                cur = []
+                cur_begin = nxt
+        if cur:
+            chunks.append((cur_begin, total, cur))
+        return chunks
+
+    def step_from_host(
+        self,
+        host_grads: torch.Tensor,
+        stream: Optional[torch.cuda.Stream] = None,
+        pipeline: int = 4,
+    ):
         """End-to-end step: copy this step's gradients from pinned host memory,
         all-reduce, and read a result digest (first element + checksum of the
-        first tensor) back to the host.  Returns the host digest tensor after
-        synchronising the stream."""
+        first tensor) back to the host.  The H2D copy is cut into `pipeline`
+        chunks on a copy stream; the all-reduces of a chunk start as soon as it
+        has landed, overlapping the rest of the transfer.  Returns the host
+        digest tensor after synchronising the stream."""
         stream = stream or torch.cuda.current_stream(self.comm.device)
+        if pipeline <= 1 or not self.use_graph:
+            with torch.cuda.stream(stream):
+                self.send[: host_grads.numel()].copy_(host_grads, non_blocking=True)
+                self.step(stream)
+        else:
+            if self._chunks is None or len(self._chunks) != pipeline:
+                self._chunks = self._pipeline_chunks(pipeline)
+                self._chunk_graphs = [None] * len(self._chunks)
+                self._copy_stream = torch.cuda.Stream(device=self.comm.device)
+                self._chunk_events = [torch.cuda.Event() for _ in self._chunks]
+            # copies are ordered after whatever the caller queued on `stream`
+            self._copy_stream.wait_stream(stream)
+            limit = host_grads.numel()
+            with torch.cuda.stream(self._copy_stream):
+                for (a, b, _), ev in zip(self._chunks, self._chunk_events):
+                    hi = min(b, limit)
+                    if hi > a:
+                        self.send[a:hi].copy_(host_grads[a:hi], non_blocking=True)
+                    ev.record(self._copy_stream)
+            for k, ((a, b, jobs), ev) in enumerate(zip(self._chunks, self._chunk_events)):
+                stream.wait_event(ev)
+                if self._chunk_graphs[k] is None:
+                    # warm, then capture this chunk's launch sequence
+                    stream.synchronize()
+                    self._issue(self._stream, jobs)
+                    self._stream.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self._stream):
+                        self._issue(self._stream, jobs)
+                    self._chunk_graphs[k] = g
+                with torch.cuda.stream(stream):
+                    self._chunk_graphs[k].replay()
         with torch.cuda.stream(stream):
-            self.send[: host_grads.numel()].copy_(host_grads, non_blocking=True)
-            self.step(stream)
             first = self.recv_views[0]
             self._result[0] = first[0].to(torch.int64)
             self._result[1] = first.to(torch.int64).sum()
@@ -156,6 +219,7 @@ class GradientSync:
 
     def close(self):
         self._graph = None
+        self._chunk_graphs = []
         if self.recv is not self.send:
             self.comm.free(self.recv)
         self.comm.free(self.send)
