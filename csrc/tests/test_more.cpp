@@ -1,0 +1,311 @@
+// Smaller components (strategy: reference tests/test/util/test_concurrent_map,
+// test_files, test_hwloc; executor/test_executor_context; transport/
+// test_tcp_sockets, test_message; proto/test_proto; snapshot/
+// test_snapshot_registry; scheduler/test_function_client_server;
+// runner/test_main; mpi/test_mpi_exec_graph, test_multiple_mpi_worlds)
+#include "fixtures.h"
+
+#include <faabric/executor/ExecutorContext.h>
+#include <faabric/mpi/MpiWorldRegistry.h>
+#include <faabric/mpi/mpi.h>
+#include <faabric/runner/FaabricMain.h>
+#include <faabric/scheduler/FunctionCallClient.h>
+#include <faabric/snapshot/SnapshotRegistry.h>
+#include <faabric/transport/tcp/Socket.h>
+#include <faabric/util/ExecGraph.h>
+#include <faabric/util/compare.h>
+#include <faabric/util/concurrent_map.h>
+#include <faabric/util/files.h>
+#include <faabric/util/hwloc.h>
+
+#include <thread>
+#include <unistd.h>
+
+using namespace tests;
+
+TEST_CASE("concurrent map operations", "[util]")
+{
+    faabric::util::ConcurrentMap<int, std::shared_ptr<int>> map;
+    REQUIRE(map.isEmpty());
+    REQUIRE(map.tryEmplace(1, std::make_shared<int>(10)));
+    REQUIRE(!map.tryEmplace(1, std::make_shared<int>(11)));
+    auto [inserted, value] = map.tryEmplaceShared(2, std::make_shared<int>(20));
+    REQUIRE(inserted);
+    REQUIRE_EQ(*value, 20);
+    auto [again, same] = map.tryEmplaceShared(2, std::make_shared<int>(21));
+    REQUIRE(!again);
+    REQUIRE_EQ(*same, 20);
+    bool wasInserted = true;
+    map.tryEmplaceThenMutate(
+      2, [&](bool ins, std::shared_ptr<int>& v) {
+          wasInserted = ins;
+          *v += 5;
+      },
+      std::make_shared<int>(0));
+    REQUIRE(!wasInserted);
+    REQUIRE_EQ(**map.get(2), 25);
+    map.insertOrAssign(3, std::make_shared<int>(30));
+    REQUIRE(map.contains(3));
+    REQUIRE(!map.get(99).has_value());
+    int seen = 0;
+    REQUIRE(map.inspect(3, [&](const std::shared_ptr<int>& v) { seen = *v; }));
+    REQUIRE_EQ(seen, 30);
+    REQUIRE_EQ(map.eraseIf([](const int& k, const std::shared_ptr<int>& v) { return *v >= 25; }), 2u);
+    REQUIRE_EQ(map.size(), 1u);
+    REQUIRE(map.erase(1));
+    REQUIRE(!map.erase(1));
+
+    // Concurrent emplaces of distinct keys all land
+    faabric::util::ConcurrentMap<int, int> counts;
+    std::vector<std::thread> ts;
+    for (int t = 0; t < 8; t++) {
+        ts.emplace_back([&, t] {
+            for (int i = 0; i < 500; i++) {
+                counts.tryEmplace(t * 1000 + i, i);
+            }
+        });
+    }
+    for (auto& t : ts) {
+        t.join();
+    }
+    REQUIRE_EQ(counts.size(), 4000u);
+}
+
+TEST_CASE("files, compare and cpu pinning helpers", "[util]")
+{
+    std::string path = "/tmp/faabric_b200_test_" + std::to_string(getpid());
+    std::vector<uint8_t> bytes = { 0x00, 0x61, 0x73, 0x6d, 1, 0, 0, 0 };
+    faabric::util::writeBytesToFile(path, bytes);
+    REQUIRE(faabric::util::readFileToBytes(path) == bytes);
+    REQUIRE_EQ(faabric::util::readFileToString(path).size(), bytes.size());
+    REQUIRE(faabric::util::isWasm(bytes));
+    REQUIRE(!faabric::util::isWasm({ 1, 2, 3, 4 }));
+    ::unlink(path.c_str());
+    REQUIRE_THROWS(faabric::util::readFileToBytes("/nonexistent/file"));
+
+    int a[3] = { 1, 2, 3 }, b[3] = { 1, 2, 3 }, c[3] = { 1, 2, 4 };
+    REQUIRE(faabric::util::compareArrays(a, b, 3));
+    REQUIRE(!faabric::util::compareArrays(a, c, 3));
+
+    int before = faabric::util::getNumFreeCpus();
+    REQUIRE(before > 0);
+    {
+        std::vector<std::unique_ptr<faabric::util::FaabricCpuSet>> pins;
+        std::thread t([&] { pins.push_back(faabric::util::pinThreadToFreeCpu(pthread_self())); });
+        t.join();
+        REQUIRE_EQ(faabric::util::getNumFreeCpus(), before - 1);
+        REQUIRE(pins[0]->getCpuIdx() >= 0);
+    }
+    // Released when the handle goes away
+    REQUIRE_EQ(faabric::util::getNumFreeCpus(), before);
+}
+
+TEST_CASE("executor context is per thread", "[executor]")
+{
+    using faabric::executor::ExecutorContext;
+    REQUIRE(!ExecutorContext::isSet());
+    REQUIRE_THROWS(ExecutorContext::get());
+    auto req = faabric::util::batchExecFactory("demo", "ctx", 3);
+    ExecutorContext::set(nullptr, req, 2);
+    REQUIRE(ExecutorContext::isSet());
+    REQUIRE_EQ(ExecutorContext::get()->getMsgIdx(), 2);
+    REQUIRE_EQ(ExecutorContext::get()->getMsg().id(), req->messages(2).id());
+    std::thread other([&] {
+        if (ExecutorContext::isSet()) {
+            fbtest::fail(__FILE__, __LINE__, "context leaked into another thread");
+        }
+    });
+    other.join();
+    ExecutorContext::unset();
+    REQUIRE(!ExecutorContext::isSet());
+}
+
+TEST_CASE("raw tcp sockets", "[transport]")
+{
+    using namespace faabric::transport::tcp;
+    int port = 9733;
+    RecvSocket server(port);
+    server.listen();
+    std::vector<uint8_t> payload(200000);
+    for (size_t i = 0; i < payload.size(); i++) {
+        payload[i] = (uint8_t)(i * 7);
+    }
+    std::thread client([&] {
+        SendSocket s("127.0.0.1", port);
+        s.dial();
+        uint32_t n = (uint32_t)payload.size();
+        s.sendOne((const uint8_t*)&n, sizeof(n));
+        s.sendOne(payload.data(), payload.size());
+    });
+    int conn = server.accept(5000);
+    REQUIRE(conn >= 0);
+    uint32_t n = 0;
+    server.recvOne(conn, (uint8_t*)&n, sizeof(n));
+    REQUIRE_EQ(n, (uint32_t)payload.size());
+    std::vector<uint8_t> got(n);
+    server.recvOne(conn, got.data(), n);
+    client.join();
+    REQUIRE(got == payload);
+    // Nobody listening: dial gives up
+    SendSocket nobody("127.0.0.1", 9734);
+    REQUIRE_THROWS(nobody.dial(2, 10));
+}
+
+TEST_CASE("transport message header and wire format", "[transport][proto]")
+{
+    uint8_t hdr[HEADER_MSG_SIZE];
+    faabric::transport::Message::writeHeader(hdr, 42, 123456789012ull, -7);
+    uint8_t code;
+    uint64_t size;
+    int32_t seq;
+    faabric::transport::Message::readHeader(hdr, code, size, seq);
+    REQUIRE_EQ((int)code, 42);
+    REQUIRE_EQ(size, 123456789012ull);
+    REQUIRE_EQ(seq, -7);
+
+    // Protobuf wire compatibility: field 1 varint, field 6 string
+    faabric::Message m;
+    m.set_id(150);
+    m.set_user("ab");
+    std::string wire = m.SerializeAsString();
+    std::string expected = { 0x08, (char)0x96, 0x01, 0x32, 0x02, 'a', 'b' };
+    REQUIRE_EQ(wire, expected);
+    // Unknown fields are skipped, negative ints are 10-byte varints
+    faabric::Message neg;
+    neg.set_returnvalue(-1);
+    REQUIRE_EQ(neg.SerializeAsString().size(), 11u);
+    faabric::Message parsed;
+    std::string withUnknown = wire + std::string({ (char)0xf8, 0x7f, 0x05 }); // field 2047 varint 5
+    REQUIRE(parsed.ParseFromString(withUnknown));
+    REQUIRE_EQ(parsed.id(), 150);
+    REQUIRE(!parsed.ParseFromString(std::string({ 0x0a, 0x7f }))); // truncated length-delimited field
+}
+
+TEST_CASE("snapshot registry", "[snapshot]")
+{
+    auto& reg = faabric::snapshot::getSnapshotRegistry();
+    reg.clear();
+    REQUIRE_EQ(reg.getSnapshotCount(), 0u);
+    auto a = std::make_shared<faabric::util::SnapshotData>(1024);
+    auto b = std::make_shared<faabric::util::SnapshotData>(2048);
+    reg.registerSnapshot("a", a);
+    reg.registerSnapshot("b", b);
+    REQUIRE_EQ(reg.getSnapshotCount(), 2u);
+    REQUIRE(reg.getSnapshot("b").get() == b.get());
+    // Re-registering replaces
+    auto a2 = std::make_shared<faabric::util::SnapshotData>(4096);
+    reg.registerSnapshot("a", a2);
+    REQUIRE_EQ(reg.getSnapshot("a")->getSize(), 4096u);
+    reg.deleteSnapshot("a");
+    REQUIRE(!reg.snapshotExists("a"));
+    REQUIRE_THROWS(reg.getSnapshot("a"));
+    reg.clear();
+}
+
+TEST_CASE("function call client records calls in mock mode", "[scheduler]")
+{
+    faabric::util::setMockMode(true);
+    faabric::scheduler::clearMockRequests();
+    auto req = faabric::util::batchExecFactory("demo", "mock", 2);
+    faabric::scheduler::FunctionCallClient cli("somewhere");
+    cli.executeFunctions(req);
+    cli.sendFlush();
+    auto res = std::make_shared<faabric::Message>(req->messages(0));
+    cli.setMessageResult(res);
+    auto batches = faabric::scheduler::getBatchRequests();
+    REQUIRE_EQ(batches.size(), 1u);
+    REQUIRE_EQ(batches[0].first, std::string("somewhere"));
+    REQUIRE_EQ(batches[0].second->messages_size(), 2);
+    REQUIRE_EQ(faabric::scheduler::getFlushCalls().size(), 1u);
+    REQUIRE_EQ(faabric::scheduler::getMessageResults().size(), 1u);
+    faabric::scheduler::clearMockRequests();
+    REQUIRE_EQ(faabric::scheduler::getBatchRequests().size(), 0u);
+    faabric::util::setMockMode(false);
+}
+
+TEST_CASE("runner boots and shuts a worker down", "[runner]")
+{
+    // Planner in-process, then a full worker through FaabricMain
+    faabric::planner::PlannerServer plannerServer;
+    plannerServer.start();
+    faabric::planner::getPlanner().reset();
+    {
+        faabric::runner::FaabricMain m(std::make_shared<TestExecutorFactory>());
+        m.startBackground();
+        auto hosts = faabric::planner::getPlannerClient().getAvailableHosts();
+        REQUIRE_EQ(hosts.size(), 1u);
+        REQUIRE(hosts[0].slots() > 0);
+        auto req = faabric::util::batchExecFactory("demo", "echo", 1);
+        req->mutable_messages(0)->set_inputdata("via runner");
+        faabric::planner::getPlannerClient().callFunctions(req);
+        auto res = faabric::planner::getPlannerClient().getMessageResult(req->messages(0), 5000);
+        REQUIRE_EQ(res.outputdata(), std::string("via runner"));
+        m.shutdown();
+        REQUIRE_EQ(faabric::planner::getPlannerClient().getAvailableHosts().size(), 0u);
+    }
+    faabric::planner::getPlanner().reset();
+    plannerServer.stop();
+    faabric::scheduler::getScheduler().reset();
+}
+
+TEST_CASE("mpi: exec graph counts messages, two worlds run side by side", "[mpi]")
+{
+    ClusterFixture f(8);
+    registerTestFunction("mpi", "graph", [&](auto*, int, int idx, auto req) {
+        MPI_Init(nullptr, nullptr);
+        int rank, size;
+        MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+        MPI_Comm_size(MPI_COMM_WORLD, &size);
+        int v = rank;
+        if (rank == 0) {
+            for (int i = 0; i < 3; i++) {
+                MPI_Send(&v, 1, MPI_INT, 1, 0, MPI_COMM_WORLD);
+            }
+        } else if (rank == 1) {
+            for (int i = 0; i < 3; i++) {
+                MPI_Recv(&v, 1, MPI_INT, 0, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+            }
+        }
+        int sum = 0;
+        MPI_Allreduce(&rank, &sum, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        MPI_Finalize();
+        return sum == size * (size - 1) / 2 ? 0 : 1;
+    });
+    // Two independent worlds of different sizes at the same time
+    auto reqA = faabric::util::batchExecFactory("mpi", "graph", 1);
+    reqA->mutable_messages(0)->set_ismpi(true);
+    reqA->mutable_messages(0)->set_mpiworldsize(3);
+    reqA->mutable_messages(0)->set_recordexecgraph(true);
+    auto reqB = faabric::util::batchExecFactory("mpi", "graph", 1);
+    reqB->mutable_messages(0)->set_ismpi(true);
+    reqB->mutable_messages(0)->set_mpiworldsize(4);
+    f.plannerCli.callFunctions(reqA);
+    f.plannerCli.callFunctions(reqB);
+    auto stA = f.awaitBatch(reqA);
+    auto stB = f.awaitBatch(reqB);
+    REQUIRE_EQ(stA->messageresults_size(), 3);
+    REQUIRE_EQ(stB->messageresults_size(), 4);
+    std::set<int> worlds;
+    for (auto* st : { stA.get(), stB.get() }) {
+        for (auto& m : st->messageresults()) {
+            REQUIRE_EQ(m.returnvalue(), 0);
+            worlds.insert(m.mpiworldid());
+        }
+    }
+    REQUIRE_EQ(worlds.size(), 2u);
+    // Rank 0 of world A recorded its three normal messages to rank 1
+    for (auto& m : stA->messageresults()) {
+        if (m.mpirank() == 0) {
+            std::string key = std::string(MPI_MSGTYPE_COUNT_PREFIX) + "-" + std::to_string((int)faabric::mpi::MpiMessageType::NORMAL) + "-1";
+            REQUIRE(m.intexecgraphdetails().count(key) == 1);
+            REQUIRE_EQ(m.intexecgraphdetails().at(key), 3);
+            REQUIRE(m.intexecgraphdetails().at(std::string(MPI_MSG_COUNT_PREFIX) + "-1") >= 3);
+            // ...and the chained ranks show up in its exec graph
+            auto graph = faabric::util::getFunctionExecGraph(m);
+            REQUIRE_EQ(faabric::util::countExecGraphNodes(graph), 3);
+            auto hosts = faabric::util::getMpiRankHostsFromExecGraph(graph);
+            REQUIRE_EQ(hosts.size(), 3u);
+        }
+    }
+    faabric::mpi::getMpiWorldRegistry().clear();
+}
