@@ -270,7 +270,7 @@ class MpiWorld
     faabric::util::TimePoint creationTime;
 
     // Grid declared by the last MPI_Cart_create (rows, cols)
-    int cartDims[2] = { 0, 0 };
+    std::atomic<int> cartDims[2]{ 0, 0 };
 
     std::atomic<int> activeLocalRanks = 0;
     std::atomic<bool> hasBeenMigrated = false;

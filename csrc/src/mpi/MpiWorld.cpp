@@ -1922,8 +1922,9 @@ void MpiWorld::getCartesianRank(int rank, int maxDims, const int* dims, int* per
     if (dims[0] * dims[1] != size) {
         throw std::runtime_error("Product of ranks across dimensions not equal to world size");
     }
-    cartDims[0] = dims[0];
-    cartDims[1] = dims[1];
+    // Every rank records the (same) grid
+    cartDims[0].store(dims[0]);
+    cartDims[1].store(dims[1]);
     // Row-major placement on the grid
     coords[0] = rank / dims[1];
     coords[1] = rank % dims[1];
@@ -1944,20 +1945,20 @@ bool MpiWorld::getCartesianDims(int* dims2) const
     if (cartDims[0] <= 0 || cartDims[1] <= 0) {
         return false;
     }
-    dims2[0] = cartDims[0];
-    dims2[1] = cartDims[1];
+    dims2[0] = cartDims[0].load();
+    dims2[1] = cartDims[1].load();
     return true;
 }
 
 void MpiWorld::getRankFromCoords(int* rank, int* coords)
 {
-    int cols = cartDims[1] > 0 ? cartDims[1] : 1;
+    int cols = std::max(1, cartDims[1].load());
     *rank = coords[1] + coords[0] * cols;
 }
 
 void MpiWorld::shiftCartesianCoords(int rank, int direction, int disp, int* source, int* destination)
 {
-    int cols = cartDims[1] > 0 ? cartDims[1] : 1;
+    int cols = std::max(1, cartDims[1].load());
     int rows = size / cols;
     int dims[2] = { rows, cols };
     int coords[2] = { rank / cols, rank % cols };

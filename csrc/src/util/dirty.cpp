@@ -408,6 +408,8 @@ struct UffdDirtyTracker::Impl
     std::thread eventThread;
     std::atomic<bool> running{ false };
     std::span<uint8_t> tracked;
+    // The event thread marks pages in the record the control calls reset
+    std::mutex recordMx;
 
     void loop()
     {
@@ -429,8 +431,11 @@ struct UffdDirtyTracker::Impl
                 continue;
             }
             void* addr = (void*)(uintptr_t)msg.arg.pagefault.address;
-            if (globalRecord.regionBase != nullptr && globalRecord.contains(addr)) {
-                globalRecord.mark(addr);
+            {
+                std::lock_guard<std::mutex> lk(recordMx);
+                if (globalRecord.regionBase != nullptr && globalRecord.contains(addr)) {
+                    globalRecord.mark(addr);
+                }
             }
             // Drop write protection on the page and wake the faulting thread
             uffdio_writeprotect wp;
@@ -520,6 +525,7 @@ UffdDirtyTracker::~UffdDirtyTracker()
 
 void UffdDirtyTracker::clearAll()
 {
+    std::lock_guard<std::mutex> lk(impl->recordMx);
     globalRecord.clear();
     threadRecord.clear();
 }
@@ -529,8 +535,11 @@ void UffdDirtyTracker::startTracking(std::span<uint8_t> region)
     if (region.empty() || region.data() == nullptr) {
         return;
     }
-    globalRecord.reset(region);
-    impl->tracked = region;
+    {
+        std::lock_guard<std::mutex> lk(impl->recordMx);
+        globalRecord.reset(region);
+        impl->tracked = region;
+    }
     size_t len = getRequiredHostPages(region.size()) * HOST_PAGE_SIZE;
     uffdio_register reg;
     memset(&reg, 0, sizeof(reg));

@@ -88,6 +88,9 @@ def main(argv=None):
         # Host code only (device code has compute-sanitizer): separate object dir
         env = dict(os.environ)
         env["FAABRIC_B200_SANITISE"] = a.kind
+        # the sanitizer runtimes ship with the system compiler
+        if os.path.exists("/usr/bin/g++"):
+            env["CXX"] = "/usr/bin/g++"
         rc = _run([sys.executable, "-m", "faabric_b200.build", "--force"], cwd=ROOT, env=env)
         if rc != 0:
             return rc
