@@ -464,8 +464,9 @@ void MpiWorld::recordExecGraph(int recvRank, MpiMessageType type)
 static int tcpPortFor(const std::string& host, int mpiPort)
 {
     auto a = faabric::transport::parseHostAddress(host);
-    // Worker processes on one box share an IP: spread their MPI ports
-    return mpiPort + a.portOffset * 64;
+    // Worker processes on one box share an IP and differ by port offset, like
+    // every other service port
+    return mpiPort + a.portOffset;
 }
 
 void MpiWorld::initSendRecvSockets(int thisRank)

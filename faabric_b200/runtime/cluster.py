@@ -21,6 +21,9 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
+_instances = 0
+
+
 class LocalCluster:
     """planner_server + ``n_workers`` faabric_worker processes.
 
@@ -43,8 +46,14 @@ class LocalCluster:
         self.log_level = log_level
         self.extra_env = dict(extra_env or {})
         self.log_dir = Path(log_dir) if log_dir else None
-        # Keep concurrent clusters (xdist) apart
-        self.base_offset = base_offset if base_offset is not None else 1000 + (os.getpid() % 40) * 1000
+        # Keep concurrent clusters apart: other processes (xdist) by pid, other
+        # instances in this process by a counter.  Offsets stay far below the
+        # ephemeral port range (highest port = 8100 + offset + 100 * workers)
+        global _instances
+        if base_offset is None:
+            base_offset = 1000 + (os.getpid() % 12) * 3000 + (_instances % 5) * 600
+        _instances += 1
+        self.base_offset = base_offset
         self.procs: list[subprocess.Popen] = []
         self.http_port = _free_port()
         self.client = PlannerHttpClient("127.0.0.1", self.http_port)
