@@ -899,6 +899,10 @@ void MpiWorld::ensureDeviceComms()
     }
     auto cfg = faabric::device::CommConfig::fromEnv();
     cfg.heapBytes = (size_t)faabric::util::getSystemConfig().symmHeapBytes;
+    if (getenv("FAABRIC_COMM_CHANNELS") == nullptr) {
+        // MPI_Iallreduce bursts pipeline over the channels: use them all
+        cfg.channels = FB_MAX_CHANNELS;
+    }
     try {
         if (allLocal) {
             std::vector<int> devices(size);
