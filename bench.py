@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-device", "mpi-symmetric", "mpi-symmetric-nb"])
     ap.add_argument("--mode", default="allreduce",
                     choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "pingpong"])
-    ap.add_argument("--algo", default="auto")
+    ap.add_argument("--algo", default="tuned",
+                    help="tuned = measure the algorithm policies in place and keep the fastest (allreduce mode)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--channels", type=int, default=4)
     ap.add_argument("--blocks", type=int, default=64, help="max CTAs per collective kernel (sweep modes)")
@@ -327,6 +328,8 @@ def mode_allreduce(args, dist: Dist):
             "cuda_graph": not args.no_graph,
             "channels": args.channels,
             "algo": args.algo,
+            "tuned_policy": sync.policy,
+            "tuned_policy_ms": sync.policy_timings,
             "algo_mix": {k: v for k, v in st.items() if k.startswith("algo_") and v},
         }
         result["_keep"] = (sync, comm, group)

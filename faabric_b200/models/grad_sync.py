@@ -22,6 +22,32 @@ import torch
 from ..parallel import Communicator
 
 
+# Candidate policies for algo="tuned": message bytes -> algorithm.  "auto" defers
+# to the communicator's table/thresholds (measured one collective at a time);
+# the others exist because the best choice under 8 concurrent lanes with few
+# CTAs per kernel differs from the isolated sweep (NVLS is latency-bound with
+# few CTAs, two-shot P2P is not).
+def _policy_auto(nbytes, has_nvls):
+    return "auto"
+
+
+def _policy_twoshot(nbytes, has_nvls):
+    if nbytes <= 32 * 1024:
+        return "ll"
+    return "twoshot"
+
+
+def _policy_nvls_large(nbytes, has_nvls):
+    if nbytes <= 32 * 1024:
+        return "ll"
+    if has_nvls and nbytes >= (4 << 20):
+        return "nvls"
+    return "twoshot"
+
+
+POLICIES = {"auto": _policy_auto, "twoshot": _policy_twoshot, "nvls-large": _policy_nvls_large}
+
+
 class GradientSync:
     def __init__(
         self,
@@ -87,6 +113,11 @@ class GradientSync:
         else:
             self._jobs = [(s, r, n) for s, r, n in zip(self.send_views, self.recv_views, self.sizes)]
         self.launches_per_step = len(self._jobs)
+        # algo="tuned": measure the candidate policies in place (same lanes,
+        # same CTA budget, same tensor mix) on first use and keep the fastest
+        self.policy = None
+        self.policy_timings = {}
+        self._esize = esize
         self._chunks = None
         self._chunk_graphs = []
 
@@ -94,8 +125,8 @@ class GradientSync:
     def _issue(self, stream, jobs=None):
         jobs = self._jobs if jobs is None else jobs
         if self.channels == 1:
-            for s, r, _ in jobs:
-                self.comm.all_reduce(s, r, op=self.op, algo=self.algo, stream=stream)
+            for s, r, n in jobs:
+                self.comm.all_reduce(s, r, op=self.op, algo=self._algo_for(n), stream=stream)
             return
         # fork: lane streams wait for everything already queued on `stream`
         self._fork.record(stream)
@@ -106,11 +137,58 @@ class GradientSync:
         for k, i in enumerate(order):
             ch = k % self.channels
             st = stream if ch == 0 else self._lanes[ch - 1]
-            self.comm.all_reduce(jobs[i][0], jobs[i][1], op=self.op, algo=self.algo, stream=st, channel=ch)
+            self.comm.all_reduce(
+                jobs[i][0], jobs[i][1], op=self.op, algo=self._algo_for(jobs[i][2]), stream=st, channel=ch
+            )
         # join
         for lane, ev in zip(self._lanes, self._joins):
             ev.record(lane)
             stream.wait_event(ev)
+
+    def _algo_for(self, numel: int) -> str:
+        if self.algo != "tuned":
+            return self.algo
+        fn = POLICIES[self.policy or "auto"]
+        return fn(numel * self._esize, self.comm.has_multicast and self.comm.size >= 4)
+
+    def _tune(self):
+        """Time each policy for the whole step (CUDA graph, device events) and
+        agree on the fastest across ranks (max over ranks, via an all-reduce)."""
+        timings = {}
+        graphs = {}
+        for name in POLICIES:
+            if name == "nvls-large" and not (self.comm.has_multicast and self.comm.size >= 4):
+                continue
+            self.policy = name
+            self._graph = None
+            self._capture()
+            g = self._graph
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(self._stream):
+                g.replay()
+                e0.record(self._stream)
+                for _ in range(5):
+                    g.replay()
+                e1.record(self._stream)
+            self._stream.synchronize()
+            timings[name] = e0.elapsed_time(e1) / 5
+            graphs[name] = g
+        names = list(timings)
+        if self.comm.size > 1:
+            # every rank must pick the same policy: compare the slowest rank
+            t = self.comm.empty(len(names), torch.float32)
+            t.copy_(torch.tensor([timings[n] for n in names], dtype=torch.float32))
+            with torch.cuda.stream(self._stream):
+                self.comm.all_reduce(t, t, op="max", stream=self._stream)
+            self._stream.synchronize()
+            agreed = t.cpu().tolist()
+            self.comm.free(t)
+            timings = dict(zip(names, agreed))
+        best = min(names, key=lambda n: timings[n])
+        self.policy = best
+        self.policy_timings = {k: round(v, 4) for k, v in timings.items()}
+        self._graph = graphs[best]
 
     def _capture(self):
         # warm the launch path once outside capture (lazy module loading)
@@ -127,7 +205,10 @@ class GradientSync:
         stream = stream or torch.cuda.current_stream(self.comm.device)
         if self.use_graph:
             if self._graph is None:
-                self._capture()
+                if self.algo == "tuned" and self.policy is None:
+                    self._tune()
+                else:
+                    self._capture()
             with torch.cuda.stream(stream):
                 self._graph.replay()
         else:
@@ -169,6 +250,8 @@ class GradientSync:
         has landed, overlapping the rest of the transfer.  Returns the host
         digest tensor after synchronising the stream."""
         stream = stream or torch.cuda.current_stream(self.comm.device)
+        if self.algo == "tuned" and self.policy is None and self.use_graph:
+            self._tune()
         if pipeline <= 1 or not self.use_graph:
             with torch.cuda.stream(stream):
                 self.send[: host_grads.numel()].copy_(host_grads, non_blocking=True)
