@@ -52,6 +52,8 @@ struct CommConfig
     size_t llMaxBytes = 32 << 10;
     size_t oneShotMaxBytes = 256 << 10;
     size_t nvlsMinBytes = 128 << 10;
+    // integer / f64 reductions use NVLS only above this size (AUTO)
+    size_t nvlsScalarMinBytes = (size_t)32 << 20;
     size_t bcast2StepMinBytes = 1 << 20;
 
     // Fills defaults from FAABRIC_* environment variables

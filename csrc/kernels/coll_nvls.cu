@@ -253,6 +253,26 @@ int nvlsVariant(int dtype, int op)
     return v;
 }
 
+// Only the floating-point variants have 16-byte (.v4) multimem forms; integer
+// and f64 reductions issue one switch request per 4/8-byte element, which
+// makes them request-rate bound for all but very large messages
+bool nvlsVectorised(int variant)
+{
+    switch (variant) {
+        case MM_ADD_F32:
+        case MM_ADD_F16:
+        case MM_MIN_F16:
+        case MM_MAX_F16:
+        case MM_ADD_BF16:
+        case MM_MIN_BF16:
+        case MM_MAX_BF16:
+        case MM_COPY:
+            return true;
+        default:
+            return false;
+    }
+}
+
 #define NVLS_CASE(V)                                                           \
     case V:                                                                    \
         nvlsKernel<V><<<blocks, threads, 0, s>>>(a);                           \

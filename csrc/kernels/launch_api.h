@@ -164,6 +164,9 @@ struct NvlsArgs
 // -1 if the (dtype, op) pair has no in-switch reduction
 int nvlsVariant(int dtype, int op);
 
+// False for variants that reduce element-wise (integers, f64)
+bool nvlsVectorised(int variant);
+
 cudaError_t launchNvls(const NvlsArgs& a,
                        int variant,
                        int blocks,

@@ -64,6 +64,7 @@ CommConfig CommConfig::fromEnv()
     c.channels = (int)envSize("FAABRIC_COMM_CHANNELS", c.channels);
     c.llMaxBytes = envSize("FAABRIC_LL_MAX_BYTES", c.llMaxBytes);
     c.oneShotMaxBytes = envSize("FAABRIC_ONESHOT_MAX_BYTES", c.oneShotMaxBytes);
+    c.nvlsScalarMinBytes = envSize("FAABRIC_NVLS_SCALAR_MIN_BYTES", c.nvlsScalarMinBytes);
     c.nvlsMinBytes = envSize("FAABRIC_NVLS_MIN_BYTES", c.nvlsMinBytes);
     c.bcast2StepMinBytes =
       envSize("FAABRIC_BCAST_2STEP_MIN_BYTES", c.bcast2StepMinBytes);
@@ -942,8 +943,13 @@ int Communicator::reduceLike(int kind,
     // ---- algorithm choice ----
     if (kind == K_ALLREDUCE) {
         if (algo == FB_ALGO_AUTO) {
+            // Element-wise multimem variants (integers, f64) are request-rate
+            // bound: AUTO leaves them to the P2P kernels unless the message is
+            // very large (measured: int32 two-shot beats NVLS 2x at 0.1-9 MB)
+            const bool nvlsWorthIt =
+              fb::nvlsVectorised(nvVariant) || bytes >= cfg_.nvlsScalarMinBytes;
             algo = pickAllReduceAlgo(
-              bytes, hasMulticast() && nvVariant >= 0 && (bytes % 16) == 0);
+              bytes, hasMulticast() && nvVariant >= 0 && (bytes % 16) == 0 && nvlsWorthIt);
         }
         if (algo == FB_ALGO_LL &&
             (bytes > FB_LL_MAX_BYTES || (((uintptr_t)send | (uintptr_t)recv) & 15))) {
