@@ -328,7 +328,7 @@ def mode_allreduce(args, dist: Dist):
             "cuda_graph": not args.no_graph,
             "channels": args.channels,
             "algo": args.algo,
-            "tuned_policy": sync.policy,
+            "tuned_policy": sync.policy_name,
             "tuned_policy_ms": sync.policy_timings,
             "algo_mix": {k: v for k, v in st.items() if k.startswith("algo_") and v},
         }

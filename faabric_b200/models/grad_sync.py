@@ -117,6 +117,8 @@ class GradientSync:
         # same CTA budget, same tensor mix) on first use and keep the fastest
         self.policy = None
         self.policy_timings = {}
+        self._small_lanes = 0
+        self.policy_name = None
         self._esize = esize
         self._chunks = None
         self._chunk_graphs = []
@@ -132,10 +134,21 @@ class GradientSync:
         self._fork.record(stream)
         for lane in self._lanes:
             lane.wait_event(self._fork)
-        # biggest tensors first, round-robin over the lanes
+        # biggest tensors first, round-robin over the lanes.  With
+        # `small_lanes` > 0 the latency-bound small messages get lanes of their
+        # own so they run in the shadow of the bandwidth-bound large ones.
         order = sorted(range(len(jobs)), key=lambda i: -jobs[i][2])
-        for k, i in enumerate(order):
-            ch = k % self.channels
+        k_small = self._small_lanes if self.channels >= 4 else 0
+        big_lanes = self.channels - k_small
+        nb = ns = 0
+        for i in order:
+            nbytes = jobs[i][2] * self._esize
+            if k_small > 0 and nbytes <= 32 * 1024:
+                ch = big_lanes + (ns % k_small)
+                ns += 1
+            else:
+                ch = nb % big_lanes
+                nb += 1
             st = stream if ch == 0 else self._lanes[ch - 1]
             self.comm.all_reduce(
                 jobs[i][0], jobs[i][1], op=self.op, algo=self._algo_for(jobs[i][2]), stream=st, channel=ch
@@ -156,10 +169,16 @@ class GradientSync:
         agree on the fastest across ranks (max over ranks, via an all-reduce)."""
         timings = {}
         graphs = {}
+        candidates = []
         for name in POLICIES:
             if name == "nvls-large" and not (self.comm.has_multicast and self.comm.size >= 4):
                 continue
+            candidates.append((name, 0))
+        if self.channels >= 4:
+            candidates += [("twoshot", 2), ("twoshot", 3)]
+        for name, k_small in candidates:
             self.policy = name
+            self._small_lanes = k_small
             self._graph = None
             self._capture()
             g = self._graph
@@ -172,8 +191,9 @@ class GradientSync:
                     g.replay()
                 e1.record(self._stream)
             self._stream.synchronize()
-            timings[name] = e0.elapsed_time(e1) / 5
-            graphs[name] = g
+            key = name if k_small == 0 else f"{name}+{k_small}small-lanes"
+            timings[key] = e0.elapsed_time(e1) / 5
+            graphs[key] = (g, name, k_small)
         names = list(timings)
         if self.comm.size > 1:
             # every rank must pick the same policy: compare the slowest rank
@@ -186,9 +206,9 @@ class GradientSync:
             self.comm.free(t)
             timings = dict(zip(names, agreed))
         best = min(names, key=lambda n: timings[n])
-        self.policy = best
+        self._graph, self.policy, self._small_lanes = graphs[best]
+        self.policy_name = best
         self.policy_timings = {k: round(v, 4) for k, v in timings.items()}
-        self._graph = graphs[best]
 
     def _capture(self):
         # warm the launch path once outside capture (lazy module loading)
