@@ -50,6 +50,28 @@ class Message final
       , payload(data, data + size)
     {}
 
+    // Non-owning view of a caller's buffer: used by the in-process sync fast
+    // path, where the handler runs on the caller's stack.  Anything that
+    // outlives the call must ensureOwned() first.
+    static Message view(uint8_t codeIn, int seqIn, const uint8_t* data, size_t size)
+    {
+        Message m;
+        m.code = codeIn;
+        m.sequenceNum = seqIn;
+        m.borrowed = std::span<const uint8_t>(data, size);
+        m.isView = true;
+        return m;
+    }
+
+    void ensureOwned()
+    {
+        if (isView) {
+            payload.assign(borrowed.begin(), borrowed.end());
+            borrowed = {};
+            isView = false;
+        }
+    }
+
     Message(Message&& other) = default;
 
     Message& operator=(Message&& other) = default;
@@ -60,21 +82,30 @@ class Message final
 
     MessageResponseCode getResponseCode() const { return failCode; }
 
-    std::vector<uint8_t> dataCopy() const { return payload; }
+    std::vector<uint8_t> dataCopy() const
+    {
+        auto d = udata();
+        return std::vector<uint8_t>(d.begin(), d.end());
+    }
 
     std::span<const uint8_t> udata() const
     {
-        return std::span<const uint8_t>(payload.data(), payload.size());
+        return isView ? borrowed : std::span<const uint8_t>(payload.data(), payload.size());
     }
 
     std::span<const char> data() const
     {
-        return std::span<const char>((const char*)payload.data(), payload.size());
+        auto d = udata();
+        return std::span<const char>((const char*)d.data(), d.size());
     }
 
-    std::vector<uint8_t>& buffer() { return payload; }
+    std::vector<uint8_t>& buffer()
+    {
+        ensureOwned();
+        return payload;
+    }
 
-    size_t size() const { return payload.size(); }
+    size_t size() const { return isView ? borrowed.size() : payload.size(); }
 
     uint8_t getMessageCode() const { return code; }
 
@@ -100,6 +131,8 @@ class Message final
     uint8_t code = NO_HEADER;
     int sequenceNum = NO_SEQUENCE_NUM;
     std::vector<uint8_t> payload;
+    std::span<const uint8_t> borrowed;
+    bool isView = false;
     MessageResponseCode failCode = MessageResponseCode::SUCCESS;
 };
 

@@ -47,6 +47,7 @@ class Queue
         {
             UniqueLock lock(mx);
             mq.emplace(std::move(value));
+            approxSize.store((long)mq.size(), std::memory_order_release);
         }
         enqueueNotifier.notify_one();
     }
@@ -57,6 +58,7 @@ class Queue
         if (!mq.empty()) {
             T value = std::move(mq.front());
             mq.pop();
+            approxSize.store((long)mq.size(), std::memory_order_release);
             emptyNotifier.notify_one();
             *res = std::move(value);
         }
@@ -64,10 +66,25 @@ class Queue
 
     T dequeue(long timeoutMs = DEFAULT_QUEUE_TIMEOUT_MS)
     {
-        UniqueLock lock(mx);
         if (timeoutMs <= 0) {
             throw std::runtime_error("Dequeue timeout must be positive");
         }
+        // A consumer in the middle of a request/response exchange gets its
+        // next item within microseconds: look for it briefly before paying
+        // for a sleep + wake-up (the yield lets a producer that shares our
+        // core run)
+        if (approxSize.load(std::memory_order_acquire) == 0) {
+            auto start = std::chrono::steady_clock::now();
+            for (int i = 0; approxSize.load(std::memory_order_acquire) == 0; i++) {
+                if ((i & 15) == 15) {
+                    std::this_thread::yield();
+                    if (std::chrono::steady_clock::now() - start > std::chrono::microseconds(20)) {
+                        break;
+                    }
+                }
+            }
+        }
+        UniqueLock lock(mx);
         if (!enqueueNotifier.wait_for(lock,
                                       std::chrono::milliseconds(timeoutMs),
                                       [this] { return !mq.empty(); })) {
@@ -75,6 +92,7 @@ class Queue
         }
         T value = std::move(mq.front());
         mq.pop();
+        approxSize.store((long)mq.size(), std::memory_order_release);
         emptyNotifier.notify_one();
         return value;
     }
@@ -109,6 +127,7 @@ class Queue
         while (!mq.empty()) {
             mq.pop();
         }
+        approxSize.store(0, std::memory_order_release);
         emptyNotifier.notify_all();
     }
 
@@ -123,10 +142,12 @@ class Queue
         UniqueLock lock(mx);
         std::queue<T> empty;
         std::swap(mq, empty);
+        approxSize.store(0, std::memory_order_release);
     }
 
   private:
     std::queue<T> mq;
+    std::atomic<long> approxSize{ 0 };
     std::condition_variable enqueueNotifier;
     std::condition_variable emptyNotifier;
     std::mutex mx;

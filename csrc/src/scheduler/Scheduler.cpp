@@ -361,6 +361,8 @@ void Scheduler::setThreadResultLocally(uint32_t appId,
 {
     std::lock_guard<std::mutex> lk(threadResultsMx);
     // Diffs attached to the result point into the transport message: keep it
+    // (a borrowed in-process view must first take a copy)
+    message.ensureOwned();
     threadResultMessages.insert_or_assign(msgId, std::move(message));
     auto it = threadResults.find(msgId);
     if (it == threadResults.end()) {

@@ -340,7 +340,7 @@ Message SyncSendMessageEndpoint::sendAwaitResponse(uint8_t header,
     }
     if (MessageEndpointServer* local = findLocalServer(true)) {
         // Direct call on the caller's thread: no serialisation hop
-        Message req(header, NO_SEQUENCE_NUM, data, dataSize);
+        Message req = Message::view(header, NO_SEQUENCE_NUM, data, dataSize);
         std::string resp = local->handleSync(req);
         return Message(NO_HEADER,
                        NO_SEQUENCE_NUM,
