@@ -551,10 +551,15 @@ def mode_snapshot(args, dist: Dist):
             row[label + "_region_GBps"] = round(size / (ms * 1e-3) / 1e9, 1)
             row[label + "_dirty_GBps"] = round(n_dirty * 4096 / (ms * 1e-3) / 1e9, 1)
         row["diff_bytes"] = int(stats[0].item())
-        # roofline: max(2*region/HBM (scan), dirty/NVLink)
+        # roofline: max(2*region/HBM (every rank scans its own copy),
+        #               incast into the main image: (N-1)*dirty / NVLink ingress of ONE GPU)
         pk = peaks()
         t_scan = 2 * size / (pk.get("hbm_gbs", 6650.0) * 1e9)
-        t_push = (n_dirty * 4096) / 770e9 if n > 1 else (n_dirty * 4096) / (pk.get("hbm_gbs", 6650.0) * 1e9)
+        if n > 1:
+            t_push = (n - 1) * (n_dirty * 4096) / 770e9
+        else:
+            t_push = (n_dirty * 4096) / (pk.get("hbm_gbs", 6650.0) * 1e9)
+        row["roofline_terms_ms"] = {"scan": round(t_scan * 1e3, 4), "incast_push": round(t_push * 1e3, 4)}
         row["roofline_ms_scan_all"] = round(max(t_scan, t_push) * 1e3, 4)
         row["frac_of_roofline_scan_all"] = round(max(t_scan, t_push) * 1e3 / row["scan_all_ms"], 3)
         rows.append(row)
