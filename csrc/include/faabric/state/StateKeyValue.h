@@ -193,6 +193,7 @@ class StateKeyValue
     // Device copy + which host chunks are newer than it / device-dirty chunks
     faabric::util::DeviceRegion deviceCopy;
     int deviceId = -1;
+    bool hostRegistered = false;
     std::vector<uint8_t> hostNewerChunks;   // per STATE_STREAMING_CHUNK
     std::vector<uint8_t> deviceDirtyChunks; // per STATE_STREAMING_CHUNK
     void invalidateDeviceRange(long offset, long len);

@@ -181,6 +181,10 @@ StateKeyValue::StateKeyValue(const std::string& userIn, const std::string& keyIn
 
 StateKeyValue::~StateKeyValue()
 {
+    if (hostRegistered && sharedMemory != nullptr) {
+        cudaHostUnregister(sharedMemory);
+        cudaGetLastError();
+    }
     if (sharedMemory != nullptr) {
         ::munmap(sharedMemory, sharedMemSize);
         sharedMemory = nullptr;
@@ -610,6 +614,14 @@ uint8_t* StateKeyValue::getDevicePtr(int device, void* stream)
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(deviceId);
+    if (!hostRegistered) {
+        // Pin the host value so chunk uploads / downloads are true async DMA
+        if (cudaHostRegister(sharedMemory, sharedMemSize, cudaHostRegisterPortable) == cudaSuccess) {
+            hostRegistered = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
     // Refresh only what the host changed since the last upload
     for (size_t c = 0; c < hostNewerChunks.size(); c++) {
         if (!hostNewerChunks[c]) {
