@@ -201,6 +201,12 @@ int fb_comm_configure(void* h, int key, uint64_t value)
         case 5:
             c.threads = (int)value;
             break;
+        case 6:
+            c.tmaMinBytes = value; // 0 = never use the bulk copy engine
+            break;
+        case 7:
+            c.nvlsScalarMinBytes = value;
+            break;
         default:
             return FB_E_INVALID;
     }
@@ -228,6 +234,7 @@ void fb_comm_stats(void* h, uint64_t* out, int reset)
     for (int i = 0; i < FB_ALGO_COUNT; i++) {
         out[3 + i] = s.algoCount[i];
     }
+    out[15] = s.tmaLaunches;
     if (reset) {
         COMM(h)->resetStats();
     }

@@ -55,6 +55,9 @@ struct CommConfig
     // integer / f64 reductions use NVLS only above this size (AUTO)
     size_t nvlsScalarMinBytes = (size_t)32 << 20;
     size_t bcast2StepMinBytes = 1 << 20;
+    // pull collectives use the TMA bulk-copy engine from this chunk size
+    // (per source/destination pair); 0 = never
+    size_t tmaMinBytes = 256 << 10;
 
     // Fills defaults from FAABRIC_* environment variables
     static CommConfig fromEnv();
@@ -66,6 +69,7 @@ struct CommStats
     uint64_t bytes = 0;
     uint64_t algoCount[FB_ALGO_COUNT] = { 0 };
     uint64_t stagedCopies = 0;
+    uint64_t tmaLaunches = 0;
 };
 
 class Communicator

@@ -227,6 +227,11 @@ cudaError_t launchSnapshotApply(uint8_t* image,
 // Preload every kernel of the library on the current device (see above)
 cudaError_t preloadAllKernels();
 cudaError_t preloadMoveKernels();
+
+// TMA bulk-copy variant of the pull collectives (coll_move_bulk.cu)
+bool moveBulkSupported(const MoveArgs& a);
+cudaError_t launchMoveBulk(const MoveArgs& a, int blocks, cudaStream_t s);
+cudaError_t preloadMoveBulkKernel();
 cudaError_t preloadNvlsKernels();
 cudaError_t preloadSnapshotKernels();
 

@@ -65,6 +65,7 @@ CommConfig CommConfig::fromEnv()
     c.llMaxBytes = envSize("FAABRIC_LL_MAX_BYTES", c.llMaxBytes);
     c.oneShotMaxBytes = envSize("FAABRIC_ONESHOT_MAX_BYTES", c.oneShotMaxBytes);
     c.nvlsScalarMinBytes = envSize("FAABRIC_NVLS_SCALAR_MIN_BYTES", c.nvlsScalarMinBytes);
+    c.tmaMinBytes = envSize("FAABRIC_TMA_MIN_BYTES", c.tmaMinBytes);
     c.nvlsMinBytes = envSize("FAABRIC_NVLS_MIN_BYTES", c.nvlsMinBytes);
     c.bcast2StepMinBytes =
       envSize("FAABRIC_BCAST_2STEP_MIN_BYTES", c.bcast2StepMinBytes);
@@ -1392,8 +1393,21 @@ int Communicator::moveLike(int mode,
                                alignWidth(a.dstStride),
                                alignWidth(a.srcStride) });
         uint64_t words = len / width;
-        cudaError_t ce = fb::launchMove(
-          a, width, blocksFor(words, 2), cfg_.threads, s);
+        cudaError_t ce;
+        if (width == 16 && cfg_.tmaMinBytes > 0 && len >= cfg_.tmaMinBytes &&
+            fb::moveBulkSupported(a)) {
+            // Large chunks: the copy engine streams 32 KiB tiles through
+            // shared memory; a few CTAs (>= 4 tiles each) saturate the link
+            const uint64_t pieces =
+              (mode == fb::MOVE_SCATTER || mode == fb::MOVE_BCAST) ? 1 : (uint64_t)n;
+            const uint64_t tiles = pieces * ((len + 32767) / 32768);
+            const int maxB = std::min(cfg_.maxBlocks, FB_MAX_BLOCKS / cfg_.channels);
+            const int blocks = (int)std::clamp<uint64_t>(tiles / 4, 1, (uint64_t)maxB);
+            ce = fb::launchMoveBulk(a, blocks, s);
+            stats_.tmaLaunches++;
+        } else {
+            ce = fb::launchMove(a, width, blocksFor(words, 2), cfg_.threads, s);
+        }
         if (ce != cudaSuccess) {
             return FB_E_CUDA;
         }

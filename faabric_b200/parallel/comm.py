@@ -193,6 +193,8 @@ class Communicator:
             "bcast2StepMinBytes": 3,
             "maxBlocks": 4,
             "threads": 5,
+            "tmaMinBytes": 6,
+            "nvlsScalarMinBytes": 7,
         }
         for k, v in kw.items():
             self._check(self._lib.fb_comm_configure(self._h, keys[k], int(v)), k)
@@ -200,7 +202,7 @@ class Communicator:
     def stats(self, reset: bool = False) -> dict:
         out = (C.c_uint64 * 16)()
         self._lib.fb_comm_stats(self._h, out, 1 if reset else 0)
-        d = {"launches": out[0], "bytes": out[1], "staged_copies": out[2]}
+        d = {"launches": out[0], "bytes": out[1], "staged_copies": out[2], "tma_launches": out[15]}
         for code, name in ALGO_NAMES.items():
             d[f"algo_{name}"] = out[3 + code]
         return d

@@ -538,3 +538,74 @@ def test_stress_random_skew_and_sizes():
             c.free(gathers[r])
             for t in recvs[r]:
                 c.free(t)
+
+
+@pytest.mark.parametrize("n", [2, 4])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_large_pull_collectives_use_the_bulk_copy_engine(n, symmetric):
+    """Chunks >= 256 KiB go through the TMA kernel (cp.async.bulk through
+    shared memory); results must match the LDG/STG path bit for bit, including
+    a chunk size that is not a multiple of the 32 KiB tile."""
+    g = group(n)
+    per = (384 << 10) // 4 + 36  # 384 KiB + 144 B per rank (int32), 16-byte multiple
+    base = [torch.randint(-(2**31), 2**31 - 1, (per * n,), dtype=torch.int32) for _ in range(n)]
+
+    def alloc(c, numel):
+        return c.empty(numel, torch.int32) if symmetric else torch.empty(numel, dtype=torch.int32, device=f"cuda:{c.device}")
+
+    sends = [alloc(c, per * n) for c in g.comms]
+    outs = [alloc(c, per * n) for c in g.comms]
+    for r, c in enumerate(g.comms):
+        sends[r].copy_(base[r].to(f"cuda:{c.device}"))
+    for c in g.comms:
+        c.stats(reset=True)
+
+    # all-gather of the first `per` elements
+    g.run(lambda c, r, st: c.all_gather(sends[r][:per], outs[r]))
+    g.synchronize()
+    no_errors(g)
+    exp = torch.cat([b[:per] for b in base])
+    for r in range(n):
+        assert torch.equal(outs[r].cpu(), exp)
+    # all-to-all
+    g.run(lambda c, r, st: c.all_to_all(sends[r], outs[r]))
+    g.synchronize()
+    no_errors(g)
+    for r in range(n):
+        exp = torch.cat([base[p][r * per : (r + 1) * per] for p in range(n)])
+        assert torch.equal(outs[r].cpu(), exp)
+    # scatter from rank 1, gather to rank 0, broadcast (below the 2-step size)
+    small = [alloc(c, per) for c in g.comms]
+    g.run(lambda c, r, st: c.scatter(sends[r], small[r], root=1))
+    g.synchronize()
+    for r in range(n):
+        assert torch.equal(small[r].cpu(), base[1][r * per : (r + 1) * per])
+    g.run(lambda c, r, st: c.gather(small[r], outs[r], root=0))
+    g.synchronize()
+    assert torch.equal(outs[0].cpu(), base[1])
+    bc = [alloc(c, per) for c in g.comms]
+    for r, c in enumerate(g.comms):
+        bc[r].copy_(base[r][:per].to(f"cuda:{c.device}"))
+    g.run(lambda c, r, st: c.broadcast(bc[r], root=n - 1))
+    g.synchronize()
+    no_errors(g)
+    for r in range(n):
+        assert torch.equal(bc[r].cpu(), base[n - 1][:per])
+    # ...and it really was the copy engine
+    assert all(c.stats()["tma_launches"] >= 5 for c in g.comms)
+    # same results with the engine switched off
+    for c in g.comms:
+        c.configure(tmaMinBytes=0)
+        c.stats(reset=True)
+    g.run(lambda c, r, st: c.all_to_all(sends[r], outs[r]))
+    g.synchronize()
+    for r in range(n):
+        exp = torch.cat([base[p][r * per : (r + 1) * per] for p in range(n)])
+        assert torch.equal(outs[r].cpu(), exp)
+    assert all(c.stats()["tma_launches"] == 0 for c in g.comms)
+    for c in g.comms:
+        c.configure(tmaMinBytes=256 << 10)
+    if symmetric:
+        for r, c in enumerate(g.comms):
+            for t in (sends[r], outs[r], small[r], bc[r]):
+                c.free(t)
