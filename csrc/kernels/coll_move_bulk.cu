@@ -206,11 +206,22 @@ bool moveBulkSupported(const MoveArgs& a)
            ((uintptr_t)a.recvLocal % 16) == 0;
 }
 
+// The opt-in to >48 KiB of dynamic shared memory is per device
 static cudaError_t configureBulk()
 {
-    static cudaError_t once = cudaFuncSetAttribute(
-      moveBulkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_STAGES * BULK_TILE);
-    return once;
+    static bool done[64] = { false };
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        e = cudaFuncSetAttribute(moveBulkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_STAGES * BULK_TILE);
+        if (e == cudaSuccess && dev >= 0 && dev < 64) {
+            done[dev] = true;
+        }
+    }
+    return e;
 }
 
 cudaError_t launchMoveBulk(const MoveArgs& a, int blocks, cudaStream_t s)
