@@ -31,6 +31,9 @@ class Planner
     // ----------
     PlannerConfig getConfig();
 
+    // Seconds without a keep-alive after which a host is dropped
+    void setHostKeepAliveTimeout(int seconds);
+
     void printConfig() const;
 
     std::string getPolicy();

@@ -8,6 +8,7 @@
 #include <faabric/util/PeriodicBackgroundThread.h>
 
 #include <future>
+#include <map>
 #include <shared_mutex>
 
 namespace faabric::planner {
@@ -18,16 +19,19 @@ class KeepAliveThread : public faabric::util::PeriodicBackgroundThread
   public:
     void doWork() override;
 
-    void setRequest(std::shared_ptr<RegisterHostRequest> thisHostReqIn);
+    // Adds (or replaces) the keep-alive of one host served by this process:
+    // this host itself and every per-GPU virtual host it exposes
+    void setRequest(std::shared_ptr<RegisterHostRequest> hostReqIn);
 
-    // Protects the request (it may be swapped while the thread runs)
+    // Returns how many hosts are still being kept alive
+    size_t removeRequest(const std::string& hostIp);
+
     std::shared_mutex keepAliveThreadMx;
 
   private:
-    std::shared_ptr<RegisterHostRequest> thisHostReq = nullptr;
+    std::map<std::string, std::shared_ptr<RegisterHostRequest>> hostReqs;
 };
 
-// Local cache of results the planner pushed to us / promises we wait on
 struct PlannerCache
 {
     std::unordered_map<uint32_t, std::promise<std::shared_ptr<faabric::Message>>>

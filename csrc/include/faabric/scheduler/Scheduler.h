@@ -17,6 +17,7 @@
 #include <faabric/util/snapshot.h>
 
 #include <future>
+#include <set>
 #include <shared_mutex>
 #include <unordered_map>
 
@@ -138,6 +139,8 @@ class Scheduler
 
     // ---- Planner ----
     faabric::planner::KeepAliveThread keepAliveThread;
+    bool keepAliveRunning = false;
+    std::set<std::string> servedHosts;
 
     // ---- Actual scheduling ----
     SchedulerReaperThread reaperThread;

@@ -239,6 +239,12 @@ void Planner::flushSchedulingState()
 // ---------------------------------------------------------------------------
 // Membership
 // ---------------------------------------------------------------------------
+void Planner::setHostKeepAliveTimeout(int seconds)
+{
+    std::unique_lock<std::shared_mutex> lock(plannerMx);
+    config.set_hosttimeout(seconds);
+}
+
 bool Planner::isHostExpired(std::shared_ptr<Host> host, long epochTimeMs)
 {
     if (epochTimeMs == 0) {

@@ -20,22 +20,37 @@ namespace faabric::planner {
 // ---------------------------------------------------------------------------
 void KeepAliveThread::doWork()
 {
-    std::shared_ptr<RegisterHostRequest> req;
+    std::vector<std::shared_ptr<RegisterHostRequest>> reqs;
     {
         std::shared_lock<std::shared_mutex> lock(keepAliveThreadMx);
-        req = thisHostReq;
+        for (const auto& [ip, req] : hostReqs) {
+            reqs.push_back(req);
+        }
     }
-    if (req != nullptr) {
-        getPlannerClient().registerHost(req);
+    for (const auto& req : reqs) {
+        try {
+            getPlannerClient().registerHost(req);
+        } catch (const std::exception& e) {
+            SPDLOG_WARN("Keep-alive for {} failed: {}", req->host().ip(), e.what());
+        }
     }
 }
 
-void KeepAliveThread::setRequest(std::shared_ptr<RegisterHostRequest> thisHostReqIn)
+void KeepAliveThread::setRequest(std::shared_ptr<RegisterHostRequest> hostReqIn)
+{
+    // Keep-alives must never reset the slot accounting: send a copy without
+    // the overwrite flag
+    auto req = std::make_shared<RegisterHostRequest>(*hostReqIn);
+    req->set_overwrite(false);
+    std::unique_lock<std::shared_mutex> lock(keepAliveThreadMx);
+    hostReqs[req->host().ip()] = std::move(req);
+}
+
+size_t KeepAliveThread::removeRequest(const std::string& hostIp)
 {
     std::unique_lock<std::shared_mutex> lock(keepAliveThreadMx);
-    thisHostReq = std::move(thisHostReqIn);
-    // Keep-alives must never reset the slot accounting
-    thisHostReq->set_overwrite(false);
+    hostReqs.erase(hostIp);
+    return hostReqs.size();
 }
 
 // ---------------------------------------------------------------------------

@@ -66,10 +66,18 @@ void Scheduler::addHostToGlobalSet(
         req->mutable_host()->set_usedslots(0);
     }
     int plannerTimeout = faabric::planner::getPlannerClient().registerHost(req);
-    // Keep-alive only for ourselves, at half the planner's timeout
-    if (hostIp == thisHost && !faabric::util::isTestMode()) {
+    // Keep-alive at half the planner's timeout for every host this process
+    // serves: itself and the per-GPU virtual hosts aliased to it
+    const bool servedHere = hostIp == thisHost || faabric::transport::resolveHostAlias(hostIp) != hostIp;
+    if (servedHere) {
+        servedHosts.insert(hostIp);
+    }
+    if (servedHere && !faabric::util::isTestMode()) {
         keepAliveThread.setRequest(req);
-        keepAliveThread.startMs(std::max(100, plannerTimeout * 1000 / 2));
+        if (!keepAliveRunning) {
+            keepAliveThread.startMs(std::max(100, plannerTimeout * 1000 / 2));
+            keepAliveRunning = true;
+        }
     }
 }
 
@@ -81,9 +89,10 @@ void Scheduler::addHostToGlobalSet()
 void Scheduler::removeHostFromGlobalSet(const std::string& hostIp)
 {
     auto req = std::make_shared<faabric::planner::RemoveHostRequest>();
-    bool isThisHost = hostIp == thisHost && keepAliveThread.getIntervalSeconds() >= 0;
-    if (isThisHost) {
+    servedHosts.erase(hostIp);
+    if (keepAliveRunning && keepAliveThread.removeRequest(hostIp) == 0) {
         keepAliveThread.stop();
+        keepAliveRunning = false;
     }
     req->mutable_host()->set_ip(hostIp);
     faabric::planner::getPlannerClient().removeHost(req);
@@ -144,11 +153,21 @@ void Scheduler::shutdown()
 {
     reset();
     reaperThread.stop();
-    try {
-        removeHostFromGlobalSet(thisHost);
-    } catch (const std::exception& e) {
-        SPDLOG_DEBUG("Could not deregister host on shutdown: {}", e.what());
+    // No more keep-alives, then withdraw every host this process served
+    if (keepAliveRunning) {
+        keepAliveThread.stop();
+        keepAliveRunning = false;
     }
+    std::set<std::string> hosts = servedHosts;
+    hosts.insert(thisHost);
+    for (const auto& h : hosts) {
+        try {
+            removeHostFromGlobalSet(h);
+        } catch (const std::exception& e) {
+            SPDLOG_DEBUG("Could not deregister host {} on shutdown: {}", h, e.what());
+        }
+    }
+    servedHosts.clear();
     _isShutdown = true;
 }
 

@@ -5,6 +5,7 @@
 
 #include <faabric/endpoint/FaabricEndpoint.h>
 #include <faabric/planner/PlannerEndpointHandler.h>
+#include <faabric/transport/common.h>
 #include <faabric/util/ExecGraph.h>
 #include <faabric/util/gids.h>
 #include <faabric/util/json.h>
@@ -429,4 +430,41 @@ TEST_CASE("executor: threads share the main function's memory", "[executor][thre
     // Everything ran in ONE executor
     REQUIRE_EQ(f.sch.getFunctionExecutorCount(req->messages(0)), 1);
     f.awaitBatch(req);
+}
+
+TEST_CASE("planner: hosts without keep-alives expire, served hosts stay", "[planner]")
+{
+    ClusterFixture f(2);
+    int oldTimeout = f.planner.getConfig().hosttimeout();
+    f.planner.setHostKeepAliveTimeout(1);
+    // Outside test mode the scheduler keeps its hosts alive, including the
+    // per-GPU virtual hosts it serves
+    faabric::util::setTestMode(false);
+    faabric::transport::registerHostAlias("gpu0", f.conf.endpointHost);
+    auto res = std::make_shared<faabric::HostResources>();
+    res->set_slots(3);
+    f.sch.addHostToGlobalSet("gpu0", res);
+    f.sch.addHostToGlobalSet();
+    // A host nobody keeps alive
+    auto stale = std::make_shared<faabric::planner::RegisterHostRequest>();
+    stale->mutable_host()->set_ip("stale-host");
+    stale->mutable_host()->set_slots(4);
+    f.plannerCli.registerHost(stale);
+    REQUIRE_EQ(f.plannerCli.getAvailableHosts().size(), 3u);
+
+    std::this_thread::sleep_for(std::chrono::milliseconds(1800));
+    std::set<std::string> alive;
+    for (auto& h : f.plannerCli.getAvailableHosts()) {
+        alive.insert(h.ip());
+    }
+    REQUIRE(alive == (std::set<std::string>{ "gpu0", f.conf.endpointHost }));
+    // Keep-alives did not disturb the slot accounting
+    for (auto& h : f.plannerCli.getAvailableHosts()) {
+        REQUIRE_EQ(h.usedslots(), 0);
+        if (h.ip() == "gpu0") {
+            REQUIRE_EQ(h.slots(), 3);
+        }
+    }
+    faabric::util::setTestMode(true);
+    f.planner.setHostKeepAliveTimeout(oldTimeout);
 }
