@@ -285,6 +285,18 @@ faabric::batch_scheduler::SchedulingDecision PlannerClient::callFunctions(
     faabric::PointToPointMappings resp;
     syncSend(PlannerCalls::CallBatch, req.get(), &resp);
     auto decision = faabric::batch_scheduler::SchedulingDecision::fromPointToPointMappings(resp);
+    // An elastically scaled-up request came back bigger than it went in: mirror
+    // the extra messages so the caller waits for (and accounts) all of them
+    if (req->elasticscalehint() && decision.nFunctions > req->messages_size() && req->messages_size() > 0) {
+        const faabric::Message proto = req->messages(req->messages_size() - 1);
+        for (int i = req->messages_size(); i < decision.nFunctions; i++) {
+            faabric::Message* m = req->add_messages();
+            *m = proto;
+            m->set_id(decision.messageIds.at(i));
+            m->set_appidx(decision.appIdxs.at(i));
+            m->set_groupidx(decision.groupIdxs.at(i));
+        }
+    }
     // The planner assigns the group id when it commits the decision: mirror it
     // into the caller's copy of the request
     if (req->messages_size() > 0 && decision.groupId > 0 && decision.groupId != req->groupid()) {

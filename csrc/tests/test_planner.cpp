@@ -468,3 +468,53 @@ TEST_CASE("planner: hosts without keep-alives expire, served hosts stay", "[plan
     faabric::util::setTestMode(true);
     f.planner.setHostKeepAliveTimeout(oldTimeout);
 }
+
+TEST_CASE("planner: elastic OpenMP scale-up fills the idle slots of the main host", "[planner]")
+{
+    ClusterFixture f(8);
+    std::atomic<bool> release{ false };
+    std::atomic<int> threadsRun{ 0 };
+    registerTestFunction("omp", "region", [&](auto* exec, int, int idx, auto req) {
+        auto& m = *req->mutable_messages(idx);
+        if (req->type() == faabric::BatchExecuteRequest::THREADS) {
+            threadsRun++;
+            return 0;
+        }
+        // Main thread: fork 2 threads but allow the planner to scale the
+        // parallel region up to whatever the host has free
+        auto threads = faabric::util::batchExecFactory("omp", "region", 2);
+        faabric::util::updateBatchExecAppId(threads, m.appid());
+        for (int i = 0; i < 2; i++) {
+            auto* t = threads->mutable_messages(i);
+            t->set_appidx(i + 1);
+            t->set_groupidx(i + 1);
+            t->set_isomp(true);
+            t->set_ompnumthreads(3);
+        }
+        threads->set_singlehost(true);
+        threads->set_singlehosthint(true);
+        threads->set_elasticscalehint(true);
+        auto results = exec->executeThreads(threads, {});
+        m.set_outputdata(std::to_string(results.size()));
+        while (!release.load()) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
+        return 0;
+    });
+    // (A main message that announces its thread count gets exactly that
+    // many slots preloaded; elastic growth applies to regions that were not
+    // announced up-front)
+    auto req = faabric::util::batchExecFactory("omp", "region", 1);
+    f.plannerCli.callFunctions(req);
+    // 8 slots, 1 taken by the main thread: the 2 requested threads grow to 7
+    for (int i = 0; i < 2000 && threadsRun.load() < 7; i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    }
+    REQUIRE_EQ(threadsRun.load(), 7);
+    release = true;
+    auto res = f.awaitResult(req->messages(0));
+    REQUIRE_EQ(res.returnvalue(), 0);
+    REQUIRE_EQ(res.outputdata(), std::string("7"));
+    f.awaitBatch(req);
+    REQUIRE_EQ(f.plannerCli.getAvailableHosts()[0].usedslots(), 0);
+}

@@ -151,6 +151,13 @@ def test_exec_graph_and_policy(cluster):
     assert cluster.client.get_policy() == "bin-pack"
     cluster.client.set_policy("compact")
     assert cluster.client.get_policy() == "compact"
+    # spot policy: the next evicted VMs are visible in the in-flight report
+    with pytest.raises(PlannerError):
+        cluster.client.set_next_evicted_vm(cluster.worker_hosts()[:1])  # only valid under "spot"
+    cluster.client.set_policy("spot")
+    cluster.client.set_next_evicted_vm(cluster.worker_hosts()[:1])
+    assert cluster.client.in_flight_apps().get("nextEvictedVmIps") == cluster.worker_hosts()[:1]
+    cluster.client.set_next_evicted_vm([])
     cluster.client.set_policy("bin-pack")
     assert cluster.client.in_flight_apps().get("apps", []) == []
 
