@@ -15,6 +15,8 @@
 #include <faabric/planner/PlannerClient.h>
 #include <faabric/runner/FaabricMain.h>
 #include <faabric/scheduler/Scheduler.h>
+#include <faabric/state/State.h>
+#include <faabric/transport/PointToPointBroker.h>
 #include <faabric/util/batch.h>
 #include <faabric/util/config.h>
 #include <faabric/util/logging.h>
@@ -82,6 +84,38 @@ static void registerFunctions()
         return 1;
     };
     functions()["demo/noop"] = [](faabric::Message&) { return 0; };
+
+    // Distributed coordination: the functions of one batch (spread over the
+    // workers) increment a shared counter held in distributed state under the
+    // group's lock, then meet at the group barrier; idx 0 reports the total.
+    functions()["ptp/counter"] = [](faabric::Message& msg) {
+        const int rounds = msg.inputdata().empty() ? 5 : std::stoi(msg.inputdata());
+        auto group = faabric::transport::PointToPointGroup::getOrAwaitGroup(msg.groupid());
+        const int idx = msg.groupidx();
+        auto& state = faabric::state::getGlobalState();
+        const std::string key = "counter-" + std::to_string(msg.appid());
+        auto kv = state.getKV("ptp", key, sizeof(int));
+        for (int i = 0; i < rounds; i++) {
+            group->lock(idx, false);
+            kv->pull();
+            int v = 0;
+            kv->get((uint8_t*)&v);
+            v++;
+            kv->set((const uint8_t*)&v);
+            kv->pushFull();
+            group->unlock(idx, false);
+        }
+        group->barrier(idx);
+        kv->pull();
+        int total = 0;
+        kv->get((uint8_t*)&total);
+        msg.set_outputdata(std::to_string(total) + " on " + faabric::scheduler::getScheduler().getThisHost());
+        group->barrier(idx);
+        if (idx == 0) {
+            state.deleteKV("ptp", key);
+        }
+        return 0;
+    };
 
     // Fork-join over THREADS: the main function spawns N threads that may land
     // on other workers; they start from its snapshot, write their own slot and

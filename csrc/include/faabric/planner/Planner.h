@@ -96,6 +96,10 @@ class Planner
     // Spot policy: which hosts go away next
     void setNextEvictedVm(const std::set<std::string>& vmIps);
 
+    // State main election: returns the main host of user/key, electing `host`
+    // if there is none and `claim` is set ("" = none); `drop` forgets it
+    std::string stateMain(const std::string& user, const std::string& key, const std::string& host, bool claim, bool drop);
+
   private:
     std::shared_mutex plannerMx;
     std::condition_variable_any appFinishedCv;

@@ -18,5 +18,7 @@ enum PlannerCalls
     GetNumMigrations = 12,
     CallBatch = 13,
     PreloadSchedulingDecision = 14,
+    // Shared registry of state mains (replaces the reference's Redis keys)
+    StateMain = 20,
 };
 }

@@ -89,6 +89,8 @@ class PlannerClient final : public faabric::transport::MessageEndpointClient
 
     int getNumMigrations();
 
+    std::string stateMain(const std::string& user, const std::string& key, const std::string& host, bool claim, bool drop = false);
+
     void preloadSchedulingDecision(
       std::shared_ptr<faabric::batch_scheduler::SchedulingDecision> preloadDec);
 

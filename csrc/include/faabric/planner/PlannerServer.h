@@ -40,6 +40,8 @@ class PlannerServer final : public faabric::transport::MessageEndpointServer
 
     std::string recvCallBatch(std::span<const uint8_t> buffer);
 
+    std::string recvStateMain(std::span<const uint8_t> buffer);
+
   private:
     faabric::planner::Planner& planner;
 };

@@ -46,6 +46,9 @@ struct PlannerState
     // Apps frozen by a spot eviction, waiting for capacity
     std::map<int, std::shared_ptr<BatchExecuteRequest>> evictedRequests;
 
+    // Main host of every in-memory state value (user_key -> host)
+    std::map<std::string, std::string> stateMains;
+
     // Hosts that will be evicted next (spot policy)
     std::set<std::string> nextEvictedHostIps;
 };

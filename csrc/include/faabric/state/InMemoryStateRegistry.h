@@ -26,9 +26,21 @@ class InMemoryStateRegistry
 
     void clear();
 
+    // Shared mode: mains are elected by the planner, so every worker process
+    // agrees (set by FaabricMain once the planner answers).  Otherwise the
+    // in-process key-value emulation arbitrates (single process, tests).
+    void setShared(bool shared) { sharedViaPlanner = shared; }
+
+    bool isShared() const { return sharedViaPlanner; }
+
+    // Forgets who the main of user/key is: locally only, or in the shared
+    // store as well (the main itself deleting the value)
+    void dropMain(const std::string& user, const std::string& key, bool everywhere);
+
   private:
     std::unordered_map<std::string, std::string> mainMap;
     std::shared_mutex mainMapMutex;
+    bool sharedViaPlanner = false;
 };
 
 InMemoryStateRegistry& getInMemoryStateRegistry();

@@ -218,6 +218,7 @@ void Planner::flushSchedulingState()
     std::unique_lock<std::shared_mutex> lock(plannerMx);
     state.policy = "bin-pack";
     faabric::batch_scheduler::resetBatchScheduler("bin-pack");
+    state.stateMains.clear();
     state.inFlightReqs.clear();
     state.finishedInFlight.clear();
     appFinishedCv.notify_all();
@@ -598,6 +599,25 @@ std::map<int32_t, std::shared_ptr<BatchExecuteRequest>> Planner::getEvictedReqs(
         out[appId] = std::make_shared<BatchExecuteRequest>(*ber);
     }
     return out;
+}
+
+std::string Planner::stateMain(const std::string& user, const std::string& key, const std::string& host, bool claim, bool drop)
+{
+    std::unique_lock<std::shared_mutex> lock(plannerMx);
+    std::string lookup = user + "_" + key;
+    if (drop) {
+        state.stateMains.erase(lookup);
+        return "";
+    }
+    auto it = state.stateMains.find(lookup);
+    if (it != state.stateMains.end()) {
+        return it->second;
+    }
+    if (!claim) {
+        return "";
+    }
+    state.stateMains[lookup] = host;
+    return host;
 }
 
 void Planner::setNextEvictedVm(const std::set<std::string>& vmIps)

@@ -324,6 +324,19 @@ int PlannerClient::getNumMigrations()
     return resp.nummigrations();
 }
 
+std::string PlannerClient::stateMain(const std::string& user, const std::string& key, const std::string& hostIn, bool claim, bool drop)
+{
+    StateMainRequest req;
+    req.set_user(user);
+    req.set_key(key);
+    req.set_host(hostIn);
+    req.set_claim(claim);
+    req.set_drop(drop);
+    StateMainResponse resp;
+    syncSend(PlannerCalls::StateMain, &req, &resp);
+    return resp.host();
+}
+
 void PlannerClient::preloadSchedulingDecision(
   std::shared_ptr<faabric::batch_scheduler::SchedulingDecision> preloadDec)
 {
@@ -378,6 +391,8 @@ std::string PlannerServer::doSyncRecv(transport::Message& message)
             return recvPreloadSchedulingDecision(message.udata());
         case PlannerCalls::CallBatch:
             return recvCallBatch(message.udata());
+        case PlannerCalls::StateMain:
+            return recvStateMain(message.udata());
         default:
             SPDLOG_ERROR("Unrecognised sync planner call header: {}", (int)header);
             return EmptyResponse().SerializeAsString();
@@ -495,6 +510,16 @@ std::string PlannerServer::recvPreloadSchedulingDecision(std::span<const uint8_t
       faabric::batch_scheduler::SchedulingDecision::fromPointToPointMappings(mappings));
     planner.preloadSchedulingDecision((int)decision->appId, decision);
     return EmptyResponse().SerializeAsString();
+}
+
+std::string PlannerServer::recvStateMain(std::span<const uint8_t> buffer)
+{
+    StateMainRequest req;
+    StateMainResponse resp;
+    if (parseInto(buffer, req)) {
+        resp.set_host(planner.stateMain(req.user(), req.key(), req.host(), req.claim(), req.drop()));
+    }
+    return resp.SerializeAsString();
 }
 
 std::string PlannerServer::recvCallBatch(std::span<const uint8_t> buffer)

@@ -2,6 +2,7 @@
 #include <faabric/runner/FaabricMain.h>
 #include <faabric/util/crash.h>
 #include <faabric/util/hwloc.h>
+#include <faabric/state/InMemoryStateRegistry.h>
 #include <faabric/state/State.h>
 #include <faabric/util/logging.h>
 #include <faabric/util/timing.h>
@@ -75,6 +76,9 @@ void FaabricMain::startRunner()
 {
     // Ensure we can ping the planner, then make this host available
     faabric::planner::getPlannerClient().ping();
+    // The planner answers: let it arbitrate state mains so that every worker
+    // process agrees on them
+    faabric::state::getInMemoryStateRegistry().setShared(true);
     auto& sch = faabric::scheduler::getScheduler();
     sch.addHostToGlobalSet();
 }
@@ -111,6 +115,7 @@ void FaabricMain::startStateServer()
 
 void FaabricMain::shutdown()
 {
+    faabric::state::getInMemoryStateRegistry().setShared(false);
     SPDLOG_INFO("Removing from global working set");
     auto& sch = faabric::scheduler::getScheduler();
     sch.shutdown();

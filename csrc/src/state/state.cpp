@@ -1,5 +1,6 @@
 // State layer: registry, key-values (host shared memory + optional device copy),
 // in-memory backend with main-host election, store-backed backend, RPC.
+#include <faabric/planner/PlannerClient.h>
 #include <faabric/redis/Redis.h>
 #include <faabric/state/InMemoryStateKeyValue.h>
 #include <faabric/state/InMemoryStateRegistry.h>
@@ -711,6 +712,14 @@ std::string InMemoryStateRegistry::getMasterIP(const std::string& user,
     if (it != mainMap.end()) {
         return it->second;
     }
+    if (sharedViaPlanner) {
+        std::string elected = faabric::planner::getPlannerClient().stateMain(user, key, thisIP, claim);
+        if (elected.empty()) {
+            throw StateKeyValueException("Found no main for state " + lookup);
+        }
+        mainMap[lookup] = elected;
+        return elected;
+    }
     // Consult (and possibly write) the shared store under its lock
     std::string storeKey = mainKeyFor(user, key);
     auto& redis = faabric::redis::Redis::getState();
@@ -745,6 +754,22 @@ std::string InMemoryStateRegistry::getMasterIPForOtherMaster(const std::string& 
         throw std::runtime_error("Attempting to pull state size on main " + userIn + "/" + keyIn);
     }
     return mainIP;
+}
+
+void InMemoryStateRegistry::dropMain(const std::string& user, const std::string& key, bool everywhere)
+{
+    {
+        std::unique_lock<std::shared_mutex> lock(mainMapMutex);
+        mainMap.erase(keyFor(user, key));
+    }
+    if (!everywhere) {
+        return;
+    }
+    if (sharedViaPlanner) {
+        faabric::planner::getPlannerClient().stateMain(user, key, "", false, true);
+    } else {
+        faabric::redis::Redis::getState().del(mainKeyFor(user, key));
+    }
 }
 
 void InMemoryStateRegistry::clear()
@@ -795,12 +820,15 @@ void InMemoryStateKeyValue::deleteFromRemote(const std::string& userIn,
 {
     InMemoryStateRegistry& reg = getInMemoryStateRegistry();
     std::string mainIP = reg.getMasterIP(userIn, keyIn, thisIPIn, false);
-    // Nothing remote to delete if we are the main
     if (mainIP == thisIPIn) {
+        // Nothing remote to delete, but the key is up for election again
+        reg.dropMain(userIn, keyIn, true);
         return;
     }
     StateClient client(userIn, keyIn, mainIP);
     client.deleteState();
+    // The main withdrew the registration; forget our cached copy of it
+    reg.dropMain(userIn, keyIn, false);
 }
 
 void InMemoryStateKeyValue::clearAll(bool global)

@@ -151,6 +151,10 @@ PLANNER = dict(
         dict(name="RemoveHostResponse", fields=[F("status", "msg:ResponseStatus", 1)]),
         dict(name="AvailableHostsResponse", fields=[F("hosts", "msg:Host", 1, rep=True)]),
         dict(name="SetEvictedVmIpsRequest", fields=[F("vmIps", "string", 1, rep=True)]),
+        # Election of the "main" host of an in-memory state value.  (The reference
+        # does this through a Redis key + Redis lock; here the planner arbitrates.)
+        dict(name="StateMainRequest", fields=[F("user", "string", 1), F("key", "string", 2), F("host", "string", 3), F("claim", "bool", 4), F("drop", "bool", 5)]),
+        dict(name="StateMainResponse", fields=[F("host", "string", 1)]),
     ],
 )
 

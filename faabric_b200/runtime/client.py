@@ -116,7 +116,7 @@ class PlannerHttpClient:
         app_id = _next_id()
         msgs = []
         for i in range(count):
-            m = {"id": _next_id(), "appId": app_id, "appIdx": i, "user": user, "function": function}
+            m = {"id": _next_id(), "appId": app_id, "appIdx": i, "groupIdx": i, "user": user, "function": function}
             if input_data is not None:
                 # bytes fields travel base64 encoded
                 import base64

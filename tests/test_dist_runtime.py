@@ -128,6 +128,18 @@ def test_mpi_migration_between_worker_processes(tmp_path):
         assert all(h.get("usedSlots", 0) == 0 for h in c.client.available_hosts())
 
 
+def test_group_locks_barriers_and_shared_state_across_workers(cluster):
+    """Four functions of one batch, two per worker process: a counter in
+    distributed state (main elected through the planner, replicas pull/push
+    over the state RPCs) incremented under the point-to-point group lock."""
+    st = cluster.client.invoke("ptp", "counter", count=4, input_data="5", timeout=60)
+    res = st["messageResults"]
+    assert len(res) == 4 and all(m.get("returnValue", 0) == 0 for m in res), res
+    outs = [m["output_data"] for m in res]
+    assert all(o.startswith("20 on ") for o in outs), outs
+    assert {o.split()[-1] for o in outs} == set(cluster.worker_hosts())
+
+
 def test_threads_fork_join_across_workers(tmp_path):
     """THREADS batch spanning two worker processes: remote threads restore the
     main thread's snapshot, their dirty pages come back as diffs and are merged
