@@ -1,5 +1,7 @@
-// Planner daemon: RPC server + snapshot server + JSON-over-HTTP control API
-// (reference: src/planner/planner_server.cpp)
+// Planner daemon.  Three services share the process: the RPC server workers
+// talk to, a snapshot server (frozen / migrating apps park their memory images
+// here) and the JSON-over-HTTP control API, which runs in the foreground until
+// SIGINT / SIGTERM.  (Counterpart of the reference's src/planner/planner_server.cpp.)
 #include <faabric/endpoint/FaabricEndpoint.h>
 #include <faabric/planner/Planner.h>
 #include <faabric/planner/PlannerEndpointHandler.h>
@@ -9,30 +11,42 @@
 #include <faabric/util/crash.h>
 #include <faabric/util/logging.h>
 
+namespace {
+// Starts a background server now and stops it when the scope unwinds
+template<typename Server>
+struct Running
+{
+    Server server;
+    const char* name;
+
+    explicit Running(const char* nameIn)
+      : name(nameIn)
+    {
+        SPDLOG_INFO("Planner: starting {}", name);
+        server.start();
+    }
+
+    ~Running()
+    {
+        SPDLOG_INFO("Planner: stopping {}", name);
+        server.stop();
+    }
+};
+}
+
 int main()
 {
     faabric::util::initLogging();
     faabric::util::setUpCrashHandler();
 
-    SPDLOG_INFO("Starting planner server");
-    faabric::planner::PlannerServer plannerServer;
-    plannerServer.start();
+    Running<faabric::planner::PlannerServer> rpc("RPC server");
+    Running<faabric::snapshot::SnapshotServer> snapshots("snapshot server");
 
-    // Snapshots of frozen / migrating apps are parked on the planner
-    SPDLOG_INFO("Starting planner snapshot server");
-    faabric::snapshot::SnapshotServer snapshotServer;
-    snapshotServer.start();
-
-    SPDLOG_INFO("Starting planner endpoint");
-    faabric::endpoint::FaabricEndpoint endpoint(faabric::util::getSystemConfig().plannerPort,
-                                                faabric::planner::getPlanner().getConfig().numthreadshttpserver(),
-                                                std::make_shared<faabric::planner::PlannerEndpointHandler>());
-    // Blocks until SIGINT / SIGTERM
-    endpoint.start(faabric::endpoint::EndpointMode::SIGNAL);
-
-    SPDLOG_INFO("Planner snapshot server shutting down");
-    snapshotServer.stop();
-    SPDLOG_INFO("Planner server shutting down");
-    plannerServer.stop();
+    const int httpPort = faabric::util::getSystemConfig().plannerPort;
+    const int httpThreads = faabric::planner::getPlanner().getConfig().numthreadshttpserver();
+    faabric::endpoint::FaabricEndpoint http(
+      httpPort, httpThreads, std::make_shared<faabric::planner::PlannerEndpointHandler>());
+    SPDLOG_INFO("Planner: serving HTTP on {} ({} threads)", httpPort, httpThreads);
+    http.start(faabric::endpoint::EndpointMode::SIGNAL);
     return 0;
 }

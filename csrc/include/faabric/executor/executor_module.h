@@ -1,0 +1,277 @@
+// Executors: thread pools that run the messages of a batch.
+//
+// One header per module: the per-class headers of the reference's layout
+// (faabric/executor/*.h) forward here, so either include style works.
+#pragma once
+
+#include <faabric/proto/faabric.pb.h>
+#include <faabric/snapshot/SnapshotRegistry.h>
+#include <faabric/util/clock.h>
+#include <faabric/util/dirty.h>
+#include <faabric/util/exception.h>
+#include <faabric/util/hwloc.h>
+#include <faabric/util/queue.h>
+#include <faabric/util/snapshot.h>
+
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <shared_mutex>
+#include <span>
+#include <stdexcept>
+#include <thread>
+#include <vector>
+
+// ==========================================================================
+// executor/ExecutorTask.h
+// ==========================================================================
+namespace faabric::executor {
+
+class ExecutorTask
+{
+  public:
+    ExecutorTask() = default;
+
+    ExecutorTask(int messageIndexIn,
+                 std::shared_ptr<faabric::BatchExecuteRequest> reqIn)
+      : req(std::move(reqIn))
+      , messageIndex(messageIndexIn)
+    {}
+
+    // Shutdown sentinel for pool threads
+    static const int POOL_SHUTDOWN = -1;
+
+    std::shared_ptr<faabric::BatchExecuteRequest> req;
+    int messageIndex = 0;
+};
+
+}
+
+// ==========================================================================
+// executor/Executor.h
+// ==========================================================================
+// Executor: a warm container for one (user, function, app) that runs the
+// messages of a batch on a pool of threads.  Users subclass it and implement
+// executeTask (reference: include/faabric/executor/Executor.h:21-118,
+// src/executor/Executor.cpp:38-743).  Additions for GPUs: every executor is
+// bound to a GPU (device id + compute stream) and may expose a device memory
+// view that is snapshot / restored / diff-pushed with the device kernels.
+
+
+
+#define POOL_SHUTDOWN -1
+
+namespace faabric::executor {
+
+class ChainedCallException : public faabric::util::FaabricException
+{
+  public:
+    explicit ChainedCallException(std::string message)
+      : FaabricException(std::move(message))
+    {}
+};
+
+class Executor : public std::enable_shared_from_this<Executor>
+{
+  public:
+    std::string id;
+
+    explicit Executor(faabric::Message& msg);
+
+    virtual ~Executor();
+
+    // Must be called before the executor is destroyed
+    void shutdown();
+
+    std::vector<std::pair<uint32_t, int32_t>> executeThreads(
+      std::shared_ptr<faabric::BatchExecuteRequest> req,
+      const std::vector<faabric::util::SnapshotMergeRegion>& mergeRegions);
+
+    void executeTasks(std::vector<int> msgIdxs,
+                      std::shared_ptr<faabric::BatchExecuteRequest> req);
+
+    // ---- hooks for subclasses ----
+    virtual void reset(faabric::Message& msg);
+
+    virtual int32_t executeTask(
+      int threadPoolIdx,
+      int msgIdx,
+      std::shared_ptr<faabric::BatchExecuteRequest> req);
+
+    virtual std::span<uint8_t> getMemoryView();
+
+    virtual void restore(const std::string& snapshotKey);
+
+    virtual void setMemorySize(size_t newSize);
+
+    virtual size_t getMaxMemorySize();
+
+    // ---- GPU binding ----
+    // App this executor is currently working for (0 when idle)
+    int getCurrentAppId() const { return currentAppId.load(); }
+
+    int getGpuIdx() const { return gpuIdx; }
+
+    // Compute stream of this executor (cudaStream_t); nullptr without a GPU
+    void* getComputeStream() const { return computeStream; }
+
+    // ---- claiming ----
+    bool tryClaim();
+
+    void claim();
+
+    void releaseClaim();
+
+    bool isExecuting();
+
+    bool isShutdown() { return _isShutdown; }
+
+    long getMillisSinceLastExec();
+
+    std::shared_ptr<faabric::util::SnapshotData> getMainThreadSnapshot(
+      faabric::Message& msg,
+      bool createIfNotExists = false);
+
+    // ---- chained calls ----
+    void addChainedMessage(const faabric::Message& msg);
+
+    const faabric::Message& getChainedMessage(int messageId);
+
+    std::set<unsigned int> getChainedMessageIds();
+
+    std::vector<faabric::util::SnapshotDiff> mergeDirtyRegions(
+      const faabric::Message& msg,
+      const std::vector<char>& extraDirtyPages = {});
+
+    // Blocks until every pool thread finished (tests)
+    void joinThreadPool();
+
+  protected:
+    virtual void setUpThreadPool();
+
+    faabric::Message boundMessage;
+
+    faabric::snapshot::SnapshotRegistry& reg;
+
+    std::shared_ptr<faabric::util::DirtyTracker> tracker;
+
+    uint32_t threadPoolSize = 0;
+
+    std::map<int, std::shared_ptr<faabric::BatchExecuteRequest>> chainedMessages;
+
+  private:
+    std::atomic<bool> claimed = false;
+
+    std::atomic<bool> _isShutdown = false;
+
+    std::atomic<int> batchCounter = 0;
+    std::atomic<int> currentAppId = 0;
+
+    std::atomic<int> threadBatchCounter = 0;
+
+    faabric::util::TimePoint lastExec;
+
+    // ---- Application threads ----
+    std::shared_mutex threadExecutionMutex;
+    std::vector<char> dirtyRegions;
+    std::vector<std::vector<char>> threadLocalDirtyRegions;
+    void deleteMainThreadSnapshot(const faabric::Message& msg);
+
+    // ---- Function execution thread pool ----
+    std::mutex threadsMutex;
+    std::vector<std::shared_ptr<std::jthread>> threadPoolThreads;
+    std::set<int> availablePoolThreads;
+
+    std::vector<faabric::util::Queue<ExecutorTask>> threadTaskQueues;
+
+    std::mutex chainedMx;
+
+    int gpuIdx = -1;
+    void* computeStream = nullptr;
+
+    void threadPoolThread(std::stop_token st, int threadPoolIdx);
+};
+
+}
+
+// ==========================================================================
+// executor/ExecutorContext.h
+// ==========================================================================
+namespace faabric::executor {
+
+class Executor;
+
+class ExecutorContextException : public std::runtime_error
+{
+  public:
+    explicit ExecutorContextException(const std::string& message)
+      : std::runtime_error(message)
+    {}
+};
+
+// Thread-local handle on "what am I executing": set around executeTask so
+// library code (MPI shim, chaining, state) can find the current message
+class ExecutorContext
+{
+  public:
+    ExecutorContext(Executor* executorIn,
+                    std::shared_ptr<faabric::BatchExecuteRequest> reqIn,
+                    int msgIdx);
+
+    static bool isSet();
+
+    static void set(Executor* executorIn,
+                    std::shared_ptr<faabric::BatchExecuteRequest> reqIn,
+                    int msgIdxIn);
+
+    static void unset();
+
+    static std::shared_ptr<ExecutorContext> get();
+
+    Executor* getExecutor() { return executor; }
+
+    std::shared_ptr<faabric::BatchExecuteRequest> getBatchRequest()
+    {
+        return req;
+    }
+
+    faabric::Message& getMsg()
+    {
+        if (req == nullptr) {
+            throw ExecutorContextException("Getting message when no request set in context");
+        }
+        return *req->mutable_messages(msgIdx);
+    }
+
+    int getMsgIdx() const { return msgIdx; }
+
+  private:
+    Executor* executor = nullptr;
+    std::shared_ptr<faabric::BatchExecuteRequest> req = nullptr;
+    int msgIdx = 0;
+};
+
+}
+
+// ==========================================================================
+// executor/ExecutorFactory.h
+// ==========================================================================
+namespace faabric::executor {
+
+class ExecutorFactory
+{
+  public:
+    virtual ~ExecutorFactory() = default;
+
+    virtual std::shared_ptr<Executor> createExecutor(faabric::Message& msg) = 0;
+
+    virtual void flushHost();
+};
+
+void setExecutorFactory(std::shared_ptr<ExecutorFactory> fac);
+
+std::shared_ptr<ExecutorFactory> getExecutorFactory();
+
+}
+

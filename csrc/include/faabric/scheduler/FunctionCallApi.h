@@ -1,11 +1,4 @@
+// Forwarding header: the declarations live in faabric/scheduler/scheduler_module.h
 #pragma once
 
-namespace faabric::scheduler {
-enum FunctionCalls
-{
-    NoFunctionCall = 0,
-    ExecuteFunctions = 1,
-    Flush = 2,
-    SetMessageResult = 3,
-};
-}
+#include <faabric/scheduler/scheduler_module.h>

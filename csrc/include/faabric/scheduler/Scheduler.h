@@ -1,159 +1,4 @@
-// Per-worker scheduler: owns the executors of this host (GPU worker), runs the
-// batches the planner dispatches, tracks thread results and asks the planner
-// for migration opportunities.  Reference: include/faabric/scheduler/
-// Scheduler.h:34-140, src/scheduler/Scheduler.cpp:25-524.
+// Forwarding header: the declarations live in faabric/scheduler/scheduler_module.h
 #pragma once
 
-#include <faabric/batch-scheduler/SchedulingDecision.h>
-#include <faabric/planner/PlannerClient.h>
-#include <faabric/proto/faabric.pb.h>
-#include <faabric/snapshot/SnapshotClient.h>
-#include <faabric/snapshot/SnapshotRegistry.h>
-#include <faabric/transport/Message.h>
-#include <faabric/transport/PointToPointBroker.h>
-#include <faabric/util/PeriodicBackgroundThread.h>
-#include <faabric/util/clock.h>
-#include <faabric/util/config.h>
-#include <faabric/util/snapshot.h>
-
-#include <future>
-#include <set>
-#include <shared_mutex>
-#include <unordered_map>
-
-#define AVAILABLE_HOST_SET "available_hosts"
-
-namespace faabric::executor {
-class Executor;
-}
-
-namespace faabric::scheduler {
-
-class Scheduler;
-
-Scheduler& getScheduler();
-
-// Reaps executors that have been idle for longer than BOUND_TIMEOUT
-class SchedulerReaperThread : public faabric::util::PeriodicBackgroundThread
-{
-  public:
-    void doWork() override;
-};
-
-class Scheduler
-{
-  public:
-    Scheduler();
-
-    ~Scheduler();
-
-    void executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req);
-
-    void reset();
-
-    void resetThreadLocalCache();
-
-    void shutdown();
-
-    bool isShutdown() { return _isShutdown; }
-
-    long getFunctionExecutorCount(const faabric::Message& msg);
-
-    void flushLocally();
-
-    // ----------------------------------
-    // Message results (threads)
-    // ----------------------------------
-    void setThreadResultLocally(uint32_t appId,
-                                uint32_t msgId,
-                                int32_t returnValue,
-                                faabric::transport::Message& message);
-
-    // The last argument keeps diff payloads alive until the result is consumed
-    std::vector<std::pair<uint32_t, int32_t>> awaitThreadResults(
-      std::shared_ptr<faabric::BatchExecuteRequest> req,
-      int timeoutMs = DEFAULT_THREAD_RESULT_TIMEOUT_MS);
-
-    size_t getCachedMessageCount();
-
-    std::string getThisHost();
-
-    void addHostToGlobalSet();
-
-    void addHostToGlobalSet(
-      const std::string& host,
-      std::shared_ptr<faabric::HostResources> overwriteResources = nullptr);
-
-    void removeHostFromGlobalSet(const std::string& host);
-
-    void setThisHostResources(faabric::HostResources& res);
-
-    // ----------------------------------
-    // Testing
-    // ----------------------------------
-    std::vector<faabric::Message> getRecordedMessages();
-
-    void clearRecordedMessages();
-
-    // ----------------------------------
-    // Function Migration
-    // ----------------------------------
-    std::shared_ptr<faabric::PendingMigration> checkForMigrationOpportunities(
-      faabric::Message& msg,
-      int overwriteNewGroupId = 0);
-
-    // Idle-executor reaping, returns how many were reaped
-    int reapStaleExecutors();
-
-    // Called by an executor when it becomes claimable again
-    void notifyExecutorIdle(const std::string& funcKey, std::weak_ptr<faabric::executor::Executor> executor);
-
-    static const int DEFAULT_THREAD_RESULT_TIMEOUT_MS = 20000;
-
-  private:
-    std::string thisHost;
-
-    faabric::util::SystemConfig& conf;
-
-    std::shared_mutex mx;
-
-    std::atomic<bool> _isShutdown = false;
-
-    // ---- Executors ----
-    std::unordered_map<std::string,
-                       std::vector<std::shared_ptr<faabric::executor::Executor>>>
-      executors;
-
-    // ---- Threads ----
-    // Recently released executors per function (hints: entries may be stale)
-    std::mutex idleMx;
-    std::unordered_map<std::string, std::vector<std::weak_ptr<faabric::executor::Executor>>> idleExecutors;
-
-    faabric::snapshot::SnapshotRegistry& reg;
-
-    std::unordered_map<uint32_t, std::promise<int32_t>> threadResults;
-    std::unordered_map<uint32_t, std::shared_future<int32_t>> threadFutures;
-    std::unordered_map<uint32_t, faabric::transport::Message>
-      threadResultMessages;
-    std::mutex threadResultsMx;
-
-    // ---- Planner ----
-    faabric::planner::KeepAliveThread keepAliveThread;
-    bool keepAliveRunning = false;
-    std::set<std::string> servedHosts;
-
-    // ---- Actual scheduling ----
-    SchedulerReaperThread reaperThread;
-
-    std::shared_ptr<faabric::executor::Executor> claimExecutor(
-      faabric::Message& msg,
-      std::unique_lock<std::shared_mutex>& schedulerLock);
-
-    // ---- Point-to-point ----
-    faabric::transport::PointToPointBroker& broker;
-
-    // ---- Mock records ----
-    std::vector<faabric::Message> recordedMessages;
-};
-
-}
+#include <faabric/scheduler/scheduler_module.h>

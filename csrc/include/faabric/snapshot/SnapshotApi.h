@@ -1,12 +1,4 @@
+// Forwarding header: the declarations live in faabric/snapshot/snapshot_module.h
 #pragma once
 
-namespace faabric::snapshot {
-enum SnapshotCalls
-{
-    NoSnapshotCall = 0,
-    PushSnapshot = 1,
-    PushSnapshotUpdate = 2,
-    DeleteSnapshot = 3,
-    ThreadResult = 4,
-};
-}
+#include <faabric/snapshot/snapshot_module.h>

@@ -1,0 +1,275 @@
+// Snapshots: registry, RPCs and device-resident images.
+//
+// One header per module: the per-class headers of the reference's layout
+// (faabric/snapshot/*.h) forward here, so either include style works.
+#pragma once
+
+#include <faabric/device/comm_abi.h>
+#include <faabric/proto/faabric.pb.h>
+#include <faabric/transport/MessageEndpointClient.h>
+#include <faabric/transport/MessageEndpointServer.h>
+#include <faabric/util/memory.h>
+#include <faabric/util/snapshot.h>
+
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+// ==========================================================================
+// snapshot/DeviceSnapshot.h
+// ==========================================================================
+// A snapshot whose image lives in GPU memory (HBM).  The hot path of the
+// reference's fork-join threading — diff the executor memory against the
+// image, apply the merge regions and push to the main copy
+// (src/executor/Executor.cpp:684-730 + src/snapshot/SnapshotClient.cpp:76-171)
+// — is ONE kernel here (snapshotDiffPushKernel) that writes straight into the
+// main image, which may be peer-mapped memory of another GPU.
+
+
+
+namespace faabric::snapshot {
+
+struct DeviceDiffStats
+{
+    uint64_t diffBytes = 0;
+    uint64_t pagesWithDiffs = 0;
+};
+
+class DeviceSnapshot
+{
+  public:
+    // Allocates `size` bytes on `device` (zeroed)
+    DeviceSnapshot(size_t sizeIn, int deviceIn);
+
+    // Wraps memory owned elsewhere (e.g. a symmetric-heap allocation that is
+    // peer-mapped on the other GPUs)
+    DeviceSnapshot(uint8_t* devicePtr, size_t sizeIn, int deviceIn);
+
+    ~DeviceSnapshot();
+
+    size_t getSize() const { return size; }
+
+    int getDevice() const { return device; }
+
+    uint8_t* getDevicePtr() const { return image; }
+
+    // Host <-> device copies (synchronous)
+    void copyInData(std::span<const uint8_t> hostData, uint64_t offset = 0);
+
+    std::vector<uint8_t> getDataCopy(uint64_t offset, size_t n);
+
+    std::vector<uint8_t> getDataCopy() { return getDataCopy(0, size); }
+
+    // Restore: device-to-device copy of the image into executor memory
+    void restoreTo(uint8_t* deviceMem, size_t n, void* stream = nullptr);
+
+    // ---- merge regions (same semantics as SnapshotData) ----
+    void addMergeRegion(uint64_t offset,
+                        size_t length,
+                        faabric::util::SnapshotDataType dataType,
+                        faabric::util::SnapshotMergeOperation operation);
+
+    void clearMergeRegions();
+
+    std::vector<faabric::util::SnapshotMergeRegion> getMergeRegions();
+
+    // Fused diff + merge + push.  `mem` is the executor's (updated) memory on
+    // this snapshot's device, this snapshot is its base image; results land in
+    // `mainImage` (local or peer-mapped).  dirtyPagesDev: optional device
+    // uint8[nPages].  If updateBase, this image is advanced to `mem` too.
+    // Asynchronous on `stream`; stats are read back by getLastStats().
+    void diffAndPush(const uint8_t* mem,
+                     size_t memSize,
+                     uint8_t* mainImage,
+                     const uint8_t* dirtyPagesDev = nullptr,
+                     bool updateBase = false,
+                     void* stream = nullptr);
+
+    // Synchronises `stream` and returns the counters of the last diffAndPush
+    DeviceDiffStats getLastStats(void* stream = nullptr);
+
+    // Applies host-side diffs (e.g. received over the control plane)
+    void applyDiffs(const std::vector<faabric::util::SnapshotDiff>& diffs,
+                    void* stream = nullptr);
+
+    // GPU dirty-page detection of `mem` against this image
+    std::vector<char> getDirtyPages(const uint8_t* mem, size_t memSize);
+
+  private:
+    size_t size = 0;
+    int device = 0;
+    uint8_t* image = nullptr;
+    faabric::util::DeviceRegion owned;
+
+    std::mutex mx;
+    std::vector<faabric::util::SnapshotMergeRegion> mergeRegions;
+
+    // Uploaded, gap-filled regions (rebuilt lazily when regions change)
+    bool regionsDirty = true;
+    faabric::util::DeviceRegion regionsDev;
+    faabric::util::DeviceRegion typedIdxDev;
+    faabric::util::DeviceRegion statsDev;
+    int nRegionsDev = 0;
+    int nTypedDev = 0;
+
+    void uploadRegions();
+};
+
+}
+
+// ==========================================================================
+// snapshot/SnapshotApi.h
+// ==========================================================================
+namespace faabric::snapshot {
+enum SnapshotCalls
+{
+    NoSnapshotCall = 0,
+    PushSnapshot = 1,
+    PushSnapshotUpdate = 2,
+    DeleteSnapshot = 3,
+    ThreadResult = 4,
+};
+}
+
+// ==========================================================================
+// snapshot/SnapshotClient.h
+// ==========================================================================
+namespace faabric::snapshot {
+
+// -----------------------------------
+// Mocking (reference: src/snapshot/SnapshotClient.cpp:18-64)
+// -----------------------------------
+struct MockSnapshotUpdate
+{
+    std::vector<faabric::util::SnapshotDiff> diffs;
+    // diffs above are non-owning: the payloads are kept here
+    std::vector<std::vector<uint8_t>> diffData;
+    std::vector<faabric::util::SnapshotMergeRegion> mergeRegions;
+};
+
+std::vector<
+  std::pair<std::string, std::shared_ptr<faabric::util::SnapshotData>>>
+getSnapshotPushes();
+
+std::vector<std::pair<std::string, std::shared_ptr<MockSnapshotUpdate>>>
+getSnapshotDiffPushes();
+
+std::vector<std::pair<std::string, std::string>> getSnapshotDeletes();
+
+std::vector<std::pair<std::string, std::tuple<int, int, std::string, int>>>
+getThreadResults();
+
+void clearMockSnapshotRequests();
+
+// -----------------------------------
+// Client
+// -----------------------------------
+class SnapshotClient final : public faabric::transport::MessageEndpointClient
+{
+  public:
+    explicit SnapshotClient(const std::string& hostIn);
+
+    void pushSnapshot(const std::string& key,
+                      std::shared_ptr<faabric::util::SnapshotData> data);
+
+    void pushSnapshotUpdate(
+      std::string snapshotKey,
+      const std::shared_ptr<faabric::util::SnapshotData>& data,
+      const std::vector<faabric::util::SnapshotDiff>& diffs);
+
+    void deleteSnapshot(const std::string& key);
+
+    void pushThreadResult(uint32_t appId,
+                          uint32_t messageId,
+                          int returnValue,
+                          const std::string& key,
+                          const std::vector<faabric::util::SnapshotDiff>& diffs);
+};
+
+std::shared_ptr<SnapshotClient> getSnapshotClient(const std::string& host);
+
+void clearSnapshotClients();
+
+}
+
+// ==========================================================================
+// snapshot/SnapshotRegistry.h
+// ==========================================================================
+namespace faabric::snapshot {
+
+class DeviceSnapshot;
+
+// key -> snapshot (host images and device images live side by side)
+class SnapshotRegistry
+{
+  public:
+    SnapshotRegistry() = default;
+
+    std::shared_ptr<faabric::util::SnapshotData> getSnapshot(
+      const std::string& key);
+
+    bool snapshotExists(const std::string& key);
+
+    void registerSnapshot(const std::string& key,
+                          std::shared_ptr<faabric::util::SnapshotData> data);
+
+    void deleteSnapshot(const std::string& key);
+
+    size_t getSnapshotCount();
+
+    // ---- device-resident images ----
+    std::shared_ptr<DeviceSnapshot> getDeviceSnapshot(const std::string& key);
+
+    bool deviceSnapshotExists(const std::string& key);
+
+    void registerDeviceSnapshot(const std::string& key,
+                                std::shared_ptr<DeviceSnapshot> data);
+
+    void deleteDeviceSnapshot(const std::string& key);
+
+    void clear();
+
+  private:
+    std::shared_mutex snapshotsMx;
+    std::unordered_map<std::string, std::shared_ptr<faabric::util::SnapshotData>>
+      snapshotMap;
+    std::unordered_map<std::string, std::shared_ptr<DeviceSnapshot>> deviceMap;
+};
+
+SnapshotRegistry& getSnapshotRegistry();
+
+}
+
+// ==========================================================================
+// snapshot/SnapshotServer.h
+// ==========================================================================
+namespace faabric::snapshot {
+
+class SnapshotServer final : public faabric::transport::MessageEndpointServer
+{
+  public:
+    SnapshotServer();
+
+  protected:
+    void doAsyncRecv(transport::Message& message) override;
+
+    std::string doSyncRecv(transport::Message& message) override;
+
+    std::string recvPushSnapshot(std::span<const uint8_t> buffer);
+
+    std::string recvPushSnapshotUpdate(std::span<const uint8_t> buffer);
+
+    std::string recvThreadResult(transport::Message& message);
+
+    void recvDeleteSnapshot(std::span<const uint8_t> buffer);
+
+  private:
+    faabric::snapshot::SnapshotRegistry& reg;
+};
+
+}
+

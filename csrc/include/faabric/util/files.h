@@ -1,17 +1,4 @@
+// Forwarding header: the declarations live in faabric/util/util_module.h
 #pragma once
 
-#include <cstdint>
-#include <string>
-#include <vector>
-
-namespace faabric::util {
-
-std::string readFileToString(const std::string& path);
-
-std::vector<uint8_t> readFileToBytes(const std::string& path);
-
-void writeBytesToFile(const std::string& path, const std::vector<uint8_t>& data);
-
-bool isWasm(const std::vector<uint8_t>& bytes);
-
-}
+#include <faabric/util/util_module.h>

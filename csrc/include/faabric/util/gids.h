@@ -1,9 +1,4 @@
+// Forwarding header: the declarations live in faabric/util/util_module.h
 #pragma once
 
-namespace faabric::util {
-
-// Globally unique-ish ids: a per-process random base mixed with host identity
-// plus an atomic counter (reference: src/util/gids.cpp:16-35)
-unsigned int generateGid();
-
-}
+#include <faabric/util/util_module.h>

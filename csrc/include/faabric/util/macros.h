@@ -1,8 +1,4 @@
+// Forwarding header: the declarations live in faabric/util/util_module.h
 #pragma once
 
-#define BYTES(arr) reinterpret_cast<uint8_t*>(arr)
-#define BYTES_CONST(arr) reinterpret_cast<const uint8_t*>(arr)
-#define UNUSED(x) (void)(x)
-
-// Symbol visibility helper for the few things looked up by dlsym / ctypes
-#define FAABRIC_EXPORT __attribute__((visibility("default")))
+#include <faabric/util/util_module.h>

@@ -1,13 +1,4 @@
+// Forwarding header: the declarations live in faabric/util/util_module.h
 #pragma once
 
-#include <string>
-
-namespace faabric::util {
-
-std::string randomString(int len);
-
-std::string randomStringFromSet(int len, const std::string& charSet);
-
-int randomInteger(int iStart, int iEnd);
-
-}
+#include <faabric/util/util_module.h>

@@ -1,9 +1,12 @@
+// Worker bootstrap: bind the GPU, make sure the planner answers, register this
+// host, then bring the four servers up (and down again in reverse order).
+// Counterpart of the reference's src/runner/FaabricMain.cpp:11-109.
 #include <faabric/planner/PlannerClient.h>
 #include <faabric/runner/FaabricMain.h>
-#include <faabric/util/crash.h>
-#include <faabric/util/hwloc.h>
 #include <faabric/state/InMemoryStateRegistry.h>
 #include <faabric/state/State.h>
+#include <faabric/util/crash.h>
+#include <faabric/util/hwloc.h>
 #include <faabric/util/logging.h>
 #include <faabric/util/timing.h>
 
@@ -17,20 +20,19 @@ FaabricMain::FaabricMain(std::shared_ptr<faabric::executor::ExecutorFactory> exe
     faabric::executor::setExecutorFactory(std::move(execFactory));
 }
 
-// Bind the worker to its GPU before any server can hand out device work.
-// Not having a GPU is fine: the runtime then runs its host paths only.
-static void bindDevice()
+// A worker without a visible GPU is fine: it then runs its host paths only.
+static void bindDefaultDevice()
 {
-    const auto& conf = faabric::util::getSystemConfig();
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
         cudaGetLastError();
         SPDLOG_INFO("No CUDA device visible, running host-only");
         return;
     }
-    // FAABRIC_GPUS is a comma-separated list; a worker owns the first entry
-    // for its default context (MPI ranks pick theirs from the decision)
-    int dev = conf.gpus.empty() ? 0 : std::atoi(conf.gpus.c_str());
+    // FAABRIC_GPUS is a comma-separated list; the first entry hosts the
+    // worker's default context (MPI ranks pick theirs from the decision)
+    const std::string& list = faabric::util::getSystemConfig().gpus;
+    int dev = list.empty() ? 0 : std::atoi(list.c_str());
     if (dev < 0 || dev >= count) {
         SPDLOG_WARN("GPU {} out of range ({} devices), using 0", dev, count);
         dev = 0;
@@ -51,42 +53,38 @@ static void bindDevice()
 
 void FaabricMain::startBackground()
 {
-    // Crash handler
     faabric::util::setUpCrashHandler();
-
     PROF_BEGIN
-
-    bindDevice();
-
-    // Start basics
+    bindDefaultDevice();
     startRunner();
-
-    // In-memory state, snapshots and point-to-point messaging
+    // State, snapshots and point-to-point messaging must answer before this
+    // host starts taking work
     startStateServer();
     startSnapshotServer();
     startPointToPointServer();
-
-    // Work sharing
     startFunctionCallServer();
-
     PROF_SUMMARY
 }
 
 void FaabricMain::startRunner()
 {
-    // Ensure we can ping the planner, then make this host available
     faabric::planner::getPlannerClient().ping();
     // The planner answers: let it arbitrate state mains so that every worker
     // process agrees on them
     faabric::state::getInMemoryStateRegistry().setShared(true);
-    auto& sch = faabric::scheduler::getScheduler();
-    sch.addHostToGlobalSet();
+    faabric::scheduler::getScheduler().addHostToGlobalSet();
 }
 
-void FaabricMain::startFunctionCallServer()
+void FaabricMain::startStateServer()
 {
-    SPDLOG_INFO("Starting function call server");
-    functionServer.start();
+    const std::string& mode = faabric::util::getSystemConfig().stateMode;
+    if (mode != "inmemory") {
+        // Values live in the external store: nothing to serve
+        SPDLOG_INFO("Not starting state server in state mode {}", mode);
+        return;
+    }
+    SPDLOG_INFO("Starting state server");
+    stateServer.start();
 }
 
 void FaabricMain::startSnapshotServer()
@@ -101,38 +99,25 @@ void FaabricMain::startPointToPointServer()
     pointToPointServer.start();
 }
 
-void FaabricMain::startStateServer()
+void FaabricMain::startFunctionCallServer()
 {
-    // Skip state server if not in in-memory mode
-    const auto& conf = faabric::util::getSystemConfig();
-    if (conf.stateMode != "inmemory") {
-        SPDLOG_INFO("Not starting state server in state mode {}", conf.stateMode);
-        return;
-    }
-    SPDLOG_INFO("Starting state server");
-    stateServer.start();
+    SPDLOG_INFO("Starting function call server");
+    functionServer.start();
 }
 
 void FaabricMain::shutdown()
 {
     faabric::state::getInMemoryStateRegistry().setShared(false);
-    SPDLOG_INFO("Removing from global working set");
-    auto& sch = faabric::scheduler::getScheduler();
-    sch.shutdown();
+    SPDLOG_INFO("Leaving the planner's host set");
+    faabric::scheduler::getScheduler().shutdown();
 
-    SPDLOG_INFO("Waiting for the state server to finish");
-    stateServer.stop();
-
-    SPDLOG_INFO("Waiting for the function server to finish");
+    // Stop taking work first, the services it depends on last
+    SPDLOG_INFO("Stopping servers");
     functionServer.stop();
-
-    SPDLOG_INFO("Waiting for the snapshot server to finish");
-    snapshotServer.stop();
-
-    SPDLOG_INFO("Waiting for the point-to-point server to finish");
     pointToPointServer.stop();
-
-    SPDLOG_INFO("Faabric pool successfully shut down");
+    snapshotServer.stop();
+    stateServer.stop();
+    SPDLOG_INFO("Worker shut down");
 }
 
 }

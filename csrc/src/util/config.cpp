@@ -1,11 +1,73 @@
+// Environment-driven configuration.  One table describes every knob (env name,
+// default, section, field); initialise() and print() both walk it, so a new
+// setting is one line.  Names and defaults of the non-GPU knobs are those of
+// the reference (src/util/config.cpp:19-84) so deployments carry over.
 #include <faabric/util/config.h>
 #include <faabric/util/environment.h>
 #include <faabric/util/logging.h>
 #include <faabric/util/network.h>
 
 #include <cstdlib>
+#include <string>
+#include <variant>
+#include <vector>
 
 namespace faabric::util {
+
+namespace {
+using Field = std::variant<std::string SystemConfig::*, int SystemConfig::*, long SystemConfig::*>;
+
+struct Knob
+{
+    const char* section;
+    const char* env;
+    const char* fallback;
+    Field field;
+};
+
+const std::vector<Knob>& knobs()
+{
+    using C = SystemConfig;
+    static const std::vector<Knob> table = {
+        { "System", "SERIALISATION", "json", &C::serialisation },
+        { "System", "LOG_LEVEL", "info", &C::logLevel },
+        { "System", "LOG_FILE", "off", &C::logFile },
+        { "System", "STATE_MODE", "inmemory", &C::stateMode },
+        { "System", "DELTA_SNAPSHOT_ENCODING", "pages=4096;xor;zstd=1", &C::deltaSnapshotEncoding },
+        { "Store", "REDIS_STATE_HOST", "localhost", &C::redisStateHost },
+        { "Store", "REDIS_QUEUE_HOST", "localhost", &C::redisQueueHost },
+        { "Store", "REDIS_PORT", "6379", &C::redisPort },
+        { "Scheduling", "OVERRIDE_CPU_COUNT", "0", &C::overrideCpuCount },
+        { "Scheduling", "OVERRIDE_FREE_CPU_START", "0", &C::overrideFreeCpuStart },
+        { "Scheduling", "BATCH_SCHEDULER_MODE", "bin-pack", &C::batchSchedulerMode },
+        { "Timeouts", "GLOBAL_MESSAGE_TIMEOUT", "60000", &C::globalMessageTimeout },
+        { "Timeouts", "BOUND_TIMEOUT", "30000", &C::boundTimeout },
+        { "Timeouts", "REAPER_INTERVAL_SECS", "30", &C::reaperIntervalSeconds },
+        { "MPI", "DEFAULT_MPI_WORLD_SIZE", "5", &C::defaultMpiWorldSize },
+        { "Endpoint", "ENDPOINT_INTERFACE", "", &C::endpointInterface },
+        { "Endpoint", "ENDPOINT_HOST", "", &C::endpointHost },
+        { "Endpoint", "ENDPOINT_PORT", "8080", &C::endpointPort },
+        { "Endpoint", "ENDPOINT_NUM_THREADS", "4", &C::endpointNumThreads },
+        { "Transport", "FUNCTION_SERVER_THREADS", "2", &C::functionServerThreads },
+        { "Transport", "STATE_SERVER_THREADS", "2", &C::stateServerThreads },
+        { "Transport", "SNAPSHOT_SERVER_THREADS", "2", &C::snapshotServerThreads },
+        { "Transport", "POINT_TO_POINT_SERVER_THREADS", "8", &C::pointToPointServerThreads },
+        { "Dirty tracking", "DIRTY_TRACKING_MODE", "segfault", &C::dirtyTrackingMode },
+        { "Dirty tracking", "DIFFING_MODE", "xor", &C::diffingMode },
+        { "Planner", "PLANNER_HOST", "planner", &C::plannerHost },
+        { "Planner", "PLANNER_PORT", "8080", &C::plannerPort },
+        { "B200", "FAABRIC_GPUS", "", &C::gpus },
+        { "B200", "FAABRIC_DEVICE_BACKEND", "cuda", &C::deviceBackend },
+        { "B200", "FAABRIC_ALLREDUCE_ALGO", "auto", &C::allreduceAlgo },
+        { "B200", "FAABRIC_USE_NVLS", "1", &C::useNvls },
+        { "B200", "FAABRIC_COMM_STREAMS", "2", &C::commStreams },
+        { "B200", "FAABRIC_SYMM_HEAP_BYTES", "1073741824", &C::symmHeapBytes },
+        { "B200", "FAABRIC_SLOTS_PER_GPU", "8", &C::slotsPerGpu },
+        { "B200", "FAABRIC_PORT_OFFSET", "0", &C::portOffset },
+    };
+    return table;
+}
+}
 
 SystemConfig& getSystemConfig()
 {
@@ -15,138 +77,59 @@ SystemConfig& getSystemConfig()
 
 SystemConfig::SystemConfig()
 {
-    this->initialise();
+    initialise();
+}
+
+int SystemConfig::getSystemConfIntParam(const char* name, const char* defaultValue)
+{
+    return (int)getSystemConfLongParam(name, defaultValue);
+}
+
+long SystemConfig::getSystemConfLongParam(const char* name, const char* defaultValue)
+{
+    return std::strtol(getEnvVar(name, defaultValue).c_str(), nullptr, 10);
 }
 
 void SystemConfig::initialise()
 {
-    // System
-    serialisation = getEnvVar("SERIALISATION", "json");
-    logLevel = getEnvVar("LOG_LEVEL", "info");
-    logFile = getEnvVar("LOG_FILE", "off");
-    stateMode = getEnvVar("STATE_MODE", "inmemory");
-    deltaSnapshotEncoding =
-      getEnvVar("DELTA_SNAPSHOT_ENCODING", "pages=4096;xor;zstd=1");
-
-    // Redis-compatible store
-    redisStateHost = getEnvVar("REDIS_STATE_HOST", "localhost");
-    redisQueueHost = getEnvVar("REDIS_QUEUE_HOST", "localhost");
-    redisPort = getEnvVar("REDIS_PORT", "6379");
-
-    // Scheduling
-    overrideCpuCount = getSystemConfIntParam("OVERRIDE_CPU_COUNT", "0");
-    overrideFreeCpuStart = getSystemConfIntParam("OVERRIDE_FREE_CPU_START", "0");
-    batchSchedulerMode = getEnvVar("BATCH_SCHEDULER_MODE", "bin-pack");
-
-    // Worker-related timeouts (all in ms)
-    globalMessageTimeout =
-      getSystemConfIntParam("GLOBAL_MESSAGE_TIMEOUT", "60000");
-    boundTimeout = getSystemConfIntParam("BOUND_TIMEOUT", "30000");
-    reaperIntervalSeconds = getSystemConfIntParam("REAPER_INTERVAL_SECS", "30");
-
-    // MPI
-    defaultMpiWorldSize = getSystemConfIntParam("DEFAULT_MPI_WORLD_SIZE", "5");
-
-    // Endpoint
-    endpointInterface = getEnvVar("ENDPOINT_INTERFACE", "");
-    endpointHost = getEnvVar("ENDPOINT_HOST", "");
-    endpointPort = getSystemConfIntParam("ENDPOINT_PORT", "8080");
-    endpointNumThreads = getSystemConfIntParam("ENDPOINT_NUM_THREADS", "4");
+    for (const Knob& k : knobs()) {
+        if (auto* s = std::get_if<std::string SystemConfig::*>(&k.field)) {
+            this->**s = getEnvVar(k.env, k.fallback);
+        } else if (auto* i = std::get_if<int SystemConfig::*>(&k.field)) {
+            this->**i = getSystemConfIntParam(k.env, k.fallback);
+        } else {
+            this->*std::get<long SystemConfig::*>(k.field) = getSystemConfLongParam(k.env, k.fallback);
+        }
+    }
     if (endpointHost.empty()) {
-        // Default to the primary IP of this machine
+        // Nothing configured: the primary address of the chosen interface
         endpointHost = getPrimaryIPForThisHost(endpointInterface);
     }
-
-    // Transport
-    functionServerThreads = getSystemConfIntParam("FUNCTION_SERVER_THREADS", "2");
-    stateServerThreads = getSystemConfIntParam("STATE_SERVER_THREADS", "2");
-    snapshotServerThreads = getSystemConfIntParam("SNAPSHOT_SERVER_THREADS", "2");
-    pointToPointServerThreads =
-      getSystemConfIntParam("POINT_TO_POINT_SERVER_THREADS", "8");
-
-    // Dirty tracking
-    dirtyTrackingMode = getEnvVar("DIRTY_TRACKING_MODE", "segfault");
-    diffingMode = getEnvVar("DIFFING_MODE", "xor");
-
-    // Planner
-    plannerHost = getEnvVar("PLANNER_HOST", "planner");
-    plannerPort = getSystemConfIntParam("PLANNER_PORT", "8080");
-
-    // B200
-    gpus = getEnvVar("FAABRIC_GPUS", "");
-    deviceBackend = getEnvVar("FAABRIC_DEVICE_BACKEND", "cuda");
-    allreduceAlgo = getEnvVar("FAABRIC_ALLREDUCE_ALGO", "auto");
-    useNvls = getSystemConfIntParam("FAABRIC_USE_NVLS", "1");
-    commStreams = getSystemConfIntParam("FAABRIC_COMM_STREAMS", "2");
-    symmHeapBytes = getSystemConfLongParam("FAABRIC_SYMM_HEAP_BYTES", "1073741824");
-    slotsPerGpu = getSystemConfIntParam("FAABRIC_SLOTS_PER_GPU", "8");
-    portOffset = getSystemConfIntParam("FAABRIC_PORT_OFFSET", "0");
-}
-
-int SystemConfig::getSystemConfIntParam(const char* name,
-                                        const char* defaultValue)
-{
-    return (int)strtol(getEnvVar(name, defaultValue).c_str(), nullptr, 10);
-}
-
-long SystemConfig::getSystemConfLongParam(const char* name,
-                                          const char* defaultValue)
-{
-    return strtol(getEnvVar(name, defaultValue).c_str(), nullptr, 10);
 }
 
 void SystemConfig::reset()
 {
-    this->initialise();
+    initialise();
 }
 
 void SystemConfig::print()
 {
-    SPDLOG_INFO("--- System ---");
-    SPDLOG_INFO("SERIALISATION              {}", serialisation);
-    SPDLOG_INFO("LOG_LEVEL                  {}", logLevel);
-    SPDLOG_INFO("LOG_FILE                   {}", logFile);
-    SPDLOG_INFO("STATE_MODE                 {}", stateMode);
-    SPDLOG_INFO("DELTA_SNAPSHOT_ENCODING    {}", deltaSnapshotEncoding);
-    SPDLOG_INFO("--- Store ---");
-    SPDLOG_INFO("REDIS_STATE_HOST           {}", redisStateHost);
-    SPDLOG_INFO("REDIS_QUEUE_HOST           {}", redisQueueHost);
-    SPDLOG_INFO("REDIS_PORT                 {}", redisPort);
-    SPDLOG_INFO("--- Scheduling ---");
-    SPDLOG_INFO("OVERRIDE_CPU_COUNT         {}", overrideCpuCount);
-    SPDLOG_INFO("OVERRIDE_FREE_CPU_START    {}", overrideFreeCpuStart);
-    SPDLOG_INFO("BATCH_SCHEDULER_MODE       {}", batchSchedulerMode);
-    SPDLOG_INFO("--- Timeouts ---");
-    SPDLOG_INFO("GLOBAL_MESSAGE_TIMEOUT     {}", globalMessageTimeout);
-    SPDLOG_INFO("BOUND_TIMEOUT              {}", boundTimeout);
-    SPDLOG_INFO("REAPER_INTERVAL_SECS       {}", reaperIntervalSeconds);
-    SPDLOG_INFO("--- MPI ---");
-    SPDLOG_INFO("DEFAULT_MPI_WORLD_SIZE     {}", defaultMpiWorldSize);
-    SPDLOG_INFO("--- Endpoint ---");
-    SPDLOG_INFO("ENDPOINT_INTERFACE         {}", endpointInterface);
-    SPDLOG_INFO("ENDPOINT_HOST              {}", endpointHost);
-    SPDLOG_INFO("ENDPOINT_PORT              {}", endpointPort);
-    SPDLOG_INFO("ENDPOINT_NUM_THREADS       {}", endpointNumThreads);
-    SPDLOG_INFO("--- Transport ---");
-    SPDLOG_INFO("FUNCTION_SERVER_THREADS    {}", functionServerThreads);
-    SPDLOG_INFO("STATE_SERVER_THREADS       {}", stateServerThreads);
-    SPDLOG_INFO("SNAPSHOT_SERVER_THREADS    {}", snapshotServerThreads);
-    SPDLOG_INFO("POINT_TO_POINT_SERVER_THREADS {}", pointToPointServerThreads);
-    SPDLOG_INFO("--- Dirty tracking ---");
-    SPDLOG_INFO("DIRTY_TRACKING_MODE        {}", dirtyTrackingMode);
-    SPDLOG_INFO("DIFFING_MODE               {}", diffingMode);
-    SPDLOG_INFO("--- Planner ---");
-    SPDLOG_INFO("PLANNER_HOST               {}", plannerHost);
-    SPDLOG_INFO("PLANNER_PORT               {}", plannerPort);
-    SPDLOG_INFO("--- B200 ---");
-    SPDLOG_INFO("FAABRIC_GPUS               {}", gpus);
-    SPDLOG_INFO("FAABRIC_DEVICE_BACKEND     {}", deviceBackend);
-    SPDLOG_INFO("FAABRIC_ALLREDUCE_ALGO     {}", allreduceAlgo);
-    SPDLOG_INFO("FAABRIC_USE_NVLS           {}", useNvls);
-    SPDLOG_INFO("FAABRIC_COMM_STREAMS       {}", commStreams);
-    SPDLOG_INFO("FAABRIC_SYMM_HEAP_BYTES    {}", symmHeapBytes);
-    SPDLOG_INFO("FAABRIC_SLOTS_PER_GPU      {}", slotsPerGpu);
-    SPDLOG_INFO("FAABRIC_PORT_OFFSET        {}", portOffset);
+    const char* section = "";
+    for (const Knob& k : knobs()) {
+        if (std::string(section) != k.section) {
+            section = k.section;
+            SPDLOG_INFO("--- {} ---", section);
+        }
+        std::string name(k.env);
+        name.resize(std::max<size_t>(name.size() + 1, 30), ' ');
+        if (auto* s = std::get_if<std::string SystemConfig::*>(&k.field)) {
+            SPDLOG_INFO("{}{}", name, this->**s);
+        } else if (auto* i = std::get_if<int SystemConfig::*>(&k.field)) {
+            SPDLOG_INFO("{}{}", name, this->**i);
+        } else {
+            SPDLOG_INFO("{}{}", name, this->*std::get<long SystemConfig::*>(k.field));
+        }
+    }
 }
 
 } // namespace faabric::util
