@@ -396,6 +396,8 @@ class MpiWorld
     std::vector<std::shared_ptr<faabric::device::Communicator>> deviceComms;
     std::vector<void*> deviceStreams; // cudaStream_t per rank
     std::atomic<uint64_t> deviceCollectives = 0;
+    // Channel streams MPI_Iallreduce may rotate over (see ensureDeviceComms)
+    std::atomic<int> nonBlockingChannels = 1;
     void ensureDeviceComms();
 
     // Eager device sends park their payload in the SENDER's symmetric heap;

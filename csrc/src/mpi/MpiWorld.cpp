@@ -911,6 +911,18 @@ void MpiWorld::ensureDeviceComms()
                 devices[r] = fromHost >= 0 ? fromHost % std::max(1, faabric::device::cudaDeviceCountSafe())
                                            : faabric::util::gpuForRank(r);
             }
+            // Ranks that share a GPU also share its hardware work queues
+            // (8 by default): keep (ranks on a device) x (channel streams)
+            // within that, or kernels of different ranks can queue up behind
+            // each other in a cycle while each waits for its peer
+            std::map<int, int> ranksOnDevice;
+            int maxShare = 1;
+            for (int d : devices) {
+                maxShare = std::max(maxShare, ++ranksOnDevice[d]);
+            }
+            // (half the queues, to leave room for streams created elsewhere)
+            nonBlockingChannels =
+              maxShare == 1 ? std::max(1, cfg.channels) : std::clamp(4 / maxShare, 1, std::max(1, cfg.channels));
             deviceComms = faabric::device::Communicator::createLocal(size, devices, cfg);
             SPDLOG_INFO("MPI world {}: device communicators up ({} ranks, backing {})", id, size, deviceComms[0]->backing());
             // Same allocation on every rank => same offset in every heap
@@ -926,6 +938,7 @@ void MpiWorld::ensureDeviceComms()
         } else if (allDistinctHosts && tls.rank >= 0) {
             // One rank per worker process: wire peer memory across processes
             deviceComms.assign(size, nullptr);
+            nonBlockingChannels = std::max(1, cfg.channels);
             deviceComms[tls.rank] = faabric::device::Communicator::createIpc(
               tls.rank, size, faabric::util::gpuForRank(tls.rank), "mpiworld-" + std::to_string(id), cfg);
         }
@@ -1067,7 +1080,7 @@ int MpiWorld::iAllReduce(int rank, uint8_t* send, uint8_t* recv, faabric_datatyp
         // Symmetric buffers may use any channel; others go through the single
         // staging area on channel 0
         const bool symmetric = comm->inHeap(send, bytes) && comm->inHeap(recv, bytes);
-        int nChannels = std::max(1, comm->config().channels);
+        int nChannels = std::clamp(nonBlockingChannels.load(), 1, std::max(1, comm->config().channels));
         int channel = symmetric ? (int)(tls.deviceCollectiveSeq++ % (uint64_t)nChannels) : 0;
         cudaStream_t s = (cudaStream_t)streamForRank(rank, channel);
         cudaSetDevice(comm->device());
