@@ -56,13 +56,15 @@ void FaabricMain::startBackground()
     faabric::util::setUpCrashHandler();
     PROF_BEGIN
     bindDefaultDevice();
-    startRunner();
-    // State, snapshots and point-to-point messaging must answer before this
-    // host starts taking work
+    // Fail fast if there is no planner to talk to
+    faabric::planner::getPlannerClient().ping();
+    // Everything must answer BEFORE the planner learns about this host: it
+    // may dispatch work the instant the registration lands
     startStateServer();
     startSnapshotServer();
     startPointToPointServer();
     startFunctionCallServer();
+    startRunner();
     PROF_SUMMARY
 }
 
