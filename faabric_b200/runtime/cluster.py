@@ -51,7 +51,9 @@ class LocalCluster:
         # ephemeral port range (highest port = 8100 + offset + 100 * workers)
         global _instances
         if base_offset is None:
-            base_offset = 1000 + (os.getpid() % 12) * 3000 + (_instances % 5) * 600
+            # (everything stays below 32768, the start of the ephemeral range:
+            # a listening port there can collide with an outgoing connection)
+            base_offset = 1000 + (os.getpid() % 7) * 3000 + (_instances % 5) * 600
         _instances += 1
         self.base_offset = base_offset
         self.procs: list[subprocess.Popen] = []
