@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-device", "mpi-symmetric", "mpi-symmetric-nb"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-host", "mpi-device", "mpi-symmetric", "mpi-symmetric-nb"])
     ap.add_argument("--mode", default="allreduce",
                     choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "pingpong"])
     ap.add_argument("--algo", default="tuned",
@@ -83,8 +83,12 @@ def refcpu_arm(args):
     sizes = resnet50_grad_sizes() if args.payload == "large" else small_sizes()
     n = max(args.gpus, 2)
     device = args.impl.startswith("mpi-")
+    # refcpu = the reference's host algorithm; mpi-host = this repo's host path
+    # (shared-memory slice-parallel all-reduce); mpi-{device,symmetric*} = HBM
+    memory = args.impl[4:] if device else "host"
     res = mpi_allreduce_bench(sizes, n, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)),
-                              memory=args.impl[4:] if device else "host")
+                              memory=memory, host_algo="reference" if args.impl == "refcpu" else "shared")
+    device = device and memory != "host"
     S = sum(sizes) * 4
     print(json.dumps({
         "metric": "mpi_allreduce_resnet50_grads_algbw_GBps",

@@ -400,6 +400,29 @@ class MpiWorld
     std::atomic<int> nonBlockingChannels = 1;
     void ensureDeviceComms();
 
+    // Host buffers, all ranks in this process: the ranks reduce straight out
+    // of each other's buffers (slice-parallel reduce-scatter + all-gather in
+    // shared memory, three barriers) instead of funnelling malloc'ed copies
+    // through rank 0.  FAABRIC_MPI_HOST_ALLREDUCE=reference keeps the
+    // reference's reduce + broadcast (used as the `refcpu` baseline).
+    struct HostCollective
+    {
+        int nRanks = 0;
+        std::atomic<int> arrived{ 0 };
+        std::atomic<uint64_t> generation{ 0 };
+        std::vector<const uint8_t*> sendPtrs;
+        std::vector<uint8_t*> recvPtrs;
+
+        void barrier(int timeoutMs);
+    };
+    std::unique_ptr<HostCollective> hostCollective;
+    bool trySharedMemoryAllReduce(int rank,
+                                  uint8_t* sendBuffer,
+                                  uint8_t* recvBuffer,
+                                  faabric_datatype_t* datatype,
+                                  int count,
+                                  faabric_op_t* operation);
+
     // Eager device sends park their payload in the SENDER's symmetric heap;
     // the receiver pulls it over NVLink through its mapping of that heap and
     // hands the block back.  One arena per rank, carved out at wiring time.

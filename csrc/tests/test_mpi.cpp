@@ -306,6 +306,53 @@ int bodyPingPongAndAllreduce(int rank, int size)
 }
 }
 
+namespace {
+// Large host all-reduces go through the shared-memory slice-parallel path
+int bodyLargeHostAllreduce(int rank, int size)
+{
+    // count not divisible by the world size, several types / ops, in place
+    const int n = 100003;
+    std::vector<double> d(n), dOut(n, 0);
+    for (int i = 0; i < n; i++) {
+        d[i] = (double)(i % 97) + rank;
+    }
+    MPI_Allreduce(d.data(), dOut.data(), n, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+    for (int i : { 0, 1, n / 2, n - 2, n - 1 }) {
+        CHECK_RANK(dOut[i] == (double)(i % 97) * size + size * (size - 1) / 2.0);
+    }
+    std::vector<float> f(n, (float)rank);
+    f[n - 1] = (float)(100 - rank);
+    MPI_Allreduce(MPI_IN_PLACE, f.data(), n, MPI_FLOAT, MPI_MAX, MPI_COMM_WORLD);
+    CHECK_RANK(f[0] == (float)(size - 1) && f[n - 1] == 100.0f);
+    std::vector<long long> l(n, rank + 1), lOut(n, 0);
+    MPI_Allreduce(l.data(), lOut.data(), n, MPI_LONG_LONG, MPI_MIN, MPI_COMM_WORLD);
+    CHECK_RANK(lOut[12345] == 1);
+    std::vector<int> v(40000, 1), vOut(40000, 0);
+    for (int round = 0; round < 5; round++) {
+        MPI_Allreduce(v.data(), vOut.data(), 40000, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+        CHECK_RANK(vOut[39999] == size);
+        v.swap(vOut);
+        std::fill(v.begin(), v.end(), 1);
+    }
+    // fewer elements than ranks per slice boundary cases
+    std::vector<int> tiny(8200, rank), tinyOut(8200, -1);
+    MPI_Allreduce(tiny.data(), tinyOut.data(), 8200, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+    CHECK_RANK(tinyOut[8199] == size * (size - 1) / 2);
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+}
+
+TEST_CASE("mpi: large host all-reduces use the shared-memory path", "[mpi]")
+{
+    runMpi("large-host-allreduce", 5, 1, bodyLargeHostAllreduce);
+    runMpi("large-host-allreduce-gpuhosts", 6, 3, bodyLargeHostAllreduce);
+    // ...and agree with the reference algorithm
+    setenv("FAABRIC_MPI_HOST_ALLREDUCE", "reference", 1);
+    runMpi("large-host-allreduce-ref", 3, 1, bodyLargeHostAllreduce);
+    unsetenv("FAABRIC_MPI_HOST_ALLREDUCE");
+}
+
 TEST_CASE("mpi: point-to-point on one host", "[mpi]")
 {
     runMpi("p2p-local", 4, 1, bodyPointToPoint);

@@ -50,14 +50,24 @@ def cpu_pingpong_bench(sizes=(8, 1024, 65536), n_workers: int = 1) -> list[dict]
     return out
 
 
-def mpi_allreduce_bench(counts: list[int], world_size: int, steps: int = 3, warmup: int = 1, memory: str = "host") -> dict:
+def mpi_allreduce_bench(
+    counts: list[int],
+    world_size: int,
+    steps: int = 3,
+    warmup: int = 1,
+    memory: str = "host",
+    host_algo: str = "shared",
+) -> dict:
     """The headline workload (one MPI_Allreduce per gradient tensor) through
     the MPI C API of a worker process.  memory="host": reduce-to-root +
     broadcast over in-memory queues, malloc+memcpy per hop - the design the
     reference ships.  memory="device": buffers in HBM, each call one fused
     P2P/NVLS kernel (needs GPUs)."""
     payload = f"{steps};{warmup};{memory};" + ",".join(str(int(c)) for c in counts)
-    with LocalCluster(n_workers=1, slots_per_worker=world_size, log_level="warn") as c:
+    # host_algo="reference": reduce to rank 0 + broadcast of malloc'ed copies
+    # (what the reference does); "shared": slice-parallel in shared memory
+    env = {"FAABRIC_MPI_HOST_ALLREDUCE": host_algo}
+    with LocalCluster(n_workers=1, slots_per_worker=world_size, log_level="warn", extra_env=env) as c:
         st = c.client.invoke("mpi", "bench-allreduce-list", mpi_world_size=world_size, input_data=payload, timeout=1800)
         bad = [m for m in st["messageResults"] if m.get("returnValue", 0) != 0]
         if bad:
@@ -66,4 +76,5 @@ def mpi_allreduce_bench(counts: list[int], world_size: int, steps: int = 3, warm
 
 
 def cpu_allreduce_bench(counts: list[int], world_size: int, steps: int = 3, warmup: int = 1) -> dict:
-    return mpi_allreduce_bench(counts, world_size, steps, warmup, memory="host")
+    """The `refcpu` baseline: the reference's algorithm on host memory."""
+    return mpi_allreduce_bench(counts, world_size, steps, warmup, memory="host", host_algo="reference")
