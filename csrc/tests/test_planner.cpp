@@ -155,7 +155,11 @@ TEST_CASE("planner: execute a batch and collect results", "[planner]")
 
 TEST_CASE("planner: executors are reused and reaped", "[planner][executor]")
 {
+    // (set through the environment before any executor thread exists: the
+    // config object is read concurrently once they run)
+    setenv("BOUND_TIMEOUT", "5", 1);
     ClusterFixture f(4);
+    unsetenv("BOUND_TIMEOUT");
     auto req = faabric::util::batchExecFactory("demo", "echo", 3);
     f.plannerCli.callFunctions(req);
     f.awaitBatch(req);
@@ -166,8 +170,8 @@ TEST_CASE("planner: executors are reused and reaped", "[planner][executor]")
     f.awaitBatch(req2);
     REQUIRE_EQ(f.sch.getFunctionExecutorCount(req->messages(0)), 3);
     // Reaping after the bound timeout
-    f.conf.boundTimeout = 1;
-    std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    REQUIRE_EQ(f.conf.boundTimeout, 5);
+    std::this_thread::sleep_for(std::chrono::milliseconds(40));
     REQUIRE_EQ(f.sch.reapStaleExecutors(), 3);
     REQUIRE_EQ(f.sch.getFunctionExecutorCount(req->messages(0)), 0);
 }
