@@ -416,6 +416,11 @@ class MpiWorld
         void barrier(int timeoutMs);
     };
     std::unique_ptr<HostCollective> hostCollective;
+    bool sharedMemoryEligible(size_t bytes) const { return hostCollective != nullptr && bytes >= 32 * 1024; }
+    void sharedBroadcast(int root, int rank, uint8_t* buffer, size_t bytes);
+    void sharedAllGather(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t sendBytes);
+    void sharedAllToAll(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t chunkBytes);
+    void sharedReduce(int rank, int root, uint8_t* sendBuffer, uint8_t* recvBuffer, faabric_datatype_t* datatype, int count, faabric_op_t* operation);
     bool trySharedMemoryAllReduce(int rank,
                                   uint8_t* sendBuffer,
                                   uint8_t* recvBuffer,

@@ -536,6 +536,100 @@ bool fusedReduce(faabric_datatype_t* dt, int opId, const uint8_t* const* srcs, i
 }
 }
 
+// Shared-memory variants of the other collectives (all ranks in this process,
+// host buffers, >= 32 KiB): publish pointers, barrier, copy / reduce straight
+// between the user buffers, barrier.
+void MpiWorld::sharedBroadcast(int root, int rank, uint8_t* buffer, size_t bytes)
+{
+    HostCollective* hc = hostCollective.get();
+    const int timeoutMs = faabric::util::getSystemConfig().globalMessageTimeout;
+    hc->sendPtrs[rank] = buffer;
+    hc->barrier(timeoutMs);
+    if (rank != root) {
+        memcpy(buffer, hc->sendPtrs[root], bytes);
+    }
+    hc->barrier(timeoutMs);
+}
+
+void MpiWorld::sharedAllGather(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t sendBytes)
+{
+    HostCollective* hc = hostCollective.get();
+    const int timeoutMs = faabric::util::getSystemConfig().globalMessageTimeout;
+    const int n = hc->nRanks;
+    hc->sendPtrs[rank] = sendBuffer;
+    hc->barrier(timeoutMs);
+    for (int q = 0; q < n; q++) {
+        int p = (rank + q) % n;
+        uint8_t* dst = recvBuffer + (size_t)p * sendBytes;
+        if (dst != hc->sendPtrs[p]) {
+            memcpy(dst, hc->sendPtrs[p], sendBytes);
+        }
+    }
+    hc->barrier(timeoutMs);
+}
+
+void MpiWorld::sharedAllToAll(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t chunkBytes)
+{
+    HostCollective* hc = hostCollective.get();
+    const int timeoutMs = faabric::util::getSystemConfig().globalMessageTimeout;
+    const int n = hc->nRanks;
+    hc->sendPtrs[rank] = sendBuffer;
+    hc->barrier(timeoutMs);
+    for (int q = 0; q < n; q++) {
+        int p = (rank + q) % n;
+        memcpy(recvBuffer + (size_t)p * chunkBytes, hc->sendPtrs[p] + (size_t)rank * chunkBytes, chunkBytes);
+    }
+    hc->barrier(timeoutMs);
+}
+
+void MpiWorld::sharedReduce(int rank,
+                            int root,
+                            uint8_t* sendBuffer,
+                            uint8_t* recvBuffer,
+                            faabric_datatype_t* datatype,
+                            int count,
+                            faabric_op_t* operation)
+{
+    HostCollective* hc = hostCollective.get();
+    const int timeoutMs = faabric::util::getSystemConfig().globalMessageTimeout;
+    const int n = hc->nRanks;
+    const size_t esize = (size_t)datatype->size;
+    hc->sendPtrs[rank] = sendBuffer;
+    hc->recvPtrs[rank] = recvBuffer;
+    hc->barrier(timeoutMs);
+    // Every rank folds its slice of all inputs into the ROOT's output
+    const size_t per = ((size_t)count + n - 1) / n;
+    const size_t beg = std::min((size_t)rank * per, (size_t)count);
+    const size_t len = std::min(per, (size_t)count - beg);
+    if (len > 0) {
+        uint8_t* dst = hc->recvPtrs[root] + beg * esize;
+        // The root's own input first: its output may alias it (MPI_IN_PLACE)
+        const uint8_t* srcs[16];
+        bool fused = n <= 16;
+        if (fused) {
+            srcs[0] = hc->sendPtrs[root] + beg * esize;
+            int k = 1;
+            for (int q = 0; q < n; q++) {
+                if (q != root) {
+                    srcs[k++] = hc->sendPtrs[q] + beg * esize;
+                }
+            }
+            fused = fusedReduce(datatype, operation->id, srcs, n, dst, len);
+        }
+        if (!fused) {
+            if (dst != hc->sendPtrs[root] + beg * esize) {
+                memcpy(dst, hc->sendPtrs[root] + beg * esize, len * esize);
+            }
+            for (int q = 0; q < n; q++) {
+                if (q != root) {
+                    op_reduce(operation, datatype, (int)len, const_cast<uint8_t*>(hc->sendPtrs[q]) + beg * esize, dst);
+                }
+            }
+        }
+    }
+    hc->barrier(timeoutMs);
+}
+
 bool MpiWorld::trySharedMemoryAllReduce(int rank,
                                         uint8_t* sendBuffer,
                                         uint8_t* recvBuffer,
@@ -1391,6 +1485,10 @@ void MpiWorld::broadcast(int rootRank,
         return;
     }
 
+    if (messageType == MpiMessageType::NORMAL && sharedMemoryEligible(bytes)) {
+        sharedBroadcast(rootRank, thisRank, buffer, bytes);
+        return;
+    }
     // Two-level tree: the root feeds its co-located ranks and one leader per
     // other host; leaders feed their own host
     const std::string rootHost = getHostForRank(rootRank);
@@ -1582,6 +1680,10 @@ void MpiWorld::allGather(int rank,
             return;
         }
     }
+    if (!isDevicePointer(sendBuffer) && !isDevicePointer(recvBuffer) && sharedMemoryEligible(sendBytes * size)) {
+        sharedAllGather(rank, sendBuffer, recvBuffer, sendBytes);
+        return;
+    }
     // gather to rank 0, then broadcast the concatenation
     const int root = MPI_MAIN_RANK;
     const int fullCount = recvCount * size;
@@ -1628,6 +1730,10 @@ void MpiWorld::reduce(int sendRank,
         return;
     }
 
+    if (sharedMemoryEligible(bytes)) {
+        sharedReduce(sendRank, recvRank, sendBuffer, recvBuffer, datatype, count, operation);
+        return;
+    }
     const std::string rootHost = getHostForRank(recvRank);
     const bool rootIsLocal = rootHost == thisHost;
     std::set<int> localRanks;
@@ -2085,6 +2191,10 @@ void MpiWorld::allToAll(int rank,
         uint8_t* r = out.out(recvBuffer, chunk * size);
         allToAll(rank, s, sendType, sendCount, r, recvType, recvCount);
         out.flush();
+        return;
+    }
+    if (sharedMemoryEligible(chunk * size)) {
+        sharedAllToAll(rank, sendBuffer, recvBuffer, chunk);
         return;
     }
     // Flat pairwise exchange: send everything, then receive in rank order

@@ -353,6 +353,82 @@ TEST_CASE("mpi: large host all-reduces use the shared-memory path", "[mpi]")
     unsetenv("FAABRIC_MPI_HOST_ALLREDUCE");
 }
 
+namespace {
+// Large host broadcast / reduce / allgather / alltoall: direct copies between
+// the user buffers when every rank lives in this process
+int bodyLargeHostCollectives(int rank, int size)
+{
+    const int n = 50001;
+    // broadcast from a non-zero root
+    const int root = size - 1;
+    std::vector<int> b(n, rank == root ? 7 : -1);
+    if (rank == root) {
+        b[n - 1] = 99;
+    }
+    MPI_Bcast(b.data(), n, MPI_INT, root, MPI_COMM_WORLD);
+    CHECK_RANK(b[0] == 7 && b[n / 2] == 7 && b[n - 1] == 99);
+
+    // reduce to a non-zero root, out of place then in place
+    std::vector<double> d(n), dOut(rank == 1 ? n : 0);
+    for (int i = 0; i < n; i++) {
+        d[i] = (double)(i % 13) + rank;
+    }
+    MPI_Reduce(d.data(), dOut.data(), n, MPI_DOUBLE, MPI_SUM, 1, MPI_COMM_WORLD);
+    if (rank == 1) {
+        for (int i : { 0, 5, n / 2, n - 1 }) {
+            CHECK_RANK(dOut[i] == (double)(i % 13) * size + size * (size - 1) / 2.0);
+        }
+    }
+    std::vector<int> m(n, rank);
+    m[3] = 100 - rank;
+    if (rank == 0) {
+        MPI_Reduce(MPI_IN_PLACE, m.data(), n, MPI_INT, MPI_MAX, 0, MPI_COMM_WORLD);
+        CHECK_RANK(m[0] == size - 1 && m[3] == 100 && m[n - 1] == size - 1);
+    } else {
+        MPI_Reduce(m.data(), nullptr, n, MPI_INT, MPI_MAX, 0, MPI_COMM_WORLD);
+        CHECK_RANK(m[0] == rank && m[3] == 100 - rank);
+    }
+
+    // allgather, out of place and in place
+    const int per = 9001;
+    std::vector<int> mine(per, rank + 1), all((size_t)per * size, 0);
+    MPI_Allgather(mine.data(), per, MPI_INT, all.data(), per, MPI_INT, MPI_COMM_WORLD);
+    for (int r = 0; r < size; r++) {
+        CHECK_RANK(all[(size_t)r * per] == r + 1 && all[(size_t)r * per + per - 1] == r + 1);
+    }
+    std::vector<int> inPlace((size_t)per * size, -1);
+    std::fill(inPlace.begin() + (size_t)rank * per, inPlace.begin() + (size_t)(rank + 1) * per, 10 * rank);
+    MPI_Allgather(MPI_IN_PLACE, 0, MPI_DATATYPE_NULL, inPlace.data(), per, MPI_INT, MPI_COMM_WORLD);
+    for (int r = 0; r < size; r++) {
+        CHECK_RANK(inPlace[(size_t)r * per + 17] == 10 * r);
+    }
+
+    // alltoall: chunk for rank r carries (me, r)
+    std::vector<int> out((size_t)per * size), in((size_t)per * size, -1);
+    for (int r = 0; r < size; r++) {
+        std::fill(out.begin() + (size_t)r * per, out.begin() + (size_t)(r + 1) * per, rank * 100 + r);
+    }
+    for (int round = 0; round < 3; round++) {
+        MPI_Alltoall(out.data(), per, MPI_INT, in.data(), per, MPI_INT, MPI_COMM_WORLD);
+        for (int r = 0; r < size; r++) {
+            CHECK_RANK(in[(size_t)r * per] == r * 100 + rank && in[(size_t)r * per + per - 1] == r * 100 + rank);
+        }
+        std::fill(in.begin(), in.end(), -1);
+    }
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+}
+
+TEST_CASE("mpi: large host collectives copy between user buffers", "[mpi]")
+{
+    runMpi("large-host-coll", 5, 1, bodyLargeHostCollectives);
+    runMpi("large-host-coll-gpuhosts", 6, 3, bodyLargeHostCollectives);
+    setenv("FAABRIC_MPI_HOST_ALLREDUCE", "reference", 1);
+    runMpi("large-host-coll-ref", 3, 1, bodyLargeHostCollectives);
+    unsetenv("FAABRIC_MPI_HOST_ALLREDUCE");
+}
+
 TEST_CASE("mpi: point-to-point on one host", "[mpi]")
 {
     runMpi("p2p-local", 4, 1, bodyPointToPoint);
