@@ -206,6 +206,9 @@ def load_tuning(comm, args, dist):
     if not path.exists():
         return None
     try:
+        if path.suffix != ".json":  # native text format (faabric_b200.parallel.autotune)
+            comm.load_tuning(path)
+            return str(path)
         t = json.loads(path.read_text())
         comm.set_allreduce_table([(e["max_bytes"], e["algo"]) for e in t["allreduce"]])
         return str(path)
@@ -451,6 +454,10 @@ def mode_sweep(args, dist: Dist):
         tp = Path("gpurun_out") / f"tuning_N{n}.json"
         tp.parent.mkdir(exist_ok=True)
         tp.write_text(json.dumps({"n_gpus": n, "allreduce": merged, "source": "bench.py --mode sweep"}, indent=1))
+        # same table in the format FAABRIC_TUNING_FILE takes
+        from faabric_b200.parallel import autotune
+
+        autotune.write_tuning_file(tp.with_suffix(".txt"), autotune.table_from_rows(rows), comment=f"bench.py --mode sweep, {n} GPUs, fp32")
     best = max((r.get("auto_busbw", 0) for r in rows), default=0)
     out = {
         "metric": "mpi_allreduce_busbw_sweep_GBps",

@@ -7,6 +7,7 @@
 #include "launch_api.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -211,6 +212,48 @@ int fb_comm_configure(void* h, int key, uint64_t value)
             return FB_E_INVALID;
     }
     return FB_OK;
+}
+
+// Applies a tuning file to a live communicator: 0, FB_E_INVALID (unreadable
+// or malformed; the message goes to stderr)
+int fb_comm_load_tuning(void* h, const char* path)
+{
+    try {
+        faabric::device::CommTuning t;
+        if (!faabric::device::CommTuning::loadFile(path, t)) {
+            return FB_E_INVALID;
+        }
+        COMM(h)->applyTuning(t);
+        return FB_OK;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "faabric_b200: %s\n", e.what());
+        return FB_E_INVALID;
+    }
+}
+
+// Parses + re-serialises tuning text without a device (format checks, tools).
+// Returns the length written (excluding NUL), or -1 on a parse error with the
+// message in `out`.
+int fb_tuning_normalise(const char* text, char* out, int cap)
+{
+    std::string res;
+    int rc = 0;
+    try {
+        res = faabric::device::CommTuning::parse(text).serialise();
+        rc = (int)res.size();
+    } catch (const std::exception& e) {
+        res = e.what();
+        rc = -1;
+    }
+    if (cap > 0) {
+        size_t n = std::min(res.size(), (size_t)cap - 1);
+        memcpy(out, res.data(), n);
+        out[n] = 0;
+        if (rc >= 0) {
+            rc = (int)n;
+        }
+    }
+    return rc;
 }
 
 int fb_comm_set_allreduce_table(void* h,

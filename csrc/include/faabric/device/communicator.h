@@ -63,6 +63,30 @@ struct CommConfig
     static CommConfig fromEnv();
 };
 
+// Tuning file written by the autotuner (`python -m faabric_b200.parallel.autotune`)
+// and read by every communicator when FAABRIC_TUNING_FILE names it.  One
+// directive per line, '#' starts a comment:
+//   allreduce <maxBytes> <oneshot|twoshot|nvls|ll>   selection table row
+//   set <key> <value>                                CommConfig threshold, keys
+//       llMaxBytes oneShotMaxBytes nvlsMinBytes nvlsScalarMinBytes
+//       bcast2StepMinBytes tmaMinBytes maxBlocks threads channels
+struct CommTuning
+{
+    std::vector<std::pair<uint64_t, int>> allReduceTable;
+    std::vector<std::pair<std::string, uint64_t>> settings;
+
+    // Throws std::runtime_error naming the offending line
+    static CommTuning parse(const std::string& text);
+    // false if the file cannot be read; parse errors throw
+    static bool loadFile(const std::string& path, CommTuning& out);
+    std::string serialise() const;
+    void applyTo(CommConfig& cfg) const;
+    bool empty() const { return allReduceTable.empty() && settings.empty(); }
+
+    static int algoFromName(const std::string& name);
+    static const char* algoName(int algo);
+};
+
 struct CommStats
 {
     uint64_t launches = 0;
@@ -191,6 +215,10 @@ class Communicator
     // Written by the autotuner; empty => built-in thresholds.
     void setAllReduceTable(const std::vector<uint64_t>& maxBytes,
                            const std::vector<int>& algos);
+    // Thresholds + table from a parsed tuning file
+    void applyTuning(const CommTuning& tuning);
+    // Reads FAABRIC_TUNING_FILE if set (malformed files are reported and ignored)
+    void applyTuningFromEnv();
     int pickAllReduceAlgo(uint64_t bytes, bool nvlsOk) const;
 
     static const char* errorString(int code);

@@ -6,6 +6,7 @@
 #include "launch_api.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <initializer_list>
 #include <barrier>
 #include <cstdlib>
@@ -70,6 +71,190 @@ CommConfig CommConfig::fromEnv()
     c.bcast2StepMinBytes =
       envSize("FAABRIC_BCAST_2STEP_MIN_BYTES", c.bcast2StepMinBytes);
     return c;
+}
+
+// ---------------------------------------------------------------------------
+// Tuning file
+// ---------------------------------------------------------------------------
+namespace {
+struct TuningKey
+{
+    const char* name;
+    uint64_t (*get)(const CommConfig&);
+    void (*set)(CommConfig&, uint64_t);
+};
+#define FB_TUNING_KEY(field, type)                                                       \
+    TuningKey{ #field,                                                                   \
+               [](const CommConfig& c) -> uint64_t { return (uint64_t)c.field; },        \
+               [](CommConfig& c, uint64_t v) { c.field = (type)v; } }
+const TuningKey TUNING_KEYS[] = {
+    FB_TUNING_KEY(llMaxBytes, size_t),         FB_TUNING_KEY(oneShotMaxBytes, size_t),
+    FB_TUNING_KEY(nvlsMinBytes, size_t),       FB_TUNING_KEY(nvlsScalarMinBytes, size_t),
+    FB_TUNING_KEY(bcast2StepMinBytes, size_t), FB_TUNING_KEY(tmaMinBytes, size_t),
+    FB_TUNING_KEY(maxBlocks, int),             FB_TUNING_KEY(threads, int),
+    FB_TUNING_KEY(channels, int),
+};
+#undef FB_TUNING_KEY
+const char* const ALGO_NAMES[FB_ALGO_COUNT] = { "auto", "oneshot", "twoshot", "nvls", "ll", "copy-engine" };
+}
+
+int CommTuning::algoFromName(const std::string& name)
+{
+    for (int i = 0; i < FB_ALGO_COUNT; i++) {
+        if (name == ALGO_NAMES[i]) {
+            return i;
+        }
+    }
+    return -1;
+}
+
+const char* CommTuning::algoName(int algo)
+{
+    return algo >= 0 && algo < FB_ALGO_COUNT ? ALGO_NAMES[algo] : "?";
+}
+
+CommTuning CommTuning::parse(const std::string& text)
+{
+    // Hand-rolled tokeniser: no locale-dependent stream extraction
+    CommTuning t;
+    int lineNo = 0;
+    auto bad = [&](const std::string& why) {
+        throw std::runtime_error("tuning file line " + std::to_string(lineNo) + ": " + why);
+    };
+    auto number = [&](const std::string& tok) -> uint64_t {
+        if (tok.empty() || tok.find_first_not_of("0123456789") != std::string::npos) {
+            bad("'" + tok + "' is not a non-negative integer");
+        }
+        return strtoull(tok.c_str(), nullptr, 10);
+    };
+    size_t pos = 0;
+    while (pos < text.size()) {
+        size_t eol = text.find('\n', pos);
+        if (eol == std::string::npos) {
+            eol = text.size();
+        }
+        std::string line = text.substr(pos, eol - pos);
+        pos = eol + 1;
+        lineNo++;
+        size_t hash = line.find('#');
+        if (hash != std::string::npos) {
+            line.resize(hash);
+        }
+        std::vector<std::string> tok;
+        size_t i = 0;
+        while (i < line.size()) {
+            while (i < line.size() && isspace((unsigned char)line[i])) {
+                i++;
+            }
+            size_t j = i;
+            while (j < line.size() && !isspace((unsigned char)line[j])) {
+                j++;
+            }
+            if (j > i) {
+                tok.push_back(line.substr(i, j - i));
+            }
+            i = j;
+        }
+        if (tok.empty()) {
+            continue;
+        }
+        if (tok[0] == "allreduce") {
+            if (tok.size() != 3) {
+                bad("expected 'allreduce <maxBytes> <algo>'");
+            }
+            int a = algoFromName(tok[2]);
+            if (a <= FB_ALGO_AUTO || a == FB_ALGO_COPY_ENGINE) {
+                bad("unknown all-reduce algorithm '" + tok[2] + "'");
+            }
+            t.allReduceTable.emplace_back(number(tok[1]), a);
+        } else if (tok[0] == "set") {
+            if (tok.size() != 3) {
+                bad("expected 'set <key> <value>'");
+            }
+            bool known = false;
+            for (const auto& k : TUNING_KEYS) {
+                known = known || tok[1] == k.name;
+            }
+            if (!known) {
+                bad("unknown key '" + tok[1] + "'");
+            }
+            t.settings.emplace_back(tok[1], number(tok[2]));
+        } else {
+            bad("unknown directive '" + tok[0] + "'");
+        }
+    }
+    std::sort(t.allReduceTable.begin(), t.allReduceTable.end());
+    return t;
+}
+
+bool CommTuning::loadFile(const std::string& path, CommTuning& out)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (f == nullptr) {
+        return false;
+    }
+    std::string text;
+    char buf[4096];
+    size_t n = 0;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) {
+        text.append(buf, n);
+    }
+    fclose(f);
+    out = parse(text);
+    return true;
+}
+
+std::string CommTuning::serialise() const
+{
+    std::string os = "# faabric_b200 communicator tuning\n";
+    for (const auto& [key, value] : settings) {
+        os += "set " + key + " " + std::to_string(value) + "\n";
+    }
+    for (const auto& [maxBytes, algo] : allReduceTable) {
+        os += "allreduce " + std::to_string(maxBytes) + " " + algoName(algo) + "\n";
+    }
+    return os;
+}
+
+void CommTuning::applyTo(CommConfig& cfg) const
+{
+    for (const auto& [key, value] : settings) {
+        for (const auto& k : TUNING_KEYS) {
+            if (key == k.name) {
+                k.set(cfg, value);
+            }
+        }
+    }
+    cfg.channels = std::clamp(cfg.channels, 1, FB_MAX_CHANNELS);
+}
+
+void Communicator::applyTuning(const CommTuning& tuning)
+{
+    // the lane count is fixed once the heap is laid out
+    const int channels = cfg_.channels;
+    tuning.applyTo(cfg_);
+    cfg_.channels = channels;
+    if (!tuning.allReduceTable.empty()) {
+        allReduceTable_ = tuning.allReduceTable;
+    }
+}
+
+void Communicator::applyTuningFromEnv()
+{
+    const char* path = getenv("FAABRIC_TUNING_FILE");
+    if (path == nullptr || *path == 0) {
+        return;
+    }
+    try {
+        CommTuning t;
+        if (CommTuning::loadFile(path, t)) {
+            applyTuning(t);
+        } else {
+            fprintf(stderr, "faabric_b200: tuning file %s not readable, using built-in thresholds\n", path);
+        }
+    } catch (const std::exception& e) {
+        fprintf(stderr, "faabric_b200: ignoring tuning file %s: %s\n", path, e.what());
+    }
 }
 
 const char* Communicator::errorString(int code)
@@ -248,6 +433,7 @@ std::vector<std::shared_ptr<Communicator>> Communicator::createLocal(
     for (int r = 0; r < nranks; r++) {
         auto c = std::shared_ptr<Communicator>(new Communicator());
         c->cfg_ = cfgIn;
+        c->applyTuningFromEnv();
         c->dev_.rank = r;
         c->dev_.nranks = nranks;
         c->device_ = devices[r];
@@ -446,6 +632,7 @@ std::shared_ptr<Communicator> Communicator::createIpc(int rank,
     }
     auto c = std::shared_ptr<Communicator>(new Communicator());
     c->cfg_ = cfgIn;
+    c->applyTuningFromEnv();
     c->dev_.rank = rank;
     c->dev_.nranks = nranks;
     c->device_ = device;

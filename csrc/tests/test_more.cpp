@@ -309,3 +309,64 @@ TEST_CASE("mpi: exec graph counts messages, two worlds run side by side", "[mpi]
     }
     faabric::mpi::getMpiWorldRegistry().clear();
 }
+
+// ---------------------------------------------------------------------------
+// Communicator tuning file (no device needed)
+// ---------------------------------------------------------------------------
+#include <faabric/device/communicator.h>
+
+TEST_CASE("device: tuning file parses, serialises and applies", "[device][config]")
+{
+    using faabric::device::CommConfig;
+    using faabric::device::CommTuning;
+    const std::string text = "# measured on 8 GPUs\n"
+                             "set oneShotMaxBytes 131072\n"
+                             "set  threads   256   # trailing comment\n"
+                             "\n"
+                             "allreduce 18446744073709551615 nvls\n"
+                             "allreduce 4096 ll\n"
+                             "allreduce 1048576 twoshot\n";
+    CommTuning t = CommTuning::parse(text);
+    REQUIRE_EQ(t.settings.size(), (size_t)2);
+    REQUIRE_EQ(t.allReduceTable.size(), (size_t)3);
+    // rows come back sorted by size
+    REQUIRE_EQ(t.allReduceTable[0].first, (uint64_t)4096);
+    REQUIRE_EQ(t.allReduceTable[0].second, (int)FB_ALGO_LL);
+    REQUIRE_EQ(t.allReduceTable[1].second, (int)FB_ALGO_TWOSHOT);
+    REQUIRE_EQ(t.allReduceTable[2].first, UINT64_MAX);
+    REQUIRE_EQ(t.allReduceTable[2].second, (int)FB_ALGO_NVLS);
+
+    CommConfig cfg;
+    const size_t llBefore = cfg.llMaxBytes;
+    t.applyTo(cfg);
+    REQUIRE_EQ(cfg.oneShotMaxBytes, (size_t)131072);
+    REQUIRE_EQ(cfg.threads, 256);
+    REQUIRE_EQ(cfg.llMaxBytes, llBefore);
+
+    // serialise -> parse is a fixed point
+    CommTuning again = CommTuning::parse(t.serialise());
+    REQUIRE(again.allReduceTable == t.allReduceTable);
+    REQUIRE(again.settings == t.settings);
+    REQUIRE_EQ(again.serialise(), t.serialise());
+
+    // file round trip
+    std::string path = "/tmp/fb_tuning_" + std::to_string(getpid()) + ".txt";
+    faabric::util::writeBytesToFile(path, faabric::util::stringToBytes(t.serialise()));
+    CommTuning fromFile;
+    REQUIRE(CommTuning::loadFile(path, fromFile));
+    REQUIRE(fromFile.allReduceTable == t.allReduceTable);
+    ::unlink(path.c_str());
+    REQUIRE(!CommTuning::loadFile(path, fromFile));
+
+    // malformed input names the line
+    for (const char* bad : { "allreduce 4096 warp9\n", "allreduce lots ll\n", "set nope 1\n", "frobnicate\n", "\nset threads\n", "allreduce 1 auto\n" }) {
+        bool threw = false;
+        try {
+            CommTuning::parse(bad);
+        } catch (const std::runtime_error& e) {
+            threw = std::string(e.what()).find("line") != std::string::npos;
+        }
+        REQUIRE(threw);
+    }
+    REQUIRE(CommTuning::parse("").empty());
+}

@@ -86,6 +86,8 @@ def load():
     _sig(lib, "fb_comm_backing", C.c_char_p, [vp])
     _sig(lib, "fb_comm_configure", i32, [vp, i32, u64])
     _sig(lib, "fb_comm_set_allreduce_table", i32, [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_int)])
+    _sig(lib, "fb_comm_load_tuning", i32, [vp, C.c_char_p])
+    _sig(lib, "fb_tuning_normalise", i32, [C.c_char_p, C.c_char_p, i32])
     _sig(lib, "fb_comm_stats", None, [vp, C.POINTER(C.c_uint64), i32])
     _sig(lib, "fb_comm_alloc", C.c_int64, [vp, u64])
     _sig(lib, "fb_comm_free", None, [vp, u64])

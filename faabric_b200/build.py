@@ -65,6 +65,54 @@ INCLUDES = [
 ]
 
 
+_STDCXX_FLAGS: list[str] | None = None
+
+
+def _stdcxx_link_flags() -> list[str]:
+    """Make sure libstdc++ is linked as the SHARED system library.
+
+    Some toolchain wrappers (e.g. a ``$CXX`` whose private lib dir only has a
+    usable ``libstdc++.a``) silently link libstdc++ statically.  A second copy
+    of libstdc++ inside libfaabric_b200.so, loaded into a Python process next
+    to torch's libstdc++.so.6, mixes the two runtimes (locale facets!) and
+    crashes in iostream code.  If the probe link does not depend on
+    libstdc++.so, point the linker at the directory that holds the system one.
+    """
+    global _STDCXX_FLAGS
+    if _STDCXX_FLAGS is not None:
+        return _STDCXX_FLAGS
+    flags: list[str] = []
+    try:
+        probe_dir = BUILD / "probe"
+        probe_dir.mkdir(parents=True, exist_ok=True)
+        src = probe_dir / "p.cpp"
+        src.write_text("#include <string>\nstd::string fb_probe(){return std::string(40, 'x');}\n")
+        out = probe_dir / "libp.so"
+
+        def links_shared(extra):
+            r = subprocess.run([CXX, "-shared", "-fPIC", str(src), "-o", str(out)] + extra, capture_output=True, text=True)
+            if r.returncode != 0:
+                return False
+            d = subprocess.run(["readelf", "-d", str(out)], capture_output=True, text=True).stdout
+            return "libstdc++.so" in d
+
+        if not links_shared([]):
+            for cand in ("g++", "/usr/bin/g++", "c++"):
+                exe = shutil.which(cand)
+                if not exe:
+                    continue
+                f = subprocess.run([exe, "-print-file-name=libstdc++.so"], capture_output=True, text=True).stdout.strip()
+                if f and os.path.isabs(f) and os.path.exists(f):
+                    extra = [f"-L{os.path.dirname(f)}"]
+                    if links_shared(extra):
+                        flags = extra
+                        break
+    except OSError:
+        pass
+    _STDCXX_FLAGS = flags
+    return flags
+
+
 def _stamp_of(paths) -> str:
     h = hashlib.sha1()
     for p in sorted(paths):
@@ -158,6 +206,7 @@ def build(force: bool = False, bins: bool = True, jobs: int | None = None, verbo
     if need_link:
         cmd = (
             [CXX, "-shared", "-o", str(LIB)]
+            + _stdcxx_link_flags()
             + [str(o) for o in objs]
             + [
                 f"-L{CUDA_HOME / 'lib64'}",
@@ -208,6 +257,7 @@ def _build_bins(stamp, relink: bool, verbose: bool) -> None:
             if rebuilt or relink or not out.exists():
                 cmd = (
                     [CXX, "-o", str(out)]
+                    + _stdcxx_link_flags()
                     + [str(o) for o in objs]
                     + [
                         f"-L{LIBDIR}",

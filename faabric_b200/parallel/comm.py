@@ -185,6 +185,10 @@ class Communicator:
         al = (C.c_int * n)(*[ALGOS[t[1]] for t in table])
         self._check(self._lib.fb_comm_set_allreduce_table(self._h, n, mb, al), "set table")
 
+    def load_tuning(self, path):
+        """Apply a tuning file (see ``faabric_b200.parallel.autotune``)."""
+        self._check(self._lib.fb_comm_load_tuning(self._h, str(path).encode()), f"load tuning {path}")
+
     def configure(self, **kw):
         keys = {
             "llMaxBytes": 0,
