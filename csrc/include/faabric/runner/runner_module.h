@@ -45,6 +45,11 @@ class FaabricMain
 
     void shutdown();
 
+    // Snapshot registry <-> FAABRIC_CHECKPOINT_DIR (no-ops when unset)
+    void restoreCheckpoint();
+
+    void writeCheckpoint();
+
   private:
     faabric::state::StateServer stateServer;
     faabric::scheduler::FunctionCallServer functionServer;

@@ -67,6 +67,20 @@ class DeviceSnapshot
     // Restore: device-to-device copy of the image into executor memory
     void restoreTo(uint8_t* deviceMem, size_t n, void* stream = nullptr);
 
+    // ---- spill / reload (checkpoint of a device image) ----
+    // Host snapshot with the same bytes and merge regions (D2H copy)
+    std::shared_ptr<faabric::util::SnapshotData> spillToHost();
+
+    // New device image on `device` from a host snapshot (H2D copy)
+    static std::shared_ptr<DeviceSnapshot> fromHost(faabric::util::SnapshotData& host, int device);
+
+    void writeToFile(const std::string& path) { spillToHost()->writeToFile(path); }
+
+    static std::shared_ptr<DeviceSnapshot> readFromFile(const std::string& path, int device)
+    {
+        return fromHost(*faabric::util::SnapshotData::readFromFile(path), device);
+    }
+
     // ---- merge regions (same semantics as SnapshotData) ----
     void addMergeRegion(uint64_t offset,
                         size_t length,
@@ -232,6 +246,15 @@ class SnapshotRegistry
     void deleteDeviceSnapshot(const std::string& key);
 
     void clear();
+
+    // ---- on-disk checkpoints: one file per snapshot under `dir` (created if
+    // missing), named by the hex-encoded key; device images are spilled
+    // through the host.  Returns the number of files written / snapshots
+    // registered.  `device` < 0 restores everything as host snapshots,
+    // otherwise images saved from device memory return to that GPU. ----
+    size_t checkpointToDir(const std::string& dir);
+
+    size_t restoreFromDir(const std::string& dir, int device = -1);
 
   private:
     std::shared_mutex snapshotsMx;

@@ -688,6 +688,8 @@ class SystemConfig
     int slotsPerGpu;
     // Offset added to every well-known port (several workers on one box)
     int portOffset;
+    // Snapshot checkpoint directory (empty = keep snapshots in memory only)
+    std::string checkpointDir;
 
     SystemConfig();
 
@@ -2073,6 +2075,14 @@ class SnapshotData
     size_t getSize() const { return size; }
 
     size_t getMaxSize() const { return maxSize; }
+
+    // ---- checkpoint persistence (the reference keeps snapshots in memory
+    // only; here a frozen app's image can outlive the process) ----
+    // Image + merge regions, written to `path` atomically (temp file + rename)
+    void writeToFile(const std::string& path);
+
+    // Throws std::runtime_error on a missing / truncated / foreign file
+    static std::shared_ptr<SnapshotData> readFromFile(const std::string& path);
 
     // Every write since the last clear as Raw/Bytewise diffs into the image
     std::vector<SnapshotDiff> getTrackedChanges();

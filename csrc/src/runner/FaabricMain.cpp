@@ -60,12 +60,44 @@ void FaabricMain::startBackground()
     faabric::planner::getPlannerClient().ping();
     // Everything must answer BEFORE the planner learns about this host: it
     // may dispatch work the instant the registration lands
+    restoreCheckpoint();
     startStateServer();
     startSnapshotServer();
     startPointToPointServer();
     startFunctionCallServer();
     startRunner();
     PROF_SUMMARY
+}
+
+// FAABRIC_CHECKPOINT_DIR: snapshots (frozen / migrating apps' memory images,
+// thread snapshots) survive a worker restart.  The reference has no on-disk
+// persistence.
+void FaabricMain::restoreCheckpoint()
+{
+    const std::string& dir = faabric::util::getSystemConfig().checkpointDir;
+    if (dir.empty()) {
+        return;
+    }
+    try {
+        size_t n = faabric::snapshot::getSnapshotRegistry().restoreFromDir(dir);
+        SPDLOG_INFO("Restored {} snapshots from {}", n, dir);
+    } catch (const std::exception& e) {
+        SPDLOG_ERROR("Ignoring checkpoint directory {}: {}", dir, e.what());
+    }
+}
+
+void FaabricMain::writeCheckpoint()
+{
+    const std::string& dir = faabric::util::getSystemConfig().checkpointDir;
+    if (dir.empty()) {
+        return;
+    }
+    try {
+        size_t n = faabric::snapshot::getSnapshotRegistry().checkpointToDir(dir);
+        SPDLOG_INFO("Checkpointed {} snapshots to {}", n, dir);
+    } catch (const std::exception& e) {
+        SPDLOG_ERROR("Checkpoint to {} failed: {}", dir, e.what());
+    }
 }
 
 void FaabricMain::startRunner()
@@ -119,6 +151,8 @@ void FaabricMain::shutdown()
     pointToPointServer.stop();
     snapshotServer.stop();
     stateServer.stop();
+    // nothing can change the images any more
+    writeCheckpoint();
     SPDLOG_INFO("Worker shut down");
 }
 

@@ -1,4 +1,5 @@
 // SnapshotRegistry, SnapshotClient, SnapshotServer, DeviceSnapshot
+#include <filesystem>
 #include <faabric/scheduler/Scheduler.h>
 #include <faabric/snapshot/DeviceSnapshot.h>
 #include <faabric/snapshot/SnapshotClient.h>
@@ -108,6 +109,107 @@ void SnapshotRegistry::clear()
     std::unique_lock<std::shared_mutex> lock(snapshotsMx);
     snapshotMap.clear();
     deviceMap.clear();
+}
+
+// On-disk checkpoints: "<hex(key)>.snap" for host images, ".dsnap" for images
+// that lived in device memory
+namespace {
+std::string hexKey(const std::string& key)
+{
+    static const char* digits = "0123456789abcdef";
+    std::string out;
+    out.reserve(key.size() * 2);
+    for (unsigned char c : key) {
+        out.push_back(digits[c >> 4]);
+        out.push_back(digits[c & 15]);
+    }
+    return out;
+}
+
+bool unhexKey(const std::string& hex, std::string& key)
+{
+    if (hex.size() % 2 != 0) {
+        return false;
+    }
+    key.clear();
+    auto nibble = [](char c) -> int {
+        if (c >= '0' && c <= '9') {
+            return c - '0';
+        }
+        if (c >= 'a' && c <= 'f') {
+            return c - 'a' + 10;
+        }
+        return -1;
+    };
+    for (size_t i = 0; i < hex.size(); i += 2) {
+        int hi = nibble(hex[i]);
+        int lo = nibble(hex[i + 1]);
+        if (hi < 0 || lo < 0) {
+            return false;
+        }
+        key.push_back((char)((hi << 4) | lo));
+    }
+    return true;
+}
+}
+
+size_t SnapshotRegistry::checkpointToDir(const std::string& dir)
+{
+    std::filesystem::create_directories(dir);
+    // Copy the maps: file IO happens outside the registry lock
+    std::unordered_map<std::string, std::shared_ptr<SnapshotData>> hostSnaps;
+    std::unordered_map<std::string, std::shared_ptr<DeviceSnapshot>> deviceSnaps;
+    {
+        std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+        hostSnaps = snapshotMap;
+        deviceSnaps = deviceMap;
+    }
+    size_t written = 0;
+    for (const auto& [key, snap] : hostSnaps) {
+        snap->writeToFile(dir + "/" + hexKey(key) + ".snap");
+        written++;
+    }
+    for (const auto& [key, snap] : deviceSnaps) {
+        snap->writeToFile(dir + "/" + hexKey(key) + ".dsnap");
+        written++;
+    }
+    // Files of snapshots that no longer exist would resurrect them on restore
+    for (const auto& entry : std::filesystem::directory_iterator(dir)) {
+        const std::filesystem::path& p = entry.path();
+        const std::string ext = p.extension().string();
+        std::string key;
+        if ((ext == ".snap" && unhexKey(p.stem().string(), key) && !hostSnaps.contains(key)) ||
+            (ext == ".dsnap" && unhexKey(p.stem().string(), key) && !deviceSnaps.contains(key))) {
+            std::error_code ec;
+            std::filesystem::remove(p, ec);
+        }
+    }
+    SPDLOG_DEBUG("Checkpointed {} snapshots to {}", written, dir);
+    return written;
+}
+
+size_t SnapshotRegistry::restoreFromDir(const std::string& dir, int device)
+{
+    size_t restored = 0;
+    if (!std::filesystem::is_directory(dir)) {
+        return 0;
+    }
+    for (const auto& entry : std::filesystem::directory_iterator(dir)) {
+        const std::filesystem::path& p = entry.path();
+        const std::string ext = p.extension().string();
+        std::string key;
+        if ((ext != ".snap" && ext != ".dsnap") || !unhexKey(p.stem().string(), key)) {
+            continue;
+        }
+        auto host = SnapshotData::readFromFile(p.string());
+        if (ext == ".dsnap" && device >= 0) {
+            registerDeviceSnapshot(key, DeviceSnapshot::fromHost(*host, device));
+        } else {
+            registerSnapshot(key, host);
+        }
+        restored++;
+    }
+    return restored;
 }
 
 // ---------------------------------------------------------------------------
@@ -468,6 +570,37 @@ std::vector<uint8_t> DeviceSnapshot::getDataCopy(uint64_t offset, size_t n)
     DeviceGuard g(device);
     DS_CUDA(cudaMemcpy(out.data(), image + offset, n, cudaMemcpyDeviceToHost));
     return out;
+}
+
+std::shared_ptr<SnapshotData> DeviceSnapshot::spillToHost()
+{
+    auto host = std::make_shared<SnapshotData>(size);
+    if (size > 0) {
+        // D2H in bounded pieces through one pinned-size staging vector
+        constexpr size_t PIECE = (size_t)64 << 20;
+        for (size_t off = 0; off < size; off += PIECE) {
+            size_t n = std::min(PIECE, size - off);
+            std::vector<uint8_t> piece = getDataCopy(off, n);
+            host->copyInData(piece, off);
+        }
+    }
+    for (const auto& r : getMergeRegions()) {
+        host->addMergeRegion(r.offset, r.length, r.dataType, r.operation);
+    }
+    host->clearTrackedChanges();
+    return host;
+}
+
+std::shared_ptr<DeviceSnapshot> DeviceSnapshot::fromHost(SnapshotData& host, int device)
+{
+    auto snap = std::make_shared<DeviceSnapshot>(host.getSize(), device);
+    if (host.getSize() > 0) {
+        snap->copyInData({ host.getDataPtr(), host.getSize() });
+    }
+    for (const auto& r : host.getMergeRegions()) {
+        snap->addMergeRegion(r.offset, r.length, r.dataType, r.operation);
+    }
+    return snap;
 }
 
 void DeviceSnapshot::restoreTo(uint8_t* deviceMem, size_t n, void* stream)

@@ -64,6 +64,7 @@ const std::vector<Knob>& knobs()
         { "B200", "FAABRIC_SYMM_HEAP_BYTES", "1073741824", &C::symmHeapBytes },
         { "B200", "FAABRIC_SLOTS_PER_GPU", "8", &C::slotsPerGpu },
         { "B200", "FAABRIC_PORT_OFFSET", "0", &C::portOffset },
+        { "B200", "FAABRIC_CHECKPOINT_DIR", "", &C::checkpointDir },
     };
     return table;
 }

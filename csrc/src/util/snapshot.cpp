@@ -5,7 +5,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 namespace faabric::util {
@@ -579,6 +581,142 @@ int SnapshotData::writeQueuedDiffs()
     queuedDiffData.clear();
     PROF_END(WriteQueuedDiffs)
     return n;
+}
+
+// ---------------------------------------------------------------------------
+// Checkpoint files.  Layout (little endian):
+//   char[8] "FBSNAP01" | u64 size | u64 maxSize | u32 nRegions | u32 reserved
+//   nRegions x { u64 offset, u64 length, u32 dataType, u32 operation }
+//   size bytes of image
+// ---------------------------------------------------------------------------
+namespace {
+constexpr char SNAP_FILE_MAGIC[8] = { 'F', 'B', 'S', 'N', 'A', 'P', '0', '1' };
+
+struct SnapFileHeader
+{
+    char magic[8];
+    uint64_t size;
+    uint64_t maxSize;
+    uint32_t nRegions;
+    uint32_t reserved;
+};
+
+struct SnapFileRegion
+{
+    uint64_t offset;
+    uint64_t length;
+    uint32_t dataType;
+    uint32_t operation;
+};
+
+void writeAll(int fd, const void* buf, size_t n, const std::string& path)
+{
+    const uint8_t* p = (const uint8_t*)buf;
+    while (n > 0) {
+        ssize_t w = ::write(fd, p, std::min(n, (size_t)1 << 30));
+        if (w < 0) {
+            if (errno == EINTR) {
+                continue;
+            }
+            throw std::runtime_error("Writing snapshot file " + path + ": " + strerror(errno));
+        }
+        p += w;
+        n -= (size_t)w;
+    }
+}
+
+void readAll(int fd, void* buf, size_t n, const std::string& path)
+{
+    uint8_t* p = (uint8_t*)buf;
+    while (n > 0) {
+        ssize_t r = ::read(fd, p, std::min(n, (size_t)1 << 30));
+        if (r < 0 && errno == EINTR) {
+            continue;
+        }
+        if (r <= 0) {
+            throw std::runtime_error("Snapshot file " + path + " is truncated or unreadable");
+        }
+        p += r;
+        n -= (size_t)r;
+    }
+}
+}
+
+void SnapshotData::writeToFile(const std::string& path)
+{
+    // Readers may keep going; writers of the image are excluded
+    SharedLock lock(snapMx);
+    const std::string tmp = path + ".tmp." + std::to_string(::getpid());
+    int out = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+    if (out < 0) {
+        throw std::runtime_error("Cannot create snapshot file " + tmp + ": " + strerror(errno));
+    }
+    try {
+        SnapFileHeader h{};
+        memcpy(h.magic, SNAP_FILE_MAGIC, sizeof(h.magic));
+        h.size = size;
+        h.maxSize = maxSize;
+        h.nRegions = (uint32_t)mergeRegions.size();
+        writeAll(out, &h, sizeof(h), tmp);
+        for (const auto& r : mergeRegions) {
+            SnapFileRegion fr{ r.offset, r.length, (uint32_t)r.dataType, (uint32_t)r.operation };
+            writeAll(out, &fr, sizeof(fr), tmp);
+        }
+        if (size > 0) {
+            writeAll(out, data.get(), size, tmp);
+        }
+        if (::fsync(out) != 0) {
+            throw std::runtime_error("fsync of " + tmp + " failed: " + strerror(errno));
+        }
+    } catch (...) {
+        ::close(out);
+        ::unlink(tmp.c_str());
+        throw;
+    }
+    ::close(out);
+    if (::rename(tmp.c_str(), path.c_str()) != 0) {
+        std::string why = strerror(errno);
+        ::unlink(tmp.c_str());
+        throw std::runtime_error("Cannot move snapshot file into place at " + path + ": " + why);
+    }
+}
+
+std::shared_ptr<SnapshotData> SnapshotData::readFromFile(const std::string& path)
+{
+    int in = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (in < 0) {
+        throw std::runtime_error("Cannot open snapshot file " + path + ": " + strerror(errno));
+    }
+    std::shared_ptr<SnapshotData> snap;
+    try {
+        SnapFileHeader h{};
+        readAll(in, &h, sizeof(h), path);
+        if (memcmp(h.magic, SNAP_FILE_MAGIC, sizeof(h.magic)) != 0) {
+            throw std::runtime_error(path + " is not a snapshot file");
+        }
+        struct stat st{};
+        const uint64_t expect = sizeof(h) + (uint64_t)h.nRegions * sizeof(SnapFileRegion) + h.size;
+        if (::fstat(in, &st) != 0 || (uint64_t)st.st_size != expect || h.maxSize < h.size) {
+            throw std::runtime_error("Snapshot file " + path + " is truncated or corrupt");
+        }
+        std::vector<SnapFileRegion> regions(h.nRegions);
+        if (h.nRegions > 0) {
+            readAll(in, regions.data(), regions.size() * sizeof(SnapFileRegion), path);
+        }
+        snap = std::make_shared<SnapshotData>((size_t)h.size, (size_t)h.maxSize);
+        if (h.size > 0) {
+            // straight into the memfd-backed mapping
+            readAll(in, snap->data.get(), h.size, path);
+        }
+        for (const auto& r : regions) {
+            snap->addMergeRegion(r.offset, r.length, (SnapshotDataType)r.dataType, (SnapshotMergeOperation)r.operation);
+        }
+    } catch (...) {
+        ::close(in);
+        throw;
+    }
+    ::close(in);
+    return snap;
 }
 
 void SnapshotData::clearTrackedChanges()

@@ -18,6 +18,7 @@
 #include <faabric/util/files.h>
 #include <faabric/util/hwloc.h>
 
+#include <filesystem>
 #include <thread>
 #include <unistd.h>
 
@@ -246,6 +247,41 @@ TEST_CASE("runner boots and shuts a worker down", "[runner]")
     faabric::planner::getPlanner().reset();
     plannerServer.stop();
     faabric::scheduler::getScheduler().reset();
+}
+
+TEST_CASE("runner checkpoints snapshots across a worker restart", "[runner][checkpoint]")
+{
+    const std::string dir = "/tmp/fb_runner_ckpt_" + std::to_string(getpid());
+    std::filesystem::remove_all(dir);
+    auto& conf = faabric::util::getSystemConfig();
+    conf.checkpointDir = dir;
+    faabric::planner::PlannerServer plannerServer;
+    plannerServer.start();
+    faabric::planner::getPlanner().reset();
+    auto& reg = faabric::snapshot::getSnapshotRegistry();
+    reg.clear();
+    std::vector<uint8_t> image(10000, 42);
+    {
+        faabric::runner::FaabricMain m(std::make_shared<TestExecutorFactory>());
+        m.startBackground();
+        reg.registerSnapshot("migration_9001", std::make_shared<faabric::util::SnapshotData>(image));
+        m.shutdown();
+    }
+    // "restart": the registry is empty until the next worker boots
+    reg.clear();
+    {
+        faabric::runner::FaabricMain m(std::make_shared<TestExecutorFactory>());
+        m.startBackground();
+        REQUIRE(reg.snapshotExists("migration_9001"));
+        REQUIRE(reg.getSnapshot("migration_9001")->getDataCopy() == image);
+        m.shutdown();
+    }
+    conf.checkpointDir.clear();
+    reg.clear();
+    faabric::planner::getPlanner().reset();
+    plannerServer.stop();
+    faabric::scheduler::getScheduler().reset();
+    std::filesystem::remove_all(dir);
 }
 
 TEST_CASE("mpi: exec graph counts messages, two worlds run side by side", "[mpi]")

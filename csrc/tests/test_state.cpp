@@ -329,3 +329,106 @@ TEST_CASE("snapshots: push, update, thread results, delete over RPC", "[snapshot
     faabric::snapshot::clearMockSnapshotRequests();
     faabric::util::setMockMode(false);
 }
+
+// ---------------------------------------------------------------------------
+// Checkpoint files (no reference counterpart: its snapshots never leave memory,
+// SURVEY §5.4)
+// ---------------------------------------------------------------------------
+#include <filesystem>
+
+TEST_CASE("snapshots: checkpoint files round-trip image and merge regions", "[snapshot][checkpoint]")
+{
+    using namespace faabric::util;
+    const std::string dir = "/tmp/fb_ckpt_" + std::to_string(getpid());
+    std::filesystem::remove_all(dir);
+    std::filesystem::create_directories(dir);
+
+    const size_t size = 5 * HOST_PAGE_SIZE + 123;
+    std::vector<uint8_t> bytes(size);
+    for (size_t i = 0; i < size; i++) {
+        bytes[i] = (uint8_t)(i * 7 + 3);
+    }
+    SnapshotData snap(bytes, 16 * HOST_PAGE_SIZE);
+    snap.addMergeRegion(64, sizeof(int), SnapshotDataType::Int, SnapshotMergeOperation::Sum);
+    snap.addMergeRegion(4096, 0, SnapshotDataType::Raw, SnapshotMergeOperation::XOR);
+    const std::string path = dir + "/one.snap";
+    snap.writeToFile(path);
+    // no temp file left behind
+    size_t nFiles = 0;
+    for (auto& e : std::filesystem::directory_iterator(dir)) {
+        (void)e;
+        nFiles++;
+    }
+    REQUIRE_EQ(nFiles, (size_t)1);
+
+    auto back = SnapshotData::readFromFile(path);
+    REQUIRE_EQ(back->getSize(), size);
+    REQUIRE_EQ(back->getMaxSize(), (size_t)(16 * HOST_PAGE_SIZE));
+    REQUIRE(back->getDataCopy() == bytes);
+    auto regions = back->getMergeRegions();
+    REQUIRE_EQ(regions.size(), (size_t)2);
+    REQUIRE_EQ(regions[0].offset, (uint64_t)64);
+    REQUIRE(regions[0].dataType == SnapshotDataType::Int);
+    REQUIRE(regions[0].operation == SnapshotMergeOperation::Sum);
+    REQUIRE_EQ(regions[1].length, (uint64_t)0);
+    REQUIRE(regions[1].operation == SnapshotMergeOperation::XOR);
+    // the restored image is a full snapshot: it can grow and be mapped
+    std::vector<uint8_t> extra(HOST_PAGE_SIZE, 9);
+    back->copyInData(extra, 8 * HOST_PAGE_SIZE);
+    REQUIRE_EQ(back->getSize(), (size_t)(9 * HOST_PAGE_SIZE));
+    MemoryRegion mem = allocatePrivateMemory(back->getSize());
+    back->mapToMemory({ mem.get(), back->getSize() });
+    REQUIRE(std::equal(bytes.begin(), bytes.end(), mem.get()));
+
+    // overwrite in place, empty snapshots, error cases
+    SnapshotData empty;
+    empty.writeToFile(path);
+    REQUIRE_EQ(SnapshotData::readFromFile(path)->getSize(), (size_t)0);
+    REQUIRE_THROWS(SnapshotData::readFromFile(dir + "/missing.snap"));
+    writeBytesToFile(dir + "/junk.snap", std::vector<uint8_t>(100, 1));
+    REQUIRE_THROWS(SnapshotData::readFromFile(dir + "/junk.snap"));
+    snap.writeToFile(path);
+    std::filesystem::resize_file(path, std::filesystem::file_size(path) - 10);
+    REQUIRE_THROWS(SnapshotData::readFromFile(path));
+    REQUIRE_THROWS(snap.writeToFile(dir + "/no/such/dir/x.snap"));
+    std::filesystem::remove_all(dir);
+}
+
+TEST_CASE("snapshots: registry checkpoints to a directory and restores", "[snapshot][checkpoint]")
+{
+    using namespace faabric::util;
+    const std::string dir = "/tmp/fb_ckpt_reg_" + std::to_string(getpid());
+    std::filesystem::remove_all(dir);
+    auto& reg = faabric::snapshot::getSnapshotRegistry();
+    reg.clear();
+    std::vector<uint8_t> a(3000, 1), b(HOST_PAGE_SIZE * 2, 2);
+    auto sa = std::make_shared<SnapshotData>(a);
+    auto sb = std::make_shared<SnapshotData>(b);
+    sb->addMergeRegion(0, 8, SnapshotDataType::Long, SnapshotMergeOperation::Max);
+    // keys with characters that are not file-name safe
+    reg.registerSnapshot("demo/echo_123", sa);
+    reg.registerSnapshot("migration_77", sb);
+    REQUIRE_EQ(reg.checkpointToDir(dir), (size_t)2);
+    // unrelated files are ignored on restore
+    writeBytesToFile(dir + "/README", stringToBytes("not a snapshot"));
+    writeBytesToFile(dir + "/zz.snap", stringToBytes("name is not hex"));
+
+    reg.clear();
+    REQUIRE_EQ(reg.getSnapshotCount(), (size_t)0);
+    REQUIRE_EQ(reg.restoreFromDir(dir), (size_t)2);
+    REQUIRE(reg.snapshotExists("demo/echo_123"));
+    REQUIRE(reg.getSnapshot("demo/echo_123")->getDataCopy() == a);
+    auto rb = reg.getSnapshot("migration_77");
+    REQUIRE(rb->getDataCopy() == b);
+    REQUIRE_EQ(rb->getMergeRegions().size(), (size_t)1);
+    REQUIRE(rb->getMergeRegions()[0].operation == SnapshotMergeOperation::Max);
+    REQUIRE_EQ(reg.restoreFromDir(dir + "/nothing-here"), (size_t)0);
+    // a later checkpoint drops the files of deleted snapshots
+    reg.deleteSnapshot("migration_77");
+    REQUIRE_EQ(reg.checkpointToDir(dir), (size_t)1);
+    reg.clear();
+    REQUIRE_EQ(reg.restoreFromDir(dir), (size_t)1);
+    REQUIRE(!reg.snapshotExists("migration_77"));
+    reg.clear();
+    std::filesystem::remove_all(dir);
+}
