@@ -1027,6 +1027,11 @@ void MpiWorld::recv(int sendRank,
                     MpiMessageType messageType)
 {
     checkRanksRange(sendRank, recvRank);
+    // Sends are only recorded in mock mode: nothing will ever arrive
+    // (reference src/mpi/MpiWorld.cpp:691-696)
+    if (faabric::util::isMockMode()) {
+        return;
+    }
     // Messages of a pair arrive in order: earlier irecvs are satisfied first
     if (!tls.pendingIrecvs[sendRank].empty()) {
         drainPendingFor(sendRank, recvRank, -1);

@@ -588,7 +588,7 @@ void PointToPointBroker::sendMessage(int groupId,
     if (mustOrderMsg && seq == NO_SEQUENCE_NUM) {
         seq = getAndIncrementSentMsgCount(groupId, sendIdx, recvIdx);
     }
-    if (isThisHost(host) && !faabric::util::isMockMode()) {
+    if (isThisHost(host)) {
         deliverLocally(groupId, sendIdx, recvIdx, buffer, bufferSize, seq);
         return;
     }

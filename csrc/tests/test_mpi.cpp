@@ -625,3 +625,208 @@ TEST_CASE("mpi: spot eviction freezes an app, it thaws when capacity returns", "
     f.planner.setPolicy("bin-pack");
     faabric::mpi::getMpiWorldRegistry().clear();
 }
+
+// ---------------------------------------------------------------------------
+// Worlds spanning two hosts, driven directly through MpiWorld in mock mode:
+// the two-level algorithms send exactly the reference's remote messages
+// (strategy: reference tests/test/mpi/test_remote_mpi_worlds.cpp:34-430)
+// ---------------------------------------------------------------------------
+namespace {
+struct TwoHostWorlds
+{
+    // ranks 0,1 on this host, 2,3 on `otherHost`
+    static constexpr int worldId = 4242;
+    static constexpr int groupId = 8484;
+    static constexpr int worldSize = 4;
+    std::string thisHost = faabric::util::getSystemConfig().endpointHost;
+    std::string otherHost = "192.0.2.201";
+    faabric::Message msg = faabric::util::messageFactory("mpi", "two-hosts");
+    faabric::mpi::MpiWorld thisWorld;
+    faabric::mpi::MpiWorld otherWorld;
+
+    TwoHostWorlds()
+    {
+        faabric::util::setMockMode(true);
+        faabric::mpi::clearMpiMockedMessages();
+        msg.set_ismpi(true);
+        msg.set_mpiworldid(worldId);
+        msg.set_mpiworldsize(worldSize);
+        msg.set_groupid(groupId);
+        faabric::batch_scheduler::SchedulingDecision decision(msg.appid(), groupId);
+        for (int r = 0; r < worldSize; r++) {
+            decision.addMessage(r < 2 ? thisHost : otherHost, msg.id() + r, r, r);
+        }
+        faabric::transport::getPointToPointBroker().setUpLocalMappingsFromSchedulingDecision(decision);
+        thisWorld.initialiseFromMsg(msg);
+        otherWorld.overrideHost(otherHost);
+        otherWorld.initialiseFromMsg(msg);
+    }
+
+    ~TwoHostWorlds()
+    {
+        faabric::mpi::clearMpiMockedMessages();
+        faabric::transport::getPointToPointBroker().clear();
+        faabric::util::setMockMode(false);
+    }
+};
+}
+
+TEST_CASE("mpi: two-host worlds place ranks and leaders", "[mpi][mock]")
+{
+    TwoHostWorlds w;
+    REQUIRE_EQ(w.thisWorld.getSize(), 4);
+    REQUIRE_EQ(w.thisWorld.getId(), (int)TwoHostWorlds::worldId);
+    REQUIRE_EQ(w.thisWorld.getHostForRank(0), w.thisHost);
+    REQUIRE_EQ(w.thisWorld.getHostForRank(1), w.thisHost);
+    REQUIRE_EQ(w.thisWorld.getHostForRank(2), w.otherHost);
+    REQUIRE_EQ(w.otherWorld.getHostForRank(3), w.otherHost);
+    REQUIRE_EQ(w.thisWorld.getUser(), std::string("mpi"));
+    REQUIRE_EQ(w.thisWorld.getFunction(), std::string("two-hosts"));
+    REQUIRE(w.thisWorld.getWTime() >= 0.0);
+}
+
+TEST_CASE("mpi: sends are captured and receives return at once (mock mode)", "[mpi][mock]")
+{
+    TwoHostWorlds w;
+    std::vector<int> data = { 1, 2, 3 };
+    // Local and remote destinations alike are recorded, nothing is queued
+    w.thisWorld.send(0, 1, BYTES(data.data()), MPI_INT, 3);
+    w.thisWorld.send(0, 3, BYTES(data.data()), MPI_INT, 3, faabric::mpi::MpiMessageType::SENDRECV);
+    REQUIRE_EQ(w.thisWorld.getLocalQueueSize(0, 1), 0L);
+    auto sent = faabric::mpi::getMpiMockedMessages(0);
+    REQUIRE_EQ(sent.size(), (size_t)2);
+    REQUIRE_EQ(sent[0].worldId, (int)TwoHostWorlds::worldId);
+    REQUIRE_EQ(sent[0].sendRank, 0);
+    REQUIRE_EQ(sent[0].recvRank, 1);
+    REQUIRE_EQ(sent[0].count, 3);
+    REQUIRE_EQ(sent[0].typeSize, (int)sizeof(int));
+    REQUIRE(sent[0].messageType == faabric::mpi::MpiMessageType::NORMAL);
+    REQUIRE(memcmp(sent[0].buffer, data.data(), 3 * sizeof(int)) == 0);
+    REQUIRE_EQ(sent[1].recvRank, 3);
+    REQUIRE(sent[1].messageType == faabric::mpi::MpiMessageType::SENDRECV);
+    REQUIRE(faabric::mpi::getMpiMockedMessages(1).empty());
+    // A receive that could never be satisfied does not block
+    std::vector<int> got(3, -1);
+    w.thisWorld.recv(2, 0, BYTES(got.data()), MPI_INT, 3, nullptr);
+    REQUIRE_EQ(got[0], -1);
+    // isend is an eager send: recorded too
+    int reqId = w.thisWorld.isend(1, 2, BYTES(data.data()), MPI_INT, 3);
+    w.thisWorld.awaitAsyncRequest(reqId);
+    REQUIRE_EQ(faabric::mpi::getMpiMockedMessages(1).size(), (size_t)1);
+    // out-of-range ranks are rejected
+    REQUIRE_THROWS(w.thisWorld.send(0, 4, BYTES(data.data()), MPI_INT, 3));
+    REQUIRE_THROWS(w.thisWorld.recv(-1, 0, BYTES(got.data()), MPI_INT, 3, nullptr));
+}
+
+TEST_CASE("mpi: broadcast fans out through one leader per host (mock mode)", "[mpi][mock]")
+{
+    TwoHostWorlds w;
+    std::vector<int> data = { 7, 8, 9, 10 };
+    auto bcast = faabric::mpi::MpiMessageType::BROADCAST;
+    // Root 0: one message to its co-located rank, one to the remote leader
+    w.thisWorld.broadcast(0, 0, BYTES(data.data()), MPI_INT, 4, bcast);
+    auto fromRoot = faabric::mpi::getMpiMockedMessages(0);
+    REQUIRE_EQ(fromRoot.size(), (size_t)2);
+    std::set<int> dests = { fromRoot[0].recvRank, fromRoot[1].recvRank };
+    REQUIRE(dests == (std::set<int>{ 1, 2 }));
+    REQUIRE(fromRoot[0].messageType == bcast);
+    // The remote leader forwards to its host, the leaf forwards nothing
+    w.otherWorld.broadcast(0, 2, BYTES(data.data()), MPI_INT, 4, bcast);
+    auto fromLeader = faabric::mpi::getMpiMockedMessages(2);
+    REQUIRE_EQ(fromLeader.size(), (size_t)1);
+    REQUIRE_EQ(fromLeader[0].recvRank, 3);
+    w.otherWorld.broadcast(0, 3, BYTES(data.data()), MPI_INT, 4, bcast);
+    REQUIRE(faabric::mpi::getMpiMockedMessages(3).empty());
+    w.thisWorld.broadcast(0, 1, BYTES(data.data()), MPI_INT, 4, bcast);
+    REQUIRE(faabric::mpi::getMpiMockedMessages(1).empty());
+
+    // A root that is not its host's lowest rank still feeds each host once
+    faabric::mpi::clearMpiMockedMessages();
+    w.otherWorld.broadcast(3, 3, BYTES(data.data()), MPI_INT, 4, bcast);
+    auto fromThree = faabric::mpi::getMpiMockedMessages(3);
+    REQUIRE_EQ(fromThree.size(), (size_t)2);
+    dests = { fromThree[0].recvRank, fromThree[1].recvRank };
+    REQUIRE(dests == (std::set<int>{ 0, 2 }));
+}
+
+TEST_CASE("mpi: reduce, gather and barrier go through the local leader (mock mode)", "[mpi][mock]")
+{
+    TwoHostWorlds w;
+    // Remote host: rank 3 hands its data to leader 2, which sends ONE message
+    // to the root
+    std::vector<int> three = { 30, 31 }, two = { 20, 21 };
+    w.otherWorld.reduce(3, 0, BYTES(three.data()), nullptr, MPI_INT, 2, MPI_SUM);
+    auto fromLeaf = faabric::mpi::getMpiMockedMessages(3);
+    REQUIRE_EQ(fromLeaf.size(), (size_t)1);
+    REQUIRE_EQ(fromLeaf[0].recvRank, 2);
+    REQUIRE(fromLeaf[0].messageType == faabric::mpi::MpiMessageType::REDUCE);
+    w.otherWorld.reduce(2, 0, BYTES(two.data()), nullptr, MPI_INT, 2, MPI_SUM);
+    auto fromLeader = faabric::mpi::getMpiMockedMessages(2);
+    REQUIRE_EQ(fromLeader.size(), (size_t)1);
+    REQUIRE_EQ(fromLeader[0].recvRank, 0);
+    REQUIRE_EQ(fromLeader[0].count, 2);
+    // the leader's own send buffer is untouched
+    REQUIRE(two[0] == 20 && two[1] == 21);
+    // Root's host: the co-located rank sends straight to the root
+    w.thisWorld.reduce(1, 0, BYTES(two.data()), nullptr, MPI_INT, 2, MPI_SUM);
+    auto fromOne = faabric::mpi::getMpiMockedMessages(1);
+    REQUIRE_EQ(fromOne.size(), (size_t)1);
+    REQUIRE_EQ(fromOne[0].recvRank, 0);
+
+    // gather: the leader packs its host's chunks into one message
+    faabric::mpi::clearMpiMockedMessages();
+    w.otherWorld.gather(3, 0, BYTES(three.data()), MPI_INT, 2, nullptr, MPI_INT, 2);
+    fromLeaf = faabric::mpi::getMpiMockedMessages(3);
+    REQUIRE_EQ(fromLeaf.size(), (size_t)1);
+    REQUIRE_EQ(fromLeaf[0].recvRank, 2);
+    REQUIRE_EQ(fromLeaf[0].count, 2);
+    w.otherWorld.gather(2, 0, BYTES(two.data()), MPI_INT, 2, nullptr, MPI_INT, 2);
+    auto packed = faabric::mpi::getMpiMockedMessages(2);
+    REQUIRE_EQ(packed.size(), (size_t)1);
+    REQUIRE_EQ(packed[0].recvRank, 0);
+    REQUIRE_EQ(packed[0].count, 4);
+    REQUIRE(((int*)packed[0].buffer)[0] == 20 && ((int*)packed[0].buffer)[1] == 21);
+
+    // barrier: everyone joins at rank 0 with an empty message
+    faabric::mpi::clearMpiMockedMessages();
+    w.otherWorld.barrier(3);
+    auto join = faabric::mpi::getMpiMockedMessages(3);
+    REQUIRE(!join.empty());
+    REQUIRE_EQ(join[0].recvRank, 0);
+    REQUIRE_EQ(join[0].count, 0);
+    REQUIRE(join[0].messageType == faabric::mpi::MpiMessageType::BARRIER_JOIN);
+}
+
+TEST_CASE("mpi: cartesian topology through the world API", "[mpi]")
+{
+    TwoHostWorlds w;
+    // 2 x 2 periodic grid
+    int dims[2] = { 2, 2 };
+    int periods[2] = { 0, 0 };
+    int coords[2] = { -1, -1 };
+    w.thisWorld.getCartesianRank(3, 2, dims, periods, coords);
+    REQUIRE(coords[0] == 1 && coords[1] == 1);
+    REQUIRE(periods[0] == 1 && periods[1] == 1);
+    int rank = -1;
+    w.thisWorld.getRankFromCoords(&rank, coords);
+    REQUIRE_EQ(rank, 3);
+    int src = -1, dst = -1;
+    w.thisWorld.shiftCartesianCoords(0, 0, 1, &src, &dst);
+    REQUIRE(src == 2 && dst == 2);
+    w.thisWorld.shiftCartesianCoords(0, 1, 1, &src, &dst);
+    REQUIRE(src == 1 && dst == 1);
+    // zero displacement: both ends are the rank itself
+    w.thisWorld.shiftCartesianCoords(1, 1, 0, &src, &dst);
+    REQUIRE(src == 1 && dst == 1);
+    // 4 x 1
+    int dims41[2] = { 4, 1 };
+    w.thisWorld.getCartesianRank(2, 2, dims41, periods, coords);
+    REQUIRE(coords[0] == 2 && coords[1] == 0);
+    // wrong grid size / more than two real dimensions
+    int bad[2] = { 3, 2 };
+    REQUIRE_THROWS(w.thisWorld.getCartesianRank(0, 2, bad, periods, coords));
+    int three[3] = { 2, 1, 2 };
+    int periods3[3] = { 0, 0, 0 };
+    int coords3[3] = { 0, 0, 0 };
+    REQUIRE_THROWS(w.thisWorld.getCartesianRank(0, 3, three, periods3, coords3));
+}

@@ -364,6 +364,134 @@ TEST_CASE("ptp: group locks, barrier and notify", "[transport][ptp]")
     group->localUnlock();
 }
 
+TEST_CASE("ptp: groups appear with their mappings, ports and host sets", "[transport][ptp]")
+{
+    PtpFixture f;
+    faabric::util::setMockMode(true);
+    clearSentMessages();
+    int appId = 41, groupId = 42;
+    REQUIRE(!PointToPointGroup::groupExists(groupId));
+    REQUIRE_THROWS(PointToPointGroup::getGroup(groupId));
+
+    // A function that starts before its mappings arrive waits for the group
+    std::shared_ptr<PointToPointGroup> awaited;
+    std::thread waiter([&] { awaited = PointToPointGroup::getOrAwaitGroup(groupId); });
+    std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    faabric::batch_scheduler::SchedulingDecision d(appId, groupId);
+    d.addMessage(f.thisHost, 1, 0, 0);
+    d.addMessage("hostB", 2, 1, 1);
+    d.addMessage(f.thisHost, 3, 2, 2);
+    d.mpiPorts = { 8020, 8021, 8022 };
+    auto registered = f.broker.setUpLocalMappingsFromSchedulingDecision(d);
+    waiter.join();
+    REQUIRE(awaited != nullptr);
+    REQUIRE(awaited == PointToPointGroup::getGroup(groupId));
+    REQUIRE(registered == (std::set<std::string>{ f.thisHost, "hostB" }));
+    REQUIRE(f.broker.getHostsRegisteredForGroup(groupId) == registered);
+    REQUIRE(f.broker.getIdxsRegisteredForGroup(groupId) == (std::set<int>{ 0, 1, 2 }));
+    REQUIRE_EQ(f.broker.getMpiPortForReceiver(groupId, 1), 8021);
+    REQUIRE_EQ(f.broker.getMpiPortForReceiver(groupId, 2), 8022);
+    REQUIRE_THROWS(f.broker.getMpiPortForReceiver(groupId, 7));
+    // only local set-up so far: nothing was sent anywhere
+    REQUIRE(getSentMappings().empty());
+
+    // addGroupIfNotExists keeps an existing group, creates a missing one
+    PointToPointGroup::addGroupIfNotExists(appId, groupId, 3);
+    REQUIRE(PointToPointGroup::getGroup(groupId) == awaited);
+    // (a group needs mappings: its coordinator is the host of idx 0)
+    REQUIRE_THROWS(PointToPointGroup::addGroupIfNotExists(appId, 43, 2));
+    f.broker.setUpLocalMappingsFromSchedulingDecision(f.localDecision(appId, 43, 2));
+    PointToPointGroup::clearGroup(43);
+    REQUIRE(!PointToPointGroup::groupExists(43));
+    PointToPointGroup::addGroupIfNotExists(appId, 43, 2);
+    REQUIRE(PointToPointGroup::groupExists(43));
+    f.broker.clearGroup(43);
+    REQUIRE(!PointToPointGroup::groupExists(43));
+
+    // A group spanning hosts asks the main host for its lock
+    awaited->lock(2, false);
+    auto locks = getSentLockMessages();
+    // idx 0 (the coordinator) lives here, so the request is served locally
+    REQUIRE(locks.empty());
+    REQUIRE_EQ(awaited->getLockOwner(false), 2);
+    awaited->unlock(2, false);
+    REQUIRE_EQ(awaited->getLockOwner(false), NO_LOCK_OWNER_IDX);
+
+    f.broker.clearGroup(groupId);
+    REQUIRE(f.broker.getHostsRegisteredForGroup(groupId).empty());
+    clearSentMessages();
+}
+
+TEST_CASE("ptp: lock requests travel to the coordinator's host (mocked)", "[transport][ptp]")
+{
+    PtpFixture f;
+    faabric::util::setMockMode(true);
+    clearSentMessages();
+    int appId = 51, groupId = 52;
+    faabric::batch_scheduler::SchedulingDecision d(appId, groupId);
+    d.addMessage("hostMain", 1, 0, 0);
+    d.addMessage(f.thisHost, 2, 1, 1);
+    f.broker.setUpLocalMappingsFromSchedulingDecision(d);
+    auto group = PointToPointGroup::getGroup(groupId);
+    // The grant would come back as a ptp message 0 -> 1: deliver it up front so
+    // the lock call finds it
+    uint8_t grant = 0;
+    f.broker.deliverLocally(groupId, POINT_TO_POINT_MAIN_IDX, 1, &grant, 1, -1);
+    group->lock(1, false);
+    group->unlock(1, false);
+    auto locks = getSentLockMessages();
+    REQUIRE_EQ(locks.size(), (size_t)2);
+    REQUIRE_EQ(std::get<0>(locks[0]), std::string("hostMain"));
+    REQUIRE(std::get<1>(locks[0]) == PointToPointCall::LOCK_GROUP);
+    REQUIRE_EQ(std::get<2>(locks[0]).groupid(), groupId);
+    REQUIRE_EQ(std::get<2>(locks[0]).sendidx(), 1);
+    REQUIRE(std::get<1>(locks[1]) == PointToPointCall::UNLOCK_GROUP);
+    // recursive flavour uses its own call codes
+    f.broker.deliverLocally(groupId, POINT_TO_POINT_MAIN_IDX, 1, &grant, 1, -1);
+    group->lock(1, true);
+    group->unlock(1, true);
+    locks = getSentLockMessages();
+    REQUIRE_EQ(locks.size(), (size_t)4);
+    REQUIRE(std::get<1>(locks[2]) == PointToPointCall::LOCK_GROUP_RECURSIVE);
+    REQUIRE(std::get<1>(locks[3]) == PointToPointCall::UNLOCK_GROUP_RECURSIVE);
+    clearSentMessages();
+}
+
+TEST_CASE("ptp: post-migration hook lines the new group up", "[transport][ptp]")
+{
+    PtpFixture f;
+    int appId = 61, oldGroup = 62, newGroup = 63, n = 3;
+    f.broker.setAndSendMappingsFromSchedulingDecision(f.localDecision(appId, oldGroup, n));
+    // The planner sends the new group's mappings while functions still run
+    f.broker.setAndSendMappingsFromSchedulingDecision(f.localDecision(appId, newGroup, n));
+    std::atomic<int> through{ 0 };
+    std::vector<std::thread> ts;
+    for (int i = 0; i < n; i++) {
+        ts.emplace_back([&, i] {
+            if (i == 2) {
+                // a straggler: nobody leaves the hook before it arrives
+                std::this_thread::sleep_for(std::chrono::milliseconds(100));
+                REQUIRE_EQ(through.load(), 0);
+            }
+            f.broker.postMigrationHook(newGroup, i);
+            through++;
+            f.broker.resetThreadLocalCache();
+        });
+    }
+    for (auto& t : ts) {
+        t.join();
+    }
+    REQUIRE_EQ(through.load(), n);
+    // notify count: idx 0 waits for the others
+    auto group = PointToPointGroup::getGroup(newGroup);
+    std::thread one([&] { group->notify(1); f.broker.resetThreadLocalCache(); });
+    std::thread two([&] { group->notify(2); f.broker.resetThreadLocalCache(); });
+    group->notify(POINT_TO_POINT_MAIN_IDX);
+    one.join();
+    two.join();
+    REQUIRE_EQ(group->getNotifyCount(), 0);
+}
+
 #include <faabric/util/fault.h>
 
 TEST_CASE("fault injection: drop, delay and fail RPCs", "[transport][fault]")
