@@ -58,8 +58,12 @@ size_t TestExecutor::getMaxMemorySize()
     return MAX_MEMORY;
 }
 
+std::atomic<int> TestExecutor::resetCount{ 0 };
+std::atomic<int> TestExecutor::restoreCount{ 0 };
+
 void TestExecutor::restore(const std::string& snapshotKey)
 {
+    restoreCount++;
     auto snap = reg.getSnapshot(snapshotKey);
     setMemorySize(snap->getSize());
     snap->mapToMemory({ memory.get(), snap->getSize() });
@@ -67,6 +71,7 @@ void TestExecutor::restore(const std::string& snapshotKey)
 
 void TestExecutor::reset(faabric::Message& msg)
 {
+    resetCount++;
     Executor::reset(msg);
 }
 

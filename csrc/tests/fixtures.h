@@ -21,6 +21,7 @@
 #include <faabric/util/func.h>
 #include <faabric/util/testing.h>
 
+#include <atomic>
 #include <functional>
 #include <map>
 
@@ -50,6 +51,10 @@ class TestExecutor : public faabric::executor::Executor
     void restore(const std::string& snapshotKey) override;
 
     void reset(faabric::Message& msg) override;
+
+    // Hook bookkeeping across all test executors
+    static std::atomic<int> resetCount;
+    static std::atomic<int> restoreCount;
 
     faabric::util::MemoryRegion memory;
     size_t memorySize = 0;

@@ -3,6 +3,8 @@
 // tests/test/executor/*.cpp, tests/test/endpoint/*.cpp)
 #include "fixtures.h"
 
+#include <numeric>
+
 #include <faabric/endpoint/FaabricEndpoint.h>
 #include <faabric/planner/PlannerEndpointHandler.h>
 #include <faabric/transport/common.h>
@@ -174,6 +176,112 @@ TEST_CASE("planner: executors are reused and reaped", "[planner][executor]")
     std::this_thread::sleep_for(std::chrono::milliseconds(40));
     REQUIRE_EQ(f.sch.reapStaleExecutors(), 3);
     REQUIRE_EQ(f.sch.getFunctionExecutorCount(req->messages(0)), 0);
+}
+
+// Executor hooks and bookkeeping (strategy: reference
+// tests/test/executor/test_executor.cpp)
+TEST_CASE("executor: reset after functions, not threads; no restore on one host", "[executor]")
+{
+    ClusterFixture f(6);
+    TestExecutor::resetCount = 0;
+    TestExecutor::restoreCount = 0;
+    auto req = faabric::util::batchExecFactory("demo", "echo", 3);
+    f.plannerCli.callFunctions(req);
+    f.awaitBatch(req);
+    // the hook runs after the result is published: give it a moment
+    for (int i = 0; i < 100 && TestExecutor::resetCount.load() < 3; i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    REQUIRE_EQ(TestExecutor::resetCount.load(), 3);
+    REQUIRE_EQ(TestExecutor::restoreCount.load(), 0);
+
+    // A THREADS batch on the main host shares memory: neither hook runs
+    std::atomic<int> ran{ 0 };
+    registerTestFunction("demo", "forker", [&](auto* exec, int, int idx, auto req) {
+        auto& msg = req->messages(idx);
+        auto threads = faabric::util::batchExecFactory("demo", "worker-thread", 2);
+        threads->set_type(faabric::BatchExecuteRequest::THREADS);
+        faabric::util::updateBatchExecAppId(threads, msg.appid());
+        for (int i = 0; i < 2; i++) {
+            threads->mutable_messages(i)->set_appidx(i + 1);
+            threads->mutable_messages(i)->set_groupidx(i + 1);
+        }
+        TestExecutor::resetCount = 0;
+        auto results = exec->executeThreads(threads, {});
+        int rc = 0;
+        for (auto& [id, ret] : results) {
+            rc += ret;
+        }
+        return rc;
+    });
+    registerTestFunction("demo", "worker-thread", [&](auto*, int, int, auto) {
+        ran++;
+        return 0;
+    });
+    auto forkReq = faabric::util::batchExecFactory("demo", "forker", 1);
+    f.plannerCli.callFunctions(forkReq);
+    auto res = f.awaitResult(forkReq->messages(0), 20000);
+    REQUIRE_EQ(res.returnvalue(), 0);
+    REQUIRE_EQ(ran.load(), 2);
+    REQUIRE_EQ(TestExecutor::restoreCount.load(), 0);
+    // only the forker itself is reset, once it returns
+    for (int i = 0; i < 100 && TestExecutor::resetCount.load() < 1; i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    REQUIRE_EQ(TestExecutor::resetCount.load(), 1);
+}
+
+TEST_CASE("executor: claims, chained messages and pool limits", "[executor]")
+{
+    ClusterFixture f(4);
+    auto msg = faabric::util::messageFactory("demo", "direct");
+    auto exec = std::make_shared<TestExecutor>(msg);
+    // claim protocol
+    REQUIRE(exec->tryClaim());
+    REQUIRE(!exec->tryClaim());
+    exec->releaseClaim();
+    // (an executor counts as busy from claim to release, not only while its
+    // pool threads run tasks as in the reference)
+    REQUIRE(!exec->isExecuting());
+    REQUIRE(exec->tryClaim());
+    REQUIRE(exec->isExecuting());
+    REQUIRE(exec->getMillisSinceLastExec() >= 0);
+
+    // chained-message registry
+    auto chained = faabric::util::messageFactory("demo", "child");
+    chained.set_inputdata("payload");
+    exec->addChainedMessage(chained);
+    REQUIRE_EQ(exec->getChainedMessage(chained.id()).inputdata(), std::string("payload"));
+    REQUIRE(exec->getChainedMessageIds() == (std::set<unsigned int>{ (unsigned int)chained.id() }));
+    REQUIRE_THROWS(exec->getChainedMessage(chained.id() + 1));
+
+    // memory view and growth
+    size_t before = exec->getMemoryView().size();
+    exec->setMemorySize(before + faabric::util::HOST_PAGE_SIZE);
+    REQUIRE_EQ(exec->getMemoryView().size(), before + faabric::util::HOST_PAGE_SIZE);
+    REQUIRE(exec->getMaxMemorySize() >= exec->getMemoryView().size());
+
+    // More concurrent functions than pool threads cannot be placed (threads
+    // of one app share pool threads by app idx instead)
+    int pool = faabric::util::getUsableCores();
+    std::atomic<bool> release{ false };
+    std::atomic<int> held{ 0 };
+    registerTestFunction("demo", "hold", [&](auto*, int, int, auto) {
+        held++;
+        while (!release.load()) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
+        return 0;
+    });
+    auto tooMany = faabric::util::batchExecFactory("demo", "hold", pool + 1);
+    std::vector<int> idxs(pool + 1);
+    std::iota(idxs.begin(), idxs.end(), 0);
+    REQUIRE_THROWS(exec->executeTasks(idxs, tooMany));
+    release = true;
+    exec->joinThreadPool();
+    REQUIRE_EQ(held.load(), pool);
+    exec->shutdown();
+    REQUIRE(exec->isShutdown());
 }
 
 TEST_CASE("planner: chained calls build an exec graph", "[planner]")

@@ -233,6 +233,103 @@ TEST_CASE("state: shared-memory mapping and locks", "[state]")
     REQUIRE_THROWS(ghost->get());
 }
 
+TEST_CASE("state: chunk bounds, dirty flags, masks and lazy pulls", "[state]")
+{
+    StateFixture f;
+    const size_t page = faabric::util::HOST_PAGE_SIZE;
+    // Value smaller than its page-rounded backing store
+    const size_t size = page + 100;
+    auto mainKv = f.mainState.getKV("demo", "bounds", size);
+    REQUIRE_EQ(mainKv->size(), size);
+    REQUIRE_EQ(mainKv->getSharedMemorySize(), 2 * page);
+    std::vector<uint8_t> values(size, 5);
+    mainKv->set(values.data());
+    // A chunk may run past the value, up to the end of the allocation...
+    std::vector<uint8_t> tail(50, 7);
+    mainKv->setChunk((long)(2 * page - 50), tail.data(), 50);
+    // ...but not past it
+    REQUIRE_THROWS(mainKv->setChunk((long)(2 * page - 49), tail.data(), 50));
+    REQUIRE_THROWS(mainKv->getChunk((long)(2 * page), 1));
+
+    // all chunks tile the value in streaming-size pieces
+    const size_t big = 2 * STATE_STREAMING_CHUNK_SIZE + 10;
+    auto bigKv = f.mainState.getKV("demo", "tiles", big);
+    std::vector<uint8_t> bigValues(big);
+    for (size_t i = 0; i < big; i++) {
+        bigValues[i] = (uint8_t)(i % 251);
+    }
+    bigKv->set(bigValues.data());
+    auto chunks = bigKv->getAllChunks();
+    REQUIRE_EQ(chunks.size(), (size_t)3);
+    REQUIRE_EQ(chunks[0].offset, 0L);
+    REQUIRE_EQ(chunks[1].offset, (long)STATE_STREAMING_CHUNK_SIZE);
+    REQUIRE_EQ(chunks[2].length, (size_t)10);
+    REQUIRE_EQ(chunks[2].data[0], bigValues[2 * STATE_STREAMING_CHUNK_SIZE]);
+
+    // Replica on another host: lazy get pulls once, pull() always re-pulls
+    State other("hostX");
+    auto replica = other.getKV("demo", "tiles", big);
+    std::vector<uint8_t> got(big, 0);
+    replica->get(got.data());
+    REQUIRE(got == bigValues);
+    uint8_t nine = 9;
+    bigKv->setChunk(5, &nine, 1);
+    replica->get(got.data());
+    REQUIRE_EQ(got[5], bigValues[5]); // still the first pull
+    replica->pull();
+    replica->get(got.data());
+    REQUIRE_EQ(got[5], 9);
+
+    // A fresh replica mapped into memory is NOT pulled by the mapping
+    auto mapped = State("hostY").getKV("demo", "tiles", big);
+    auto region = faabric::util::allocatePrivateMemory(faabric::util::getRequiredHostPages(big) * faabric::util::HOST_PAGE_SIZE);
+    mapped->mapSharedMemory(region.get(), 0, (long)faabric::util::getRequiredHostPages(big));
+    REQUIRE_EQ(region[100], 0);
+    mapped->unmapSharedMemory(region.get());
+
+    // Pushes are no-ops unless something is dirty
+    auto quiet = State("hostZ").getKV("demo", "tiles", big);
+    quiet->get(got.data());
+    quiet->pushFull();
+    quiet->pushPartial();
+    REQUIRE_EQ(*bigKv->getChunk(5, 1), 9);
+    // Writing through a mapped pointer needs an explicit flag
+    uint8_t* raw = quiet->get();
+    raw[10] = 77;
+    raw[20] = 78;
+    quiet->pushPartial();
+    REQUIRE_EQ(*bigKv->getChunk(10, 1), bigValues[10]);
+    quiet->flagChunkDirty(10, 1);
+    quiet->pushPartial();
+    REQUIRE_EQ(*bigKv->getChunk(10, 1), 77);
+    REQUIRE_EQ(*bigKv->getChunk(20, 1), bigValues[20]);
+    quiet->flagDirty();
+    quiet->pushFull();
+    REQUIRE_EQ(*bigKv->getChunk(20, 1), 78);
+
+    // Partial push driven by a mask held in another KV
+    auto mask = State("hostZ").getKV("demo", "tiles-mask", big);
+    std::vector<uint8_t> maskBytes(big, 0);
+    std::fill(maskBytes.begin() + 1000, maskBytes.begin() + 1010, 1);
+    mask->set(maskBytes.data());
+    raw[1005] = 55;
+    raw[2000] = 56; // outside the mask: stays local
+    quiet->pushPartialMask(mask); // clean value: nothing goes out
+    REQUIRE_EQ(*bigKv->getChunk(1005, 1), bigValues[1005]);
+    quiet->flagDirty();
+    quiet->pushPartialMask(mask);
+    REQUIRE_EQ(*bigKv->getChunk(1005, 1), 55);
+    REQUIRE_EQ(*bigKv->getChunk(2000, 1), bigValues[2000]);
+    auto wrongMask = State("hostZ").getKV("demo", "small-mask", 10);
+    REQUIRE_THROWS(quiet->pushPartialMask(wrongMask));
+
+    // Local deletion forgets the replica, not the value
+    size_t before = f.mainState.getKVCount();
+    f.mainState.deleteKVLocally("demo", "bounds");
+    REQUIRE_EQ(f.mainState.getKVCount(), before - 1);
+    REQUIRE_EQ(f.mainState.getThisIP(), faabric::util::getSystemConfig().endpointHost);
+}
+
 TEST_CASE("state: redis-backed mode", "[state][redis]")
 {
     StateFixture f;
