@@ -20,9 +20,13 @@ void printStackTrace(void* contextR)
     ::backtrace_symbols_fd(frames, n, STDERR_FILENO);
 }
 
-static void crashHandler(int sig) noexcept
+static void crashHandler(int sig, siginfo_t* info, void*) noexcept
 {
-    fprintf(stderr, "Caught fatal signal %d\n", sig);
+    if (info != nullptr && (sig == SIGSEGV || sig == SIGBUS)) {
+        fprintf(stderr, "Caught fatal signal %d (fault address %p)\n", sig, info->si_addr);
+    } else {
+        fprintf(stderr, "Caught fatal signal %d\n", sig);
+    }
     printStackTrace();
     if (sig != TEST_SIGNAL) {
         ::signal(sig, SIG_DFL);
@@ -34,10 +38,10 @@ static void crashHandler(int sig) noexcept
 static void installHandler(int s)
 {
     struct sigaction sa{};
-    sa.sa_handler = crashHandler;
+    sa.sa_sigaction = crashHandler;
     sigemptyset(&sa.sa_mask);
     // Run on the alternate stack so stack overflows still get a trace
-    sa.sa_flags = SA_ONSTACK;
+    sa.sa_flags = SA_ONSTACK | SA_SIGINFO;
     if (::sigaction(s, &sa, nullptr) != 0) {
         SPDLOG_WARN("Could not install crash handler for signal {}", s);
     }
@@ -50,7 +54,7 @@ void setUpCrashHandler(int sig)
     int signals[] = { SIGSEGV, SIGABRT, SIGILL, SIGFPE, SIGBUS };
     if (sig >= 0) {
         if (sig == TEST_SIGNAL) {
-            crashHandler(sig);
+            crashHandler(sig, nullptr, nullptr);
             return;
         }
         installHandler(sig);

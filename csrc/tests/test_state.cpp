@@ -213,7 +213,9 @@ TEST_CASE("state: shared-memory mapping and locks", "[state]")
     REQUIRE_EQ(region[10], 3);
     region[10] = 9; // writes through to the KV
     REQUIRE_EQ(*kv->getChunk(10, 1), 9);
-    kv->unmapSharedMemory(region.get());
+    // the KV unmapped the range: the region must not unmap it again later
+    // (by then the addresses may belong to somebody else)
+    kv->unmapSharedMemory(region.release());
 
     // Write lock excludes readers
     kv->lockWrite();
@@ -285,7 +287,7 @@ TEST_CASE("state: chunk bounds, dirty flags, masks and lazy pulls", "[state]")
     auto region = faabric::util::allocatePrivateMemory(faabric::util::getRequiredHostPages(big) * faabric::util::HOST_PAGE_SIZE);
     mapped->mapSharedMemory(region.get(), 0, (long)faabric::util::getRequiredHostPages(big));
     REQUIRE_EQ(region[100], 0);
-    mapped->unmapSharedMemory(region.get());
+    mapped->unmapSharedMemory(region.release());
 
     // Pushes are no-ops unless something is dirty
     auto quiet = State("hostZ").getKV("demo", "tiles", big);
