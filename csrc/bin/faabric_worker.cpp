@@ -353,6 +353,57 @@ static void registerFunctions()
         return 0;
     });
 
+    // One-sided communication: puts and gets to every rank of the world, in
+    // this process (direct copies) or another one (shipped at the fence)
+    mpiFunction("rma", [](int rank, int size, faabric::Message& msg) {
+        const int n = size + 2;
+        std::vector<long> window(n, -1);
+        MPI_Win win = nullptr;
+        MPI_Win_create(window.data(), n * sizeof(long), sizeof(long), MPI_INFO_NULL, MPI_COMM_WORLD, &win);
+        MPI_Win_fence(0, win);
+        long mine = 100 + rank;
+        for (int t = 0; t < size; t++) {
+            MPI_Put(&mine, 1, MPI_LONG, t, rank, 1, MPI_LONG, win);
+        }
+        MPI_Win_fence(0, win);
+        for (int r = 0; r < size; r++) {
+            EXPECT(window[r] == 100 + r);
+        }
+        // second epoch: everybody reads everybody's last-but-one slot and
+        // streams a large strip into the next rank
+        window[size] = 9000 + rank;
+        const int big = 300000;
+        std::vector<long> strip(big, rank), landing(big, -1);
+        MPI_Win bigWin = nullptr;
+        MPI_Win_create(landing.data(), big * sizeof(long), sizeof(long), MPI_INFO_NULL, MPI_COMM_WORLD, &bigWin);
+        MPI_Win_fence(0, win);
+        MPI_Win_fence(0, bigWin);
+        std::vector<long> seen(size, 0);
+        for (int t = 0; t < size; t++) {
+            MPI_Get(&seen[t], 1, MPI_LONG, t, size, 1, MPI_LONG, win);
+        }
+        MPI_Put(strip.data(), big, MPI_LONG, (rank + 1) % size, 0, big, MPI_LONG, bigWin);
+        MPI_Win_fence(0, bigWin);
+        MPI_Win_fence(0, win);
+        for (int t = 0; t < size; t++) {
+            EXPECT(seen[t] == 9000 + t);
+        }
+        int left = (rank + size - 1) % size;
+        EXPECT(landing[0] == left && landing[big - 1] == left);
+        MPI_Win_free(&bigWin);
+        MPI_Win_free(&win);
+        // shared windows need one address space
+        long* shared = nullptr;
+        MPI_Win sharedWin = nullptr;
+        int rc = MPI_Win_allocate_shared(64, 8, MPI_INFO_NULL, MPI_COMM_WORLD, &shared, &sharedWin);
+        bool oneProcess = faabric::mpi::getMpiWorldRegistry().getWorld(msg.mpiworldid()).allRanksLocal();
+        EXPECT((rc == MPI_SUCCESS) == oneProcess);
+        if (rc == MPI_SUCCESS) {
+            MPI_Win_free(&sharedWin);
+        }
+        return 0;
+    });
+
     // Iterates with an all-reduce per loop; halfway through every rank hits a
     // migration point.  Ranks that are moved resume from the loop index they
     // carried over, with their memory restored from the snapshot.

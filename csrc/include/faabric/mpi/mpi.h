@@ -17,6 +17,10 @@ extern "C"
 #define MPI_SUCCESS 0
 #define MPI_ERR_OTHER 1
 #define MPI_ERR_NO_MEM 2
+#define MPI_ERR_OP 3
+#define MPI_ERR_WIN 4
+#define MPI_ERR_RANK 5
+#define MPI_ERR_ARG 6
 #define MPI_MAX_OBJECT_NAME 128
 
     /* ---- opaque-ish handle structs ---- */
@@ -47,6 +51,10 @@ extern "C"
         int size;
         void* basePtr;
         int dispUnit;
+        /* window id inside the world (addition to the reference's layout) */
+        int id;
+        /* memory allocated by MPI_Win_allocate_shared, released by Win_free */
+        void* ownedPtr;
     };
     struct faabric_op_t
     {

@@ -46,6 +46,9 @@ enum MpiMessageType : int32_t
     // Special message types for async messaging
     UNACKED_MPI_MESSAGE = 13,
     HANDSHAKE = 14,
+    // One-sided operations shipped to another worker process at a fence
+    RMA_OP = 15,
+    RMA_DATA = 16,
 };
 
 // POD descriptor travelling through the per-pair queues / sockets (40 bytes,
@@ -115,6 +118,23 @@ typedef faabric::util::SpinLockQueue<MpiMessage> InMemoryMpiQueue;
 #else
 typedef faabric::util::FixedCapacityQueue<MpiMessage> InMemoryMpiQueue;
 #endif
+
+// ---- user-defined reduction operations (MPI_Op_create) ----
+// The reference declares MPI_Op_create and throws; here user functions run on
+// the host path (device buffers are staged).  Non-commutative operations are
+// folded in rank order at the root.
+constexpr int FAABRIC_OP_USER_BASE = 1000;
+
+int registerUserOp(MPI_User_function* fn, bool commutes);
+
+bool unregisterUserOp(int opId);
+
+bool getUserOp(int opId, MPI_User_function** fn, bool* commutes);
+
+inline bool isUserOp(const faabric_op_t* op)
+{
+    return op != nullptr && op->id >= FAABRIC_OP_USER_BASE;
+}
 
 // Messages "sent" to remote ranks in mock mode
 std::vector<MpiMessage> getMpiMockedMessages(int sendRank);
@@ -311,6 +331,30 @@ class MpiWorld
 
     void barrier(int thisRank);
 
+    // ---- one-sided communication (MPI_Win_*, MPI_Put / MPI_Get) ----
+    // The reference declares these and throws (mpi_native.cpp:649-683).  Here
+    // a target in this process is written / read directly (host memory, or
+    // device memory through peer access), a target in another worker process
+    // has its operations shipped and applied at the closing fence.
+    // Collective; every rank gets the same window id
+    int winCreate(int rank, void* base, int64_t sizeBytes, int dispUnit);
+
+    // Collective
+    void winFree(int rank, int winId);
+
+    // Collective: completes every operation of the epoch at origin and target
+    void winFence(int rank, int winId);
+
+    void winPut(int rank, int winId, const uint8_t* origin, size_t bytes, int targetRank, int64_t targetDisp);
+
+    void winGet(int rank, int winId, uint8_t* origin, size_t bytes, int targetRank, int64_t targetDisp);
+
+    // Window segment of `rank`; false if the window is unknown
+    bool winQuery(int winId, int rank, void** base, int64_t* sizeBytes, int* dispUnit);
+
+    // True if every rank of the world lives in this process
+    bool allRanksLocal();
+
     // ---- introspection / tests ----
     std::shared_ptr<InMemoryMpiQueue> getLocalQueue(int sendRank, int recvRank);
 
@@ -366,6 +410,36 @@ class MpiWorld
     bool isLocalRank(int rank) { return hostForRank.at(rank) == thisHost; }
     int getLocalLeader() { return leaderForHost.at(thisHost); }
 
+    // ---- one-sided windows ----
+    struct RmaOp
+    {
+        int kind; // 0 = put, 1 = get
+        int target;
+        uint64_t dispBytes;
+        uint64_t bytes;
+        uint8_t* origin;
+    };
+    struct RmaWindow
+    {
+        std::mutex mx;
+        bool filled = false;
+        int freed = 0;
+        std::vector<uint64_t> bases;
+        std::vector<int64_t> sizes;
+        std::vector<int32_t> dispUnits;
+        // operations queued for other processes, one list per ORIGIN rank
+        // (only that rank's thread touches its list)
+        std::vector<std::vector<RmaOp>> pending;
+    };
+    std::mutex windowsMx;
+    std::map<int, std::shared_ptr<RmaWindow>> windows;
+    // windows created so far by each rank (collective order => same ids)
+    std::vector<int> windowsCreated;
+    std::shared_ptr<RmaWindow> getWindow(int winId);
+    uint8_t* winTargetPtr(RmaWindow& w, int targetRank, int64_t targetDisp, size_t bytes);
+    void rmaSendOps(RmaWindow& w, int rank, int peer);
+    void rmaRecvOps(RmaWindow& w, int rank, int peer, int nOps);
+
     // ---- local queues (size x size, lazily created) ----
     std::vector<std::shared_ptr<InMemoryMpiQueue>> localQueues;
     void initLocalQueues();
@@ -416,6 +490,8 @@ class MpiWorld
         void barrier(int timeoutMs);
     };
     std::unique_ptr<HostCollective> hostCollective;
+    // Rank-ordered fold at the root for non-commutative user operations
+    void orderedReduce(int sendRank, int recvRank, uint8_t* sendBuffer, uint8_t* recvBuffer, faabric_datatype_t* datatype, int count, faabric_op_t* operation);
     bool sharedMemoryEligible(size_t bytes) const { return hostCollective != nullptr && bytes >= 32 * 1024; }
     void sharedBroadcast(int root, int rank, uint8_t* buffer, size_t bytes);
     void sharedAllGather(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t sendBytes);

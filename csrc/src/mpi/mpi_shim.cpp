@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -553,12 +554,23 @@ int MPI_Type_commit(MPI_Datatype* type)
 
 int MPI_Op_create(MPI_User_function* user_fn, int commute, MPI_Op* op)
 {
-    return notImplemented("MPI_Op_create");
+    SPDLOG_TRACE("MPI - MPI_Op_create");
+    // (the reference throws "not implemented", mpi_native.cpp:764-772)
+    *op = new faabric_op_t{ registerUserOp(user_fn, commute != 0) };
+    return MPI_SUCCESS;
 }
 
 int MPI_Op_free(MPI_Op* op)
 {
-    return notImplemented("MPI_Op_free");
+    SPDLOG_TRACE("MPI - MPI_Op_free");
+    if (op == nullptr || *op == nullptr || !isUserOp(*op)) {
+        // predefined operations cannot be freed
+        return MPI_ERR_OP;
+    }
+    unregisterUserOp((*op)->id);
+    delete *op;
+    *op = MPI_OP_NULL;
+    return MPI_SUCCESS;
 }
 
 int MPI_Alloc_mem(MPI_Aint size, MPI_Info info, void* baseptr)
@@ -646,46 +658,133 @@ int MPI_Win_get_attr(MPI_Win win, int win_keyval, void* attribute_val, int* flag
     return MPI_SUCCESS;
 }
 
+// ---- one-sided communication.  The reference declares these and throws
+// (tests/dist/mpi/mpi_native.cpp:649-683); see MpiWorld::winCreate. ----
 int MPI_Win_fence(int assert, MPI_Win win)
 {
-    return notImplemented("MPI_Win_fence");
+    SPDLOG_TRACE("MPI - MPI_Win_fence");
+    if (win == nullptr) {
+        return MPI_ERR_WIN;
+    }
+    getExecutingWorld().winFence(executingContext.getRank(), win->id);
+    return MPI_SUCCESS;
 }
 
 int MPI_Get(void* origin_addr, int origin_count, MPI_Datatype origin_datatype, int target_rank,
             MPI_Aint target_disp, int target_count, MPI_Datatype target_datatype, MPI_Win win)
 {
-    return notImplemented("MPI_Get");
+    SPDLOG_TRACE("MPI - MPI_Get");
+    if (win == nullptr) {
+        return MPI_ERR_WIN;
+    }
+    const size_t bytes = (size_t)origin_count * origin_datatype->size;
+    if (bytes != (size_t)target_count * target_datatype->size) {
+        return MPI_ERR_ARG;
+    }
+    getExecutingWorld().winGet(executingContext.getRank(), win->id, (uint8_t*)origin_addr, bytes, target_rank, target_disp);
+    return MPI_SUCCESS;
 }
 
 int MPI_Put(const void* origin_addr, int origin_count, MPI_Datatype origin_datatype, int target_rank,
             MPI_Aint target_disp, int target_count, MPI_Datatype target_datatype, MPI_Win win)
 {
-    return notImplemented("MPI_Put");
+    SPDLOG_TRACE("MPI - MPI_Put");
+    if (win == nullptr) {
+        return MPI_ERR_WIN;
+    }
+    const size_t bytes = (size_t)origin_count * origin_datatype->size;
+    if (bytes != (size_t)target_count * target_datatype->size) {
+        return MPI_ERR_ARG;
+    }
+    getExecutingWorld().winPut(executingContext.getRank(), win->id, (const uint8_t*)origin_addr, bytes, target_rank, target_disp);
+    return MPI_SUCCESS;
 }
 
 int MPI_Win_free(MPI_Win* win)
 {
-    return notImplemented("MPI_Win_free");
+    SPDLOG_TRACE("MPI - MPI_Win_free");
+    if (win == nullptr || *win == nullptr) {
+        return MPI_ERR_WIN;
+    }
+    getExecutingWorld().winFree(executingContext.getRank(), (*win)->id);
+    if ((*win)->ownedPtr != nullptr) {
+        MPI_Free_mem((*win)->ownedPtr);
+    }
+    delete *win;
+    *win = nullptr;
+    return MPI_SUCCESS;
 }
 
 int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, MPI_Win* win)
 {
-    return notImplemented("MPI_Win_create");
+    SPDLOG_TRACE("MPI - MPI_Win_create");
+    MpiWorld& world = getExecutingWorld();
+    const int rank = executingContext.getRank();
+    int winId = world.winCreate(rank, base, (int64_t)size, disp_unit);
+    *win = new faabric_win_t{ world.getId(), rank, (int)size, base, disp_unit, winId, nullptr };
+    return MPI_SUCCESS;
 }
 
 int MPI_Win_allocate_shared(MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, void* baseptr, MPI_Win* win)
 {
-    return notImplemented("MPI_Win_allocate_shared");
+    SPDLOG_TRACE("MPI - MPI_Win_allocate_shared");
+    MpiWorld& world = getExecutingWorld();
+    if (!world.allRanksLocal()) {
+        // Load/store access needs one address space: ranks of this world
+        // live in several worker processes
+        SPDLOG_ERROR("MPI_Win_allocate_shared on a world that spans worker processes");
+        return MPI_ERR_OTHER;
+    }
+    // MPI_INFO_FAABRIC_DEVICE puts the segment in the rank's symmetric heap
+    void* mem = nullptr;
+    if (info == MPI_INFO_FAABRIC_DEVICE) {
+        int rc = MPI_Alloc_mem(size, info, &mem);
+        if (rc != MPI_SUCCESS) {
+            return rc;
+        }
+    } else {
+        // cache-line aligned, zeroed
+        size_t rounded = ((size_t)size + 63) & ~(size_t)63;
+        if (posix_memalign(&mem, 64, std::max<size_t>(rounded, 64)) != 0) {
+            return MPI_ERR_NO_MEM;
+        }
+        memset(mem, 0, std::max<size_t>(rounded, 64));
+    }
+    const int rank = executingContext.getRank();
+    int winId = world.winCreate(rank, mem, (int64_t)size, disp_unit);
+    *((void**)baseptr) = mem;
+    *win = new faabric_win_t{ world.getId(), rank, (int)size, mem, disp_unit, winId, mem };
+    return MPI_SUCCESS;
 }
 
 int MPI_Win_shared_query(MPI_Win win, int rank, MPI_Aint* size, int* disp_unit, void* baseptr)
 {
-    return notImplemented("MPI_Win_shared_query");
+    SPDLOG_TRACE("MPI - MPI_Win_shared_query");
+    if (win == nullptr) {
+        return MPI_ERR_WIN;
+    }
+    void* base = nullptr;
+    int64_t bytes = 0;
+    int unit = 0;
+    if (!getExecutingWorld().winQuery(win->id, rank, &base, &bytes, &unit)) {
+        return MPI_ERR_RANK;
+    }
+    *size = (MPI_Aint)bytes;
+    *disp_unit = unit;
+    *((void**)baseptr) = base;
+    return MPI_SUCCESS;
 }
 
 int MPI_Comm_dup(MPI_Comm comm, MPI_Comm* newcomm)
 {
-    return notImplemented("MPI_Comm_dup");
+    SPDLOG_TRACE("MPI - MPI_Comm_dup");
+    // One communication context per world: the duplicate is the same handle
+    // (the reference throws, mpi_native.cpp:686-690)
+    if (comm != MPI_COMM_WORLD) {
+        throw std::runtime_error("MPI_Comm_dup is only supported on MPI_COMM_WORLD");
+    }
+    *newcomm = comm;
+    return MPI_SUCCESS;
 }
 
 MPI_Fint MPI_Comm_c2f(MPI_Comm comm)

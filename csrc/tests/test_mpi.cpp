@@ -429,6 +429,206 @@ TEST_CASE("mpi: large host collectives copy between user buffers", "[mpi]")
     unsetenv("FAABRIC_MPI_HOST_ALLREDUCE");
 }
 
+namespace {
+// ---- user-defined operations ----
+// commutative: product modulo a prime
+void mulModFn(void* in, void* inout, int* len, MPI_Datatype*)
+{
+    auto* a = (long*)in;
+    auto* b = (long*)inout;
+    for (int i = 0; i < *len; i++) {
+        b[i] = (a[i] * b[i]) % 1000003L;
+    }
+}
+
+// associative but NOT commutative: composition of affine maps x -> a*x + b,
+// stored as consecutive (a, b) int pairs; inout = in o inout
+void composeFn(void* in, void* inout, int* len, MPI_Datatype*)
+{
+    auto* f = (int*)in;
+    auto* g = (int*)inout;
+    for (int i = 0; i + 1 < *len; i += 2) {
+        int a = f[i], b = f[i + 1], c = g[i], d = g[i + 1];
+        g[i] = a * c;
+        g[i + 1] = a * d + b;
+    }
+}
+
+int bodyUserOps(int rank, int size)
+{
+    MPI_Op mulMod = nullptr, compose = nullptr;
+    CHECK_RANK(MPI_Op_create(mulModFn, 1, &mulMod) == MPI_SUCCESS);
+    CHECK_RANK(MPI_Op_create(composeFn, 0, &compose) == MPI_SUCCESS);
+    CHECK_RANK(mulMod != nullptr && compose != nullptr && mulMod->id != compose->id);
+
+    long expectedProd = 1;
+    for (int r = 0; r < size; r++) {
+        expectedProd = (expectedProd * (r + 2)) % 1000003L;
+    }
+    // rank-ordered composition f0 o f1 o ... with f_r = ((r % 3) + 1, r + 1)
+    std::vector<std::pair<int, int>> prefix(size);
+    int ea = 1, eb = 0;
+    for (int r = 0; r < size; r++) {
+        int c = (r % 3) + 1, d = r + 1;
+        eb = ea * d + eb;
+        ea = ea * c;
+        prefix[r] = { ea, eb };
+    }
+
+    // small and large (>= 32 KiB) messages take different host paths
+    for (int n : { 6, 10000 }) {
+        std::vector<long> mine(n, rank + 2), out(n, 0);
+        MPI_Reduce(mine.data(), out.data(), n, MPI_LONG, mulMod, size - 1, MPI_COMM_WORLD);
+        if (rank == size - 1) {
+            CHECK_RANK(out[0] == expectedProd && out[n - 1] == expectedProd);
+        }
+        MPI_Allreduce(mine.data(), out.data(), n, MPI_LONG, mulMod, MPI_COMM_WORLD);
+        CHECK_RANK(out[0] == expectedProd && out[n / 2] == expectedProd);
+        CHECK_RANK(mine[0] == rank + 2);
+        MPI_Allreduce(MPI_IN_PLACE, mine.data(), n, MPI_LONG, mulMod, MPI_COMM_WORLD);
+        CHECK_RANK(mine[n - 1] == expectedProd);
+
+        std::vector<int> f(2 * n), g(2 * n, -1);
+        for (int i = 0; i < n; i++) {
+            f[2 * i] = (rank % 3) + 1;
+            f[2 * i + 1] = rank + 1;
+        }
+        MPI_Reduce(f.data(), g.data(), 2 * n, MPI_INT, compose, 1 % size, MPI_COMM_WORLD);
+        if (rank == 1 % size) {
+            CHECK_RANK(g[0] == ea && g[1] == eb);
+            CHECK_RANK(g[2 * n - 2] == ea && g[2 * n - 1] == eb);
+        }
+        std::fill(g.begin(), g.end(), -1);
+        MPI_Allreduce(f.data(), g.data(), 2 * n, MPI_INT, compose, MPI_COMM_WORLD);
+        CHECK_RANK(g[0] == ea && g[1] == eb && g[2 * n - 1] == eb);
+        // in place at the root
+        std::vector<int> h = f;
+        if (rank == 0) {
+            MPI_Reduce(MPI_IN_PLACE, h.data(), 2 * n, MPI_INT, compose, 0, MPI_COMM_WORLD);
+            CHECK_RANK(h[0] == ea && h[1] == eb);
+        } else {
+            MPI_Reduce(h.data(), nullptr, 2 * n, MPI_INT, compose, 0, MPI_COMM_WORLD);
+        }
+        // inclusive prefix in rank order
+        std::fill(g.begin(), g.end(), -1);
+        MPI_Scan(f.data(), g.data(), 2 * n, MPI_INT, compose, MPI_COMM_WORLD);
+        CHECK_RANK(g[0] == prefix[rank].first && g[1] == prefix[rank].second);
+    }
+
+    CHECK_RANK(MPI_Op_free(&mulMod) == MPI_SUCCESS && mulMod == MPI_OP_NULL);
+    CHECK_RANK(MPI_Op_free(&compose) == MPI_SUCCESS);
+    MPI_Op predefined = MPI_SUM;
+    CHECK_RANK(MPI_Op_free(&predefined) == MPI_ERR_OP);
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+}
+
+TEST_CASE("mpi: user-defined operations, commutative and rank-ordered", "[mpi]")
+{
+    runMpi("user-ops", 5, 1, bodyUserOps);
+    runMpi("user-ops-gpuhosts", 6, 3, bodyUserOps);
+    setenv("FAABRIC_MPI_HOST_ALLREDUCE", "reference", 1);
+    runMpi("user-ops-ref", 4, 1, bodyUserOps);
+    unsetenv("FAABRIC_MPI_HOST_ALLREDUCE");
+}
+
+namespace {
+// ---- one-sided communication ----
+int bodyRma(int rank, int size)
+{
+    const int right = (rank + 1) % size, left = (rank + size - 1) % size;
+    // Each rank exposes `size` slots of doubles plus a tail
+    const int n = size + 4;
+    std::vector<double> window(n, -1.0);
+    MPI_Win win = nullptr;
+    CHECK_RANK(MPI_Win_create(window.data(), n * sizeof(double), sizeof(double), MPI_INFO_NULL, MPI_COMM_WORLD, &win) == MPI_SUCCESS);
+    void* base = nullptr;
+    int flag = 0;
+    MPI_Win_get_attr(win, MPI_WIN_BASE, &base, &flag);
+    CHECK_RANK(flag == 1 && base == window.data());
+    MPI_Aint winSize = 0;
+    MPI_Win_get_attr(win, MPI_WIN_SIZE, &winSize, &flag);
+    CHECK_RANK(winSize == (MPI_Aint)(n * sizeof(double)));
+
+    MPI_Win_fence(0, win);
+    // everybody deposits its signature in slot [rank] of EVERY window
+    double mine = 100.0 + rank;
+    for (int t = 0; t < size; t++) {
+        MPI_Put(&mine, 1, MPI_DOUBLE, t, rank, 1, MPI_DOUBLE, win);
+    }
+    MPI_Win_fence(0, win);
+    for (int r = 0; r < size; r++) {
+        CHECK_RANK(window[r] == 100.0 + r);
+    }
+    CHECK_RANK(window[size] == -1.0);
+
+    // get a strip from the right neighbour, put two elements into the left's tail
+    window[size + 1] = 1000.0 + rank;
+    MPI_Win_fence(0, win);
+    std::vector<double> strip(3, 0.0);
+    MPI_Get(strip.data(), 3, MPI_DOUBLE, right, size - 1, 3, MPI_DOUBLE, win);
+    double pair[2] = { 7.0 + rank, 8.0 + rank };
+    MPI_Put(pair, 2, MPI_DOUBLE, left, size + 2, 2, MPI_DOUBLE, win);
+    MPI_Win_fence(0, win);
+    CHECK_RANK(strip[0] == 100.0 + (size - 1) && strip[1] == -1.0 && strip[2] == 1000.0 + right);
+    CHECK_RANK(window[size + 2] == 7.0 + right && window[size + 3] == 8.0 + right);
+
+    // accesses outside the target's segment are refused
+    bool threw = false;
+    try {
+        MPI_Put(pair, 2, MPI_DOUBLE, right, n - 1, 2, MPI_DOUBLE, win);
+    } catch (const std::runtime_error&) {
+        threw = true;
+    }
+    CHECK_RANK(threw);
+    CHECK_RANK(MPI_Put(pair, 2, MPI_DOUBLE, right, 0, 1, MPI_DOUBLE, win) == MPI_ERR_ARG);
+    CHECK_RANK(MPI_Win_free(&win) == MPI_SUCCESS && win == nullptr);
+
+    // Shared windows: load/store straight into a peer's segment
+    long* myShared = nullptr;
+    MPI_Win shared = nullptr;
+    CHECK_RANK(MPI_Win_allocate_shared(8 * sizeof(long), sizeof(long), MPI_INFO_NULL, MPI_COMM_WORLD, &myShared, &shared) == MPI_SUCCESS);
+    CHECK_RANK(myShared != nullptr && ((uintptr_t)myShared % 64) == 0 && myShared[3] == 0);
+    long* leftShared = nullptr;
+    MPI_Aint leftSize = 0;
+    int leftUnit = 0;
+    CHECK_RANK(MPI_Win_shared_query(shared, left, &leftSize, &leftUnit, &leftShared) == MPI_SUCCESS);
+    CHECK_RANK(leftSize == (MPI_Aint)(8 * sizeof(long)) && leftUnit == (int)sizeof(long) && leftShared != nullptr);
+    CHECK_RANK(size == 1 || leftShared != myShared);
+    CHECK_RANK(MPI_Win_shared_query(shared, size, &leftSize, &leftUnit, &leftShared) == MPI_ERR_RANK);
+    MPI_Win_shared_query(shared, left, &leftSize, &leftUnit, &leftShared);
+    MPI_Win_fence(0, shared);
+    leftShared[5] = 5000 + rank;
+    MPI_Win_fence(0, shared);
+    CHECK_RANK(myShared[5] == 5000 + right);
+    // two windows can be alive at once and keep separate ids
+    std::vector<int> small(4, rank);
+    MPI_Win second = nullptr;
+    MPI_Win_create(small.data(), 4 * sizeof(int), sizeof(int), MPI_INFO_NULL, MPI_COMM_WORLD, &second);
+    CHECK_RANK(second->id != shared->id);
+    int got = -1;
+    MPI_Win_fence(0, second);
+    MPI_Get(&got, 1, MPI_INT, right, 2, 1, MPI_INT, second);
+    MPI_Win_fence(0, second);
+    CHECK_RANK(got == right);
+    MPI_Win_free(&second);
+    MPI_Win_free(&shared);
+
+    MPI_Comm dup = nullptr;
+    CHECK_RANK(MPI_Comm_dup(MPI_COMM_WORLD, &dup) == MPI_SUCCESS && dup == MPI_COMM_WORLD);
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+}
+
+TEST_CASE("mpi: one-sided windows, put/get/fence and shared segments", "[mpi][rma]")
+{
+    runMpi("rma-local", 5, 1, bodyRma);
+    runMpi("rma-gpuhosts", 6, 3, bodyRma);
+    runMpi("rma-one", 1, 1, bodyRma);
+}
+
 TEST_CASE("mpi: point-to-point on one host", "[mpi]")
 {
     runMpi("p2p-local", 4, 1, bodyPointToPoint);

@@ -85,6 +85,7 @@ MPI_FUNCTIONS = [
     "order",
     "status-probe",
     "cart",
+    "rma",
 ]
 
 
