@@ -353,6 +353,44 @@ static void registerFunctions()
         return 0;
     });
 
+    // Sub-communicators whose members sit in different worker processes
+    mpiFunction("subcomm", [](int rank, int size, faabric::Message& msg) {
+        MPI_Comm half = nullptr;
+        MPI_Comm_split(MPI_COMM_WORLD, rank % 2, rank, &half);
+        int hRank = -1, hSize = -1;
+        MPI_Comm_rank(half, &hRank);
+        MPI_Comm_size(half, &hSize);
+        EXPECT(hRank == rank / 2);
+        EXPECT(hSize == (size + (rank % 2 == 0 ? 1 : 0)) / 2);
+        long mine = rank, sum = -1;
+        MPI_Allreduce(&mine, &sum, 1, MPI_LONG, MPI_SUM, half);
+        long expected = 0;
+        for (int r = rank % 2; r < size; r += 2) {
+            expected += r;
+        }
+        EXPECT(sum == expected);
+        std::vector<double> big(50000, hRank == 0 ? 3.5 + rank : 0.0);
+        MPI_Bcast(big.data(), (int)big.size(), MPI_DOUBLE, 0, half);
+        EXPECT(big[0] == 3.5 + rank % 2 && big.back() == 3.5 + rank % 2);
+        std::vector<int> all(hSize, -1);
+        MPI_Allgather(&rank, 1, MPI_INT, all.data(), 1, MPI_INT, half);
+        for (int i = 0; i < hSize; i++) {
+            EXPECT(all[i] == rank % 2 + 2 * i);
+        }
+        MPI_Barrier(half);
+        // ranks of this worker process
+        MPI_Comm node = nullptr;
+        MPI_Comm_split_type(MPI_COMM_WORLD, MPI_COMM_TYPE_SHARED, rank, MPI_INFO_NULL, &node);
+        int nodeSize = -1, nodeSum = 0, one = 1;
+        MPI_Comm_size(node, &nodeSize);
+        MPI_Allreduce(&one, &nodeSum, 1, MPI_INT, MPI_SUM, node);
+        EXPECT(nodeSum == nodeSize);
+        msg.set_outputdata("node of " + std::to_string(nodeSize));
+        MPI_Comm_free(&node);
+        MPI_Comm_free(&half);
+        return 0;
+    });
+
     // One-sided communication: puts and gets to every rank of the world, in
     // this process (direct copies) or another one (shipped at the fence)
     mpiFunction("rma", [](int rank, int size, faabric::Message& msg) {

@@ -13,6 +13,8 @@
 #include <faabric/util/config.h>
 #include <faabric/util/logging.h>
 
+#include "subcomm.h"
+
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -50,6 +52,7 @@ int terminateMpi()
     // Destroy the MPI world
     bool mustClear = getExecutingWorld().destroy();
     if (mustClear) {
+        clearSubCommunicators(executingContext.getWorldId());
         getMpiWorldRegistry().clearWorld(executingContext.getWorldId());
     }
     mpiFinalised = true;
@@ -73,6 +76,64 @@ static void copyAny(void* dst, const void* src, size_t bytes)
     } else {
         memcpy(dst, src, bytes);
     }
+}
+
+// ---- sub-communicators ----
+// Calls on MPI_COMM_WORLD (and cartesian views of it) take the world's fused
+// paths; anything else resolves to a SubCommunicator
+std::shared_ptr<SubCommunicator> subOf(MPI_Comm comm)
+{
+    if (comm == nullptr || comm->id == FAABRIC_COMM_WORLD) {
+        return nullptr;
+    }
+    if (comm->id == FAABRIC_COMM_NULL) {
+        throw std::runtime_error("MPI call on MPI_COMM_NULL");
+    }
+    auto sub = getSubCommunicator(comm->id);
+    if (sub == nullptr) {
+        throw std::runtime_error("Unknown communicator " + std::to_string(comm->id));
+    }
+    return sub;
+}
+
+// Rank of `comm` -> rank of the world
+int toWorldRank(MPI_Comm comm, int rank)
+{
+    auto sub = subOf(comm);
+    return sub == nullptr ? rank : sub->worldRankOf(rank);
+}
+
+void subCommOnly(MPI_Comm comm, const char* what)
+{
+    if (subOf(comm) != nullptr) {
+        throw std::runtime_error(std::string(what) + " is only implemented on MPI_COMM_WORLD");
+    }
+}
+
+// Creating calls issued so far on each parent communicator by this rank (they
+// are collective, so every member counts the same)
+thread_local std::map<int, int> commCreateSeq;
+
+// Ranks (world numbering) of a communicator, in communicator order
+std::vector<int> ranksOf(MPI_Comm comm)
+{
+    auto sub = subOf(comm);
+    if (sub != nullptr) {
+        return sub->ranks();
+    }
+    std::vector<int> all(getExecutingWorld().getSize());
+    for (int r = 0; r < (int)all.size(); r++) {
+        all[r] = r;
+    }
+    return all;
+}
+
+MPI_Comm makeCommHandle(int parentId, int seq, uint64_t discriminator, const std::vector<int>& worldRanks)
+{
+    int worldId = executingContext.getWorldId();
+    int id = deriveCommId(worldId, parentId, seq, discriminator);
+    registerSubCommunicator(id, worldId, worldRanks);
+    return new faabric_communicator_t{ id };
 }
 
 std::map<int, faabric_request_t*>& requestTable()
@@ -108,6 +169,7 @@ int MPI_Init(int* argc, char*** argv)
     }
     mpiInitialised = true;
     mpiFinalised = false;
+    commCreateSeq.clear();
     if (!resuming) {
         // Everyone lines up once the world is wired
         getExecutingWorld().barrier(executingContext.getRank());
@@ -152,6 +214,10 @@ int MPI_Get_version(int* version, int* subversion)
 int MPI_Comm_rank(MPI_Comm comm, int* rank)
 {
     SPDLOG_TRACE("MPI - MPI_Comm_rank");
+    if (auto sub = subOf(comm)) {
+        *rank = sub->commRankOf(executingContext.getRank());
+        return MPI_SUCCESS;
+    }
     *rank = executingContext.getRank();
     return MPI_SUCCESS;
 }
@@ -159,6 +225,10 @@ int MPI_Comm_rank(MPI_Comm comm, int* rank)
 int MPI_Comm_size(MPI_Comm comm, int* size)
 {
     SPDLOG_TRACE("MPI - MPI_Comm_size");
+    if (auto sub = subOf(comm)) {
+        *size = sub->size();
+        return MPI_SUCCESS;
+    }
     *size = getExecutingWorld().getSize();
     return MPI_SUCCESS;
 }
@@ -178,7 +248,7 @@ int MPI_Abort(MPI_Comm comm, int errorcode)
 int MPI_Send(const void* buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Send {} -> {}", executingContext.getRank(), dest);
-    getExecutingWorld().send(executingContext.getRank(), dest, (const uint8_t*)buf, datatype, count);
+    getExecutingWorld().send(executingContext.getRank(), toWorldRank(comm, dest), (const uint8_t*)buf, datatype, count);
     return MPI_SUCCESS;
 }
 
@@ -191,7 +261,10 @@ int MPI_Rsend(const void* buf, int count, MPI_Datatype datatype, int dest, int t
 int MPI_Recv(void* buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Status* status)
 {
     SPDLOG_TRACE("MPI - MPI_Recv {} <- {}", executingContext.getRank(), source);
-    getExecutingWorld().recv(source, executingContext.getRank(), (uint8_t*)buf, datatype, count, status);
+    getExecutingWorld().recv(toWorldRank(comm, source), executingContext.getRank(), (uint8_t*)buf, datatype, count, status);
+    if (status != MPI_STATUS_IGNORE && subOf(comm) != nullptr) {
+        status->MPI_SOURCE = source;
+    }
     return MPI_SUCCESS;
 }
 
@@ -200,16 +273,19 @@ int MPI_Sendrecv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, int 
                  MPI_Comm comm, MPI_Status* status)
 {
     SPDLOG_TRACE("MPI - MPI_Sendrecv");
-    getExecutingWorld().sendRecv((uint8_t*)sendbuf, sendcount, sendtype, dest,
-                                 (uint8_t*)recvbuf, recvcount, recvtype, source,
+    getExecutingWorld().sendRecv((uint8_t*)sendbuf, sendcount, sendtype, toWorldRank(comm, dest),
+                                 (uint8_t*)recvbuf, recvcount, recvtype, toWorldRank(comm, source),
                                  executingContext.getRank(), status);
+    if (status != MPI_STATUS_IGNORE && subOf(comm) != nullptr) {
+        status->MPI_SOURCE = source;
+    }
     return MPI_SUCCESS;
 }
 
 int MPI_Isend(const void* buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPI_Request* request)
 {
     SPDLOG_TRACE("MPI - MPI_Isend {} -> {}", executingContext.getRank(), dest);
-    int id = getExecutingWorld().isend(executingContext.getRank(), dest, (const uint8_t*)buf, datatype, count);
+    int id = getExecutingWorld().isend(executingContext.getRank(), toWorldRank(comm, dest), (const uint8_t*)buf, datatype, count);
     auto* r = new faabric_request_t{ id };
     requestTable()[id] = r;
     *request = r;
@@ -219,7 +295,7 @@ int MPI_Isend(const void* buf, int count, MPI_Datatype datatype, int dest, int t
 int MPI_Irecv(void* buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Request* request)
 {
     SPDLOG_TRACE("MPI - MPI_Irecv {} <- {}", executingContext.getRank(), source);
-    int id = getExecutingWorld().irecv(source, executingContext.getRank(), (uint8_t*)buf, datatype, count);
+    int id = getExecutingWorld().irecv(toWorldRank(comm, source), executingContext.getRank(), (uint8_t*)buf, datatype, count);
     auto* r = new faabric_request_t{ id };
     requestTable()[id] = r;
     *request = r;
@@ -287,13 +363,20 @@ int MPI_Get_count(const MPI_Status* status, MPI_Datatype datatype, int* count)
 int MPI_Probe(int source, int tag, MPI_Comm comm, MPI_Status* status)
 {
     SPDLOG_TRACE("MPI - MPI_Probe");
-    getExecutingWorld().probe(source, executingContext.getRank(), status);
+    getExecutingWorld().probe(toWorldRank(comm, source), executingContext.getRank(), status);
+    if (status != MPI_STATUS_IGNORE && subOf(comm) != nullptr) {
+        status->MPI_SOURCE = source;
+    }
     return MPI_SUCCESS;
 }
 
 int MPI_Barrier(MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Barrier");
+    if (auto sub = subOf(comm)) {
+        sub->barrier(getExecutingWorld(), executingContext.getRank());
+        return MPI_SUCCESS;
+    }
     getExecutingWorld().barrier(executingContext.getRank());
     return MPI_SUCCESS;
 }
@@ -301,6 +384,10 @@ int MPI_Barrier(MPI_Comm comm)
 int MPI_Bcast(void* buffer, int count, MPI_Datatype datatype, int root, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Bcast {} -> all", root);
+    if (auto sub = subOf(comm)) {
+        sub->broadcast(getExecutingWorld(), executingContext.getRank(), root, (uint8_t*)buffer, datatype, count);
+        return MPI_SUCCESS;
+    }
     getExecutingWorld().broadcast(root, executingContext.getRank(), (uint8_t*)buffer, datatype, count, MpiMessageType::BROADCAST);
     return MPI_SUCCESS;
 }
@@ -309,6 +396,14 @@ int MPI_Scatter(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void*
                 MPI_Datatype recvtype, int root, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Scatter {} -> all", root);
+    if (auto sub = subOf(comm)) {
+        // MPI_IN_PLACE as the root's receive buffer: its chunk stays where it is
+        uint8_t* recv = recvbuf == MPI_IN_PLACE ? nullptr : (uint8_t*)recvbuf;
+        const bool isRoot = sub->commRankOf(executingContext.getRank()) == root;
+        sub->scatter(getExecutingWorld(), executingContext.getRank(), root, (const uint8_t*)sendbuf, recv,
+                     isRoot ? sendtype : recvtype, isRoot ? sendcount : recvcount);
+        return MPI_SUCCESS;
+    }
     getExecutingWorld().scatter(root, executingContext.getRank(), (const uint8_t*)sendbuf, sendtype, sendcount,
                                 (uint8_t*)recvbuf, recvtype, recvcount);
     return MPI_SUCCESS;
@@ -319,6 +414,13 @@ int MPI_Gather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* 
 {
     SPDLOG_TRACE("MPI - MPI_Gather all -> {}", root);
     int rank = executingContext.getRank();
+    if (auto sub = subOf(comm)) {
+        const bool isRoot = sub->commRankOf(rank) == root;
+        const uint8_t* chunk = sendbuf == MPI_IN_PLACE ? nullptr : (const uint8_t*)sendbuf;
+        sub->gather(getExecutingWorld(), rank, root, chunk, (uint8_t*)recvbuf, isRoot ? recvtype : sendtype,
+                    isRoot ? recvcount : sendcount);
+        return MPI_SUCCESS;
+    }
     const uint8_t* send = (const uint8_t*)sendbuf;
     if (sendbuf == MPI_IN_PLACE) {
         // The root's chunk is already in place in the receive buffer
@@ -334,6 +436,7 @@ int MPI_Gatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void*
                 const int* recvcounts, const int* displs, MPI_Datatype recvtype, int root, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Gatherv");
+    subCommOnly(comm, "MPI_Gatherv");
     MpiWorld& world = getExecutingWorld();
     int rank = executingContext.getRank();
     int size = world.getSize();
@@ -359,6 +462,13 @@ int MPI_Allgather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, voi
 {
     SPDLOG_TRACE("MPI - MPI_Allgather");
     int rank = executingContext.getRank();
+    if (auto sub = subOf(comm)) {
+        const uint8_t* chunk = sendbuf == MPI_IN_PLACE
+                                 ? (const uint8_t*)recvbuf + (size_t)sub->commRankOf(rank) * recvcount * recvtype->size
+                                 : (const uint8_t*)sendbuf;
+        sub->allGather(getExecutingWorld(), rank, chunk, (uint8_t*)recvbuf, recvtype, recvcount);
+        return MPI_SUCCESS;
+    }
     const uint8_t* send = (const uint8_t*)sendbuf;
     if (sendbuf == MPI_IN_PLACE) {
         send = (const uint8_t*)recvbuf + (size_t)rank * recvcount * recvtype->size;
@@ -373,6 +483,7 @@ int MPI_Allgatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, vo
                    const int* recvcounts, const int* displs, MPI_Datatype recvtype, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Allgatherv");
+    subCommOnly(comm, "MPI_Allgatherv");
     MpiWorld& world = getExecutingWorld();
     int size = world.getSize();
     // Equal, contiguous counts are a plain all-gather (fused device kernel)
@@ -396,6 +507,11 @@ int MPI_Allgatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, vo
 int MPI_Reduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, int root, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Reduce all -> {}", root);
+    if (auto sub = subOf(comm)) {
+        sub->reduce(getExecutingWorld(), executingContext.getRank(), root, (const uint8_t*)resolveInPlace(sendbuf, recvbuf),
+                    (uint8_t*)recvbuf, datatype, count, op);
+        return MPI_SUCCESS;
+    }
     getExecutingWorld().reduce(executingContext.getRank(), root, (uint8_t*)resolveInPlace(sendbuf, recvbuf),
                                (uint8_t*)recvbuf, datatype, count, op);
     return MPI_SUCCESS;
@@ -405,6 +521,7 @@ int MPI_Reduce_scatter(const void* sendbuf, void* recvbuf, const int* recvcounts
                        MPI_Op op, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Reduce_scatter");
+    subCommOnly(comm, "MPI_Reduce_scatter");
     MpiWorld& world = getExecutingWorld();
     int size = world.getSize();
     for (int r = 1; r < size; r++) {
@@ -425,6 +542,11 @@ int MPI_Reduce_scatter(const void* sendbuf, void* recvbuf, const int* recvcounts
 int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Allreduce");
+    if (auto sub = subOf(comm)) {
+        sub->allReduce(getExecutingWorld(), executingContext.getRank(), (const uint8_t*)resolveInPlace(sendbuf, recvbuf),
+                       (uint8_t*)recvbuf, datatype, count, op);
+        return MPI_SUCCESS;
+    }
     getExecutingWorld().allReduce(executingContext.getRank(), (uint8_t*)resolveInPlace(sendbuf, recvbuf),
                                   (uint8_t*)recvbuf, datatype, count, op);
     return MPI_SUCCESS;
@@ -433,6 +555,11 @@ int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype da
 int MPI_Scan(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Scan");
+    if (auto sub = subOf(comm)) {
+        sub->scan(getExecutingWorld(), executingContext.getRank(), (const uint8_t*)resolveInPlace(sendbuf, recvbuf),
+                  (uint8_t*)recvbuf, datatype, count, op);
+        return MPI_SUCCESS;
+    }
     getExecutingWorld().scan(executingContext.getRank(), (uint8_t*)resolveInPlace(sendbuf, recvbuf),
                              (uint8_t*)recvbuf, datatype, count, op);
     return MPI_SUCCESS;
@@ -442,6 +569,10 @@ int MPI_Alltoall(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void
                  MPI_Datatype recvtype, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Alltoall");
+    if (auto sub = subOf(comm)) {
+        sub->allToAll(getExecutingWorld(), executingContext.getRank(), (const uint8_t*)sendbuf, (uint8_t*)recvbuf, sendtype, sendcount);
+        return MPI_SUCCESS;
+    }
     getExecutingWorld().allToAll(executingContext.getRank(), (uint8_t*)sendbuf, sendtype, sendcount,
                                  (uint8_t*)recvbuf, recvtype, recvcount);
     return MPI_SUCCESS;
@@ -451,6 +582,7 @@ int MPI_Alltoallv(const void* sendbuf, const int sendcounts[], const int sdispls
                   void* recvbuf, const int recvcounts[], const int rdispls[], MPI_Datatype recvtype, MPI_Comm comm)
 {
     SPDLOG_TRACE("MPI - MPI_Alltoallv");
+    subCommOnly(comm, "MPI_Alltoallv");
     MpiWorld& world = getExecutingWorld();
     int rank = executingContext.getRank();
     int size = world.getSize();
@@ -480,6 +612,7 @@ int MPI_Alltoallv(const void* sendbuf, const int sendcounts[], const int sdispls
 int MPI_Cart_create(MPI_Comm old_comm, int ndims, const int dims[], const int periods[], int reorder, MPI_Comm* comm)
 {
     SPDLOG_TRACE("MPI - MPI_Cart_create");
+    subCommOnly(old_comm, "MPI_Cart_create");
     // The grid is remembered by the world; the communicator stays the world
     int rank = executingContext.getRank();
     std::vector<int> p(std::max(ndims, 2), 1);
@@ -610,6 +743,7 @@ int MPI_Free_mem(void* base)
 int MPI_Iallreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm, MPI_Request* request)
 {
     SPDLOG_TRACE("MPI - MPI_Iallreduce");
+    subCommOnly(comm, "MPI_Iallreduce");
     int id = getExecutingWorld().iAllReduce(executingContext.getRank(),
                                             (uint8_t*)resolveInPlace(sendbuf, recvbuf),
                                             (uint8_t*)recvbuf,
@@ -718,6 +852,7 @@ int MPI_Win_free(MPI_Win* win)
 int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, MPI_Win* win)
 {
     SPDLOG_TRACE("MPI - MPI_Win_create");
+    subCommOnly(comm, "MPI_Win_create");
     MpiWorld& world = getExecutingWorld();
     const int rank = executingContext.getRank();
     int winId = world.winCreate(rank, base, (int64_t)size, disp_unit);
@@ -728,6 +863,7 @@ int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_
 int MPI_Win_allocate_shared(MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, void* baseptr, MPI_Win* win)
 {
     SPDLOG_TRACE("MPI - MPI_Win_allocate_shared");
+    subCommOnly(comm, "MPI_Win_allocate_shared");
     MpiWorld& world = getExecutingWorld();
     if (!world.allRanksLocal()) {
         // Load/store access needs one address space: ranks of this world
@@ -799,45 +935,161 @@ MPI_Comm MPI_Comm_f2c(MPI_Fint comm)
     return nullptr;
 }
 
+// ---- communicator and group management.  The reference declares these
+// and throws (mpi_native.cpp:686-735); see src/mpi/subcomm.h ----
 int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm* newcomm)
 {
-    return notImplemented("MPI_Comm_split");
+    SPDLOG_TRACE("MPI - MPI_Comm_split");
+    MpiWorld& world = getExecutingWorld();
+    const int me = executingContext.getRank();
+    std::vector<int> parentRanks = ranksOf(comm);
+    const int n = (int)parentRanks.size();
+    const int parentId = comm->id;
+    const int seq = commCreateSeq[parentId]++;
+    // Everybody learns everybody's (color, key)
+    int mine[2] = { color, key };
+    std::vector<int> all(2 * (size_t)n);
+    faabric_datatype_t* intType = getFaabricDatatypeFromId(FAABRIC_INT);
+    if (auto sub = subOf(comm)) {
+        sub->allGather(world, me, (const uint8_t*)mine, (uint8_t*)all.data(), intType, 2);
+    } else {
+        world.allGather(me, (const uint8_t*)mine, intType, 2, (uint8_t*)all.data(), intType, 2);
+    }
+    if (color == MPI_UNDEFINED) {
+        *newcomm = MPI_COMM_NULL;
+        return MPI_SUCCESS;
+    }
+    // Members of my color, ordered by key then by rank in the parent
+    std::vector<std::pair<std::pair<int, int>, int>> members;
+    for (int r = 0; r < n; r++) {
+        if (all[2 * r] == color) {
+            members.push_back({ { all[2 * r + 1], r }, parentRanks[r] });
+        }
+    }
+    std::sort(members.begin(), members.end());
+    std::vector<int> worldRanks;
+    for (auto& m : members) {
+        worldRanks.push_back(m.second);
+    }
+    *newcomm = makeCommHandle(parentId, seq, (uint64_t)(uint32_t)color, worldRanks);
+    return MPI_SUCCESS;
 }
 
 int MPI_Comm_split_type(MPI_Comm comm, int split_type, int key, MPI_Info info, MPI_Comm* newcomm)
 {
-    return notImplemented("MPI_Comm_split_type");
-}
-
-int MPI_Comm_create(MPI_Comm comm, MPI_Group group, MPI_Comm* newcomm)
-{
-    return notImplemented("MPI_Comm_create");
-}
-
-int MPI_Comm_create_group(MPI_Comm comm, MPI_Group group, int tag, MPI_Comm* newcomm)
-{
-    return notImplemented("MPI_Comm_create_group");
+    SPDLOG_TRACE("MPI - MPI_Comm_split_type");
+    if (split_type != MPI_COMM_TYPE_SHARED) {
+        throw std::runtime_error("MPI_Comm_split_type: only MPI_COMM_TYPE_SHARED is supported");
+    }
+    // Ranks that share an address space: those served by the same worker
+    // process.  Colour = lowest world rank on my host.
+    MpiWorld& world = getExecutingWorld();
+    const std::string myHost = world.getHostForRank(executingContext.getRank());
+    int color = executingContext.getRank();
+    for (int r = 0; r < world.getSize(); r++) {
+        if (world.getHostForRank(r) == myHost) {
+            color = r;
+            break;
+        }
+    }
+    return MPI_Comm_split(comm, color, key, newcomm);
 }
 
 int MPI_Comm_group(MPI_Comm comm, MPI_Group* group)
 {
-    return notImplemented("MPI_Comm_group");
+    SPDLOG_TRACE("MPI - MPI_Comm_group");
+    *group = new faabric_group_t{ registerGroup(ranksOf(comm)) };
+    return MPI_SUCCESS;
 }
 
 int MPI_Group_incl(MPI_Group group, int n, const int ranks[], MPI_Group* newgroup)
 {
-    return notImplemented("MPI_Group_incl");
+    SPDLOG_TRACE("MPI - MPI_Group_incl");
+    std::vector<int> parent;
+    if (group == nullptr || !getGroup(group->id, parent)) {
+        return MPI_ERR_ARG;
+    }
+    std::vector<int> subset;
+    for (int i = 0; i < n; i++) {
+        if (ranks[i] < 0 || ranks[i] >= (int)parent.size()) {
+            return MPI_ERR_RANK;
+        }
+        subset.push_back(parent[ranks[i]]);
+    }
+    *newgroup = new faabric_group_t{ registerGroup(std::move(subset)) };
+    return MPI_SUCCESS;
 }
 
 int MPI_Group_free(MPI_Group* group)
 {
-    return notImplemented("MPI_Group_free");
+    SPDLOG_TRACE("MPI - MPI_Group_free");
+    if (group == nullptr || *group == nullptr) {
+        return MPI_ERR_ARG;
+    }
+    freeGroup((*group)->id);
+    delete *group;
+    *group = nullptr;
+    return MPI_SUCCESS;
+}
+
+static uint64_t hashRanks(const std::vector<int>& ranks)
+{
+    uint64_t h = 1469598103934665603ULL;
+    for (int r : ranks) {
+        h = (h ^ (uint64_t)(uint32_t)r) * 1099511628211ULL;
+    }
+    return h;
+}
+
+int MPI_Comm_create(MPI_Comm comm, MPI_Group group, MPI_Comm* newcomm)
+{
+    SPDLOG_TRACE("MPI - MPI_Comm_create");
+    // Collective over `comm`; ranks outside the group get MPI_COMM_NULL
+    const int parentId = comm->id;
+    const int seq = commCreateSeq[parentId]++;
+    std::vector<int> members;
+    if (group == nullptr || !getGroup(group->id, members)) {
+        return MPI_ERR_ARG;
+    }
+    const int me = executingContext.getRank();
+    if (std::find(members.begin(), members.end(), me) == members.end()) {
+        *newcomm = MPI_COMM_NULL;
+        return MPI_SUCCESS;
+    }
+    *newcomm = makeCommHandle(parentId, seq, hashRanks(members), members);
+    return MPI_SUCCESS;
+}
+
+int MPI_Comm_create_group(MPI_Comm comm, MPI_Group group, int tag, MPI_Comm* newcomm)
+{
+    SPDLOG_TRACE("MPI - MPI_Comm_create_group");
+    // Collective over the GROUP only: the tag (not a per-parent counter, which
+    // non-members do not advance) tells concurrent creations apart
+    std::vector<int> members;
+    if (group == nullptr || !getGroup(group->id, members)) {
+        return MPI_ERR_ARG;
+    }
+    const int me = executingContext.getRank();
+    if (std::find(members.begin(), members.end(), me) == members.end()) {
+        *newcomm = MPI_COMM_NULL;
+        return MPI_SUCCESS;
+    }
+    *newcomm = makeCommHandle(comm->id, -1 - tag, hashRanks(members), members);
+    return MPI_SUCCESS;
 }
 
 int MPI_Comm_free(MPI_Comm* comm)
 {
     SPDLOG_TRACE("MPI - MPI_Comm_free");
-    // Communicators are not owned by the caller
+    if (comm == nullptr || *comm == nullptr) {
+        return MPI_ERR_ARG;
+    }
+    // The predefined communicators (and cartesian views of the world) are not
+    // owned by the caller; handles of sub-communicators are
+    if ((*comm)->id != FAABRIC_COMM_WORLD && (*comm)->id != FAABRIC_COMM_NULL) {
+        delete *comm;
+    }
+    *comm = MPI_COMM_NULL;
     return MPI_SUCCESS;
 }
 

@@ -629,6 +629,174 @@ TEST_CASE("mpi: one-sided windows, put/get/fence and shared segments", "[mpi][rm
     runMpi("rma-one", 1, 1, bodyRma);
 }
 
+namespace {
+// ---- sub-communicators ----
+int bodySubComms(int rank, int size)
+{
+    // Even / odd halves, ranked in REVERSE world order through the key
+    MPI_Comm half = nullptr;
+    CHECK_RANK(MPI_Comm_split(MPI_COMM_WORLD, rank % 2, -rank, &half) == MPI_SUCCESS);
+    int hRank = -1, hSize = -1;
+    MPI_Comm_rank(half, &hRank);
+    MPI_Comm_size(half, &hSize);
+    const int nEven = (size + 1) / 2, nOdd = size / 2;
+    CHECK_RANK(hSize == (rank % 2 == 0 ? nEven : nOdd));
+    // members sorted by descending world rank
+    std::vector<int> members;
+    for (int r = size - 1; r >= 0; r--) {
+        if (r % 2 == rank % 2) {
+            members.push_back(r);
+        }
+    }
+    CHECK_RANK(members[hRank] == rank);
+
+    // point to point in communicator ranks
+    int right = (hRank + 1) % hSize, left = (hRank + hSize - 1) % hSize;
+    int token = rank, got = -1;
+    MPI_Status status{};
+    MPI_Sendrecv(&token, 1, MPI_INT, right, 0, &got, 1, MPI_INT, left, 0, half, &status);
+    CHECK_RANK(got == members[left]);
+    CHECK_RANK(status.MPI_SOURCE == left);
+
+    // collectives stay inside the half
+    int root = hSize - 1;
+    std::vector<int> b(100, hRank == root ? 1000 + rank % 2 : -1);
+    MPI_Bcast(b.data(), 100, MPI_INT, root, half);
+    CHECK_RANK(b[0] == 1000 + rank % 2 && b[99] == 1000 + rank % 2);
+    long mine = rank + 1, sum = 0;
+    MPI_Allreduce(&mine, &sum, 1, MPI_LONG, MPI_SUM, half);
+    long expected = 0;
+    for (int m : members) {
+        expected += m + 1;
+    }
+    CHECK_RANK(sum == expected);
+    long inPlace = rank + 1;
+    MPI_Allreduce(MPI_IN_PLACE, &inPlace, 1, MPI_LONG, MPI_SUM, half);
+    CHECK_RANK(inPlace == expected);
+    long maxAtRoot = -1;
+    MPI_Reduce(&mine, &maxAtRoot, 1, MPI_LONG, MPI_MAX, 0, half);
+    if (hRank == 0) {
+        CHECK_RANK(maxAtRoot == members[0] + 1);
+    }
+    long prefix = 0;
+    MPI_Scan(&mine, &prefix, 1, MPI_LONG, MPI_SUM, half);
+    long expectedPrefix = 0;
+    for (int i = 0; i <= hRank; i++) {
+        expectedPrefix += members[i] + 1;
+    }
+    CHECK_RANK(prefix == expectedPrefix);
+
+    std::vector<int> gathered(2 * hSize, -1);
+    int pair[2] = { rank, rank * 10 };
+    MPI_Gather(pair, 2, MPI_INT, gathered.data(), 2, MPI_INT, root, half);
+    if (hRank == root) {
+        for (int i = 0; i < hSize; i++) {
+            CHECK_RANK(gathered[2 * i] == members[i] && gathered[2 * i + 1] == members[i] * 10);
+        }
+    }
+    std::vector<int> toScatter(hSize);
+    for (int i = 0; i < hSize; i++) {
+        toScatter[i] = 500 + i;
+    }
+    int piece = -1;
+    MPI_Scatter(toScatter.data(), 1, MPI_INT, &piece, 1, MPI_INT, 0, half);
+    CHECK_RANK(piece == 500 + hRank);
+    std::vector<int> everyone(hSize, -1);
+    MPI_Allgather(&rank, 1, MPI_INT, everyone.data(), 1, MPI_INT, half);
+    CHECK_RANK(everyone == members);
+    std::vector<int> everyoneInPlace(hSize, -1);
+    everyoneInPlace[hRank] = rank;
+    MPI_Allgather(MPI_IN_PLACE, 0, MPI_DATATYPE_NULL, everyoneInPlace.data(), 1, MPI_INT, half);
+    CHECK_RANK(everyoneInPlace == members);
+    std::vector<int> out(hSize), in(hSize, -1);
+    for (int i = 0; i < hSize; i++) {
+        out[i] = rank * 100 + members[i];
+    }
+    MPI_Alltoall(out.data(), 1, MPI_INT, in.data(), 1, MPI_INT, half);
+    for (int i = 0; i < hSize; i++) {
+        CHECK_RANK(in[i] == members[i] * 100 + rank);
+    }
+    MPI_Barrier(half);
+
+    // splitting a sub-communicator again
+    MPI_Comm quarter = nullptr;
+    MPI_Comm_split(half, hRank < hSize / 2 ? 0 : 1, hRank, &quarter);
+    int qRank = -1, qSize = -1;
+    MPI_Comm_rank(quarter, &qRank);
+    MPI_Comm_size(quarter, &qSize);
+    CHECK_RANK(qSize == (hRank < hSize / 2 ? hSize / 2 : hSize - hSize / 2));
+    int qSum = 0, one = 1;
+    MPI_Allreduce(&one, &qSum, 1, MPI_INT, MPI_SUM, quarter);
+    CHECK_RANK(qSum == qSize);
+    MPI_Comm_free(&quarter);
+    CHECK_RANK(quarter == MPI_COMM_NULL);
+
+    // MPI_UNDEFINED opts out
+    MPI_Comm notZero = nullptr;
+    MPI_Comm_split(MPI_COMM_WORLD, rank == 0 ? MPI_UNDEFINED : 7, rank, &notZero);
+    if (rank == 0) {
+        CHECK_RANK(notZero == MPI_COMM_NULL);
+    } else {
+        int nzSize = -1, nzRank = -1;
+        MPI_Comm_size(notZero, &nzSize);
+        MPI_Comm_rank(notZero, &nzRank);
+        CHECK_RANK(nzSize == size - 1 && nzRank == rank - 1);
+        MPI_Comm_free(&notZero);
+    }
+
+    // groups: the first three world ranks, reversed
+    MPI_Group worldGroup = nullptr, firstThree = nullptr;
+    MPI_Comm_group(MPI_COMM_WORLD, &worldGroup);
+    int pick[3] = { 2, 1, 0 };
+    CHECK_RANK(MPI_Group_incl(worldGroup, 3, pick, &firstThree) == MPI_SUCCESS);
+    int bad[1] = { size };
+    MPI_Group broken = nullptr;
+    CHECK_RANK(MPI_Group_incl(worldGroup, 1, bad, &broken) == MPI_ERR_RANK);
+    MPI_Comm three = nullptr;
+    MPI_Comm_create(MPI_COMM_WORLD, firstThree, &three);
+    if (rank < 3) {
+        int tRank = -1, tSize = -1;
+        MPI_Comm_rank(three, &tRank);
+        MPI_Comm_size(three, &tSize);
+        CHECK_RANK(tSize == 3 && tRank == 2 - rank);
+        int v = rank, total = 0;
+        MPI_Allreduce(&v, &total, 1, MPI_INT, MPI_SUM, three);
+        CHECK_RANK(total == 3);
+        // only the members take part in this one
+        MPI_Comm again = nullptr;
+        MPI_Comm_create_group(MPI_COMM_WORLD, firstThree, 42, &again);
+        int aSize = -1;
+        MPI_Comm_size(again, &aSize);
+        CHECK_RANK(aSize == 3 && again->id != three->id);
+        MPI_Comm_free(&again);
+        MPI_Comm_free(&three);
+    } else {
+        CHECK_RANK(three == MPI_COMM_NULL);
+    }
+    MPI_Group_free(&firstThree);
+    MPI_Group_free(&worldGroup);
+    CHECK_RANK(worldGroup == nullptr);
+
+    // ranks that share this process's address space
+    MPI_Comm node = nullptr;
+    MPI_Comm_split_type(MPI_COMM_WORLD, MPI_COMM_TYPE_SHARED, rank, MPI_INFO_NULL, &node);
+    int nodeSize = -1;
+    MPI_Comm_size(node, &nodeSize);
+    CHECK_RANK(nodeSize == size);
+    MPI_Comm_free(&node);
+    MPI_Comm_free(&half);
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+}
+
+TEST_CASE("mpi: sub-communicators, groups and their collectives", "[mpi][subcomm]")
+{
+    runMpi("subcomm-local", 7, 1, bodySubComms);
+    runMpi("subcomm-gpuhosts", 6, 3, bodySubComms);
+    runMpi("subcomm-four", 4, 1, bodySubComms);
+}
+
 TEST_CASE("mpi: point-to-point on one host", "[mpi]")
 {
     runMpi("p2p-local", 4, 1, bodyPointToPoint);

@@ -86,6 +86,7 @@ MPI_FUNCTIONS = [
     "status-probe",
     "cart",
     "rma",
+    "subcomm",
 ]
 
 
@@ -99,6 +100,9 @@ def test_mpi_across_two_workers(cluster, fn):
     assert [m.get("mpiRank", 0) for m in res] == [0, 1, 2, 3]
     assert all(m.get("returnValue", 0) == 0 for m in res), res
     assert {m["executedHost"] for m in res} == set(cluster.worker_hosts())
+    if fn == "subcomm":
+        # MPI_COMM_TYPE_SHARED groups the two ranks of each worker process
+        assert all(m["output_data"] == "node of 2" for m in res), res
 
 
 def test_mpi_benchmarks_report(cluster):
