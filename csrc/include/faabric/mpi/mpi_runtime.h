@@ -136,6 +136,17 @@ inline bool isUserOp(const faabric_op_t* op)
     return op != nullptr && op->id >= FAABRIC_OP_USER_BASE;
 }
 
+// ---- derived datatypes (MPI_Type_contiguous) ----
+// `count` consecutive elements of a predefined type.  Data movement only needs
+// the size; reductions resolve the type back to (base type, count).
+constexpr int FAABRIC_DERIVED_TYPE_BASE = 1000;
+
+int registerContiguousType(int baseTypeId, int count);
+
+bool getContiguousType(int typeId, int* baseTypeId, int* count);
+
+bool unregisterContiguousType(int typeId);
+
 // Messages "sent" to remote ranks in mock mode
 std::vector<MpiMessage> getMpiMockedMessages(int sendRank);
 

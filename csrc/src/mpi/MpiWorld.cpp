@@ -141,6 +141,44 @@ bool getUserOp(int opId, MPI_User_function** fn, bool* commutes)
     return true;
 }
 
+// ---------------------------------------------------------------------------
+// Derived (contiguous) datatypes
+// ---------------------------------------------------------------------------
+namespace {
+std::shared_mutex derivedTypesMx;
+std::map<int, std::pair<int, int>> derivedTypes;
+int nextDerivedTypeId = FAABRIC_DERIVED_TYPE_BASE;
+}
+
+int registerContiguousType(int baseTypeId, int count)
+{
+    if (count <= 0) {
+        throw std::invalid_argument("Contiguous datatype needs a positive count");
+    }
+    std::unique_lock<std::shared_mutex> lk(derivedTypesMx);
+    int id = nextDerivedTypeId++;
+    derivedTypes[id] = { baseTypeId, count };
+    return id;
+}
+
+bool getContiguousType(int typeId, int* baseTypeId, int* count)
+{
+    std::shared_lock<std::shared_mutex> lk(derivedTypesMx);
+    auto it = derivedTypes.find(typeId);
+    if (it == derivedTypes.end()) {
+        return false;
+    }
+    *baseTypeId = it->second.first;
+    *count = it->second.second;
+    return true;
+}
+
+bool unregisterContiguousType(int typeId)
+{
+    std::unique_lock<std::shared_mutex> lk(derivedTypesMx);
+    return derivedTypes.erase(typeId) > 0;
+}
+
 std::vector<MpiMessage> getMpiMockedMessages(int sendRank)
 {
     std::lock_guard<std::mutex> lk(mockMx);
@@ -2143,6 +2181,16 @@ void MpiWorld::op_reduce(faabric_op_t* operation,
                          uint8_t* inBuffer,
                          uint8_t* resultBuffer)
 {
+    if (datatype->id >= FAABRIC_DERIVED_TYPE_BASE) {
+        // n elements of "k x base" are n*k elements of base; user functions see
+        // the base type too
+        int baseId = 0, per = 0;
+        if (!getContiguousType(datatype->id, &baseId, &per)) {
+            throw std::runtime_error("Reduction on an unknown derived datatype");
+        }
+        op_reduce(operation, getFaabricDatatypeFromId(baseId), count * per, inBuffer, resultBuffer);
+        return;
+    }
     const int op = operation->id;
     if (isUserOp(operation)) {
         MPI_User_function* fn = nullptr;

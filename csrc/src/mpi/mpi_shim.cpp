@@ -41,12 +41,6 @@ faabric::Message* getExecutingCall()
     return &faabric::executor::ExecutorContext::get()->getMsg();
 }
 
-int notImplemented(const std::string& funcName)
-{
-    SPDLOG_TRACE("MPI - {}", funcName);
-    throw std::runtime_error(funcName + " not implemented.");
-}
-
 int terminateMpi()
 {
     // Destroy the MPI world
@@ -524,16 +518,42 @@ int MPI_Reduce_scatter(const void* sendbuf, void* recvbuf, const int* recvcounts
     subCommOnly(comm, "MPI_Reduce_scatter");
     MpiWorld& world = getExecutingWorld();
     int size = world.getSize();
-    for (int r = 1; r < size; r++) {
-        if (recvcounts[r] != recvcounts[0]) {
-            return notImplemented("MPI_Reduce_scatter with unequal counts");
-        }
-    }
     int rank = executingContext.getRank();
     const void* send = sendbuf;
-    std::vector<uint8_t> tmp;
     if (sendbuf == MPI_IN_PLACE) {
         send = recvbuf;
+    }
+    bool equal = true;
+    for (int r = 1; r < size; r++) {
+        equal = equal && recvcounts[r] == recvcounts[0];
+    }
+    if (!equal) {
+        // Irregular blocks: reduce everything at rank 0, then hand out the
+        // blocks (the fused kernel only knows equal shards)
+        size_t total = 0;
+        std::vector<size_t> offsets(size);
+        for (int r = 0; r < size; r++) {
+            offsets[r] = total;
+            total += (size_t)recvcounts[r];
+        }
+        std::vector<uint8_t> reduced(rank == 0 ? total * datatype->size : 0);
+        std::vector<uint8_t> hostSend;
+        const uint8_t* src = (const uint8_t*)send;
+        if (MpiWorld::isDevicePointer(src)) {
+            hostSend.resize(total * datatype->size);
+            copyAny(hostSend.data(), src, hostSend.size());
+            src = hostSend.data();
+        }
+        world.reduce(rank, 0, (uint8_t*)src, reduced.data(), datatype, (int)total, op);
+        if (rank == 0) {
+            for (int r = 1; r < size; r++) {
+                world.send(0, r, reduced.data() + offsets[r] * datatype->size, datatype, recvcounts[r], MpiMessageType::SCATTER);
+            }
+            copyAny(recvbuf, reduced.data(), (size_t)recvcounts[0] * datatype->size);
+        } else {
+            world.recv(0, rank, (uint8_t*)recvbuf, datatype, recvcounts[rank], nullptr, MpiMessageType::SCATTER);
+        }
+        return MPI_SUCCESS;
     }
     world.reduceScatter(rank, (uint8_t*)send, (uint8_t*)recvbuf, datatype, recvcounts[0], op);
     return MPI_SUCCESS;
@@ -670,12 +690,28 @@ int MPI_Type_size(MPI_Datatype type, int* size)
 
 int MPI_Type_free(MPI_Datatype* datatype)
 {
-    return notImplemented("MPI_Type_free");
+    SPDLOG_TRACE("MPI - MPI_Type_free");
+    // Only derived types can be freed (the reference throws for all of them,
+    // mpi_native.cpp:541-545)
+    if (datatype == nullptr || *datatype == nullptr || (*datatype)->id < FAABRIC_DERIVED_TYPE_BASE) {
+        return MPI_ERR_ARG;
+    }
+    unregisterContiguousType((*datatype)->id);
+    delete *datatype;
+    *datatype = MPI_DATATYPE_NULL;
+    return MPI_SUCCESS;
 }
 
 int MPI_Type_contiguous(int count, MPI_Datatype oldtype, MPI_Datatype* newtype)
 {
     SPDLOG_TRACE("MPI - MPI_Type_contiguous");
+    // (a no-op in the reference, which leaves *newtype untouched)
+    int baseId = oldtype->id, per = 1;
+    if (oldtype->id >= FAABRIC_DERIVED_TYPE_BASE && !getContiguousType(oldtype->id, &baseId, &per)) {
+        return MPI_ERR_ARG;
+    }
+    int id = registerContiguousType(baseId, count * per);
+    *newtype = new faabric_datatype_t{ id, count * oldtype->size };
     return MPI_SUCCESS;
 }
 
@@ -923,16 +959,22 @@ int MPI_Comm_dup(MPI_Comm comm, MPI_Comm* newcomm)
     return MPI_SUCCESS;
 }
 
+// Fortran handles are the communicator ids
 MPI_Fint MPI_Comm_c2f(MPI_Comm comm)
 {
-    notImplemented("MPI_Comm_c2f");
-    return 0;
+    return comm == nullptr ? FAABRIC_COMM_NULL : comm->id;
 }
 
 MPI_Comm MPI_Comm_f2c(MPI_Fint comm)
 {
-    notImplemented("MPI_Comm_f2c");
-    return nullptr;
+    if (comm == FAABRIC_COMM_WORLD) {
+        return MPI_COMM_WORLD;
+    }
+    if (comm == FAABRIC_COMM_NULL || getSubCommunicator(comm) == nullptr) {
+        return MPI_COMM_NULL;
+    }
+    // a fresh handle; release it with MPI_Comm_free like any other
+    return new faabric_communicator_t{ comm };
 }
 
 // ---- communicator and group management.  The reference declares these

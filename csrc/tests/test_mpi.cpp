@@ -797,6 +797,84 @@ TEST_CASE("mpi: sub-communicators, groups and their collectives", "[mpi][subcomm
     runMpi("subcomm-four", 4, 1, bodySubComms);
 }
 
+namespace {
+// ---- derived datatypes, handle conversion, irregular reduce-scatter ----
+int bodyTypesAndHandles(int rank, int size)
+{
+    // three ints travel as one element
+    MPI_Datatype triple = nullptr;
+    CHECK_RANK(MPI_Type_contiguous(3, MPI_INT, &triple) == MPI_SUCCESS);
+    MPI_Type_commit(&triple);
+    int typeSize = 0;
+    MPI_Type_size(triple, &typeSize);
+    CHECK_RANK(typeSize == 3 * (int)sizeof(int));
+    int right = (rank + 1) % size, left = (rank + size - 1) % size;
+    int out[6] = { rank, rank + 1, rank + 2, rank + 3, rank + 4, rank + 5 }, in[6] = { 0 };
+    MPI_Status status{};
+    MPI_Sendrecv(out, 2, triple, right, 0, in, 2, triple, left, 0, MPI_COMM_WORLD, &status);
+    CHECK_RANK(in[0] == left && in[5] == left + 5);
+    int count = 0;
+    MPI_Get_count(&status, triple, &count);
+    CHECK_RANK(count == 2);
+    // reductions see through the derived type
+    int sums[6] = { 0 };
+    MPI_Allreduce(out, sums, 2, triple, MPI_SUM, MPI_COMM_WORLD);
+    int base = size * (size - 1) / 2;
+    CHECK_RANK(sums[0] == base && sums[5] == base + 5 * size);
+    // nested: two triples
+    MPI_Datatype six = nullptr;
+    MPI_Type_contiguous(2, triple, &six);
+    MPI_Type_size(six, &typeSize);
+    CHECK_RANK(typeSize == 6 * (int)sizeof(int));
+    int maxes[6] = { 0 };
+    MPI_Allreduce(out, maxes, 1, six, MPI_MAX, MPI_COMM_WORLD);
+    CHECK_RANK(maxes[0] == size - 1 && maxes[5] == size + 4);
+    CHECK_RANK(MPI_Type_free(&six) == MPI_SUCCESS && six == MPI_DATATYPE_NULL);
+    CHECK_RANK(MPI_Type_free(&triple) == MPI_SUCCESS);
+    MPI_Datatype predefined = MPI_INT;
+    CHECK_RANK(MPI_Type_free(&predefined) == MPI_ERR_ARG);
+
+    // Fortran handles
+    CHECK_RANK(MPI_Comm_f2c(MPI_Comm_c2f(MPI_COMM_WORLD)) == MPI_COMM_WORLD);
+    CHECK_RANK(MPI_Comm_f2c(MPI_Comm_c2f(MPI_COMM_NULL)) == MPI_COMM_NULL);
+    MPI_Comm half = nullptr;
+    MPI_Comm_split(MPI_COMM_WORLD, rank % 2, rank, &half);
+    MPI_Comm same = MPI_Comm_f2c(MPI_Comm_c2f(half));
+    int a = -1, b = -2;
+    MPI_Comm_rank(half, &a);
+    MPI_Comm_rank(same, &b);
+    CHECK_RANK(a == b);
+    MPI_Comm_free(&same);
+    MPI_Comm_free(&half);
+    CHECK_RANK(MPI_Comm_f2c(123456) == MPI_COMM_NULL);
+
+    // reduce-scatter with a different block per rank: rank r gets r + 1 sums
+    std::vector<int> counts(size);
+    int total = 0;
+    for (int r = 0; r < size; r++) {
+        counts[r] = r + 1;
+        total += r + 1;
+    }
+    std::vector<long> contrib(total), block(rank + 1, -1);
+    for (int i = 0; i < total; i++) {
+        contrib[i] = i + rank;
+    }
+    MPI_Reduce_scatter(contrib.data(), block.data(), counts.data(), MPI_LONG, MPI_SUM, MPI_COMM_WORLD);
+    int myOffset = rank * (rank + 1) / 2;
+    for (int i = 0; i <= rank; i++) {
+        CHECK_RANK(block[i] == (long)(myOffset + i) * size + base);
+    }
+    MPI_Barrier(MPI_COMM_WORLD);
+    return 0;
+}
+}
+
+TEST_CASE("mpi: derived datatypes, handle conversion, irregular reduce-scatter", "[mpi]")
+{
+    runMpi("types-local", 5, 1, bodyTypesAndHandles);
+    runMpi("types-gpuhosts", 4, 2, bodyTypesAndHandles);
+}
+
 TEST_CASE("mpi: point-to-point on one host", "[mpi]")
 {
     runMpi("p2p-local", 4, 1, bodyPointToPoint);
