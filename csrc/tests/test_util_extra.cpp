@@ -1,0 +1,269 @@
+// Utilities without a dedicated case elsewhere (strategy: reference
+// tests/test/util/test_{periodic_thread,tokens,environment,network,memory,
+// batch,func}.cpp)
+#include "harness.h"
+
+#include <faabric/proto/faabric.pb.h>
+#include <faabric/util/PeriodicBackgroundThread.h>
+#include <faabric/util/batch.h>
+#include <faabric/util/config.h>
+#include <faabric/util/environment.h>
+#include <faabric/util/func.h>
+#include <faabric/util/locks.h>
+#include <faabric/util/memory.h>
+#include <faabric/util/network.h>
+#include <faabric/util/queue.h>
+
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <unistd.h>
+
+using namespace faabric::util;
+
+namespace {
+class CountingThread : public PeriodicBackgroundThread
+{
+  public:
+    std::atomic<int> ticks{ 0 };
+    std::atomic<int> tidied{ 0 };
+
+    void doWork() override { ticks++; }
+
+    void tidyUp() override { tidied++; }
+};
+}
+
+TEST_CASE("periodic background thread ticks, stops promptly and tidies up", "[util]")
+{
+    CountingThread t;
+    t.startMs(5);
+    for (int i = 0; i < 400 && t.ticks.load() < 3; i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    REQUIRE(t.ticks.load() >= 3);
+    auto t0 = std::chrono::steady_clock::now();
+    t.stop();
+    auto stopMs = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+    REQUIRE(stopMs < 1000);
+    REQUIRE_EQ(t.tidied.load(), 1);
+    int after = t.ticks.load();
+    std::this_thread::sleep_for(std::chrono::milliseconds(30));
+    REQUIRE_EQ(t.ticks.load(), after);
+    // stopping twice / never-started threads is harmless
+    t.stop();
+    CountingThread idle;
+    idle.stop();
+    // a long interval does not delay shutdown
+    CountingThread slow;
+    slow.start(3600);
+    REQUIRE_EQ(slow.getIntervalSeconds(), 3600);
+    t0 = std::chrono::steady_clock::now();
+    slow.stop();
+    stopMs = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+    REQUIRE(stopMs < 1000);
+    REQUIRE_EQ(slow.ticks.load(), 0);
+}
+
+TEST_CASE("token pool hands out each token once and blocks when empty", "[util]")
+{
+    TokenPool pool(3);
+    REQUIRE_EQ(pool.size(), 3);
+    REQUIRE_EQ(pool.free(), 3);
+    std::set<int> got = { pool.getToken(), pool.getToken(), pool.getToken() };
+    REQUIRE_EQ(got.size(), (size_t)3);
+    REQUIRE_EQ(pool.taken(), 3);
+    REQUIRE_EQ(pool.free(), 0);
+    // a fourth taker waits for a release
+    std::atomic<int> late{ -1 };
+    std::thread waiter([&] { late = pool.getToken(); });
+    std::this_thread::sleep_for(std::chrono::milliseconds(30));
+    REQUIRE_EQ(late.load(), -1);
+    pool.releaseToken(*got.begin());
+    waiter.join();
+    REQUIRE_EQ(late.load(), *got.begin());
+    pool.reset();
+    REQUIRE_EQ(pool.free(), 3);
+    // a pool of zero never blocks: it hands out a dummy token
+    TokenPool none(0);
+    REQUIRE_EQ(none.getToken(), -1);
+}
+
+TEST_CASE("environment variables and core counts", "[util]")
+{
+    REQUIRE_EQ(getEnvVar("FB_TEST_SURELY_UNSET", "fallback"), std::string("fallback"));
+    setEnvVar("FB_TEST_VAR", "abc");
+    REQUIRE_EQ(getEnvVar("FB_TEST_VAR", "fallback"), std::string("abc"));
+    // empty counts as unset
+    setEnvVar("FB_TEST_VAR", "");
+    REQUIRE_EQ(getEnvVar("FB_TEST_VAR", "fallback"), std::string("fallback"));
+    unsetEnvVar("FB_TEST_VAR");
+    REQUIRE_EQ(getEnvVar("FB_TEST_VAR", "gone"), std::string("gone"));
+
+    unsigned int real = getUsableCores();
+    REQUIRE(real >= 1);
+    auto& conf = getSystemConfig();
+    int before = conf.overrideCpuCount;
+    conf.overrideCpuCount = 3;
+    REQUIRE_EQ(getUsableCores(), 3u);
+    conf.overrideCpuCount = before;
+    REQUIRE_EQ(getUsableCores(), real);
+    REQUIRE(getUsableGpus() >= 0);
+}
+
+TEST_CASE("network helpers resolve names and this host's address", "[util]")
+{
+    REQUIRE_EQ(getIPFromHostname("localhost"), std::string("127.0.0.1"));
+    REQUIRE_EQ(getIPFromHostname("127.0.0.1"), std::string("127.0.0.1"));
+    // unknown names come back empty (callers fall back to the name itself)
+    REQUIRE_EQ(getIPFromHostname("no-such-host.invalid"), std::string(""));
+    std::string ip = getPrimaryIPForThisHost("");
+    REQUIRE(!ip.empty());
+    REQUIRE_EQ(std::count(ip.begin(), ip.end(), '.'), 3L);
+    REQUIRE_EQ(getPrimaryIPForThisHost("lo"), std::string("127.0.0.1"));
+}
+
+TEST_CASE("memory regions: fds, shared and private mappings", "[util][memory]")
+{
+    const size_t page = HOST_PAGE_SIZE;
+    REQUIRE(isPageAligned((void*)(uintptr_t)(4 * page)));
+    REQUIRE(!isPageAligned((void*)(uintptr_t)(4 * page + 8)));
+
+    // fresh memory is zeroed, writable and page aligned
+    MemoryRegion priv = allocatePrivateMemory(3 * page);
+    MemoryRegion shared = allocateSharedMemory(3 * page);
+    REQUIRE(isPageAligned(priv.get()) && isPageAligned(shared.get()));
+    REQUIRE(priv[0] == 0 && priv[3 * page - 1] == 0);
+    priv[10] = 1;
+    shared[10] = 2;
+
+    // a memfd backs two views: shared ones see each other's writes, a private
+    // one keeps its own copy after the first write
+    int fd = createFd(2 * page, "fb-test");
+    REQUIRE(fd > 0);
+    std::vector<uint8_t> pattern(2 * page);
+    for (size_t i = 0; i < pattern.size(); i++) {
+        pattern[i] = (uint8_t)(i % 251);
+    }
+    writeToFd(fd, 0, pattern);
+    MemoryRegion viewA = allocatePrivateMemory(2 * page);
+    MemoryRegion viewB = allocatePrivateMemory(2 * page);
+    MemoryRegion viewC = allocatePrivateMemory(2 * page);
+    mapMemoryShared({ viewA.get(), 2 * page }, fd);
+    mapMemoryShared({ viewB.get(), 2 * page }, fd);
+    mapMemoryPrivate({ viewC.get(), 2 * page }, fd);
+    REQUIRE(memcmp(viewA.get(), pattern.data(), 2 * page) == 0);
+    REQUIRE(memcmp(viewC.get(), pattern.data(), 2 * page) == 0);
+    viewA[5] = 200;
+    REQUIRE_EQ(viewB[5], 200);
+    REQUIRE_EQ(viewC[5], 200); // untouched private pages still follow the file
+    viewC[6] = 77;             // copy-on-write from here on
+    REQUIRE_EQ(viewA[6], pattern[6]);
+    viewA[7] = 201;
+    REQUIRE_EQ(viewC[7], pattern[7]);
+
+    // growing the file and appending
+    resizeFd(fd, 3 * page);
+    std::vector<uint8_t> extra(page, 9);
+    writeToFd(fd, (off_t)(2 * page), extra);
+    MemoryRegion grown = allocatePrivateMemory(3 * page);
+    mapMemoryShared({ grown.get(), 3 * page }, fd);
+    REQUIRE_EQ(grown[2 * page + 17], 9);
+    std::vector<uint8_t> tail(page, 4);
+    appendDataToFd(fd, tail);
+    MemoryRegion appended = allocatePrivateMemory(4 * page);
+    mapMemoryShared({ appended.get(), 4 * page }, fd);
+    REQUIRE_EQ(appended[3 * page + 1], 4);
+    ::close(fd);
+
+    // misaligned targets and bad fds are refused
+    REQUIRE_THROWS(mapMemoryShared({ viewA.get() + 8, page }, fd));
+    int other = createFd(page, "fb-test-2");
+    REQUIRE_THROWS(mapMemoryShared({ viewA.get() + 8, page }, other));
+    ::close(other);
+    REQUIRE_THROWS(mapMemoryPrivate({ viewA.get(), page }, -1));
+
+    // reserve-then-claim
+    MemoryRegion reserved = allocateVirtualMemory(8 * page);
+    claimVirtualMemory({ reserved.get(), 2 * page });
+    reserved[2 * page - 1] = 5;
+    REQUIRE_EQ(reserved[2 * page - 1], 5);
+}
+
+TEST_CASE("batch helpers: validity, ids and status objects", "[util]")
+{
+    auto ber = batchExecFactory("demo", "echo", 3);
+    REQUIRE(isBatchExecRequestValid(ber));
+    REQUIRE_EQ(ber->messages_size(), 3);
+    for (const auto& m : ber->messages()) {
+        REQUIRE_EQ(m.appid(), ber->appid());
+        REQUIRE_EQ(m.user(), std::string("demo"));
+    }
+    REQUIRE(!isBatchExecRequestValid(nullptr));
+    // a message that disagrees with the request invalidates it
+    auto broken = batchExecFactory("demo", "echo", 2);
+    broken->mutable_messages(1)->set_function("other");
+    REQUIRE(!isBatchExecRequestValid(broken));
+    auto wrongApp = batchExecFactory("demo", "echo", 2);
+    wrongApp->mutable_messages(0)->set_appid(wrongApp->appid() + 1);
+    REQUIRE(!isBatchExecRequestValid(wrongApp));
+    REQUIRE(!isBatchExecRequestValid(batchExecFactory()));
+
+    updateBatchExecAppId(ber, 4321);
+    updateBatchExecGroupId(ber, 8765);
+    REQUIRE_EQ(ber->appid(), 4321);
+    REQUIRE_EQ(ber->groupid(), 8765);
+    for (const auto& m : ber->messages()) {
+        REQUIRE_EQ(m.appid(), 4321);
+        REQUIRE_EQ(m.groupid(), 8765);
+    }
+    REQUIRE(isBatchExecRequestValid(ber));
+
+    auto status = batchExecStatusFactory(ber);
+    REQUIRE_EQ(status->appid(), 4321);
+    REQUIRE_EQ(status->expectednummessages(), 3);
+    REQUIRE(!status->finished());
+    REQUIRE_EQ(batchExecStatusFactory(99)->appid(), 99);
+}
+
+TEST_CASE("function helpers: names, keys and async responses", "[util]")
+{
+    auto msg = messageFactory("demo", "echo");
+    REQUIRE(msg.id() > 0);
+    REQUIRE_EQ(funcToString(msg, false), std::string("demo/echo"));
+    REQUIRE_EQ(funcToString(msg, true), "demo/echo:" + std::to_string(msg.id()));
+    auto ber = batchExecFactory("demo", "echo", 2);
+    REQUIRE_EQ(funcToString(ber), "demo/echo:" + std::to_string(ber->appid()));
+
+    // ids: kept when present, generated (with the derived keys) when missing
+    unsigned int original = msg.id();
+    REQUIRE_EQ(setMessageId(msg), original);
+    faabric::Message blank;
+    unsigned int fresh = setMessageId(blank);
+    REQUIRE(fresh > 0);
+    REQUIRE_EQ(blank.id(), (int)fresh);
+    REQUIRE_EQ(blank.resultkey(), resultKeyFromMessageId(fresh));
+    REQUIRE_EQ(blank.statuskey(), statusKeyFromMessageId(fresh));
+    REQUIRE(resultKeyFromMessageId(7) != statusKeyFromMessageId(7));
+    REQUIRE_EQ(buildAsyncResponse(msg), std::to_string(msg.id()));
+
+    // every thread of an app shares one main-thread snapshot key
+    auto other = messageFactory("demo", "echo");
+    other.set_appid(msg.appid());
+    REQUIRE_EQ(getMainThreadSnapshotKey(msg), getMainThreadSnapshotKey(other));
+    other.set_appid(msg.appid() + 1);
+    REQUIRE(getMainThreadSnapshotKey(msg) != getMainThreadSnapshotKey(other));
+
+    msg.set_cmdline("prog --alpha 1  beta");
+    auto argv = getArgvForMessage(msg);
+    REQUIRE(argv == (std::vector<std::string>{ "function.wasm", "prog", "--alpha", "1", "beta" }));
+
+    auto shared = messageFactoryShared("demo", "x");
+    REQUIRE(shared != nullptr && shared->function() == "x");
+    // wire round trip
+    faabric::Message parsed;
+    auto bytes = messageToBytes(msg);
+    REQUIRE(parsed.ParseFromArray(bytes.data(), (int)bytes.size()));
+    REQUIRE_EQ(parsed.id(), msg.id());
+    REQUIRE_EQ(parsed.cmdline(), msg.cmdline());
+}
