@@ -353,6 +353,107 @@ static void registerFunctions()
         return 0;
     });
 
+    // Many messages / collectives back to back (reference dist tests
+    // mpi_send_many, mpi_reduce_many, mpi_alltoall_many, mpi_send_sync_async,
+    // mpi_typesize)
+    mpiFunction("send-many", [](int rank, int size, faabric::Message&) {
+        const int n = 2000;
+        if (rank == 0) {
+            for (int i = 0; i < n; i++) {
+                for (int r = 1; r < size; r++) {
+                    int v = i * size + r;
+                    MPI_Send(&v, 1, MPI_INT, r, 0, MPI_COMM_WORLD);
+                }
+            }
+        } else {
+            for (int i = 0; i < n; i++) {
+                int v = -1;
+                MPI_Recv(&v, 1, MPI_INT, 0, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+                EXPECT(v == i * size + rank);
+            }
+        }
+        return 0;
+    });
+
+    mpiFunction("reduce-many", [](int rank, int size, faabric::Message&) {
+        for (int i = 0; i < 300; i++) {
+            int root = i % size;
+            long mine[3] = { rank + i, 2L * rank, 1 }, out[3] = { 0, 0, 0 };
+            MPI_Reduce(mine, out, 3, MPI_LONG, MPI_SUM, root, MPI_COMM_WORLD);
+            if (rank == root) {
+                long base = (long)size * (size - 1) / 2;
+                EXPECT(out[0] == base + (long)i * size && out[1] == 2 * base && out[2] == size);
+            }
+        }
+        return 0;
+    });
+
+    mpiFunction("alltoall-many", [](int rank, int size, faabric::Message&) {
+        std::vector<int> out(size * 4), in(size * 4);
+        for (int i = 0; i < 200; i++) {
+            for (int r = 0; r < size; r++) {
+                for (int k = 0; k < 4; k++) {
+                    out[r * 4 + k] = i * 1000 + rank * 10 + r;
+                }
+            }
+            MPI_Alltoall(out.data(), 4, MPI_INT, in.data(), 4, MPI_INT, MPI_COMM_WORLD);
+            for (int r = 0; r < size; r++) {
+                EXPECT(in[r * 4] == i * 1000 + r * 10 + rank && in[r * 4 + 3] == in[r * 4]);
+            }
+        }
+        return 0;
+    });
+
+    mpiFunction("sync-async", [](int rank, int size, faabric::Message&) {
+        // every rank in turn sends to all: blocking first, then non-blocking
+        for (int sender = 0; sender < size; sender++) {
+            if (rank == sender) {
+                std::vector<MPI_Request> reqs;
+                std::vector<int> vals(size);
+                for (int r = 0; r < size; r++) {
+                    if (r == rank) {
+                        continue;
+                    }
+                    int v = sender * 100 + r;
+                    MPI_Send(&v, 1, MPI_INT, r, 0, MPI_COMM_WORLD);
+                    vals[r] = v + 1;
+                    MPI_Request rq;
+                    MPI_Isend(&vals[r], 1, MPI_INT, r, 0, MPI_COMM_WORLD, &rq);
+                    reqs.push_back(rq);
+                }
+                MPI_Waitall((int)reqs.size(), reqs.data(), MPI_STATUSES_IGNORE);
+            } else {
+                int a = -1, b = -1;
+                MPI_Request rq;
+                MPI_Recv(&a, 1, MPI_INT, sender, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+                MPI_Irecv(&b, 1, MPI_INT, sender, 0, MPI_COMM_WORLD, &rq);
+                MPI_Wait(&rq, MPI_STATUS_IGNORE);
+                EXPECT(a == sender * 100 + rank && b == a + 1);
+            }
+        }
+        return 0;
+    });
+
+    mpiFunction("typesize", [](int rank, int size, faabric::Message&) {
+        struct Expect
+        {
+            MPI_Datatype type;
+            int bytes;
+        };
+        const Expect table[] = {
+            { MPI_INT8_T, 1 },   { MPI_INT16_T, 2 },  { MPI_INT32_T, 4 },  { MPI_INT64_T, 8 },   { MPI_UINT8_T, 1 },
+            { MPI_UINT16_T, 2 }, { MPI_UINT32_T, 4 }, { MPI_UINT64_T, 8 }, { MPI_INT, 4 },       { MPI_LONG, 8 },
+            { MPI_LONG_LONG, 8 }, { MPI_FLOAT, 4 },   { MPI_DOUBLE, 8 },   { MPI_DOUBLE_INT, 16 }, { MPI_CHAR, 1 },
+            { MPI_BYTE, 1 },
+        };
+        for (const auto& e : table) {
+            int got = 0;
+            MPI_Type_size(e.type, &got);
+            EXPECT(got == e.bytes);
+        }
+        return 0;
+    });
+
     // Sub-communicators whose members sit in different worker processes
     mpiFunction("subcomm", [](int rank, int size, faabric::Message& msg) {
         MPI_Comm half = nullptr;

@@ -87,6 +87,11 @@ MPI_FUNCTIONS = [
     "cart",
     "rma",
     "subcomm",
+    "send-many",
+    "reduce-many",
+    "alltoall-many",
+    "sync-async",
+    "typesize",
 ]
 
 
