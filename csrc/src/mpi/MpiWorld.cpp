@@ -425,6 +425,30 @@ bool MpiWorld::destroy()
     if (!tls.requests.empty()) {
         SPDLOG_WARN("Destroying world {} with {} outstanding async requests on rank {}", id, tls.requests.size(), tls.rank);
     }
+    // Device-plane counters of this rank travel with the exec graph (HTTP
+    // GET_EXEC_GRAPH): launches, bytes and the algorithm mix
+    std::shared_ptr<faabric::device::Communicator> myComm;
+    if (tls.msg != nullptr && tls.msg->recordexecgraph()) {
+        // (only look, never wire the device plane up just for this)
+        std::lock_guard<std::mutex> lk(deviceMx);
+        if (tls.rank >= 0 && tls.rank < (int)deviceComms.size()) {
+            myComm = deviceComms[tls.rank];
+        }
+    }
+    if (myComm != nullptr) {
+        const faabric::device::CommStats& st = myComm->stats();
+        auto* details = tls.msg->mutable_intexecgraphdetails();
+        (*details)["mpi-device-launches"] = (int)std::min<uint64_t>(st.launches, INT32_MAX);
+        (*details)["mpi-device-mbytes"] = (int)std::min<uint64_t>(st.bytes >> 20, INT32_MAX);
+        (*details)["mpi-device-staged-copies"] = (int)std::min<uint64_t>(st.stagedCopies, INT32_MAX);
+        (*details)["mpi-device-tma-launches"] = (int)std::min<uint64_t>(st.tmaLaunches, INT32_MAX);
+        for (int a = 1; a < FB_ALGO_COUNT; a++) {
+            if (st.algoCount[a] > 0) {
+                (*details)[std::string("mpi-device-algo-") + faabric::device::CommTuning::algoName(a)] =
+                  (int)std::min<uint64_t>(st.algoCount[a], INT32_MAX);
+            }
+        }
+    }
     tls.reset();
     int left = activeLocalRanks.fetch_sub(1) - 1;
     // Only a host the world has migrated away from clears it eagerly; otherwise
