@@ -57,6 +57,11 @@ CXX_FLAGS = [
 _SAN = os.environ.get("FAABRIC_B200_SANITISE", "")
 if _SAN:
     CXX_FLAGS += [f"-fsanitize={_SAN}", "-O1"]
+# FAABRIC_B200_COVERAGE=1: gcov instrumentation of the host code (the
+# reference's FAABRIC_CODE_COVERAGE option); see `cli coverage`
+_COV = os.environ.get("FAABRIC_B200_COVERAGE", "") not in ("", "0")
+if _COV:
+    CXX_FLAGS = [f for f in CXX_FLAGS if f != "-O2"] + ["--coverage", "-O0"]
 INCLUDES = [
     f"-I{CSRC / 'include'}",
     f"-I{CSRC / 'kernels'}",
@@ -218,6 +223,7 @@ def build(force: bool = False, bins: bool = True, jobs: int | None = None, verbo
                 "-Wl,--export-dynamic",
             ]
             + ([f"-fsanitize={_SAN}"] if _SAN else [])
+            + (["--coverage"] if _COV else [])
         )
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -272,6 +278,7 @@ def _build_bins(stamp, relink: bool, verbose: bool) -> None:
                         "-ldl",
                     ]
                     + ([f"-fsanitize={_SAN}"] if _SAN else [])
+                    + (["--coverage"] if _COV else [])
                 )
                 r = subprocess.run(cmd, capture_output=True, text=True)
                 if r.returncode != 0:

@@ -27,6 +27,61 @@ def _run(cmd, **kw):
     return subprocess.call(cmd, **kw)
 
 
+def _coverage() -> int:
+    """Line coverage of the host code by the C++ suite and the multi-process
+    tests (gcov; the reference's `inv dev.coverage-report`)."""
+    import glob
+    import gzip  # noqa: F401  (gcov -t prints plain JSON)
+    import subprocess
+
+    env = dict(os.environ)
+    env["FAABRIC_B200_COVERAGE"] = "1"
+    if os.path.exists("/usr/bin/g++"):
+        env["CXX"] = "/usr/bin/g++"
+    obj = ROOT / "build" / "obj"
+    for f in glob.glob(str(obj / "*.gcda")):
+        os.unlink(f)
+    rc = _run([sys.executable, "-m", "faabric_b200.build", "--force"], cwd=ROOT, env=env)
+    if rc != 0:
+        return rc
+    _run([str(ROOT / "build" / "bin" / "faabric_tests")], env=env)
+    _run([sys.executable, "-m", "pytest", "tests", "-q", "-m", "not gpu"], cwd=ROOT, env=env)
+    per_file: dict[str, dict[int, int]] = {}
+    for gcda in sorted(glob.glob(str(obj / "*.gcda"))):
+        r = subprocess.run(["gcov", "-j", "-t", gcda], capture_output=True, text=True, cwd=obj)
+        if r.returncode != 0 or not r.stdout.strip():
+            continue
+        for doc in r.stdout.splitlines():
+            try:
+                data = json.loads(doc)
+            except ValueError:
+                continue
+            for f in data.get("files", []):
+                name = os.path.normpath(os.path.join(str(obj), f["file"]))
+                if "/csrc/src/" not in name and "/csrc/capi/" not in name:
+                    continue
+                lines = per_file.setdefault(name, {})
+                for ln in f["lines"]:
+                    lines[ln["line_number"]] = lines.get(ln["line_number"], 0) + ln["count"]
+    by_dir: dict[str, list[int]] = {}
+    for name, lines in per_file.items():
+        d = os.path.relpath(os.path.dirname(name), ROOT / "csrc")
+        tot = by_dir.setdefault(d, [0, 0])
+        tot[0] += sum(1 for c in lines.values() if c > 0)
+        tot[1] += len(lines)
+    print(f"{'directory':<28}{'lines':>8}{'covered':>9}{'%':>7}")
+    all_cov = all_tot = 0
+    for d in sorted(by_dir):
+        cov, tot = by_dir[d]
+        all_cov += cov
+        all_tot += tot
+        print(f"{d:<28}{tot:>8}{cov:>9}{100.0 * cov / max(tot, 1):>7.1f}")
+    print(f"{'TOTAL':<28}{all_tot:>8}{all_cov:>9}{100.0 * all_cov / max(all_tot, 1):>7.1f}")
+    (ROOT / "build" / "coverage.json").write_text(json.dumps({"dirs": by_dir, "covered": all_cov, "lines": all_tot}))
+    print("(rebuild without instrumentation: python -m faabric_b200.build --force)")
+    return 0
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="faabric_b200.cli")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -50,6 +105,7 @@ def main(argv=None):
     i.add_argument("--port", type=int, default=8080)
     s = sub.add_parser("sanitise")
     s.add_argument("kind", choices=["address", "thread", "undefined"])
+    sub.add_parser("coverage")
     sa = sub.add_parser("sass")
     sa.add_argument("regex")
     a = ap.parse_args(argv)
@@ -95,6 +151,8 @@ def main(argv=None):
         if rc != 0:
             return rc
         return _run([str(ROOT / "build" / "bin" / "faabric_tests")], env=env)
+    if a.cmd == "coverage":
+        return _coverage()
     if a.cmd == "sass":
         lib = ROOT / "faabric_b200" / "lib" / "libfaabric_b200.so"
         return _run(["bash", "-c", f"cuobjdump -sass {lib} | grep -E -A400 'Function : .*({a.regex})' | head -n 600"])
