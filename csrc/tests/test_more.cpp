@@ -249,6 +249,54 @@ TEST_CASE("runner boots and shuts a worker down", "[runner]")
     faabric::scheduler::getScheduler().reset();
 }
 
+TEST_CASE("local cluster: one process serves a planner and per-GPU virtual hosts", "[runner]")
+{
+    registerTestFunction("demo", "where", [](auto*, int, int idx, auto req) {
+        auto& m = *req->mutable_messages(idx);
+        m.set_outputdata(m.executedhost());
+        return 0;
+    });
+    {
+        faabric::runner::LocalCluster cluster(std::make_shared<TestExecutorFactory>(), 4, 2);
+        REQUIRE_EQ(cluster.hosts().size(), (size_t)4);
+        auto hosts = faabric::planner::getPlannerClient().getAvailableHosts();
+        REQUIRE_EQ(hosts.size(), (size_t)4);
+        std::set<std::string> names;
+        for (auto& h : hosts) {
+            names.insert(h.ip());
+            REQUIRE_EQ(h.slots(), 2);
+        }
+        REQUIRE(names == std::set<std::string>(cluster.hosts().begin(), cluster.hosts().end()));
+        // eight functions fill every virtual host
+        auto req = faabric::util::batchExecFactory("demo", "where", 8);
+        auto decision = faabric::planner::getPlannerClient().callFunctions(req);
+        REQUIRE_EQ(decision.nFunctions, 8);
+        auto status = cluster.awaitBatch(req, 20000);
+        REQUIRE_EQ(status->messageresults_size(), 8);
+        std::map<std::string, int> perHost;
+        for (auto& m : status->messageresults()) {
+            REQUIRE_EQ(m.returnvalue(), 0);
+            perHost[m.executedhost()]++;
+        }
+        REQUIRE_EQ(perHost.size(), (size_t)4);
+        for (auto& [h, n] : perHost) {
+            REQUIRE_EQ(n, 2);
+        }
+        // a batch nobody submitted is not in flight: no results, no waiting
+        auto ghost = faabric::util::batchExecFactory("demo", "where", 1);
+        REQUIRE_EQ(cluster.awaitBatch(ghost, 100)->messageresults_size(), 0);
+    }
+    // a plain cluster: just this host
+    {
+        faabric::runner::LocalCluster plain(std::make_shared<TestExecutorFactory>(), 0, 3);
+        REQUIRE_EQ(plain.hosts().size(), (size_t)1);
+        auto hosts = faabric::planner::getPlannerClient().getAvailableHosts();
+        REQUIRE_EQ(hosts.size(), (size_t)1);
+        REQUIRE_EQ(hosts[0].slots(), 3);
+    }
+    faabric::scheduler::getScheduler().reset();
+}
+
 TEST_CASE("runner checkpoints snapshots across a worker restart", "[runner][checkpoint]")
 {
     const std::string dir = "/tmp/fb_runner_ckpt_" + std::to_string(getpid());
