@@ -110,6 +110,19 @@ def test_mpi_across_two_workers(cluster, fn):
         assert all(m["output_data"] == "node of 2" for m in res), res
 
 
+def test_mpi_across_three_workers(tmp_path):
+    """Six ranks over three worker processes: every rank has peers in its own
+    process and in two others (pairwise fence exchanges, sub-communicators
+    that straddle processes, two-level collectives with three leaders)."""
+    with LocalCluster(n_workers=3, slots_per_worker=2, log_dir=tmp_path) as c:
+        for fn in ("rma", "subcomm", "reduce-scan", "alltoall"):
+            st = c.client.invoke("mpi", fn, mpi_world_size=6, timeout=60)
+            res = _results(st)
+            assert len(res) == 6, (fn, res)
+            assert all(m.get("returnValue", 0) == 0 for m in res), (fn, res)
+            assert len({m["executedHost"] for m in res}) == 3, (fn, res)
+
+
 def test_mpi_benchmarks_report(cluster):
     st = cluster.client.invoke("mpi", "bench-pingpong", mpi_world_size=2, input_data="64", timeout=120)
     out = json.loads(_results(st)[0]["output_data"])
