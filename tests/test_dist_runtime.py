@@ -123,6 +123,43 @@ def test_mpi_across_three_workers(tmp_path):
             assert len({m["executedHost"] for m in res}) == 3, (fn, res)
 
 
+def test_servers_survive_garbage_on_every_port(tmp_path):
+    """Random bytes, truncated frames and absurd length fields on every
+    listening port of the planner and the workers (RPC, HTTP): connections are
+    dropped, the processes keep serving."""
+    import random
+    import socket
+
+    import psutil
+
+    with LocalCluster(n_workers=2, slots_per_worker=2, log_dir=tmp_path) as c:
+        children = psutil.Process().children(recursive=True)
+        ports = set()
+        for ch in children:
+            try:
+                for con in ch.net_connections(kind="tcp"):
+                    if con.status == "LISTEN":
+                        ports.add(con.laddr.port)
+            except psutil.Error:
+                pass
+        assert len(ports) >= 6, ports
+        rnd = random.Random(7)
+        for p in sorted(ports):
+            for i in range(12):
+                try:
+                    with socket.create_connection(("127.0.0.1", p), timeout=1) as s:
+                        n = rnd.choice([1, 7, 16, 17, 64, 1000, 70000])
+                        s.sendall(bytes(rnd.getrandbits(8) for _ in range(n)))
+                        if i % 3 == 0:
+                            s.sendall(b"\x05\x00\x00\x00" + (2**40).to_bytes(8, "little") + b"\x00" * 4)
+                except OSError:
+                    pass
+        assert all(ch.is_running() and ch.status() != psutil.STATUS_ZOMBIE for ch in children)
+        assert len(c.client.available_hosts()) == 2
+        st = c.client.invoke("mpi", "allreduce", mpi_world_size=4, timeout=60)
+        assert [m.get("returnValue", 0) for m in _results(st)] == [0, 0, 0, 0]
+
+
 def test_mpi_benchmarks_report(cluster):
     st = cluster.client.invoke("mpi", "bench-pingpong", mpi_world_size=2, input_data="64", timeout=120)
     out = json.loads(_results(st)[0]["output_data"])
