@@ -160,6 +160,33 @@ def test_servers_survive_garbage_on_every_port(tmp_path):
         assert [m.get("returnValue", 0) for m in _results(st)] == [0, 0, 0, 0]
 
 
+def test_killed_worker_expires_and_the_rest_keep_serving(tmp_path):
+    """Failure detection is membership by keep-alive (reference
+    src/planner/Planner.cpp:267-291): a worker that dies silently drops out of
+    the host set after the timeout and new batches avoid it."""
+    import signal
+    import time
+
+    with LocalCluster(
+        n_workers=2, slots_per_worker=2, log_dir=tmp_path, extra_env={"PLANNER_HOST_KEEPALIVE_TIMEOUT": "1"}
+    ) as c:
+        assert len(c.client.available_hosts()) == 2
+        survivor = c.worker_hosts()[0]
+        victim = c.procs[-1]
+        victim.send_signal(signal.SIGKILL)
+        victim.wait()
+        deadline = time.time() + 10
+        while time.time() < deadline and len(c.client.available_hosts()) != 1:
+            time.sleep(0.1)
+        hosts = c.client.available_hosts()
+        assert [h["ip"] for h in hosts] == [survivor], hosts
+        st = c.client.invoke("demo", "hello", count=2, timeout=30)
+        assert [m["output_data"] for m in st["messageResults"]] == [f"hello from {survivor}"] * 2
+        # a batch larger than what is left is refused, not queued
+        with pytest.raises(PlannerError):
+            c.client.invoke("demo", "hello", count=3, timeout=10)
+
+
 def test_mpi_benchmarks_report(cluster):
     st = cluster.client.invoke("mpi", "bench-pingpong", mpi_world_size=2, input_data="64", timeout=120)
     out = json.loads(_results(st)[0]["output_data"])
