@@ -22,6 +22,10 @@ def _free_port() -> int:
 
 
 _instances = 0
+# port slots of clusters that are up right now (a long-lived fixture must not
+# be hit by the rotation coming round again)
+_live_slots: set = set()
+_N_SLOTS = 5
 
 
 class LocalCluster:
@@ -50,10 +54,19 @@ class LocalCluster:
         # instances in this process by a counter.  Offsets stay far below the
         # ephemeral port range (highest port = 8100 + offset + 100 * workers)
         global _instances
+        self._slot = None
         if base_offset is None:
             # (everything stays below 32768, the start of the ephemeral range:
             # a listening port there can collide with an outgoing connection)
-            base_offset = 1000 + (os.getpid() % 7) * 3000 + (_instances % 5) * 600
+            for probe in range(_N_SLOTS):
+                slot = (_instances + probe) % _N_SLOTS
+                if slot not in _live_slots:
+                    break
+            else:
+                raise RuntimeError(f"more than {_N_SLOTS} LocalClusters alive in one process")
+            self._slot = slot
+            _live_slots.add(slot)
+            base_offset = 1000 + (os.getpid() % 7) * 3000 + slot * 600
         _instances += 1
         self.base_offset = base_offset
         self.procs: list[subprocess.Popen] = []
@@ -132,6 +145,15 @@ class LocalCluster:
                 p.kill()
                 p.wait()
         self.procs.clear()
+        if self._slot is not None:
+            _live_slots.discard(self._slot)
+            self._slot = None
+
+    def __del__(self):
+        # a cluster that was never started (or never stopped) gives its slot back
+        slot = getattr(self, "_slot", None)
+        if slot is not None:
+            _live_slots.discard(slot)
 
     def __enter__(self):
         return self.start()
