@@ -816,9 +816,18 @@ int MPI_Win_get_attr(MPI_Win win, int win_keyval, void* attribute_val, int* flag
         case MPI_WIN_BASE:
             *((void**)attribute_val) = win->basePtr;
             break;
-        case MPI_WIN_SIZE:
-            *((MPI_Aint*)attribute_val) = (MPI_Aint)win->size;
+        case MPI_WIN_SIZE: {
+            // (the handle's `size` field is an int as in the reference; the
+            // world keeps the real extent for windows beyond 2 GiB)
+            void* base = nullptr;
+            int64_t bytes = win->size;
+            int unit = 0;
+            if (win->id > 0) {
+                getExecutingWorld().winQuery(win->id, win->rank, &base, &bytes, &unit);
+            }
+            *((MPI_Aint*)attribute_val) = (MPI_Aint)bytes;
             break;
+        }
         case MPI_WIN_DISP_UNIT:
             *((int*)attribute_val) = win->dispUnit;
             break;
@@ -892,7 +901,7 @@ int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_
     MpiWorld& world = getExecutingWorld();
     const int rank = executingContext.getRank();
     int winId = world.winCreate(rank, base, (int64_t)size, disp_unit);
-    *win = new faabric_win_t{ world.getId(), rank, (int)size, base, disp_unit, winId, nullptr };
+    *win = new faabric_win_t{ world.getId(), rank, (int)std::min<MPI_Aint>(size, INT32_MAX), base, disp_unit, winId, nullptr };
     return MPI_SUCCESS;
 }
 
@@ -925,7 +934,7 @@ int MPI_Win_allocate_shared(MPI_Aint size, int disp_unit, MPI_Info info, MPI_Com
     const int rank = executingContext.getRank();
     int winId = world.winCreate(rank, mem, (int64_t)size, disp_unit);
     *((void**)baseptr) = mem;
-    *win = new faabric_win_t{ world.getId(), rank, (int)size, mem, disp_unit, winId, mem };
+    *win = new faabric_win_t{ world.getId(), rank, (int)std::min<MPI_Aint>(size, INT32_MAX), mem, disp_unit, winId, mem };
     return MPI_SUCCESS;
 }
 
