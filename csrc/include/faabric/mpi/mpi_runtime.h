@@ -131,6 +131,9 @@ bool unregisterUserOp(int opId);
 
 bool getUserOp(int opId, MPI_User_function** fn, bool* commutes);
 
+// True for user operations created with commute = 0 (rank-ordered fold)
+bool isOrderedUserOp(const faabric_op_t* op);
+
 inline bool isUserOp(const faabric_op_t* op)
 {
     return op != nullptr && op->id >= FAABRIC_OP_USER_BASE;
