@@ -510,6 +510,8 @@ class MpiWorld
     void sharedBroadcast(int root, int rank, uint8_t* buffer, size_t bytes);
     void sharedAllGather(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t sendBytes);
     void sharedAllToAll(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t chunkBytes);
+    void sharedGather(int rank, int root, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t sendBytes, bool rootInPlace);
+    void sharedScatter(int rank, int root, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t chunkBytes);
     void sharedReduce(int rank, int root, uint8_t* sendBuffer, uint8_t* recvBuffer, faabric_datatype_t* datatype, int count, faabric_op_t* operation);
     bool trySharedMemoryAllReduce(int rank,
                                   uint8_t* sendBuffer,

@@ -1316,6 +1316,15 @@ void MpiWorld::scatter(int sendRank,
             return;
         }
     }
+    {
+        // counts on the sending side only mean something at the root
+        const size_t myChunk = recvRank == sendRank ? chunk : (size_t)recvCount * recvType->size;
+        if (!isDevicePointer(recvBuffer) && !(recvRank == sendRank && isDevicePointer(sendBuffer)) &&
+            sharedMemoryEligible(myChunk * size)) {
+            sharedScatter(recvRank, sendRank, sendBuffer, recvBuffer, myChunk);
+            return;
+        }
+    }
     // Flat: the root sends chunk r to rank r
     if (recvRank == sendRank) {
         HostStage in;
@@ -1362,6 +1371,10 @@ void MpiWorld::gather(int sendRank,
         }
     }
 
+    if (!isDevicePointer(sendBuffer) && !(isRoot && isDevicePointer(recvBuffer)) && sharedMemoryEligible(sendBytes * size)) {
+        sharedGather(sendRank, recvRank, sendBuffer, recvBuffer, sendBytes, inPlace);
+        return;
+    }
     const std::string rootHost = getHostForRank(recvRank);
     const bool rootIsLocal = rootHost == thisHost;
     std::set<int> localRanks;
@@ -1573,14 +1586,9 @@ void MpiWorld::orderedReduce(int sendRank,
         gather(sendRank, recvRank, sendBuffer, datatype, count, nullptr, datatype, count);
         return;
     }
+    // (`all` never aliases the user's buffers, in-place reduce or not)
     std::vector<uint8_t> all(bytes * (size_t)size);
-    if (sendBuffer == recvBuffer) {
-        // gather's in-place convention: the root's chunk already sits in place
-        memcpy(all.data() + (size_t)recvRank * bytes, sendBuffer, bytes);
-        gather(sendRank, recvRank, all.data() + (size_t)recvRank * bytes, datatype, count, all.data(), datatype, count);
-    } else {
-        gather(sendRank, recvRank, sendBuffer, datatype, count, all.data(), datatype, count);
-    }
+    gather(sendRank, recvRank, sendBuffer, datatype, count, all.data(), datatype, count);
     memcpy(recvBuffer, all.data() + (size_t)(size - 1) * bytes, bytes);
     for (int r = size - 2; r >= 0; r--) {
         op_reduce(operation, datatype, count, all.data() + (size_t)r * bytes, recvBuffer);

@@ -164,6 +164,40 @@ void MpiWorld::sharedAllToAll(int rank, const uint8_t* sendBuffer, uint8_t* recv
     hc->barrier(timeoutMs);
 }
 
+void MpiWorld::sharedGather(int rank, int root, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t sendBytes, bool rootInPlace)
+{
+    HostCollective* hc = hostCollective.get();
+    const int timeoutMs = faabric::util::getSystemConfig().globalMessageTimeout;
+    hc->sendPtrs[rank] = sendBuffer;
+    hc->barrier(timeoutMs);
+    if (rank == root) {
+        for (int p = 0; p < hc->nRanks; p++) {
+            uint8_t* dst = recvBuffer + (size_t)p * sendBytes;
+            // (in place: the root passes the receive buffer itself and its
+            // chunk already sits in its slot)
+            if (!(p == root && rootInPlace) && dst != hc->sendPtrs[p]) {
+                memcpy(dst, hc->sendPtrs[p], sendBytes);
+            }
+        }
+    }
+    hc->barrier(timeoutMs);
+}
+
+void MpiWorld::sharedScatter(int rank, int root, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t chunkBytes)
+{
+    HostCollective* hc = hostCollective.get();
+    const int timeoutMs = faabric::util::getSystemConfig().globalMessageTimeout;
+    if (rank == root) {
+        hc->sendPtrs[root] = sendBuffer;
+    }
+    hc->barrier(timeoutMs);
+    const uint8_t* mine = hc->sendPtrs[root] + (size_t)rank * chunkBytes;
+    if (recvBuffer != nullptr && recvBuffer != mine) {
+        memcpy(recvBuffer, mine, chunkBytes);
+    }
+    hc->barrier(timeoutMs);
+}
+
 void MpiWorld::sharedReduce(int rank,
                             int root,
                             uint8_t* sendBuffer,

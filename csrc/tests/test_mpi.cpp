@@ -403,6 +403,30 @@ int bodyLargeHostCollectives(int rank, int size)
         CHECK_RANK(inPlace[(size_t)r * per + 17] == 10 * r);
     }
 
+    // gather to / scatter from a non-zero root, plus the in-place forms
+    const int gRoot = size / 2;
+    std::vector<int> gathered(rank == gRoot ? (size_t)per * size : 0, -1);
+    MPI_Gather(mine.data(), per, MPI_INT, gathered.data(), per, MPI_INT, gRoot, MPI_COMM_WORLD);
+    if (rank == gRoot) {
+        for (int r = 0; r < size; r++) {
+            CHECK_RANK(gathered[(size_t)r * per] == r + 1 && gathered[(size_t)r * per + per - 1] == r + 1);
+        }
+        std::fill(gathered.begin(), gathered.end(), -1);
+        std::fill(gathered.begin() + (size_t)rank * per, gathered.begin() + (size_t)(rank + 1) * per, rank + 1);
+        MPI_Gather(MPI_IN_PLACE, 0, MPI_DATATYPE_NULL, gathered.data(), per, MPI_INT, gRoot, MPI_COMM_WORLD);
+        for (int r = 0; r < size; r++) {
+            CHECK_RANK(gathered[(size_t)r * per + 3] == r + 1);
+        }
+    } else {
+        MPI_Gather(mine.data(), per, MPI_INT, nullptr, 0, MPI_DATATYPE_NULL, gRoot, MPI_COMM_WORLD);
+    }
+    std::vector<int> toScatter(rank == gRoot ? (size_t)per * size : 0), piece(per, -1);
+    for (size_t i = 0; i < toScatter.size(); i++) {
+        toScatter[i] = (int)(i / per) * 7;
+    }
+    MPI_Scatter(toScatter.data(), per, MPI_INT, piece.data(), per, MPI_INT, gRoot, MPI_COMM_WORLD);
+    CHECK_RANK(piece[0] == rank * 7 && piece[per - 1] == rank * 7);
+
     // alltoall: chunk for rank r carries (me, r)
     std::vector<int> out((size_t)per * size), in((size_t)per * size, -1);
     for (int r = 0; r < size; r++) {
