@@ -693,6 +693,44 @@ static void registerFunctions()
 
     // The headline: one "step" of ResNet-50 gradient sync = one int32
     // MPI_Allreduce per parameter tensor, on host memory (reference CPU path)
+    // Host-buffer collectives, "bytesPerRank[,steps]": microseconds per call
+    mpiFunction("bench-collectives", [](int rank, int size, faabric::Message& msg) {
+        size_t bytes = 1 << 20;
+        int steps = 20;
+        if (!msg.inputdata().empty()) {
+            auto comma = msg.inputdata().find(',');
+            bytes = std::stoul(msg.inputdata().substr(0, comma));
+            if (comma != std::string::npos) {
+                steps = std::stoi(msg.inputdata().substr(comma + 1));
+            }
+        }
+        const int n = (int)(bytes / sizeof(int));
+        std::vector<int> mine(n, rank + 1), big((size_t)n * size, 0), other((size_t)n * size, rank);
+        std::string json = "{\"bytes_per_rank\": " + std::to_string(bytes) + ", \"ranks\": " + std::to_string(size);
+        auto timeIt = [&](const char* name, const std::function<void()>& call) {
+            call();
+            MPI_Barrier(MPI_COMM_WORLD);
+            auto t0 = std::chrono::steady_clock::now();
+            for (int i = 0; i < steps; i++) {
+                call();
+            }
+            MPI_Barrier(MPI_COMM_WORLD);
+            double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / steps;
+            json += std::string(", \"") + name + "_us\": " + std::to_string(us);
+        };
+        timeIt("bcast", [&] { MPI_Bcast(mine.data(), n, MPI_INT, 0, MPI_COMM_WORLD); });
+        timeIt("reduce", [&] { MPI_Reduce(mine.data(), big.data(), n, MPI_INT, MPI_SUM, 0, MPI_COMM_WORLD); });
+        timeIt("allreduce", [&] { MPI_Allreduce(mine.data(), big.data(), n, MPI_INT, MPI_SUM, MPI_COMM_WORLD); });
+        timeIt("gather", [&] { MPI_Gather(mine.data(), n, MPI_INT, big.data(), n, MPI_INT, 0, MPI_COMM_WORLD); });
+        timeIt("scatter", [&] { MPI_Scatter(other.data(), n, MPI_INT, mine.data(), n, MPI_INT, 0, MPI_COMM_WORLD); });
+        timeIt("allgather", [&] { MPI_Allgather(mine.data(), n, MPI_INT, big.data(), n, MPI_INT, MPI_COMM_WORLD); });
+        timeIt("alltoall", [&] { MPI_Alltoall(other.data(), n, MPI_INT, big.data(), n, MPI_INT, MPI_COMM_WORLD); });
+        if (rank == 0) {
+            msg.set_outputdata(json + "}");
+        }
+        return 0;
+    });
+
     mpiFunction("bench-allreduce", [](int rank, int size, faabric::Message& msg) {
         // "count[,steps]" in elements; default: a 25.6M-element model in 214
         // tensors is driven from Python, this is the single-size kernel

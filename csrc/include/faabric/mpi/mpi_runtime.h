@@ -497,7 +497,14 @@ class MpiWorld
     {
         int nRanks = 0;
         std::atomic<int> arrived{ 0 };
-        std::atomic<uint64_t> generation{ 0 };
+        // 32 bits: waiters park on it with futex(2)
+        std::atomic<uint32_t> generation{ 0 };
+        std::atomic<int> sleepers{ 0 };
+        // microseconds a waiter polls before it parks
+        int spinIterations = 0;
+        // smallest payload worth two barriers (copy collectives; all-reduce
+        // pays off from 32 KiB everywhere)
+        size_t minCopyBytes = 32 * 1024;
         std::vector<const uint8_t*> sendPtrs;
         std::vector<uint8_t*> recvPtrs;
 
@@ -506,7 +513,7 @@ class MpiWorld
     std::unique_ptr<HostCollective> hostCollective;
     // Rank-ordered fold at the root for non-commutative user operations
     void orderedReduce(int sendRank, int recvRank, uint8_t* sendBuffer, uint8_t* recvBuffer, faabric_datatype_t* datatype, int count, faabric_op_t* operation);
-    bool sharedMemoryEligible(size_t bytes) const { return hostCollective != nullptr && bytes >= 32 * 1024; }
+    bool sharedMemoryEligible(size_t bytes) const { return hostCollective != nullptr && bytes >= hostCollective->minCopyBytes; }
     void sharedBroadcast(int root, int rank, uint8_t* buffer, size_t bytes);
     void sharedAllGather(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t sendBytes);
     void sharedAllToAll(int rank, const uint8_t* sendBuffer, uint8_t* recvBuffer, size_t chunkBytes);

@@ -450,6 +450,13 @@ void MpiWorld::initLocalQueues()
     if (!referenceOnly && ranksForHost.size() == 1 && (int)it->second.size() == size && size > 1) {
         hostCollective = std::make_unique<HostCollective>();
         hostCollective->nRanks = size;
+        // Polling budget before a waiter parks: generous when ranks (plus the
+        // runtime's own threads) fit on the machine, token otherwise
+        const bool roomy = (unsigned)size * 2 <= faabric::util::getUsableCores();
+        hostCollective->spinIterations = roomy ? 200 : 20;
+        // parked waiters make the barriers dearer: measured break-even of the
+        // copy collectives moves from ~32 KiB to ~256 KiB
+        hostCollective->minCopyBytes = roomy ? 32 * 1024 : 256 * 1024;
         hostCollective->sendPtrs.assign(size, nullptr);
         hostCollective->recvPtrs.assign(size, nullptr);
     }

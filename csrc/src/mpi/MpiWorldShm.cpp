@@ -11,27 +11,60 @@
 #include <stdexcept>
 #include <thread>
 
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 namespace faabric::mpi {
 
+namespace {
+long futexCall(std::atomic<uint32_t>* addr, int op, uint32_t val, const timespec* timeout)
+{
+    return ::syscall(SYS_futex, reinterpret_cast<uint32_t*>(addr), op, val, timeout, nullptr, 0);
+}
+}
+
+// Sense-reversing barrier.  Waiters poll for a few microseconds when every rank
+// can have a core of its own, then park on a futex: a spinning waiter on an
+// oversubscribed machine only steals time from the rank everybody waits for.
 void MpiWorld::HostCollective::barrier(int timeoutMs)
 {
-    const uint64_t gen = generation.load(std::memory_order_acquire);
+    const uint32_t gen = generation.load(std::memory_order_acquire);
     if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == nRanks) {
         arrived.store(0, std::memory_order_relaxed);
-        generation.fetch_add(1, std::memory_order_release);
+        generation.fetch_add(1, std::memory_order_seq_cst);
+        if (sleepers.load(std::memory_order_seq_cst) > 0) {
+            futexCall(&generation, FUTEX_WAKE_PRIVATE, INT32_MAX, nullptr);
+        }
         return;
     }
     auto start = std::chrono::steady_clock::now();
-    for (int i = 0; generation.load(std::memory_order_acquire) == gen; i++) {
-        if ((i & 63) == 63) {
-            std::this_thread::yield();
-            auto waited = std::chrono::steady_clock::now() - start;
-            if (waited > std::chrono::milliseconds(timeoutMs)) {
-                throw std::runtime_error("Timed out in shared-memory MPI barrier (a rank is missing)");
+    // Phase 1: poll, handing the core over between bursts (`spinIterations`
+    // is the polling budget in microseconds)
+    while (true) {
+        for (int i = 0; i < 64; i++) {
+            if (generation.load(std::memory_order_acquire) != gen) {
+                return;
             }
-            if (waited > std::chrono::microseconds(200)) {
-                std::this_thread::sleep_for(std::chrono::microseconds(20));
-            }
+            __builtin_ia32_pause();
+        }
+        if (std::chrono::steady_clock::now() - start > std::chrono::microseconds(spinIterations)) {
+            break;
+        }
+        std::this_thread::yield();
+    }
+    // Phase 2: park
+    while (generation.load(std::memory_order_acquire) == gen) {
+        sleepers.fetch_add(1, std::memory_order_seq_cst);
+        // Re-checked by the kernel: returns at once if the generation moved on
+        timespec slice{ 0, 50 * 1000 * 1000 };
+        futexCall(&generation, FUTEX_WAIT_PRIVATE, gen, &slice);
+        sleepers.fetch_sub(1, std::memory_order_seq_cst);
+        if (generation.load(std::memory_order_acquire) != gen) {
+            break;
+        }
+        if (std::chrono::steady_clock::now() - start > std::chrono::milliseconds(timeoutMs)) {
+            throw std::runtime_error("Timed out in shared-memory MPI barrier (a rank is missing)");
         }
     }
 }

@@ -358,7 +358,8 @@ namespace {
 // the user buffers when every rank lives in this process
 int bodyLargeHostCollectives(int rank, int size)
 {
-    const int n = 50001;
+    // (above the 256 KiB break-even used when ranks outnumber cores)
+    const int n = 80001;
     // broadcast from a non-zero root
     const int root = size - 1;
     std::vector<int> b(n, rank == root ? 7 : -1);
@@ -390,7 +391,7 @@ int bodyLargeHostCollectives(int rank, int size)
     }
 
     // allgather, out of place and in place
-    const int per = 9001;
+    const int per = 20001;
     std::vector<int> mine(per, rank + 1), all((size_t)per * size, 0);
     MPI_Allgather(mine.data(), per, MPI_INT, all.data(), per, MPI_INT, MPI_COMM_WORLD);
     for (int r = 0; r < size; r++) {
