@@ -130,6 +130,24 @@ class LocalCluster:
             time.sleep(0.05)
         return self
 
+    def add_worker(self, slots: int | None = None, timeout: float = 30.0) -> str:
+        """Start one more worker while the cluster runs; returns its host name
+        once the planner lists it.  (At most 5 workers fit a port slot.)"""
+        if self.n_workers >= 5:
+            raise RuntimeError("port slot exhausted: at most 5 workers per LocalCluster")
+        i = self.n_workers
+        self.n_workers += 1
+        host = self.worker_hosts()[i]
+        proc = self._spawn("faabric_worker", self.base_offset + 100 * (i + 1), slots or self.slots, f"worker{i}")
+        deadline = time.time() + timeout
+        while host not in {h["ip"] for h in self.client.available_hosts()}:
+            if proc.poll() is not None:
+                raise RuntimeError(f"new worker exited with {proc.returncode}")
+            if time.time() > deadline:
+                raise RuntimeError("new worker did not register")
+            time.sleep(0.05)
+        return host
+
     def worker_hosts(self) -> list[str]:
         return [f"127.0.0.1:{self.base_offset + 100 * (i + 1)}" for i in range(self.n_workers)]
 

@@ -187,6 +187,24 @@ def test_killed_worker_expires_and_the_rest_keep_serving(tmp_path):
             c.client.invoke("demo", "hello", count=3, timeout=10)
 
 
+def test_worker_joining_later_takes_work(tmp_path):
+    """Elastic membership: a batch that does not fit is refused; once another
+    worker has registered the same batch spans both, MPI world included."""
+    with LocalCluster(n_workers=1, slots_per_worker=2, log_dir=tmp_path) as c:
+        first = c.worker_hosts()[0]
+        with pytest.raises(PlannerError):
+            c.client.invoke("demo", "hello", count=4, timeout=10)
+        second = c.add_worker()
+        assert {h["ip"] for h in c.client.available_hosts()} == {first, second}
+        st = c.client.invoke("demo", "hello", count=4, timeout=30)
+        outs = sorted(m["output_data"] for m in st["messageResults"])
+        assert outs == sorted([f"hello from {first}"] * 2 + [f"hello from {second}"] * 2)
+        st = c.client.invoke("mpi", "allreduce", mpi_world_size=4, timeout=60)
+        res = _results(st)
+        assert all(m.get("returnValue", 0) == 0 for m in res), res
+        assert {m["executedHost"] for m in res} == {first, second}
+
+
 def test_mpi_benchmarks_report(cluster):
     st = cluster.client.invoke("mpi", "bench-pingpong", mpi_world_size=2, input_data="64", timeout=120)
     out = json.loads(_results(st)[0]["output_data"])
