@@ -78,6 +78,15 @@ class Message final
       , payload(data, data + size)
     {}
 
+    // Adopts a handler's response string as it is (the in-process sync fast
+    // path hands it to the caller without another copy)
+    Message(uint8_t codeIn, int seqIn, std::string&& textIn)
+      : code(codeIn)
+      , sequenceNum(seqIn)
+      , text(std::move(textIn))
+      , isText(true)
+    {}
+
     // Non-owning view of a caller's buffer: used by the in-process sync fast
     // path, where the handler runs on the caller's stack.  Anything that
     // outlives the call must ensureOwned() first.
@@ -97,6 +106,11 @@ class Message final
             payload.assign(borrowed.begin(), borrowed.end());
             borrowed = {};
             isView = false;
+        }
+        if (isText) {
+            payload.assign(text.begin(), text.end());
+            std::string().swap(text);
+            isText = false;
         }
     }
 
@@ -118,7 +132,13 @@ class Message final
 
     std::span<const uint8_t> udata() const
     {
-        return isView ? borrowed : std::span<const uint8_t>(payload.data(), payload.size());
+        if (isView) {
+            return borrowed;
+        }
+        if (isText) {
+            return std::span<const uint8_t>((const uint8_t*)text.data(), text.size());
+        }
+        return std::span<const uint8_t>(payload.data(), payload.size());
     }
 
     std::span<const char> data() const
@@ -133,7 +153,7 @@ class Message final
         return payload;
     }
 
-    size_t size() const { return isView ? borrowed.size() : payload.size(); }
+    size_t size() const { return udata().size(); }
 
     uint8_t getMessageCode() const { return code; }
 
@@ -161,6 +181,8 @@ class Message final
     std::vector<uint8_t> payload;
     std::span<const uint8_t> borrowed;
     bool isView = false;
+    std::string text;
+    bool isText = false;
     MessageResponseCode failCode = MessageResponseCode::SUCCESS;
 };
 

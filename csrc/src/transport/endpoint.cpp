@@ -341,11 +341,7 @@ Message SyncSendMessageEndpoint::sendAwaitResponse(uint8_t header,
     if (MessageEndpointServer* local = findLocalServer(true)) {
         // Direct call on the caller's thread: no serialisation hop
         Message req = Message::view(header, NO_SEQUENCE_NUM, data, dataSize);
-        std::string resp = local->handleSync(req);
-        return Message(NO_HEADER,
-                       NO_SEQUENCE_NUM,
-                       (const uint8_t*)resp.data(),
-                       resp.size());
+        return Message(NO_HEADER, NO_SEQUENCE_NUM, local->handleSync(req));
     }
     std::lock_guard<std::mutex> lk(sockMx);
     int fd;
