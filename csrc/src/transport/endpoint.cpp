@@ -643,16 +643,34 @@ void MessageEndpointServerHandler::start(int timeoutMs)
     for (int t = 0; t < nThreads; t++) {
         im.workers.emplace_back([this] {
             Impl& im = *impl;
+            // After serving a request a worker polls briefly for the next one
+            // before it blocks: bursts (1024 results of a fan-out, streams of
+            // point-to-point messages) otherwise pay a futex wake per message
+            bool hot = false;
             while (true) {
                 std::shared_ptr<WorkItem> item;
-                try {
-                    item = im.work.dequeue(1000);
-                } catch (const faabric::util::QueueTimeoutException&) {
-                    if (!im.running.load()) {
-                        break;
-                    }
-                    continue;
+                if (hot) {
+                    auto pollStart = std::chrono::steady_clock::now();
+                    do {
+                        im.work.dequeueIfPresent(&item);
+                        if (item != nullptr) {
+                            break;
+                        }
+                        std::this_thread::yield();
+                    } while (std::chrono::steady_clock::now() - pollStart < std::chrono::microseconds(30));
                 }
+                if (item == nullptr) {
+                    hot = false;
+                    try {
+                        item = im.work.dequeue(1000);
+                    } catch (const faabric::util::QueueTimeoutException&) {
+                        if (!im.running.load()) {
+                            break;
+                        }
+                        continue;
+                    }
+                }
+                hot = true;
                 if (item->poison) {
                     break;
                 }
