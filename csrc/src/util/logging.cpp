@@ -47,6 +47,11 @@ void initLogging()
     SystemConfig& conf = getSystemConfig();
     currentLevel.store((int)parseLevel(conf.logLevel));
     std::lock_guard<std::mutex> lk(logMx);
+    // Re-initialising switches sinks: back to stderr, or on to another file
+    if (logSink != nullptr) {
+        fclose(logSink);
+        logSink = nullptr;
+    }
     if (conf.logFile != "off" && conf.logFile != "on" && !conf.logFile.empty()) {
         FILE* f = fopen(conf.logFile.c_str(), "a");
         if (f != nullptr) {

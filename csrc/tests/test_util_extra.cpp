@@ -267,3 +267,150 @@ TEST_CASE("function helpers: names, keys and async responses", "[util]")
     REQUIRE_EQ(parsed.id(), msg.id());
     REQUIRE_EQ(parsed.cmdline(), msg.cmdline());
 }
+
+// ---------------------------------------------------------------------------
+// Timers, logging, config dump, exec-graph helpers, crash handler
+// ---------------------------------------------------------------------------
+#include <faabric/util/ExecGraph.h>
+#include <faabric/util/crash.h>
+#include <faabric/util/files.h>
+#include <faabric/util/logging.h>
+#include <faabric/util/timing.h>
+
+#include <filesystem>
+
+TEST_CASE("timers accumulate per label and print a sorted table", "[util]")
+{
+    clearTimerTotals();
+    startGlobalTimer();
+    auto t = startTimer();
+    std::this_thread::sleep_for(std::chrono::milliseconds(3));
+    REQUIRE(getTimeDiffNanos(t) >= 3'000'000L);
+    REQUIRE(getTimeDiffMicros(t) >= 3000L);
+    REQUIRE(getTimeDiffMillis(t) >= 3.0);
+    logEndTimer("slow", t);
+    auto quick = startTimer();
+    logEndTimer("quick", quick);
+    logEndTimer("quick", quick);
+    std::string totals = getTimerTotalsString();
+    // "label:totalMicros:count" lines, largest total first
+    REQUIRE(totals.find("slow:") < totals.find("quick:"));
+    REQUIRE(totals.find("quick:") != std::string::npos);
+    REQUIRE(totals.substr(totals.find("quick:")).find(":2") != std::string::npos);
+    printTimerTotals();
+    clearTimerTotals();
+    REQUIRE(getTimerTotalsString().find("slow") == std::string::npos);
+
+    timespec ts{ 3, 500 };
+    REQUIRE_EQ(timespecToNanos(&ts), (uint64_t)3'000'000'500ULL);
+    timespec back{};
+    nanosToTimespec(3'000'000'500ULL, &back);
+    REQUIRE(back.tv_sec == 3 && back.tv_nsec == 500);
+}
+
+TEST_CASE("logging levels filter, names parse, LOG_FILE redirects", "[util]")
+{
+    LogLevel before = getLogLevel();
+    setLogLevel("debug");
+    REQUIRE(getLogLevel() == LogLevel::debug);
+    setLogLevel("warn");
+    REQUIRE(getLogLevel() == LogLevel::warn);
+    setLogLevel("off");
+    REQUIRE(getLogLevel() == LogLevel::off);
+    setLogLevel(LogLevel::err);
+    REQUIRE(getLogLevel() == LogLevel::err);
+    // unknown names mean the default
+    setLogLevel("shouting");
+    REQUIRE(getLogLevel() == LogLevel::info);
+
+    // LOG_FILE: lines land in the file with the reference's pattern
+    const std::string path = "/tmp/fb_log_" + std::to_string(getpid()) + ".log";
+    ::unlink(path.c_str());
+    auto& conf = getSystemConfig();
+    std::string oldFile = conf.logFile, oldLevel = conf.logLevel;
+    conf.logFile = path;
+    conf.logLevel = "info";
+    initLogging();
+    SPDLOG_INFO("hello {} and {}", 42, "world");
+    SPDLOG_DEBUG("filtered {}", 1);
+    conf.logFile = oldFile;
+    conf.logLevel = oldLevel;
+    initLogging();
+    std::string contents = readFileToString(path);
+    REQUIRE(contents.find("hello 42 and world") != std::string::npos);
+    REQUIRE(contents.find("[I]") != std::string::npos);
+    REQUIRE(contents.find("filtered") == std::string::npos);
+    ::unlink(path.c_str());
+    setLogLevel(before);
+}
+
+TEST_CASE("config dump lists every knob", "[util]")
+{
+    auto& conf = getSystemConfig();
+    LogLevel before = getLogLevel();
+    const std::string path = "/tmp/fb_conf_" + std::to_string(getpid()) + ".log";
+    std::string oldFile = conf.logFile;
+    conf.logFile = path;
+    initLogging();
+    setLogLevel(LogLevel::info);
+    conf.print();
+    conf.logFile = oldFile;
+    initLogging();
+    setLogLevel(before);
+    std::string dump = readFileToString(path);
+    ::unlink(path.c_str());
+    for (const char* knob : { "LOG_LEVEL", "BATCH_SCHEDULER_MODE", "GLOBAL_MESSAGE_TIMEOUT", "DIRTY_TRACKING_MODE", "PLANNER_HOST", "FAABRIC_GPUS", "FAABRIC_CHECKPOINT_DIR" }) {
+        REQUIRE(dump.find(knob) != std::string::npos);
+    }
+}
+
+TEST_CASE("exec graph helpers: counting, hosts, MPI ranks, JSON, details", "[util]")
+{
+    auto mk = [](int id, const std::string& host, int rank = -1) {
+        faabric::Message m = messageFactory("demo", "node");
+        m.set_id(id);
+        m.set_executedhost(host);
+        if (rank >= 0) {
+            m.set_ismpi(true);
+            m.set_mpirank(rank);
+            m.set_mpiworldsize(3);
+        }
+        return m;
+    };
+    ExecGraphNode leafA{ mk(2, "hostB", 1), {} };
+    ExecGraphNode leafB{ mk(3, "hostA", 2), {} };
+    ExecGraphNode root{ mk(1, "hostA", 0), { leafA, leafB } };
+    ExecGraph graph{ root };
+    REQUIRE_EQ(countExecGraphNodes(graph), 3);
+    REQUIRE(getExecGraphHosts(graph) == (std::set<std::string>{ "hostA", "hostB" }));
+    REQUIRE(getMpiRankHostsFromExecGraph(graph) == (std::vector<std::string>{ "hostA", "hostB", "hostA" }));
+    std::string json = execGraphToJson(graph);
+    REQUIRE(json.find("\"root\"") != std::string::npos);
+    REQUIRE(json.find("\"chained\"") != std::string::npos);
+    REQUIRE(json.find("hostB") != std::string::npos);
+    REQUIRE(execNodeToJson(leafA).find("\"msg\"") != std::string::npos);
+
+    // chained-call bookkeeping and detail counters only when recording
+    faabric::Message parent = messageFactory("demo", "parent");
+    faabric::Message child = messageFactory("demo", "child");
+    logChainedFunction(parent, child);
+    REQUIRE(getChainedFunctions(parent) == (std::set<unsigned int>{ (unsigned int)child.id() }));
+    addDetail(parent, "note", "ignored");
+    incrementCounter(parent, "hits");
+    REQUIRE_EQ(parent.execgraphdetails_size(), 0);
+    REQUIRE_EQ(parent.intexecgraphdetails_size(), 0);
+    parent.set_recordexecgraph(true);
+    addDetail(parent, "note", "kept");
+    incrementCounter(parent, "hits");
+    incrementCounter(parent, "hits", 4);
+    REQUIRE_EQ(parent.execgraphdetails().at("note"), std::string("kept"));
+    REQUIRE_EQ(parent.intexecgraphdetails().at("hits"), 5);
+}
+
+TEST_CASE("crash handler prints a stack trace for the test signal", "[util]")
+{
+    // The real signals re-raise; the test signal only reports
+    setUpCrashHandler(12341234);
+    printStackTrace(nullptr);
+    REQUIRE(true);
+}

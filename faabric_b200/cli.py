@@ -77,7 +77,13 @@ def _coverage() -> int:
         all_tot += tot
         print(f"{d:<28}{tot:>8}{cov:>9}{100.0 * cov / max(tot, 1):>7.1f}")
     print(f"{'TOTAL':<28}{all_tot:>8}{all_cov:>9}{100.0 * all_cov / max(all_tot, 1):>7.1f}")
-    (ROOT / "build" / "coverage.json").write_text(json.dumps({"dirs": by_dir, "covered": all_cov, "lines": all_tot}))
+    files = {
+        os.path.relpath(name, ROOT / "csrc"): [sum(1 for c in lines.values() if c > 0), len(lines)]
+        for name, lines in per_file.items()
+    }
+    (ROOT / "build" / "coverage.json").write_text(
+        json.dumps({"dirs": by_dir, "files": files, "covered": all_cov, "lines": all_tot}, indent=1)
+    )
     print("(rebuild without instrumentation: python -m faabric_b200.build --force)")
     return 0
 
