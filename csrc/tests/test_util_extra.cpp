@@ -414,3 +414,131 @@ TEST_CASE("crash handler prints a stack trace for the test signal", "[util]")
     printStackTrace(nullptr);
     REQUIRE(true);
 }
+
+// ---------------------------------------------------------------------------
+// Wire codec and JSON layer under hostile input
+// ---------------------------------------------------------------------------
+#include <faabric/proto/wire.h>
+#include <faabric/util/json.h>
+
+TEST_CASE("wire reader: skipping, truncation and overlong varints", "[proto]")
+{
+    using faabric::proto::Reader;
+    using faabric::proto::Writer;
+    Writer w;
+    w.varint(1, 300, false);
+    w.varint(2, 0, false); // default: omitted
+    w.varint(3, 0, true);  // forced
+    w.str(4, "payload", false);
+    w.str(5, "", false);
+    std::string buf = w.take();
+    Reader r(buf);
+    uint32_t field = 0;
+    int wt = -1;
+    std::vector<uint32_t> seen;
+    while (r.next(field, wt)) {
+        seen.push_back(field);
+        REQUIRE(r.skip(wt));
+    }
+    REQUIRE(r.ok());
+    REQUIRE(seen == (std::vector<uint32_t>{ 1, 3, 4 }));
+
+    // fixed-width fields of unknown messages are skipped too
+    std::string fixed = { 0x0d, 1, 2, 3, 4, 0x11, 1, 2, 3, 4, 5, 6, 7, 8, 0x18, 0x05 };
+    Reader rf(fixed);
+    int n = 0;
+    while (rf.next(field, wt)) {
+        REQUIRE(rf.skip(wt));
+        n++;
+    }
+    REQUIRE(rf.ok());
+    REQUIRE_EQ(n, 3);
+
+    // every prefix of a valid message either parses or fails cleanly
+    faabric::Message m = messageFactory("demo", "echo");
+    m.set_inputdata(std::string(300, 'x'));
+    m.set_cmdline("a b c");
+    (*m.mutable_intexecgraphdetails())["k"] = 7;
+    m.add_chainedmsgids(9);
+    std::string wire = m.SerializeAsString();
+    int parsedOk = 0;
+    for (size_t cut = 0; cut <= wire.size(); cut++) {
+        faabric::Message p;
+        if (p.ParseFromArray(wire.data(), (int)cut)) {
+            parsedOk++;
+        }
+    }
+    REQUIRE(parsedOk >= 2); // the empty prefix and the whole message at least
+    faabric::Message whole;
+    REQUIRE(whole.ParseFromString(wire));
+    REQUIRE_EQ(whole.intexecgraphdetails().at("k"), 7);
+    REQUIRE_EQ(whole.chainedmsgids(0), 9u);
+
+    // an 11-byte varint and a group wire type are rejected
+    std::string overlong(11, (char)0x80);
+    overlong.insert(overlong.begin(), 0x08);
+    faabric::Message p;
+    REQUIRE(!p.ParseFromString(overlong));
+    REQUIRE(!p.ParseFromString(std::string({ 0x0b })));
+    // random bytes never crash the parser
+    uint32_t seed = 12345;
+    for (int i = 0; i < 2000; i++) {
+        std::string junk;
+        int len = (int)(seed % 64);
+        for (int j = 0; j < len; j++) {
+            seed = seed * 1664525u + 1013904223u;
+            junk.push_back((char)(seed >> 24));
+        }
+        faabric::BatchExecuteRequest ber;
+        (void)ber.ParseFromString(junk);
+        seed = seed * 1664525u + 1013904223u;
+    }
+}
+
+TEST_CASE("json layer: values, escapes, errors and schema names", "[proto]")
+{
+    using faabric::proto::JsonValue;
+    JsonValue v = JsonValue::parse(R"({"a": [1, -2.5, "3", true, null], "b": {"nested": "x\n\"y\" é"}, "big": "9007199254740993"})");
+    REQUIRE(v.isObject());
+    const JsonValue* a = v.find("a");
+    REQUIRE(a != nullptr && a->isArray() && a->elements().size() == 5);
+    REQUIRE_EQ(a->elements()[0].asInt(), (int64_t)1);
+    REQUIRE_EQ(a->elements()[1].asDouble(), -2.5);
+    REQUIRE_EQ(a->elements()[2].asInt(), (int64_t)3); // numbers as strings
+    REQUIRE(a->elements()[3].asBool());
+    REQUIRE(a->elements()[4].isNull());
+    REQUIRE(v.find("b")->find("nested")->asString().find("\"y\"") != std::string::npos);
+    REQUIRE_EQ(v.find("big")->asInt(), (int64_t)9007199254740993LL);
+    REQUIRE(v.find("missing") == nullptr);
+    for (const char* bad : { "{", "{\"a\": }", "[1, 2", "{\"a\" 1}", "tru", "\"unterminated", "{\"a\": 1} trailing", "" }) {
+        REQUIRE_THROWS(JsonValue::parse(bad));
+    }
+
+    // base64 for bytes fields, both directions, all paddings
+    for (const std::string& raw : { std::string(""), std::string("f"), std::string("fo"), std::string("foo"), std::string("\x00\xff\x10", 3) }) {
+        REQUIRE_EQ(faabric::proto::base64Decode(faabric::proto::base64Encode(raw)), raw);
+    }
+    REQUIRE_EQ(faabric::proto::base64Encode("foob"), std::string("Zm9vYg=="));
+
+    // messages use the schema's json names and survive a round trip
+    faabric::Message m = messageFactory("demo", "echo");
+    m.set_inputdata(std::string("\x01\x02\x03", 3));
+    m.set_outputdata("line\nbreak \"quoted\"");
+    m.set_mpiworldsize(4);
+    m.set_ismpi(true);
+    std::string json = messageToJson(m);
+    REQUIRE(json.find("\"input_data\"") != std::string::npos);
+    REQUIRE(json.find("\"mpi_world_size\"") != std::string::npos);
+    faabric::Message back;
+    jsonToMessage(json, &back);
+    REQUIRE_EQ(back.inputdata(), m.inputdata());
+    REQUIRE_EQ(back.outputdata(), m.outputdata());
+    REQUIRE_EQ(back.mpiworldsize(), 4);
+    REQUIRE(back.ismpi());
+    // unknown keys are ignored, wrong shapes are errors
+    faabric::Message lenient;
+    jsonToMessage(R"({"id": 5, "no_such_field": [1, 2, 3]})", &lenient);
+    REQUIRE_EQ(lenient.id(), 5);
+    REQUIRE_THROWS(jsonToMessage("[1, 2]", &lenient));
+    REQUIRE_THROWS(jsonToMessage("not json", &lenient));
+}
