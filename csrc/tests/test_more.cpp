@@ -152,6 +152,54 @@ TEST_CASE("raw tcp sockets", "[transport]")
     REQUIRE_THROWS(nobody.dial(2, 10));
 }
 
+TEST_CASE("raw tcp sockets: timeouts, closed peers, moved handles", "[transport]")
+{
+    using namespace faabric::transport::tcp;
+    int port = 9735;
+    RecvSocket server(port);
+    server.listen();
+    REQUIRE_EQ(server.getPort(), port);
+    // nobody connects: accept gives up after the timeout
+    auto t0 = std::chrono::steady_clock::now();
+    REQUIRE_THROWS(server.accept(50));
+    auto waited = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+    REQUIRE(waited >= 40 && waited < 2000);
+
+    // the port is taken: a second listener is refused
+    RecvSocket clash(port);
+    REQUIRE_THROWS(clash.listen());
+
+    // a peer that dies mid-message surfaces as an error, not a hang
+    std::thread client([&] {
+        SendSocket s("127.0.0.1", port);
+        s.dial();
+        uint8_t half[10] = { 1, 2, 3, 4, 5, 6, 7, 8, 9, 10 };
+        s.sendOne(half, sizeof(half));
+        // destructor closes the connection with 10 of 64 bytes sent
+    });
+    int conn = server.accept(5000);
+    client.join();
+    std::vector<uint8_t> buf(64);
+    REQUIRE_THROWS(server.recvOne(conn, buf.data(), buf.size()));
+
+    // sockets are movable handles
+    Socket a;
+    int fd = a.get();
+    REQUIRE(fd >= 0);
+    Socket b(std::move(a));
+    REQUIRE_EQ(b.get(), fd);
+    REQUIRE(a.get() < 0);
+    Socket c;
+    c = std::move(b);
+    REQUIRE_EQ(c.get(), fd);
+    c.close();
+    REQUIRE(c.get() < 0);
+    // sending on an unconnected socket fails cleanly
+    SendSocket idle("127.0.0.1", port + 1);
+    uint8_t byte = 0;
+    REQUIRE_THROWS(idle.sendOne(&byte, 1));
+}
+
 TEST_CASE("transport message header and wire format", "[transport][proto]")
 {
     uint8_t hdr[HEADER_MSG_SIZE];
