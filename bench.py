@@ -14,6 +14,8 @@ Other modes (each prints one JSON line and appends to --out):
   alltoall  all-to-all bus GB/s 1 KB..64 MB per rank, ours vs NCCL
   snapshot  1 GB region diff+push at 1..50 % dirty (MB/s), vs CPU oracle rate
   planner   1024-function fan-out / fan-in through the native planner (us)
+  pingpong  MPI ping-pong RTT, 2 ranks in one worker and in two (CPU)
+  hostcoll  host-buffer MPI collectives: reference algorithms vs shared memory (CPU)
 
 Launch:  python bench.py --gpus 1          (single process)
          python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
@@ -40,7 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-host", "mpi-device", "mpi-symmetric", "mpi-symmetric-nb"])
     ap.add_argument("--mode", default="allreduce",
-                    choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "pingpong"])
+                    choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "pingpong", "hostcoll"])
     ap.add_argument("--algo", default="tuned",
                     help="tuned = measure the algorithm policies in place and keep the fastest (allreduce mode)")
     ap.add_argument("--no-graph", action="store_true")
@@ -126,6 +128,28 @@ def mode_pingpong(args):
         "n_gpus": 0,
         "world_size": 2,
         "details": {"same_worker_queue": local, "two_workers_tcp": tcp},
+    }), flush=True)
+    return 0
+
+
+def mode_hostcoll(args):
+    """Host-buffer MPI collectives inside one worker: reference algorithms vs
+    the shared-memory path (CPU only; table in profiles/README.md)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from faabric_b200.runtime import host_collectives_bench
+
+    cells = host_collectives_bench(repeats=max(1, min(args.steps, 5)))
+    key = "shared-8-8388608"
+    ref = "reference-8-8388608"
+    print(json.dumps({
+        "metric": "mpi_host_allreduce_8MiB_8ranks_us",
+        "value": cells[key]["allreduce_us"],
+        "unit": "us",
+        "higher_is_better": False,
+        "n_gpus": 0,
+        "reference_algorithm_us": cells[ref]["allreduce_us"],
+        "details": cells,
     }), flush=True)
     return 0
 
@@ -624,6 +648,8 @@ def main():
         return refcpu_arm(args)
     if args.mode == "pingpong":
         return mode_pingpong(args)
+    if args.mode == "hostcoll":
+        return mode_hostcoll(args)
     if args.mode == "planner":
         # CPU only: no process group / GPU needed
         if int(os.environ.get("RANK", "0")) == 0:

@@ -9,7 +9,13 @@
 
 from .client import PlannerHttpClient, HttpMessageType, PlannerError
 from .cluster import LocalCluster
-from .benchmarks import planner_fanout_bench, cpu_pingpong_bench, cpu_allreduce_bench, mpi_allreduce_bench
+from .benchmarks import (
+    planner_fanout_bench,
+    cpu_pingpong_bench,
+    cpu_allreduce_bench,
+    mpi_allreduce_bench,
+    host_collectives_bench,
+)
 
 __all__ = [
     "PlannerHttpClient",
@@ -18,6 +24,7 @@ __all__ = [
     "LocalCluster",
     "planner_fanout_bench",
     "cpu_pingpong_bench",
+    "host_collectives_bench",
     "cpu_allreduce_bench",
     "mpi_allreduce_bench",
 ]

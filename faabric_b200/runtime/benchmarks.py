@@ -78,3 +78,25 @@ def mpi_allreduce_bench(
 def cpu_allreduce_bench(counts: list[int], world_size: int, steps: int = 3, warmup: int = 1) -> dict:
     """The `refcpu` baseline: the reference's algorithm on host memory."""
     return mpi_allreduce_bench(counts, world_size, steps, warmup, memory="host", host_algo="reference")
+
+
+def host_collectives_bench(ranks=(4, 8), sizes=(65536, 1 << 20, 8 << 20), repeats: int = 3, calls: int = 10) -> dict:
+    """Host-buffer collectives with every rank in one worker: the reference's
+    message algorithms (FAABRIC_MPI_HOST_ALLREDUCE=reference) against the
+    shared-memory path.  Microseconds per call, minimum over `repeats` runs."""
+    best: dict = {}
+    for _ in range(repeats):
+        for mode in ("shared", "reference"):
+            with LocalCluster(
+                n_workers=1, slots_per_worker=max(ranks), log_level="warn", extra_env={"FAABRIC_MPI_HOST_ALLREDUCE": mode}
+            ) as c:
+                for n in ranks:
+                    for b in sizes:
+                        st = c.client.invoke("mpi", "bench-collectives", mpi_world_size=n, input_data=f"{b},{calls}", timeout=600)
+                        out = _first_output(st)
+                        cell = best.setdefault(f"{mode}-{n}-{b}", out)
+                        for k, v in out.items():
+                            if k.endswith("_us"):
+                                cell[k] = min(cell[k], v)
+    return best
+
