@@ -117,6 +117,43 @@ static void registerFunctions()
         return 0;
     };
 
+    // Ordered point-to-point streams between every pair of group members
+    // (reference dist test "many in-order messages", tests/dist/transport)
+    functions()["ptp/stream"] = [](faabric::Message& msg) {
+        const int n = msg.inputdata().empty() ? 500 : std::stoi(msg.inputdata());
+        auto& broker = faabric::transport::getPointToPointBroker();
+        auto group = faabric::transport::PointToPointGroup::getOrAwaitGroup(msg.groupid());
+        const int idx = msg.groupidx();
+        const int size = msg.groupsize() > 0 ? msg.groupsize() : (int)broker.getIdxsRegisteredForGroup(msg.groupid()).size();
+        // everybody streams n numbered messages to everybody else...
+        for (int i = 0; i < n; i++) {
+            for (int peer = 0; peer < size; peer++) {
+                if (peer != idx) {
+                    int payload[2] = { idx, i };
+                    broker.sendMessage(msg.groupid(), idx, peer, (const uint8_t*)payload, sizeof(payload), true);
+                }
+            }
+        }
+        // ...and must see each stream in order
+        int bad = 0;
+        for (int peer = 0; peer < size; peer++) {
+            if (peer == idx) {
+                continue;
+            }
+            for (int i = 0; i < n; i++) {
+                auto bytes = broker.recvMessage(msg.groupid(), peer, idx, true);
+                const int* payload = (const int*)bytes.data();
+                if (bytes.size() != 2 * sizeof(int) || payload[0] != peer || payload[1] != i) {
+                    bad++;
+                }
+            }
+        }
+        group->barrier(idx);
+        msg.set_outputdata(std::to_string(bad) + " out of order on " + faabric::scheduler::getScheduler().getThisHost());
+        broker.resetThreadLocalCache();
+        return bad == 0 ? 0 : 1;
+    };
+
     // Fork-join over THREADS: the main function spawns N threads that may land
     // on other workers; they start from its snapshot, write their own slot and
     // add into a Sum-merged word; the diffs are merged back into main memory.
