@@ -216,6 +216,23 @@ def test_ordered_ptp_streams_between_workers(cluster):
     assert {m["output_data"].split()[-1] for m in res} == set(cluster.worker_hosts())
 
 
+def test_two_mpi_worlds_run_concurrently(tmp_path):
+    """Two applications share the workers at the same time (reference dist
+    test "multiple MPI worlds"): each gets its own world, group and ports."""
+    with LocalCluster(n_workers=2, slots_per_worker=4, log_dir=tmp_path) as c:
+        first = c.client.make_batch("mpi", "alltoall-many", mpi_world_size=4)
+        second = c.client.make_batch("mpi", "reduce-many", mpi_world_size=4)
+        c.client.execute_batch(first)
+        c.client.execute_batch(second)
+        for batch in (first, second):
+            st = c.client.wait_for_batch(batch["appId"], timeout=90)
+            res = _results(st)
+            assert len(res) == 4, res
+            assert all(m.get("returnValue", 0) == 0 for m in res), res
+            assert len({m["mpiWorldId"] for m in res}) == 1
+        assert all(h.get("usedSlots", 0) == 0 for h in c.client.available_hosts())
+
+
 def test_mpi_benchmarks_report(cluster):
     st = cluster.client.invoke("mpi", "bench-pingpong", mpi_world_size=2, input_data="64", timeout=120)
     out = json.loads(_results(st)[0]["output_data"])
