@@ -846,6 +846,7 @@ class WorkerExecutorFactory : public ExecutorFactory
 int main()
 {
     faabric::util::initLogging();
+    faabric::util::exitWithParentIfAsked();
     registerFunctions();
     auto& conf = faabric::util::getSystemConfig();
     SPDLOG_INFO("Starting worker {} (port offset {}), planner at {}", conf.endpointHost, conf.portOffset, conf.plannerHost);

@@ -38,6 +38,7 @@ int main()
 {
     faabric::util::initLogging();
     faabric::util::setUpCrashHandler();
+    faabric::util::exitWithParentIfAsked();
 
     Running<faabric::planner::PlannerServer> rpc("RPC server");
     Running<faabric::snapshot::SnapshotServer> snapshots("snapshot server");

@@ -952,6 +952,11 @@ std::string setEnvVar(const std::string& varName, const std::string& value);
 
 void unsetEnvVar(const std::string& varName);
 
+// FAABRIC_EXIT_WITH_PARENT=1: ask the kernel to SIGTERM this process when the
+// process that started it dies (test clusters must not outlive a killed
+// test runner).  No-op otherwise.
+void exitWithParentIfAsked();
+
 // Hardware threads usable by this process (OVERRIDE_CPU_COUNT wins)
 unsigned int getUsableCores();
 

@@ -1,5 +1,7 @@
 // Small utilities: gids, random, environment, network, files, bytes, strings,
 // testing flags.
+#include <csignal>
+#include <sys/prctl.h>
 #include <faabric/util/bytes.h>
 #include <faabric/util/config.h>
 #include <faabric/util/environment.h>
@@ -84,6 +86,18 @@ int randomInteger(int iStart, int iEnd)
 }
 
 // ----------------------------------------------------------- environment ---
+void exitWithParentIfAsked()
+{
+    if (getEnvVar("FAABRIC_EXIT_WITH_PARENT", "0") != "1") {
+        return;
+    }
+    ::prctl(PR_SET_PDEATHSIG, SIGTERM);
+    // the parent may already be gone: we have been re-parented to init
+    if (::getppid() == 1) {
+        ::raise(SIGTERM);
+    }
+}
+
 std::string getEnvVar(const std::string& key, const std::string& deflt)
 {
     const char* v = getenv(key.c_str());

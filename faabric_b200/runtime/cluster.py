@@ -83,6 +83,8 @@ class LocalCluster:
                 "PLANNER_HOST": f"127.0.0.1:{self.base_offset}",
                 "PLANNER_PORT": str(self.http_port),
                 "FAABRIC_PORT_OFFSET": str(offset),
+                # a killed test runner must not leave servers behind
+                "FAABRIC_EXIT_WITH_PARENT": "1",
                 "FAABRIC_DEVICE_BACKEND": os.environ.get("FAABRIC_DEVICE_BACKEND", "cuda"),
             }
         )

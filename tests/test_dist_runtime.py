@@ -233,6 +233,36 @@ def test_two_mpi_worlds_run_concurrently(tmp_path):
         assert all(h.get("usedSlots", 0) == 0 for h in c.client.available_hosts())
 
 
+def test_cluster_processes_do_not_outlive_a_killed_parent(tmp_path):
+    """A test runner that dies without clean-up (SIGKILL, os._exit) must not
+    leave planners and workers behind holding their ports."""
+    import subprocess
+    import sys
+    import time
+
+    import psutil
+
+    script = tmp_path / "abrupt.py"
+    script.write_text(
+        "import os, sys, pathlib\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from faabric_b200.runtime import LocalCluster\n"
+        f"c = LocalCluster(n_workers=2, slots_per_worker=2, log_dir=pathlib.Path({str(tmp_path)!r}))\n"
+        "c.start()\n"
+        "print(' '.join(str(p.pid) for p in c.procs), flush=True)\n"
+        "os._exit(1)\n"
+    )
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    pids = [int(x) for x in out.stdout.split()[-3:]]
+    assert len(pids) == 3, (out.stdout, out.stderr)
+    deadline = time.time() + 10
+    alive = pids
+    while alive and time.time() < deadline:
+        alive = [p for p in alive if psutil.pid_exists(p) and psutil.Process(p).status() != psutil.STATUS_ZOMBIE]
+        time.sleep(0.1)
+    assert not alive, alive
+
+
 def test_mpi_benchmarks_report(cluster):
     st = cluster.client.invoke("mpi", "bench-pingpong", mpi_world_size=2, input_data="64", timeout=120)
     out = json.loads(_results(st)[0]["output_data"])
