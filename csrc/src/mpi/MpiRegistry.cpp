@@ -1,5 +1,7 @@
 #include <faabric/mpi/MpiContext.h>
 #include <faabric/mpi/MpiWorldRegistry.h>
+
+#include "subcomm.h"
 #include <faabric/util/config.h>
 #include <faabric/util/gids.h>
 #include <faabric/util/logging.h>
@@ -72,11 +74,14 @@ bool MpiWorldRegistry::worldExists(int worldId)
 
 void MpiWorldRegistry::clearWorld(int worldId)
 {
+    // sub-communicators live and die with their world
+    clearSubCommunicators(worldId);
     worldMap.erase(worldId);
 }
 
 void MpiWorldRegistry::clear()
 {
+    clearSubCommunicators(-1);
     worldMap.clear();
 }
 

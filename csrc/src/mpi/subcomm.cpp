@@ -303,9 +303,10 @@ std::shared_ptr<SubCommunicator> getSubCommunicator(int commId)
 
 void clearSubCommunicators(int worldId)
 {
+    // worldId < 0: every world
     std::unique_lock<std::shared_mutex> lk(commsMx);
     for (auto it = comms.begin(); it != comms.end();) {
-        it = it->second->worldId() == worldId ? comms.erase(it) : std::next(it);
+        it = (worldId < 0 || it->second->worldId() == worldId) ? comms.erase(it) : std::next(it);
     }
 }
 

@@ -71,6 +71,7 @@ std::shared_ptr<SubCommunicator> registerSubCommunicator(int commId, int worldId
 // nullptr for MPI_COMM_WORLD / unknown ids
 std::shared_ptr<SubCommunicator> getSubCommunicator(int commId);
 
+// worldId < 0 clears the communicators of every world
 void clearSubCommunicators(int worldId);
 
 // Groups are local objects: plain lists of world ranks

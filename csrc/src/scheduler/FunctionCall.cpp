@@ -1,4 +1,5 @@
 #include <faabric/planner/PlannerClient.h>
+#include <faabric/mpi/MpiWorldRegistry.h>
 #include <faabric/scheduler/FunctionCallClient.h>
 #include <faabric/scheduler/FunctionCallServer.h>
 #include <faabric/scheduler/Scheduler.h>
@@ -166,6 +167,9 @@ std::string FunctionCallServer::recvFlush(std::span<const uint8_t> buffer)
     // Clear out any cached state, executors and the factory's host state
     faabric::state::getGlobalState().forceClearAll(false);
     scheduler.flushLocally();
+    // Finished MPI worlds stay registered for late joiners (as in the
+    // reference); a flush is where a long-running worker lets go of them
+    faabric::mpi::getMpiWorldRegistry().clear();
     return faabric::EmptyResponse().SerializeAsString();
 }
 
