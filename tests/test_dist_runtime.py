@@ -247,7 +247,8 @@ def test_cluster_processes_do_not_outlive_a_killed_parent(tmp_path):
         "import os, sys, pathlib\n"
         f"sys.path.insert(0, {str(ROOT)!r})\n"
         "from faabric_b200.runtime import LocalCluster\n"
-        f"c = LocalCluster(n_workers=2, slots_per_worker=2, log_dir=pathlib.Path({str(tmp_path)!r}))\n"
+        # (its own port block: the child cannot see which slots this process uses)
+        f"c = LocalCluster(n_workers=2, slots_per_worker=2, base_offset=23000, log_dir=pathlib.Path({str(tmp_path)!r}))\n"
         "c.start()\n"
         "print(' '.join(str(p.pid) for p in c.procs), flush=True)\n"
         "os._exit(1)\n"
