@@ -542,3 +542,75 @@ TEST_CASE("json layer: values, escapes, errors and schema names", "[proto]")
     REQUIRE_THROWS(jsonToMessage("[1, 2]", &lenient));
     REQUIRE_THROWS(jsonToMessage("not json", &lenient));
 }
+
+// ---------------------------------------------------------------------------
+// CPU pinning / GPU placement helpers
+// ---------------------------------------------------------------------------
+#include <faabric/util/hwloc.h>
+
+#include <sched.h>
+
+TEST_CASE("cpu pinning: claims are exclusive, released and exhaustible", "[util]")
+{
+    auto& conf = getSystemConfig();
+    const int before = conf.overrideCpuCount;
+    const int free0 = getNumFreeCpus();
+    REQUIRE(free0 >= 1);
+    std::set<int> cpus;
+    {
+        std::vector<std::unique_ptr<FaabricCpuSet>> pins;
+        // each thread gets a CPU of its own and really runs there
+        std::mutex mx;
+        std::vector<std::thread> ts;
+        const int n = std::min(free0, 3);
+        std::atomic<int> wrongCpu{ 0 };
+        for (int i = 0; i < n; i++) {
+            ts.emplace_back([&] {
+                auto pin = pinThreadNearGpu(pthread_self(), 0); // no GPU here: any free CPU
+                if (sched_getcpu() != pin->getCpuIdx()) {
+                    wrongCpu++;
+                }
+                REQUIRE(CPU_ISSET(pin->getCpuIdx(), pin->get()));
+                REQUIRE_EQ(CPU_COUNT(pin->get()), 1);
+                std::lock_guard<std::mutex> lk(mx);
+                cpus.insert(pin->getCpuIdx());
+                pins.push_back(std::move(pin));
+            });
+        }
+        for (auto& t : ts) {
+            t.join();
+        }
+        REQUIRE_EQ(wrongCpu.load(), 0);
+        REQUIRE_EQ((int)cpus.size(), n);
+        REQUIRE_EQ(getNumFreeCpus(), free0 - n);
+        // claim the rest, then one more
+        std::thread rest([&] {
+            while (getNumFreeCpus() > 0) {
+                pins.push_back(pinThreadToFreeCpu(pthread_self()));
+            }
+            bool threw = false;
+            try {
+                pinThreadToFreeCpu(pthread_self());
+            } catch (const std::runtime_error&) {
+                threw = true;
+            }
+            REQUIRE(threw);
+        });
+        rest.join();
+        REQUIRE_EQ(getNumFreeCpus(), 0);
+    }
+    // RAII: everything is free again
+    REQUIRE_EQ(getNumFreeCpus(), free0);
+    conf.overrideCpuCount = before;
+
+    // placement: no GPU -> -1, and binding is a no-op rather than an error
+    if (getUsableGpus() == 0) {
+        REQUIRE_EQ(gpuForRank(0), -1);
+        REQUIRE_EQ(gpuForRank(5), -1);
+    } else {
+        REQUIRE_EQ(gpuForRank(0), 0);
+        REQUIRE_EQ(gpuForRank(getUsableGpus()), 0);
+    }
+    bindThreadToGpu(-1);
+    bindThreadToGpu(0);
+}
