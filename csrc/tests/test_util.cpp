@@ -340,6 +340,29 @@ TEST_CASE("dirty tracking: uffd", "[util][dirty]")
     checkTracker("uffd");
 }
 
+// Every userfaultfd flavour the reference names (write-protect vs missing-page
+// faults, SIGBUS vs event thread) must report the same pages
+TEST_CASE("dirty tracking: uffd-wp, uffd-thread, uffd-thread-wp", "[util][dirty]")
+{
+    if (!UffdDirtyTracker::isSupported()) {
+        SKIP_TEST("userfaultfd write-protect not available");
+    }
+    for (const char* mode : { "uffd-wp", "uffd-thread", "uffd-thread-wp" }) {
+        checkTracker(mode);
+    }
+}
+
+TEST_CASE("dirty tracking: unknown mode is rejected", "[util][dirty]")
+{
+    auto& conf = getSystemConfig();
+    conf.dirtyTrackingMode = "telepathy";
+    // (the tracker is rebuilt eagerly)
+    REQUIRE_THROWS(resetDirtyTracker());
+    conf.reset();
+    resetDirtyTracker();
+    REQUIRE(getDirtyTracker() != nullptr);
+}
+
 TEST_CASE("snapshot: typed merge diffs and application", "[util][snapshot]")
 {
     getSystemConfig().diffingMode = "bytewise";
