@@ -567,11 +567,12 @@ TEST_CASE("cpu pinning: claims are exclusive, released and exhaustible", "[util]
         for (int i = 0; i < n; i++) {
             ts.emplace_back([&] {
                 auto pin = pinThreadNearGpu(pthread_self(), 0); // no GPU here: any free CPU
-                if (sched_getcpu() != pin->getCpuIdx()) {
+                // (assertions stay on the main thread: the harness counts them
+                // without synchronisation)
+                if (sched_getcpu() != pin->getCpuIdx() || !CPU_ISSET(pin->getCpuIdx(), pin->get()) ||
+                    CPU_COUNT(pin->get()) != 1) {
                     wrongCpu++;
                 }
-                REQUIRE(CPU_ISSET(pin->getCpuIdx(), pin->get()));
-                REQUIRE_EQ(CPU_COUNT(pin->get()), 1);
                 std::lock_guard<std::mutex> lk(mx);
                 cpus.insert(pin->getCpuIdx());
                 pins.push_back(std::move(pin));
@@ -584,19 +585,19 @@ TEST_CASE("cpu pinning: claims are exclusive, released and exhaustible", "[util]
         REQUIRE_EQ((int)cpus.size(), n);
         REQUIRE_EQ(getNumFreeCpus(), free0 - n);
         // claim the rest, then one more
+        std::atomic<bool> exhaustedThrew{ false };
         std::thread rest([&] {
             while (getNumFreeCpus() > 0) {
                 pins.push_back(pinThreadToFreeCpu(pthread_self()));
             }
-            bool threw = false;
             try {
                 pinThreadToFreeCpu(pthread_self());
             } catch (const std::runtime_error&) {
-                threw = true;
+                exhaustedThrew = true;
             }
-            REQUIRE(threw);
         });
         rest.join();
+        REQUIRE(exhaustedThrew.load());
         REQUIRE_EQ(getNumFreeCpus(), 0);
     }
     // RAII: everything is free again
