@@ -284,6 +284,55 @@ TEST_CASE("executor: claims, chained messages and pool limits", "[executor]")
     REQUIRE(exec->isShutdown());
 }
 
+// The remaining client verbs (strategy: reference
+// tests/test/planner/test_planner_client_server.cpp)
+TEST_CASE("planner client: ping, decisions in flight, migrations counter, state mains", "[planner]")
+{
+    ClusterFixture f(4);
+    REQUIRE_NOTHROW(f.plannerCli.ping());
+    REQUIRE_EQ(f.plannerCli.getNumMigrations(), 0);
+
+    // The decision of an app can be asked for while it is in flight
+    std::atomic<bool> release{ false };
+    registerTestFunction("demo", "wait", [&](auto*, int, int, auto) {
+        while (!release.load()) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
+        return 0;
+    });
+    auto req = faabric::util::batchExecFactory("demo", "wait", 3);
+    auto decision = f.plannerCli.callFunctions(req);
+    REQUIRE_EQ(decision.nFunctions, 3);
+    auto asked = f.plannerCli.getSchedulingDecision(req);
+    REQUIRE_EQ(asked.appId, decision.appId);
+    REQUIRE_EQ(asked.groupId, decision.groupId);
+    REQUIRE(asked.hosts == decision.hosts);
+    REQUIRE(asked.messageIds == decision.messageIds);
+    // nothing finished yet
+    auto partial = f.plannerCli.getBatchResults(req);
+    REQUIRE(partial != nullptr);
+    REQUIRE(!partial->finished());
+    REQUIRE_EQ(partial->messageresults_size(), 0);
+    release = true;
+    auto status = f.awaitBatch(req);
+    REQUIRE(status->finished());
+    // ...and once it has left the in-flight set there is no decision any more
+    auto gone = f.plannerCli.getSchedulingDecision(req);
+    REQUIRE_EQ(gone.nFunctions, 0);
+    // an app the planner never saw
+    auto unknown = faabric::util::batchExecFactory("demo", "wait", 1);
+    REQUIRE_EQ(f.plannerCli.getSchedulingDecision(unknown).nFunctions, 0);
+
+    // State mains: first claim wins, later claimants learn the owner, dropping
+    // the main lets somebody else take over
+    REQUIRE_EQ(f.plannerCli.stateMain("demo", "k", "hostA", true), std::string("hostA"));
+    REQUIRE_EQ(f.plannerCli.stateMain("demo", "k", "hostB", true), std::string("hostA"));
+    REQUIRE_EQ(f.plannerCli.stateMain("demo", "k", "hostB", false), std::string("hostA"));
+    REQUIRE_EQ(f.plannerCli.stateMain("demo", "other", "hostB", false), std::string(""));
+    f.plannerCli.stateMain("demo", "k", "hostA", false, true);
+    REQUIRE_EQ(f.plannerCli.stateMain("demo", "k", "hostB", true), std::string("hostB"));
+}
+
 TEST_CASE("planner: chained calls build an exec graph", "[planner]")
 {
     ClusterFixture f(8);
