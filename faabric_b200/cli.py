@@ -6,7 +6,9 @@
   python -m faabric_b200.cli cluster [--workers N] [--slots S]   # planner + workers until Ctrl-C
   python -m faabric_b200.cli invoke USER FUNCTION [--count N] [--mpi SIZE] [--input DATA] --port P
   python -m faabric_b200.cli sanitise {address,thread,undefined}   # rebuild host code with a sanitizer, run the C++ suite
+  python -m faabric_b200.cli coverage                              # gcov line coverage of the host code
   python -m faabric_b200.cli sass KERNEL_REGEX                     # dump SASS of matching kernels
+  python -m faabric_b200.cli format [--check]                      # clang-format over csrc/ (when installed)
 """
 
 from __future__ import annotations
@@ -112,6 +114,8 @@ def main(argv=None):
     s = sub.add_parser("sanitise")
     s.add_argument("kind", choices=["address", "thread", "undefined"])
     sub.add_parser("coverage")
+    fm = sub.add_parser("format")
+    fm.add_argument("--check", action="store_true")
     sa = sub.add_parser("sass")
     sa.add_argument("regex")
     a = ap.parse_args(argv)
@@ -159,6 +163,17 @@ def main(argv=None):
         return _run([str(ROOT / "build" / "bin" / "faabric_tests")], env=env)
     if a.cmd == "coverage":
         return _coverage()
+    if a.cmd == "format":
+        # the reference's `inv format-code`; style file at the repo root
+        import shutil
+
+        exe = shutil.which("clang-format")
+        if exe is None:
+            print("clang-format is not installed", file=sys.stderr)
+            return 2
+        files = [str(p) for pat in ("**/*.cpp", "**/*.h", "**/*.cu", "**/*.cuh") for p in (ROOT / "csrc").glob(pat)]
+        files = [f for f in files if not f.endswith(".pb.h")]
+        return _run([exe, "--dry-run", "--Werror"] + files if a.check else [exe, "-i"] + files)
     if a.cmd == "sass":
         lib = ROOT / "faabric_b200" / "lib" / "libfaabric_b200.so"
         return _run(["bash", "-c", f"cuobjdump -sass {lib} | grep -E -A400 'Function : .*({a.regex})' | head -n 600"])
