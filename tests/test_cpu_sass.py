@@ -58,3 +58,19 @@ def test_peer_loads_are_system_scope_and_vectorised(native_lib):
     assert r.stdout.count("LDG.E.STRONG.SYS") > 100
     assert r.stdout.count("LDG.E.128") > 100
     assert "STG.E.128" in r.stdout
+
+
+def test_kernels_fit_their_launch_bounds_without_spilling(native_lib):
+    """Resource usage straight from the cubins: every kernel stays within 128
+    registers (two 512-thread CTAs of the collectives per SM) and keeps at
+    most a few words on the stack."""
+    r = subprocess.run([CUOBJDUMP, "-res-usage", str(_lib.lib_path())], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    usage = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", r.stdout)
+    assert len(usage) > 500, len(usage)
+    assert max(int(u[1]) for u in usage) <= 128
+    assert max(int(u[2]) for u in usage) <= 64
+    assert all(int(u[4]) == 0 for u in usage)
+    # the hot int32 SUM all-reduce (headline dtype) needs few registers
+    hot = [u for u in usage if "llAllReduceKernel" in u[0]]
+    assert hot and max(int(u[1]) for u in hot) <= 64
