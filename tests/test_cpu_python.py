@@ -90,3 +90,15 @@ def test_http_client_builds_the_reference_requests():
     with pytest.raises(PlannerError) as e:
         c.execute_batch(several)
     assert e.value.status == 500 and "No available hosts" in e.value.body
+
+
+def test_local_cluster_example_runs():
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "examples" / "local_cluster.py")], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "echo -> hello" in r.stdout
+    assert r.stdout.count("ran on") == 4
