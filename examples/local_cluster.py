@@ -12,7 +12,9 @@ from faabric_b200.runtime import LocalCluster  # noqa: E402
 
 
 def main() -> int:
-    with LocalCluster(n_workers=2, slots_per_worker=2) as cluster:
+    # optional: first port block to use (python examples/local_cluster.py 22000)
+    base_offset = int(sys.argv[1]) if len(sys.argv) > 1 else None
+    with LocalCluster(n_workers=2, slots_per_worker=2, base_offset=base_offset) as cluster:
         client = cluster.client
         print("hosts:", [(h["ip"], h["slots"]) for h in client.available_hosts()])
 

@@ -98,7 +98,10 @@ def test_local_cluster_example_runs():
     from pathlib import Path
 
     root = Path(__file__).resolve().parents[1]
-    r = subprocess.run([sys.executable, str(root / "examples" / "local_cluster.py")], capture_output=True, text=True, timeout=180)
+    # (a port block of its own: the child cannot see which ones this process uses)
+    r = subprocess.run(
+        [sys.executable, str(root / "examples" / "local_cluster.py"), "22000"], capture_output=True, text=True, timeout=180
+    )
     assert r.returncode == 0, r.stdout + r.stderr
     assert "echo -> hello" in r.stdout
     assert r.stdout.count("ran on") == 4
