@@ -873,6 +873,13 @@ int bodyTypesAndHandles(int rank, int size)
     MPI_Comm_free(&half);
     CHECK_RANK(MPI_Comm_f2c(123456) == MPI_COMM_NULL);
 
+    // non-blocking all-reduce on host buffers completes at the wait
+    std::vector<int> nbIn(100, rank), nbOut(100, -1);
+    MPI_Request nbReq = nullptr;
+    CHECK_RANK(MPI_Iallreduce(nbIn.data(), nbOut.data(), 100, MPI_INT, MPI_SUM, MPI_COMM_WORLD, &nbReq) == MPI_SUCCESS);
+    MPI_Wait(&nbReq, MPI_STATUS_IGNORE);
+    CHECK_RANK(nbOut[0] == base && nbOut[99] == base);
+
     // reduce-scatter with a different block per rank: rank r gets r + 1 sums
     std::vector<int> counts(size);
     int total = 0;
