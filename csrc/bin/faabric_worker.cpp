@@ -31,6 +31,7 @@
 #include <map>
 #include <numeric>
 #include <thread>
+#include <unistd.h>
 
 using namespace faabric::executor;
 
@@ -595,8 +596,15 @@ static void registerFunctions()
         }
         for (int i = start; i < nLoops; i++) {
             if (i == checkAt && start == 0) {
-                // Give the test time to change the cluster under us
-                std::this_thread::sleep_for(std::chrono::milliseconds(300));
+                // Give the test time to change the cluster under us: a fixed
+                // pause, or (cmdline = path) until the test creates that file
+                if (msg.cmdline().empty()) {
+                    std::this_thread::sleep_for(std::chrono::milliseconds(300));
+                } else {
+                    for (int waited = 0; waited < 30000 && ::access(msg.cmdline().c_str(), F_OK) != 0; waited += 5) {
+                        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+                    }
+                }
                 MPI_Barrier(MPI_COMM_WORLD);
                 faabric::mpi::mpiMigrationPoint(i);
             }

@@ -292,6 +292,31 @@ def test_mpi_migration_between_worker_processes(tmp_path):
         assert all(h.get("usedSlots", 0) == 0 for h in c.client.available_hosts())
 
 
+def test_spot_eviction_moves_ranks_off_the_tainted_worker(tmp_path):
+    """Policy `spot`: while the app runs, one worker is announced as the next
+    to be evicted; at the migration point its ranks move to the other worker
+    process (reference dist test "SPOT eviction migration")."""
+    with LocalCluster(n_workers=2, slots_per_worker=4, log_dir=tmp_path) as c:
+        a, b = c.worker_hosts()
+        c.client.set_policy("spot")
+        gate = tmp_path / "gate"
+        batch = c.client.make_batch("mpi", "migrate", mpi_world_size=4)
+        batch["messages"][0]["cmdline"] = str(gate)  # ranks wait for this file before the migration point
+        c.client.preload_decision(batch, [a, a, b, b])
+        c.client.execute_batch(batch)
+        c.client.set_next_evicted_vm([b])
+        assert c.client.in_flight_apps().get("nextEvictedVmIps") == [b]
+        gate.write_text("go")
+        st = c.client.wait_for_batch(batch["appId"], timeout=60)
+        res = _results(st)
+        assert len(res) == 4, res
+        assert all(m.get("returnValue", 0) == 0 for m in res), res
+        assert {m["executedHost"] for m in res} == {a}, res
+        assert sorted(m["output_data"] for m in res) == ["resumed at 3", "resumed at 3", "stayed", "stayed"]
+        assert c.client.in_flight_apps().get("numMigrations", 0) == 1
+        assert all(h.get("usedSlots", 0) == 0 for h in c.client.available_hosts())
+
+
 def test_group_locks_barriers_and_shared_state_across_workers(cluster):
     """Four functions of one batch, two per worker process: a counter in
     distributed state (main elected through the planner, replicas pull/push
