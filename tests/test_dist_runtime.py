@@ -205,15 +205,16 @@ def test_worker_joining_later_takes_work(tmp_path):
         assert {m["executedHost"] for m in res} == {first, second}
 
 
-def test_ordered_ptp_streams_between_workers(cluster):
+def test_ordered_ptp_streams_between_workers(tmp_path):
     """Every pair of four functions (two per worker process) exchanges 500
     sequence-numbered messages; receivers re-order what the network delivers
     out of order."""
-    st = cluster.client.invoke("ptp", "stream", count=4, input_data="500", timeout=60)
-    res = st["messageResults"]
-    assert len(res) == 4 and all(m.get("returnValue", 0) == 0 for m in res), res
-    assert all(m["output_data"].startswith("0 out of order") for m in res), res
-    assert {m["output_data"].split()[-1] for m in res} == set(cluster.worker_hosts())
+    with LocalCluster(n_workers=2, slots_per_worker=2, log_dir=tmp_path) as c:
+        st = c.client.invoke("ptp", "stream", count=4, input_data="500", timeout=90)
+        res = st["messageResults"]
+        assert len(res) == 4 and all(m.get("returnValue", 0) == 0 for m in res), res
+        assert all(m["output_data"].startswith("0 out of order") for m in res), res
+        assert {m["output_data"].split()[-1] for m in res} == set(c.worker_hosts())
 
 
 def test_two_mpi_worlds_run_concurrently(tmp_path):
