@@ -133,7 +133,9 @@ def test_servers_survive_garbage_on_every_port(tmp_path):
     import psutil
 
     with LocalCluster(n_workers=2, slots_per_worker=2, log_dir=tmp_path) as c:
-        children = psutil.Process().children(recursive=True)
+        # only THIS cluster's processes (the module-wide fixture keeps serving
+        # other tests and must not be poked)
+        children = [psutil.Process(p.pid) for p in c.procs]
         ports = set()
         for ch in children:
             try:
