@@ -175,8 +175,21 @@ def main(argv=None):
         files = [f for f in files if not f.endswith(".pb.h")]
         return _run([exe, "--dry-run", "--Werror"] + files if a.check else [exe, "-i"] + files)
     if a.cmd == "sass":
+        import re
+        import subprocess
+
         lib = ROOT / "faabric_b200" / "lib" / "libfaabric_b200.so"
-        return _run(["bash", "-c", f"cuobjdump -sass {lib} | grep -E -A400 'Function : .*({a.regex})' | head -n 600"])
+        listing = subprocess.run(["cuobjdump", "-res-usage", str(lib)], capture_output=True, text=True).stdout
+        names = [n for n in re.findall(r"Function (\S+):", listing) if re.search(a.regex, n)]
+        if not names:
+            print(f"no kernel matches {a.regex!r}", file=sys.stderr)
+            return 1
+        if len(names) > 3:
+            print(f"# {len(names)} kernels match, showing the first 3", file=sys.stderr)
+        rc = 0
+        for n in names[:3]:
+            rc |= _run(["cuobjdump", "-sass", "-fun", n, str(lib)])
+        return rc
     return 1
 
 
