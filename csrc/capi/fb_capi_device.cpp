@@ -45,6 +45,9 @@ struct FbConfigC
     uint64_t oneShotMaxBytes;
     uint64_t nvlsMinBytes;
     uint64_t bcast2StepMinBytes;
+    uint64_t p2pBounceBytes;
+    int32_t groupBlocks;
+    int32_t streamSync; // -1 auto, 0 in-kernel barriers, 1 stream memory ops
 };
 
 const char* fb_last_error()
@@ -74,6 +77,9 @@ void fb_default_config(FbConfigC* out)
     out->oneShotMaxBytes = c.oneShotMaxBytes;
     out->nvlsMinBytes = c.nvlsMinBytes;
     out->bcast2StepMinBytes = c.bcast2StepMinBytes;
+    out->p2pBounceBytes = c.p2pBounceBytes;
+    out->groupBlocks = c.groupBlocks;
+    out->streamSync = c.streamSync;
 }
 
 static CommConfig fromC(const FbConfigC* in)
@@ -95,6 +101,9 @@ static CommConfig fromC(const FbConfigC* in)
     c.oneShotMaxBytes = in->oneShotMaxBytes;
     c.nvlsMinBytes = in->nvlsMinBytes;
     c.bcast2StepMinBytes = in->bcast2StepMinBytes;
+    c.p2pBounceBytes = in->p2pBounceBytes;
+    c.groupBlocks = in->groupBlocks;
+    c.streamSync = in->streamSync;
     return c;
 }
 
@@ -207,6 +216,9 @@ int fb_comm_configure(void* h, int key, uint64_t value)
             break;
         case 7:
             c.nvlsScalarMinBytes = value;
+            break;
+        case 8:
+            c.groupBlocks = (int)value;
             break;
         default:
             return FB_E_INVALID;
@@ -442,6 +454,113 @@ int fb_send(void* h, const void* buf, uint64_t bytes, int peer, void* stream)
 int fb_recv(void* h, void* buf, uint64_t bytes, int peer, void* stream)
 {
     return COMM(h)->recv(buf, bytes, peer, (cudaStream_t)stream);
+}
+
+int fb_sendrecv(void* h,
+                const void* sendBuf,
+                uint64_t sendBytes,
+                int dst,
+                void* recvBuf,
+                uint64_t recvBytes,
+                int src,
+                void* stream)
+{
+    return COMM(h)->sendRecv(
+      sendBuf, sendBytes, dst, recvBuf, recvBytes, src, (cudaStream_t)stream);
+}
+
+int fb_comm_stream_sync(void* h)
+{
+    return COMM(h)->streamSync() ? 1 : 0;
+}
+
+int fb_comm_stream_wait_supported(void* h)
+{
+    return COMM(h)->streamWaitSupported() ? 1 : 0;
+}
+
+// 1 = stream drained, 0 = timed out (pending stream waits were released and
+// the error word set)
+int fb_comm_sync_bounded(void* h, void* stream, uint64_t timeoutMs)
+{
+    return COMM(h)->syncStreamBounded((cudaStream_t)stream, timeoutMs) ? 1 : 0;
+}
+
+// ---- grouped all-reduce ----
+struct FbGroupPlanHandle
+{
+    std::shared_ptr<Communicator::GroupPlan> plan;
+};
+
+static std::vector<Communicator::GroupItem> groupItems(int n,
+                                                       const void* const* send,
+                                                       void* const* recv,
+                                                       const uint64_t* counts)
+{
+    std::vector<Communicator::GroupItem> items((size_t)n);
+    for (int i = 0; i < n; i++) {
+        items[i].send = send[i];
+        items[i].recv = recv[i];
+        items[i].count = (size_t)counts[i];
+    }
+    return items;
+}
+
+void* fb_group_prepare(void* h,
+                       int n,
+                       const void* const* send,
+                       void* const* recv,
+                       const uint64_t* counts,
+                       int dtype)
+{
+    FB_TRY
+    auto items = groupItems(n, send, recv, counts);
+    int rc = FB_OK;
+    auto plan = COMM(h)->prepareGroup(items.data(), items.size(), dtype, &rc);
+    if (!plan) {
+        g_lastError = std::string("prepareGroup: ") + Communicator::errorString(rc);
+        return nullptr;
+    }
+    auto* ph = new FbGroupPlanHandle();
+    ph->plan = plan;
+    return ph;
+    FB_CATCH(nullptr)
+}
+
+int fb_group_allreduce(void* h, void* plan, int op, int flags, void* stream)
+{
+    if (plan == nullptr) {
+        return FB_E_INVALID;
+    }
+    return COMM(h)->allReduceGroup(
+      *((FbGroupPlanHandle*)plan)->plan, op, flags, (cudaStream_t)stream);
+}
+
+int fb_group_plan_launches(void* plan)
+{
+    return plan ? (int)Communicator::groupPlanLaunches(*((FbGroupPlanHandle*)plan)->plan) : 0;
+}
+
+void fb_group_plan_free(void* plan)
+{
+    delete (FbGroupPlanHandle*)plan;
+}
+
+int fb_allreduce_many(void* h,
+                      int n,
+                      const void* const* send,
+                      void* const* recv,
+                      const uint64_t* counts,
+                      int dtype,
+                      int op,
+                      int flags,
+                      void* stream)
+{
+    FB_TRY
+    auto items = groupItems(n, send, recv, counts);
+    return COMM(h)->allReduceMany(
+      items.data(), items.size(), dtype, op, flags, (cudaStream_t)stream);
+    FB_CATCH(FB_E_CUDA)
 }
 
 int fb_put_signal(void* h,

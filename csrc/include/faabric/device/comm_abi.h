@@ -25,22 +25,36 @@ extern "C" {
 // Signal pad layout (uint32 words):
 //   [0, FB_MAX_BLOCKS*FB_MAX_RANKS)            barrier flags  flag[block][peer]
 //   [FB_SIG_EPOCH_OFF, +FB_MAX_BLOCKS)         per-block local epoch counters
-//   [FB_SIG_MBOX_OFF, ...)                     p2p mailbox sequence words
+//   [FB_SIG_MBOX_OFF, ...)                     p2p words (see below)
 //   [FB_SIG_USER_OFF, ...)                     user signal words
 #define FB_SIG_FLAG_WORDS (FB_MAX_BLOCKS * FB_MAX_RANKS)
 #define FB_SIG_EPOCH_OFF FB_SIG_FLAG_WORDS
 #define FB_SIG_MBOX_OFF (FB_SIG_EPOCH_OFF + FB_MAX_BLOCKS)
-// p2p mailbox: FB_P2P_BLOCKS sub-channels per ordered pair; four arrays of
-// [rank][block] words: ready (in receiver pad), ack (in sender pad), and the
-// local send / recv sequence counters
-#define FB_P2P_BLOCKS 8
-#define FB_P2P_FLAG_WORDS (FB_MAX_RANKS * FB_P2P_BLOCKS)
-#define FB_SIG_USER_OFF (FB_SIG_MBOX_OFF + 4 * FB_P2P_FLAG_WORDS)
+// Point-to-point: per ordered pair (src -> dst)
+//   ready[src]   in dst's pad : sequence number of the last message posted
+//   desc[src][k] in dst's pad : {offLo, offHi, lenLo, lenHi} of message k % RING
+//   ack[dst]     in src's pad : sequence number of the last message pulled
+//   done[2][peer] local       : CTA completion counters of the send / pull kernels
+// The payload itself stays in the SENDER's symmetric heap (bounce ring or the
+// user's own symmetric buffer); the receiver pulls it over NVLink.
+#define FB_P2P_RING 4
+#define FB_P2P_READY_OFF FB_SIG_MBOX_OFF
+#define FB_P2P_ACK_OFF (FB_P2P_READY_OFF + FB_MAX_RANKS)
+#define FB_P2P_DONE_OFF (FB_P2P_ACK_OFF + FB_MAX_RANKS)
+#define FB_P2P_DESC_OFF (FB_P2P_DONE_OFF + 2 * FB_MAX_RANKS)
+#define FB_P2P_WORDS (4 * FB_MAX_RANKS + FB_MAX_RANKS * FB_P2P_RING * 4)
+#define FB_SIG_USER_OFF (FB_SIG_MBOX_OFF + 512)
 // user signals (put-with-signal): value words then consumed-count words
 #define FB_SIG_USER_WORDS 256
 // per-CTA epoch words of the LL all-reduce (FB_LL_BLOCKS words per channel)
 #define FB_SIG_LL_EPOCH_OFF (FB_SIG_USER_OFF + 2 * FB_SIG_USER_WORDS)
 #define FB_MAX_CHANNELS 8
+// stream-ordered barrier flags (one word per peer per channel): used when the
+// cross-rank synchronisation is done with stream memory operations instead of
+// in-kernel spins (several ranks time-sharing ONE GPU, profilers that
+// serialise kernels)
+#define FB_SIG_SBAR_OFF (FB_SIG_LL_EPOCH_OFF + 64)
+#define FB_SIG_SBAR_WORDS (FB_MAX_CHANNELS * FB_MAX_RANKS)
 #define FB_SIG_TOTAL_WORDS 4096
 #define FB_SIG_BYTES (FB_SIG_TOTAL_WORDS * 4)
 
@@ -48,6 +62,8 @@ extern "C" {
 #define FB_ERR_NONE 0u
 #define FB_ERR_BARRIER_TIMEOUT 1u
 #define FB_ERR_FLAG_TIMEOUT 2u
+#define FB_ERR_BAD_DESC 3u
+#define FB_ERR_HOST_ABORT 4u
 
 typedef struct FbCommDev {
     int32_t rank;

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstddef>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -41,7 +42,18 @@ struct CommConfig
 {
     size_t heapBytes = (size_t)256 << 20; // user-visible symmetric heap
     size_t stageBytes = (size_t)32 << 20; // each of the two staging buffers
-    size_t slotBytes = (size_t)128 << 10; // p2p eager slot
+    size_t slotBytes = (size_t)128 << 10; // (legacy knob, unused)
+    // p2p: bytes of bounce ring per destination peer in the sender's heap;
+    // messages up to half of it are sent eagerly in one piece
+    size_t p2pBounceBytes = (size_t)8 << 20;
+    // CTAs of a grouped all-reduce launch (0 = as many as there are barrier
+    // slots for the channel, capped at 128)
+    int groupBlocks = 0;
+    // Cross-rank synchronisation with stream memory operations instead of
+    // in-kernel spins: needed when kernels of different ranks may not be
+    // co-resident (ranks sharing one GPU, kernel-serialising profilers).
+    // -1 = decide at creation (on when two ranks share a device)
+    int streamSync = -1;
     uint64_t timeoutMs = 10000;           // device spin watchdog
     bool useVmm = true;
     bool useMulticast = true;
@@ -188,9 +200,51 @@ class Communicator
                  cudaStream_t s);
     int barrier(cudaStream_t s);
 
-    // ---- point to point (device-side mailbox, per-pair FIFO) ----
+    // ---- grouped all-reduce: many independent all-reduces, ONE launch ----
+    struct GroupItem
+    {
+        const void* send; // symmetric heap, 16-byte aligned
+        void* recv;       // symmetric heap, 16-byte aligned (may equal send)
+        size_t count;     // elements
+    };
+    struct GroupPlan;
+    // Builds (and uploads) this rank's segment tables.  Collective: every rank
+    // must pass the same list (same offsets, same counts).  Returns null and
+    // sets *rc when an item is not symmetric / aligned.
+    std::shared_ptr<GroupPlan> prepareGroup(const GroupItem* items,
+                                            size_t nItems,
+                                            int dtype,
+                                            int* rc = nullptr);
+    int allReduceGroup(const GroupPlan& plan, int op, int flags, cudaStream_t s);
+    // prepare + launch for a transient list (MPI_Iallreduce bursts); falls back
+    // to per-item allReduce calls when the list cannot be grouped
+    int allReduceMany(const GroupItem* items,
+                      size_t nItems,
+                      int dtype,
+                      int op,
+                      int flags,
+                      cudaStream_t s);
+    static size_t groupPlanLaunches(const GroupPlan& plan);
+
+    // ---- point to point (per-pair FIFO; no kernel ever spins on a peer) ----
+    // Operations on one ordered pair must be issued in a consistent stream
+    // order on both sides.  `peer == rank()` is allowed (self message).
     int send(const void* buf, size_t bytes, int peer, cudaStream_t s);
     int recv(void* buf, size_t bytes, int peer, cudaStream_t s);
+    // Exchange without the send-before-recv ordering hazard of big messages:
+    // chunks of both directions are interleaved
+    int sendRecv(const void* sendBuf,
+                 size_t sendBytes,
+                 int dst,
+                 void* recvBuf,
+                 size_t recvBytes,
+                 int src,
+                 cudaStream_t s);
+    bool streamSync() const { return streamSync_; }
+    bool streamWaitSupported() const { return streamWaitOk_; }
+    // Bounded wait for `s` (polls; never blocks forever on a stream-level wait
+    // whose peer died).  Returns false after releasing the stuck waits.
+    bool syncStreamBounded(cudaStream_t s, uint64_t timeoutMs);
     // zero-copy put into a peer's symmetric buffer + signal bump
     int putSignal(const void* local,
                   uint64_t dstOffset,
@@ -236,7 +290,18 @@ class Communicator
 
     // heap layout (offsets from heap base)
     uint64_t llOff_ = 0;
-    uint64_t mboxOff_ = 0;
+    uint64_t mboxOff_ = 0; // p2p bounce rings: [peer][2 slots]
+    uint64_t bounceSlotBytes_ = 0;
+    uint32_t sendSeq_[FB_MAX_RANKS] = { 0 };
+    uint32_t recvSeq_[FB_MAX_RANKS] = { 0 };
+    uint32_t sbarEpoch_[FB_MAX_CHANNELS] = { 0 };
+    uint32_t userSigConsumed_[FB_SIG_USER_WORDS] = { 0 };
+    bool streamSync_ = false;
+    bool streamWaitOk_ = false;
+    // transient group tables (allReduceMany)
+    struct ManySlot;
+    std::vector<std::shared_ptr<ManySlot>> manySlots_;
+    size_t manyNext_ = 0;
     uint64_t stageSendOff_ = 0;
     uint64_t stageRecvOff_ = 0;
     uint64_t userOff_ = 0;
@@ -259,6 +324,12 @@ class Communicator
     int blocksFor(uint64_t vecs, int perThread) const;
     int widthFor(const void* a, const void* b, uint64_t bytes) const;
     FbCommDev devFor(int flags) const;
+    void finishSetup();
+    int streamWaitGe(cudaStream_t s, const uint32_t* localWord, uint32_t value);
+    int streamBarrier(int flags, cudaStream_t s);
+    int sendChunk(const uint8_t* buf, size_t len, int peer, cudaStream_t s);
+    int recvChunk(uint8_t* buf, size_t len, int peer, cudaStream_t s);
+    void abortPendingWaits();
 
     int reduceLike(int kind,
                    const void* send,

@@ -67,6 +67,16 @@ struct DriverApi
                                           CUmulticastGranularity_flags) =
       nullptr;
 
+    // stream memory operations (optional): waits that occupy no SM
+    CUresult (*cuStreamWaitValue32)(CUstream,
+                                    CUdeviceptr,
+                                    cuuint32_t,
+                                    unsigned int) = nullptr;
+    CUresult (*cuStreamWriteValue32)(CUstream,
+                                     CUdeviceptr,
+                                     cuuint32_t,
+                                     unsigned int) = nullptr;
+
     std::string errStr(CUresult r) const;
 };
 

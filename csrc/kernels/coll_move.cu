@@ -273,207 +273,161 @@ cudaError_t launchBarrier(const FbCommDev& c, cudaStream_t s)
 }
 
 // ----------------------------------------------------------------------------
-// Point-to-point mailbox.
+// Point to point.
 //
-// Every ordered pair (src -> dst) owns, in the *receiver's* memory,
-// FB_P2P_BLOCKS sub-channels with two eager slots each.  CTA b of the send
-// kernel on src streams its share of the message into sub-channel b of dst
-// (16-byte peer stores) and publishes a sequence number with st.release.sys;
-// CTA b of the recv kernel acquires it, drains the slot into the user buffer
-// and acknowledges into the *sender's* pad so the slot can be reused.  Sequence
-// counters live in device memory, so send/recv compose in stream order and
-// under CUDA-graph replay with no host involvement: per-pair FIFO ordering
-// (the reference's per-(sender,receiver) queue semantics) comes for free.
+// send(buf -> dst):  ONE kernel copies the payload into the sender's bounce
+// ring (its own symmetric heap, i.e. local HBM), and the last CTA to finish
+// posts a descriptor {offset, length} plus a sequence number into the
+// RECEIVER's signal pad.  The sender never waits for the receiver inside a
+// kernel: slot reuse is guarded by a stream-level wait on the ack word.
+//
+// recv(buf <- src):  the stream waits (cuStreamWaitValue32, no SM is occupied)
+// until the sequence number arrives, then ONE kernel pulls the payload from
+// the sender's heap over NVLink straight into the user buffer and the last
+// CTA acknowledges into the sender's pad.
+//
+// No kernel ever spins on a peer, so ranks that time-share a GPU, hardware
+// queue aliasing or a profiler serialising kernels cannot deadlock it; the
+// reference's per-(sender, receiver) FIFO (src/mpi/MpiWorld.cpp:590-784) falls
+// out of the per-pair sequence numbers.
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t* p2pReadyFlag(const FbCommDev& c,
-                                                  int onRank,
-                                                  int src,
-                                                  int blk)
+__device__ __forceinline__ bool lastBlockDone(uint32_t* counter)
 {
-    return c.sig[onRank] + FB_SIG_MBOX_OFF + (src * FB_P2P_BLOCKS + blk);
-}
-__device__ __forceinline__ uint32_t* p2pAckFlag(const FbCommDev& c,
-                                                int onRank,
-                                                int dst,
-                                                int blk)
-{
-    return c.sig[onRank] + FB_SIG_MBOX_OFF + FB_P2P_FLAG_WORDS +
-           (dst * FB_P2P_BLOCKS + blk);
-}
-__device__ __forceinline__ uint32_t* p2pSendSeq(const FbCommDev& c,
-                                                int dst,
-                                                int blk)
-{
-    return c.sig[c.rank] + FB_SIG_MBOX_OFF + 2 * FB_P2P_FLAG_WORDS +
-           (dst * FB_P2P_BLOCKS + blk);
-}
-__device__ __forceinline__ uint32_t* p2pRecvSeq(const FbCommDev& c,
-                                                int src,
-                                                int blk)
-{
-    return c.sig[c.rank] + FB_SIG_MBOX_OFF + 3 * FB_P2P_FLAG_WORDS +
-           (src * FB_P2P_BLOCKS + blk);
-}
-
-// Bytes handled by CTA b: the message is cut into FB_P2P_BLOCKS contiguous
-// shares (16-byte aligned except the last)
-__device__ __forceinline__ void p2pShare(uint64_t bytes,
-                                         int blk,
-                                         uint64_t& beg,
-                                         uint64_t& end)
-{
-    uint64_t share = ((bytes + FB_P2P_BLOCKS - 1) / FB_P2P_BLOCKS + 15) &
-                     ~(uint64_t)15;
-    beg = min((uint64_t)blk * share, bytes);
-    end = min(beg + share, bytes);
-}
-
-template<int W>
-__device__ __forceinline__ void blockCopy(uint8_t* dst,
-                                          const uint8_t* src,
-                                          uint64_t bytes)
-{
-    gridCopy<W>(dst, src, bytes, threadIdx.x, blockDim.x);
+    __shared__ int sLast;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t prev = atomicAdd(counter, 1u);
+        sLast = (prev == gridDim.x - 1) ? 1 : 0;
+        if (sLast) {
+            *counter = 0; // next launch on this (stream-ordered) pair starts clean
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    return sLast != 0;
 }
 
 template<int W>
 __global__ void __launch_bounds__(512, 1) p2pSendKernel(const P2PArgs a)
 {
     const FbCommDev& c = a.comm;
-    const int blk = blockIdx.x;
-    uint64_t beg, end;
-    p2pShare(a.bytes, blk, beg, end);
-
-    __shared__ uint32_t sSeq;
-    __shared__ int sOk;
-    if (threadIdx.x == 0) {
-        sSeq = *p2pSendSeq(c, a.peer, blk);
-        sOk = 1;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    if (a.stage) {
+        uint8_t* dst = c.heap[c.rank] + a.srcOff;
+        const uint64_t lenW = a.bytes - (a.bytes % W);
+        gridCopy<W>(dst, a.local, lenW, tid, nthreads);
+        if (tid == 0) {
+            for (uint64_t b = lenW; b < a.bytes; b++) {
+                dst[b] = a.local[b];
+            }
+        }
     }
-    __syncthreads();
-    uint32_t seq = sSeq;
-
-    uint8_t* slots = c.heap[a.peer] + a.mboxOff +
-                     ((uint64_t)c.rank * FB_P2P_BLOCKS + blk) * 2 *
-                       a.slotBytes;
-    // Always send at least one (possibly empty) chunk so zero-byte messages
-    // still synchronise, like the reference's empty MPI messages
-    uint64_t off = beg;
-    do {
-        uint64_t len = min(a.slotBytes, end - off);
-        seq += 1;
-        // wait until the slot we are about to overwrite was drained: the
-        // receiver must have acked chunk (seq - 2)
-        if (threadIdx.x == 0) {
-            bool ok = waitFlagGe(
-              c, p2pAckFlag(c, c.rank, a.peer, blk), seq - 2, FB_ERR_FLAG_TIMEOUT);
-            if (!ok) {
-                sOk = 0;
-            }
-        }
-        __syncthreads();
-        if (!sOk) {
-            break;
-        }
-        uint8_t* slot = slots + (uint64_t)(seq & 1) * a.slotBytes;
-        uint64_t lenW = len - (len % W);
-        blockCopy<W>(slot, a.local + off, lenW);
-        if (threadIdx.x == 0) {
-            for (uint64_t b = lenW; b < len; b++) {
-                slot[b] = a.local[off + b];
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            stReleaseSys(p2pReadyFlag(c, a.peer, c.rank, blk), seq);
-        }
-        off += len;
-    } while (off < end);
-
-    if (threadIdx.x == 0) {
-        *p2pSendSeq(c, a.peer, blk) = seq;
+    uint32_t* done = c.sig[c.rank] + FB_P2P_DONE_OFF + a.peer;
+    if (lastBlockDone(done) && threadIdx.x == 0) {
+        uint32_t* desc = c.sig[a.peer] + FB_P2P_DESC_OFF +
+                         ((uint32_t)c.rank * FB_P2P_RING + (a.seq % FB_P2P_RING)) * 4;
+        desc[0] = (uint32_t)(a.srcOff & 0xffffffffu);
+        desc[1] = (uint32_t)(a.srcOff >> 32);
+        desc[2] = (uint32_t)(a.bytes & 0xffffffffu);
+        desc[3] = (uint32_t)(a.bytes >> 32);
+        // release: payload (local HBM) and descriptor are visible before seq
+        stReleaseSys(c.sig[a.peer] + FB_P2P_READY_OFF + c.rank, a.seq);
     }
 }
 
 template<int W>
-__global__ void __launch_bounds__(512, 1) p2pRecvKernel(const P2PArgs a)
+__global__ void __launch_bounds__(512, 1) p2pPullKernel(const P2PArgs a)
 {
     const FbCommDev& c = a.comm;
-    const int blk = blockIdx.x;
-    uint64_t beg, end;
-    p2pShare(a.bytes, blk, beg, end);
-
-    __shared__ uint32_t sSeq;
-    __shared__ int sOk;
-    if (threadIdx.x == 0) {
-        sSeq = *p2pRecvSeq(c, a.peer, blk);
-        sOk = 1;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    // the stream-level wait already saw seq; the acquire orders the reads below
+    const uint32_t seen = ldAcquireSys(c.sig[c.rank] + FB_P2P_READY_OFF + a.peer);
+    const uint32_t* desc = c.sig[c.rank] + FB_P2P_DESC_OFF +
+                           ((uint32_t)a.peer * FB_P2P_RING + (a.seq % FB_P2P_RING)) * 4;
+    const uint64_t srcOff = (uint64_t)desc[0] | ((uint64_t)desc[1] << 32);
+    uint64_t len = (uint64_t)desc[2] | ((uint64_t)desc[3] << 32);
+    bool ok = (int32_t)(seen - a.seq) >= 0 && len <= a.bytes &&
+              srcOff + len <= a.heapBytes;
+    if (!ok) {
+        // never posted (host abort released the wait) or a size mismatch
+        if (tid == 0 && c.err != nullptr) {
+            stRelaxedSys(c.err, FB_ERR_BAD_DESC);
+        }
+        len = 0;
     }
-    __syncthreads();
-    uint32_t seq = sSeq;
-
-    const uint8_t* slots = c.heap[c.rank] + a.mboxOff +
-                           ((uint64_t)a.peer * FB_P2P_BLOCKS + blk) * 2 *
-                             a.slotBytes;
-    uint64_t off = beg;
-    do {
-        uint64_t len = min(a.slotBytes, end - off);
-        seq += 1;
-        if (threadIdx.x == 0) {
-            bool ok = waitFlagGe(c,
-                                 p2pReadyFlag(c, c.rank, a.peer, blk),
-                                 seq,
-                                 FB_ERR_FLAG_TIMEOUT);
-            if (!ok) {
-                sOk = 0;
-            }
+    const uint8_t* src = c.heap[a.peer] + srcOff;
+    const uint64_t lenW = len - (len % W);
+    gridCopy<W>(a.local, src, lenW, tid, nthreads);
+    if (tid == 0) {
+        for (uint64_t b = lenW; b < len; b++) {
+            a.local[b] = src[b];
         }
-        __syncthreads();
-        if (!sOk) {
-            break;
-        }
-        const uint8_t* slot = slots + (uint64_t)(seq & 1) * a.slotBytes;
-        uint64_t lenW = len - (len % W);
-        blockCopy<W>(a.local + off, slot, lenW);
-        if (threadIdx.x == 0) {
-            for (uint64_t b = lenW; b < len; b++) {
-                a.local[off + b] = slot[b];
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            // slot drained: let the sender reuse it
-            stReleaseSys(p2pAckFlag(c, a.peer, c.rank, blk), seq);
-        }
-        off += len;
-    } while (off < end);
-
-    if (threadIdx.x == 0) {
-        *p2pRecvSeq(c, a.peer, blk) = seq;
+    }
+    uint32_t* done = c.sig[c.rank] + FB_P2P_DONE_OFF + FB_MAX_RANKS + a.peer;
+    if (lastBlockDone(done) && threadIdx.x == 0) {
+        // every CTA's loads have completed (they fed stores): the sender may
+        // recycle the bounce slot / its own buffer
+        stReleaseSys(c.sig[a.peer] + FB_P2P_ACK_OFF + c.rank, a.seq);
     }
 }
 
-cudaError_t launchP2PSend(const P2PArgs& a, int width, cudaStream_t s)
+// Fallback for drivers without stream memory operations: a one-thread spin
+// (this one DOES depend on the peer's kernel making progress)
+__global__ void waitWordKernel(const FbCommDev c, const uint32_t* word, uint32_t target)
+{
+    waitFlagGe(c, word, target, FB_ERR_FLAG_TIMEOUT);
+}
+
+// Stream-ordered barrier, signalling half: tell every peer "I am at epoch e"
+__global__ void signalPeersKernel(const FbCommDev c, uint32_t wordOff, uint32_t value)
+{
+    if ((int)threadIdx.x < c.nranks && (int)threadIdx.x != c.rank) {
+        stReleaseSys(c.sig[threadIdx.x] + wordOff + c.rank, value);
+    }
+}
+
+cudaError_t launchP2PSend(const P2PArgs& a, int width, int blocks, cudaStream_t s)
 {
     if (width == 16) {
-        p2pSendKernel<16><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+        p2pSendKernel<16><<<blocks, 512, 0, s>>>(a);
     } else if (width == 4) {
-        p2pSendKernel<4><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+        p2pSendKernel<4><<<blocks, 512, 0, s>>>(a);
     } else {
-        p2pSendKernel<1><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+        p2pSendKernel<1><<<blocks, 512, 0, s>>>(a);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launchP2PRecv(const P2PArgs& a, int width, cudaStream_t s)
+cudaError_t launchP2PPull(const P2PArgs& a, int width, int blocks, cudaStream_t s)
 {
     if (width == 16) {
-        p2pRecvKernel<16><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+        p2pPullKernel<16><<<blocks, 512, 0, s>>>(a);
     } else if (width == 4) {
-        p2pRecvKernel<4><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+        p2pPullKernel<4><<<blocks, 512, 0, s>>>(a);
     } else {
-        p2pRecvKernel<1><<<FB_P2P_BLOCKS, 512, 0, s>>>(a);
+        p2pPullKernel<1><<<blocks, 512, 0, s>>>(a);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launchWaitWord(const FbCommDev& c,
+                           const uint32_t* word,
+                           uint32_t target,
+                           cudaStream_t s)
+{
+    waitWordKernel<<<1, 1, 0, s>>>(c, word, target);
+    return cudaGetLastError();
+}
+
+cudaError_t launchSignalPeers(const FbCommDev& c,
+                              uint32_t wordOff,
+                              uint32_t value,
+                              cudaStream_t s)
+{
+    signalPeersKernel<<<1, 32, 0, s>>>(c, wordOff, value);
     return cudaGetLastError();
 }
 
@@ -557,13 +511,15 @@ cudaError_t preloadMoveKernels()
     FB_PRELOAD((moveKernel<W, 4>))                                             \
     FB_PRELOAD((moveKernel<W, 8>))                                             \
     FB_PRELOAD((p2pSendKernel<W>))                                             \
-    FB_PRELOAD((p2pRecvKernel<W>))                                             \
+    FB_PRELOAD((p2pPullKernel<W>))                                             \
     FB_PRELOAD((putSignalKernel<W>))
     FB_PRELOAD_W(16)
     FB_PRELOAD_W(4)
     FB_PRELOAD_W(1)
     FB_PRELOAD(barrierKernel)
     FB_PRELOAD(waitSignalKernel)
+    FB_PRELOAD(waitWordKernel)
+    FB_PRELOAD(signalPeersKernel)
 #undef FB_PRELOAD_W
 #undef FB_PRELOAD
     return e;

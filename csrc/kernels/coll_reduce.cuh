@@ -348,6 +348,206 @@ cudaError_t launchLL(const LLArgs& a, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+
+// ----------------------------------------------------------------------------
+// Grouped all-reduce: every tensor of a group (e.g. the 214 gradient tensors of
+// one training step, or an MPI_Iallreduce burst) in ONE launch per rank.
+// Semantics are those of independent per-tensor all-reduces; what is shared is
+// the synchronisation: two cross-rank barriers per GROUP instead of per tensor
+// (the per-call latency is what bounded the reference benchmark, which issues
+// 214 MPI_Allreduce calls per pass: tests/dist/mpi/benchmarks/mpi_allreduce.cpp
+// :24-50).  Work is cut into warp-sized chunks of the rank's segment list so
+// tiny tensors cost one warp iteration, not one kernel.
+// ----------------------------------------------------------------------------
+template<typename VR>
+__device__ __forceinline__ void groupTail(const FbCommDev& c,
+                                          const GroupSeg& sg,
+                                          int n)
+{
+    constexpr int EB = VR::ELEM_BYTES;
+    const uint64_t base = (uint64_t)sg.nVec * 16;
+    for (uint32_t e = 0; e + EB <= sg.tailBytes; e += EB) {
+        alignas(16) uint8_t acc[16];
+        alignas(16) uint8_t in[16];
+        const uint8_t* s0 = c.heap[0] + sg.sendOff + base + e;
+        for (int b = 0; b < EB; b++) {
+            acc[b] = s0[b];
+        }
+        for (int p = 1; p < n; p++) {
+            const uint8_t* sp = c.heap[p] + sg.sendOff + base + e;
+            for (int b = 0; b < EB; b++) {
+                in[b] = sp[b];
+            }
+            VR::applyTail(acc, in);
+        }
+        for (int p = 0; p < n; p++) {
+            uint8_t* d = c.heap[p] + sg.recvOff + base + e;
+            for (int b = 0; b < EB; b++) {
+                d[b] = acc[b];
+            }
+        }
+    }
+}
+
+template<typename VR, int NR>
+__global__ void __launch_bounds__(512, 1) groupAllReduceKernel(
+  const GroupArgs a)
+{
+    extern __shared__ __align__(16) uint8_t sGroupRaw[];
+    GroupSeg* sSegs = reinterpret_cast<GroupSeg*>(sGroupRaw);
+    const FbCommDev& c = a.comm;
+    const int n = (NR > 0) ? NR : c.nranks;
+    // the segment table is local memory: fetch it while the peers arrive
+    {
+        const Vec16* src = reinterpret_cast<const Vec16*>(a.segs);
+        Vec16* dst = reinterpret_cast<Vec16*>(sGroupRaw);
+        for (uint32_t i = threadIdx.x; i < a.nSegs * 2; i += blockDim.x) {
+            dst[i] = src[i];
+        }
+    }
+    BlockBarrier bar;
+    bar.load(c);
+    bool ok = true;
+    if (!a.noSync) {
+        ok = bar.sync(c); // (also publishes sSegs to the CTA)
+    } else {
+        __syncthreads();
+    }
+
+    if (ok && a.nSegs > 0) {
+        constexpr int UNROLL = (NR == 8) ? 2 : 4;
+        constexpr uint32_t CHUNK = 32u * UNROLL;
+        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t warpsPerCta = blockDim.x >> 5;
+        const uint32_t warpStride = gridDim.x * warpsPerCta;
+        int cur = 0;
+        for (uint32_t ch = blockIdx.x * warpsPerCta + (threadIdx.x >> 5);
+             ch < a.totalChunks;
+             ch += warpStride) {
+            // segment owning chunk `ch`: usually the same or the next one
+            if (!(sSegs[cur].chunk0 <= ch &&
+                  (cur + 1 == (int)a.nSegs || ch < sSegs[cur + 1].chunk0))) {
+                int lo = 0;
+                int hi = (int)a.nSegs - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if (sSegs[mid].chunk0 <= ch) {
+                        lo = mid;
+                    } else {
+                        hi = mid - 1;
+                    }
+                }
+                cur = lo;
+            }
+            const GroupSeg sg = sSegs[cur];
+            const uint32_t v0 = (ch - sg.chunk0) * CHUNK;
+            const uint64_t sOff = sg.sendOff + (uint64_t)v0 * 16;
+            const uint64_t rOff = sg.recvOff + (uint64_t)v0 * 16;
+            const uint32_t rem = sg.nVec > v0 ? sg.nVec - v0 : 0;
+            if (rem >= CHUNK) {
+                Vec16 acc[UNROLL];
+                if constexpr (NR > 0) {
+                    Vec16 v[UNROLL][NR];
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+#pragma unroll
+                        for (int p = 0; p < NR; p++) {
+                            v[u][p] = ldVecStream(c.heap[p] + sOff +
+                                                  (uint64_t)(u * 32 + lane) * 16);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        acc[u] = v[u][0];
+#pragma unroll
+                        for (int p = 1; p < NR; p++) {
+                            acc[u] = VR::apply(acc[u], v[u][p]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+#pragma unroll
+                        for (int p = 0; p < NR; p++) {
+                            stVec(c.heap[p] + rOff + (uint64_t)(u * 32 + lane) * 16,
+                                  acc[u]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        acc[u] = ldVecStream(c.heap[0] + sOff +
+                                             (uint64_t)(u * 32 + lane) * 16);
+                    }
+                    for (int p = 1; p < n; p++) {
+                        Vec16 v[UNROLL];
+#pragma unroll
+                        for (int u = 0; u < UNROLL; u++) {
+                            v[u] = ldVecStream(c.heap[p] + sOff +
+                                               (uint64_t)(u * 32 + lane) * 16);
+                        }
+#pragma unroll
+                        for (int u = 0; u < UNROLL; u++) {
+                            acc[u] = VR::apply(acc[u], v[u]);
+                        }
+                    }
+                    for (int p = 0; p < n; p++) {
+#pragma unroll
+                        for (int u = 0; u < UNROLL; u++) {
+                            stVec(c.heap[p] + rOff + (uint64_t)(u * 32 + lane) * 16,
+                                  acc[u]);
+                        }
+                    }
+                }
+            } else {
+                // ragged end of a segment (or a whole tiny tensor)
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const uint32_t i = (uint32_t)u * 32 + lane;
+                    if (i < rem) {
+                        Vec16 acc = ldVecStream(c.heap[0] + sOff + (uint64_t)i * 16);
+                        for (int p = 1; p < n; p++) {
+                            Vec16 v = ldVecStream(c.heap[p] + sOff + (uint64_t)i * 16);
+                            acc = VR::apply(acc, v);
+                        }
+                        for (int p = 0; p < n; p++) {
+                            stVec(c.heap[p] + rOff + (uint64_t)i * 16, acc);
+                        }
+                    }
+                }
+                // the < 16-byte tail rides with the segment's last chunk
+                if (sg.tailBytes != 0 && lane == 0 && v0 + CHUNK > sg.nVec) {
+                    groupTail<VR>(c, sg, n);
+                }
+            }
+        }
+    }
+
+    if (!a.noSync) {
+        bar.sync(c);
+    }
+    bar.store(c);
+}
+
+template<typename VR>
+cudaError_t launchGroup(const GroupArgs& a,
+                        int blocks,
+                        int threads,
+                        cudaStream_t stream)
+{
+    const size_t smem = (size_t)a.nSegs * sizeof(GroupSeg);
+    const int nr = a.comm.nranks;
+    if (nr == 2) {
+        groupAllReduceKernel<VR, 2><<<blocks, threads, smem, stream>>>(a);
+    } else if (nr == 4) {
+        groupAllReduceKernel<VR, 4><<<blocks, threads, smem, stream>>>(a);
+    } else if (nr == 8) {
+        groupAllReduceKernel<VR, 8><<<blocks, threads, smem, stream>>>(a);
+    } else {
+        groupAllReduceKernel<VR, 0><<<blocks, threads, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
 template<typename VR>
 cudaError_t preloadReduce()
 {
@@ -365,6 +565,10 @@ cudaError_t preloadReduce()
     FB_PRELOAD((llAllReduceKernel<VR, 2>))
     FB_PRELOAD((llAllReduceKernel<VR, 4>))
     FB_PRELOAD((llAllReduceKernel<VR, 8>))
+    FB_PRELOAD((groupAllReduceKernel<VR, 0>))
+    FB_PRELOAD((groupAllReduceKernel<VR, 2>))
+    FB_PRELOAD((groupAllReduceKernel<VR, 4>))
+    FB_PRELOAD((groupAllReduceKernel<VR, 8>))
 #undef FB_PRELOAD
     return e;
 }
@@ -374,6 +578,7 @@ const ReduceLaunchers* launchersFor()
 {
     static const ReduceLaunchers l = { &launchReduce<VR>,
                                        &launchLL<VR>,
+                                       &launchGroup<VR>,
                                        &preloadReduce<VR> };
     return &l;
 }

@@ -58,10 +58,53 @@ struct LLArgs
 
 typedef cudaError_t (*LLLaunchFn)(const LLArgs& a, cudaStream_t stream);
 
+// ---- grouped all-reduce: MANY independent all-reduces in ONE launch ----
+// The host cuts the concatenation of all tensors into N equal ownership ranges
+// (one per rank) and hands every rank the list of (tensor ∩ its range)
+// segments.  The kernel pays the two cross-rank barriers once for the whole
+// group: barrier, every warp walks "chunks" of segments (gather from all peers,
+// reduce in registers, push to all peers), barrier.
+struct GroupSeg
+{
+    uint64_t sendOff;   // symmetric offset of this segment's input
+    uint64_t recvOff;   // symmetric offset of this segment's output
+    uint32_t nVec;      // full 16-byte vectors in the segment
+    uint32_t chunk0;    // index of the segment's first chunk in the flat chunk space
+    uint32_t tailBytes; // 1..15: a partial vector follows the nVec full ones
+    uint32_t pad;
+};
+
+struct GroupArgs
+{
+    FbCommDev comm;
+    const GroupSeg* segs; // device memory of THIS rank
+    uint32_t nSegs;
+    uint32_t totalChunks;
+    int32_t noSync;
+    int32_t pad;
+};
+
+// vectors per warp-chunk for a world of n ranks (host and kernel must agree)
+static inline int fbGroupUnroll(int nranks)
+{
+    return (nranks == 8) ? 2 : 4;
+}
+static inline uint32_t fbGroupChunkVecs(int nranks)
+{
+    return 32u * (uint32_t)fbGroupUnroll(nranks);
+}
+#define FB_GROUP_MAX_SEGS 1024
+
+typedef cudaError_t (*GroupLaunchFn)(const GroupArgs& a,
+                                     int blocks,
+                                     int threads,
+                                     cudaStream_t stream);
+
 struct ReduceLaunchers
 {
     ReduceLaunchFn reduce;
     LLLaunchFn ll;
+    GroupLaunchFn group;
     // Forces the CUDA module/function load of every variant (lazy loading may
     // otherwise synchronise the context while a peer rank's kernel is spinning
     // on this one => deadlock until the watchdog fires)
@@ -105,10 +148,13 @@ struct P2PArgs
 {
     FbCommDev comm;
     uint8_t* local;     // user buffer (send source / recv destination)
-    uint64_t bytes;
-    uint64_t mboxOff;   // symmetric offset of the mailbox slot area
-    uint64_t slotBytes; // bytes per eager slot
+    uint64_t bytes;     // send: payload bytes; pull: capacity of `local`
+    uint64_t srcOff;    // send: symmetric offset the receiver will pull from
+    uint64_t heapBytes; // pull: bound for descriptor validation
+    uint32_t seq;       // per ordered pair, starts at 1
     int32_t peer;
+    int32_t stage; // send: copy `local` to heap[rank]+srcOff first (0 = zero copy)
+    int32_t pad;
 };
 
 struct PutArgs
@@ -127,8 +173,18 @@ cudaError_t launchMove(const MoveArgs& a,
                        int threads,
                        cudaStream_t s);
 cudaError_t launchBarrier(const FbCommDev& c, cudaStream_t s);
-cudaError_t launchP2PSend(const P2PArgs& a, int width, cudaStream_t s);
-cudaError_t launchP2PRecv(const P2PArgs& a, int width, cudaStream_t s);
+cudaError_t launchP2PSend(const P2PArgs& a, int width, int blocks, cudaStream_t s);
+cudaError_t launchP2PPull(const P2PArgs& a, int width, int blocks, cudaStream_t s);
+// one-thread spin on a local word (fallback when stream memory ops are missing)
+cudaError_t launchWaitWord(const FbCommDev& c,
+                           const uint32_t* word,
+                           uint32_t target,
+                           cudaStream_t s);
+// writes `value` to sig[p][wordOff + rank] of every peer p
+cudaError_t launchSignalPeers(const FbCommDev& c,
+                              uint32_t wordOff,
+                              uint32_t value,
+                              cudaStream_t s);
 cudaError_t launchPutSignal(const PutArgs& a,
                             int width,
                             int blocks,

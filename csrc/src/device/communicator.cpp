@@ -6,6 +6,8 @@
 #include "launch_api.h"
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <initializer_list>
 #include <barrier>
@@ -68,6 +70,11 @@ CommConfig CommConfig::fromEnv()
     c.nvlsScalarMinBytes = envSize("FAABRIC_NVLS_SCALAR_MIN_BYTES", c.nvlsScalarMinBytes);
     c.tmaMinBytes = envSize("FAABRIC_TMA_MIN_BYTES", c.tmaMinBytes);
     c.nvlsMinBytes = envSize("FAABRIC_NVLS_MIN_BYTES", c.nvlsMinBytes);
+    c.p2pBounceBytes = envSize("FAABRIC_P2P_BOUNCE_BYTES", c.p2pBounceBytes);
+    c.groupBlocks = (int)envSize("FAABRIC_GROUP_BLOCKS", (size_t)c.groupBlocks);
+    if (getenv("FAABRIC_STREAM_SYNC") != nullptr) {
+        c.streamSync = envSize("FAABRIC_STREAM_SYNC", 0) != 0 ? 1 : 0;
+    }
     c.bcast2StepMinBytes =
       envSize("FAABRIC_BCAST_2STEP_MIN_BYTES", c.bcast2StepMinBytes);
     return c;
@@ -92,7 +99,7 @@ const TuningKey TUNING_KEYS[] = {
     FB_TUNING_KEY(nvlsMinBytes, size_t),       FB_TUNING_KEY(nvlsScalarMinBytes, size_t),
     FB_TUNING_KEY(bcast2StepMinBytes, size_t), FB_TUNING_KEY(tmaMinBytes, size_t),
     FB_TUNING_KEY(maxBlocks, int),             FB_TUNING_KEY(threads, int),
-    FB_TUNING_KEY(channels, int),
+    FB_TUNING_KEY(channels, int),              FB_TUNING_KEY(groupBlocks, int),
 };
 #undef FB_TUNING_KEY
 const char* const ALGO_NAMES[FB_ALGO_COUNT] = { "auto", "oneshot", "twoshot", "nvls", "ll", "copy-engine" };
@@ -354,8 +361,11 @@ void Communicator::computeLayout()
     llOff_ = 0;
     mboxOff_ = roundUp(
       llOff_ + (uint64_t)cfg_.channels * FB_LL_AREA_BYTES(n), 4096);
-    stageSendOff_ = roundUp(
-      mboxOff_ + (uint64_t)n * FB_P2P_BLOCKS * 2 * cfg_.slotBytes, 4096);
+    cfg_.p2pBounceBytes =
+      roundUp(std::max<size_t>(cfg_.p2pBounceBytes, 64 << 10), 8192);
+    bounceSlotBytes_ = cfg_.p2pBounceBytes / 2;
+    stageSendOff_ =
+      roundUp(mboxOff_ + (uint64_t)n * cfg_.p2pBounceBytes, 4096);
     stageRecvOff_ = stageSendOff_ + cfg_.stageBytes;
     userOff_ = stageRecvOff_ + cfg_.stageBytes;
     heapTotal_ = userOff_ + roundUp(cfg_.heapBytes, 4096);
@@ -611,6 +621,10 @@ std::vector<std::shared_ptr<Communicator>> Communicator::createLocal(
         c->backingState_ = backing;
         c->backing_ = kind;
         c->localGroup_ = group;
+        if (c->cfg_.streamSync < 0) {
+            c->cfg_.streamSync = allDistinct ? 0 : 1;
+        }
+        c->finishSetup();
     }
     return comms;
 }
@@ -880,6 +894,10 @@ std::shared_ptr<Communicator> Communicator::createIpc(int rank,
     c->dev_.timeoutNs = c->cfg_.timeoutMs * 1000000ull;
     c->backingState_ = backing;
     c->backing_ = kind;
+    if (c->cfg_.streamSync < 0) {
+        c->cfg_.streamSync = 0;
+    }
+    c->finishSetup();
     // nobody may touch a peer's pad before it has been zeroed
     bs.barrier();
     return c;
@@ -1064,9 +1082,10 @@ int Communicator::pickAllReduceAlgo(uint64_t bytes, bool nvlsOk) const
 uint32_t Communicator::checkError(cudaStream_t s)
 {
     cudaSetDevice(device_);
-    if (cudaStreamSynchronize(s) != cudaSuccess) {
-        cudaGetLastError();
-        return 0xffffffffu;
+    // bounded: a stream-level wait whose peer died would block forever
+    if (!syncStreamBounded(s, cfg_.timeoutMs * 3)) {
+        uint32_t e = peekError();
+        return e != FB_ERR_NONE ? e : 0xffffffffu;
     }
     return peekError();
 }
@@ -1111,7 +1130,9 @@ int Communicator::reduceLike(int kind,
     }
     cudaSetDevice(device_);
     const bool symmetric = (flags & FB_FLAG_SYMMETRIC) != 0;
-    const int noSync = (flags & FB_FLAG_NOSYNC) ? 1 : 0;
+    // stream-ordered synchronisation replaces the in-kernel barriers
+    const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
+    const int noSync = ((flags & FB_FLAG_NOSYNC) || ss) ? 1 : 0;
     const bool isRootOrAll = (kind != K_REDUCE) || (rank == root);
 
     // message bytes each rank contributes
@@ -1139,8 +1160,10 @@ int Communicator::reduceLike(int kind,
             algo = pickAllReduceAlgo(
               bytes, hasMulticast() && nvVariant >= 0 && (bytes % 16) == 0 && nvlsWorthIt);
         }
+        // (the LL kernel synchronises through its data slots: no stream mode)
         if (algo == FB_ALGO_LL &&
-            (bytes > FB_LL_MAX_BYTES || (((uintptr_t)send | (uintptr_t)recv) & 15))) {
+            (ss || bytes > FB_LL_MAX_BYTES ||
+             (((uintptr_t)send | (uintptr_t)recv) & 15))) {
             algo = FB_ALGO_ONESHOT;
         }
         if (algo == FB_ALGO_NVLS &&
@@ -1256,6 +1279,9 @@ int Communicator::reduceLike(int kind,
         const uint64_t nVec = len / 16;
         uint64_t per = (nVec + n - 1) / n; // slice size in vectors
         cudaError_t ce = cudaSuccess;
+        if (ss && streamBarrier(flags, s) != FB_OK) {
+            return FB_E_CUDA;
+        }
 
         if (algo == FB_ALGO_NVLS) {
             fb::NvlsArgs a;
@@ -1343,6 +1369,9 @@ int Communicator::reduceLike(int kind,
         if (ce != cudaSuccess) {
             return FB_E_CUDA;
         }
+        if (ss && streamBarrier(flags, s) != FB_OK) {
+            return FB_E_CUDA;
+        }
         stats_.launches++;
         stats_.bytes += len;
         if (stageRecv && isRootOrAll) {
@@ -1426,6 +1455,333 @@ int Communicator::scan(const void* send,
 }
 
 // ---------------------------------------------------------------------------
+// Grouped all-reduce
+// ---------------------------------------------------------------------------
+struct Communicator::GroupPlan
+{
+    struct Launch
+    {
+        fb::GroupSeg* dSegs = nullptr;
+        uint32_t nSegs = 0;
+        uint32_t totalChunks = 0;
+        uint64_t vecsPerRank = 0; // same on every rank: sizes the grid
+        uint64_t bytes = 0;
+    };
+    std::vector<Launch> launches;
+    int dtype = 0;
+    int device = 0;
+    size_t items = 0;
+
+    ~GroupPlan()
+    {
+        cudaSetDevice(device);
+        for (auto& l : launches) {
+            if (l.dSegs != nullptr) {
+                cudaFree(l.dSegs);
+            }
+        }
+        cudaGetLastError();
+    }
+};
+
+struct Communicator::ManySlot
+{
+    fb::GroupSeg* dSegs = nullptr;
+    fb::GroupSeg* hSegs = nullptr;
+    cudaEvent_t ev = nullptr;
+    int device = 0;
+    bool used = false;
+    ~ManySlot()
+    {
+        cudaSetDevice(device);
+        if (dSegs != nullptr) {
+            cudaFree(dSegs);
+        }
+        if (hSegs != nullptr) {
+            cudaFreeHost(hSegs);
+        }
+        if (ev != nullptr) {
+            cudaEventDestroy(ev);
+        }
+        cudaGetLastError();
+    }
+};
+
+size_t Communicator::groupPlanLaunches(const GroupPlan& plan)
+{
+    return plan.launches.size();
+}
+
+namespace {
+struct SegBuild
+{
+    std::vector<fb::GroupSeg> segs;
+    uint32_t totalChunks = 0;
+    uint64_t vecsPerRank = 0;
+    uint64_t bytes = 0;
+};
+}
+
+// This rank's share of items[0..n): the concatenation of all tensors (in
+// 16-byte vectors) is cut into nranks equal ranges; a segment is the
+// intersection of one tensor with this rank's range.
+static int buildGroupSegs(const Communicator& c,
+                          const Communicator::GroupItem* items,
+                          size_t nItems,
+                          size_t esize,
+                          SegBuild& out)
+{
+    const int n = c.size();
+    const int rank = c.rank();
+    const uint32_t chunk = fb::fbGroupChunkVecs(n);
+    uint64_t V = 0;
+    for (size_t i = 0; i < nItems; i++) {
+        const uint64_t bytes = (uint64_t)items[i].count * esize;
+        if (bytes == 0) {
+            continue;
+        }
+        if (!c.inHeap(items[i].send, bytes) || !c.inHeap(items[i].recv, bytes) ||
+            (((uintptr_t)items[i].send | (uintptr_t)items[i].recv) & 15)) {
+            return FB_E_INVALID;
+        }
+        V += (bytes + 15) / 16;
+        out.bytes += bytes;
+    }
+    const uint64_t lo = V * (uint64_t)rank / n;
+    const uint64_t hi = V * (uint64_t)(rank + 1) / n;
+    out.vecsPerRank = (V + n - 1) / n;
+    uint64_t flat = 0;
+    uint64_t chunks = 0;
+    for (size_t i = 0; i < nItems; i++) {
+        const uint64_t bytes = (uint64_t)items[i].count * esize;
+        if (bytes == 0) {
+            continue;
+        }
+        const uint64_t vecs = (bytes + 15) / 16;
+        const uint64_t full = bytes / 16;
+        const uint32_t tail = (uint32_t)(bytes % 16);
+        const uint64_t a = std::max(flat, lo);
+        const uint64_t b = std::min(flat + vecs, hi);
+        if (a < b) {
+            const uint64_t v0 = a - flat;
+            const uint64_t v1 = b - flat;
+            fb::GroupSeg sg;
+            memset(&sg, 0, sizeof(sg));
+            sg.nVec = (uint32_t)(std::min(v1, full) > v0 ? std::min(v1, full) - v0 : 0);
+            sg.tailBytes = (tail != 0 && v1 == vecs) ? tail : 0;
+            if (sg.nVec != 0 || sg.tailBytes != 0) {
+                sg.sendOff = c.offsetOf(items[i].send) + v0 * 16;
+                sg.recvOff = c.offsetOf(items[i].recv) + v0 * 16;
+                sg.chunk0 = (uint32_t)chunks;
+                chunks += ((uint64_t)sg.nVec + (sg.tailBytes ? 1 : 0) + chunk - 1) / chunk;
+                out.segs.push_back(sg);
+            }
+        }
+        flat += vecs;
+    }
+    if (chunks > 0xffffffffull) {
+        return FB_E_TOO_LARGE;
+    }
+    out.totalChunks = (uint32_t)chunks;
+    return FB_OK;
+}
+
+// items per launch: every item yields at most one segment per rank
+static const size_t GROUP_ITEMS_PER_LAUNCH = FB_GROUP_MAX_SEGS - 8;
+
+std::shared_ptr<Communicator::GroupPlan> Communicator::prepareGroup(
+  const GroupItem* items,
+  size_t nItems,
+  int dtype,
+  int* rcOut)
+{
+    int rcLocal = FB_OK;
+    int& rc = rcOut ? *rcOut : rcLocal;
+    rc = FB_OK;
+    const size_t esize = fbDtypeSize(dtype);
+    if (esize == 0) {
+        rc = FB_E_INVALID;
+        return nullptr;
+    }
+    cudaSetDevice(device_);
+    auto plan = std::make_shared<GroupPlan>();
+    plan->dtype = dtype;
+    plan->device = device_;
+    plan->items = nItems;
+    for (size_t begin = 0; begin < nItems; begin += GROUP_ITEMS_PER_LAUNCH) {
+        const size_t cnt = std::min(GROUP_ITEMS_PER_LAUNCH, nItems - begin);
+        SegBuild sb;
+        rc = buildGroupSegs(*this, items + begin, cnt, esize, sb);
+        if (rc != FB_OK) {
+            return nullptr;
+        }
+        GroupPlan::Launch l;
+        l.nSegs = (uint32_t)sb.segs.size();
+        l.totalChunks = sb.totalChunks;
+        l.vecsPerRank = sb.vecsPerRank;
+        l.bytes = sb.bytes;
+        // (a rank may own nothing of a tiny group: it still takes part in the
+        // barriers, with an empty table)
+        const size_t tb = std::max<size_t>(sb.segs.size(), 1) * sizeof(fb::GroupSeg);
+        if (cudaMalloc((void**)&l.dSegs, tb) != cudaSuccess) {
+            cudaGetLastError();
+            rc = FB_E_CUDA;
+            return nullptr;
+        }
+        plan->launches.push_back(l);
+        if (!sb.segs.empty() &&
+            cudaMemcpy(l.dSegs, sb.segs.data(), sb.segs.size() * sizeof(fb::GroupSeg), cudaMemcpyHostToDevice) !=
+              cudaSuccess) {
+            cudaGetLastError();
+            rc = FB_E_CUDA;
+            return nullptr;
+        }
+    }
+    return plan;
+}
+
+static int groupGrid(const CommConfig& cfg, int nranks, uint64_t vecsPerRank)
+{
+    // Derived ONLY from quantities that are identical on every rank: CTA b of
+    // one rank meets CTA b of every peer at the barriers
+    const int slots = FB_MAX_BLOCKS / cfg.channels;
+    const int cap = std::min(slots, cfg.groupBlocks > 0 ? cfg.groupBlocks : 128);
+    const uint64_t warps = (uint64_t)cfg.threads / 32;
+    const uint64_t chunks = (vecsPerRank + fb::fbGroupChunkVecs(nranks) - 1) / fb::fbGroupChunkVecs(nranks);
+    const uint64_t want = (chunks + warps * 2 - 1) / (warps * 2); // >= 2 chunks per warp
+    return (int)std::clamp<uint64_t>(want, 1, (uint64_t)cap);
+}
+
+int Communicator::allReduceGroup(const GroupPlan& plan, int op, int flags, cudaStream_t s)
+{
+    NvtxRange nvtxRange("fb::allReduceGroup");
+    const fb::ReduceLaunchers* L = fb::findReduceLaunchers(plan.dtype, op);
+    if (L == nullptr || L->group == nullptr) {
+        return FB_E_UNSUPPORTED;
+    }
+    cudaSetDevice(device_);
+    const int n = dev_.nranks;
+    const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
+    for (const auto& l : plan.launches) {
+        fb::GroupArgs a;
+        memset(&a, 0, sizeof(a));
+        a.comm = devFor(flags);
+        a.segs = l.dSegs;
+        a.nSegs = l.nSegs;
+        a.totalChunks = l.totalChunks;
+        a.noSync = ((flags & FB_FLAG_NOSYNC) || ss) ? 1 : 0;
+        if (ss && streamBarrier(flags, s) != FB_OK) {
+            return FB_E_CUDA;
+        }
+        if (L->group(a, groupGrid(cfg_, n, l.vecsPerRank), cfg_.threads, s) != cudaSuccess) {
+            return FB_E_CUDA;
+        }
+        if (ss && streamBarrier(flags, s) != FB_OK) {
+            return FB_E_CUDA;
+        }
+        stats_.launches++;
+        stats_.bytes += l.bytes;
+        stats_.algoCount[FB_ALGO_TWOSHOT]++;
+    }
+    lastAlgo_ = FB_ALGO_TWOSHOT;
+    return FB_OK;
+}
+
+int Communicator::allReduceMany(const GroupItem* items,
+                                size_t nItems,
+                                int dtype,
+                                int op,
+                                int flags,
+                                cudaStream_t s)
+{
+    NvtxRange nvtxRange("fb::allReduceMany");
+    const size_t esize = fbDtypeSize(dtype);
+    const fb::ReduceLaunchers* L = fb::findReduceLaunchers(dtype, op);
+    if (esize == 0) {
+        return FB_E_INVALID;
+    }
+    if (L == nullptr) {
+        return FB_E_UNSUPPORTED;
+    }
+    cudaSetDevice(device_);
+    const int n = dev_.nranks;
+    const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
+    // try the grouped path batch by batch; anything not symmetric / aligned
+    // goes through the per-tensor calls (the choice depends only on arguments
+    // that are symmetric across ranks)
+    for (size_t begin = 0; begin < nItems; begin += GROUP_ITEMS_PER_LAUNCH) {
+        const size_t cnt = std::min(GROUP_ITEMS_PER_LAUNCH, nItems - begin);
+        SegBuild sb;
+        int rc = (L->group != nullptr) ? buildGroupSegs(*this, items + begin, cnt, esize, sb)
+                                       : FB_E_UNSUPPORTED;
+        if (rc != FB_OK) {
+            for (size_t i = begin; i < begin + cnt; i++) {
+                int f = flags;
+                if (!inHeap(items[i].send, items[i].count * esize)) {
+                    f &= ~FB_FLAG_SYMMETRIC;
+                }
+                int r2 = allReduce(items[i].send, items[i].recv, items[i].count, dtype, op, FB_ALGO_AUTO, f, s);
+                if (r2 != FB_OK) {
+                    return r2;
+                }
+            }
+            continue;
+        }
+        // table slot: pinned staging + device copy, recycled after its launch
+        if (manySlots_.empty()) {
+            manySlots_.resize(8);
+        }
+        auto& slotPtr = manySlots_[manyNext_++ % manySlots_.size()];
+        if (!slotPtr) {
+            slotPtr = std::make_shared<ManySlot>();
+            slotPtr->device = device_;
+            if (cudaMalloc((void**)&slotPtr->dSegs, FB_GROUP_MAX_SEGS * sizeof(fb::GroupSeg)) != cudaSuccess ||
+                cudaHostAlloc((void**)&slotPtr->hSegs, FB_GROUP_MAX_SEGS * sizeof(fb::GroupSeg), cudaHostAllocDefault) !=
+                  cudaSuccess ||
+                cudaEventCreateWithFlags(&slotPtr->ev, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                slotPtr.reset();
+                return FB_E_CUDA;
+            }
+        }
+        ManySlot& slot = *slotPtr;
+        if (slot.used) {
+            cudaEventSynchronize(slot.ev);
+        }
+        if (!sb.segs.empty()) {
+            memcpy(slot.hSegs, sb.segs.data(), sb.segs.size() * sizeof(fb::GroupSeg));
+            if (cudaMemcpyAsync(slot.dSegs, slot.hSegs, sb.segs.size() * sizeof(fb::GroupSeg), cudaMemcpyHostToDevice, s) !=
+                cudaSuccess) {
+                return FB_E_CUDA;
+            }
+        }
+        fb::GroupArgs a;
+        memset(&a, 0, sizeof(a));
+        a.comm = devFor(flags);
+        a.segs = slot.dSegs;
+        a.nSegs = (uint32_t)sb.segs.size();
+        a.totalChunks = sb.totalChunks;
+        a.noSync = ((flags & FB_FLAG_NOSYNC) || ss) ? 1 : 0;
+        if (ss && streamBarrier(flags, s) != FB_OK) {
+            return FB_E_CUDA;
+        }
+        if (L->group(a, groupGrid(cfg_, n, sb.vecsPerRank), cfg_.threads, s) != cudaSuccess) {
+            return FB_E_CUDA;
+        }
+        if (ss && streamBarrier(flags, s) != FB_OK) {
+            return FB_E_CUDA;
+        }
+        cudaEventRecord(slot.ev, s);
+        slot.used = true;
+        stats_.launches++;
+        stats_.bytes += sb.bytes;
+        stats_.algoCount[FB_ALGO_TWOSHOT]++;
+    }
+    lastAlgo_ = FB_ALGO_TWOSHOT;
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Data movement
 // ---------------------------------------------------------------------------
 int Communicator::moveLike(int mode,
@@ -1440,7 +1796,8 @@ int Communicator::moveLike(int mode,
     const int rank = dev_.rank;
     cudaSetDevice(device_);
     const bool symmetric = (flags & FB_FLAG_SYMMETRIC) != 0;
-    const int noSync = (flags & FB_FLAG_NOSYNC) ? 1 : 0;
+    const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
+    const int noSync = ((flags & FB_FLAG_NOSYNC) || ss) ? 1 : 0;
     if (chunkBytes == 0) {
         return barrier(s);
     }
@@ -1486,14 +1843,19 @@ int Communicator::moveLike(int mode,
         stats_.algoCount[FB_ALGO_NVLS]++;
         stats_.launches++;
         stats_.bytes += chunkBytes;
-        return fb::launchNvls(a, -1, blocksFor(nVec, 4), cfg_.threads, s) ==
-                   cudaSuccess
-                 ? FB_OK
-                 : FB_E_CUDA;
+        if (ss && streamBarrier(flags, s) != FB_OK) {
+            return FB_E_CUDA;
+        }
+        if (fb::launchNvls(a, -1, blocksFor(nVec, 4), cfg_.threads, s) !=
+            cudaSuccess) {
+            return FB_E_CUDA;
+        }
+        return ss ? streamBarrier(flags, s) : FB_OK;
     }
 
     // ---- large symmetric broadcast: scatter + allgather in one kernel ----
-    if (mode == fb::MOVE_BCAST && symmetric &&
+    // (it has a barrier between its two steps: not available in stream mode)
+    if (mode == fb::MOVE_BCAST && symmetric && !ss &&
         chunkBytes >= cfg_.bcast2StepMinBytes && (chunkBytes % 16) == 0) {
         fb::MoveArgs a;
         memset(&a, 0, sizeof(a));
@@ -1581,6 +1943,9 @@ int Communicator::moveLike(int mode,
                                alignWidth(a.srcStride) });
         uint64_t words = len / width;
         cudaError_t ce;
+        if (ss && streamBarrier(flags, s) != FB_OK) {
+            return FB_E_CUDA;
+        }
         if (width == 16 && cfg_.tmaMinBytes > 0 && len >= cfg_.tmaMinBytes &&
             fb::moveBulkSupported(a)) {
             // Large chunks: the copy engine streams 32 KiB tiles through
@@ -1596,6 +1961,9 @@ int Communicator::moveLike(int mode,
             ce = fb::launchMove(a, width, blocksFor(words, 2), cfg_.threads, s);
         }
         if (ce != cudaSuccess) {
+            return FB_E_CUDA;
+        }
+        if (ss && streamBarrier(flags, s) != FB_OK) {
             return FB_E_CUDA;
         }
         stats_.launches++;
@@ -1684,51 +2052,274 @@ int Communicator::barrier(cudaStream_t s)
         return FB_OK;
     }
     stats_.launches++;
+    if (streamSync_) {
+        return streamBarrier(0, s);
+    }
     return fb::launchBarrier(dev_, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------
+// Set-up tail shared by both wiring modes
+// ---------------------------------------------------------------------------
+void Communicator::finishSetup()
+{
+    streamSync_ = cfg_.streamSync > 0;
+    streamWaitOk_ = false;
+    const DriverApi& api = getDriverApi();
+    const char* off = getenv("FAABRIC_STREAM_MEMOPS");
+    if (api.cuStreamWaitValue32 != nullptr && !(off != nullptr && off[0] == '0')) {
+        // self-test: a wait that is already satisfied on a word of our own pad
+        cudaSetDevice(device_);
+        cudaStream_t t = nullptr;
+        if (cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking) == cudaSuccess) {
+            CUresult r = api.cuStreamWaitValue32(
+              (CUstream)t,
+              (CUdeviceptr)(uintptr_t)(dev_.sig[dev_.rank] + FB_SIG_SBAR_OFF),
+              0,
+              CU_STREAM_WAIT_VALUE_GEQ);
+            if (r == CUDA_SUCCESS && cudaStreamSynchronize(t) == cudaSuccess) {
+                streamWaitOk_ = true;
+            } else {
+                cudaGetLastError();
+            }
+            cudaStreamDestroy(t);
+        }
+    }
+}
+
+int Communicator::streamWaitGe(cudaStream_t s,
+                               const uint32_t* localWord,
+                               uint32_t value)
+{
+    if (streamWaitOk_) {
+        CUresult r = getDriverApi().cuStreamWaitValue32(
+          (CUstream)s,
+          (CUdeviceptr)(uintptr_t)localWord,
+          value,
+          CU_STREAM_WAIT_VALUE_GEQ);
+        if (r == CUDA_SUCCESS) {
+            return FB_OK;
+        }
+        // e.g. not permitted in this capture mode: use the spin kernel
+    }
+    return fb::launchWaitWord(dev_, localWord, value, s) == cudaSuccess
+             ? FB_OK
+             : FB_E_CUDA;
+}
+
+// Stream-ordered barrier of one channel: every rank signals every peer from a
+// (non-spinning) kernel and then waits for all of them at stream level.
+int Communicator::streamBarrier(int flags, cudaStream_t s)
+{
+    const int n = dev_.nranks;
+    if (n == 1) {
+        return FB_OK;
+    }
+    int ch = FB_FLAG_GET_CHANNEL(flags) % cfg_.channels;
+    const uint32_t e = ++sbarEpoch_[ch];
+    const uint32_t wordOff = FB_SIG_SBAR_OFF + (uint32_t)ch * FB_MAX_RANKS;
+    if (fb::launchSignalPeers(dev_, wordOff, e, s) != cudaSuccess) {
+        return FB_E_CUDA;
+    }
+    for (int p = 0; p < n; p++) {
+        if (p == dev_.rank) {
+            continue;
+        }
+        int rc = streamWaitGe(s, dev_.sig[dev_.rank] + wordOff + p, e);
+        if (rc != FB_OK) {
+            return rc;
+        }
+    }
+    return FB_OK;
+}
+
+bool Communicator::syncStreamBounded(cudaStream_t s, uint64_t timeoutMs)
+{
+    cudaSetDevice(device_);
+    const auto t0 = std::chrono::steady_clock::now();
+    uint32_t spins = 0;
+    while (true) {
+        cudaError_t e = cudaStreamQuery(s);
+        if (e == cudaSuccess) {
+            return true;
+        }
+        if (e != cudaErrorNotReady) {
+            cudaGetLastError();
+            return false;
+        }
+        if (++spins > 2000) {
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+            auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(
+                        std::chrono::steady_clock::now() - t0)
+                        .count();
+            if ((uint64_t)ms > timeoutMs) {
+                abortPendingWaits();
+                cudaStreamSynchronize(s);
+                return false;
+            }
+        }
+    }
+}
+
+// A peer never arrived: flag the error and satisfy every stream-level wait
+// this rank may have queued so the stream drains instead of hanging forever
+// (stream memory operations have no timeout of their own).
+void Communicator::abortPendingWaits()
+{
+    *reinterpret_cast<volatile uint32_t*>(dev_.err) = FB_ERR_HOST_ABORT;
+    cudaStream_t t = nullptr;
+    if (cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    uint32_t* pad = dev_.sig[dev_.rank];
+    cudaMemcpyAsync(pad + FB_P2P_READY_OFF, recvSeq_, sizeof(recvSeq_), cudaMemcpyHostToDevice, t);
+    cudaMemcpyAsync(pad + FB_P2P_ACK_OFF, sendSeq_, sizeof(sendSeq_), cudaMemcpyHostToDevice, t);
+    std::vector<uint32_t> sb(FB_SIG_SBAR_WORDS);
+    for (int ch = 0; ch < FB_MAX_CHANNELS; ch++) {
+        for (int p = 0; p < FB_MAX_RANKS; p++) {
+            sb[ch * FB_MAX_RANKS + p] = sbarEpoch_[ch];
+        }
+    }
+    cudaMemcpyAsync(pad + FB_SIG_SBAR_OFF, sb.data(), sb.size() * 4, cudaMemcpyHostToDevice, t);
+    cudaMemcpyAsync(pad + FB_SIG_USER_OFF, userSigConsumed_, sizeof(userSigConsumed_), cudaMemcpyHostToDevice, t);
+    cudaStreamSynchronize(t);
+    cudaStreamDestroy(t);
+    cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
 // Point to point
 // ---------------------------------------------------------------------------
-int Communicator::send(const void* buf, size_t bytes, int peer, cudaStream_t s)
+static int p2pBlocks(size_t len)
 {
-    NvtxRange nvtxRange("fb::send");
-    if (peer < 0 || peer >= dev_.nranks || peer == dev_.rank) {
-        return FB_E_INVALID;
+    return (int)std::clamp<size_t>(len / (64 << 10), 1, 32);
+}
+
+int Communicator::sendChunk(const uint8_t* buf, size_t len, int peer, cudaStream_t s)
+{
+    const uint32_t seq = ++sendSeq_[peer];
+    if (seq > 2) {
+        // the bounce slot (and descriptor ring entry) of message seq-2 must
+        // have been drained by the receiver
+        int rc = streamWaitGe(s, dev_.sig[dev_.rank] + FB_P2P_ACK_OFF + peer, seq - 2);
+        if (rc != FB_OK) {
+            return rc;
+        }
     }
-    cudaSetDevice(device_);
     fb::P2PArgs a;
     memset(&a, 0, sizeof(a));
     a.comm = dev_;
-    a.local = (uint8_t*)buf;
-    a.bytes = bytes;
-    a.mboxOff = mboxOff_;
-    a.slotBytes = cfg_.slotBytes;
+    a.local = const_cast<uint8_t*>(buf);
+    a.bytes = len;
+    a.srcOff = mboxOff_ + ((uint64_t)peer * 2 + (seq & 1)) * bounceSlotBytes_;
+    a.seq = seq;
+    a.peer = peer;
+    a.stage = 1;
+    stats_.launches++;
+    stats_.bytes += len;
+    int w = alignWidth((uint64_t)(uintptr_t)buf);
+    return fb::launchP2PSend(a, w, p2pBlocks(len), s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+}
+
+int Communicator::recvChunk(uint8_t* buf, size_t len, int peer, cudaStream_t s)
+{
+    const uint32_t seq = ++recvSeq_[peer];
+    int rc = streamWaitGe(s, dev_.sig[dev_.rank] + FB_P2P_READY_OFF + peer, seq);
+    if (rc != FB_OK) {
+        return rc;
+    }
+    fb::P2PArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = dev_;
+    a.local = buf;
+    a.bytes = len;
+    a.heapBytes = heapTotal_;
+    a.seq = seq;
     a.peer = peer;
     stats_.launches++;
-    stats_.bytes += bytes;
     int w = alignWidth((uint64_t)(uintptr_t)buf);
-    return fb::launchP2PSend(a, w, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+    return fb::launchP2PPull(a, w, p2pBlocks(len), s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+}
+
+int Communicator::send(const void* buf, size_t bytes, int peer, cudaStream_t s)
+{
+    NvtxRange nvtxRange("fb::send");
+    if (peer < 0 || peer >= dev_.nranks) {
+        return FB_E_INVALID;
+    }
+    cudaSetDevice(device_);
+    // zero-byte messages still synchronise (one empty chunk), like the
+    // reference's empty MPI messages
+    size_t off = 0;
+    do {
+        size_t len = std::min<size_t>(bounceSlotBytes_, bytes - off);
+        int rc = sendChunk((const uint8_t*)buf + off, len, peer, s);
+        if (rc != FB_OK) {
+            return rc;
+        }
+        off += len;
+    } while (off < bytes);
+    return FB_OK;
 }
 
 int Communicator::recv(void* buf, size_t bytes, int peer, cudaStream_t s)
 {
     NvtxRange nvtxRange("fb::recv");
-    if (peer < 0 || peer >= dev_.nranks || peer == dev_.rank) {
+    if (peer < 0 || peer >= dev_.nranks) {
         return FB_E_INVALID;
     }
     cudaSetDevice(device_);
-    fb::P2PArgs a;
-    memset(&a, 0, sizeof(a));
-    a.comm = dev_;
-    a.local = (uint8_t*)buf;
-    a.bytes = bytes;
-    a.mboxOff = mboxOff_;
-    a.slotBytes = cfg_.slotBytes;
-    a.peer = peer;
-    stats_.launches++;
-    int w = alignWidth((uint64_t)(uintptr_t)buf);
-    return fb::launchP2PRecv(a, w, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
+    size_t off = 0;
+    do {
+        size_t len = std::min<size_t>(bounceSlotBytes_, bytes - off);
+        int rc = recvChunk((uint8_t*)buf + off, len, peer, s);
+        if (rc != FB_OK) {
+            return rc;
+        }
+        off += len;
+    } while (off < bytes);
+    return FB_OK;
+}
+
+int Communicator::sendRecv(const void* sendBuf,
+                           size_t sendBytes,
+                           int dst,
+                           void* recvBuf,
+                           size_t recvBytes,
+                           int src,
+                           cudaStream_t s)
+{
+    NvtxRange nvtxRange("fb::sendRecv");
+    if (dst < 0 || dst >= dev_.nranks || src < 0 || src >= dev_.nranks) {
+        return FB_E_INVALID;
+    }
+    cudaSetDevice(device_);
+    size_t so = 0;
+    size_t ro = 0;
+    bool sendDone = false;
+    bool recvDone = false;
+    while (!sendDone || !recvDone) {
+        if (!sendDone) {
+            size_t len = std::min<size_t>(bounceSlotBytes_, sendBytes - so);
+            int rc = sendChunk((const uint8_t*)sendBuf + so, len, dst, s);
+            if (rc != FB_OK) {
+                return rc;
+            }
+            so += len;
+            sendDone = so >= sendBytes;
+        }
+        if (!recvDone) {
+            size_t len = std::min<size_t>(bounceSlotBytes_, recvBytes - ro);
+            int rc = recvChunk((uint8_t*)recvBuf + ro, len, src, s);
+            if (rc != FB_OK) {
+                return rc;
+            }
+            ro += len;
+            recvDone = ro >= recvBytes;
+        }
+    }
+    return FB_OK;
 }
 
 int Communicator::putSignal(const void* local,
@@ -1766,6 +2357,11 @@ int Communicator::waitSignal(int signalIdx, uint32_t count, cudaStream_t s)
         return FB_E_INVALID;
     }
     cudaSetDevice(device_);
+    if (streamSync_) {
+        userSigConsumed_[signalIdx] += count;
+        return streamWaitGe(
+          s, dev_.sig[dev_.rank] + FB_SIG_USER_OFF + signalIdx, userSigConsumed_[signalIdx]);
+    }
     stats_.launches++;
     return fb::launchWaitSignal(dev_, signalIdx, count, s) == cudaSuccess
              ? FB_OK

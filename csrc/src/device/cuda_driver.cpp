@@ -58,6 +58,8 @@ static DriverApi loadApi()
     FB_RESOLVE(cuMulticastAddDevice);
     FB_RESOLVE(cuMulticastBindMem);
     FB_RESOLVE(cuMulticastGetGranularity);
+    FB_RESOLVE(cuStreamWaitValue32);
+    FB_RESOLVE(cuStreamWriteValue32);
 #undef FB_RESOLVE
     api.loaded = core;
     return api;

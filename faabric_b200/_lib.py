@@ -31,6 +31,9 @@ class FbConfig(C.Structure):
         ("oneShotMaxBytes", C.c_uint64),
         ("nvlsMinBytes", C.c_uint64),
         ("bcast2StepMinBytes", C.c_uint64),
+        ("p2pBounceBytes", C.c_uint64),
+        ("groupBlocks", C.c_int32),
+        ("streamSync", C.c_int32),
     ]
 
 
@@ -108,6 +111,17 @@ def load():
     _sig(lib, "fb_barrier", i32, [vp, vp])
     _sig(lib, "fb_send", i32, [vp, vp, u64, i32, vp])
     _sig(lib, "fb_recv", i32, [vp, vp, u64, i32, vp])
+    _sig(lib, "fb_sendrecv", i32, [vp, vp, u64, i32, vp, u64, i32, vp])
+    _sig(lib, "fb_comm_stream_sync", i32, [vp])
+    _sig(lib, "fb_comm_stream_wait_supported", i32, [vp])
+    _sig(lib, "fb_comm_sync_bounded", i32, [vp, vp, u64])
+    vpp = C.POINTER(C.c_void_p)
+    u64p = C.POINTER(C.c_uint64)
+    _sig(lib, "fb_group_prepare", vp, [vp, i32, vpp, vpp, u64p, i32])
+    _sig(lib, "fb_group_allreduce", i32, [vp, vp, i32, i32, vp])
+    _sig(lib, "fb_group_plan_launches", i32, [vp])
+    _sig(lib, "fb_group_plan_free", None, [vp])
+    _sig(lib, "fb_allreduce_many", i32, [vp, i32, vpp, vpp, u64p, i32, i32, i32, vp])
     _sig(lib, "fb_put_signal", i32, [vp, vp, u64, u64, i32, i32, i32, vp])
     _sig(lib, "fb_wait_signal", i32, [vp, i32, u32, vp])
 

@@ -1,10 +1,15 @@
 """Data-parallel gradient synchronisation — the flagship workload.
 
 ``GradientSync`` owns one flat symmetric-heap buffer holding every gradient
-tensor of the model and all-reduces them **one MPI_Allreduce-shaped call per
-tensor** (the reference benchmark's semantics), each call being a single fused
-peer-memory kernel.  The per-step launch sequence is captured once into a CUDA
-graph and replayed, so a step costs one graph launch on the host.
+tensor of the model and all-reduces them with the semantics of **one
+MPI_Allreduce per tensor** (the reference benchmark issues 214 of them per
+pass).  Two execution modes:
+
+* ``mode="grouped"`` (default): ONE fused peer-memory kernel per step walks a
+  device-resident table of all tensors (``Communicator.prepare_group``): the
+  cross-rank barriers are paid once per step instead of once per tensor.
+* ``mode="lanes"``: one kernel per tensor, spread over `channels` concurrent
+  lanes and replayed from a CUDA graph (the round-1 design, kept for comparison).
 
 Public API used by bench.py / users:
 
@@ -58,15 +63,19 @@ class GradientSync:
         algo: str = "auto",
         use_graph: bool = True,
         in_place: bool = False,
-        channels: int = 4,
+        channels: int = 8,
         bucket_bytes: int = 0,
+        mode: str = "grouped",
     ):
         self.comm = comm
         self.sizes = [int(s) for s in sizes]
         self.dtype = dtype
         self.op = op
         self.algo = algo
-        self.use_graph = use_graph
+        # stream-ordered synchronisation (ranks sharing a GPU) is driven from
+        # the host and cannot be replayed from a graph
+        self.use_graph = use_graph and not comm.stream_sync
+        self.mode = mode
         esize = torch.empty((), dtype=dtype).element_size()
         # every tensor starts on a 256-byte boundary inside the flat buffers
         self.offsets = []
@@ -113,6 +122,11 @@ class GradientSync:
         else:
             self._jobs = [(s, r, n) for s, r, n in zip(self.send_views, self.recv_views, self.sizes)]
         self.launches_per_step = len(self._jobs)
+        self._plan = None
+        if self.mode == "grouped":
+            self._plan = comm.prepare_group([j[0] for j in self._jobs], [j[1] for j in self._jobs])
+            self.launches_per_step = self._plan.launches
+        self._e2e = None
         # algo="tuned": measure the candidate policies in place (same lanes,
         # same CTA budget, same tensor mix) on first use and keep the fastest
         self.policy = None
@@ -223,6 +237,9 @@ class GradientSync:
     def step(self, stream: Optional[torch.cuda.Stream] = None):
         """All-reduce every gradient tensor (async on `stream`)."""
         stream = stream or torch.cuda.current_stream(self.comm.device)
+        if self._plan is not None:
+            self.comm.all_reduce_group(self._plan, op=self.op, stream=stream)
+            return
         if self.use_graph:
             if self._graph is None:
                 if self.algo == "tuned" and self.policy is None:
@@ -261,15 +278,18 @@ class GradientSync:
         self,
         host_grads: torch.Tensor,
         stream: Optional[torch.cuda.Stream] = None,
-        pipeline: int = 4,
+        pipeline: int = 8,
+        out_host: Optional[torch.Tensor] = None,
     ):
         """End-to-end step: copy this step's gradients from pinned host memory,
-        all-reduce, and read a result digest (first element + checksum of the
-        first tensor) back to the host.  The H2D copy is cut into `pipeline`
+        all-reduce, and copy the reduced gradients back to pinned host memory
+        (``out_host``, grouped mode: the FULL result; lanes mode: a digest).  The H2D copy is cut into `pipeline`
         chunks on a copy stream; the all-reduces of a chunk start as soon as it
         has landed, overlapping the rest of the transfer.  Returns the host
         digest tensor after synchronising the stream."""
         stream = stream or torch.cuda.current_stream(self.comm.device)
+        if self._plan is not None:
+            return self._step_from_host_grouped(host_grads, out_host, stream, pipeline)
         if self.algo == "tuned" and self.policy is None and self.use_graph:
             self._tune()
         if pipeline <= 1 or not self.use_graph:
@@ -312,15 +332,66 @@ class GradientSync:
         stream.synchronize()
         return self._result_host
 
+    def _step_from_host_grouped(self, host_grads, out_host, stream, pipeline):
+        """H2D -> grouped all-reduce -> D2H, cut into `pipeline` chunks of
+        whole tensors on three streams so the PCIe copies of both directions
+        overlap each other and the all-reduces of the neighbouring chunks."""
+        dev = self.comm.device
+        if self._e2e is None or self._e2e["k"] != pipeline:
+            chunks = self._pipeline_chunks(max(1, pipeline))
+            plans = [self.comm.prepare_group([j[0] for j in jobs], [j[1] for j in jobs]) for _, _, jobs in chunks]
+            self._e2e = {
+                "k": pipeline,
+                "chunks": chunks,
+                "plans": plans,
+                "h2d": torch.cuda.Stream(device=dev),
+                "d2h": torch.cuda.Stream(device=dev),
+                "in_ev": [torch.cuda.Event() for _ in chunks],
+                "red_ev": [torch.cuda.Event() for _ in chunks],
+            }
+        e = self._e2e
+        if out_host is None:
+            if e.get("out") is None:
+                e["out"] = torch.empty(self.total_padded, dtype=self.dtype).pin_memory()
+            out_host = e["out"]
+        e["h2d"].wait_stream(stream)
+        e["d2h"].wait_stream(stream)
+        limit = host_grads.numel()
+        with torch.cuda.stream(e["h2d"]):
+            for (a, b, _), ev in zip(e["chunks"], e["in_ev"]):
+                hi = min(b, limit)
+                if hi > a:
+                    self.send[a:hi].copy_(host_grads[a:hi], non_blocking=True)
+                ev.record(e["h2d"])
+        for (a, b, _), plan, iev, rev in zip(e["chunks"], e["plans"], e["in_ev"], e["red_ev"]):
+            stream.wait_event(iev)
+            self.comm.all_reduce_group(plan, op=self.op, stream=stream)
+            rev.record(stream)
+            with torch.cuda.stream(e["d2h"]):
+                e["d2h"].wait_event(rev)
+                out_host[a:b].copy_(self.recv[a:b], non_blocking=True)
+        stream.wait_stream(e["d2h"])
+        stream.synchronize()
+        return out_host
+
     @property
     def h2d_bytes_per_step(self):
         return self.total_padded * self.send.element_size()
 
     @property
     def d2h_bytes_per_step(self):
+        if self._plan is not None:
+            return self.total_padded * self.send.element_size()
         return self._result_host.numel() * 8
 
     def close(self):
+        if self._e2e is not None:
+            for p in self._e2e["plans"]:
+                p.close()
+            self._e2e = None
+        if self._plan is not None:
+            self._plan.close()
+            self._plan = None
         self._graph = None
         self._chunk_graphs = []
         if self.recv is not self.send:

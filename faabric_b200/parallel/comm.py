@@ -99,6 +99,10 @@ class Communicator:
         self.device = self._lib.fb_comm_device(self._h)
         self.backing = self._lib.fb_comm_backing(self._h).decode()
         self.has_multicast = bool(self._lib.fb_comm_has_multicast(self._h))
+        # cross-rank synchronisation through stream memory operations instead
+        # of in-kernel spins (ranks sharing a GPU): not CUDA-graph capturable
+        self.stream_sync = bool(self._lib.fb_comm_stream_sync(self._h))
+        self.stream_wait_supported = bool(self._lib.fb_comm_stream_wait_supported(self._h))
         self._allocs: dict[int, int] = {}
 
     # ------------------------------------------------------------ lifecycle
@@ -199,6 +203,7 @@ class Communicator:
             "threads": 5,
             "tmaMinBytes": 6,
             "nvlsScalarMinBytes": 7,
+            "groupBlocks": 8,
         }
         for k, v in kw.items():
             self._check(self._lib.fb_comm_configure(self._h, keys[k], int(v)), k)
@@ -365,6 +370,61 @@ class Communicator:
         self._check(rc, "all_to_all")
         return recv
 
+    # ------------------------------------------------- grouped all-reduce
+    def _group_arrays(self, sends, recvs):
+        n = len(sends)
+        sp = (C.c_void_p * n)(*[t.data_ptr() for t in sends])
+        rp = (C.c_void_p * n)(*[t.data_ptr() for t in recvs])
+        cnt = (C.c_uint64 * n)(*[t.numel() for t in sends])
+        return n, sp, rp, cnt
+
+    def prepare_group(self, sends, recvs=None) -> "GroupPlan":
+        """Plan ONE launch that all-reduces every tensor of ``sends`` (each with
+        per-tensor semantics).  Tensors must live in the symmetric heap at
+        16-byte aligned addresses; call collectively with the same list."""
+        recvs = sends if recvs is None else recvs
+        if len(sends) != len(recvs) or not sends:
+            raise CommError("prepare_group: need equally long, non-empty lists")
+        dt = self._dtype(sends[0])
+        n, sp, rp, cnt = self._group_arrays(sends, recvs)
+        h = self._lib.fb_group_prepare(self._h, n, sp, rp, cnt, dt)
+        if not h:
+            raise CommError(f"prepare_group failed [{_lib.last_error()}]")
+        return GroupPlan(self, h, n, sum(t.numel() * t.element_size() for t in sends))
+
+    def all_reduce_group(self, plan: "GroupPlan", op="sum", stream=None, channel=0, flags=FLAG_SYMMETRIC):
+        rc = self._lib.fb_group_allreduce(
+            self._h, plan._h, OPS[op], flags | ((channel & 0xF) << 8), self._stream(stream)
+        )
+        self._check(rc, "all_reduce_group")
+
+    def all_reduce_many(self, sends, recvs=None, op="sum", stream=None, channel=0):
+        """Transient variant of :meth:`prepare_group` + :meth:`all_reduce_group`
+        (the table is rebuilt and uploaded in stream order on every call)."""
+        recvs = sends if recvs is None else recvs
+        dt = self._dtype(sends[0])
+        n, sp, rp, cnt = self._group_arrays(sends, recvs)
+        f = self._sym(*sends) | ((channel & 0xF) << 8)
+        rc = self._lib.fb_allreduce_many(self._h, n, sp, rp, cnt, dt, OPS[op], f, self._stream(stream))
+        self._check(rc, "all_reduce_many")
+
+    def send_recv(self, send_buf, dst, recv_buf, src, stream=None):
+        rc = self._lib.fb_sendrecv(
+            self._h,
+            C.c_void_p(send_buf.data_ptr()),
+            send_buf.numel() * send_buf.element_size(),
+            dst,
+            C.c_void_p(recv_buf.data_ptr()),
+            recv_buf.numel() * recv_buf.element_size(),
+            src,
+            self._stream(stream),
+        )
+        self._check(rc, "send_recv")
+
+    def synchronize(self, stream=None, timeout_ms: int = 30000) -> bool:
+        """Bounded wait for ``stream``; False if it had to be aborted."""
+        return bool(self._lib.fb_comm_sync_bounded(self._h, self._stream(stream), int(timeout_ms)))
+
     def barrier(self, stream=None):
         self._check(self._lib.fb_barrier(self._h, self._stream(stream)), "barrier")
 
@@ -408,6 +468,28 @@ class Communicator:
             self._lib.fb_wait_signal(self._h, signal, count, self._stream(stream)),
             "wait_signal",
         )
+
+
+class GroupPlan:
+    """Device-resident segment tables of a grouped all-reduce."""
+
+    def __init__(self, comm: Communicator, handle, n_tensors: int, nbytes: int):
+        self._comm = comm
+        self._h = C.c_void_p(handle)
+        self.n_tensors = n_tensors
+        self.nbytes = nbytes
+        self.launches = int(comm._lib.fb_group_plan_launches(self._h))
+
+    def close(self):
+        if self._h:
+            self._comm._lib.fb_group_plan_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class LocalGroup:
@@ -461,6 +543,18 @@ class LocalGroup:
 
     def check_errors(self):
         return [c.check_error(self.streams[r]) for r, c in enumerate(self.comms)]
+
+    @property
+    def shares_devices(self) -> bool:
+        return len(set(self.devices)) < len(self.devices)
+
+    def coresident(self) -> bool:
+        """Probe for groups that synchronise INSIDE kernels while several ranks
+        share a GPU: one barrier kernel per rank must meet on the device.  False
+        (and a poisoned group: close it) when the ranks' kernels do not overlap,
+        e.g. their streams alias one hardware queue or a tool serialises them."""
+        self.run(lambda c, r, st: c.barrier())
+        return self.check_errors() == [0] * self.size
 
     def close(self):
         for c in self.comms:

@@ -14,9 +14,13 @@ pytestmark = pytest.mark.gpu
 from faabric_b200.parallel import LocalGroup  # noqa: E402
 
 GROUPS = {}
+SPIN_GROUPS = {}
 
 
 def group(n):
+    """Default wiring.  Ranks that share a GPU synchronise with stream memory
+    operations (no kernel ever waits for another rank's kernel), ranks on
+    distinct GPUs with the in-kernel flag barriers."""
     if n not in GROUPS:
         GROUPS[n] = LocalGroup(
             n,
@@ -28,12 +32,38 @@ def group(n):
     return GROUPS[n]
 
 
+def spin_group(n):
+    """In-kernel barriers (the multi-GPU product path: LL slots, two-step
+    broadcast, CUDA-graph replay) even when the ranks share one GPU.  That
+    needs the ranks' kernels to be co-resident, which is ASSERTED first: the
+    test is skipped, not failed, where the device does not overlap them."""
+    if n not in SPIN_GROUPS:
+        g = LocalGroup(
+            n,
+            heapBytes=64 << 20,
+            stageBytes=4 << 20,
+            maxBlocks=4,
+            timeoutMs=2000,
+            streamSync=0,
+        )
+        if g.shares_devices and not g.coresident():
+            g.close()
+            SPIN_GROUPS[n] = None
+        else:
+            SPIN_GROUPS[n] = g
+    if SPIN_GROUPS[n] is None:
+        pytest.skip("kernels of different ranks are not co-resident on this GPU")
+    return SPIN_GROUPS[n]
+
+
 @pytest.fixture(scope="module", autouse=True)
 def _cleanup():
     yield
-    for g in GROUPS.values():
-        g.close()
+    for g in list(GROUPS.values()) + list(SPIN_GROUPS.values()):
+        if g is not None:
+            g.close()
     GROUPS.clear()
+    SPIN_GROUPS.clear()
 
 
 def make_inputs(n, numel, dtype, dev, seed=0):
@@ -334,35 +364,84 @@ def test_large_symmetric_broadcast_two_step():
     g.run(lambda c, r, st: c.broadcast(bufs[r], root=2))
     g.synchronize()
     no_errors(g)
-    assert g.comms[0].last_algo == "twoshot"
+    if not g.comms[0].stream_sync:
+        assert g.comms[0].last_algo == "twoshot"
     for r in range(n):
         assert torch.equal(bufs[r].cpu(), torch.arange(numel, dtype=torch.int32))
     for c, b in zip(g.comms, bufs):
         c.free(b)
 
 
-@pytest.mark.parametrize("nbytes", [0, 1, 15, 4096, 300001, 5 << 20])
-def test_send_recv_ring(nbytes):
-    n = 4
-    g = group(n)
+def _ring_payload(g, nbytes):
     srcs = [
         (torch.arange(nbytes, dtype=torch.int64) * (r + 3) % 251).to(torch.uint8).to(f"cuda:{c.device}")
         for r, c in enumerate(g.comms)
     ]
     dsts = [torch.zeros(nbytes, dtype=torch.uint8, device=f"cuda:{c.device}") for c in g.comms]
-    side = [torch.cuda.Stream(device=c.device) for c in g.comms]
+    return srcs, dsts
+
+
+@pytest.mark.parametrize("nbytes", [0, 1, 15, 4096, 300001, 3 << 20])
+def test_send_recv_ring(nbytes):
+    """Ring r -> r+1 with a plain send followed by a recv on the SAME stream:
+    sends are eager (payload parked in the sender's heap, descriptor posted), no
+    kernel waits for a peer, so the ring cannot deadlock whatever the device
+    does with the four ranks' kernels (reference: MpiWorld::send never blocks,
+    src/mpi/MpiWorld.cpp:590-649)."""
+    n = 4
+    g = group(n)
+    srcs, dsts = _ring_payload(g, nbytes)
     torch.cuda.synchronize()
-    # ring: r sends to r+1, receives from r-1 (recv on a side stream so the
-    # exchange cannot deadlock, like MpiWorld::sendRecv = irecv + send + wait)
-    for r, c in enumerate(g.comms):
-        c.recv(dsts[r], (r - 1) % n, stream=side[r])
-    g.run(lambda c, r, st: c.send(srcs[r], (r + 1) % n))
+
+    def step(c, r, st):
+        c.send(srcs[r], (r + 1) % n)
+        c.recv(dsts[r], (r - 1) % n)
+
+    for _ in range(3):  # sequence numbers / slot reuse across messages
+        g.run(step)
     g.synchronize()
-    for s in side:
-        s.synchronize()
     no_errors(g)
     for r in range(n):
         assert torch.equal(dsts[r].cpu(), srcs[(r - 1) % n].cpu())
+
+
+@pytest.mark.parametrize("nbytes", [64, 300001, 20 << 20])
+def test_sendrecv_exchange_larger_than_the_bounce_ring(nbytes):
+    """MPI_Sendrecv-shaped exchange: chunks of both directions are interleaved,
+    so messages far beyond the eager capacity (8 MiB per peer) still flow."""
+    n = 4
+    g = group(n)
+    srcs, dsts = _ring_payload(g, nbytes)
+    torch.cuda.synchronize()
+    g.run(lambda c, r, st: c.send_recv(srcs[r], (r + 1) % n, dsts[r], (r - 1) % n))
+    g.synchronize()
+    no_errors(g)
+    for r in range(n):
+        assert torch.equal(dsts[r].cpu(), srcs[(r - 1) % n].cpu())
+
+
+def test_send_to_self():
+    g = group(2)
+    c = g.comms[0]
+    src = torch.arange(70000, dtype=torch.int32, device=f"cuda:{c.device}")
+    dst = torch.zeros_like(src)
+    c.send(src, 0, stream=g.streams[0])
+    c.recv(dst, 0, stream=g.streams[0])
+    g.synchronize()
+    no_errors(g)
+    assert torch.equal(src, dst)
+
+
+def test_recv_without_sender_is_aborted_not_hung():
+    """Stream-level waits have no timeout of their own: the bounded host wait
+    releases them and reports the failure (SURVEY 5.3 failure detection)."""
+    g = LocalGroup(2, heapBytes=1 << 20, stageBytes=1 << 20, maxBlocks=2, timeoutMs=200)
+    try:
+        dst = torch.zeros(1024, dtype=torch.uint8, device=f"cuda:{g.comms[0].device}")
+        g.comms[0].recv(dst, 1, stream=g.streams[0])
+        assert g.comms[0].check_error(g.streams[0]) != 0
+    finally:
+        g.close()
 
 
 def test_send_recv_fifo_order():
@@ -429,7 +508,7 @@ def test_graph_capture_replay():
     """Collectives keep their epochs in device memory so a captured graph can be
     replayed (launch-bound loops are captured once, replayed many times)."""
     n = 2
-    g = group(n)
+    g = spin_group(n)
     numel = 2048
     bufs = [c.empty(numel, torch.float32) for c in g.comms]
     outs = [c.empty(numel, torch.float32) for c in g.comms]
@@ -463,7 +542,7 @@ def test_graph_capture_replay():
 def test_watchdog_reports_missing_peer():
     """A rank that never shows up must not hang the GPU: the bounded spin sets
     the error word and the kernel retires (failure-detection)."""
-    g = LocalGroup(2, heapBytes=1 << 20, stageBytes=1 << 20, maxBlocks=2, timeoutMs=300)
+    g = LocalGroup(2, heapBytes=1 << 20, stageBytes=1 << 20, maxBlocks=2, timeoutMs=300, streamSync=0)
     try:
         t = torch.ones(1 << 16, device="cuda:0")
         o = torch.empty_like(t)
@@ -610,3 +689,125 @@ def test_large_pull_collectives_use_the_bulk_copy_engine(n, symmetric):
         for r, c in enumerate(g.comms):
             for t in (sends[r], outs[r], small[r], bc[r]):
                 c.free(t)
+
+
+# ---------------------------------------------------------------------------
+# grouped all-reduce: many tensors, one launch
+# ---------------------------------------------------------------------------
+GROUP_SIZES = [1, 3, 4, 7, 64, 1000, 4099, 65536 + 5, 9408, 300000, 2, 33]
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 3])
+@pytest.mark.parametrize("dtype,op", [(torch.int32, "sum"), (torch.float32, "sum"), (torch.bfloat16, "max"), (torch.int64, "min"), (torch.uint8, "bor")])
+def test_grouped_allreduce_matches_per_tensor_reference(n, dtype, op):
+    """One launch over a mixed list of tensors (odd sizes: < 16-byte tails,
+    tensors smaller than one vector, tensors spanning several ranks' ownership
+    ranges) equals an independent all-reduce of every tensor."""
+    g = group(n)
+    esize = torch.empty((), dtype=dtype).element_size()
+    sends = [[c.empty(s, dtype) for s in GROUP_SIZES] for c in g.comms]
+    recvs = [[c.empty(s, dtype) for s in GROUP_SIZES] for c in g.comms]
+    ins = [make_inputs(n, s, dtype, "cpu", seed=s) for s in GROUP_SIZES]
+    for r in range(n):
+        for i, t in enumerate(sends[r]):
+            t.copy_(ins[i][r])
+            recvs[r][i].fill_(0)
+    torch.cuda.synchronize()
+    plans = [c.prepare_group(sends[r], recvs[r]) for r, c in enumerate(g.comms)]
+    assert plans[0].launches == 1
+    for _ in range(2):
+        g.run(lambda c, r, st: c.all_reduce_group(plans[r], op=op))
+    g.synchronize()
+    no_errors(g)
+    for i, s in enumerate(GROUP_SIZES):
+        ref = ref_reduce([x.to("cpu") for x in ins[i]], op)
+        for r in range(n):
+            check(recvs[r][i].cpu(), ref, dtype)
+    # in place + transient table
+    g.run(lambda c, r, st: c.all_reduce_many(sends[r], op=op))
+    g.synchronize()
+    no_errors(g)
+    for i, s in enumerate(GROUP_SIZES):
+        ref = ref_reduce([x.to("cpu") for x in ins[i]], op)
+        for r in range(n):
+            check(sends[r][i].cpu(), ref, dtype)
+    for p in plans:
+        p.close()
+    for r, c in enumerate(g.comms):
+        for t in sends[r] + recvs[r]:
+            c.free(t)
+    assert esize > 0
+
+
+def test_grouped_allreduce_many_tensors_split_into_launches():
+    n = 2
+    g = group(n)
+    k = 1500  # > FB_GROUP_MAX_SEGS: two launches
+    flat = [c.empty(k * 64, torch.int32) for c in g.comms]
+    for r, f in enumerate(flat):
+        f.copy_(torch.arange(k * 64, dtype=torch.int32) + r)
+    torch.cuda.synchronize()
+    views = [[f[i * 64 : i * 64 + 1 + (i % 60)] for i in range(k)] for f in flat]
+    plans = [c.prepare_group(views[r]) for r, c in enumerate(g.comms)]
+    assert plans[0].launches == 2
+    g.run(lambda c, r, st: c.all_reduce_group(plans[r]))
+    g.synchronize()
+    no_errors(g)
+    base = torch.arange(k * 64, dtype=torch.int32)
+    touched = torch.zeros(k * 64, dtype=torch.bool)
+    for i in range(k):
+        touched[i * 64 : i * 64 + 1 + (i % 60)] = True
+    for r in range(n):
+        # reduced positions hold the sum over ranks, the padding between the
+        # views keeps this rank's own values
+        exp = torch.where(touched, n * base + n * (n - 1) // 2, base + r)
+        assert torch.equal(flat[r].cpu(), exp)
+    for p in plans:
+        p.close()
+    for c, f in zip(g.comms, flat):
+        c.free(f)
+
+
+def test_grouped_rejects_non_symmetric_tensors():
+    g = group(2)
+    c = g.comms[0]
+    t = torch.zeros(64, dtype=torch.int32, device=f"cuda:{c.device}")
+    from faabric_b200.parallel.comm import CommError
+
+    with pytest.raises(CommError):
+        c.prepare_group([t])
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_in_kernel_barrier_path_ll_oneshot_twoshot(n):
+    """The product path on one GPU: LL slots, in-kernel flag barriers, grouped
+    kernel with its two barriers (co-residency asserted by spin_group)."""
+    g = spin_group(n)
+    assert not g.comms[0].stream_sync
+    for algo, numel in (("ll", 1000), ("oneshot", 5000), ("twoshot", 70001)):
+        sends = [c.empty(numel, torch.int32) for c in g.comms]
+        recvs = [c.empty(numel, torch.int32) for c in g.comms]
+        for r, t in enumerate(sends):
+            t.copy_(torch.arange(numel, dtype=torch.int32) * (r + 1))
+        torch.cuda.synchronize()
+        g.run(lambda c, r, st: c.all_reduce(sends[r], recvs[r], algo=algo))
+        g.synchronize()
+        no_errors(g)
+        assert g.comms[0].last_algo == algo
+        exp = torch.arange(numel, dtype=torch.int32) * (n * (n + 1) // 2)
+        for r in range(n):
+            assert torch.equal(recvs[r].cpu(), exp)
+        plans = [c.prepare_group([sends[r]], [recvs[r]]) for r, c in enumerate(g.comms)]
+        for t in recvs:
+            t.zero_()
+        torch.cuda.synchronize()
+        g.run(lambda c, r, st: c.all_reduce_group(plans[r]))
+        g.synchronize()
+        no_errors(g)
+        for r in range(n):
+            assert torch.equal(recvs[r].cpu(), exp)
+        for p in plans:
+            p.close()
+        for c, a, b in zip(g.comms, sends, recvs):
+            c.free(a)
+            c.free(b)
