@@ -72,6 +72,18 @@ class ChainedCallException : public faabric::util::FaabricException
     {}
 };
 
+// Function memory that lives in HBM (B200): executors that return a non-empty
+// view take the device paths of restore / THREADS fork-join, where the
+// snapshot image, the per-host base image and the merge all stay on the GPUs
+struct DeviceMemoryView
+{
+    uint8_t* ptr = nullptr;
+    size_t size = 0;
+    int device = -1;
+
+    bool empty() const { return ptr == nullptr || size == 0; }
+};
+
 class Executor : public std::enable_shared_from_this<Executor>
 {
   public:
@@ -100,6 +112,9 @@ class Executor : public std::enable_shared_from_this<Executor>
       std::shared_ptr<faabric::BatchExecuteRequest> req);
 
     virtual std::span<uint8_t> getMemoryView();
+
+    // Device-resident function memory (default: none => host paths)
+    virtual DeviceMemoryView getDeviceMemoryView();
 
     virtual void restore(const std::string& snapshotKey);
 
@@ -143,6 +158,22 @@ class Executor : public std::enable_shared_from_this<Executor>
     std::vector<faabric::util::SnapshotDiff> mergeDirtyRegions(
       const faabric::Message& msg,
       const std::vector<char>& extraDirtyPages = {});
+
+    // Device flavour of mergeDirtyRegions: ONE fused kernel diffs this
+    // executor's HBM memory against its private base image, applies the merge
+    // regions and stores the result straight into the main image (local or a
+    // peer GPU's memory).  Returns the number of bytes merged.
+    uint64_t mergeDirtyRegionsOnDevice(const faabric::Message& msg);
+
+    // Device-resident main-thread snapshot (created from the device memory
+    // view on first use)
+    std::shared_ptr<faabric::snapshot::DeviceSnapshot> getMainThreadDeviceSnapshot(
+      faabric::Message& msg,
+      bool createIfNotExists = false);
+
+    uint64_t getDeviceMergeCount() const { return deviceMergeCount.load(); }
+
+    uint64_t getLastDeviceDiffBytes() const { return lastDeviceDiffBytes.load(); }
 
     // Blocks until every pool thread finished (tests)
     void joinThreadPool();
@@ -190,7 +221,43 @@ class Executor : public std::enable_shared_from_this<Executor>
     int gpuIdx = -1;
     void* computeStream = nullptr;
 
+    // THREADS on device memory: private base image of this host's copy and the
+    // main image the merge is pushed into
+    std::shared_ptr<faabric::snapshot::DeviceSnapshot> threadsBase;
+    std::shared_ptr<faabric::snapshot::DeviceSnapshot> threadsMain;
+    std::atomic<uint64_t> deviceMergeCount = 0;
+    std::atomic<uint64_t> lastDeviceDiffBytes = 0;
+
+    void prepareDeviceThreads(const std::string& key, bool isMain);
+
     void threadPoolThread(std::stop_token st, int threadPoolIdx);
+};
+
+}
+
+namespace faabric::executor {
+
+// Ready-made executor whose function memory is a growable HBM allocation on
+// the GPU the executor is bound to (reference analogue: the memory an embedder
+// such as Faasm hands out through getMemoryView, here device-resident).
+// Subclasses implement executeTask and work on getDeviceMemoryView().
+class DeviceExecutor : public Executor
+{
+  public:
+    DeviceExecutor(faabric::Message& msg, size_t initialSize, size_t maxSize);
+
+    ~DeviceExecutor() override;
+
+    DeviceMemoryView getDeviceMemoryView() override;
+
+    void setMemorySize(size_t newSize) override;
+
+    size_t getMaxMemorySize() override { return maxSize; }
+
+  private:
+    faabric::util::DeviceRegion memory;
+    size_t currentSize = 0;
+    size_t maxSize = 0;
 };
 
 }

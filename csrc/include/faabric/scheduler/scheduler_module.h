@@ -150,6 +150,9 @@ class Scheduler
 
     ~Scheduler();
 
+    // Key of the warm-executor pools (function, plus the virtual host)
+    static std::string executorKeyFor(const faabric::Message& msg);
+
     void executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req);
 
     void reset();

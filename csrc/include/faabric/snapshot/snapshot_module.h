@@ -39,6 +39,20 @@ struct DeviceDiffStats
     uint64_t pagesWithDiffs = 0;
 };
 
+// What travels over the control plane INSTEAD of the image when both ends are
+// GPU hosts of one box: where the image lives and how to map it.  The
+// reference serialises the whole image into the request
+// (src/snapshot/SnapshotClient.cpp:76-108).
+struct DeviceSnapshotDescriptor
+{
+    uint64_t size = 0;
+    int device = -1;
+    int ownerPid = 0;
+    uint64_t devicePtr = 0;  // valid inside the owner process
+    std::string ipcHandle;   // cudaIpcMemHandle_t bytes (empty: not exportable)
+    std::vector<faabric::util::SnapshotMergeRegion> mergeRegions;
+};
+
 class DeviceSnapshot
 {
   public:
@@ -113,6 +127,18 @@ class DeviceSnapshot
     // GPU dirty-page detection of `mem` against this image
     std::vector<char> getDirtyPages(const uint8_t* mem, size_t memSize);
 
+    // ---- control-plane descriptor (cross-process mapping through CUDA IPC) ----
+    DeviceSnapshotDescriptor describe();
+
+    // Maps an image owned by ANOTHER process of this box (throws if the
+    // descriptor carries no IPC handle)
+    static std::shared_ptr<DeviceSnapshot> fromDescriptor(const DeviceSnapshotDescriptor& desc);
+
+    // How many fused diff+push launches this image has issued (tests, metrics)
+    uint64_t getDiffPushCount() const { return diffPushCount; }
+
+    static uint64_t getGlobalDiffPushCount();
+
   private:
     size_t size = 0;
     int device = 0;
@@ -131,6 +157,9 @@ class DeviceSnapshot
     int nTypedDev = 0;
 
     void uploadRegions();
+
+    void* ipcMapped = nullptr;
+    uint64_t diffPushCount = 0;
 };
 
 }
@@ -177,6 +206,10 @@ std::vector<std::pair<std::string, std::string>> getSnapshotDeletes();
 std::vector<std::pair<std::string, std::tuple<int, int, std::string, int>>>
 getThreadResults();
 
+// (host, key, descriptor) of every device-image descriptor pushed in mock mode
+std::vector<std::tuple<std::string, std::string, DeviceSnapshotDescriptor>>
+getDeviceSnapshotPushes();
+
 void clearMockSnapshotRequests();
 
 // -----------------------------------
@@ -202,6 +235,25 @@ class SnapshotClient final : public faabric::transport::MessageEndpointClient
                           int returnValue,
                           const std::string& key,
                           const std::vector<faabric::util::SnapshotDiff>& diffs);
+
+    // ---- GPU hosts: control descriptors only, the bytes stay in HBM ----
+    // "Push" of a device-resident image: the receiver learns where it lives
+    void pushDeviceSnapshot(const std::string& key,
+                            const DeviceSnapshotDescriptor& desc);
+
+    // Thread result whose diffs were already merged into the main image by
+    // the fused kernel on the sender's GPU
+    void pushDeviceThreadResult(uint32_t appId,
+                                uint32_t messageId,
+                                int returnValue,
+                                const std::string& key,
+                                uint64_t diffBytes);
+
+  private:
+    // True when `host` is served by this process and its registry (ours)
+    // already holds this very object under `key`
+    bool receiverSharesRegistry(const std::string& key,
+                                const std::shared_ptr<faabric::util::SnapshotData>& data);
 };
 
 std::shared_ptr<SnapshotClient> getSnapshotClient(const std::string& host);
@@ -245,6 +297,15 @@ class SnapshotRegistry
 
     void deleteDeviceSnapshot(const std::string& key);
 
+    // Descriptors of device images owned elsewhere (resolved to a mapped
+    // DeviceSnapshot by getDeviceSnapshot on first use)
+    void registerDeviceDescriptor(const std::string& key,
+                                  const DeviceSnapshotDescriptor& desc);
+
+    bool deviceDescriptorExists(const std::string& key);
+
+    DeviceSnapshotDescriptor getDeviceDescriptor(const std::string& key);
+
     void clear();
 
     // ---- on-disk checkpoints: one file per snapshot under `dir` (created if
@@ -261,6 +322,7 @@ class SnapshotRegistry
     std::unordered_map<std::string, std::shared_ptr<faabric::util::SnapshotData>>
       snapshotMap;
     std::unordered_map<std::string, std::shared_ptr<DeviceSnapshot>> deviceMap;
+    std::unordered_map<std::string, DeviceSnapshotDescriptor> descriptorMap;
 };
 
 SnapshotRegistry& getSnapshotRegistry();

@@ -936,6 +936,13 @@ void clearHostAliases();
 
 std::string resolveHostAlias(const std::string& host);
 
+// True if `host` is a registered virtual host name
+bool isHostAlias(const std::string& host);
+
+// Same worker? (a virtual host and the address serving it, two virtual hosts
+// of one worker, ...).  Empty names match nothing.
+bool sameWorker(const std::string& hostA, const std::string& hostB);
+
 std::string makeHostAddress(const std::string& ip, int portOffset);
 
 // Address other workers use to reach this worker

@@ -5,6 +5,7 @@
 #include <faabric/mpi/MpiWorldRegistry.h>
 #include <faabric/planner/PlannerClient.h>
 #include <faabric/scheduler/Scheduler.h>
+#include <faabric/snapshot/DeviceSnapshot.h>
 #include <faabric/snapshot/SnapshotClient.h>
 #include <faabric/transport/PointToPointBroker.h>
 #include <faabric/transport/common.h>
@@ -193,7 +194,7 @@ void Executor::releaseClaim()
 {
     claimed.store(false);
     // Tell the scheduler so the next claim does not have to search for us
-    faabric::scheduler::getScheduler().notifyExecutorIdle(faabric::util::funcToString(boundMessage, false),
+    faabric::scheduler::getScheduler().notifyExecutorIdle(faabric::scheduler::Scheduler::executorKeyFor(boundMessage),
                                                           weak_from_this());
 }
 
@@ -208,8 +209,53 @@ long Executor::getMillisSinceLastExec()
     return faabric::util::getGlobalClock().timeDiff(now, lastExec);
 }
 
+namespace {
+struct GpuGuard
+{
+    int prev = -1;
+    explicit GpuGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (dev >= 0) {
+            cudaSetDevice(dev);
+        }
+    }
+    ~GpuGuard()
+    {
+        if (prev >= 0) {
+            cudaSetDevice(prev);
+        }
+        cudaGetLastError();
+    }
+};
+
+void cudaCheck(cudaError_t e, const char* what)
+{
+    if (e != cudaSuccess) {
+        throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+    }
+}
+}
+
+// The planner host this message executes on: a per-GPU virtual host name when
+// the worker serves several, else the worker's own address
+static std::string servedHost(const faabric::Message& msg)
+{
+    return msg.executedhost().empty() ? faabric::transport::getThisHostAddress() : msg.executedhost();
+}
+
+static bool mainHostIsHere(const faabric::Message& msg)
+{
+    return msg.mainhost().empty() || msg.mainhost() == servedHost(msg);
+}
+
 // ---- hooks (defaults) ----
 void Executor::reset(faabric::Message& msg) {}
+
+DeviceMemoryView Executor::getDeviceMemoryView()
+{
+    return {};
+}
 
 int32_t Executor::executeTask(int threadPoolIdx,
                               int msgIdx,
@@ -237,6 +283,32 @@ size_t Executor::getMaxMemorySize()
 
 void Executor::restore(const std::string& snapshotKey)
 {
+    DeviceMemoryView dv = getDeviceMemoryView();
+    if (!dv.empty()) {
+        // Device-resident function memory: the restore is a device copy (peer
+        // copy over NVLink when the image lives on another GPU), or one H2D
+        // copy when only a host image exists (thaw from a checkpoint)
+        GpuGuard g(dv.device);
+        auto stream = (cudaStream_t)computeStream;
+        if (reg.deviceSnapshotExists(snapshotKey)) {
+            auto snap = reg.getDeviceSnapshot(snapshotKey);
+            if (snap->getSize() > dv.size) {
+                setMemorySize(snap->getSize());
+                dv = getDeviceMemoryView();
+            }
+            snap->restoreTo(dv.ptr, std::min(dv.size, snap->getSize()), stream);
+        } else {
+            auto snap = reg.getSnapshot(snapshotKey);
+            if (snap->getSize() > dv.size) {
+                setMemorySize(snap->getSize());
+                dv = getDeviceMemoryView();
+            }
+            cudaCheck(cudaMemcpyAsync(dv.ptr, snap->getDataPtr(), std::min(dv.size, snap->getSize()), cudaMemcpyHostToDevice, stream),
+                      "restore H2D");
+        }
+        cudaCheck(cudaStreamSynchronize(stream), "restore sync");
+        return;
+    }
     std::span<uint8_t> memView = getMemoryView();
     if (memView.empty()) {
         SPDLOG_WARN("Not restoring {}: empty memory view", snapshotKey);
@@ -315,6 +387,83 @@ void Executor::deleteMainThreadSnapshot(const faabric::Message& msg)
     if (reg.snapshotExists(key)) {
         reg.deleteSnapshot(key);
     }
+    if (reg.deviceSnapshotExists(key)) {
+        reg.deleteDeviceSnapshot(key);
+    }
+}
+
+std::shared_ptr<faabric::snapshot::DeviceSnapshot> Executor::getMainThreadDeviceSnapshot(
+  faabric::Message& msg,
+  bool createIfNotExists)
+{
+    std::string key = faabric::util::getMainThreadSnapshotKey(msg);
+    std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
+    if (reg.deviceSnapshotExists(key)) {
+        return reg.getDeviceSnapshot(key);
+    }
+    if (!createIfNotExists) {
+        SPDLOG_ERROR("No main thread device snapshot {}", key);
+        throw std::runtime_error("No main thread device snapshot");
+    }
+    DeviceMemoryView dv = getDeviceMemoryView();
+    if (dv.empty()) {
+        throw std::runtime_error("Executor has no device memory view");
+    }
+    SPDLOG_DEBUG("Creating main thread device snapshot: {} ({} bytes on GPU {})", key, dv.size, dv.device);
+    auto snap = std::make_shared<faabric::snapshot::DeviceSnapshot>(dv.size, dv.device);
+    reg.registerDeviceSnapshot(key, snap);
+    return snap;
+}
+
+// Every host of a THREADS batch (the main one included) diffs against a PRIVATE
+// copy of what it started from: the main image is being written by the other
+// hosts' merge kernels while this host still runs.
+void Executor::prepareDeviceThreads(const std::string& key, bool isMain)
+{
+    DeviceMemoryView dv = getDeviceMemoryView();
+    auto mainSnap = reg.getDeviceSnapshot(key);
+    GpuGuard g(dv.device);
+    auto stream = (cudaStream_t)computeStream;
+    if (!isMain) {
+        if (mainSnap->getSize() > dv.size) {
+            setMemorySize(mainSnap->getSize());
+            dv = getDeviceMemoryView();
+        }
+        mainSnap->restoreTo(dv.ptr, std::min(dv.size, mainSnap->getSize()), stream);
+    }
+    const size_t n = std::min(dv.size, mainSnap->getSize());
+    if (threadsBase == nullptr || threadsBase->getSize() != n || threadsBase->getDevice() != dv.device) {
+        threadsBase = std::make_shared<faabric::snapshot::DeviceSnapshot>(n, dv.device);
+    }
+    cudaCheck(cudaMemcpyAsync(threadsBase->getDevicePtr(), dv.ptr, n, cudaMemcpyDeviceToDevice, stream), "thread base copy");
+    threadsBase->clearMergeRegions();
+    for (const auto& r : mainSnap->getMergeRegions()) {
+        threadsBase->addMergeRegion(r.offset, r.length, r.dataType, r.operation);
+    }
+    cudaCheck(cudaStreamSynchronize(stream), "thread base sync");
+    threadsMain = mainSnap;
+}
+
+uint64_t Executor::mergeDirtyRegionsOnDevice(const faabric::Message& msg)
+{
+    if (threadsBase == nullptr || threadsMain == nullptr) {
+        throw std::runtime_error("No device thread state to merge");
+    }
+    DeviceMemoryView dv = getDeviceMemoryView();
+    GpuGuard g(dv.device);
+    auto stream = (cudaStream_t)computeStream;
+    // scan + diff + typed merge + store into the (possibly remote) main image
+    threadsBase->diffAndPush(dv.ptr, dv.size, threadsMain->getDevicePtr(), nullptr, false, stream);
+    auto stats = threadsBase->getLastStats(stream); // synchronises: the merge has landed
+    deviceMergeCount.fetch_add(1);
+    lastDeviceDiffBytes.store(stats.diffBytes);
+    SPDLOG_DEBUG("{} merged {} bytes ({} pages) of message {} into the main image on the device",
+                 id,
+                 stats.diffBytes,
+                 stats.pagesWithDiffs,
+                 msg.id());
+    threadsMain = nullptr;
+    return stats.diffBytes;
 }
 
 std::vector<faabric::util::SnapshotDiff> Executor::mergeDirtyRegions(
@@ -361,15 +510,21 @@ void Executor::executeTasks(std::vector<int> msgIdxs,
         std::string key = faabric::util::getMainThreadSnapshotKey(first);
         SPDLOG_DEBUG("Restoring {} from snapshot {} before executing {} threads", funcStr, key, nMessages);
         std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
-        bool isMain = first.mainhost() == faabric::transport::getThisHostAddress() || first.mainhost().empty();
-        if (!isMain) {
-            restore(key);
+        bool isMain = mainHostIsHere(first);
+        if (!getDeviceMemoryView().empty() && reg.deviceSnapshotExists(key)) {
+            // Device memory: restore is a (peer) device copy, change detection
+            // is the fused compare-with-base kernel at merge time
+            prepareDeviceThreads(key, isMain);
+        } else {
+            if (!isMain) {
+                restore(key);
+            }
+            std::span<uint8_t> memView = getMemoryView();
+            tracker->clearAll();
+            tracker->startTracking(memView);
+            threadLocalDirtyRegions.clear();
+            dirtyRegions.clear();
         }
-        std::span<uint8_t> memView = getMemoryView();
-        tracker->clearAll();
-        tracker->startTracking(memView);
-        threadLocalDirtyRegions.clear();
-        dirtyRegions.clear();
     } else if (!isThreads && !first.snapshotkey().empty()) {
         // A function resuming from a snapshot (migration / thaw)
         restore(first.snapshotkey());
@@ -412,6 +567,48 @@ std::vector<std::pair<uint32_t, int32_t>> Executor::executeThreads(
     SPDLOG_DEBUG("Executor {} executing {} threads", id, req->messages_size());
     faabric::Message& msg = *req->mutable_messages(0);
     std::string key = faabric::util::getMainThreadSnapshotKey(msg);
+    // The main host of the threads is the (virtual) host this executor serves
+    std::string myHost = boundMessage.executedhost();
+    if (ExecutorContext::isSet() && ExecutorContext::get()->getExecutor() == this) {
+        myHost = ExecutorContext::get()->getMsg().executedhost();
+    }
+    if (faabric::transport::isHostAlias(myHost)) {
+        for (int i = 0; i < req->messages_size(); i++) {
+            req->mutable_messages(i)->set_mainhost(myHost);
+        }
+    }
+    DeviceMemoryView dv = getDeviceMemoryView();
+    if (!dv.empty()) {
+        // ---- device-resident fork-join ----
+        auto snap = getMainThreadDeviceSnapshot(msg, true);
+        {
+            // The main thread is authoritative: bring the image up to date
+            GpuGuard g(dv.device);
+            auto stream = (cudaStream_t)computeStream;
+            cudaCheck(cudaMemcpyAsync(snap->getDevicePtr(), dv.ptr, std::min(dv.size, snap->getSize()), cudaMemcpyDeviceToDevice, stream),
+                      "main image refresh");
+            cudaCheck(cudaStreamSynchronize(stream), "main image refresh sync");
+        }
+        snap->clearMergeRegions();
+        for (const auto& r : mergeRegions) {
+            snap->addMergeRegion(r.offset, r.length, r.dataType, r.operation);
+        }
+        req->set_type(faabric::BatchExecuteRequest::THREADS);
+        auto decision = faabric::planner::getPlannerClient().callFunctions(req);
+        if ((int)decision.appId == NOT_ENOUGH_SLOTS) {
+            throw std::runtime_error("Not enough slots to execute threads");
+        }
+        auto results = faabric::scheduler::getScheduler().awaitThreadResults(req);
+        if (!decision.isSingleHost()) {
+            // every host's merge kernel has completed before its result was
+            // published: the image now holds the merged state
+            GpuGuard g(dv.device);
+            auto stream = (cudaStream_t)computeStream;
+            snap->restoreTo(dv.ptr, std::min(dv.size, snap->getSize()), stream);
+            cudaCheck(cudaStreamSynchronize(stream), "merged image restore");
+        }
+        return results;
+    }
     bool existed = reg.snapshotExists(key);
     auto snap = getMainThreadSnapshot(msg, true);
     std::span<uint8_t> memView = getMemoryView();
@@ -477,7 +674,8 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
         faabric::Message& msg = *req->mutable_messages(task.messageIndex);
         const bool isThreads = req->type() == faabric::BatchExecuteRequest::THREADS;
         const bool isMigration = req->type() == faabric::BatchExecuteRequest::MIGRATION;
-        const bool doDirtyTracking = isThreads && !req->singlehost();
+        const bool deviceThreads = isThreads && !req->singlehost() && threadsBase != nullptr && threadsMain != nullptr;
+        const bool doDirtyTracking = isThreads && !req->singlehost() && !deviceThreads;
         if (doDirtyTracking) {
             tracker->startThreadLocalTracking(getMemoryView());
         }
@@ -534,6 +732,17 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
 
         // The last thread diffs this host's memory against the snapshot
         std::vector<faabric::util::SnapshotDiff> diffs;
+        bool deviceMerged = false;
+        uint64_t deviceDiffBytes = 0;
+        if (isLastThreadInBatch && deviceThreads) {
+            try {
+                std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
+                deviceDiffBytes = mergeDirtyRegionsOnDevice(msg);
+                deviceMerged = true;
+            } catch (const std::exception& ex) {
+                SPDLOG_ERROR("Failed merging device memory for {}: {}", msg.id(), ex.what());
+            }
+        }
         if (isLastThreadInBatch && doDirtyTracking) {
             try {
                 std::unique_lock<std::shared_mutex> lock(threadExecutionMutex);
@@ -564,13 +773,17 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
 
         msg.set_finishtimestamp(faabric::util::getGlobalClock().epochMillis());
         if (isThreads) {
-            bool mainIsHere = msg.mainhost().empty() || msg.mainhost() == faabric::transport::getThisHostAddress();
+            bool mainIsHere = mainHostIsHere(msg);
             if (!diffs.empty() || isLastThreadInBatch) {
                 std::string key = faabric::util::getMainThreadSnapshotKey(msg);
                 if (mainIsHere) {
                     if (!diffs.empty()) {
                         reg.getSnapshot(key)->queueDiffs(diffs);
                     }
+                } else if (deviceMerged) {
+                    // the bytes are already in the main image: control message only
+                    faabric::snapshot::getSnapshotClient(msg.mainhost())
+                      ->pushDeviceThreadResult(msg.appid(), msg.id(), returnValue, key, deviceDiffBytes);
                 } else if (!diffs.empty()) {
                     faabric::snapshot::getSnapshotClient(msg.mainhost())
                       ->pushThreadResult(msg.appid(), msg.id(), returnValue, key, diffs);
@@ -583,6 +796,39 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
     // Thread-local caches die with the thread
     sch.resetThreadLocalCache();
     broker.resetThreadLocalCache();
+}
+
+// ---------------------------------------------------------------------------
+// DeviceExecutor
+// ---------------------------------------------------------------------------
+DeviceExecutor::DeviceExecutor(faabric::Message& msg, size_t initialSize, size_t maxSizeIn)
+  : Executor(msg)
+  , currentSize(initialSize)
+  , maxSize(std::max(initialSize, maxSizeIn))
+{
+    if (getGpuIdx() < 0) {
+        throw std::runtime_error("DeviceExecutor needs a GPU");
+    }
+    // Reserve the maximum up front (HBM is plentiful: 180 GB per B200), expose
+    // `currentSize` of it, like the reference's virtual reservation + mprotect
+    memory = faabric::util::allocateDeviceMemory(maxSize, getGpuIdx());
+    GpuGuard g(getGpuIdx());
+    cudaCheck(cudaMemset(memory.ptr, 0, maxSize), "device executor memset");
+}
+
+DeviceExecutor::~DeviceExecutor() = default;
+
+DeviceMemoryView DeviceExecutor::getDeviceMemoryView()
+{
+    return { memory.ptr, currentSize, getGpuIdx() };
+}
+
+void DeviceExecutor::setMemorySize(size_t newSize)
+{
+    if (newSize > maxSize) {
+        throw std::runtime_error("Device executor memory beyond its maximum");
+    }
+    currentSize = newSize;
 }
 
 } // namespace faabric::executor

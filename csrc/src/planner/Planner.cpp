@@ -917,6 +917,14 @@ void Planner::dispatchSchedulingDecision(
         if (isThreads && !singleHost) {
             std::string key = faabric::util::getMainThreadSnapshotKey(hr->messages(0));
             try {
+                if (snapshotRegistry.deviceDescriptorExists(key)) {
+                    // device-resident image: forward the descriptor only
+                    if (host != req->messages(0).mainhost()) {
+                        faabric::snapshot::getSnapshotClient(host)->pushDeviceSnapshot(
+                          key, snapshotRegistry.getDeviceDescriptor(key));
+                    }
+                    goto dispatchFunctions;
+                }
                 auto snap = snapshotRegistry.getSnapshot(key);
                 if (host != req->messages(0).mainhost()) {
                     faabric::snapshot::getSnapshotClient(host)->pushSnapshot(key, snap);
@@ -937,6 +945,7 @@ void Planner::dispatchSchedulingDecision(
                 }
             }
         }
+    dispatchFunctions:
         faabric::scheduler::getFunctionCallClient(host)->executeFunctions(hr);
     }
 }

@@ -258,12 +258,23 @@ faabric::batch_scheduler::SchedulingDecision PlannerClient::callFunctions(
     // must have it (full image the first time, tracked changes after that)
     bool isThreads = req->type() == faabric::BatchExecuteRequest::THREADS;
     if (isThreads && req->messages_size() > 0) {
+        // (an executor serving a per-GPU virtual host has already stamped its
+        // own name: several "hosts" share this process)
         std::string mainHost = faabric::transport::getThisHostAddress();
         for (int i = 0; i < req->messages_size(); i++) {
-            req->mutable_messages(i)->set_mainhost(mainHost);
+            if (req->messages(i).mainhost().empty() || !faabric::transport::isHostAlias(req->messages(i).mainhost())) {
+                req->mutable_messages(i)->set_mainhost(mainHost);
+            }
         }
         if (!req->singlehosthint()) {
             std::string key = faabric::util::getMainThreadSnapshotKey(req->messages(0));
+            if (snapshotRegistry.deviceSnapshotExists(key)) {
+                // Device-resident image: the planner only needs to know where
+                // it lives (control descriptor), the bytes stay in HBM
+                auto dsnap = snapshotRegistry.getDeviceSnapshot(key);
+                faabric::snapshot::getSnapshotClient(host)->pushDeviceSnapshot(key, dsnap->describe());
+                goto snapshotDone;
+            }
             auto snap = snapshotRegistry.getSnapshot(key);
             bool firstPush;
             {
@@ -281,6 +292,7 @@ faabric::batch_scheduler::SchedulingDecision PlannerClient::callFunctions(
             snap->clearTrackedChanges();
         }
     }
+snapshotDone:
 
     faabric::PointToPointMappings resp;
     syncSend(PlannerCalls::CallBatch, req.get(), &resp);

@@ -227,7 +227,7 @@ long Scheduler::getFunctionExecutorCount(const faabric::Message& msg)
     long n = 0;
     std::string prefix = faabric::util::funcToString(msg, false);
     for (const auto& [key, vec] : executors) {
-        if (key == prefix || key.rfind(prefix + ":", 0) == 0) {
+        if (key == prefix || key.rfind(prefix + ":", 0) == 0 || key.rfind(prefix + "@", 0) == 0) {
             n += (long)vec.size();
         }
     }
@@ -244,10 +244,21 @@ void Scheduler::flushLocally()
 // ---------------------------------------------------------------------------
 // Execution
 // ---------------------------------------------------------------------------
+std::string Scheduler::executorKeyFor(const faabric::Message& msg)
+{
+    // Executors are warm per user/function and reused across apps.  One
+    // scheduler may serve several per-GPU virtual hosts: an executor is bound
+    // to the GPU of the host it was created for, so the host is part of the key
+    std::string key = faabric::util::funcToString(msg, false);
+    if (!msg.executedhost().empty() && faabric::transport::isHostAlias(msg.executedhost())) {
+        key += "@" + msg.executedhost();
+    }
+    return key;
+}
+
 static std::string executorKey(const faabric::Message& msg)
 {
-    // Executors are warm per user/function and reused across apps
-    return faabric::util::funcToString(msg, false);
+    return Scheduler::executorKeyFor(msg);
 }
 
 std::shared_ptr<faabric::executor::Executor> Scheduler::claimExecutor(
@@ -316,11 +327,19 @@ void Scheduler::executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req)
         faabric::Message& first = *req->mutable_messages(0);
         std::shared_ptr<faabric::executor::Executor> e;
         try {
-            auto& candidates = executors[executorKey(first)];
-            for (auto& c : candidates) {
-                if (c->isExecuting() && c->getCurrentAppId() == first.appid()) {
-                    e = c;
-                    break;
+            // (several per-GPU virtual hosts may share this scheduler: threads
+            // addressed to a host other than the main one get an executor -
+            // and a GPU - of their own)
+            const bool onMainHost = first.mainhost().empty() || first.executedhost().empty() ||
+                                    first.mainhost() == first.executedhost() ||
+                                    !faabric::transport::isHostAlias(first.executedhost());
+            if (onMainHost) {
+                auto& candidates = executors[executorKey(first)];
+                for (auto& c : candidates) {
+                    if (c->isExecuting() && c->getCurrentAppId() == first.appid()) {
+                        e = c;
+                        break;
+                    }
                 }
             }
             if (e == nullptr) {

@@ -16,7 +16,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <unistd.h>
 
 namespace faabric::snapshot {
 
@@ -77,19 +79,58 @@ size_t SnapshotRegistry::getSnapshotCount()
 
 std::shared_ptr<DeviceSnapshot> SnapshotRegistry::getDeviceSnapshot(const std::string& key)
 {
-    std::shared_lock<std::shared_mutex> lock(snapshotsMx);
-    auto it = deviceMap.find(key);
-    if (it == deviceMap.end()) {
-        SPDLOG_ERROR("Device snapshot for {} does not exist", key);
-        throw std::runtime_error("Device snapshot doesn't exist");
+    DeviceSnapshotDescriptor desc;
+    {
+        std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+        auto it = deviceMap.find(key);
+        if (it != deviceMap.end()) {
+            return it->second;
+        }
+        auto dit = descriptorMap.find(key);
+        if (dit == descriptorMap.end()) {
+            SPDLOG_ERROR("Device snapshot for {} does not exist", key);
+            throw std::runtime_error("Device snapshot doesn't exist");
+        }
+        desc = dit->second;
     }
+    // An image owned by another process of this box: map it once
+    auto mapped = DeviceSnapshot::fromDescriptor(desc);
+    std::unique_lock<std::shared_mutex> lock(snapshotsMx);
+    auto [it, inserted] = deviceMap.try_emplace(key, mapped);
     return it->second;
 }
 
 bool SnapshotRegistry::deviceSnapshotExists(const std::string& key)
 {
     std::shared_lock<std::shared_mutex> lock(snapshotsMx);
-    return deviceMap.find(key) != deviceMap.end();
+    if (deviceMap.find(key) != deviceMap.end()) {
+        return true;
+    }
+    auto dit = descriptorMap.find(key);
+    return dit != descriptorMap.end() && !dit->second.ipcHandle.empty() &&
+           dit->second.ownerPid != (int)::getpid() && faabric::util::getUsableGpus() > 0;
+}
+
+void SnapshotRegistry::registerDeviceDescriptor(const std::string& key, const DeviceSnapshotDescriptor& desc)
+{
+    std::unique_lock<std::shared_mutex> lock(snapshotsMx);
+    descriptorMap.insert_or_assign(key, desc);
+}
+
+bool SnapshotRegistry::deviceDescriptorExists(const std::string& key)
+{
+    std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+    return descriptorMap.find(key) != descriptorMap.end();
+}
+
+DeviceSnapshotDescriptor SnapshotRegistry::getDeviceDescriptor(const std::string& key)
+{
+    std::shared_lock<std::shared_mutex> lock(snapshotsMx);
+    auto it = descriptorMap.find(key);
+    if (it == descriptorMap.end()) {
+        throw std::runtime_error("Device snapshot descriptor doesn't exist");
+    }
+    return it->second;
 }
 
 void SnapshotRegistry::registerDeviceSnapshot(const std::string& key, std::shared_ptr<DeviceSnapshot> data)
@@ -102,6 +143,7 @@ void SnapshotRegistry::deleteDeviceSnapshot(const std::string& key)
 {
     std::unique_lock<std::shared_mutex> lock(snapshotsMx);
     deviceMap.erase(key);
+    descriptorMap.erase(key);
 }
 
 void SnapshotRegistry::clear()
@@ -109,6 +151,7 @@ void SnapshotRegistry::clear()
     std::unique_lock<std::shared_mutex> lock(snapshotsMx);
     snapshotMap.clear();
     deviceMap.clear();
+    descriptorMap.clear();
 }
 
 // On-disk checkpoints: "<hex(key)>.snap" for host images, ".dsnap" for images
@@ -220,6 +263,13 @@ static std::vector<std::pair<std::string, std::shared_ptr<SnapshotData>>> snapsh
 static std::vector<std::pair<std::string, std::shared_ptr<MockSnapshotUpdate>>> snapshotDiffPushes;
 static std::vector<std::pair<std::string, std::string>> snapshotDeletes;
 static std::vector<std::pair<std::string, std::tuple<int, int, std::string, int>>> threadResults;
+static std::vector<std::tuple<std::string, std::string, DeviceSnapshotDescriptor>> deviceSnapshotPushes;
+
+std::vector<std::tuple<std::string, std::string, DeviceSnapshotDescriptor>> getDeviceSnapshotPushes()
+{
+    std::lock_guard<std::mutex> lk(mockMutex);
+    return deviceSnapshotPushes;
+}
 
 std::vector<std::pair<std::string, std::shared_ptr<SnapshotData>>> getSnapshotPushes()
 {
@@ -252,6 +302,7 @@ void clearMockSnapshotRequests()
     snapshotDiffPushes.clear();
     snapshotDeletes.clear();
     threadResults.clear();
+    deviceSnapshotPushes.clear();
 }
 
 static thread_local std::unordered_map<std::string, std::shared_ptr<SnapshotClient>> tlsSnapClients;
@@ -300,6 +351,18 @@ static void fillDiffs(faabric::proto::RepeatedField<faabric::SnapshotDiffRequest
     }
 }
 
+bool SnapshotClient::receiverSharesRegistry(const std::string& key, const std::shared_ptr<SnapshotData>& data)
+{
+    // served from this process? (virtual hosts of one worker, in-process planner)
+    auto addr = faabric::transport::parseHostAddress(host); // resolves virtual host names
+    if (!faabric::transport::isLocalAddress(addr.ip) ||
+        faabric::transport::MessageEndpointServer::findLocal(SNAPSHOT_SYNC_PORT + addr.portOffset, true) == nullptr) {
+        return false;
+    }
+    auto& reg = getSnapshotRegistry();
+    return reg.snapshotExists(key) && reg.getSnapshot(key) == data;
+}
+
 void SnapshotClient::pushSnapshot(const std::string& key, std::shared_ptr<SnapshotData> data)
 {
     if (data->getSize() == 0) {
@@ -310,6 +373,13 @@ void SnapshotClient::pushSnapshot(const std::string& key, std::shared_ptr<Snapsh
     if (faabric::util::isMockMode()) {
         std::lock_guard<std::mutex> lk(mockMutex);
         snapshotPushes.emplace_back(host, data);
+        return;
+    }
+    if (receiverSharesRegistry(key, data)) {
+        // The destination is another (virtual) host of THIS worker: it reads
+        // the same registry, and replacing the object under the key would cut
+        // the owner off from the diffs queued on it
+        SPDLOG_DEBUG("Snapshot {} already visible to {} (same worker)", key, host);
         return;
     }
     faabric::SnapshotPushRequest req;
@@ -326,6 +396,9 @@ void SnapshotClient::pushSnapshotUpdate(std::string snapshotKey,
                                         const std::vector<SnapshotDiff>& diffs)
 {
     SPDLOG_DEBUG("Pushing update to snapshot {} to {} ({} diffs)", snapshotKey, host, diffs.size());
+    if (!faabric::util::isMockMode() && receiverSharesRegistry(snapshotKey, data)) {
+        return; // same object: the tracked changes are already in it
+    }
     if (faabric::util::isMockMode()) {
         auto upd = std::make_shared<MockSnapshotUpdate>();
         for (const auto& d : diffs) {
@@ -379,6 +452,50 @@ void SnapshotClient::pushThreadResult(uint32_t appId,
     syncSend(SnapshotCalls::ThreadResult, &req, &resp);
 }
 
+void SnapshotClient::pushDeviceSnapshot(const std::string& key, const DeviceSnapshotDescriptor& desc)
+{
+    SPDLOG_DEBUG("Pushing device snapshot descriptor {} to {} ({} bytes stay on GPU {})", key, host, desc.size, desc.device);
+    if (faabric::util::isMockMode()) {
+        std::lock_guard<std::mutex> lk(mockMutex);
+        deviceSnapshotPushes.emplace_back(host, key, desc);
+        return;
+    }
+    faabric::SnapshotPushRequest req;
+    req.set_key(key);
+    req.set_deviceresident(true);
+    req.set_devicesize(desc.size);
+    req.set_deviceid(desc.device);
+    req.set_ownerpid(desc.ownerPid);
+    req.set_deviceptr(desc.devicePtr);
+    req.set_ipchandle(desc.ipcHandle.data(), desc.ipcHandle.size());
+    fillRegions(req.mutable_mergeregions(), desc.mergeRegions);
+    faabric::EmptyResponse resp;
+    syncSend(SnapshotCalls::PushSnapshot, &req, &resp);
+}
+
+void SnapshotClient::pushDeviceThreadResult(uint32_t appId,
+                                            uint32_t messageId,
+                                            int returnValue,
+                                            const std::string& key,
+                                            uint64_t diffBytes)
+{
+    if (faabric::util::isMockMode()) {
+        std::lock_guard<std::mutex> lk(mockMutex);
+        threadResults.emplace_back(host, std::make_tuple((int)messageId, returnValue, key, 0));
+        return;
+    }
+    SPDLOG_DEBUG("Sending thread result for {} to {} ({} bytes already merged on the device)", messageId, host, diffBytes);
+    faabric::ThreadResultRequest req;
+    req.set_appid((int32_t)appId);
+    req.set_messageid((int32_t)messageId);
+    req.set_returnvalue(returnValue);
+    req.set_key(key);
+    req.set_devicemerged(true);
+    req.set_devicediffbytes(diffBytes);
+    faabric::EmptyResponse resp;
+    syncSend(SnapshotCalls::ThreadResult, &req, &resp);
+}
+
 // ---------------------------------------------------------------------------
 // Server
 // ---------------------------------------------------------------------------
@@ -420,6 +537,22 @@ std::string SnapshotServer::recvPushSnapshot(std::span<const uint8_t> buffer)
     faabric::SnapshotPushRequest r;
     if (!r.ParseFromArray(buffer.data(), (int)buffer.size())) {
         throw std::runtime_error("Could not parse snapshot push");
+    }
+    if (r.deviceresident()) {
+        // Control descriptor only: the image stays where it is (HBM of a GPU
+        // of this box); it is mapped on first use
+        DeviceSnapshotDescriptor d;
+        d.size = r.devicesize();
+        d.device = r.deviceid();
+        d.ownerPid = r.ownerpid();
+        d.devicePtr = r.deviceptr();
+        d.ipcHandle.assign(r.ipchandle().data(), r.ipchandle().size());
+        for (const auto& mr : r.mergeregions()) {
+            d.mergeRegions.emplace_back(mr.offset(), mr.length(), (SnapshotDataType)mr.datatype(), (SnapshotMergeOperation)mr.mergeop());
+        }
+        SPDLOG_DEBUG("Receiving device snapshot descriptor {} ({} bytes on GPU {} of pid {})", r.key(), d.size, d.device, d.ownerPid);
+        reg.registerDeviceDescriptor(r.key(), d);
+        return faabric::EmptyResponse().SerializeAsString();
     }
     if (r.contents().empty()) {
         SPDLOG_ERROR("Received shapshot {} with zero size", r.key());
@@ -550,7 +683,59 @@ DeviceSnapshot::DeviceSnapshot(uint8_t* devicePtr, size_t sizeIn, int deviceIn)
     statsDev = faabric::util::allocateDeviceMemory(64, device);
 }
 
-DeviceSnapshot::~DeviceSnapshot() = default;
+DeviceSnapshot::~DeviceSnapshot()
+{
+    if (ipcMapped != nullptr) {
+        cudaIpcCloseMemHandle(ipcMapped);
+        cudaGetLastError();
+    }
+}
+
+static std::atomic<uint64_t> globalDiffPushCount{ 0 };
+
+uint64_t DeviceSnapshot::getGlobalDiffPushCount()
+{
+    return globalDiffPushCount.load();
+}
+
+DeviceSnapshotDescriptor DeviceSnapshot::describe()
+{
+    DeviceSnapshotDescriptor d;
+    d.size = size;
+    d.device = device;
+    d.ownerPid = (int)::getpid();
+    d.devicePtr = (uint64_t)(uintptr_t)image;
+    d.mergeRegions = getMergeRegions();
+    if (owned.ptr != nullptr && ipcMapped == nullptr) {
+        DeviceGuard g(device);
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, image) == cudaSuccess) {
+            d.ipcHandle.assign((const char*)&h, sizeof(h));
+        } else {
+            cudaGetLastError(); // e.g. VMM-backed memory: same-process use only
+        }
+    }
+    return d;
+}
+
+std::shared_ptr<DeviceSnapshot> DeviceSnapshot::fromDescriptor(const DeviceSnapshotDescriptor& desc)
+{
+    if (desc.ipcHandle.size() != sizeof(cudaIpcMemHandle_t)) {
+        throw std::runtime_error("Device snapshot descriptor carries no IPC handle");
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, desc.ipcHandle.data(), sizeof(h));
+    void* p = nullptr;
+    DS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    int cur = 0;
+    cudaGetDevice(&cur);
+    auto snap = std::make_shared<DeviceSnapshot>((uint8_t*)p, (size_t)desc.size, cur);
+    snap->ipcMapped = p;
+    for (const auto& r : desc.mergeRegions) {
+        snap->addMergeRegion(r.offset, r.length, r.dataType, r.operation);
+    }
+    return snap;
+}
 
 void DeviceSnapshot::copyInData(std::span<const uint8_t> hostData, uint64_t offset)
 {
@@ -700,6 +885,8 @@ void DeviceSnapshot::diffAndPush(const uint8_t* mem,
     a.stats = (uint64_t*)statsDev.ptr;
     a.updateBase = updateBase ? 1 : 0;
     DS_CUDA(fb::launchSnapshotDiffPush(a, 296, (cudaStream_t)stream));
+    diffPushCount++;
+    globalDiffPushCount.fetch_add(1);
 }
 
 DeviceDiffStats DeviceSnapshot::getLastStats(void* stream)

@@ -54,6 +54,20 @@ std::string resolveHostAlias(const std::string& host)
     return it == hostAliases.end() ? host : it->second;
 }
 
+bool isHostAlias(const std::string& host)
+{
+    std::shared_lock<std::shared_mutex> lk(aliasMx);
+    return hostAliases.find(host) != hostAliases.end();
+}
+
+bool sameWorker(const std::string& hostA, const std::string& hostB)
+{
+    if (hostA.empty() || hostB.empty()) {
+        return false;
+    }
+    return resolveHostAlias(hostA) == resolveHostAlias(hostB);
+}
+
 HostAddress parseHostAddress(const std::string& hostIn)
 {
     HostAddress a;

@@ -9,6 +9,9 @@
 #include <cstdio>
 #include <cstring>
 
+// Helper processes of tests that need a second process (test_threads_device.cpp)
+int ipcMapChildMain(const char* hexHandle, const char* size);
+
 namespace fbtest {
 std::vector<TestCase>& registry()
 {
@@ -29,6 +32,9 @@ int main(int argc, char** argv)
     faabric::util::setTestMode(true);
     faabric::util::initLogging();
 
+    if (argc == 4 && !strcmp(argv[1], "--ipc-map-child")) {
+        return ipcMapChildMain(argv[2], argv[3]);
+    }
     bool list = false;
     std::string tag;
     std::vector<std::string> filters;

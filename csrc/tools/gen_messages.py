@@ -106,10 +106,10 @@ FAABRIC = dict(
         # src/flat/faabric.fbs:1-38; offsets widened to 64 bit here) ---
         dict(name="SnapshotMergeRegionRequest", fields=[F("offset", "uint64", 1), F("length", "uint64", 2), F("dataType", "int32", 3, "data_type"), F("mergeOp", "int32", 4, "merge_op")]),
         dict(name="SnapshotDiffRequest", fields=[F("offset", "uint64", 1), F("dataType", "int32", 2, "data_type"), F("mergeOp", "int32", 3, "merge_op"), F("data", "bytes", 4)]),
-        dict(name="SnapshotPushRequest", fields=[F("key", "string", 1), F("maxSize", "uint64", 2, "max_size"), F("contents", "bytes", 3), F("mergeRegions", "msg:SnapshotMergeRegionRequest", 4, "merge_regions", rep=True), F("deviceResident", "bool", 5), F("devicePtr", "uint64", 6), F("deviceId", "int32", 7)]),
+        dict(name="SnapshotPushRequest", fields=[F("key", "string", 1), F("maxSize", "uint64", 2, "max_size"), F("contents", "bytes", 3), F("mergeRegions", "msg:SnapshotMergeRegionRequest", 4, "merge_regions", rep=True), F("deviceResident", "bool", 5), F("devicePtr", "uint64", 6), F("deviceId", "int32", 7), F("ownerPid", "int32", 8, "owner_pid"), F("ipcHandle", "bytes", 9, "ipc_handle"), F("deviceSize", "uint64", 10, "device_size")]),
         dict(name="SnapshotDeleteRequest", fields=[F("key", "string", 1)]),
         dict(name="SnapshotUpdateRequest", fields=[F("key", "string", 1), F("mergeRegions", "msg:SnapshotMergeRegionRequest", 2, "merge_regions", rep=True), F("diffs", "msg:SnapshotDiffRequest", 3, rep=True)]),
-        dict(name="ThreadResultRequest", fields=[F("appId", "int32", 1, "app_id"), F("messageId", "int32", 2, "message_id"), F("returnValue", "int32", 3, "return_value"), F("key", "string", 4), F("diffs", "msg:SnapshotDiffRequest", 5, rep=True)]),
+        dict(name="ThreadResultRequest", fields=[F("appId", "int32", 1, "app_id"), F("messageId", "int32", 2, "message_id"), F("returnValue", "int32", 3, "return_value"), F("key", "string", 4), F("diffs", "msg:SnapshotDiffRequest", 5, rep=True), F("deviceMerged", "bool", 6, "device_merged"), F("deviceDiffBytes", "uint64", 7, "device_diff_bytes")]),
     ],
 )
 
