@@ -520,7 +520,8 @@ void Executor::executeTasks(std::vector<int> msgIdxs,
                 restore(key);
             }
             std::span<uint8_t> memView = getMemoryView();
-            tracker->clearAll();
+            // (startTracking resets this region's record; clearAll would also
+            // wipe the records of executors of other virtual hosts)
             tracker->startTracking(memView);
             threadLocalDirtyRegions.clear();
             dirtyRegions.clear();

@@ -99,7 +99,7 @@ std::vector<char> NoneDirtyTracker::getBothDirtyPages(std::span<uint8_t> region)
 
 // ---------------------------------------------------------------------------
 // Shared record of the region currently being tracked by fault-driven
-// trackers.  One tracked region per process at a time (like the reference),
+// trackers.  Process-wide records live in a table (RegionTable below),
 // plus a thread-local record for per-thread attribution.
 // ---------------------------------------------------------------------------
 namespace {
@@ -153,7 +153,93 @@ struct TrackingRecord
     }
 };
 
-TrackingRecord globalRecord;
+// Process-wide records: one per tracked region.  A worker that serves several
+// per-GPU virtual hosts runs several executors side by side, each tracking its
+// own function memory (the reference tracks one region per process).  Fixed
+// slots, published by storing regionBase last, so the SIGSEGV handler can walk
+// the table without locks or allocation.
+struct RegionTable
+{
+    static constexpr int SLOTS = 64;
+    TrackingRecord slots[SLOTS];
+    std::mutex mx; // writers only (never taken in a signal handler)
+
+    TrackingRecord* find(const void* addr)
+    {
+        for (auto& r : slots) {
+            uint8_t* base = __atomic_load_n(&r.regionBase, __ATOMIC_ACQUIRE);
+            if (base != nullptr && addr >= base && addr < r.regionTop) {
+                return &r;
+            }
+        }
+        return nullptr;
+    }
+
+    void reset(std::span<uint8_t> region)
+    {
+        std::lock_guard<std::mutex> lk(mx);
+        TrackingRecord* slot = nullptr;
+        for (auto& r : slots) {
+            if (r.regionBase == region.data()) {
+                slot = &r;
+                break;
+            }
+        }
+        if (slot == nullptr) {
+            for (auto& r : slots) {
+                if (r.regionBase == nullptr) {
+                    slot = &r;
+                    break;
+                }
+            }
+        }
+        if (slot == nullptr) {
+            throw std::runtime_error("Too many regions under dirty tracking");
+        }
+        // unpublish, rebuild, publish
+        __atomic_store_n(&slot->regionBase, (uint8_t*)nullptr, __ATOMIC_RELEASE);
+        TrackingRecord fresh;
+        fresh.reset(region);
+        slot->regionTop = fresh.regionTop;
+        slot->nPages = fresh.nPages;
+        slot->flags = std::move(fresh.flags);
+        __atomic_store_n(&slot->regionBase, region.data(), __ATOMIC_RELEASE);
+    }
+
+    void clear()
+    {
+        std::lock_guard<std::mutex> lk(mx);
+        for (auto& r : slots) {
+            __atomic_store_n(&r.regionBase, (uint8_t*)nullptr, __ATOMIC_RELEASE);
+            r.clear();
+        }
+    }
+
+    void release(std::span<uint8_t> region)
+    {
+        std::lock_guard<std::mutex> lk(mx);
+        for (auto& r : slots) {
+            if (r.regionBase == region.data()) {
+                // keep the flags readable until the next reset of the slot
+                return;
+            }
+        }
+    }
+
+    std::vector<char> snapshot(std::span<uint8_t> region)
+    {
+        const size_t want = getRequiredHostPages(region.size());
+        std::lock_guard<std::mutex> lk(mx);
+        for (auto& r : slots) {
+            if (r.regionBase == region.data()) {
+                return r.snapshot(want);
+            }
+        }
+        return std::vector<char>(want, 0);
+    }
+};
+
+RegionTable globalRecords;
 thread_local TrackingRecord threadRecord;
 }
 
@@ -176,11 +262,11 @@ void SegfaultDirtyTracker::handler(int sig, void* infoV, void* context) noexcept
         threadRecord.mark(faultAddr);
         handled = true;
     }
-    if (globalRecord.regionBase != nullptr && globalRecord.contains(faultAddr)) {
+    if (TrackingRecord* rec = globalRecords.find(faultAddr)) {
         // Only attribute to the global record when no thread-local tracking
         // is active for this thread (matches the reference's split)
         if (!handled) {
-            globalRecord.mark(faultAddr);
+            rec->mark(faultAddr);
         }
         handled = true;
     }
@@ -220,7 +306,7 @@ void SegfaultDirtyTracker::setUpSignalHandler()
 
 void SegfaultDirtyTracker::clearAll()
 {
-    globalRecord.clear();
+    globalRecords.clear();
     threadRecord.clear();
 }
 
@@ -230,7 +316,10 @@ void SegfaultDirtyTracker::startTracking(std::span<uint8_t> region)
         return;
     }
     PROF_START(MprotectStart)
-    globalRecord.reset(region);
+    // (a crash handler installed after this tracker was created would have
+    // taken SIGSEGV over: make sure our handler is in front, chaining to it)
+    setUpSignalHandler();
+    globalRecords.reset(region);
     if (::mprotect(region.data(), region.size(), PROT_READ) != 0) {
         SPDLOG_ERROR("Failed to start tracking with mprotect: {}", strerror(errno));
         throw std::runtime_error("Failed mprotect to start tracking");
@@ -251,7 +340,7 @@ void SegfaultDirtyTracker::stopTracking(std::span<uint8_t> region)
 
 std::vector<char> SegfaultDirtyTracker::getDirtyPages(std::span<uint8_t> region)
 {
-    return globalRecord.snapshot(getRequiredHostPages(region.size()));
+    return globalRecords.snapshot(region);
 }
 
 void SegfaultDirtyTracker::startThreadLocalTracking(std::span<uint8_t> region)
@@ -433,8 +522,8 @@ struct UffdDirtyTracker::Impl
             void* addr = (void*)(uintptr_t)msg.arg.pagefault.address;
             {
                 std::lock_guard<std::mutex> lk(recordMx);
-                if (globalRecord.regionBase != nullptr && globalRecord.contains(addr)) {
-                    globalRecord.mark(addr);
+                if (TrackingRecord* rec = globalRecords.find(addr)) {
+                    rec->mark(addr);
                 }
             }
             // Drop write protection on the page and wake the faulting thread
@@ -526,7 +615,7 @@ UffdDirtyTracker::~UffdDirtyTracker()
 void UffdDirtyTracker::clearAll()
 {
     std::lock_guard<std::mutex> lk(impl->recordMx);
-    globalRecord.clear();
+    globalRecords.clear();
     threadRecord.clear();
 }
 
@@ -537,7 +626,7 @@ void UffdDirtyTracker::startTracking(std::span<uint8_t> region)
     }
     {
         std::lock_guard<std::mutex> lk(impl->recordMx);
-        globalRecord.reset(region);
+        globalRecords.reset(region);
         impl->tracked = region;
     }
     size_t len = getRequiredHostPages(region.size()) * HOST_PAGE_SIZE;
@@ -574,7 +663,7 @@ void UffdDirtyTracker::stopTracking(std::span<uint8_t> region)
 
 std::vector<char> UffdDirtyTracker::getDirtyPages(std::span<uint8_t> region)
 {
-    return globalRecord.snapshot(getRequiredHostPages(region.size()));
+    return globalRecords.snapshot(region);
 }
 
 void UffdDirtyTracker::startThreadLocalTracking(std::span<uint8_t> region) {}
