@@ -708,6 +708,43 @@ int fb_dirty_scan(const void* mem,
              : FB_E_CUDA;
 }
 
+// ---- device-resident state: fused dirty scan + push + mask clear ----
+int fb_state_push_dirty(void* mask,
+                        const void* src,
+                        void* dst,
+                        uint64_t size,
+                        void* statsDev,
+                        int blocks,
+                        void* stream)
+{
+    return fb::launchStatePushDirty((uint8_t*)mask,
+                                    (const uint8_t*)src,
+                                    (uint8_t*)dst,
+                                    size,
+                                    (uint64_t*)statsDev,
+                                    blocks,
+                                    (cudaStream_t)stream) == cudaSuccess
+             ? FB_OK
+             : FB_E_CUDA;
+}
+
+int fb_state_flag_range(void* mask, uint64_t offset, uint64_t length, void* stream)
+{
+    if (length == 0) {
+        return FB_OK;
+    }
+    uint64_t b0 = offset / FB_STATE_BLOCK_BYTES;
+    uint64_t b1 = (offset + length - 1) / FB_STATE_BLOCK_BYTES;
+    return fb::launchStateFlagRange((uint8_t*)mask, b0, b1 - b0 + 1, (cudaStream_t)stream) == cudaSuccess
+             ? FB_OK
+             : FB_E_CUDA;
+}
+
+int fb_state_block_bytes()
+{
+    return FB_STATE_BLOCK_BYTES;
+}
+
 int fb_flags_or(void* dst, const void* src, uint64_t n, void* stream)
 {
     return fb::launchFlagsOr(

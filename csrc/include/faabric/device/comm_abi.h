@@ -32,17 +32,19 @@ extern "C" {
 #define FB_SIG_MBOX_OFF (FB_SIG_EPOCH_OFF + FB_MAX_BLOCKS)
 // Point-to-point: per ordered pair (src -> dst)
 //   ready[src]   in dst's pad : sequence number of the last message posted
-//   desc[src][k] in dst's pad : {offLo, offHi, lenLo, lenHi} of message k % RING
+//   desc[src][k] in dst's HEAP: {offLo, offHi, lenLo, lenHi} of message k % RING
+//                               (FB_P2P_RING entries per source, 16 bytes each)
 //   ack[dst]     in src's pad : sequence number of the last message pulled
 //   done[2][peer] local       : CTA completion counters of the send / pull kernels
 // The payload itself stays in the SENDER's symmetric heap (bounce ring or the
 // user's own symmetric buffer); the receiver pulls it over NVLink.
-#define FB_P2P_RING 4
+#define FB_P2P_RING 64
 #define FB_P2P_READY_OFF FB_SIG_MBOX_OFF
 #define FB_P2P_ACK_OFF (FB_P2P_READY_OFF + FB_MAX_RANKS)
 #define FB_P2P_DONE_OFF (FB_P2P_ACK_OFF + FB_MAX_RANKS)
-#define FB_P2P_DESC_OFF (FB_P2P_DONE_OFF + 2 * FB_MAX_RANKS)
-#define FB_P2P_WORDS (4 * FB_MAX_RANKS + FB_MAX_RANKS * FB_P2P_RING * 4)
+#define FB_P2P_WORDS (4 * FB_MAX_RANKS)
+// bytes of descriptor ring area in every rank's heap
+#define FB_P2P_DESC_BYTES (FB_MAX_RANKS * FB_P2P_RING * 16)
 #define FB_SIG_USER_OFF (FB_SIG_MBOX_OFF + 512)
 // user signals (put-with-signal): value words then consumed-count words
 #define FB_SIG_USER_WORDS 256

@@ -15,6 +15,7 @@
 
 #include <cstdint>
 #include <cstddef>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -290,8 +291,19 @@ class Communicator
 
     // heap layout (offsets from heap base)
     uint64_t llOff_ = 0;
-    uint64_t mboxOff_ = 0; // p2p bounce rings: [peer][2 slots]
-    uint64_t bounceSlotBytes_ = 0;
+    uint64_t mboxOff_ = 0; // p2p bounce rings: one byte ring per destination
+    uint64_t p2pDescOff_ = 0; // descriptor rings written by the senders
+    uint64_t bounceSlotBytes_ = 0; // largest single eager message (ring / 2)
+    // host model of every destination's byte ring: messages issued whose
+    // release (ack) has not been waited for yet, oldest first
+    struct BounceMsg
+    {
+        uint32_t seq;
+        uint64_t off;
+        uint64_t len;
+    };
+    std::deque<BounceMsg> bounceInflight_[FB_MAX_RANKS];
+    uint64_t bounceHead_[FB_MAX_RANKS] = { 0 };
     uint32_t sendSeq_[FB_MAX_RANKS] = { 0 };
     uint32_t recvSeq_[FB_MAX_RANKS] = { 0 };
     uint32_t sbarEpoch_[FB_MAX_CHANNELS] = { 0 };

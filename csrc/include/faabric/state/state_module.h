@@ -548,6 +548,111 @@ class RedisStateKeyValue final : public StateKeyValue
 }
 
 // ==========================================================================
+// state/DeviceStateKeyValue.h
+// ==========================================================================
+namespace faabric::state {
+
+struct DeviceStateRun
+{
+    uint64_t offset;
+    uint64_t length;
+};
+
+// A state value whose authoritative bytes live in HBM of the GPU that first
+// claimed the key (the "main" GPU, the role of the main host in the
+// reference).  Other GPUs hold replicas and move data with device copies over
+// NVLink: lazy chunk pulls are peer copies, a partial push is ONE kernel that
+// scans a device-resident dirty mask (one byte per 128-byte block), stores the
+// dirty blocks straight into the main copy and clears the mask.  The host sees
+// the value through a pinned mirror that is filled on demand.
+// (Reference counterpart: StateKeyValue pull / push / dirty-chunk scan,
+// src/state/StateKeyValue.cpp:61,394-543,592-629.)
+class DeviceStateKeyValue
+{
+  public:
+    DeviceStateKeyValue(std::string userIn,
+                        std::string keyIn,
+                        size_t sizeIn,
+                        int deviceIn,
+                        std::shared_ptr<DeviceStateKeyValue> mainIn);
+
+    ~DeviceStateKeyValue();
+
+    const std::string user;
+    const std::string key;
+
+    size_t size() const { return valueSize; }
+
+    int getDevice() const { return device; }
+
+    bool isMain() const { return main == nullptr; }
+
+    // Device pointer of this GPU's copy (the value itself on the main GPU)
+    uint8_t* getDevicePtr() { return data.ptr; }
+
+    // ---- replica <- main ----
+    void pull(void* stream = nullptr);
+
+    // Lazy: copies only the 64 KiB chunks of [offset, offset+len) this replica
+    // has not pulled yet
+    void pullChunk(long offset, size_t length, void* stream = nullptr);
+
+    bool isChunkPulled(long offset, size_t length);
+
+    // ---- replica -> main ----
+    // Mark [offset, offset+len) as written on this GPU (device-resident mask;
+    // user kernels may also set mask bytes themselves: getDirtyMaskPtr())
+    void flagChunkDirty(long offset, long len, void* stream = nullptr);
+
+    void flagDirty(void* stream = nullptr);
+
+    uint8_t* getDirtyMaskPtr() { return mask.ptr; }
+
+    // Fused dirty scan + push + clear.  Returns the number of bytes pushed
+    // (block granularity); synchronises `stream`.
+    uint64_t pushPartial(void* stream = nullptr);
+
+    void pushFull(void* stream = nullptr);
+
+    // Dirty runs (block granularity) without pushing: device scan kernel
+    std::vector<DeviceStateRun> getDirtyChunks(void* stream = nullptr);
+
+    // ---- host access (pinned mirror, filled / flushed on demand) ----
+    void get(uint8_t* buffer);
+
+    void getChunk(long offset, uint8_t* buffer, size_t length);
+
+    void set(const uint8_t* buffer);
+
+    void setChunk(long offset, const uint8_t* buffer, size_t length);
+
+    // Pinned host view of the whole value as of now (D2H copy of what changed
+    // since the last call is not tracked: the whole value is refreshed)
+    uint8_t* syncHostMirror(void* stream = nullptr);
+
+    uint64_t getPushKernelLaunches() const { return pushLaunches; }
+
+    uint64_t getBytesPulled() const { return bytesPulled; }
+
+  private:
+    size_t valueSize;
+    int device;
+    std::shared_ptr<DeviceStateKeyValue> main; // null on the main copy
+    faabric::util::DeviceRegion data;
+    faabric::util::DeviceRegion mask;  // one byte per FB_STATE_BLOCK_BYTES
+    faabric::util::DeviceRegion stats; // 16 bytes
+    faabric::util::DeviceRegion hostMirror; // pinned, lazy
+    std::vector<uint8_t> pulledChunks; // per STATE_STREAMING_CHUNK_SIZE
+    std::mutex mx;
+    uint64_t pushLaunches = 0;
+    uint64_t bytesPulled = 0;
+
+    void checkRange(long offset, size_t length) const;
+};
+
+}
+
+// ==========================================================================
 // state/State.h
 // ==========================================================================
 #define STATE_INPROC_LABEL_KV "state-kv"
@@ -589,6 +694,19 @@ class State
 
     size_t getKVCount();
 
+    // ---- device-resident values ----
+    // The first GPU to ask for user/key becomes its main GPU; later callers on
+    // other GPUs get replicas that talk to it over NVLink.  One object per
+    // (key, device).
+    std::shared_ptr<DeviceStateKeyValue> getDeviceKV(const std::string& user,
+                                                    const std::string& key,
+                                                    size_t size,
+                                                    int device);
+
+    void deleteDeviceKV(const std::string& user, const std::string& key);
+
+    size_t getDeviceKVCount();
+
     std::string getThisIP();
 
   private:
@@ -596,6 +714,9 @@ class State
 
     std::unordered_map<std::string, std::shared_ptr<StateKeyValue>> kvMap;
     std::shared_mutex mapMutex;
+    // "user_key" -> per-device copies; entry -1 names the main device
+    std::unordered_map<std::string, std::map<int, std::shared_ptr<DeviceStateKeyValue>>> deviceKvMap;
+    std::unordered_map<std::string, int> deviceKvMain;
 
     std::shared_ptr<StateKeyValue> doGetKV(const std::string& user,
                                            const std::string& key,

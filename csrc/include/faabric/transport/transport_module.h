@@ -693,6 +693,12 @@ namespace faabric::transport {
 
 class PointToPointBroker;
 
+}
+namespace faabric::device {
+class Communicator;
+}
+namespace faabric::transport {
+
 class PointToPointGroup
 {
   public:
@@ -724,7 +730,15 @@ class PointToPointGroup
 
     bool localTryLock();
 
+    // All members on GPU hosts with a device communicator attached
+    // (PointToPointBroker::createLocalDeviceGroup / joinDeviceGroup): the
+    // barrier is a device barrier (flag exchange over NVLink), stream-ordered;
+    // otherwise the message-based barrier of the reference
+    // (src/transport/PointToPointBroker.cpp:317-379)
     void barrier(int groupIdx);
+
+    // Stream-ordered variant: returns without synchronising `stream`
+    void deviceBarrier(int groupIdx, void* stream);
 
     void notify(int groupIdx);
 
@@ -821,6 +835,40 @@ class PointToPointBroker
 
     void postMigrationHook(int groupId, int groupIdx);
 
+    // ---- device data plane: group idx <-> GPU ----
+    // Messages whose payload lives in HBM move with the communicator's
+    // point-to-point kernels (eager send into the sender's heap + pull over
+    // NVLink).  Per (sender, receiver) FIFO ordering is inherent, so the
+    // reference's sequence numbers / out-of-order buffer
+    // (src/transport/PointToPointBroker.cpp:557-600,778-859) are not needed.
+    //
+    // All members in this process (one worker serving per-GPU virtual hosts):
+    // devices[i] is the GPU of group idx i; empty => taken from the host names
+    // of the group's mappings ("gpuN" -> N).
+    void createLocalDeviceGroup(int groupId, std::vector<int> devices = {});
+
+    // One member per process: collective call, every idx joins
+    void joinDeviceGroup(int groupId, int groupIdx, int groupSize, int device);
+
+    bool isDeviceGroup(int groupId);
+
+    std::shared_ptr<faabric::device::Communicator> getDeviceCommunicator(int groupId, int groupIdx);
+
+    // Stream-ordered; the buffers are device pointers
+    void sendDeviceMessage(int groupId,
+                           int sendIdx,
+                           int recvIdx,
+                           const void* deviceBuffer,
+                           size_t bufferSize,
+                           void* stream);
+
+    void recvDeviceMessage(int groupId,
+                           int sendIdx,
+                           int recvIdx,
+                           void* deviceBuffer,
+                           size_t bufferSize,
+                           void* stream);
+
     // Delivery into the local mailbox of (group, send, recv); used by the
     // server for messages that arrive from other hosts
     void deliverLocally(int groupId,
@@ -841,6 +889,9 @@ class PointToPointBroker
 
     std::unordered_map<int, std::shared_ptr<faabric::util::FlagWaiter>>
       groupFlags;
+
+    // groupId -> communicator of every idx served by this process
+    std::unordered_map<int, std::map<int, std::shared_ptr<faabric::device::Communicator>>> deviceComms;
 
     // Sender side sequence counters, keyed by (group, send, recv)
     std::mutex seqMx;

@@ -326,12 +326,12 @@ __global__ void __launch_bounds__(512, 1) p2pSendKernel(const P2PArgs a)
     }
     uint32_t* done = c.sig[c.rank] + FB_P2P_DONE_OFF + a.peer;
     if (lastBlockDone(done) && threadIdx.x == 0) {
-        uint32_t* desc = c.sig[a.peer] + FB_P2P_DESC_OFF +
+        uint32_t* desc = reinterpret_cast<uint32_t*>(c.heap[a.peer] + a.descOff) +
                          ((uint32_t)c.rank * FB_P2P_RING + (a.seq % FB_P2P_RING)) * 4;
-        desc[0] = (uint32_t)(a.srcOff & 0xffffffffu);
-        desc[1] = (uint32_t)(a.srcOff >> 32);
-        desc[2] = (uint32_t)(a.bytes & 0xffffffffu);
-        desc[3] = (uint32_t)(a.bytes >> 32);
+        stRelaxedSys(desc + 0, (uint32_t)(a.srcOff & 0xffffffffu));
+        stRelaxedSys(desc + 1, (uint32_t)(a.srcOff >> 32));
+        stRelaxedSys(desc + 2, (uint32_t)(a.bytes & 0xffffffffu));
+        stRelaxedSys(desc + 3, (uint32_t)(a.bytes >> 32));
         // release: payload (local HBM) and descriptor are visible before seq
         stReleaseSys(c.sig[a.peer] + FB_P2P_READY_OFF + c.rank, a.seq);
     }
@@ -345,10 +345,10 @@ __global__ void __launch_bounds__(512, 1) p2pPullKernel(const P2PArgs a)
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
     // the stream-level wait already saw seq; the acquire orders the reads below
     const uint32_t seen = ldAcquireSys(c.sig[c.rank] + FB_P2P_READY_OFF + a.peer);
-    const uint32_t* desc = c.sig[c.rank] + FB_P2P_DESC_OFF +
+    const uint32_t* desc = reinterpret_cast<const uint32_t*>(c.heap[c.rank] + a.descOff) +
                            ((uint32_t)a.peer * FB_P2P_RING + (a.seq % FB_P2P_RING)) * 4;
-    const uint64_t srcOff = (uint64_t)desc[0] | ((uint64_t)desc[1] << 32);
-    uint64_t len = (uint64_t)desc[2] | ((uint64_t)desc[3] << 32);
+    const uint64_t srcOff = (uint64_t)ldRelaxedSys(desc + 0) | ((uint64_t)ldRelaxedSys(desc + 1) << 32);
+    uint64_t len = (uint64_t)ldRelaxedSys(desc + 2) | ((uint64_t)ldRelaxedSys(desc + 3) << 32);
     bool ok = (int32_t)(seen - a.seq) >= 0 && len <= a.bytes &&
               srcOff + len <= a.heapBytes;
     if (!ok) {

@@ -70,6 +70,9 @@ cudaError_t preloadAllKernels()
         e = preloadNvlsKernels();
     }
     if (e == cudaSuccess) {
+        e = preloadStateKernels();
+    }
+    if (e == cudaSuccess) {
         e = preloadSnapshotKernels();
     }
     return e;

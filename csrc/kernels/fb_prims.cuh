@@ -365,19 +365,27 @@ struct VecReduce
             return reduceVec<T, OP>(a, b);
         }
     }
-    // scalar tail (byte pointers, element index)
+    // scalar tail: `acc` and `in` are byte buffers, so the element is moved
+    // in and out with memcpy (reading a byte array through a T lvalue is
+    // undefined behaviour and was miscompiled in fully unrolled variants)
     __device__ __forceinline__ static void applyTail(uint8_t* acc,
                                                      const uint8_t* in)
     {
         if constexpr (PAIR) {
             using P = PairVI<T>;
-            P a = *reinterpret_cast<P*>(acc);
-            P b = *reinterpret_cast<const P*>(in);
-            *reinterpret_cast<P*>(acc) = reducePair<T, OP>(a, b);
+            P a;
+            P b;
+            memcpy(&a, acc, sizeof(P));
+            memcpy(&b, in, sizeof(P));
+            P r = reducePair<T, OP>(a, b);
+            memcpy(acc, &r, sizeof(P));
         } else {
-            T a = *reinterpret_cast<T*>(acc);
-            T b = *reinterpret_cast<const T*>(in);
-            *reinterpret_cast<T*>(acc) = reduceElem<T, OP>(a, b);
+            T a;
+            T b;
+            memcpy(&a, acc, sizeof(T));
+            memcpy(&b, in, sizeof(T));
+            T r = reduceElem<T, OP>(a, b);
+            memcpy(acc, &r, sizeof(T));
         }
     }
 };

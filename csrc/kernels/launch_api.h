@@ -151,6 +151,7 @@ struct P2PArgs
     uint64_t bytes;     // send: payload bytes; pull: capacity of `local`
     uint64_t srcOff;    // send: symmetric offset the receiver will pull from
     uint64_t heapBytes; // pull: bound for descriptor validation
+    uint64_t descOff;   // symmetric offset of the descriptor rings
     uint32_t seq;       // per ordered pair, starts at 1
     int32_t peer;
     int32_t stage; // send: copy `local` to heap[rank]+srcOff first (0 = zero copy)
@@ -279,6 +280,24 @@ cudaError_t launchSnapshotApply(uint8_t* image,
                                 uint32_t nDescs,
                                 cudaStream_t s);
 
+
+// ----------------------------------------------------------------- state ----
+// dirty mask granularity of device-resident state values
+#define FB_STATE_BLOCK_BYTES 128
+// Fused dirty scan + push + mask clear: every block of `src` whose mask byte is
+// set is copied to `dst` (local or peer-mapped); stats[0] += dirty blocks
+cudaError_t launchStatePushDirty(uint8_t* mask,
+                                 const uint8_t* src,
+                                 uint8_t* dst,
+                                 uint64_t size,
+                                 uint64_t* stats,
+                                 int blocks,
+                                 cudaStream_t s);
+cudaError_t launchStateFlagRange(uint8_t* mask,
+                                 uint64_t firstBlock,
+                                 uint64_t nBlocks,
+                                 cudaStream_t s);
+cudaError_t preloadStateKernels();
 
 // Preload every kernel of the library on the current device (see above)
 cudaError_t preloadAllKernels();

@@ -359,8 +359,9 @@ void Communicator::computeLayout()
     cfg_.slotBytes = roundUp(std::max<size_t>(cfg_.slotBytes, 4096), 4096);
     cfg_.channels = std::clamp(cfg_.channels, 1, FB_MAX_CHANNELS);
     llOff_ = 0;
-    mboxOff_ = roundUp(
+    p2pDescOff_ = roundUp(
       llOff_ + (uint64_t)cfg_.channels * FB_LL_AREA_BYTES(n), 4096);
+    mboxOff_ = roundUp(p2pDescOff_ + FB_P2P_DESC_BYTES, 4096);
     cfg_.p2pBounceBytes =
       roundUp(std::max<size_t>(cfg_.p2pBounceBytes, 64 << 10), 8192);
     bounceSlotBytes_ = cfg_.p2pBounceBytes / 2;
@@ -2199,20 +2200,39 @@ static int p2pBlocks(size_t len)
 int Communicator::sendChunk(const uint8_t* buf, size_t len, int peer, cudaStream_t s)
 {
     const uint32_t seq = ++sendSeq_[peer];
-    if (seq > 2) {
-        // the bounce slot (and descriptor ring entry) of message seq-2 must
-        // have been drained by the receiver
-        int rc = streamWaitGe(s, dev_.sig[dev_.rank] + FB_P2P_ACK_OFF + peer, seq - 2);
+    // ---- space in the byte ring of this destination (FIFO allocation) ----
+    const uint64_t ringBytes = cfg_.p2pBounceBytes;
+    const uint64_t need = roundUp(std::max<size_t>(len, 16), 256);
+    uint64_t off = bounceHead_[peer];
+    if (off + need > ringBytes) {
+        off = 0; // wrap: the tail end of the ring stays unused this lap
+    }
+    auto& inflight = bounceInflight_[peer];
+    uint32_t waitFor = 0;
+    auto overlaps = [&](const BounceMsg& m) { return m.off < off + need && off < m.off + m.len; };
+    while (!inflight.empty() &&
+           (inflight.size() >= FB_P2P_RING - 1 || overlaps(inflight.front()))) {
+        // the oldest message must have been pulled before its bytes (or its
+        // descriptor slot) are reused: wait for its ack, at stream level
+        waitFor = inflight.front().seq;
+        inflight.pop_front();
+    }
+    if (waitFor != 0) {
+        int rc = streamWaitGe(s, dev_.sig[dev_.rank] + FB_P2P_ACK_OFF + peer, waitFor);
         if (rc != FB_OK) {
             return rc;
         }
     }
+    inflight.push_back({ seq, off, need });
+    bounceHead_[peer] = off + need;
+
     fb::P2PArgs a;
     memset(&a, 0, sizeof(a));
     a.comm = dev_;
     a.local = const_cast<uint8_t*>(buf);
     a.bytes = len;
-    a.srcOff = mboxOff_ + ((uint64_t)peer * 2 + (seq & 1)) * bounceSlotBytes_;
+    a.srcOff = mboxOff_ + (uint64_t)peer * ringBytes + off;
+    a.descOff = p2pDescOff_;
     a.seq = seq;
     a.peer = peer;
     a.stage = 1;
@@ -2235,6 +2255,7 @@ int Communicator::recvChunk(uint8_t* buf, size_t len, int peer, cudaStream_t s)
     a.local = buf;
     a.bytes = len;
     a.heapBytes = heapTotal_;
+    a.descOff = p2pDescOff_;
     a.seq = seq;
     a.peer = peer;
     stats_.launches++;

@@ -67,6 +67,8 @@ void State::forceClearAll(bool global)
     }
     std::unique_lock<std::shared_mutex> lock(mapMutex);
     kvMap.clear();
+    deviceKvMap.clear();
+    deviceKvMain.clear();
 }
 
 size_t State::getStateSize(const std::string& user, const std::string& keyIn)

@@ -5,6 +5,10 @@
 #include <faabric/util/config.h>
 #include <faabric/util/logging.h>
 #include <faabric/util/testing.h>
+#include <faabric/device/communicator.h>
+#include <faabric/util/hwloc.h>
+
+#include <cuda_runtime.h>
 
 #include <map>
 
@@ -351,8 +355,30 @@ bool PointToPointGroup::localTryLock()
     return localMx.try_lock();
 }
 
+void PointToPointGroup::deviceBarrier(int groupIdx, void* stream)
+{
+    auto comm = getPointToPointBroker().getDeviceCommunicator(groupId, groupIdx);
+    if (comm == nullptr) {
+        throw std::runtime_error("Group " + std::to_string(groupId) + " idx " + std::to_string(groupIdx) +
+                                 " has no device communicator");
+    }
+    if (comm->barrier((cudaStream_t)stream) != FB_OK) {
+        throw std::runtime_error("Device barrier launch failed");
+    }
+}
+
 void PointToPointGroup::barrier(int groupIdx)
 {
+    PointToPointBroker& devBroker = getPointToPointBroker();
+    if (devBroker.isDeviceGroup(groupId)) {
+        // every member sits on a GPU: meet on the device
+        auto comm = devBroker.getDeviceCommunicator(groupId, groupIdx);
+        deviceBarrier(groupIdx, nullptr);
+        if (!comm->syncStreamBounded(nullptr, (uint64_t)timeoutMs)) {
+            throw std::runtime_error("Device barrier timed out");
+        }
+        return;
+    }
     if (isSingleHost()) {
         localBarrier->wait();
         return;
@@ -635,11 +661,110 @@ std::vector<uint8_t> PointToPointBroker::recvMessage(int groupId,
     }
 }
 
+// ---------------------------------------------------------------------------
+// Device data plane
+// ---------------------------------------------------------------------------
+void PointToPointBroker::createLocalDeviceGroup(int groupId, std::vector<int> devices)
+{
+    std::set<int> idxs = getIdxsRegisteredForGroup(groupId);
+    if (idxs.empty()) {
+        throw std::runtime_error("No mappings for group " + std::to_string(groupId));
+    }
+    const int n = (int)idxs.size();
+    if (*idxs.rbegin() != n - 1) {
+        throw std::runtime_error("Device groups need dense idxs 0..n-1");
+    }
+    if (devices.empty()) {
+        int nGpus = faabric::util::getUsableGpus();
+        for (int i = 0; i < n; i++) {
+            int g = faabric::util::gpuIndexFromHostName(getHostForReceiver(groupId, i));
+            devices.push_back(g >= 0 && nGpus > 0 ? g % nGpus : (nGpus > 0 ? i % nGpus : 0));
+        }
+    }
+    if ((int)devices.size() != n) {
+        throw std::runtime_error("createLocalDeviceGroup: one device per group idx");
+    }
+    faabric::device::CommConfig cfg = faabric::device::CommConfig::fromEnv();
+    cfg.heapBytes = std::min<size_t>(cfg.heapBytes, (size_t)64 << 20); // messaging only
+    cfg.stageBytes = (size_t)1 << 20;
+    auto comms = faabric::device::Communicator::createLocal(n, devices, cfg);
+    std::unique_lock<std::shared_mutex> lk(brokerMutex);
+    auto& slot = deviceComms[groupId];
+    for (int i = 0; i < n; i++) {
+        slot[i] = comms[i];
+    }
+}
+
+void PointToPointBroker::joinDeviceGroup(int groupId, int groupIdx, int groupSize, int device)
+{
+    faabric::device::CommConfig cfg = faabric::device::CommConfig::fromEnv();
+    cfg.heapBytes = std::min<size_t>(cfg.heapBytes, (size_t)64 << 20);
+    cfg.stageBytes = (size_t)1 << 20;
+    auto comm = faabric::device::Communicator::createIpc(
+      groupIdx, groupSize, device, "ptp-group-" + std::to_string(groupId), cfg);
+    std::unique_lock<std::shared_mutex> lk(brokerMutex);
+    deviceComms[groupId][groupIdx] = comm;
+}
+
+bool PointToPointBroker::isDeviceGroup(int groupId)
+{
+    std::shared_lock<std::shared_mutex> lk(brokerMutex);
+    return deviceComms.find(groupId) != deviceComms.end();
+}
+
+std::shared_ptr<faabric::device::Communicator> PointToPointBroker::getDeviceCommunicator(int groupId, int groupIdx)
+{
+    std::shared_lock<std::shared_mutex> lk(brokerMutex);
+    auto it = deviceComms.find(groupId);
+    if (it == deviceComms.end()) {
+        return nullptr;
+    }
+    auto jt = it->second.find(groupIdx);
+    return jt == it->second.end() ? nullptr : jt->second;
+}
+
+void PointToPointBroker::sendDeviceMessage(int groupId,
+                                           int sendIdx,
+                                           int recvIdx,
+                                           const void* deviceBuffer,
+                                           size_t bufferSize,
+                                           void* stream)
+{
+    auto comm = getDeviceCommunicator(groupId, sendIdx);
+    if (comm == nullptr) {
+        throw std::runtime_error("No device communicator for group " + std::to_string(groupId) + " idx " +
+                                 std::to_string(sendIdx));
+    }
+    int rc = comm->send(deviceBuffer, bufferSize, recvIdx, (cudaStream_t)stream);
+    if (rc != FB_OK) {
+        throw std::runtime_error(std::string("Device send failed: ") + faabric::device::Communicator::errorString(rc));
+    }
+}
+
+void PointToPointBroker::recvDeviceMessage(int groupId,
+                                           int sendIdx,
+                                           int recvIdx,
+                                           void* deviceBuffer,
+                                           size_t bufferSize,
+                                           void* stream)
+{
+    auto comm = getDeviceCommunicator(groupId, recvIdx);
+    if (comm == nullptr) {
+        throw std::runtime_error("No device communicator for group " + std::to_string(groupId) + " idx " +
+                                 std::to_string(recvIdx));
+    }
+    int rc = comm->recv(deviceBuffer, bufferSize, sendIdx, (cudaStream_t)stream);
+    if (rc != FB_OK) {
+        throw std::runtime_error(std::string("Device recv failed: ") + faabric::device::Communicator::errorString(rc));
+    }
+}
+
 void PointToPointBroker::clearGroup(int groupId)
 {
     std::set<int> idxs;
     {
         std::unique_lock<std::shared_mutex> lk(brokerMutex);
+        deviceComms.erase(groupId);
         auto it = groupIdIdxsMap.find(groupId);
         if (it != groupIdIdxsMap.end()) {
             idxs = it->second;
@@ -675,6 +800,7 @@ void PointToPointBroker::clear()
         mappings.clear();
         mpiPortMappings.clear();
         groupFlags.clear();
+        deviceComms.clear();
     }
     {
         std::lock_guard<std::mutex> lk(seqMx);

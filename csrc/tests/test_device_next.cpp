@@ -12,6 +12,7 @@
 #include <faabric/mpi/mpi.h>
 #include <faabric/snapshot/DeviceSnapshot.h>
 #include <faabric/snapshot/SnapshotRegistry.h>
+#include <faabric/state/State.h>
 #include <faabric/util/snapshot.h>
 
 #include <cuda_runtime.h>
@@ -198,4 +199,218 @@ TEST_CASE("next: a tuning file steers the all-reduce algorithm", "[unverified][d
     // 4 KiB would be LL by the built-in thresholds; the file says two-shot
     REQUIRE_EQ(comms[0]->pickAllReduceAlgo(4096, false), (int)FB_ALGO_TWOSHOT);
     REQUIRE_EQ(comms[0]->pickAllReduceAlgo(8 << 20, false), (int)FB_ALGO_ONESHOT);
+}
+
+// ---------------------------------------------------------------------------
+// device-resident state values
+// ---------------------------------------------------------------------------
+TEST_CASE("device state: main copy in HBM, replicas pull chunks and push dirty blocks with one kernel", "[gpu][state]")
+{
+    NEED_GPU();
+    int nDev = 0;
+    cudaGetDeviceCount(&nDev);
+    const int devMain = 0;
+    const int devReplica = nDev > 1 ? 1 : 0; // on one GPU the "peer" is the same device
+    faabric::state::State state("test-host");
+    const size_t size = (3 << 20) + 777; // not a multiple of anything interesting
+    auto mainKv = state.getDeviceKV("demo", "weights", size, devMain);
+    REQUIRE(mainKv->isMain());
+    // a second object for the same device is the same object
+    REQUIRE(state.getDeviceKV("demo", "weights", size, devMain) == mainKv);
+
+    std::vector<uint8_t> init(size);
+    for (size_t i = 0; i < size; i++) {
+        init[i] = (uint8_t)(i * 7 + 3);
+    }
+    mainKv->set(init.data());
+
+    // replica (size taken from the main copy)
+    std::shared_ptr<faabric::state::DeviceStateKeyValue> rep;
+    if (devReplica != devMain) {
+        rep = state.getDeviceKV("demo", "weights", 0, devReplica);
+    } else {
+        rep = std::make_shared<faabric::state::DeviceStateKeyValue>("demo", "weights", size, devReplica, mainKv);
+    }
+    REQUIRE(!rep->isMain());
+    REQUIRE_EQ(rep->size(), size);
+
+    // lazy chunk pull: only the 64 KiB chunks that cover the request move
+    REQUIRE(!rep->isChunkPulled(100000, 10));
+    std::vector<uint8_t> got(5000);
+    rep->getChunk(100000, got.data(), got.size());
+    REQUIRE(memcmp(got.data(), init.data() + 100000, got.size()) == 0);
+    REQUIRE(rep->isChunkPulled(100000, 5000));
+    REQUIRE(!rep->isChunkPulled(1 << 20, 10));
+    REQUIRE_EQ(rep->getBytesPulled(), (uint64_t)STATE_STREAMING_CHUNK_SIZE); // bytes 100000..104999 sit in chunk 1
+    rep->pull();
+    std::vector<uint8_t> whole(size);
+    rep->get(whole.data());
+    REQUIRE(whole == init);
+
+    // modify scattered ranges ON THE DEVICE, flag them, push partially
+    struct Edit
+    {
+        long off;
+        long len;
+        uint8_t val;
+    };
+    std::vector<Edit> edits = { { 5, 3, 0xa1 }, { 4096 * 9 + 100, 1000, 0xb2 }, { 1 << 20, 128, 0xc3 }, { (long)size - 50, 50, 0xd4 } };
+    cudaSetDevice(devReplica);
+    for (auto& e : edits) {
+        cudaMemset(rep->getDevicePtr() + e.off, e.val, e.len);
+        rep->flagChunkDirty(e.off, e.len);
+        memset(init.data() + e.off, e.val, e.len);
+    }
+    cudaDeviceSynchronize();
+    // the device scan reports exactly the flagged blocks, as runs
+    auto runs = rep->getDirtyChunks();
+    REQUIRE_EQ(runs.size(), 4u);
+    REQUIRE_EQ(runs[0].offset, 0u);
+    REQUIRE_EQ(runs[0].length, 128u);
+    REQUIRE_EQ(runs[1].offset, (uint64_t)(4096 * 9));      // 36864 = 288 * 128
+    REQUIRE_EQ(runs[1].length, (uint64_t)(9 * 128));        // 36964..37964 touches blocks 288..296
+    REQUIRE_EQ(runs[3].offset + runs[3].length, (uint64_t)size);
+    uint64_t pushed = rep->pushPartial();
+    REQUIRE_EQ(rep->getPushKernelLaunches(), 1u);
+    REQUIRE(pushed >= 3 + 1000 + 128 + 50);
+    REQUIRE(pushed <= (uint64_t)(1 + 9 + 1 + 2) * 128);
+    // the main copy now has the edits and nothing else changed
+    mainKv->get(whole.data());
+    REQUIRE(whole == init);
+    // the mask was cleared by the kernel: a second push moves nothing
+    REQUIRE_EQ(rep->pushPartial(), 0u);
+    REQUIRE(rep->getDirtyChunks().empty());
+    // host mirror
+    uint8_t* mirror = mainKv->syncHostMirror();
+    REQUIRE(memcmp(mirror, init.data(), size) == 0);
+    state.deleteDeviceKV("demo", "weights");
+    REQUIRE_EQ(state.getDeviceKVCount(), 0u);
+}
+
+// ---------------------------------------------------------------------------
+// point-to-point groups on the device
+// ---------------------------------------------------------------------------
+namespace {
+faabric::batch_scheduler::SchedulingDecision gpuDecision(int appId, int groupId, int n)
+{
+    faabric::batch_scheduler::SchedulingDecision d(appId, groupId);
+    for (int i = 0; i < n; i++) {
+        faabric::Message m;
+        m.set_appid(appId);
+        m.set_groupid(groupId);
+        m.set_groupidx(i);
+        m.set_appidx(i);
+        m.set_id(1000 + i);
+        d.addMessage("gpu" + std::to_string(i), m);
+    }
+    return d;
+}
+}
+
+TEST_CASE("ptp on device buffers: many in-order messages between group members", "[gpu][ptp]")
+{
+    NEED_GPU();
+    ClusterFixture f(0, 4, 1);
+    auto& broker = faabric::transport::getPointToPointBroker();
+    const int groupId = 7701;
+    const int n = 4;
+    broker.setUpLocalMappingsFromSchedulingDecision(gpuDecision(77, groupId, n));
+    broker.createLocalDeviceGroup(groupId);
+    REQUIRE(broker.isDeviceGroup(groupId));
+    // (reference test: "Test many in-order messages",
+    //  tests/dist/transport/functions.cpp - here the payloads never leave HBM)
+    const int nMsgs = 60;
+    std::vector<std::thread> members;
+    std::atomic<int> failures{ 0 };
+    for (int idx = 0; idx < n; idx++) {
+        members.emplace_back([&, idx] {
+            auto comm = broker.getDeviceCommunicator(groupId, idx);
+            cudaSetDevice(comm->device());
+            cudaStream_t s;
+            cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+            const int next = (idx + 1) % n;
+            const int prev = (idx + n - 1) % n;
+            std::vector<int*> outs(nMsgs), ins(nMsgs);
+            for (int k = 0; k < nMsgs; k++) {
+                size_t count = 1 + (size_t)k * 37; // growing sizes, odd byte counts
+                cudaMalloc(&outs[k], count * 4);
+                cudaMalloc(&ins[k], count * 4);
+                std::vector<int> h(count, idx * 100000 + k);
+                cudaMemcpy(outs[k], h.data(), count * 4, cudaMemcpyHostToDevice);
+                cudaMemset(ins[k], 0, count * 4);
+            }
+            // all sends first (eager), then all receives: order must hold
+            for (int k = 0; k < nMsgs; k++) {
+                broker.sendDeviceMessage(groupId, idx, next, outs[k], (1 + (size_t)k * 37) * 4, s);
+            }
+            for (int k = 0; k < nMsgs; k++) {
+                broker.recvDeviceMessage(groupId, prev, idx, ins[k], (1 + (size_t)k * 37) * 4, s);
+            }
+            if (!comm->syncStreamBounded(s, 20000) || comm->peekError() != 0) {
+                failures++;
+            }
+            for (int k = 0; k < nMsgs; k++) {
+                size_t count = 1 + (size_t)k * 37;
+                std::vector<int> h(count);
+                cudaMemcpy(h.data(), ins[k], count * 4, cudaMemcpyDeviceToHost);
+                for (size_t i = 0; i < count; i++) {
+                    if (h[i] != prev * 100000 + k) {
+                        failures++;
+                        break;
+                    }
+                }
+                cudaFree(outs[k]);
+                cudaFree(ins[k]);
+            }
+            cudaStreamDestroy(s);
+        });
+    }
+    for (auto& t : members) {
+        t.join();
+    }
+    REQUIRE_EQ(failures.load(), 0);
+    broker.clearGroup(groupId);
+    REQUIRE(!broker.isDeviceGroup(groupId));
+}
+
+TEST_CASE("ptp group barrier on the device", "[gpu][ptp]")
+{
+    NEED_GPU();
+    ClusterFixture f(0, 4, 1);
+    auto& broker = faabric::transport::getPointToPointBroker();
+    const int groupId = 7702;
+    const int n = 4;
+    broker.setUpLocalMappingsFromSchedulingDecision(gpuDecision(78, groupId, n));
+    faabric::transport::PointToPointGroup::addGroupIfNotExists(78, groupId, n);
+    broker.createLocalDeviceGroup(groupId);
+    auto group = faabric::transport::PointToPointGroup::getGroup(groupId);
+    // (reference test: "Test distributed barrier", tests/dist/transport/functions.cpp:
+    //  nobody may enter round r+1 before everybody finished round r)
+    const int rounds = 25;
+    std::atomic<int> arrived{ 0 };
+    std::atomic<int> violations{ 0 };
+    std::vector<std::thread> members;
+    for (int idx = 0; idx < n; idx++) {
+        members.emplace_back([&, idx] {
+            auto comm = broker.getDeviceCommunicator(groupId, idx);
+            cudaSetDevice(comm->device());
+            for (int r = 0; r < rounds; r++) {
+                if (idx == r % n) {
+                    std::this_thread::sleep_for(std::chrono::milliseconds(3)); // a straggler per round
+                }
+                arrived++;
+                group->barrier(idx);
+                if (arrived.load() < (r + 1) * n) {
+                    violations++;
+                }
+                group->barrier(idx);
+            }
+        });
+    }
+    for (auto& t : members) {
+        t.join();
+    }
+    REQUIRE_EQ(violations.load(), 0);
+    REQUIRE_EQ(arrived.load(), rounds * n);
+    broker.clearGroup(groupId);
 }

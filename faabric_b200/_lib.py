@@ -140,6 +140,9 @@ def load():
     )
     _sig(lib, "fb_dirty_scan", i32, [vp, vp, u64, vp, vp, i32, vp])
     _sig(lib, "fb_flags_or", i32, [vp, vp, u64, vp])
+    _sig(lib, "fb_state_push_dirty", i32, [vp, vp, vp, u64, vp, i32, vp])
+    _sig(lib, "fb_state_flag_range", i32, [vp, u64, u64, vp])
+    _sig(lib, "fb_state_block_bytes", i32, [])
     _sig(lib, "fb_chunk_runs", i32, [vp, u64, u32, u64, vp, u32, vp, vp])
     _sig(lib, "fb_snapshot_apply", i32, [vp, u64, vp, vp, vp, u32, vp])
     _lib = lib
