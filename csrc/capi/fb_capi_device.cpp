@@ -27,6 +27,37 @@ static thread_local std::string g_lastError;
         return ret;                                                            \
     }
 
+namespace {
+// The kernels below run on the device that OWNS the buffers, whatever the
+// calling thread's current device happens to be (other calls of this library
+// and of the caller's framework move it around)
+struct OwnerDeviceGuard
+{
+    int prev = -1;
+    explicit OwnerDeviceGuard(const void* devicePtr)
+    {
+        cudaPointerAttributes attr;
+        if (devicePtr != nullptr && cudaPointerGetAttributes(&attr, devicePtr) == cudaSuccess &&
+            (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+            cudaGetDevice(&prev);
+            if (prev != attr.device) {
+                cudaSetDevice(attr.device);
+            } else {
+                prev = -1;
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
+    ~OwnerDeviceGuard()
+    {
+        if (prev >= 0) {
+            cudaSetDevice(prev);
+        }
+    }
+};
+}
+
 extern "C" {
 
 struct FbConfigC
@@ -661,6 +692,7 @@ int fb_snapshot_diff_push(const void* mem,
                           int blocks,
                           void* stream)
 {
+    OwnerDeviceGuard ownerGuard(mem);
     fb::SnapDiffArgs a;
     memset(&a, 0, sizeof(a));
     a.mem = (const uint8_t*)mem;
@@ -694,6 +726,7 @@ int fb_dirty_scan(const void* mem,
                   int blocks,
                   void* stream)
 {
+    OwnerDeviceGuard ownerGuard(mem);
     if (blocks <= 0) {
         blocks = 148 * 2;
     }
@@ -717,6 +750,7 @@ int fb_state_push_dirty(void* mask,
                         int blocks,
                         void* stream)
 {
+    OwnerDeviceGuard ownerGuard(mask);
     return fb::launchStatePushDirty((uint8_t*)mask,
                                     (const uint8_t*)src,
                                     (uint8_t*)dst,
@@ -730,6 +764,7 @@ int fb_state_push_dirty(void* mask,
 
 int fb_state_flag_range(void* mask, uint64_t offset, uint64_t length, void* stream)
 {
+    OwnerDeviceGuard ownerGuard(mask);
     if (length == 0) {
         return FB_OK;
     }
@@ -747,6 +782,7 @@ int fb_state_block_bytes()
 
 int fb_flags_or(void* dst, const void* src, uint64_t n, void* stream)
 {
+    OwnerDeviceGuard ownerGuard(dst);
     return fb::launchFlagsOr(
              (uint8_t*)dst, (const uint8_t*)src, n, (cudaStream_t)stream) ==
                cudaSuccess
@@ -763,6 +799,7 @@ int fb_chunk_runs(const void* flagsDev,
                   void* countDev,
                   void* stream)
 {
+    OwnerDeviceGuard ownerGuard(flagsDev);
     return fb::launchChunkRuns((const uint8_t*)flagsDev,
                                nChunks,
                                chunkBytes,
@@ -783,6 +820,7 @@ int fb_snapshot_apply(void* image,
                       uint32_t nDescs,
                       void* stream)
 {
+    OwnerDeviceGuard ownerGuard(image);
     return fb::launchSnapshotApply((uint8_t*)image,
                                    imageSize,
                                    (const FbDiffDesc*)descsDev,

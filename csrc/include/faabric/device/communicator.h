@@ -241,11 +241,20 @@ class Communicator
                  size_t recvBytes,
                  int src,
                  cudaStream_t s);
+    // A non-blocking stream owned by this communicator, for host-driven
+    // operations that have no caller stream (group barriers).  Never the
+    // legacy default stream: ranks sharing a device would serialise on it.
+    cudaStream_t internalStream();
     bool streamSync() const { return streamSync_; }
     bool streamWaitSupported() const { return streamWaitOk_; }
     // Bounded wait for `s` (polls; never blocks forever on a stream-level wait
     // whose peer died).  Returns false after releasing the stuck waits.
     bool syncStreamBounded(cudaStream_t s, uint64_t timeoutMs);
+    // Low-latency completion wait for host-synchronous callers (the MPI C
+    // API): a stream-ordered write into host-mapped memory is polled by the
+    // CPU, which saves the driver round trip of cudaStreamSynchronize.  Falls
+    // back to it without stream memory operations.  False on a CUDA error.
+    bool waitStreamFast(cudaStream_t s);
     // zero-copy put into a peer's symmetric buffer + signal bump
     int putSignal(const void* local,
                   uint64_t dstOffset,
@@ -310,6 +319,9 @@ class Communicator
     uint32_t userSigConsumed_[FB_SIG_USER_WORDS] = { 0 };
     bool streamSync_ = false;
     bool streamWaitOk_ = false;
+    bool streamWriteOk_ = false;
+    cudaStream_t internalStream_ = nullptr;
+    uint32_t doneSeq_ = 0;
     // transient group tables (allReduceMany)
     struct ManySlot;
     std::vector<std::shared_ptr<ManySlot>> manySlots_;

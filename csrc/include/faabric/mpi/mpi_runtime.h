@@ -486,6 +486,10 @@ class MpiWorld
     std::atomic<uint64_t> deviceCollectives = 0;
     // Channel streams MPI_Iallreduce may rotate over (see ensureDeviceComms)
     std::atomic<int> nonBlockingChannels = 1;
+    // MPI_Iallreduce bursts on symmetric device buffers are coalesced into one
+    // grouped kernel at the next wait (FAABRIC_MPI_GROUP_IALLREDUCE=0: one
+    // kernel per call over the channels, the round-1 behaviour)
+    bool groupIallreduce = true;
     void ensureDeviceComms();
 
     // Host buffers, all ranks in this process: the ranks reduce straight out

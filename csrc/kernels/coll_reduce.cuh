@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(FB_LL_THREADS, 1) llAllReduceKernel(
         const uint32_t valid =
           (a.bytes - byteOff) >= 16 ? 16u : (uint32_t)(a.bytes - byteOff);
         Vec16 mine;
-        if (valid == 16) {
+        if (valid == 16 && !a.byteAccess) {
             mine = ldVec(a.sendLocal + byteOff);
         } else {
             mine.w[0] = mine.w[1] = mine.w[2] = mine.w[3] = 0;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(FB_LL_THREADS, 1) llAllReduceKernel(
             acc = (p == 0) ? v : VR::apply(acc, v);
         }
         if (ok) {
-            if (valid == 16) {
+            if (valid == 16 && !a.byteAccess) {
                 stVec(a.recvLocal + byteOff, acc);
             } else {
                 const uint8_t* ab = reinterpret_cast<const uint8_t*>(&acc);
@@ -359,32 +359,74 @@ cudaError_t launchLL(const LLArgs& a, cudaStream_t stream)
 // :24-50).  Work is cut into warp-sized chunks of the rank's segment list so
 // tiny tensors cost one warp iteration, not one kernel.
 // ----------------------------------------------------------------------------
+// One element at an element-aligned address, moved as an integer of its size
+template<typename E>
+__device__ __forceinline__ E ldElemGlobal(const uint8_t* p)
+{
+    E out;
+    if constexpr (sizeof(E) == 1) {
+        uint8_t v = *reinterpret_cast<const volatile uint8_t*>(p);
+        memcpy(&out, &v, 1);
+    } else if constexpr (sizeof(E) == 2) {
+        uint16_t v = *reinterpret_cast<const volatile uint16_t*>(p);
+        memcpy(&out, &v, 2);
+    } else if constexpr (sizeof(E) == 4) {
+        uint32_t v = *reinterpret_cast<const volatile uint32_t*>(p);
+        memcpy(&out, &v, 4);
+    } else if constexpr (sizeof(E) == 8) {
+        uint64_t v = *reinterpret_cast<const volatile uint64_t*>(p);
+        memcpy(&out, &v, 8);
+    } else {
+        Vec16 v = ldVec(p);
+        memcpy(&out, &v, 16);
+    }
+    return out;
+}
+
+template<typename E>
+__device__ __forceinline__ void stElemGlobal(uint8_t* p, const E& in)
+{
+    if constexpr (sizeof(E) == 1) {
+        uint8_t v;
+        memcpy(&v, &in, 1);
+        *reinterpret_cast<volatile uint8_t*>(p) = v;
+    } else if constexpr (sizeof(E) == 2) {
+        uint16_t v;
+        memcpy(&v, &in, 2);
+        *reinterpret_cast<volatile uint16_t*>(p) = v;
+    } else if constexpr (sizeof(E) == 4) {
+        uint32_t v;
+        memcpy(&v, &in, 4);
+        *reinterpret_cast<volatile uint32_t*>(p) = v;
+    } else if constexpr (sizeof(E) == 8) {
+        uint64_t v;
+        memcpy(&v, &in, 8);
+        *reinterpret_cast<volatile uint64_t*>(p) = v;
+    } else {
+        Vec16 v;
+        memcpy(&v, &in, 16);
+        stVec(p, v);
+    }
+}
+
 template<typename VR>
 __device__ __forceinline__ void groupTail(const FbCommDev& c,
                                           const GroupSeg& sg,
                                           int n)
 {
-    constexpr int EB = VR::ELEM_BYTES;
+    // Elements sit at element-aligned addresses (16-byte aligned tensor start
+    // + a multiple of the element size): move them by value
+    using Elem = typename VR::Elem;
+    constexpr uint32_t EB = VR::ELEM_BYTES;
     const uint64_t base = (uint64_t)sg.nVec * 16;
     for (uint32_t e = 0; e + EB <= sg.tailBytes; e += EB) {
-        alignas(16) uint8_t acc[16];
-        alignas(16) uint8_t in[16];
-        const uint8_t* s0 = c.heap[0] + sg.sendOff + base + e;
-        for (int b = 0; b < EB; b++) {
-            acc[b] = s0[b];
-        }
+        Elem acc = ldElemGlobal<Elem>(c.heap[0] + sg.sendOff + base + e);
         for (int p = 1; p < n; p++) {
-            const uint8_t* sp = c.heap[p] + sg.sendOff + base + e;
-            for (int b = 0; b < EB; b++) {
-                in[b] = sp[b];
-            }
-            VR::applyTail(acc, in);
+            Elem v = ldElemGlobal<Elem>(c.heap[p] + sg.sendOff + base + e);
+            acc = VR::combine(acc, v);
         }
         for (int p = 0; p < n; p++) {
-            uint8_t* d = c.heap[p] + sg.recvOff + base + e;
-            for (int b = 0; b < EB; b++) {
-                d[b] = acc[b];
-            }
+            stElemGlobal<Elem>(c.heap[p] + sg.recvOff + base + e, acc);
         }
     }
 }

@@ -351,6 +351,17 @@ __device__ __forceinline__ Vec16 reduceVecPair(const Vec16& a, const Vec16& b)
     return ur.v;
 }
 
+template<typename T, bool PAIR>
+struct ElemOf
+{
+    using type = T;
+};
+template<typename T>
+struct ElemOf<T, true>
+{
+    using type = PairVI<T>;
+};
+
 // Tag type so a single kernel template handles scalar and pair element kinds
 template<typename T, int OP, bool PAIR>
 struct VecReduce
@@ -363,6 +374,16 @@ struct VecReduce
             return reduceVecPair<T, OP>(a, b);
         } else {
             return reduceVec<T, OP>(a, b);
+        }
+    }
+    // one element, by value (tails of grouped launches)
+    using Elem = typename ElemOf<T, PAIR>::type;
+    __device__ __forceinline__ static Elem combine(Elem a, Elem b)
+    {
+        if constexpr (PAIR) {
+            return reducePair<T, OP>(a, b);
+        } else {
+            return reduceElem<T, OP>(a, b);
         }
     }
     // scalar tail: `acc` and `in` are byte buffers, so the element is moved

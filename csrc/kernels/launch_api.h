@@ -54,6 +54,8 @@ struct LLArgs
     uint8_t* recvLocal;
     uint64_t bytes;
     uint64_t llOff; // symmetric offset of the LL slot area
+    int32_t byteAccess; // local buffers are not 16-byte aligned
+    int32_t pad;
 };
 
 typedef cudaError_t (*LLLaunchFn)(const LLArgs& a, cudaStream_t stream);

@@ -117,6 +117,9 @@ __device__ __forceinline__ uint32_t warpSegment(const SnapDiffArgs& a,
                 if (a.updateBase) {
                     a.origW[p] = m;
                 }
+                if (a.chunkFlags != nullptr) {
+                    a.chunkFlags[p >> 7] = 1; // benign same-value race
+                }
             }
         }
         chunkAny |= diffBytes;
@@ -136,6 +139,9 @@ __device__ __forceinline__ uint32_t warpSegment(const SnapDiffArgs& a,
             if (a.updateBase) {
                 a.origW[p] = m;
             }
+            if (a.chunkFlags != nullptr) {
+                a.chunkFlags[p >> 7] = 1;
+            }
         }
     }
     for (uint64_t p = ve + lane; p < end; p += 32) {
@@ -151,6 +157,9 @@ __device__ __forceinline__ uint32_t warpSegment(const SnapDiffArgs& a,
             }
             if (a.updateBase) {
                 a.origW[p] = m;
+            }
+            if (a.chunkFlags != nullptr) {
+                a.chunkFlags[p >> 7] = 1;
             }
         }
     }
@@ -284,6 +293,100 @@ __device__ __forceinline__ void atomicRmwSys(T* addr, F f)
     }
 }
 
+// Native system-scope reductions where the ISA has them (integers): one
+// fire-and-forget red.* instead of a CAS round trip over NVLink
+__device__ __forceinline__ void redAddSys(int32_t* p, int32_t v)
+{
+    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void redAddSys(int64_t* p, int64_t v)
+{
+    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void redMaxSys(int32_t* p, int32_t v)
+{
+    asm volatile("red.relaxed.sys.global.max.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void redMaxSys(int64_t* p, int64_t v)
+{
+    asm volatile("red.relaxed.sys.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void redMinSys(int32_t* p, int32_t v)
+{
+    asm volatile("red.relaxed.sys.global.min.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void redMinSys(int64_t* p, int64_t v)
+{
+    asm volatile("red.relaxed.sys.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// (the hardware f32 add flushes subnormals to zero; the host merge of the
+// reference does not, so float sums keep the exact CAS loop)
+__device__ __forceinline__ void redAddSys(float* p, float v)
+{
+    atomicRmwSys<float>(p, [v](float c) { return c + v; });
+}
+__device__ __forceinline__ void redAddSys(double* p, double v)
+{
+    asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ bool cas128Sys(void* p,
+                                          uint64_t c0,
+                                          uint64_t c1,
+                                          uint64_t n0,
+                                          uint64_t n1,
+                                          uint64_t& r0,
+                                          uint64_t& r1)
+{
+    asm volatile("{\n\t.reg .b128 c, n, r;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, "
+                 "{%4, %5};\n\tatom.relaxed.sys.global.cas.b128 r, [%6], c, n;\n\tmov.b128 "
+                 "{%0, %1}, r;\n\t}"
+                 : "=l"(r0), "=l"(r1)
+                 : "l"(c0), "l"(c1), "l"(n0), "l"(n1), "l"(p)
+                 : "memory");
+    return r0 == c0 && r1 == c1;
+}
+
+// RMW of a scalar that is NOT naturally aligned (an application may declare a
+// typed merge region at any byte offset), atomic with respect to the other
+// GPUs merging into the same image: one 128-bit compare-and-swap on the
+// enclosing 16-byte block (SASS ATOMG.E.CAS.128.STRONG.SYS) recomputes the
+// scalar from the bytes it observed.  A scalar that crosses a 16-byte
+// boundary has no single atomic that covers it: returns false and the caller
+// falls back to load / modify / store (last writer wins for that scalar).
+template<typename T, typename F>
+__device__ __forceinline__ bool atomicRmwUnalignedSys(uint8_t* d, F f)
+{
+    const uintptr_t addr = (uintptr_t)d;
+    const int shift = (int)(addr & 15);
+    if (shift + (int)sizeof(T) > 16) {
+        return false;
+    }
+    uint64_t* blk = reinterpret_cast<uint64_t*>(addr & ~(uintptr_t)15);
+    uint64_t o0 = *reinterpret_cast<volatile uint64_t*>(blk);
+    uint64_t o1 = *reinterpret_cast<volatile uint64_t*>(blk + 1);
+    while (true) {
+        uint8_t bytes[16];
+        memcpy(bytes, &o0, 8);
+        memcpy(bytes + 8, &o1, 8);
+        T cur;
+        memcpy(&cur, bytes + shift, sizeof(T));
+        T nv = f(cur);
+        memcpy(bytes + shift, &nv, sizeof(T));
+        uint64_t n0;
+        uint64_t n1;
+        memcpy(&n0, bytes, 8);
+        memcpy(&n1, bytes + 8, 8);
+        uint64_t r0;
+        uint64_t r1;
+        if (cas128Sys(blk, o0, o1, n0, n1, r0, r1)) {
+            return true;
+        }
+        o0 = r0;
+        o1 = r1;
+    }
+}
+
 // Merge one scalar.  Returns true if a diff was produced.
 template<typename T>
 __device__ __forceinline__ bool mergeScalar(const SnapDiffArgs& a,
@@ -297,24 +400,27 @@ __device__ __forceinline__ bool mergeScalar(const SnapDiffArgs& a,
     }
     uint8_t* d = a.dst + off;
     const bool aligned = ((uintptr_t)d % sizeof(T)) == 0;
+    constexpr bool isInt = (T)0.5 == (T)0; // integer types truncate
     switch (op) {
         case FB_MERGE_SUM: {
             T delta = m - o;
             if (aligned) {
-                atomicRmwSys<T>(reinterpret_cast<T*>(d),
-                                [delta](T c) { return (T)(c + delta); });
+                redAddSys(reinterpret_cast<T*>(d), delta);
             } else {
-                storeUnaligned<T>(d, (T)(loadUnaligned<T>(d) + delta));
+                if (!atomicRmwUnalignedSys<T>(d, [delta](T c) { return (T)(c + delta); })) {
+                    storeUnaligned<T>(d, (T)(loadUnaligned<T>(d) + delta));
+                }
             }
             break;
         }
         case FB_MERGE_SUBTRACT: {
             T diff = o - m; // applied as main - diff
             if (aligned) {
-                atomicRmwSys<T>(reinterpret_cast<T*>(d),
-                                [diff](T c) { return (T)(c - diff); });
+                redAddSys(reinterpret_cast<T*>(d), (T)(-diff));
             } else {
-                storeUnaligned<T>(d, (T)(loadUnaligned<T>(d) - diff));
+                if (!atomicRmwUnalignedSys<T>(d, [diff](T c) { return (T)(c - diff); })) {
+                    storeUnaligned<T>(d, (T)(loadUnaligned<T>(d) - diff));
+                }
             }
             break;
         }
@@ -324,27 +430,41 @@ __device__ __forceinline__ bool mergeScalar(const SnapDiffArgs& a,
                 atomicRmwSys<T>(reinterpret_cast<T*>(d),
                                 [q](T c) { return (T)(c * q); });
             } else {
-                storeUnaligned<T>(d, (T)(loadUnaligned<T>(d) * q));
+                if (!atomicRmwUnalignedSys<T>(d, [q](T c) { return (T)(c * q); })) {
+                    storeUnaligned<T>(d, (T)(loadUnaligned<T>(d) * q));
+                }
             }
             break;
         }
         case FB_MERGE_MAX: {
             if (aligned) {
-                atomicRmwSys<T>(reinterpret_cast<T*>(d),
-                                [m](T c) { return c > m ? c : m; });
+                if constexpr (isInt) {
+                    redMaxSys(reinterpret_cast<T*>(d), m);
+                } else {
+                    atomicRmwSys<T>(reinterpret_cast<T*>(d),
+                                    [m](T c) { return c > m ? c : m; });
+                }
             } else {
-                T c = loadUnaligned<T>(d);
-                storeUnaligned<T>(d, c > m ? c : m);
+                if (!atomicRmwUnalignedSys<T>(d, [m](T c) { return c > m ? c : m; })) {
+                    T c = loadUnaligned<T>(d);
+                    storeUnaligned<T>(d, c > m ? c : m);
+                }
             }
             break;
         }
         case FB_MERGE_MIN: {
             if (aligned) {
-                atomicRmwSys<T>(reinterpret_cast<T*>(d),
-                                [m](T c) { return c < m ? c : m; });
+                if constexpr (isInt) {
+                    redMinSys(reinterpret_cast<T*>(d), m);
+                } else {
+                    atomicRmwSys<T>(reinterpret_cast<T*>(d),
+                                    [m](T c) { return c < m ? c : m; });
+                }
             } else {
-                T c = loadUnaligned<T>(d);
-                storeUnaligned<T>(d, c < m ? c : m);
+                if (!atomicRmwUnalignedSys<T>(d, [m](T c) { return c < m ? c : m; })) {
+                    T c = loadUnaligned<T>(d);
+                    storeUnaligned<T>(d, c < m ? c : m);
+                }
             }
             break;
         }
@@ -353,6 +473,10 @@ __device__ __forceinline__ bool mergeScalar(const SnapDiffArgs& a,
     }
     if (a.updateBase) {
         storeUnaligned<T>(a.origW + off, m);
+    }
+    if (a.chunkFlags != nullptr) {
+        a.chunkFlags[off >> 7] = 1;
+        a.chunkFlags[(off + sizeof(T) - 1) >> 7] = 1;
     }
     return true;
 }

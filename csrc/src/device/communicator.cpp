@@ -904,8 +904,25 @@ std::shared_ptr<Communicator> Communicator::createIpc(int rank,
     return c;
 }
 
+cudaStream_t Communicator::internalStream()
+{
+    if (internalStream_ == nullptr) {
+        cudaSetDevice(device_);
+        if (cudaStreamCreateWithFlags(&internalStream_, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            internalStream_ = nullptr;
+        }
+    }
+    return internalStream_;
+}
+
 Communicator::~Communicator()
 {
+    if (internalStream_ != nullptr) {
+        cudaSetDevice(device_);
+        cudaStreamDestroy(internalStream_);
+        cudaGetLastError();
+    }
     // Backing is shared: freed when the last rank's communicator dies
 }
 
@@ -1130,7 +1147,7 @@ int Communicator::reduceLike(int kind,
         return FB_E_UNSUPPORTED;
     }
     cudaSetDevice(device_);
-    const bool symmetric = (flags & FB_FLAG_SYMMETRIC) != 0;
+    bool symmetric = (flags & FB_FLAG_SYMMETRIC) != 0;
     // stream-ordered synchronisation replaces the in-kernel barriers
     const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
     const int noSync = ((flags & FB_FLAG_NOSYNC) || ss) ? 1 : 0;
@@ -1147,6 +1164,20 @@ int Communicator::reduceLike(int kind,
     if (symmetric && (!inHeap(send, bytes))) {
         return FB_E_INVALID;
     }
+    if (symmetric && (kind == K_SCAN || kind == K_REDUCE_SCATTER)) {
+        // These read the peers' inputs while every rank writes its output with
+        // no barrier in between: an output that overlaps the (symmetric) input
+        // range would be clobbered under a peer's loads.  Heap offsets are the
+        // same on every rank, so every rank takes the same decision: go
+        // through the staging copy of the input.
+        const uint8_t* s0 = (const uint8_t*)send;
+        const uint8_t* r0 = (const uint8_t*)recv;
+        const uint64_t outBytes = (kind == K_REDUCE_SCATTER) ? (uint64_t)count * esize : bytes;
+        if (r0 < s0 + bytes && s0 < r0 + outBytes) {
+            symmetric = false;
+            flags &= ~FB_FLAG_SYMMETRIC;
+        }
+    }
 
     const int nvVariant = fb::nvlsVariant(dtype, op);
 
@@ -1162,9 +1193,10 @@ int Communicator::reduceLike(int kind,
               bytes, hasMulticast() && nvVariant >= 0 && (bytes % 16) == 0 && nvlsWorthIt);
         }
         // (the LL kernel synchronises through its data slots: no stream mode)
-        if (algo == FB_ALGO_LL &&
-            (ss || bytes > FB_LL_MAX_BYTES ||
-             (((uintptr_t)send | (uintptr_t)recv) & 15))) {
+        // (decided from quantities every rank shares; a rank whose local
+        // pointers are not 16-byte aligned stays in LL and moves its bytes
+        // element-wise inside the kernel)
+        if (algo == FB_ALGO_LL && (ss || bytes > FB_LL_MAX_BYTES)) {
             algo = FB_ALGO_ONESHOT;
         }
         if (algo == FB_ALGO_NVLS &&
@@ -1220,6 +1252,7 @@ int Communicator::reduceLike(int kind,
         a.sendLocal = (const uint8_t*)send;
         a.recvLocal = (uint8_t*)recv;
         a.bytes = bytes;
+        a.byteAccess = ((((uintptr_t)send) | ((uintptr_t)recv)) & 15) ? 1 : 0;
         a.llOff = llOff_ + (uint64_t)(a.comm.llEpochBase / FB_LL_BLOCKS) *
                              FB_LL_AREA_BYTES(n);
         stats_.launches++;
@@ -1243,14 +1276,25 @@ int Communicator::reduceLike(int kind,
     } else if (isRootOrAll && (((uintptr_t)recv) & 15)) {
         stageRecv = true; // vector stores need 16-byte alignment
     }
-    if (kind == K_REDUCE_SCATTER && stageSend && bytes > cfg_.stageBytes) {
+    // slices are addressed inside the whole message: no piecewise launches
+    if (kind == K_REDUCE_SCATTER && (stageSend || stageRecv) && bytes > cfg_.stageBytes) {
         return FB_E_TOO_LARGE;
     }
     if ((stageSend || stageRecv) && chanDev.blockBase != 0) {
         return FB_E_INVALID; // staging buffers exist once, on channel 0 only
     }
+    // The number of launches must be the same on every rank (the per-CTA
+    // barrier epochs advance with it), so it only depends on `symmetric`,
+    // `algo`, `kind` and `bytes`; a rank-LOCAL need for output staging (an
+    // unaligned destination) must fit one piece
+    // (whether the output lives in the symmetric heap is part of the call's
+    // contract: all ranks pass the same kind of buffer)
+    const bool stageRecvGlobal = pushes && (kind == K_REDUCE || !symmetric || !inHeap(recv, bytes));
     const uint64_t chunkMax =
-      (stageSend || stageRecv) ? (uint64_t)cfg_.stageBytes : bytes;
+      (stageSend || stageRecvGlobal) ? (uint64_t)cfg_.stageBytes : bytes;
+    if (stageRecv && !stageRecvGlobal && !stageSend && bytes > cfg_.stageBytes) {
+        return FB_E_TOO_LARGE;
+    }
 
     for (uint64_t done = 0; done < bytes; done += chunkMax) {
         const uint64_t len = std::min<uint64_t>(chunkMax, bytes - done);
@@ -2083,6 +2127,19 @@ void Communicator::finishSetup()
             } else {
                 cudaGetLastError();
             }
+            // completion word: err[1], host-mapped next to the error word
+            if (api.cuStreamWriteValue32 != nullptr && dev_.err != nullptr) {
+                void* devPtr = nullptr;
+                if (cudaHostGetDevicePointer(&devPtr, (void*)(dev_.err + 1), 0) == cudaSuccess) {
+                    r = api.cuStreamWriteValue32((CUstream)t, (CUdeviceptr)(uintptr_t)devPtr, 0x5a5a0001u, 0);
+                    if (r == CUDA_SUCCESS && cudaStreamSynchronize(t) == cudaSuccess &&
+                        *reinterpret_cast<volatile uint32_t*>(dev_.err + 1) == 0x5a5a0001u) {
+                        streamWriteOk_ = true;
+                    }
+                }
+                cudaGetLastError();
+                dev_.err[1] = 0;
+            }
             cudaStreamDestroy(t);
         }
     }
@@ -2160,6 +2217,31 @@ bool Communicator::syncStreamBounded(cudaStream_t s, uint64_t timeoutMs)
             }
         }
     }
+}
+
+bool Communicator::waitStreamFast(cudaStream_t s)
+{
+    cudaSetDevice(device_);
+    if (streamWriteOk_) {
+        void* devPtr = nullptr;
+        cudaHostGetDevicePointer(&devPtr, (void*)(dev_.err + 1), 0);
+        const uint32_t seq = ++doneSeq_ | 0x80000000u;
+        if (getDriverApi().cuStreamWriteValue32((CUstream)s, (CUdeviceptr)(uintptr_t)devPtr, seq, 0) == CUDA_SUCCESS) {
+            volatile uint32_t* word = reinterpret_cast<volatile uint32_t*>(dev_.err + 1);
+            // typical wait is a few microseconds; give up spinning after ~1 ms
+            for (int spin = 0; spin < 200000; spin++) {
+                if (*word == seq) {
+                    return true;
+                }
+                __builtin_ia32_pause();
+            }
+        }
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
 }
 
 // A peer never arrived: flag the error and satisfy every stream-level wait

@@ -41,6 +41,8 @@ struct AsyncRequest
     MpiMessageType messageType = MpiMessageType::NORMAL;
     // Stream-ordered device collective: complete when `stream` drains
     bool isDeviceCollective = false;
+    // part of a burst that has not been issued yet (grouped at the next wait)
+    bool deferred = false;
     void* stream = nullptr;
     std::shared_ptr<faabric::device::Communicator> comm;
 };
@@ -67,6 +69,14 @@ struct RankState
     // Non-blocking device collectives rotate over the communicator's
     // channels (every rank issues the same sequence => same channel)
     uint64_t deviceCollectiveSeq = 0;
+    // MPI_Iallreduce burst on symmetric device buffers: deferred and issued
+    // as ONE grouped kernel at the next wait (or any other device operation)
+    std::shared_ptr<faabric::device::Communicator> groupComm;
+    int groupDtype = -1;
+    int groupOp = -1;
+    void* groupStream = nullptr;
+    std::vector<faabric::device::Communicator::GroupItem> groupItems;
+    std::vector<int> groupRequests;
 
     void reset()
     {
@@ -81,6 +91,9 @@ struct RankState
         pendingIrecvs.clear();
         probed.clear();
         deviceCollectiveSeq = 0;
+        groupComm = nullptr;
+        groupItems.clear();
+        groupRequests.clear();
         nextRequestId = 1;
     }
 };
@@ -828,6 +841,35 @@ int MpiWorld::irecv(int sendRank,
     return requestId;
 }
 
+// Issues the deferred MPI_Iallreduce burst of this rank thread as one grouped
+// launch (every rank defers and flushes at the same program points)
+static void flushPendingGroup()
+{
+    if (tls.groupItems.empty()) {
+        return;
+    }
+    auto comm = tls.groupComm;
+    auto items = std::move(tls.groupItems);
+    auto reqs = std::move(tls.groupRequests);
+    tls.groupItems.clear();
+    tls.groupRequests.clear();
+    tls.groupComm = nullptr;
+    cudaSetDevice(comm->device());
+    int rc = comm->allReduceMany(
+      items.data(), items.size(), tls.groupDtype, tls.groupOp, FB_FLAG_SYMMETRIC, (cudaStream_t)tls.groupStream);
+    if (rc != FB_OK) {
+        throw std::runtime_error(std::string("Grouped device all-reduce failed: ") +
+                                 faabric::device::Communicator::errorString(rc));
+    }
+    for (int id : reqs) {
+        auto it = tls.requests.find(id);
+        if (it != tls.requests.end()) {
+            it->second.stream = tls.groupStream;
+            it->second.deferred = false;
+        }
+    }
+}
+
 void MpiWorld::awaitAsyncRequest(int requestId)
 {
     auto it = tls.requests.find(requestId);
@@ -836,11 +878,14 @@ void MpiWorld::awaitAsyncRequest(int requestId)
         return;
     }
     if (it->second.isDeviceCollective) {
+        if (it->second.deferred) {
+            flushPendingGroup();
+            it = tls.requests.find(requestId);
+        }
         AsyncRequest req = it->second;
         tls.requests.erase(it);
         cudaSetDevice(req.comm->device());
-        if (cudaStreamSynchronize((cudaStream_t)req.stream) != cudaSuccess) {
-            cudaGetLastError();
+        if (!req.comm->waitStreamFast((cudaStream_t)req.stream)) {
             throw std::runtime_error("Device collective failed at synchronisation");
         }
         if (req.comm->peekError() != 0) {
@@ -948,6 +993,9 @@ void MpiWorld::ensureDeviceComms()
     }
     auto cfg = faabric::device::CommConfig::fromEnv();
     cfg.heapBytes = (size_t)faabric::util::getSystemConfig().symmHeapBytes;
+    if (const char* g = getenv("FAABRIC_MPI_GROUP_IALLREDUCE")) {
+        groupIallreduce = g[0] != '0';
+    }
     if (getenv("FAABRIC_COMM_CHANNELS") == nullptr) {
         // MPI_Iallreduce bursts pipeline over the channels: use them all
         cfg.channels = FB_MAX_CHANNELS;
@@ -1073,6 +1121,8 @@ static bool runDevice(std::shared_ptr<faabric::device::Communicator> comm,
     if (comm == nullptr) {
         return false;
     }
+    // keep the issue order identical on every rank
+    flushPendingGroup();
     cudaSetDevice(comm->device());
     int rc = fn(*comm, (cudaStream_t)stream);
     if (rc == FB_E_UNSUPPORTED || rc == FB_E_TOO_LARGE) {
@@ -1081,7 +1131,7 @@ static bool runDevice(std::shared_ptr<faabric::device::Communicator> comm,
     if (rc != FB_OK) {
         throw std::runtime_error(std::string("Device collective failed: ") + faabric::device::Communicator::errorString(rc));
     }
-    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    if (!comm->waitStreamFast((cudaStream_t)stream)) {
         throw std::runtime_error("Device collective failed at synchronisation");
     }
     uint32_t err = comm->peekError();
@@ -1129,6 +1179,27 @@ int MpiWorld::iAllReduce(int rank, uint8_t* send, uint8_t* recv, faabric_datatyp
         // Symmetric buffers may use any channel; others go through the single
         // staging area on channel 0
         const bool symmetric = comm->inHeap(send, bytes) && comm->inHeap(recv, bytes);
+        if (symmetric && ((((uintptr_t)send) | ((uintptr_t)recv)) & 15) == 0 && groupIallreduce) {
+            // Deferred: the whole burst becomes ONE kernel at the next wait
+            if (!tls.groupItems.empty() &&
+                (tls.groupComm != comm || tls.groupDtype != fdt || tls.groupOp != fop || tls.groupItems.size() >= 4096)) {
+                flushPendingGroup();
+            }
+            tls.groupComm = comm;
+            tls.groupDtype = fdt;
+            tls.groupOp = fop;
+            tls.groupStream = streamForRank(rank, 0);
+            tls.groupItems.push_back({ send, recv, (size_t)count });
+            tls.groupRequests.push_back(requestId);
+            deviceCollectives.fetch_add(1);
+            r.isDeviceCollective = true;
+            r.deferred = true;
+            r.stream = tls.groupStream;
+            r.comm = comm;
+            tls.requests[requestId] = r;
+            return requestId;
+        }
+        flushPendingGroup();
         int nChannels = std::clamp(nonBlockingChannels.load(), 1, std::max(1, comm->config().channels));
         int channel = symmetric ? (int)(tls.deviceCollectiveSeq++ % (uint64_t)nChannels) : 0;
         cudaStream_t s = (cudaStream_t)streamForRank(rank, channel);
@@ -1368,10 +1439,17 @@ void MpiWorld::gather(int sendRank,
     // In place: the root's contribution already sits in its slot
     const bool inPlace = isRoot && sendBuffer == recvBuffer;
 
-    if (sendBytes > 0 && isDevicePointer(sendBuffer) && !inPlace) {
+    // The device-or-host choice must come out the same on every rank, and only
+    // the root knows whether it passed MPI_IN_PLACE: so the root's in-place
+    // case takes the device path too (its chunk already sits in the receive
+    // buffer), and no rank relies on symmetric offsets - every contribution is
+    // staged through the symmetric staging area.
+    const bool deviceCall = isDevicePointer(isRoot && inPlace ? recvBuffer : sendBuffer);
+    if (sendBytes > 0 && deviceCall) {
         auto comm = getDeviceComm(sendRank);
+        const uint8_t* contribution = (isRoot && inPlace) ? recvBuffer + (size_t)recvRank * recvBytes : sendBuffer;
         if (runDevice(comm, streamForRank(sendRank), [&](faabric::device::Communicator& c, cudaStream_t s) {
-                return c.gather(sendBuffer, recvBuffer, sendBytes, recvRank, symFlag(c, sendBuffer, sendBytes), s);
+                return c.gather(contribution, recvBuffer, sendBytes, recvRank, 0, s);
             })) {
             deviceCollectives.fetch_add(1);
             return;
@@ -1488,12 +1566,15 @@ void MpiWorld::reduce(int sendRank,
     const bool isRoot = sendRank == recvRank;
     const bool inPlace = sendBuffer == recvBuffer;
 
-    if (bytes > 0 && isDevicePointer(sendBuffer) && !inPlace) {
+    // Same choice on every rank (only the root can see MPI_IN_PLACE): in-place
+    // at the root stays on the device; inputs are staged, so aliasing the
+    // root's input and output is safe and no symmetric offsets are assumed.
+    if (bytes > 0 && isDevicePointer(sendBuffer)) {
         int fdt = fbDtypeFor(datatype);
         int fop = fbOpFor(operation);
         auto comm = (fdt >= 0 && fop >= 0) ? getDeviceComm(sendRank) : nullptr;
         if (runDevice(comm, streamForRank(sendRank), [&](faabric::device::Communicator& c, cudaStream_t s) {
-                return c.reduce(sendBuffer, recvBuffer, (size_t)count, fdt, fop, recvRank, symFlag(c, sendBuffer, bytes), s);
+                return c.reduce(sendBuffer, recvBuffer, (size_t)count, fdt, fop, recvRank, 0, s);
             })) {
             deviceCollectives.fetch_add(1);
             return;

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
 #include <atomic>
 #include <cstring>
 #include <unistd.h>
@@ -903,15 +904,59 @@ void DeviceSnapshot::applyDiffs(const std::vector<SnapshotDiff>& diffs, void* st
     if (diffs.empty()) {
         return;
     }
+    // The kernel applies the descriptors of one launch concurrently, the
+    // reference applies a diff list in order (SnapshotData::applyDiffs).  Diffs
+    // that touch the same bytes (several Sum diffs onto one scalar, a Bytewise
+    // diff followed by an XOR ...) therefore go into successive "waves": a
+    // diff's wave is one more than the highest wave among the earlier diffs it
+    // overlaps.  Waves are launched back to back on the stream.
+    std::vector<int> waveOf(diffs.size(), 0);
+    int nWaves = 1;
+    {
+        std::map<uint64_t, std::pair<uint64_t, int>> spans; // start -> (end, wave)
+        for (size_t i = 0; i < diffs.size(); i++) {
+            uint64_t b = diffs[i].getOffset();
+            uint64_t e = b + std::max<size_t>(diffs[i].getData().size(), 1);
+            int wave = 0;
+            auto it = spans.lower_bound(b);
+            if (it != spans.begin()) {
+                --it;
+            }
+            uint64_t nb = b;
+            uint64_t ne = e;
+            while (it != spans.end() && it->first < e) {
+                if (it->second.first > b) {
+                    wave = std::max(wave, it->second.second + 1);
+                    nb = std::min(nb, it->first);
+                    ne = std::max(ne, it->second.first);
+                    it = spans.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+            spans[nb] = { ne, wave };
+            waveOf[i] = wave;
+            nWaves = std::max(nWaves, wave + 1);
+        }
+    }
     std::vector<FbDiffDesc> descs;
     std::vector<uint64_t> offs;
     std::vector<uint8_t> blob;
-    for (const auto& d : diffs) {
-        descs.push_back({ d.getOffset(), d.getData().size(), (int32_t)d.getDataType(), (int32_t)d.getOperation() });
-        offs.push_back(blob.size());
-        blob.insert(blob.end(), d.getData().begin(), d.getData().end());
-        blob.resize((blob.size() + 15) / 16 * 16);
+    std::vector<uint32_t> waveStart(nWaves + 1, 0);
+    for (int w = 0; w < nWaves; w++) {
+        waveStart[w] = (uint32_t)descs.size();
+        for (size_t i = 0; i < diffs.size(); i++) {
+            if (waveOf[i] != w) {
+                continue;
+            }
+            const auto& d = diffs[i];
+            descs.push_back({ d.getOffset(), d.getData().size(), (int32_t)d.getDataType(), (int32_t)d.getOperation() });
+            offs.push_back(blob.size());
+            blob.insert(blob.end(), d.getData().begin(), d.getData().end());
+            blob.resize((blob.size() + 15) / 16 * 16);
+        }
     }
+    waveStart[nWaves] = (uint32_t)descs.size();
     DeviceGuard g(device);
     auto dDescs = faabric::util::allocateDeviceMemory(descs.size() * sizeof(FbDiffDesc), device);
     auto dOffs = faabric::util::allocateDeviceMemory(offs.size() * sizeof(uint64_t), device);
@@ -921,13 +966,19 @@ void DeviceSnapshot::applyDiffs(const std::vector<SnapshotDiff>& diffs, void* st
     if (!blob.empty()) {
         DS_CUDA(cudaMemcpy(dBlob.ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     }
-    DS_CUDA(fb::launchSnapshotApply(image,
-                                    size,
-                                    (const FbDiffDesc*)dDescs.ptr,
-                                    (const uint64_t*)dOffs.ptr,
-                                    dBlob.ptr,
-                                    (uint32_t)descs.size(),
-                                    (cudaStream_t)stream));
+    for (int w = 0; w < nWaves; w++) {
+        uint32_t n = waveStart[w + 1] - waveStart[w];
+        if (n == 0) {
+            continue;
+        }
+        DS_CUDA(fb::launchSnapshotApply(image,
+                                        size,
+                                        (const FbDiffDesc*)dDescs.ptr + waveStart[w],
+                                        (const uint64_t*)dOffs.ptr + waveStart[w],
+                                        dBlob.ptr,
+                                        n,
+                                        (cudaStream_t)stream));
+    }
     DS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
 }
 

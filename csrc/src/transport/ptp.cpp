@@ -373,8 +373,9 @@ void PointToPointGroup::barrier(int groupIdx)
     if (devBroker.isDeviceGroup(groupId)) {
         // every member sits on a GPU: meet on the device
         auto comm = devBroker.getDeviceCommunicator(groupId, groupIdx);
-        deviceBarrier(groupIdx, nullptr);
-        if (!comm->syncStreamBounded(nullptr, (uint64_t)timeoutMs)) {
+        cudaStream_t s = comm->internalStream();
+        deviceBarrier(groupIdx, s);
+        if (!comm->syncStreamBounded(s, (uint64_t)timeoutMs)) {
             throw std::runtime_error("Device barrier timed out");
         }
         return;

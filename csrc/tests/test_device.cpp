@@ -124,6 +124,32 @@ int deviceCollectivesBody(int rank, int size)
     MPI_Reduce_scatter(rsIn.p, rsOut.p, counts.data(), MPI_INT, MPI_SUM, MPI_COMM_WORLD);
     CHECK_RANK(rsOut.download()[7] == size * (size - 1) / 2);
 
+    // MPI_IN_PLACE at the root, device buffers: only the root can see that it
+    // is in place, yet every rank must end up on the same (device) path
+    DevBuf<int> ip(500);
+    ip.upload(std::vector<int>(500, rank + 1));
+    if (rank == 0) {
+        MPI_Reduce(MPI_IN_PLACE, ip.p, 500, MPI_INT, MPI_SUM, 0, MPI_COMM_WORLD);
+        auto red = ip.download();
+        CHECK_RANK(red[0] == size * (size + 1) / 2 && red[499] == red[0]);
+    } else {
+        MPI_Reduce(ip.p, nullptr, 500, MPI_INT, MPI_SUM, 0, MPI_COMM_WORLD);
+    }
+    const int gRoot = size - 1;
+    DevBuf<int> gAll(64 * (size_t)size);
+    if (rank == gRoot) {
+        std::vector<int> pre(64 * (size_t)size, -7);
+        std::fill(pre.begin() + (size_t)gRoot * 64, pre.begin() + (size_t)(gRoot + 1) * 64, gRoot * 3);
+        gAll.upload(pre);
+        MPI_Gather(MPI_IN_PLACE, 0, MPI_DATATYPE_NULL, gAll.p, 64, MPI_INT, gRoot, MPI_COMM_WORLD);
+        auto gg = gAll.download();
+        for (int r = 0; r < size; r++) {
+            CHECK_RANK(gg[(size_t)r * 64] == r * 3 && gg[(size_t)r * 64 + 63] == r * 3);
+        }
+    } else {
+        MPI_Gather(mine.p, 64, MPI_INT, nullptr, 0, MPI_INT, gRoot, MPI_COMM_WORLD);
+    }
+
     // Point to point with device buffers (both ends on the device, and mixed)
     int right = (rank + 1) % size, left = (rank + size - 1) % size;
     DevBuf<int> tok(2048), got(2048);

@@ -414,3 +414,43 @@ TEST_CASE("ptp group barrier on the device", "[gpu][ptp]")
     REQUIRE_EQ(arrived.load(), rounds * n);
     broker.clearGroup(groupId);
 }
+
+TEST_CASE("device snapshot: overlapping diffs are applied in order, like the host image", "[gpu][snapshot]")
+{
+    NEED_GPU();
+    using namespace faabric::util;
+    const size_t size = 4 * HOST_PAGE_SIZE;
+    std::vector<uint8_t> base(size, 0);
+    int start = 10;
+    memcpy(base.data() + 128, &start, 4);
+    auto host = std::make_shared<SnapshotData>(std::span<const uint8_t>(base.data(), base.size()));
+    faabric::snapshot::DeviceSnapshot dsnap(size, 0);
+    dsnap.copyInData(base);
+    // five Sum diffs onto ONE int (what five threads reducing into a shared
+    // variable produce), a Bytewise diff overwritten by a later one, and an
+    // XOR on top of a Bytewise diff
+    std::vector<std::vector<uint8_t>> payloads;
+    std::vector<SnapshotDiff> diffs;
+    auto add = [&](SnapshotDataType t, SnapshotMergeOperation op, uint32_t off, std::vector<uint8_t> bytes) {
+        payloads.push_back(std::move(bytes));
+        diffs.emplace_back(t, op, off, payloads.back());
+    };
+    payloads.reserve(16);
+    for (int k = 1; k <= 5; k++) {
+        std::vector<uint8_t> b(4);
+        memcpy(b.data(), &k, 4);
+        add(SnapshotDataType::Int, SnapshotMergeOperation::Sum, 128, b);
+    }
+    add(SnapshotDataType::Raw, SnapshotMergeOperation::Bytewise, 1000, std::vector<uint8_t>(64, 0x11));
+    add(SnapshotDataType::Raw, SnapshotMergeOperation::Bytewise, 1032, std::vector<uint8_t>(64, 0x22));
+    add(SnapshotDataType::Raw, SnapshotMergeOperation::XOR, 1000, std::vector<uint8_t>(8, 0xff));
+    host->applyDiffs(diffs);
+    dsnap.applyDiffs(diffs);
+    auto got = dsnap.getDataCopy();
+    REQUIRE(memcmp(got.data(), host->getDataPtr(), size) == 0);
+    int sum = 0;
+    memcpy(&sum, got.data() + 128, 4);
+    REQUIRE_EQ(sum, 10 + 15);
+    REQUIRE_EQ((int)got[1000], 0xee);
+    REQUIRE_EQ((int)got[1040], 0x22);
+}

@@ -108,14 +108,18 @@ def test_diff_push_bytewise_and_xor(size, fill):
     exp_pages = np.array([(orig[p * PAGE : (p + 1) * PAGE] != mem[p * PAGE : (p + 1) * PAGE]).any() for p in range(n_pages)])
     assert np.array_equal(page_flags.cpu().numpy().astype(bool), exp_pages)
     assert int(stats[1].item()) == int(exp_pages.sum())
-    # the runs derived from chunk flags cover every differing aligned vector
+    # the runs derived from chunk flags cover EVERY byte that produced a diff:
+    # unaligned heads / tails of regions, the tail of the image and the typed
+    # scalars included (ignored regions produce no diff)
     runs = snap.chunk_runs(chunk_flags, size)
     covered = np.zeros(size, dtype=bool)
     for off, ln in runs:
         covered[off : off + ln] = True
-    vec_end = size & ~15
-    differs = (orig != mem)[:vec_end]
-    assert covered[:vec_end][differs].all()
+    differs = orig != mem
+    for r in regs.host:
+        if r.op == snap.IGNORE:
+            differs[r.offset : (r.offset + r.length) if r.length else size] = False
+    assert covered[differs].all()
 
 
 def test_dirty_page_hint_skips_clean_pages():
@@ -225,6 +229,55 @@ def test_concurrent_writers_merge():
         exp[i + 1] ^= 0xF0
     exp[0:4] = np.array([orig[0:4].view(np.int32)[0] + 16], dtype=np.int32).view(np.uint8)
     assert np.array_equal(d_main.cpu().numpy(), exp)
+
+
+def test_concurrent_writers_merge_unaligned_typed_regions():
+    """Typed merge regions at odd byte offsets (an int at +6, a long at +3 and
+    a double at +5 of their 16-byte blocks): many writers add into the same
+    scalars at once; the 128-bit CAS keeps every contribution."""
+    size = PAGE * 4
+    orig = np.zeros(size, dtype=np.uint8)
+    offs = {"int": 64 + 6, "long": 256 + 3, "double": 1024 + 5}
+    orig[offs["int"] : offs["int"] + 4] = np.array([1000], dtype=np.int32).view(np.uint8)
+    orig[offs["long"] : offs["long"] + 8] = np.array([1 << 40], dtype=np.int64).view(np.uint8)
+    orig[offs["double"] : offs["double"] + 8] = np.array([2.5], dtype=np.float64).view(np.uint8)
+    regs = snap.prepare_regions(
+        [
+            snap.MergeRegion(offs["int"], 4, snap.INT, snap.SUM),
+            snap.MergeRegion(offs["long"], 8, snap.LONG, snap.SUM),
+            snap.MergeRegion(offs["double"], 8, snap.DOUBLE, snap.SUM),
+        ],
+        size,
+        "cuda",
+    )
+    n_writers = 8
+    d_main = dev(orig)
+    d_orig = dev(orig)
+    d_mems = []
+    for w in range(n_writers):
+        m = orig.copy()
+        m[offs["int"] : offs["int"] + 4] = np.array([1000 + (w + 1)], dtype=np.int32).view(np.uint8)
+        m[offs["long"] : offs["long"] + 8] = np.array([(1 << 40) + 10 * (w + 1)], dtype=np.int64).view(np.uint8)
+        m[offs["double"] : offs["double"] + 8] = np.array([2.5 + 0.25 * (w + 1)], dtype=np.float64).view(np.uint8)
+        d_mems.append(dev(m))
+    streams = [torch.cuda.Stream() for _ in range(n_writers)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        d_main.copy_(d_orig)
+        torch.cuda.synchronize()
+        for w in range(n_writers):
+            with torch.cuda.stream(streams[w]):
+                snap.diff_push(d_mems[w], d_orig, d_main, regs)
+        torch.cuda.synchronize()
+        got = d_main.cpu().numpy()
+        tot = n_writers * (n_writers + 1) // 2
+        assert int(got[offs["int"] : offs["int"] + 4].view(np.int32)[0]) == 1000 + tot
+        assert int(got[offs["long"] : offs["long"] + 8].view(np.int64)[0]) == (1 << 40) + 10 * tot
+        assert float(got[offs["double"] : offs["double"] + 8].view(np.float64)[0]) == 2.5 + 0.25 * tot
+        untouched = np.ones(size, dtype=bool)
+        for k, ln in (("int", 4), ("long", 8), ("double", 8)):
+            untouched[offs[k] : offs[k] + ln] = False
+        assert not got[untouched].any()
 
 
 def test_dirty_scan_and_flags_or():
