@@ -652,13 +652,19 @@ def mode_planner(args, dist: Dist):
     from faabric_b200.runtime import planner_fanout_bench
 
     res = planner_fanout_bench(n_functions=1024, n_hosts=8, iters=max(args.steps, 5), warmup=max(args.warmup, 2))
+    ref = planner_fanout_bench(n_functions=1024, n_hosts=8, iters=max(args.steps, 5), warmup=max(args.warmup, 2), mode="refcpu")
     out = {
         "metric": "planner_fanout_fanin_1024_us",
         "value": res["us_per_batch_median"],
         "unit": "us",
         "higher_is_better": False,
         "n_gpus": 0,
+        "refcpu_us": ref["us_per_batch_median"],
+        "vs_refcpu": round(ref["us_per_batch_median"] / res["us_per_batch_median"], 2),
         "details": res,
+        "refcpu_details": ref,
+        "note": "refcpu = the reference's design (every request/result encoded + sent over a loopback socket + decoded), "
+                "run by this repo's planner on the same box",
     }
     return out, {}
 

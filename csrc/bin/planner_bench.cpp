@@ -8,9 +8,94 @@
 #include <faabric/util/logging.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
+#include <map>
 #include <numeric>
+
+#include <cxxabi.h>
+#include <dlfcn.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <sys/time.h>
+
+// ---- --profile: a tiny sampling profiler (SIGPROF every 200 us of CPU time,
+// delivered to whichever thread is running); prints the hottest functions by
+// inclusive samples.  No external tools are available in the build image.
+namespace {
+constexpr int MAX_SAMPLES = 200000;
+constexpr int DEPTH = 24;
+void* g_samples[MAX_SAMPLES][DEPTH];
+int g_depths[MAX_SAMPLES];
+std::atomic<int> g_nSamples{ 0 };
+
+void profHandler(int, siginfo_t*, void*)
+{
+    int i = g_nSamples.fetch_add(1);
+    if (i < MAX_SAMPLES) {
+        g_depths[i] = backtrace(g_samples[i], DEPTH);
+    }
+}
+
+void startProfiler()
+{
+    void* warm[4];
+    backtrace(warm, 4); // loads libgcc outside the handler
+    struct sigaction sa{};
+    sa.sa_sigaction = profHandler;
+    sa.sa_flags = SA_SIGINFO | SA_RESTART;
+    sigaction(SIGPROF, &sa, nullptr);
+    itimerval tv{};
+    tv.it_interval.tv_usec = 200;
+    tv.it_value.tv_usec = 200;
+    setitimer(ITIMER_PROF, &tv, nullptr);
+}
+
+void reportProfiler()
+{
+    itimerval tv{};
+    setitimer(ITIMER_PROF, &tv, nullptr);
+    int n = std::min(g_nSamples.load(), MAX_SAMPLES);
+    std::map<std::string, int> inclusive, self;
+    for (int i = 0; i < n; i++) {
+        std::map<std::string, bool> seen;
+        for (int d = 2; d < g_depths[i]; d++) { // skip handler + signal frame
+            Dl_info info;
+            std::string name = "?";
+            if (dladdr(g_samples[i][d], &info) && info.dli_sname) {
+                int st = 0;
+                char* dem = abi::__cxa_demangle(info.dli_sname, nullptr, nullptr, &st);
+                name = st == 0 && dem ? dem : info.dli_sname;
+                free(dem);
+            }
+            if (name.size() > 90) {
+                name.resize(90);
+            }
+            if (d == 2) {
+                self[name]++;
+            }
+            if (!seen[name]) {
+                seen[name] = true;
+                inclusive[name]++;
+            }
+        }
+    }
+    auto top = [&](std::map<std::string, int>& m, const char* title) {
+        std::vector<std::pair<int, std::string>> v;
+        for (auto& [k, c] : m) {
+            v.emplace_back(c, k);
+        }
+        std::sort(v.rbegin(), v.rend());
+        fprintf(stderr, "---- %s (of %d samples) ----\n", title, n);
+        for (size_t i = 0; i < v.size() && i < 28; i++) {
+            fprintf(stderr, "%6.2f%%  %s\n", 100.0 * v[i].first / std::max(n, 1), v[i].second.c_str());
+        }
+    };
+    top(self, "self");
+    top(inclusive, "inclusive");
+}
+}
 
 using namespace faabric::executor;
 
@@ -36,7 +121,30 @@ class NoopFactory : public ExecutorFactory
 int main(int argc, char** argv)
 {
     int nFunctions = 1024, nHosts = 8, iters = 20, warmup = 3;
+    bool profile = false;
+    // --mode refcpu: the reference's control-plane design on the same box -
+    // every request and result is encoded, sent over a (loopback) socket and
+    // decoded again, results funnel through the planner's RPC workers
+    // (reference: src/planner/Planner.cpp:807-1394, PlannerServer.cpp:227-248,
+    // FunctionCallClient.cpp:66-131).  Default: this repo's typed in-process
+    // hand-off between the planner and the per-GPU hosts of one worker.
+    std::string mode = "native";
+    for (int i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "--profile")) {
+            profile = true;
+        }
+        if (!strcmp(argv[i], "--mode") && i + 1 < argc) {
+            mode = argv[i + 1];
+        }
+    }
+    if (mode == "refcpu") {
+        setenv("FAABRIC_INPROC_RPC", "0", 1);
+    }
     for (int i = 1; i + 1 < argc; i += 2) {
+        if (!strcmp(argv[i], "--profile")) {
+            i--;
+            continue;
+        }
         if (!strcmp(argv[i], "--functions")) {
             nFunctions = atoi(argv[i + 1]);
         } else if (!strcmp(argv[i], "--hosts")) {
@@ -45,6 +153,8 @@ int main(int argc, char** argv)
             iters = atoi(argv[i + 1]);
         } else if (!strcmp(argv[i], "--warmup")) {
             warmup = atoi(argv[i + 1]);
+        } else if (!strcmp(argv[i], "--mode")) {
+            // parsed above
         }
     }
     setenv("LOG_LEVEL", "warn", 0);
@@ -57,6 +167,9 @@ int main(int argc, char** argv)
 
     std::vector<double> totalUs, scheduleUs;
     for (int it = 0; it < warmup + iters; it++) {
+        if (profile && it == warmup) {
+            startProfiler();
+        }
         auto req = faabric::util::batchExecFactory("bench", "noop", nFunctions);
         auto t0 = std::chrono::steady_clock::now();
         auto decision = cli.callFunctions(req);
@@ -76,12 +189,16 @@ int main(int argc, char** argv)
             totalUs.push_back(std::chrono::duration<double, std::micro>(t2 - t0).count());
         }
     }
+    if (profile) {
+        reportProfiler();
+    }
     std::sort(totalUs.begin(), totalUs.end());
     std::sort(scheduleUs.begin(), scheduleUs.end());
     double med = totalUs[totalUs.size() / 2];
-    printf("{\"bench\": \"planner_fanout\", \"functions\": %d, \"hosts\": %d, \"iters\": %d, "
+    printf("{\"bench\": \"planner_fanout\", \"mode\": \"%s\", \"functions\": %d, \"hosts\": %d, \"iters\": %d, "
            "\"e2e_us_median\": %.1f, \"e2e_us_min\": %.1f, \"e2e_us_max\": %.1f, \"schedule_us_median\": %.1f, "
            "\"functions_per_s\": %.0f}\n",
+           mode.c_str(),
            nFunctions,
            nHosts,
            iters,

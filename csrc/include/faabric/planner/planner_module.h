@@ -134,6 +134,8 @@ struct PlannerState
     // inFlightReqs: results are recorded in O(1) and the request/decision
     // vectors are compacted in one pass before anybody reads them
     std::map<int, std::unordered_set<int>> finishedInFlight;
+    // appId -> (message id -> position in the app's scheduling decision)
+    std::map<int, std::unordered_map<int, int>> inFlightIdPos;
 
     // Placements fixed ahead of time (MPI / OpenMP two-step creation, tests)
     std::map<int, std::shared_ptr<batch_scheduler::SchedulingDecision>>

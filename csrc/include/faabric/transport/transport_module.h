@@ -4,6 +4,8 @@
 // (faabric/transport/*.h) forward here, so either include style works.
 #pragma once
 
+#include <functional>
+
 #include <faabric/batch-scheduler/SchedulingDecision.h>
 #include <faabric/proto/faabric.pb.h>
 #include <faabric/util/barrier.h>
@@ -527,6 +529,10 @@ class MessageEndpointServerHandler
     // In-process delivery: enqueue for a worker (async)
     void deliverLocal(Message&& msg);
 
+    // In-process delivery of a TYPED request: the closure runs on a worker in
+    // place of doAsyncRecv (no encode / decode of the payload)
+    void deliverLocalTask(std::function<void()> task);
+
     int getPort() const { return port; }
 
   private:
@@ -577,6 +583,14 @@ class MessageEndpointServer
     MessageEndpointServerHandler* getAsyncHandler() { return &asyncHandler; }
 
     static MessageEndpointServer* findLocal(int port, bool sync);
+
+    // Typed in-process requests (see deliverLocalTask)
+    void runAsyncTask(const std::function<void()>& task);
+
+    // The server of this process listening on `port`, if any, when `host`
+    // resolves to this process (virtual hosts included) and the in-process
+    // fast path is enabled
+    static MessageEndpointServer* localServerFor(const std::string& host, int basePort, bool sync);
 
   protected:
     int asyncPort;

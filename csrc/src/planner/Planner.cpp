@@ -221,6 +221,7 @@ void Planner::flushSchedulingState()
     state.stateMains.clear();
     state.inFlightReqs.clear();
     state.finishedInFlight.clear();
+    state.inFlightIdPos.clear();
     appFinishedCv.notify_all();
     state.appResults.clear();
     state.appResultWaiters.clear();
@@ -380,8 +381,24 @@ void Planner::setMessageResult(std::shared_ptr<faabric::Message> msg)
             auto& done = state.finishedInFlight[appId];
             // Ids are plain ints: a linear look-up is cheap, moving Message
             // objects around for every result is not
+            // position of the message in the decision: hashed once per app (a
+            // linear look-up per result is quadratic for a 1024-way fan-out)
             const auto& ids = decision->messageIds;
-            auto pos = std::find(ids.begin(), ids.end(), msgId);
+            auto& posOf = state.inFlightIdPos[appId];
+            if (posOf.size() != ids.size()) {
+                posOf.clear();
+                posOf.reserve(ids.size());
+                for (size_t k = 0; k < ids.size(); k++) {
+                    posOf.emplace(ids[k], (int)k);
+                }
+            }
+            auto posIt = posOf.find(msgId);
+            auto pos = posIt == posOf.end() ? ids.end() : ids.begin() + posIt->second;
+            if (pos != ids.end() && *pos != msgId) {
+                // the decision was edited (message removed / reordered): rebuild
+                posOf.clear();
+                pos = std::find(ids.begin(), ids.end(), msgId);
+            }
             if (pos != ids.end() && done.insert(msgId).second) {
                 int port = decision->mpiPorts.at((size_t)(pos - ids.begin()));
                 if (hostIt != state.hostMap.end()) {
@@ -391,6 +408,7 @@ void Planner::setMessageResult(std::shared_ptr<faabric::Message> msg)
                     SPDLOG_DEBUG("Planner removing app {} from in-flight", appId);
                     state.inFlightReqs.erase(inFlight);
                     state.finishedInFlight.erase(appId);
+                    state.inFlightIdPos.erase(appId);
                     state.preloadedSchedulingDecisions.erase(appId);
                     appFinishedCv.notify_all();
                 }
@@ -549,6 +567,7 @@ void Planner::compactInFlightLocked()
         it->second.second = newDecision;
     }
     state.finishedInFlight.clear();
+    state.inFlightIdPos.clear();
 }
 
 bool Planner::waitForAppToFinish(int32_t appId, int timeoutMs)

@@ -147,8 +147,25 @@ void PlannerClient::removeHost(std::shared_ptr<RemoveHostRequest> req)
     syncSend(PlannerCalls::RemoveHost, req.get(), &resp);
 }
 
+// The planner of THIS process (a worker that embeds it: LocalCluster, the
+// single-box deployment)?  The hot calls of a fan-out then hand typed objects
+// over directly instead of encoding / decoding every message of the batch.
+static bool plannerIsInProcess(const std::string& plannerHost)
+{
+    if (faabric::util::isMockMode() || faabric::util::FaultInjector::get().armed()) {
+        return false;
+    }
+    return faabric::transport::MessageEndpointServer::localServerFor(plannerHost, PLANNER_SYNC_PORT, true) != nullptr;
+}
+
 void PlannerClient::setMessageResult(std::shared_ptr<faabric::Message> msg)
 {
+    if (plannerIsInProcess(host)) {
+        // runs on the executor's thread: results of a fan-out are recorded in
+        // parallel instead of queueing for the planner's RPC workers
+        faabric::planner::getPlanner().setMessageResult(std::move(msg));
+        return;
+    }
     asyncSend(PlannerCalls::SetMessageResult, msg.get());
 }
 
@@ -246,6 +263,14 @@ faabric::Message PlannerClient::doGetMessageResult(std::shared_ptr<faabric::Mess
 std::shared_ptr<faabric::BatchExecuteRequestStatus> PlannerClient::getBatchResults(
   std::shared_ptr<faabric::BatchExecuteRequest> req)
 {
+    if (plannerIsInProcess(host)) {
+        auto direct = faabric::planner::getPlanner().getBatchResults(req->appid());
+        if (direct == nullptr) {
+            direct = faabric::util::batchExecStatusFactory(req->appid());
+            direct->set_appid(0);
+        }
+        return direct;
+    }
     auto status = std::make_shared<faabric::BatchExecuteRequestStatus>();
     syncSend(PlannerCalls::GetBatchResults, req.get(), status.get());
     return status;
@@ -294,9 +319,17 @@ faabric::batch_scheduler::SchedulingDecision PlannerClient::callFunctions(
     }
 snapshotDone:
 
-    faabric::PointToPointMappings resp;
-    syncSend(PlannerCalls::CallBatch, req.get(), &resp);
-    auto decision = faabric::batch_scheduler::SchedulingDecision::fromPointToPointMappings(resp);
+    faabric::batch_scheduler::SchedulingDecision decision(NOT_ENOUGH_SLOTS, NOT_ENOUGH_SLOTS);
+    if (plannerIsInProcess(host)) {
+        // the planner keeps (and mutates) its own copy of the request, exactly
+        // as it would after decoding one from the wire
+        auto own = std::make_shared<faabric::BatchExecuteRequest>(*req);
+        decision = *faabric::planner::getPlanner().callBatch(own);
+    } else {
+        faabric::PointToPointMappings resp;
+        syncSend(PlannerCalls::CallBatch, req.get(), &resp);
+        decision = faabric::batch_scheduler::SchedulingDecision::fromPointToPointMappings(resp);
+    }
     // An elastically scaled-up request came back bigger than it went in: mirror
     // the extra messages so the caller waits for (and accounts) all of them
     if (req->elasticscalehint() && decision.nFunctions > req->messages_size() && req->messages_size() > 0) {

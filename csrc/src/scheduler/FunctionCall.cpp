@@ -113,6 +113,24 @@ void FunctionCallClient::executeFunctions(std::shared_ptr<faabric::BatchExecuteR
         batchMessages.emplace_back(host, req);
         return;
     }
+    if (!faabric::util::FaultInjector::get().armed()) {
+        if (auto* local = faabric::transport::MessageEndpointServer::localServerFor(host, FUNCTION_CALL_ASYNC_PORT, false)) {
+            // Same process (a worker serving this - possibly virtual - host):
+            // hand the request object to the server's workers as it is
+            std::string target = host;
+            local->getAsyncHandler()->deliverLocalTask([req, target] {
+                auto& sch = faabric::scheduler::getScheduler();
+                long now = faabric::util::getGlobalClock().epochMillis();
+                for (int i = 0; i < req->messages_size(); i++) {
+                    auto* m = req->mutable_messages(i);
+                    m->set_starttimestamp(now);
+                    m->set_executedhost(target.empty() ? sch.getThisHost() : target);
+                }
+                sch.executeBatch(req);
+            });
+            return;
+        }
+    }
     std::string buf = wrapWithHost(host, req->SerializeAsString());
     asyncSend(FunctionCalls::ExecuteFunctions, (const uint8_t*)buf.data(), buf.size());
 }

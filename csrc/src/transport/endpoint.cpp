@@ -484,6 +484,7 @@ struct WorkItem
     int fd = -1; // connection to answer on (sync), -1 for in-process
     Message msg;
     bool poison = false;
+    std::function<void()> task; // typed in-process request
 };
 
 struct Conn
@@ -524,6 +525,13 @@ void MessageEndpointServerHandler::deliverLocal(Message&& msg)
 {
     auto item = std::make_shared<WorkItem>();
     item->msg = std::move(msg);
+    impl->work.enqueue(std::move(item));
+}
+
+void MessageEndpointServerHandler::deliverLocalTask(std::function<void()> task)
+{
+    auto item = std::make_shared<WorkItem>();
+    item->task = std::move(task);
     impl->work.enqueue(std::move(item));
 }
 
@@ -689,7 +697,9 @@ void MessageEndpointServerHandler::start(int timeoutMs)
                     break;
                 }
                 try {
-                    if (async) {
+                    if (item->task) {
+                        server->runAsyncTask(item->task);
+                    } else if (async) {
                         server->handleAsync(item->msg);
                     } else {
                         std::string resp = server->handleSync(item->msg);
@@ -820,6 +830,24 @@ void MessageEndpointServer::handleAsync(Message& msg)
 {
     doAsyncRecv(msg);
     afterRequest();
+}
+
+void MessageEndpointServer::runAsyncTask(const std::function<void()>& task)
+{
+    task();
+    afterRequest();
+}
+
+MessageEndpointServer* MessageEndpointServer::localServerFor(const std::string& host, int basePort, bool sync)
+{
+    if (!inprocRpcEnabled()) {
+        return nullptr;
+    }
+    HostAddress a = parseHostAddress(host);
+    if (!isLocalAddress(a.ip)) {
+        return nullptr;
+    }
+    return findLocal(basePort + a.portOffset, sync);
 }
 
 std::string MessageEndpointServer::handleSync(Message& msg)

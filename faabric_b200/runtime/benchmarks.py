@@ -9,16 +9,18 @@ import subprocess
 from .cluster import BINDIR, LocalCluster
 
 
-def planner_fanout_bench(n_functions: int = 1024, n_hosts: int = 8, iters: int = 20, warmup: int = 3) -> dict:
+def planner_fanout_bench(n_functions: int = 1024, n_hosts: int = 8, iters: int = 20, warmup: int = 3, mode: str = "native") -> dict:
     """Batch-schedule `n_functions` no-ops over `n_hosts` (virtual GPU) hosts,
-    fan-out + fan-in, planner and worker in one process."""
+    fan-out + fan-in, planner and worker in one process.  ``mode="refcpu"``
+    runs the reference's control-plane design on the same box: every request
+    and result encoded, sent over a loopback socket and decoded."""
     exe = BINDIR / "planner_bench"
     if not exe.exists():
         from .. import build as _build
 
         _build.build(verbose=False)
     r = subprocess.run(
-        [str(exe), "--functions", str(n_functions), "--hosts", str(n_hosts), "--iters", str(iters), "--warmup", str(warmup)],
+        [str(exe), "--functions", str(n_functions), "--hosts", str(n_hosts), "--iters", str(iters), "--warmup", str(warmup), "--mode", mode],
         capture_output=True,
         text=True,
         timeout=600,
