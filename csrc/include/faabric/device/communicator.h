@@ -50,6 +50,10 @@ struct CommConfig
     // CTAs of a grouped all-reduce launch (0 = as many as there are barrier
     // slots for the channel, capped at 128)
     int groupBlocks = 0;
+    // Loopback backend (FAABRIC_DEVICE_BACKEND=loopback): heaps and signal
+    // pads in host memory, every kernel replaced by its host twin executed on
+    // the calling rank thread.  No GPU needed; one thread per rank.
+    bool loopback = false;
     // Cross-rank synchronisation with stream memory operations instead of
     // in-kernel spins: needed when kernels of different ranks may not be
     // co-resident (ranks sharing one GPU, kernel-serialising profilers).
@@ -129,6 +133,7 @@ class Communicator
     int size() const { return dev_.nranks; }
     int device() const { return device_; }
     bool hasMulticast() const { return dev_.mcHeap != nullptr; }
+    bool isLoopback() const { return loop_; }
     const std::string& backing() const { return backing_; }
     const FbCommDev& devStruct() const { return dev_; }
     CommConfig& config() { return cfg_; }
@@ -287,6 +292,10 @@ class Communicator
 
     static const char* errorString(int code);
 
+    // Loopback backend: is `p` inside the heap of some loopback communicator?
+    // (the MPI layer treats that memory as "device" memory)
+    static bool isLoopbackHeapPointer(const void* p);
+
   private:
     Communicator() = default;
 
@@ -317,6 +326,9 @@ class Communicator
     uint32_t recvSeq_[FB_MAX_RANKS] = { 0 };
     uint32_t sbarEpoch_[FB_MAX_CHANNELS] = { 0 };
     uint32_t userSigConsumed_[FB_SIG_USER_WORDS] = { 0 };
+    bool loop_ = false;
+    void bindDevice() const;
+    cudaError_t copyD2D(void* dst, const void* src, size_t bytes, cudaStream_t s);
     bool streamSync_ = false;
     bool streamWaitOk_ = false;
     bool streamWriteOk_ = false;

@@ -490,6 +490,8 @@ class MpiWorld
     // grouped kernel at the next wait (FAABRIC_MPI_GROUP_IALLREDUCE=0: one
     // kernel per call over the channels, the round-1 behaviour)
     bool groupIallreduce = true;
+    // FAABRIC_ALLREDUCE_ALGO (FbAlgo; AUTO = measured table / thresholds)
+    int forcedAllReduceAlgo = 0;
     void ensureDeviceComms();
 
     // Host buffers, all ranks in this process: the ranks reduce straight out

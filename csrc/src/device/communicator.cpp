@@ -4,6 +4,7 @@
 #include "faabric/device/bootstrap.h"
 #include "faabric/device/cuda_driver.h"
 #include "launch_api.h"
+#include "loopback_kernels.h"
 
 #include <algorithm>
 #include <chrono>
@@ -72,6 +73,9 @@ CommConfig CommConfig::fromEnv()
     c.nvlsMinBytes = envSize("FAABRIC_NVLS_MIN_BYTES", c.nvlsMinBytes);
     c.p2pBounceBytes = envSize("FAABRIC_P2P_BOUNCE_BYTES", c.p2pBounceBytes);
     c.groupBlocks = (int)envSize("FAABRIC_GROUP_BLOCKS", (size_t)c.groupBlocks);
+    if (const char* be = getenv("FAABRIC_DEVICE_BACKEND")) {
+        c.loopback = std::string(be) == "loopback";
+    }
     if (getenv("FAABRIC_STREAM_SYNC") != nullptr) {
         c.streamSync = envSize("FAABRIC_STREAM_SYNC", 0) != 0 ? 1 : 0;
     }
@@ -284,6 +288,22 @@ const char* Communicator::errorString(int code)
     }
 }
 
+namespace {
+std::mutex loopRangesMx;
+std::vector<std::pair<const uint8_t*, size_t>> loopRanges;
+}
+
+bool Communicator::isLoopbackHeapPointer(const void* p)
+{
+    std::lock_guard<std::mutex> lk(loopRangesMx);
+    for (const auto& [base, n] : loopRanges) {
+        if ((const uint8_t*)p >= base && (const uint8_t*)p < base + n) {
+            return true;
+        }
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------------------
 // Backing memory
 // ---------------------------------------------------------------------------
@@ -303,9 +323,22 @@ struct Communicator::Backing
     bool hasMc = false;
     std::vector<uint32_t*> errWords;
     std::vector<int> errDevices;
+    std::vector<void*> hostAllocs; // loopback backend
 
     ~Backing()
     {
+        if (!hostAllocs.empty()) {
+            {
+                std::lock_guard<std::mutex> lk(loopRangesMx);
+                for (void* p : hostAllocs) {
+                    std::erase_if(loopRanges, [p](const auto& r) { return r.first == (const uint8_t*)p; });
+                }
+            }
+            for (void* p : hostAllocs) {
+                ::free(p);
+            }
+            return;
+        }
         const DriverApi& api = getDriverApi();
         for (void* p : ipcOpened) {
             cudaIpcCloseMemHandle(p);
@@ -437,7 +470,7 @@ std::vector<std::shared_ptr<Communicator>> Communicator::createLocal(
     if (nranks < 1 || nranks > FB_MAX_RANKS || (int)devices.size() != nranks) {
         throw std::invalid_argument("createLocal: bad rank/device list");
     }
-    if (!cudaAvailable()) {
+    if (!cfgIn.loopback && !cudaAvailable()) {
         throw std::runtime_error("createLocal: no CUDA device");
     }
     std::vector<std::shared_ptr<Communicator>> comms;
@@ -453,6 +486,46 @@ std::vector<std::shared_ptr<Communicator>> Communicator::createLocal(
         comms.push_back(c);
     }
     const size_t total = SIG_REGION + comms[0]->heapTotal_;
+    if (cfgIn.loopback) {
+        // ---- loopback: host memory, host twins of the kernels ----
+        auto backing = std::make_shared<Backing>();
+        auto group = std::make_shared<LocalGroup>(nranks);
+        std::vector<uint8_t*> bases(nranks, nullptr);
+        for (int r = 0; r < nranks; r++) {
+            void* p = nullptr;
+            if (posix_memalign(&p, 4096, total) != 0) {
+                throw std::bad_alloc();
+            }
+            // only the control areas need zeroing (the user heap may be GiBs)
+            memset(p, 0, SIG_REGION + comms[r]->userOff_);
+            backing->hostAllocs.push_back(p);
+            bases[r] = (uint8_t*)p;
+            std::lock_guard<std::mutex> lk(loopRangesMx);
+            loopRanges.emplace_back((const uint8_t*)p, total);
+        }
+        for (int r = 0; r < nranks; r++) {
+            void* e = nullptr;
+            if (posix_memalign(&e, 256, 256) != 0) {
+                throw std::bad_alloc();
+            }
+            memset(e, 0, 256);
+            backing->hostAllocs.push_back(e);
+            auto& c = comms[r];
+            c->loop_ = true;
+            for (int p = 0; p < nranks; p++) {
+                c->dev_.sig[p] = reinterpret_cast<uint32_t*>(bases[p]);
+                c->dev_.heap[p] = bases[p] + SIG_REGION;
+            }
+            c->dev_.mcHeap = nullptr;
+            c->dev_.err = (uint32_t*)e;
+            c->dev_.timeoutNs = c->cfg_.timeoutMs * 1000000ull;
+            c->backingState_ = backing;
+            c->backing_ = "loopback";
+            c->localGroup_ = group;
+            c->finishSetup();
+        }
+        return comms;
+    }
     std::set<int> distinct(devices.begin(), devices.end());
     std::vector<int> distinctDevs(distinct.begin(), distinct.end());
     const bool allDistinct = (int)distinct.size() == nranks;
@@ -904,10 +977,29 @@ std::shared_ptr<Communicator> Communicator::createIpc(int rank,
     return c;
 }
 
+void Communicator::bindDevice() const
+{
+    if (!loop_) {
+        cudaSetDevice(device_);
+    }
+}
+
+cudaError_t Communicator::copyD2D(void* dst, const void* src, size_t bytes, cudaStream_t s)
+{
+    if (loop_) {
+        memmove(dst, src, bytes);
+        return cudaSuccess;
+    }
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
+}
+
 cudaStream_t Communicator::internalStream()
 {
+    if (loop_) {
+        return nullptr;
+    }
     if (internalStream_ == nullptr) {
-        cudaSetDevice(device_);
+        bindDevice();
         if (cudaStreamCreateWithFlags(&internalStream_, cudaStreamNonBlocking) != cudaSuccess) {
             cudaGetLastError();
             internalStream_ = nullptr;
@@ -919,7 +1011,7 @@ cudaStream_t Communicator::internalStream()
 Communicator::~Communicator()
 {
     if (internalStream_ != nullptr) {
-        cudaSetDevice(device_);
+        bindDevice();
         cudaStreamDestroy(internalStream_);
         cudaGetLastError();
     }
@@ -1099,7 +1191,7 @@ int Communicator::pickAllReduceAlgo(uint64_t bytes, bool nvlsOk) const
 
 uint32_t Communicator::checkError(cudaStream_t s)
 {
-    cudaSetDevice(device_);
+    bindDevice();
     // bounded: a stream-level wait whose peer died would block forever
     if (!syncStreamBounded(s, cfg_.timeoutMs * 3)) {
         uint32_t e = peekError();
@@ -1146,7 +1238,7 @@ int Communicator::reduceLike(int kind,
     if (L == nullptr) {
         return FB_E_UNSUPPORTED;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     bool symmetric = (flags & FB_FLAG_SYMMETRIC) != 0;
     // stream-ordered synchronisation replaces the in-kernel barriers
     const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
@@ -1257,6 +1349,9 @@ int Communicator::reduceLike(int kind,
                              FB_LL_AREA_BYTES(n);
         stats_.launches++;
         stats_.bytes += bytes;
+        if (loop_) {
+            return fb::host::llAllReduce(a, dtype, op) == 0 ? FB_OK : FB_E_CUDA;
+        }
         return L->ll(a, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
     }
 
@@ -1300,11 +1395,7 @@ int Communicator::reduceLike(int kind,
         const uint64_t len = std::min<uint64_t>(chunkMax, bytes - done);
         uint64_t sendOff;
         if (stageSend) {
-            if (cudaMemcpyAsync(heapPtr(stageSendOff_),
-                                (const uint8_t*)send + done,
-                                len,
-                                cudaMemcpyDeviceToDevice,
-                                s) != cudaSuccess) {
+            if (copyD2D(heapPtr(stageSendOff_), (const uint8_t*)send + done, len, s) != cudaSuccess) {
                 return FB_E_CUDA;
             }
             stats_.stagedCopies++;
@@ -1409,7 +1500,11 @@ int Communicator::reduceLike(int kind,
                 a.tailOwner = -2;
             }
             int perThread = (n == 8) ? 2 : 4;
-            ce = L->reduce(a, n, blocksFor(work, perThread), cfg_.threads, s);
+            if (loop_) {
+                ce = fb::host::reduceKernel(a, dtype, op, blocksFor(work, perThread)) == 0 ? cudaSuccess : cudaErrorUnknown;
+            } else {
+                ce = L->reduce(a, n, blocksFor(work, perThread), cfg_.threads, s);
+            }
         }
         if (ce != cudaSuccess) {
             return FB_E_CUDA;
@@ -1421,11 +1516,7 @@ int Communicator::reduceLike(int kind,
         stats_.bytes += len;
         if (stageRecv && isRootOrAll) {
             uint64_t outLen = (kind == K_REDUCE_SCATTER) ? count * esize : len;
-            if (cudaMemcpyAsync((uint8_t*)recv + done,
-                                heapPtr(stageRecvOff_),
-                                outLen,
-                                cudaMemcpyDeviceToDevice,
-                                s) != cudaSuccess) {
+            if (copyD2D((uint8_t*)recv + done, heapPtr(stageRecvOff_), outLen, s) != cudaSuccess) {
                 return FB_E_CUDA;
             }
             stats_.stagedCopies++;
@@ -1516,9 +1607,16 @@ struct Communicator::GroupPlan
     int dtype = 0;
     int device = 0;
     size_t items = 0;
+    bool hostTables = false; // loopback: plain heap memory
 
     ~GroupPlan()
     {
+        if (hostTables) {
+            for (auto& l : launches) {
+                ::free(l.dSegs);
+            }
+            return;
+        }
         cudaSetDevice(device);
         for (auto& l : launches) {
             if (l.dSegs != nullptr) {
@@ -1648,7 +1746,7 @@ std::shared_ptr<Communicator::GroupPlan> Communicator::prepareGroup(
         rc = FB_E_INVALID;
         return nullptr;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     auto plan = std::make_shared<GroupPlan>();
     plan->dtype = dtype;
     plan->device = device_;
@@ -1668,6 +1766,15 @@ std::shared_ptr<Communicator::GroupPlan> Communicator::prepareGroup(
         // (a rank may own nothing of a tiny group: it still takes part in the
         // barriers, with an empty table)
         const size_t tb = std::max<size_t>(sb.segs.size(), 1) * sizeof(fb::GroupSeg);
+        if (loop_) {
+            plan->hostTables = true;
+            l.dSegs = (fb::GroupSeg*)::malloc(tb);
+            if (!sb.segs.empty()) {
+                memcpy(l.dSegs, sb.segs.data(), sb.segs.size() * sizeof(fb::GroupSeg));
+            }
+            plan->launches.push_back(l);
+            continue;
+        }
         if (cudaMalloc((void**)&l.dSegs, tb) != cudaSuccess) {
             cudaGetLastError();
             rc = FB_E_CUDA;
@@ -1704,7 +1811,7 @@ int Communicator::allReduceGroup(const GroupPlan& plan, int op, int flags, cudaS
     if (L == nullptr || L->group == nullptr) {
         return FB_E_UNSUPPORTED;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     const int n = dev_.nranks;
     const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
     for (const auto& l : plan.launches) {
@@ -1718,7 +1825,9 @@ int Communicator::allReduceGroup(const GroupPlan& plan, int op, int flags, cudaS
         if (ss && streamBarrier(flags, s) != FB_OK) {
             return FB_E_CUDA;
         }
-        if (L->group(a, groupGrid(cfg_, n, l.vecsPerRank), cfg_.threads, s) != cudaSuccess) {
+        if (loop_) {
+            fb::host::groupAllReduce(a, plan.dtype, op, groupGrid(cfg_, n, l.vecsPerRank));
+        } else if (L->group(a, groupGrid(cfg_, n, l.vecsPerRank), cfg_.threads, s) != cudaSuccess) {
             return FB_E_CUDA;
         }
         if (ss && streamBarrier(flags, s) != FB_OK) {
@@ -1748,7 +1857,7 @@ int Communicator::allReduceMany(const GroupItem* items,
     if (L == nullptr) {
         return FB_E_UNSUPPORTED;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     const int n = dev_.nranks;
     const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
     // try the grouped path batch by batch; anything not symmetric / aligned
@@ -1770,6 +1879,20 @@ int Communicator::allReduceMany(const GroupItem* items,
                     return r2;
                 }
             }
+            continue;
+        }
+        if (loop_) {
+            fb::GroupArgs la;
+            memset(&la, 0, sizeof(la));
+            la.comm = devFor(flags);
+            la.segs = sb.segs.data();
+            la.nSegs = (uint32_t)sb.segs.size();
+            la.totalChunks = sb.totalChunks;
+            la.noSync = (flags & FB_FLAG_NOSYNC) ? 1 : 0;
+            fb::host::groupAllReduce(la, dtype, op, groupGrid(cfg_, n, sb.vecsPerRank));
+            stats_.launches++;
+            stats_.bytes += sb.bytes;
+            stats_.algoCount[FB_ALGO_TWOSHOT]++;
             continue;
         }
         // table slot: pinned staging + device copy, recycled after its launch
@@ -1810,7 +1933,10 @@ int Communicator::allReduceMany(const GroupItem* items,
         if (ss && streamBarrier(flags, s) != FB_OK) {
             return FB_E_CUDA;
         }
-        if (L->group(a, groupGrid(cfg_, n, sb.vecsPerRank), cfg_.threads, s) != cudaSuccess) {
+        if (loop_) {
+            a.segs = sb.segs.data(); // the host twin reads the table in place
+            fb::host::groupAllReduce(a, dtype, op, groupGrid(cfg_, n, sb.vecsPerRank));
+        } else if (L->group(a, groupGrid(cfg_, n, sb.vecsPerRank), cfg_.threads, s) != cudaSuccess) {
             return FB_E_CUDA;
         }
         if (ss && streamBarrier(flags, s) != FB_OK) {
@@ -1839,7 +1965,7 @@ int Communicator::moveLike(int mode,
 {
     const int n = dev_.nranks;
     const int rank = dev_.rank;
-    cudaSetDevice(device_);
+    bindDevice();
     const bool symmetric = (flags & FB_FLAG_SYMMETRIC) != 0;
     const bool ss = streamSync_ && !(flags & FB_FLAG_NOSYNC) && n > 1;
     const int noSync = ((flags & FB_FLAG_NOSYNC) || ss) ? 1 : 0;
@@ -1916,6 +2042,9 @@ int Communicator::moveLike(int mode,
         stats_.algoCount[FB_ALGO_TWOSHOT]++;
         stats_.launches++;
         stats_.bytes += chunkBytes;
+        if (loop_) {
+            return fb::host::moveKernel(a, blocksFor(chunkBytes / 16 / n, 4)) == 0 ? FB_OK : FB_E_CUDA;
+        }
         return fb::launchMove(
                  a, 16, blocksFor(chunkBytes / 16 / n, 4), cfg_.threads, s) ==
                    cudaSuccess
@@ -1960,11 +2089,12 @@ int Communicator::moveLike(int mode,
                   (const uint8_t*)((mode == fb::MOVE_BCAST) ? recv : send);
                 cudaError_t ce;
                 if (srcRows == 1) {
-                    ce = cudaMemcpyAsync(heapPtr(stageSendOff_),
-                                         src + done,
-                                         len,
-                                         cudaMemcpyDeviceToDevice,
-                                         s);
+                    ce = copyD2D(heapPtr(stageSendOff_), src + done, len, s);
+                } else if (loop_) {
+                    for (int row = 0; row < srcRows; row++) {
+                        memcpy(heapPtr(stageSendOff_) + (size_t)row * len, src + done + (size_t)row * chunkBytes, len);
+                    }
+                    ce = cudaSuccess;
                 } else {
                     ce = cudaMemcpy2DAsync(heapPtr(stageSendOff_),
                                            len,
@@ -1991,8 +2121,10 @@ int Communicator::moveLike(int mode,
         if (ss && streamBarrier(flags, s) != FB_OK) {
             return FB_E_CUDA;
         }
-        if (width == 16 && cfg_.tmaMinBytes > 0 && len >= cfg_.tmaMinBytes &&
-            fb::moveBulkSupported(a)) {
+        if (loop_) {
+            ce = fb::host::moveKernel(a, blocksFor(words, 2)) == 0 ? cudaSuccess : cudaErrorUnknown;
+        } else if (width == 16 && cfg_.tmaMinBytes > 0 && len >= cfg_.tmaMinBytes &&
+                   fb::moveBulkSupported(a)) {
             // Large chunks: the copy engine streams 32 KiB tiles through
             // shared memory; a few CTAs (>= 4 tiles each) saturate the link
             const uint64_t pieces =
@@ -2092,13 +2224,16 @@ int Communicator::allToAll(const void* send,
 int Communicator::barrier(cudaStream_t s)
 {
     NvtxRange nvtxRange("fb::barrier");
-    cudaSetDevice(device_);
+    bindDevice();
     if (dev_.nranks == 1) {
         return FB_OK;
     }
     stats_.launches++;
     if (streamSync_) {
         return streamBarrier(0, s);
+    }
+    if (loop_) {
+        return fb::host::barrierKernel(dev_) == 0 ? FB_OK : FB_E_CUDA;
     }
     return fb::launchBarrier(dev_, s) == cudaSuccess ? FB_OK : FB_E_CUDA;
 }
@@ -2108,13 +2243,20 @@ int Communicator::barrier(cudaStream_t s)
 // ---------------------------------------------------------------------------
 void Communicator::finishSetup()
 {
+    if (loop_) {
+        // the host twins synchronise inside the "kernels", like the GPU ones
+        streamSync_ = false;
+        streamWaitOk_ = false;
+        streamWriteOk_ = false;
+        return;
+    }
     streamSync_ = cfg_.streamSync > 0;
     streamWaitOk_ = false;
     const DriverApi& api = getDriverApi();
     const char* off = getenv("FAABRIC_STREAM_MEMOPS");
     if (api.cuStreamWaitValue32 != nullptr && !(off != nullptr && off[0] == '0')) {
         // self-test: a wait that is already satisfied on a word of our own pad
-        cudaSetDevice(device_);
+        bindDevice();
         cudaStream_t t = nullptr;
         if (cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking) == cudaSuccess) {
             CUresult r = api.cuStreamWaitValue32(
@@ -2160,6 +2302,9 @@ int Communicator::streamWaitGe(cudaStream_t s,
         }
         // e.g. not permitted in this capture mode: use the spin kernel
     }
+    if (loop_) {
+        return fb::host::waitFlagGe(dev_, localWord, value, FB_ERR_FLAG_TIMEOUT) ? FB_OK : FB_E_CUDA;
+    }
     return fb::launchWaitWord(dev_, localWord, value, s) == cudaSuccess
              ? FB_OK
              : FB_E_CUDA;
@@ -2176,7 +2321,9 @@ int Communicator::streamBarrier(int flags, cudaStream_t s)
     int ch = FB_FLAG_GET_CHANNEL(flags) % cfg_.channels;
     const uint32_t e = ++sbarEpoch_[ch];
     const uint32_t wordOff = FB_SIG_SBAR_OFF + (uint32_t)ch * FB_MAX_RANKS;
-    if (fb::launchSignalPeers(dev_, wordOff, e, s) != cudaSuccess) {
+    if (loop_) {
+        fb::host::signalPeers(dev_, wordOff, e);
+    } else if (fb::launchSignalPeers(dev_, wordOff, e, s) != cudaSuccess) {
         return FB_E_CUDA;
     }
     for (int p = 0; p < n; p++) {
@@ -2193,7 +2340,10 @@ int Communicator::streamBarrier(int flags, cudaStream_t s)
 
 bool Communicator::syncStreamBounded(cudaStream_t s, uint64_t timeoutMs)
 {
-    cudaSetDevice(device_);
+    if (loop_) {
+        return true; // every call already ran to completion
+    }
+    bindDevice();
     const auto t0 = std::chrono::steady_clock::now();
     uint32_t spins = 0;
     while (true) {
@@ -2221,7 +2371,10 @@ bool Communicator::syncStreamBounded(cudaStream_t s, uint64_t timeoutMs)
 
 bool Communicator::waitStreamFast(cudaStream_t s)
 {
-    cudaSetDevice(device_);
+    if (loop_) {
+        return true;
+    }
+    bindDevice();
     if (streamWriteOk_) {
         void* devPtr = nullptr;
         cudaHostGetDevicePointer(&devPtr, (void*)(dev_.err + 1), 0);
@@ -2250,6 +2403,9 @@ bool Communicator::waitStreamFast(cudaStream_t s)
 void Communicator::abortPendingWaits()
 {
     *reinterpret_cast<volatile uint32_t*>(dev_.err) = FB_ERR_HOST_ABORT;
+    if (loop_) {
+        return;
+    }
     cudaStream_t t = nullptr;
     if (cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
@@ -2321,6 +2477,9 @@ int Communicator::sendChunk(const uint8_t* buf, size_t len, int peer, cudaStream
     stats_.launches++;
     stats_.bytes += len;
     int w = alignWidth((uint64_t)(uintptr_t)buf);
+    if (loop_) {
+        return fb::host::p2pSend(a) == 0 ? FB_OK : FB_E_CUDA;
+    }
     return fb::launchP2PSend(a, w, p2pBlocks(len), s) == cudaSuccess ? FB_OK : FB_E_CUDA;
 }
 
@@ -2342,6 +2501,9 @@ int Communicator::recvChunk(uint8_t* buf, size_t len, int peer, cudaStream_t s)
     a.peer = peer;
     stats_.launches++;
     int w = alignWidth((uint64_t)(uintptr_t)buf);
+    if (loop_) {
+        return fb::host::p2pPull(a) == 0 ? FB_OK : FB_E_CUDA;
+    }
     return fb::launchP2PPull(a, w, p2pBlocks(len), s) == cudaSuccess ? FB_OK : FB_E_CUDA;
 }
 
@@ -2351,7 +2513,7 @@ int Communicator::send(const void* buf, size_t bytes, int peer, cudaStream_t s)
     if (peer < 0 || peer >= dev_.nranks) {
         return FB_E_INVALID;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     // zero-byte messages still synchronise (one empty chunk), like the
     // reference's empty MPI messages
     size_t off = 0;
@@ -2372,7 +2534,7 @@ int Communicator::recv(void* buf, size_t bytes, int peer, cudaStream_t s)
     if (peer < 0 || peer >= dev_.nranks) {
         return FB_E_INVALID;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     size_t off = 0;
     do {
         size_t len = std::min<size_t>(bounceSlotBytes_, bytes - off);
@@ -2397,7 +2559,7 @@ int Communicator::sendRecv(const void* sendBuf,
     if (dst < 0 || dst >= dev_.nranks || src < 0 || src >= dev_.nranks) {
         return FB_E_INVALID;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     size_t so = 0;
     size_t ro = 0;
     bool sendDone = false;
@@ -2437,7 +2599,7 @@ int Communicator::putSignal(const void* local,
         signalIdx >= FB_SIG_USER_WORDS || blocks < 1) {
         return FB_E_INVALID;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     fb::PutArgs a;
     memset(&a, 0, sizeof(a));
     a.comm = dev_;
@@ -2450,6 +2612,9 @@ int Communicator::putSignal(const void* local,
                      alignWidth(dstOffset));
     stats_.launches++;
     stats_.bytes += bytes;
+    if (loop_) {
+        return fb::host::putSignal(a, blocks) == 0 ? FB_OK : FB_E_CUDA;
+    }
     return fb::launchPutSignal(a, w, blocks, s) == cudaSuccess ? FB_OK
                                                                : FB_E_CUDA;
 }
@@ -2459,13 +2624,16 @@ int Communicator::waitSignal(int signalIdx, uint32_t count, cudaStream_t s)
     if (signalIdx < 0 || signalIdx >= FB_SIG_USER_WORDS) {
         return FB_E_INVALID;
     }
-    cudaSetDevice(device_);
+    bindDevice();
     if (streamSync_) {
         userSigConsumed_[signalIdx] += count;
         return streamWaitGe(
           s, dev_.sig[dev_.rank] + FB_SIG_USER_OFF + signalIdx, userSigConsumed_[signalIdx]);
     }
     stats_.launches++;
+    if (loop_) {
+        return fb::host::waitSignal(dev_, signalIdx, count) == 0 ? FB_OK : FB_E_CUDA;
+    }
     return fb::launchWaitSignal(dev_, signalIdx, count, s) == cudaSuccess
              ? FB_OK
              : FB_E_CUDA;

@@ -201,7 +201,13 @@ int fbOpFor(faabric_op_t* op)
 
 bool MpiWorld::isDevicePointer(const void* p)
 {
-    if (p == nullptr || !faabric::device::cudaAvailable()) {
+    if (p == nullptr) {
+        return false;
+    }
+    if (faabric::device::Communicator::isLoopbackHeapPointer(p)) {
+        return true; // loopback backend: heap memory plays the device's role
+    }
+    if (!faabric::device::cudaAvailable()) {
         return false;
     }
     cudaPointerAttributes attr;
@@ -957,6 +963,9 @@ void* MpiWorld::streamForRank(int rank, int channel)
         deviceStreams.resize((size_t)size * perRank, nullptr);
     }
     size_t idx = (size_t)rank * perRank + (size_t)(channel % perRank);
+    if (rank < (int)deviceComms.size() && deviceComms[rank] != nullptr && deviceComms[rank]->isLoopback()) {
+        return nullptr; // loopback: calls complete synchronously
+    }
     if (deviceStreams[idx] == nullptr) {
         // Same GPU as the rank's communicator when there is one
         int dev = (rank < (int)deviceComms.size() && deviceComms[rank] != nullptr) ? deviceComms[rank]->device()
@@ -981,7 +990,9 @@ void MpiWorld::ensureDeviceComms()
         return;
     }
     deviceTried = true;
-    if (!faabric::device::cudaAvailable() || faabric::util::getSystemConfig().deviceBackend != "cuda") {
+    const std::string& backend = faabric::util::getSystemConfig().deviceBackend;
+    const bool loopback = backend == "loopback";
+    if (!loopback && (!faabric::device::cudaAvailable() || backend != "cuda")) {
         return;
     }
     bool allLocal;
@@ -992,11 +1003,27 @@ void MpiWorld::ensureDeviceComms()
         allDistinctHosts = (int)ranksForHost.size() == size;
     }
     auto cfg = faabric::device::CommConfig::fromEnv();
+    cfg.loopback = loopback;
     cfg.heapBytes = (size_t)faabric::util::getSystemConfig().symmHeapBytes;
     if (const char* g = getenv("FAABRIC_MPI_GROUP_IALLREDUCE")) {
         groupIallreduce = g[0] != '0';
     }
-    if (getenv("FAABRIC_COMM_CHANNELS") == nullptr) {
+    // FAABRIC_ALLREDUCE_ALGO pins the algorithm of every MPI_Allreduce on
+    // device buffers (auto | ll | oneshot | twoshot | nvls); FAABRIC_COMM_STREAMS
+    // caps the number of channels (streams) a non-coalesced MPI_Iallreduce
+    // burst is spread over
+    {
+        const auto& sysConf = faabric::util::getSystemConfig();
+        int forced = faabric::device::CommTuning::algoFromName(sysConf.allreduceAlgo);
+        forcedAllReduceAlgo = forced > 0 ? forced : FB_ALGO_AUTO;
+        if (forced < 0) {
+            SPDLOG_WARN("Ignoring unknown FAABRIC_ALLREDUCE_ALGO={}", sysConf.allreduceAlgo);
+        }
+        if (getenv("FAABRIC_COMM_CHANNELS") == nullptr && getenv("FAABRIC_COMM_STREAMS") != nullptr) {
+            cfg.channels = std::clamp(sysConf.commStreams, 1, FB_MAX_CHANNELS);
+        }
+    }
+    if (getenv("FAABRIC_COMM_CHANNELS") == nullptr && getenv("FAABRIC_COMM_STREAMS") == nullptr) {
         // MPI_Iallreduce bursts pipeline over the channels: use them all
         cfg.channels = FB_MAX_CHANNELS;
     }
@@ -1155,7 +1182,7 @@ bool MpiWorld::tryDeviceAllReduce(int rank, uint8_t* send, uint8_t* recv, faabri
     }
     auto comm = getDeviceComm(rank);
     bool ran = runDevice(comm, streamForRank(rank), [&](faabric::device::Communicator& c, cudaStream_t s) {
-        return c.allReduce(send, recv, (size_t)count, fdt, fop, FB_ALGO_AUTO, symFlag(c, send, (size_t)count * dt->size), s);
+        return c.allReduce(send, recv, (size_t)count, fdt, fop, forcedAllReduceAlgo, symFlag(c, send, (size_t)count * dt->size), s);
     });
     if (ran) {
         deviceCollectives.fetch_add(1);
@@ -1205,7 +1232,7 @@ int MpiWorld::iAllReduce(int rank, uint8_t* send, uint8_t* recv, faabric_datatyp
         cudaStream_t s = (cudaStream_t)streamForRank(rank, channel);
         cudaSetDevice(comm->device());
         int flags = (symmetric ? FB_FLAG_SYMMETRIC : 0) | FB_FLAG_CHANNEL(channel);
-        int rc = comm->allReduce(send, recv, (size_t)count, fdt, fop, FB_ALGO_AUTO, flags, s);
+        int rc = comm->allReduce(send, recv, (size_t)count, fdt, fop, forcedAllReduceAlgo, flags, s);
         if (rc == FB_OK) {
             deviceCollectives.fetch_add(1);
             r.isDeviceCollective = true;

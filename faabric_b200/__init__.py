@@ -14,6 +14,16 @@ Layout:
 
 __version__ = "0.1.0"
 
+import os as _os
+
+# CUDA maps streams onto a limited number of hardware work queues (8 by
+# default).  Streams that share a queue serialise: a stream-level wait (or a
+# kernel polling a flag) of one rank can then sit in front of the very signal
+# kernel of another rank it is waiting for.  Several ranks per GPU times several
+# lanes per rank needs more queues than the default; the variable is only read
+# when the CUDA context is created, so it has to be in place at import time.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from . import _lib  # noqa: F401
 
 

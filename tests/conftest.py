@@ -4,6 +4,9 @@ from pathlib import Path
 
 import pytest
 
+# before anything creates a CUDA context (see faabric_b200/__init__.py)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
@@ -25,6 +28,11 @@ def _cuda_ok():
 
 def pytest_collection_modifyitems(config, items):
     if _cuda_ok():
+        # a wedged stream must cost minutes, not the whole session: the
+        # thread method ends the process even while it is blocked inside CUDA
+        for item in items:
+            if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(420, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
