@@ -313,6 +313,10 @@ class StateKeyValue
 
     void unmapSharedMemory(void* mappedAddr);
 
+    // Unmaps exactly the `nPages` that were mapped (the one-argument form
+    // keeps the reference's behaviour: it unmaps the size of the whole value)
+    void unmapSharedMemory(void* mappedAddr, long nPages);
+
     void flagDirty();
 
     void flagChunkDirty(long offset, long len);

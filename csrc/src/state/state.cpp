@@ -491,6 +491,17 @@ void StateKeyValue::unmapSharedMemory(void* mappedAddr)
     }
 }
 
+void StateKeyValue::unmapSharedMemory(void* mappedAddr, long nPages)
+{
+    std::unique_lock<std::shared_mutex> lock(valueMutex);
+    if (!faabric::util::isPageAligned(mappedAddr)) {
+        throw std::runtime_error("Attempting to unmap non-page-aligned memory");
+    }
+    if (nPages <= 0 || ::munmap(mappedAddr, (size_t)nPages * faabric::util::HOST_PAGE_SIZE) != 0) {
+        throw std::runtime_error("Failed unmapping shared memory");
+    }
+}
+
 void StateKeyValue::pushFull()
 {
     if (!isDirty) {
