@@ -448,16 +448,19 @@ __global__ void __launch_bounds__(512, 1) groupAllReduceKernel(
         }
     }
     BlockBarrier bar;
-    bar.load(c);
+    bar.epoch = 0;
     bool ok = true;
     if (!a.noSync) {
+        bar.load(c);
         ok = bar.sync(c); // (also publishes sSegs to the CTA)
     } else {
+        // no cross-rank synchronisation (single rank, or done at stream
+        // level): the grid is not tied to the barrier slots either
         __syncthreads();
     }
 
     if (ok && a.nSegs > 0) {
-        constexpr int UNROLL = (NR == 8) ? 2 : 4;
+        constexpr int UNROLL = (NR == 8) ? 2 : (NR == 1 ? 8 : 4);
         constexpr uint32_t CHUNK = 32u * UNROLL;
         const uint32_t lane = threadIdx.x & 31;
         const uint32_t warpsPerCta = blockDim.x >> 5;
@@ -566,8 +569,8 @@ __global__ void __launch_bounds__(512, 1) groupAllReduceKernel(
 
     if (!a.noSync) {
         bar.sync(c);
+        bar.store(c);
     }
-    bar.store(c);
 }
 
 template<typename VR>
@@ -578,7 +581,9 @@ cudaError_t launchGroup(const GroupArgs& a,
 {
     const size_t smem = (size_t)a.nSegs * sizeof(GroupSeg);
     const int nr = a.comm.nranks;
-    if (nr == 2) {
+    if (nr == 1) {
+        groupAllReduceKernel<VR, 1><<<blocks, threads, smem, stream>>>(a);
+    } else if (nr == 2) {
         groupAllReduceKernel<VR, 2><<<blocks, threads, smem, stream>>>(a);
     } else if (nr == 4) {
         groupAllReduceKernel<VR, 4><<<blocks, threads, smem, stream>>>(a);
@@ -608,6 +613,7 @@ cudaError_t preloadReduce()
     FB_PRELOAD((llAllReduceKernel<VR, 4>))
     FB_PRELOAD((llAllReduceKernel<VR, 8>))
     FB_PRELOAD((groupAllReduceKernel<VR, 0>))
+    FB_PRELOAD((groupAllReduceKernel<VR, 1>))
     FB_PRELOAD((groupAllReduceKernel<VR, 2>))
     FB_PRELOAD((groupAllReduceKernel<VR, 4>))
     FB_PRELOAD((groupAllReduceKernel<VR, 8>))

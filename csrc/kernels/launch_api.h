@@ -89,7 +89,8 @@ struct GroupArgs
 // vectors per warp-chunk for a world of n ranks (host and kernel must agree)
 static inline int fbGroupUnroll(int nranks)
 {
-    return (nranks == 8) ? 2 : 4;
+    // (one rank: a pure copy, as many loads in flight per thread as possible)
+    return (nranks == 8) ? 2 : (nranks == 1 ? 8 : 4);
 }
 static inline uint32_t fbGroupChunkVecs(int nranks)
 {

@@ -35,6 +35,22 @@ __global__ void __launch_bounds__(256) statePushDirtyKernel(uint8_t* mask,
             continue;
         }
         pushed += __popc(bal);
+        if (bal == 0xffffffffu && (g + 1) * 32 * FB_STATE_BLOCK_BYTES <= size) {
+            // a fully dirty group is one contiguous 4 KiB run: coalesced copy
+            // with eight vectors in flight per lane
+            const uint64_t base = g * 32 * FB_STATE_BLOCK_BYTES;
+            Vec16 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                v[k] = ldVecStream(src + base + (uint64_t)(k * 32 + lane) * 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                stVec(dst + base + (uint64_t)(k * 32 + lane) * 16, v[k]);
+            }
+            mask[myBlock] = 0;
+            continue;
+        }
         const uint32_t sub = lane >> 3; // which of the 4 blocks in flight
         const uint32_t part = lane & 7; // 16-byte piece of the 128-byte block
         uint32_t rest = bal;

@@ -1796,8 +1796,10 @@ static int groupGrid(const CommConfig& cfg, int nranks, uint64_t vecsPerRank)
 {
     // Derived ONLY from quantities that are identical on every rank: CTA b of
     // one rank meets CTA b of every peer at the barriers
-    const int slots = FB_MAX_BLOCKS / cfg.channels;
-    const int cap = std::min(slots, cfg.groupBlocks > 0 ? cfg.groupBlocks : 128);
+    // a lone rank does not synchronise with anybody: two CTAs per SM for an
+    // HBM-bound copy; otherwise the grid is bounded by the barrier slots
+    const int slots = nranks == 1 ? 2 * 148 : FB_MAX_BLOCKS / cfg.channels;
+    const int cap = std::min(slots, cfg.groupBlocks > 0 ? cfg.groupBlocks : (nranks == 1 ? 2 * 148 : 128));
     const uint64_t warps = (uint64_t)cfg.threads / 32;
     const uint64_t chunks = (vecsPerRank + fb::fbGroupChunkVecs(nranks) - 1) / fb::fbGroupChunkVecs(nranks);
     const uint64_t want = (chunks + warps * 2 - 1) / (warps * 2); // >= 2 chunks per warp
@@ -1821,7 +1823,7 @@ int Communicator::allReduceGroup(const GroupPlan& plan, int op, int flags, cudaS
         a.segs = l.dSegs;
         a.nSegs = l.nSegs;
         a.totalChunks = l.totalChunks;
-        a.noSync = ((flags & FB_FLAG_NOSYNC) || ss) ? 1 : 0;
+        a.noSync = ((flags & FB_FLAG_NOSYNC) || ss || n == 1) ? 1 : 0;
         if (ss && streamBarrier(flags, s) != FB_OK) {
             return FB_E_CUDA;
         }
@@ -1929,7 +1931,7 @@ int Communicator::allReduceMany(const GroupItem* items,
         a.segs = slot.dSegs;
         a.nSegs = (uint32_t)sb.segs.size();
         a.totalChunks = sb.totalChunks;
-        a.noSync = ((flags & FB_FLAG_NOSYNC) || ss) ? 1 : 0;
+        a.noSync = ((flags & FB_FLAG_NOSYNC) || ss || n == 1) ? 1 : 0;
         if (ss && streamBarrier(flags, s) != FB_OK) {
             return FB_E_CUDA;
         }

@@ -10,6 +10,7 @@ run() { # n port args...
 echo "== bench n8 (grouped)"; nvidia-smi nvlink -gt d -i 0 > gpurun_out/e_nvlink_before.txt 2>&1
 run 8 29601 --steps 50 --warmup 10 > gpurun_out/e_bench8.json 2> gpurun_out/e_bench8.err; echo "rc=$?"; cat gpurun_out/e_bench8.json | cut -c1-900; tail -2 gpurun_out/e_bench8.err
 nvidia-smi nvlink -gt d -i 0 > gpurun_out/e_nvlink_after.txt 2>&1
+for gb in 148 64; do echo "== bench n8 groupBlocks=$gb"; FAABRIC_GROUP_BLOCKS=$gb run 8 2961$((gb % 10)) --steps 50 --warmup 10 --no-nccl > gpurun_out/e_bench8_gb$gb.json 2> gpurun_out/e_bench8_gb$gb.err; echo "rc=$?"; cut -c1-260 gpurun_out/e_bench8_gb$gb.json; done
 echo "== bench n4"; run 4 29602 --steps 50 --warmup 10 > gpurun_out/e_bench4.json 2> gpurun_out/e_bench4.err; echo "rc=$?"; cut -c1-420 gpurun_out/e_bench4.json
 echo "== bench n2"; run 2 29603 --steps 50 --warmup 10 > gpurun_out/e_bench2.json 2> gpurun_out/e_bench2.err; echo "rc=$?"; cut -c1-420 gpurun_out/e_bench2.json
 echo "== multi-gpu tests (8 GPUs, one process)"; timeout 600 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/e_multi.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/e_multi.log

@@ -17,7 +17,13 @@ pytestmark = pytest.mark.gpu
 
 def test_cpp_gpu_suite():
     fb_build.build(verbose=False)
-    r = subprocess.run([str(BIN / "faabric_tests"), "--tag", "gpu"], capture_output=True, text=True, timeout=900)
+    try:
+        # (shorter than the per-test limit of the session, so that a wedged run
+        # is killed here - with its output - and does not outlive pytest)
+        r = subprocess.run([str(BIN / "faabric_tests"), "--tag", "gpu"], capture_output=True, text=True, timeout=300)
+    except subprocess.TimeoutExpired as e:
+        out = (e.stdout or b"").decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
+        raise AssertionError("C++ GPU suite timed out; last output:\n" + "\n".join(out.splitlines()[-40:]))
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-60:])
     assert r.returncode == 0, tail
     last = [l for l in r.stdout.splitlines() if l.startswith("====")][-1]
