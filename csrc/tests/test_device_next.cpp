@@ -17,6 +17,7 @@
 
 #include <cuda_runtime.h>
 
+#include <barrier>
 #include <filesystem>
 #include <unistd.h>
 
@@ -322,6 +323,7 @@ TEST_CASE("ptp on device buffers: many in-order messages between group members",
     const int nMsgs = 60;
     std::vector<std::thread> members;
     std::atomic<int> failures{ 0 };
+    std::barrier allDrained(n);
     for (int idx = 0; idx < n; idx++) {
         members.emplace_back([&, idx] {
             auto comm = broker.getDeviceCommunicator(groupId, idx);
@@ -339,6 +341,8 @@ TEST_CASE("ptp on device buffers: many in-order messages between group members",
                 cudaMemcpy(outs[k], h.data(), count * 4, cudaMemcpyHostToDevice);
                 cudaMemset(ins[k], 0, count * 4);
             }
+            // (allocation may synchronise with the device too: see below)
+            allDrained.arrive_and_wait();
             // all sends first (eager), then all receives: order must hold
             for (int k = 0; k < nMsgs; k++) {
                 broker.sendDeviceMessage(groupId, idx, next, outs[k], (1 + (size_t)k * 37) * 4, s);
@@ -349,6 +353,11 @@ TEST_CASE("ptp on device buffers: many in-order messages between group members",
             if (!comm->syncStreamBounded(s, 20000) || comm->peekError() != 0) {
                 failures++;
             }
+            // cudaFree (below) waits for the WHOLE device to go idle while it
+            // holds the context: a member that frees early would stall the
+            // members that have not issued their sends yet, whose messages the
+            // device is waiting for.  Free only once every stream has drained.
+            allDrained.arrive_and_wait();
             for (int k = 0; k < nMsgs; k++) {
                 size_t count = 1 + (size_t)k * 37;
                 std::vector<int> h(count);
