@@ -14,6 +14,7 @@ Other modes (each prints one JSON line and appends to --out):
   alltoall  all-to-all bus GB/s 1 KB..64 MB per rank, ours vs NCCL
   snapshot  1 GB region diff+push at 1..50 % dirty (MB/s), vs CPU oracle rate
   planner   1024-function fan-out / fan-in through the native planner (us)
+  threads   THREADS fork-join of a 1 GiB device function memory through the runtime (ms)
   pingpong  MPI ping-pong RTT, 2 ranks in one worker and in two (CPU)
   hostcoll  host-buffer MPI collectives: reference algorithms vs shared memory (CPU)
 
@@ -42,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-host", "mpi-device", "mpi-symmetric", "mpi-symmetric-nb"])
     ap.add_argument("--mode", default="allreduce",
-                    choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "pingpong", "hostcoll"])
+                    choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "threads", "pingpong", "hostcoll"])
     ap.add_argument("--algo", default="tuned",
                     help="tuned = measure the algorithm policies in place and keep the fastest (allreduce mode)")
     ap.add_argument("--no-graph", action="store_true")
@@ -669,6 +670,30 @@ def mode_planner(args, dist: Dist):
     return out, {}
 
 
+def mode_threads(args, dist: Dist):
+    """THREADS fork-join through the whole runtime on device memory, against the
+    reference's host-memory design (mprotect tracking + byte diffs) on the same box."""
+    from faabric_b200.runtime import threads_forkjoin_bench
+
+    hosts = args.gpus if args.gpus > 1 else 2
+    dev = threads_forkjoin_bench("device", hosts=hosts, iters=max(args.steps, 5), warmup=max(args.warmup, 2))
+    ref = threads_forkjoin_bench("host", hosts=hosts, iters=5, warmup=1)
+    out = {
+        "metric": "threads_forkjoin_1GiB_ms",
+        "value": dev.get("ms_median"),
+        "unit": "ms",
+        "higher_is_better": False,
+        "n_gpus": dev.get("gpus"),
+        "refcpu_ms": ref.get("ms_median"),
+        "vs_refcpu": round(ref["ms_median"] / dev["ms_median"], 2) if dev.get("ms_median") else None,
+        "details": dev,
+        "refcpu_details": ref,
+        "note": "executeThreads() wall time, one thread per virtual GPU host, 1% of a 1 GiB function memory dirtied per join; "
+                "refcpu = host memory, mprotect dirty tracking, byte diffs through the snapshot server",
+    }
+    return out, {}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -679,10 +704,10 @@ def main():
         return mode_pingpong(args)
     if args.mode == "hostcoll":
         return mode_hostcoll(args)
-    if args.mode == "planner":
-        # CPU only: no process group / GPU needed
+    if args.mode in ("planner", "threads"):
+        # one process drives everything: no process group needed
         if int(os.environ.get("RANK", "0")) == 0:
-            out, _ = mode_planner(args, None)
+            out, _ = (mode_planner if args.mode == "planner" else mode_threads)(args, None)
             print(json.dumps(out), flush=True)
         return 0
     dist = Dist(args.gpus)

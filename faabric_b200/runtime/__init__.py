@@ -11,6 +11,7 @@ from .client import PlannerHttpClient, HttpMessageType, PlannerError
 from .cluster import LocalCluster
 from .benchmarks import (
     planner_fanout_bench,
+    threads_forkjoin_bench,
     cpu_pingpong_bench,
     cpu_allreduce_bench,
     mpi_allreduce_bench,
@@ -23,6 +24,7 @@ __all__ = [
     "PlannerError",
     "LocalCluster",
     "planner_fanout_bench",
+    "threads_forkjoin_bench",
     "cpu_pingpong_bench",
     "host_collectives_bench",
     "cpu_allreduce_bench",

@@ -32,6 +32,30 @@ def planner_fanout_bench(n_functions: int = 1024, n_hosts: int = 8, iters: int =
     return res
 
 
+def threads_forkjoin_bench(memory: str = "device", hosts: int = 0, mem_mb: int = 1024, dirty_pct: float = 1.0,
+                           iters: int = 10, warmup: int = 2) -> dict:
+    """THREADS fork-join through planner, scheduler, executors and the snapshot
+    registry: one thread per (virtual GPU) host, each dirtying its share of a
+    `mem_mb` function memory, merged back at the join.  memory="device": HBM
+    images, peer-copy restore, one fused diff+push kernel per host;
+    memory="host": the reference's mprotect + byte-diff design on this box."""
+    exe = BINDIR / "threads_bench"
+    if not exe.exists():
+        from .. import build as _build
+
+        _build.build(verbose=False)
+    r = subprocess.run(
+        [str(exe), "--memory", memory, "--hosts", str(hosts), "--mem-mb", str(mem_mb), "--dirty-pct", str(dirty_pct),
+         "--iters", str(iters), "--warmup", str(warmup)],
+        capture_output=True,
+        text=True,
+        timeout=900,
+    )
+    if r.returncode != 0:
+        raise RuntimeError(f"threads_bench failed: {r.stdout[-500:]} {r.stderr[-800:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def _first_output(status: dict) -> dict:
     for m in sorted(status["messageResults"], key=lambda m: m.get("mpiRank", 0)):
         if m.get("output_data"):

@@ -19,3 +19,6 @@ cp gpurun_out/tuning_N8.json gpurun_out/e_tuning_N8.json 2>/dev/null; cp gpurun_
 echo "== sweep n4"; run 4 29605 --mode sweep --max-bytes 268435456 --out gpurun_out/e_sweep4.json > /dev/null 2> gpurun_out/e_sweep4.err; echo "rc=$?"; grep "\[sweep\]" gpurun_out/e_sweep4.err | cut -c1-330 | tail -12
 cp gpurun_out/tuning_N4.json gpurun_out/e_tuning_N4.json 2>/dev/null; cp gpurun_out/tuning_N4.txt gpurun_out/e_tuning_N4.txt 2>/dev/null
 echo "== bench n8 lanes (round-1 path, for comparison)"; run 8 29606 --sync-mode lanes --no-nccl --steps 20 > gpurun_out/e_bench8_lanes.json 2> gpurun_out/e_bench8_lanes.err; echo "rc=$?"; cut -c1-330 gpurun_out/e_bench8_lanes.json
+echo "== threads fork-join through the runtime (8 virtual GPU hosts, 1 GiB)"; timeout 300 build/bin/threads_bench --memory device --hosts 8 --iters 10 --warmup 2 2> gpurun_out/e_threads.err | tee gpurun_out/e_threads.json | cut -c1-420; tail -3 gpurun_out/e_threads.err
+timeout 300 build/bin/threads_bench --memory device --hosts 8 --dirty-pct 10 --iters 10 --warmup 2 2>/dev/null | tee -a gpurun_out/e_threads.json | cut -c1-420
+timeout 300 build/bin/threads_bench --memory host --hosts 8 --iters 5 --warmup 1 2>/dev/null | tee -a gpurun_out/e_threads.json | cut -c1-420
