@@ -48,6 +48,7 @@ def parse():
                     help="tuned = measure the algorithm policies in place and keep the fastest (allreduce mode)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--channels", type=int, default=8, help="lanes of --sync-mode lanes")
+    ap.add_argument("--no-mpi-api", action="store_true", help="skip the MPI C-API arm reported under 'mpi_api'")
     ap.add_argument("--sync-mode", default="grouped", choices=["grouped", "lanes"],
                     help="grouped = ONE fused kernel per step over all 214 tensors; lanes = one kernel per tensor")
     ap.add_argument("--no-nccl", action="store_true", help="skip the in-process graph-captured NCCL comparison")
@@ -694,6 +695,23 @@ def mode_threads(args, dist: Dist):
     return out, {}
 
 
+def mpi_api_arm(n: int) -> dict:
+    """Runs `bench.py --impl mpi-symmetric-nb` in a child (its own worker process with n rank threads)."""
+    import subprocess
+
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "MASTER_ADDR",
+                        "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "mpi-symmetric-nb", "--gpus", str(n),
+                            "--steps", "10", "--warmup", "3"], capture_output=True, text=True, timeout=300, env=env)
+        res = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"impl": "MPI_Iallreduce x214 + MPI_Waitall (C API, symmetric device memory)", "world_size": res["world_size"],
+                "ms_per_step": res["ms_per_step"], "us_per_allreduce": round(res["ms_per_step"] * 1000 / res["config"]["tensors"], 3)}
+    except Exception as e:  # the headline never depends on this arm
+        return {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -719,6 +737,13 @@ def main():
         "planner": mode_planner,
     }[args.mode]
     out, keep = fn(args, dist)
+    if args.mode == "allreduce" and args.impl == "ours" and not args.no_mpi_api:
+        # the same 214 reductions through the product's MPI C API (MPI_Iallreduce x214 + MPI_Waitall on
+        # symmetric device memory, ranks = executor threads of one worker process), reported next to the headline
+        keep = None
+        dist.torch.cuda.synchronize()
+        if dist.rank == 0:
+            out["mpi_api"] = mpi_api_arm(max(dist.world, 2))
     if dist.rank == 0:
         line = json.dumps(out)
         print(line, flush=True)

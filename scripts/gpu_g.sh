@@ -9,3 +9,4 @@ echo "== bench n1"; timeout 200 python bench.py --gpus 1 > gpurun_out/g_bench1.j
 echo "== planner fan-out variants ($(nproc) cores)"
 for v in workers direct; do FAABRIC_PLANNER_RESULTS=$v timeout 200 build/bin/planner_bench --mode native --iters 30 2>/dev/null | tail -1 | sed "s/^/$v: /" | tee -a gpurun_out/g_planner.jsonl | cut -c1-250; done
 timeout 200 build/bin/planner_bench --mode refcpu --iters 30 2>/dev/null | tail -1 | tee -a gpurun_out/g_planner.jsonl | cut -c1-250
+echo "== threads fork-join (2 virtual hosts on one GPU, 1 GiB)"; timeout 200 build/bin/threads_bench --memory device --hosts 2 --iters 10 --warmup 2 2> gpurun_out/g_threads.err | tee gpurun_out/g_threads.json | cut -c1-420; tail -3 gpurun_out/g_threads.err
