@@ -267,6 +267,9 @@ class RecvSocket
 
     int getPort() const { return port; }
 
+    // the listening socket, for callers that poll it next to other fds
+    int getFd() const { return sock.get(); }
+
   private:
     std::string host;
     int port;
@@ -428,6 +431,126 @@ class AsyncInternalRecvMessageEndpoint final
 // Direct pair: same thing under the names the reference uses
 using AsyncDirectSendEndpoint = AsyncInternalSendMessageEndpoint;
 using AsyncDirectRecvEndpoint = AsyncInternalRecvMessageEndpoint;
+
+// ---- stand-alone receiving endpoints (reference: MessageEndpoint.h:158-253).
+// The servers of this runtime are MessageEndpointServer instances; these are
+// the building blocks under their reference names for code that wants a bare
+// socket to pull from: a bound port (or an in-process label) whose messages
+// are read by one listener thread and handed out by recv().
+class PortListener;
+
+// Identifies one attached worker of a fan endpoint and the connection of the
+// message it is working on (where sendResponse() replies)
+class MessageContext final
+{
+  public:
+    MessageContext() = default;
+
+    int getWorkerId() const { return workerId; }
+
+    bool isValid() const { return workerId >= 0; }
+
+  private:
+    friend class FanMessageEndpoint;
+    friend class RecvMessageEndpoint;
+    int workerId = -1;
+    mutable int replyFd = -1;
+    mutable int replySeq = NO_SEQUENCE_NUM;
+};
+
+class RecvMessageEndpoint
+{
+  public:
+    // bound TCP port
+    RecvMessageEndpoint(int portIn, int timeoutMsIn);
+
+    // in-process label
+    RecvMessageEndpoint(const std::string& inprocLabel, int timeoutMsIn);
+
+    virtual ~RecvMessageEndpoint();
+
+    // The next message; a Message with response code TIMEOUT when none arrived
+    // in time, TERM once the endpoint was stopped
+    virtual Message recv();
+
+    int getPort() const { return port; }
+
+    void stop();
+
+  protected:
+    int port = 0;
+    int timeoutMs;
+    std::shared_ptr<PortListener> listener;
+    std::shared_ptr<InprocMailbox> mailbox;
+    MessageContext last;
+
+    Message doRecv(MessageContext& ctx);
+
+    void reply(const MessageContext& ctx, uint8_t header, const uint8_t* data, size_t dataSize);
+};
+
+// PULL-like: messages only
+class AsyncRecvMessageEndpoint final : public RecvMessageEndpoint
+{
+  public:
+    explicit AsyncRecvMessageEndpoint(int portIn, int timeoutMs = DEFAULT_SOCKET_TIMEOUT_MS);
+
+    explicit AsyncRecvMessageEndpoint(const std::string& inprocLabel, int timeoutMs = DEFAULT_SOCKET_TIMEOUT_MS);
+};
+
+// REP-like: every received message is answered on its connection
+class SyncRecvMessageEndpoint final : public RecvMessageEndpoint
+{
+  public:
+    explicit SyncRecvMessageEndpoint(int portIn, int timeoutMs = DEFAULT_SOCKET_TIMEOUT_MS);
+
+    void sendResponse(uint8_t header, const uint8_t* data, size_t dataSize);
+};
+
+// One bound port whose messages are shared out between attached workers
+// (reference: the fan-in / fan-out pair in front of a server's worker threads)
+class FanMessageEndpoint
+{
+  public:
+    FanMessageEndpoint(int portIn, int timeoutMsIn, bool isAsyncIn);
+
+    virtual ~FanMessageEndpoint();
+
+    MessageContext attachFanOut();
+
+    // Blocks for this worker's next message (TIMEOUT / TERM codes as above)
+    Message recv(const MessageContext& ctx);
+
+    void sendResponse(const MessageContext& ctx, uint8_t header, const uint8_t* data, size_t dataSize);
+
+    // Every blocked and future recv() returns TERM
+    void stop();
+
+    int getPort() const { return port; }
+
+  private:
+    int port;
+    int timeoutMs;
+    bool isAsync;
+    std::shared_ptr<PortListener> listener;
+    std::atomic<int> nWorkers{ 0 };
+};
+
+class AsyncFanMessageEndpoint final : public FanMessageEndpoint
+{
+  public:
+    explicit AsyncFanMessageEndpoint(int portIn, int timeoutMs = DEFAULT_SOCKET_TIMEOUT_MS)
+      : FanMessageEndpoint(portIn, timeoutMs, true)
+    {}
+};
+
+class SyncFanMessageEndpoint final : public FanMessageEndpoint
+{
+  public:
+    explicit SyncFanMessageEndpoint(int portIn, int timeoutMs = DEFAULT_SOCKET_TIMEOUT_MS)
+      : FanMessageEndpoint(portIn, timeoutMs, false)
+    {}
+};
 
 }
 
