@@ -43,6 +43,8 @@ struct AsyncRequest
     bool isDeviceCollective = false;
     // part of a burst that has not been issued yet (grouped at the next wait)
     bool deferred = false;
+    // which grouped launch of this rank thread it went out with (0 = none)
+    uint64_t groupSeq = 0;
     void* stream = nullptr;
     std::shared_ptr<faabric::device::Communicator> comm;
 };
@@ -77,6 +79,11 @@ struct RankState
     void* groupStream = nullptr;
     std::vector<faabric::device::Communicator::GroupItem> groupItems;
     std::vector<int> groupRequests;
+    // grouped launches go out on one stream, in order: once a request of
+    // launch k was waited for, every request of launches <= k is complete
+    uint64_t groupLaunchSeq = 0;
+    uint64_t groupCompletedSeq = 0;
+    void* groupCompletedStream = nullptr;
 
     void reset()
     {
@@ -867,11 +874,13 @@ static void flushPendingGroup()
         throw std::runtime_error(std::string("Grouped device all-reduce failed: ") +
                                  faabric::device::Communicator::errorString(rc));
     }
+    const uint64_t seq = ++tls.groupLaunchSeq;
     for (int id : reqs) {
         auto it = tls.requests.find(id);
         if (it != tls.requests.end()) {
             it->second.stream = tls.groupStream;
             it->second.deferred = false;
+            it->second.groupSeq = seq;
         }
     }
 }
@@ -890,9 +899,17 @@ void MpiWorld::awaitAsyncRequest(int requestId)
         }
         AsyncRequest req = it->second;
         tls.requests.erase(it);
+        if (req.groupSeq != 0 && req.groupSeq <= tls.groupCompletedSeq && req.stream == tls.groupCompletedStream) {
+            // an earlier wait already saw this launch complete
+            return;
+        }
         cudaSetDevice(req.comm->device());
         if (!req.comm->waitStreamFast((cudaStream_t)req.stream)) {
             throw std::runtime_error("Device collective failed at synchronisation");
+        }
+        if (req.groupSeq != 0) {
+            tls.groupCompletedSeq = req.groupSeq;
+            tls.groupCompletedStream = req.stream;
         }
         if (req.comm->peekError() != 0) {
             throw std::runtime_error("Device collective watchdog fired (peer missing?)");
