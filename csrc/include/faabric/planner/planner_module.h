@@ -215,6 +215,14 @@ class Planner
     // ----------
     void setMessageResult(std::shared_ptr<faabric::Message> msg);
 
+    // Many results under one acquisition of the planner's lock
+    void setMessageResults(const std::vector<std::shared_ptr<faabric::Message>>& msgs);
+
+    // Combining entry point for result producers in the planner's process:
+    // the result is recorded by this call or by a concurrent caller that is
+    // already draining (returns at once in that case)
+    void submitMessageResult(std::shared_ptr<faabric::Message> msg);
+
     // Non-blocking: nullptr if not ready (and the caller is registered as a
     // waiter when it named its main host)
     std::shared_ptr<faabric::Message> getMessageResult(
@@ -255,6 +263,13 @@ class Planner
 
   private:
     std::shared_mutex plannerMx;
+
+    std::mutex pendingResultsMx;
+    std::vector<std::shared_ptr<faabric::Message>> pendingResults;
+    bool drainingResults = false;
+
+    // Caller holds plannerMx exclusively
+    void recordResultLocked(const std::shared_ptr<faabric::Message>& msg, std::vector<std::string>& toNotify);
     std::condition_variable_any appFinishedCv;
 
     void compactInFlightLocked();

@@ -338,8 +338,6 @@ void Planner::removeHost(const Host& hostIn)
 // ---------------------------------------------------------------------------
 void Planner::setMessageResult(std::shared_ptr<faabric::Message> msg)
 {
-    int appId = msg->appid();
-    int msgId = msg->id();
     // A migrated message carries on elsewhere: its result comes later
     if (msg->returnvalue() == MIGRATED_FUNCTION_RETURN_VALUE) {
         return;
@@ -347,85 +345,147 @@ void Planner::setMessageResult(std::shared_ptr<faabric::Message> msg)
     std::vector<std::string> toNotify;
     {
         std::unique_lock<std::shared_mutex> lock(plannerMx);
-        bool isFrozen = msg->returnvalue() == FROZEN_FUNCTION_RETURN_VALUE;
-        if (isFrozen) {
-            auto ev = state.evictedRequests.find(appId);
-            if (ev == state.evictedRequests.end()) {
-                SPDLOG_ERROR("Message {} is frozen but app {} not in map!", msgId, appId);
-                throw std::runtime_error("Orphaned frozen message!");
-            }
-            // Remember where to resume from
-            for (int i = 0; i < ev->second->messages_size(); i++) {
-                auto* m = ev->second->mutable_messages(i);
-                if (m->id() == msgId) {
-                    m->set_funcptr(msg->funcptr());
-                    m->set_inputdata(msg->inputdata());
-                    m->set_snapshotkey(msg->snapshotkey());
-                    m->set_returnvalue(msg->returnvalue());
-                    break;
-                }
-            }
-        }
-        auto hostIt = state.hostMap.find(msg->executedhost());
-        bool firstResult = state.appResults[appId].count(msgId) == 0;
-        if (hostIt != state.hostMap.end() && (firstResult || isFrozen)) {
-            releaseHostSlots(hostIt->second);
-        }
-        if (!isFrozen) {
-            state.appResults[appId][msgId] = msg;
-        }
-        auto inFlight = state.inFlightReqs.find(appId);
-        if (inFlight != state.inFlightReqs.end()) {
-            auto& req = inFlight->second.first;
-            auto& decision = inFlight->second.second;
-            auto& done = state.finishedInFlight[appId];
-            // Ids are plain ints: a linear look-up is cheap, moving Message
-            // objects around for every result is not
-            // position of the message in the decision: hashed once per app (a
-            // linear look-up per result is quadratic for a 1024-way fan-out)
-            const auto& ids = decision->messageIds;
-            auto& posOf = state.inFlightIdPos[appId];
-            if (posOf.size() != ids.size()) {
-                posOf.clear();
-                posOf.reserve(ids.size());
-                for (size_t k = 0; k < ids.size(); k++) {
-                    posOf.emplace(ids[k], (int)k);
-                }
-            }
-            auto posIt = posOf.find(msgId);
-            auto pos = posIt == posOf.end() ? ids.end() : ids.begin() + posIt->second;
-            if (pos != ids.end() && *pos != msgId) {
-                // the decision was edited (message removed / reordered): rebuild
-                posOf.clear();
-                pos = std::find(ids.begin(), ids.end(), msgId);
-            }
-            if (pos != ids.end() && done.insert(msgId).second) {
-                int port = decision->mpiPorts.at((size_t)(pos - ids.begin()));
-                if (hostIt != state.hostMap.end()) {
-                    releaseHostMpiPort(hostIt->second, port);
-                }
-                if ((int)done.size() == req->messages_size()) {
-                    SPDLOG_DEBUG("Planner removing app {} from in-flight", appId);
-                    state.inFlightReqs.erase(inFlight);
-                    state.finishedInFlight.erase(appId);
-                    state.inFlightIdPos.erase(appId);
-                    state.preloadedSchedulingDecisions.erase(appId);
-                    appFinishedCv.notify_all();
-                }
-            }
-        }
-        if (isFrozen) {
-            return;
-        }
-        auto w = state.appResultWaiters.find(msgId);
-        if (w != state.appResultWaiters.end()) {
-            toNotify = std::move(w->second);
-            state.appResultWaiters.erase(w);
-        }
+        recordResultLocked(msg, toNotify);
     }
     // Notify outside the lock
     for (const auto& host : toNotify) {
         faabric::scheduler::getFunctionCallClient(host)->setMessageResult(msg);
+    }
+}
+
+// A fan-in of N results costs ONE exclusive acquisition of the planner's lock
+void Planner::setMessageResults(const std::vector<std::shared_ptr<faabric::Message>>& msgs)
+{
+    std::vector<std::pair<std::shared_ptr<faabric::Message>, std::vector<std::string>>> notify;
+    {
+        std::unique_lock<std::shared_mutex> lock(plannerMx);
+        for (const auto& msg : msgs) {
+            if (msg->returnvalue() == MIGRATED_FUNCTION_RETURN_VALUE) {
+                continue;
+            }
+            std::vector<std::string> toNotify;
+            try {
+                recordResultLocked(msg, toNotify);
+            } catch (const std::exception& e) {
+                SPDLOG_ERROR("Planner could not record the result of message {}: {}", msg->id(), e.what());
+            }
+            if (!toNotify.empty()) {
+                notify.emplace_back(msg, std::move(toNotify));
+            }
+        }
+    }
+    for (const auto& [msg, hosts] : notify) {
+        for (const auto& host : hosts) {
+            faabric::scheduler::getFunctionCallClient(host)->setMessageResult(msg);
+        }
+    }
+}
+
+// Flat combining: whoever finds nobody draining takes the whole pending list
+// through the planner in one go; everybody else just leaves their result
+void Planner::submitMessageResult(std::shared_ptr<faabric::Message> msg)
+{
+    {
+        std::lock_guard<std::mutex> lk(pendingResultsMx);
+        pendingResults.push_back(std::move(msg));
+        if (drainingResults) {
+            return;
+        }
+        drainingResults = true;
+    }
+    std::vector<std::shared_ptr<faabric::Message>> batch;
+    while (true) {
+        batch.clear();
+        {
+            std::lock_guard<std::mutex> lk(pendingResultsMx);
+            if (pendingResults.empty()) {
+                drainingResults = false;
+                return;
+            }
+            batch.swap(pendingResults);
+        }
+        setMessageResults(batch);
+    }
+}
+
+void Planner::recordResultLocked(const std::shared_ptr<faabric::Message>& msg, std::vector<std::string>& toNotify)
+{
+    int appId = msg->appid();
+    int msgId = msg->id();
+    bool isFrozen = msg->returnvalue() == FROZEN_FUNCTION_RETURN_VALUE;
+    if (isFrozen) {
+        auto ev = state.evictedRequests.find(appId);
+        if (ev == state.evictedRequests.end()) {
+            SPDLOG_ERROR("Message {} is frozen but app {} not in map!", msgId, appId);
+            throw std::runtime_error("Orphaned frozen message!");
+        }
+        // Remember where to resume from
+        for (int i = 0; i < ev->second->messages_size(); i++) {
+            auto* m = ev->second->mutable_messages(i);
+            if (m->id() == msgId) {
+                m->set_funcptr(msg->funcptr());
+                m->set_inputdata(msg->inputdata());
+                m->set_snapshotkey(msg->snapshotkey());
+                m->set_returnvalue(msg->returnvalue());
+                break;
+            }
+        }
+    }
+    auto hostIt = state.hostMap.find(msg->executedhost());
+    bool firstResult = state.appResults[appId].count(msgId) == 0;
+    if (hostIt != state.hostMap.end() && (firstResult || isFrozen)) {
+        releaseHostSlots(hostIt->second);
+    }
+    if (!isFrozen) {
+        state.appResults[appId][msgId] = msg;
+    }
+    auto inFlight = state.inFlightReqs.find(appId);
+    if (inFlight != state.inFlightReqs.end()) {
+        auto& req = inFlight->second.first;
+        auto& decision = inFlight->second.second;
+        auto& done = state.finishedInFlight[appId];
+        // Ids are plain ints: a linear look-up is cheap, moving Message
+        // objects around for every result is not
+        // position of the message in the decision: hashed once per app (a
+        // linear look-up per result is quadratic for a 1024-way fan-out)
+        const auto& ids = decision->messageIds;
+        auto& posOf = state.inFlightIdPos[appId];
+        if (posOf.size() != ids.size()) {
+            posOf.clear();
+            posOf.reserve(ids.size());
+            for (size_t k = 0; k < ids.size(); k++) {
+                posOf.emplace(ids[k], (int)k);
+            }
+        }
+        auto posIt = posOf.find(msgId);
+        auto pos = posIt == posOf.end() ? ids.end() : ids.begin() + posIt->second;
+        if (pos != ids.end() && *pos != msgId) {
+            // the decision was edited (message removed / reordered): rebuild
+            posOf.clear();
+            pos = std::find(ids.begin(), ids.end(), msgId);
+        }
+        if (pos != ids.end() && done.insert(msgId).second) {
+            int port = decision->mpiPorts.at((size_t)(pos - ids.begin()));
+            if (hostIt != state.hostMap.end()) {
+                releaseHostMpiPort(hostIt->second, port);
+            }
+            if ((int)done.size() == req->messages_size()) {
+                SPDLOG_DEBUG("Planner removing app {} from in-flight", appId);
+                state.inFlightReqs.erase(inFlight);
+                state.finishedInFlight.erase(appId);
+                state.inFlightIdPos.erase(appId);
+                state.preloadedSchedulingDecisions.erase(appId);
+                appFinishedCv.notify_all();
+            }
+        }
+    }
+    if (isFrozen) {
+        return;
+    }
+    auto w = state.appResultWaiters.find(msgId);
+    if (w != state.appResultWaiters.end()) {
+        toNotify = std::move(w->second);
+        state.appResultWaiters.erase(w);
     }
 }
 
