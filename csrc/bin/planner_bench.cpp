@@ -106,8 +106,25 @@ class NoopExecutor : public Executor
       : Executor(msg)
     {}
 
-    int32_t executeTask(int, int, std::shared_ptr<faabric::BatchExecuteRequest>) override { return 0; }
+    int32_t executeTask(int, int, std::shared_ptr<faabric::BatchExecuteRequest>) override
+    {
+        // when did the first / last function of the batch actually run
+        int64_t now = std::chrono::steady_clock::now().time_since_epoch().count();
+        int64_t seen = firstExec.load(std::memory_order_relaxed);
+        while (now < seen && !firstExec.compare_exchange_weak(seen, now)) {
+        }
+        seen = lastExec.load(std::memory_order_relaxed);
+        while (now > seen && !lastExec.compare_exchange_weak(seen, now)) {
+        }
+        return 0;
+    }
+
+    static std::atomic<int64_t> firstExec;
+    static std::atomic<int64_t> lastExec;
 };
+
+std::atomic<int64_t> NoopExecutor::firstExec{ INT64_MAX };
+std::atomic<int64_t> NoopExecutor::lastExec{ 0 };
 
 class NoopFactory : public ExecutorFactory
 {
@@ -165,12 +182,14 @@ int main(int argc, char** argv)
     faabric::runner::LocalCluster cluster(std::make_shared<NoopFactory>(), nHosts, perHost);
     auto& cli = faabric::planner::getPlannerClient();
 
-    std::vector<double> totalUs, scheduleUs;
+    std::vector<double> totalUs, scheduleUs, firstRunUs, lastRunUs;
     for (int it = 0; it < warmup + iters; it++) {
         if (profile && it == warmup) {
             startProfiler();
         }
         auto req = faabric::util::batchExecFactory("bench", "noop", nFunctions);
+        NoopExecutor::firstExec.store(INT64_MAX);
+        NoopExecutor::lastExec.store(0);
         auto t0 = std::chrono::steady_clock::now();
         auto decision = cli.callFunctions(req);
         auto t1 = std::chrono::steady_clock::now();
@@ -187,6 +206,9 @@ int main(int argc, char** argv)
         if (it >= warmup) {
             scheduleUs.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
             totalUs.push_back(std::chrono::duration<double, std::micro>(t2 - t0).count());
+            int64_t base = t0.time_since_epoch().count();
+            firstRunUs.push_back((double)(NoopExecutor::firstExec.load() - base) / 1e3);
+            lastRunUs.push_back((double)(NoopExecutor::lastExec.load() - base) / 1e3);
         }
     }
     if (profile) {
@@ -194,9 +216,12 @@ int main(int argc, char** argv)
     }
     std::sort(totalUs.begin(), totalUs.end());
     std::sort(scheduleUs.begin(), scheduleUs.end());
+    std::sort(firstRunUs.begin(), firstRunUs.end());
+    std::sort(lastRunUs.begin(), lastRunUs.end());
     double med = totalUs[totalUs.size() / 2];
     printf("{\"bench\": \"planner_fanout\", \"mode\": \"%s\", \"functions\": %d, \"hosts\": %d, \"iters\": %d, "
            "\"e2e_us_median\": %.1f, \"e2e_us_min\": %.1f, \"e2e_us_max\": %.1f, \"schedule_us_median\": %.1f, "
+           "\"first_function_runs_at_us\": %.1f, \"last_function_runs_at_us\": %.1f, "
            "\"functions_per_s\": %.0f}\n",
            mode.c_str(),
            nFunctions,
@@ -206,6 +231,8 @@ int main(int argc, char** argv)
            totalUs.front(),
            totalUs.back(),
            scheduleUs[scheduleUs.size() / 2],
+           firstRunUs[firstRunUs.size() / 2],
+           lastRunUs[lastRunUs.size() / 2],
            nFunctions / med * 1e6);
     return 0;
 }

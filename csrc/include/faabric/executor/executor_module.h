@@ -44,6 +44,9 @@ class ExecutorTask
 
     std::shared_ptr<faabric::BatchExecuteRequest> req;
     int messageIndex = 0;
+    // Run by the pool thread before the task itself: the scheduler uses it to
+    // spread the launch of a wide batch over the threads it has already woken
+    std::function<void()> prelude;
 };
 
 }
@@ -101,7 +104,8 @@ class Executor : public std::enable_shared_from_this<Executor>
       const std::vector<faabric::util::SnapshotMergeRegion>& mergeRegions);
 
     void executeTasks(std::vector<int> msgIdxs,
-                      std::shared_ptr<faabric::BatchExecuteRequest> req);
+                      std::shared_ptr<faabric::BatchExecuteRequest> req,
+                      std::function<void()> prelude = nullptr);
 
     // ---- hooks for subclasses ----
     virtual void reset(faabric::Message& msg);

@@ -494,7 +494,8 @@ std::vector<faabric::util::SnapshotDiff> Executor::mergeDirtyRegions(
 // Running tasks
 // ---------------------------------------------------------------------------
 void Executor::executeTasks(std::vector<int> msgIdxs,
-                            std::shared_ptr<faabric::BatchExecuteRequest> req)
+                            std::shared_ptr<faabric::BatchExecuteRequest> req,
+                            std::function<void()> prelude)
 {
     const int nMessages = (int)msgIdxs.size();
     lastExec = faabric::util::getGlobalClock().now();
@@ -552,7 +553,12 @@ void Executor::executeTasks(std::vector<int> msgIdxs,
             poolIdx = *availablePoolThreads.begin();
             availablePoolThreads.erase(availablePoolThreads.begin());
         }
-        threadTaskQueues[poolIdx].enqueue(ExecutorTask(msgIdx, req));
+        ExecutorTask task(msgIdx, req);
+        if (prelude) {
+            task.prelude = std::move(prelude);
+            prelude = nullptr;
+        }
+        threadTaskQueues[poolIdx].enqueue(std::move(task));
         std::lock_guard<std::mutex> lk(threadsMutex);
         if (threadPoolThreads[poolIdx] == nullptr) {
             threadPoolThreads[poolIdx] = std::make_shared<std::jthread>(
@@ -670,6 +676,14 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
         if (task.messageIndex == POOL_SHUTDOWN) {
             SPDLOG_DEBUG("Killing thread pool thread {}:{}", id, threadPoolIdx);
             break;
+        }
+        if (task.prelude) {
+            try {
+                task.prelude();
+            } catch (const std::exception& ex) {
+                SPDLOG_ERROR("Launching the rest of a batch from {} failed: {}", id, ex.what());
+            }
+            task.prelude = nullptr;
         }
         auto req = task.req;
         faabric::Message& msg = *req->mutable_messages(task.messageIndex);

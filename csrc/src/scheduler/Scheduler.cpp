@@ -306,6 +306,37 @@ std::shared_ptr<faabric::executor::Executor> Scheduler::claimExecutor(
     return e;
 }
 
+// Starting a function costs a thread wake-up (a few microseconds of the
+// caller's time each).  A wide batch is launched as a tree: half of what is left
+// is handed to the pool thread woken next, which launches it before running its
+// own message, so 128 functions are running after ~7 wake-up latencies instead
+// of after 128 wake-ups issued by one thread.
+namespace {
+using LaunchList = std::vector<std::pair<std::shared_ptr<faabric::executor::Executor>, int>>;
+constexpr int LAUNCH_TREE_LEAF = 4;
+
+void launchTree(std::shared_ptr<LaunchList> list, int lo, int hi, std::shared_ptr<faabric::BatchExecuteRequest> req)
+{
+    if (hi < 0) {
+        hi = (int)list->size();
+    }
+    while (hi - lo > LAUNCH_TREE_LEAF) {
+        int mid = lo + (hi - lo) / 2;
+        // [mid + 1, hi) travels with element `mid`
+        int subLo = mid + 1, subHi = hi;
+        std::function<void()> rest;
+        if (subHi > subLo) {
+            rest = [list, subLo, subHi, req] { launchTree(list, subLo, subHi, req); };
+        }
+        (*list)[mid].first->executeTasks({ (*list)[mid].second }, req, std::move(rest));
+        hi = mid;
+    }
+    for (int i = lo; i < hi; i++) {
+        (*list)[i].first->executeTasks({ (*list)[i].second }, req);
+    }
+}
+}
+
 void Scheduler::executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req)
 {
     std::unique_lock<std::shared_mutex> lock(mx);
@@ -378,9 +409,7 @@ void Scheduler::executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req)
         }
     }
     lock.unlock();
-    for (auto& [e, idx] : launches) {
-        e->executeTasks({ idx }, req);
-    }
+    launchTree(std::make_shared<LaunchList>(std::move(launches)), 0, -1, req);
     for (int idx : failed) {
         auto m = std::make_shared<faabric::Message>(req->messages(idx));
         m->set_returnvalue(1);
