@@ -57,9 +57,15 @@ void reportProfiler()
     itimerval tv{};
     setitimer(ITIMER_PROF, &tv, nullptr);
     int n = std::min(g_nSamples.load(), MAX_SAMPLES);
-    std::map<std::string, int> inclusive, self;
+    std::map<std::string, int> inclusive, self, under;
+    // PROFILE_ROOT=<substring>: a third table, inclusive counts of the samples
+    // whose stack contains a matching frame
+    const char* rootEnv = getenv("PROFILE_ROOT");
+    std::string root = rootEnv ? rootEnv : "";
+    int nUnder = 0;
     for (int i = 0; i < n; i++) {
         std::map<std::string, bool> seen;
+        std::vector<std::string> names;
         for (int d = 2; d < g_depths[i]; d++) { // skip handler + signal frame
             Dl_info info;
             std::string name = "?";
@@ -78,6 +84,19 @@ void reportProfiler()
             if (!seen[name]) {
                 seen[name] = true;
                 inclusive[name]++;
+                names.push_back(name);
+            }
+        }
+        if (!root.empty()) {
+            bool has = false;
+            for (auto& nm : names) {
+                has = has || nm.find(root) != std::string::npos;
+            }
+            if (has) {
+                nUnder++;
+                for (auto& nm : names) {
+                    under[nm]++;
+                }
             }
         }
     }
@@ -94,6 +113,10 @@ void reportProfiler()
     };
     top(self, "self");
     top(inclusive, "inclusive");
+    if (!root.empty()) {
+        fprintf(stderr, "(%d samples under *%s*)\n", nUnder, root.c_str());
+        top(under, "inclusive, under the root");
+    }
 }
 }
 
