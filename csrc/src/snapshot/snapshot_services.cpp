@@ -858,6 +858,33 @@ void DeviceSnapshot::uploadRegions()
     regionsDirty = false;
 }
 
+// The fused kernel stores straight into `target`: when that lives on another
+// GPU the launching device needs peer access to it (cudaMalloc memory is not
+// peer-mapped by default, unlike the communicators' VMM heaps)
+static void ensurePeerAccessTo(int fromDevice, const void* target)
+{
+    static std::mutex peerMx;
+    static std::set<std::pair<int, int>> enabled;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, target) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return;
+    }
+    if (attr.device == fromDevice) {
+        return;
+    }
+    std::lock_guard<std::mutex> lk(peerMx);
+    if (!enabled.insert({ fromDevice, attr.device }).second) {
+        return;
+    }
+    DeviceGuard g(fromDevice);
+    cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        SPDLOG_ERROR("No peer access from GPU {} to GPU {}: {}", fromDevice, attr.device, cudaGetErrorString(e));
+    }
+    cudaGetLastError();
+}
+
 void DeviceSnapshot::diffAndPush(const uint8_t* mem,
                                  size_t memSize,
                                  uint8_t* mainImage,
@@ -870,6 +897,9 @@ void DeviceSnapshot::diffAndPush(const uint8_t* mem,
         uploadRegions();
     }
     DeviceGuard g(device);
+    if (mainImage != nullptr) {
+        ensurePeerAccessTo(device, mainImage);
+    }
     DS_CUDA(cudaMemsetAsync(statsDev.ptr, 0, 16, (cudaStream_t)stream));
     fb::SnapDiffArgs a;
     memset(&a, 0, sizeof(a));
