@@ -489,23 +489,14 @@ def mode_sweep(args, dist: Dist):
     err = comm.check_error()
     # measured selection table: fastest algorithm per size bucket
     table = []
-    for r in rows:
-        cands = {a: r[a + "_us"] for a in ("ll", "oneshot", "twoshot", "nvls") if (a + "_us") in r}
-        if cands:
-            table.append({"max_bytes": r["bytes"], "algo": min(cands, key=cands.get), "us": min(cands.values())})
-    merged = []
-    for e in table:
-        if merged and merged[-1]["algo"] == e["algo"]:
-            merged[-1]["max_bytes"] = e["max_bytes"]
-        else:
-            merged.append(dict(e))
+    from faabric_b200.parallel import autotune
+
+    merged = autotune.json_table_from_rows(rows)
     if dist.rank == 0:
         tp = Path("gpurun_out") / f"tuning_N{n}.json"
         tp.parent.mkdir(exist_ok=True)
-        tp.write_text(json.dumps({"n_gpus": n, "allreduce": merged, "source": "bench.py --mode sweep"}, indent=1))
+        tp.write_text(json.dumps({"n_gpus": n, "allreduce": merged, "source": "bench.py --mode sweep", "rows": rows}, indent=1))
         # same table in the format FAABRIC_TUNING_FILE takes
-        from faabric_b200.parallel import autotune
-
         autotune.write_tuning_file(tp.with_suffix(".txt"), autotune.table_from_rows(rows), comment=f"bench.py --mode sweep, {n} GPUs, fp32")
     best = max((r.get("auto_busbw", 0) for r in rows), default=0)
     out = {

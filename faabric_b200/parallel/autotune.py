@@ -48,6 +48,25 @@ U64_MAX = (1 << 64) - 1
 Table = List[Tuple[int, str]]
 
 
+def row_times(r: dict) -> Dict[str, float]:
+    """Per-algorithm time of one sweep row.  The `auto` column is a second
+    sample of whichever algorithm the policy picked: latency samples are
+    one-sided noisy, so the smaller of the two stands for that algorithm."""
+    cands = {a: float(r[a + "_us"]) for a in TABLE_ALGOS if isinstance(r.get(a + "_us"), (int, float))}
+    pick = r.get("auto_pick")
+    if pick in cands and isinstance(r.get("auto_us"), (int, float)):
+        cands[pick] = min(cands[pick], float(r["auto_us"]))
+    return cands
+
+
+def pick_for(table: Sequence[Tuple[int, str]], nbytes: int) -> Optional[str]:
+    """What a table answers for a message of `nbytes` (first range that covers it)."""
+    for max_bytes, algo in sorted(table):
+        if nbytes <= max_bytes:
+            return algo
+    return None
+
+
 def table_from_rows(rows: Iterable[dict], hysteresis: float = 0.03) -> Table:
     """Fastest algorithm per measured size, merged into ``(max_bytes, algo)``
     ranges.  A challenger must beat the algorithm of the previous (smaller)
@@ -56,7 +75,7 @@ def table_from_rows(rows: Iterable[dict], hysteresis: float = 0.03) -> Table:
     table: Table = []
     prev: Optional[str] = None
     for r in sorted(rows, key=lambda r: r["bytes"]):
-        cands = {a: float(r[a + "_us"]) for a in TABLE_ALGOS if isinstance(r.get(a + "_us"), (int, float))}
+        cands = row_times(r)
         if not cands:
             continue
         best = min(cands, key=cands.get)
@@ -70,6 +89,19 @@ def table_from_rows(rows: Iterable[dict], hysteresis: float = 0.03) -> Table:
     if table:
         table[-1] = (U64_MAX, table[-1][1])
     return table
+
+
+def json_table_from_rows(rows: Iterable[dict]) -> List[dict]:
+    """The same table as ``table_from_rows`` in the JSON shape of ``profiles/tuning_N*.json``."""
+    rows = list(rows)
+    out = []
+    lo = 0
+    for max_bytes, algo in table_from_rows(rows):
+        inside = [row_times(r)[algo] for r in rows if lo < int(r["bytes"]) <= max_bytes and algo in row_times(r)]
+        out.append({"max_bytes": max(int(r["bytes"]) for r in rows) if max_bytes == U64_MAX else max_bytes, "algo": algo,
+                    "us": round(min(inside), 2) if inside else None})
+        lo = max_bytes
+    return out
 
 
 def format_tuning(table: Sequence[Tuple[int, str]] = (), settings: Optional[Dict[str, int]] = None, comment: str = "") -> str:

@@ -73,3 +73,32 @@ def test_cli_converts_measured_json(tmp_path):
     assert [a for _, a in table] == [e["algo"] for e in measured]
     assert table[-1][0] == autotune.U64_MAX
     assert settings == {"nvlsScalarMinBytes": 33554432}
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_committed_tables_pick_within_noise_of_the_best_algorithm(n):
+    """The table measured on B200s (profiles/tuning_N*.json) never answers with
+    an algorithm that the same sweep measured more than 15 % slower than the
+    best one at that size - the AUTO policy may not lose to a fixed algorithm."""
+    import json
+    from pathlib import Path
+
+    from faabric_b200.parallel import autotune
+
+    path = Path(__file__).resolve().parent.parent / "profiles" / f"tuning_N{n}.json"
+    if not path.exists():
+        pytest.skip(f"no measured table for {n} GPUs")
+    doc = json.loads(path.read_text())
+    rows = doc["rows"] if "rows" in doc else doc.get("sweep", [])
+    if not rows:
+        pytest.skip("table file carries no sweep rows")
+    table = autotune.table_from_rows(rows)
+    assert table and table[-1][0] == autotune.U64_MAX
+    for r in rows:
+        times = autotune.row_times(r)
+        if not times:
+            continue
+        pick = autotune.pick_for(table, int(r["bytes"]))
+        assert pick in times, (r["bytes"], pick)
+        best = min(times.values())
+        assert times[pick] <= best * 1.15 + 0.5, (n, r["bytes"], pick, times)
