@@ -146,6 +146,10 @@ class Communicator
     void free(uint64_t offset);
     uint8_t* heapPtr(uint64_t offset, int rank = -1) const;
     bool inHeap(const void* p, size_t bytes = 1) const;
+
+    // In the symmetric heap of ANY communicator of this process (device or
+    // loopback): a range check, no driver call
+    static bool isHeapPointer(const void* p);
     uint64_t offsetOf(const void* p) const;
     size_t userHeapBytes() const { return cfg_.heapBytes; }
 
@@ -342,6 +346,7 @@ class Communicator
     uint64_t stageRecvOff_ = 0;
     uint64_t userOff_ = 0;
     uint64_t heapTotal_ = 0;
+    bool heapRegistered_ = false;
 
     // allocator state
     std::mutex allocMx_;

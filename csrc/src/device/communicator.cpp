@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <set>
+#include <shared_mutex>
 #include <stdexcept>
 #include <unistd.h>
 
@@ -293,8 +294,35 @@ std::mutex loopRangesMx;
 std::vector<std::pair<const uint8_t*, size_t>> loopRanges;
 }
 
+// Symmetric heaps of the communicators alive in this process: lets hot paths
+// (every MPI call classifies its buffers) recognise heap memory with a range
+// check instead of a driver query
+namespace {
+std::shared_mutex heapRangesMx;
+std::vector<std::pair<const uint8_t*, size_t>> heapRanges;
+std::atomic<int> nHeapRanges{ 0 };
+std::atomic<int> nLoopRanges{ 0 };
+}
+
+bool Communicator::isHeapPointer(const void* p)
+{
+    if (nHeapRanges.load(std::memory_order_acquire) == 0) {
+        return false;
+    }
+    std::shared_lock<std::shared_mutex> lk(heapRangesMx);
+    for (const auto& [base, n] : heapRanges) {
+        if ((const uint8_t*)p >= base && (const uint8_t*)p < base + n) {
+            return true;
+        }
+    }
+    return false;
+}
+
 bool Communicator::isLoopbackHeapPointer(const void* p)
 {
+    if (nLoopRanges.load(std::memory_order_acquire) == 0) {
+        return false;
+    }
     std::lock_guard<std::mutex> lk(loopRangesMx);
     for (const auto& [base, n] : loopRanges) {
         if ((const uint8_t*)p >= base && (const uint8_t*)p < base + n) {
@@ -331,7 +359,8 @@ struct Communicator::Backing
             {
                 std::lock_guard<std::mutex> lk(loopRangesMx);
                 for (void* p : hostAllocs) {
-                    std::erase_if(loopRanges, [p](const auto& r) { return r.first == (const uint8_t*)p; });
+                    size_t gone = std::erase_if(loopRanges, [p](const auto& r) { return r.first == (const uint8_t*)p; });
+                    nLoopRanges.fetch_sub((int)gone, std::memory_order_release);
                 }
             }
             for (void* p : hostAllocs) {
@@ -502,6 +531,7 @@ std::vector<std::shared_ptr<Communicator>> Communicator::createLocal(
             bases[r] = (uint8_t*)p;
             std::lock_guard<std::mutex> lk(loopRangesMx);
             loopRanges.emplace_back((const uint8_t*)p, total);
+            nLoopRanges.fetch_add(1, std::memory_order_release);
         }
         for (int r = 0; r < nranks; r++) {
             void* e = nullptr;
@@ -1010,6 +1040,15 @@ cudaStream_t Communicator::internalStream()
 
 Communicator::~Communicator()
 {
+    if (heapRegistered_) {
+        std::unique_lock<std::shared_mutex> lk(heapRangesMx);
+        const uint8_t* base = dev_.heap[dev_.rank];
+        auto it = std::find_if(heapRanges.begin(), heapRanges.end(), [base](const auto& r) { return r.first == base; });
+        if (it != heapRanges.end()) {
+            heapRanges.erase(it);
+            nHeapRanges.fetch_sub(1, std::memory_order_release);
+        }
+    }
     if (internalStream_ != nullptr) {
         bindDevice();
         cudaStreamDestroy(internalStream_);
@@ -2245,6 +2284,12 @@ int Communicator::barrier(cudaStream_t s)
 // ---------------------------------------------------------------------------
 void Communicator::finishSetup()
 {
+    if (dev_.heap[dev_.rank] != nullptr && heapTotal_ > 0) {
+        std::unique_lock<std::shared_mutex> lk(heapRangesMx);
+        heapRanges.emplace_back((const uint8_t*)dev_.heap[dev_.rank], heapTotal_);
+        nHeapRanges.fetch_add(1, std::memory_order_release);
+        heapRegistered_ = true;
+    }
     if (loop_) {
         // the host twins synchronise inside the "kernels", like the GPU ones
         streamSync_ = false;

@@ -211,6 +211,9 @@ bool MpiWorld::isDevicePointer(const void* p)
     if (p == nullptr) {
         return false;
     }
+    if (faabric::device::Communicator::isHeapPointer(p)) {
+        return true; // symmetric heap of a communicator here: no driver query needed
+    }
     if (faabric::device::Communicator::isLoopbackHeapPointer(p)) {
         return true; // loopback backend: heap memory plays the device's role
     }
