@@ -268,8 +268,21 @@ class Planner
     std::vector<std::shared_ptr<faabric::Message>> pendingResults;
     bool drainingResults = false;
 
+    // Look-ups shared by consecutive results of one app / one host
+    struct ResultContext
+    {
+        bool valid = false;
+        int appId = 0;
+        std::map<int, std::shared_ptr<faabric::Message>>* results = nullptr;
+        std::string hostName;
+        std::shared_ptr<Host> host;
+        bool hostKnown = false;
+    };
+
     // Caller holds plannerMx exclusively
-    void recordResultLocked(const std::shared_ptr<faabric::Message>& msg, std::vector<std::string>& toNotify);
+    void recordResultLocked(const std::shared_ptr<faabric::Message>& msg,
+                            std::vector<std::string>& toNotify,
+                            ResultContext* ctx = nullptr);
     std::condition_variable_any appFinishedCv;
 
     void compactInFlightLocked();

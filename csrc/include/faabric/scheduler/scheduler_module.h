@@ -255,6 +255,11 @@ class Scheduler
       faabric::Message& msg,
       std::unique_lock<std::shared_mutex>& schedulerLock);
 
+    std::shared_ptr<faabric::executor::Executor> claimExecutorForKey(
+      const std::string& key,
+      faabric::Message& msg,
+      std::unique_lock<std::shared_mutex>& schedulerLock);
+
     // ---- Point-to-point ----
     faabric::transport::PointToPointBroker& broker;
 

@@ -359,13 +359,16 @@ void Planner::setMessageResults(const std::vector<std::shared_ptr<faabric::Messa
     std::vector<std::pair<std::shared_ptr<faabric::Message>, std::vector<std::string>>> notify;
     {
         std::unique_lock<std::shared_mutex> lock(plannerMx);
+        // results of a fan-in mostly belong to one app and a handful of
+        // hosts: the look-ups they share are done once
+        ResultContext ctx;
         for (const auto& msg : msgs) {
             if (msg->returnvalue() == MIGRATED_FUNCTION_RETURN_VALUE) {
                 continue;
             }
             std::vector<std::string> toNotify;
             try {
-                recordResultLocked(msg, toNotify);
+                recordResultLocked(msg, toNotify, &ctx);
             } catch (const std::exception& e) {
                 SPDLOG_ERROR("Planner could not record the result of message {}: {}", msg->id(), e.what());
             }
@@ -408,10 +411,29 @@ void Planner::submitMessageResult(std::shared_ptr<faabric::Message> msg)
     }
 }
 
-void Planner::recordResultLocked(const std::shared_ptr<faabric::Message>& msg, std::vector<std::string>& toNotify)
+void Planner::recordResultLocked(const std::shared_ptr<faabric::Message>& msg,
+                                 std::vector<std::string>& toNotify,
+                                 ResultContext* ctx)
 {
     int appId = msg->appid();
     int msgId = msg->id();
+    ResultContext local;
+    if (ctx == nullptr) {
+        ctx = &local;
+    }
+    if (!ctx->valid || ctx->appId != appId) {
+        ctx->valid = true;
+        ctx->appId = appId;
+        ctx->results = &state.appResults[appId];
+        ctx->hostName.clear();
+        ctx->host = nullptr;
+    }
+    if (ctx->host == nullptr || ctx->hostName != msg->executedhost()) {
+        auto found = state.hostMap.find(msg->executedhost());
+        ctx->hostName = msg->executedhost();
+        ctx->host = found == state.hostMap.end() ? nullptr : found->second;
+        ctx->hostKnown = found != state.hostMap.end();
+    }
     bool isFrozen = msg->returnvalue() == FROZEN_FUNCTION_RETURN_VALUE;
     if (isFrozen) {
         auto ev = state.evictedRequests.find(appId);
@@ -431,13 +453,19 @@ void Planner::recordResultLocked(const std::shared_ptr<faabric::Message>& msg, s
             }
         }
     }
-    auto hostIt = state.hostMap.find(msg->executedhost());
-    bool firstResult = state.appResults[appId].count(msgId) == 0;
-    if (hostIt != state.hostMap.end() && (firstResult || isFrozen)) {
-        releaseHostSlots(hostIt->second);
+    const bool hostKnown = ctx->hostKnown && ctx->host != nullptr;
+    auto& appResultsOfApp = *ctx->results;
+    auto slot = appResultsOfApp.find(msgId);
+    bool firstResult = slot == appResultsOfApp.end();
+    if (hostKnown && (firstResult || isFrozen)) {
+        releaseHostSlots(ctx->host);
     }
     if (!isFrozen) {
-        state.appResults[appId][msgId] = msg;
+        if (firstResult) {
+            appResultsOfApp.emplace_hint(appResultsOfApp.end(), msgId, msg);
+        } else {
+            slot->second = msg;
+        }
     }
     auto inFlight = state.inFlightReqs.find(appId);
     if (inFlight != state.inFlightReqs.end()) {
@@ -466,8 +494,8 @@ void Planner::recordResultLocked(const std::shared_ptr<faabric::Message>& msg, s
         }
         if (pos != ids.end() && done.insert(msgId).second) {
             int port = decision->mpiPorts.at((size_t)(pos - ids.begin()));
-            if (hostIt != state.hostMap.end()) {
-                releaseHostMpiPort(hostIt->second, port);
+            if (hostKnown) {
+                releaseHostMpiPort(ctx->host, port);
             }
             if ((int)done.size() == req->messages_size()) {
                 SPDLOG_DEBUG("Planner removing app {} from in-flight", appId);

@@ -265,7 +265,14 @@ std::shared_ptr<faabric::executor::Executor> Scheduler::claimExecutor(
   faabric::Message& msg,
   std::unique_lock<std::shared_mutex>& schedulerLock)
 {
-    std::string key = executorKey(msg);
+    return claimExecutorForKey(executorKey(msg), msg, schedulerLock);
+}
+
+std::shared_ptr<faabric::executor::Executor> Scheduler::claimExecutorForKey(
+  const std::string& key,
+  faabric::Message& msg,
+  std::unique_lock<std::shared_mutex>& schedulerLock)
+{
     // Fast path: somebody told us they are idle
     for (;;) {
         std::shared_ptr<faabric::executor::Executor> candidate;
@@ -399,10 +406,20 @@ void Scheduler::executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req)
     std::vector<std::pair<std::shared_ptr<faabric::executor::Executor>, int>> launches;
     std::vector<int> failed;
     std::string failure;
+    // (the messages of one per-host request nearly always share their key:
+    // build it once, not 128 times under the scheduler's lock)
+    launches.reserve(n);
+    const faabric::Message* keyOf = nullptr;
+    std::string key;
     for (int i = 0; i < n; i++) {
         faabric::Message& m = *req->mutable_messages(i);
         try {
-            launches.emplace_back(claimExecutor(m, lock), i);
+            if (keyOf == nullptr || m.user() != keyOf->user() || m.function() != keyOf->function() ||
+                m.executedhost() != keyOf->executedhost()) {
+                key = executorKey(m);
+                keyOf = &m;
+            }
+            launches.emplace_back(claimExecutorForKey(key, m, lock), i);
         } catch (const std::exception& ex) {
             failure = ex.what();
             failed.push_back(i);
