@@ -177,6 +177,8 @@ class Executor : public std::enable_shared_from_this<Executor>
 
     uint64_t getDeviceMergeCount() const { return deviceMergeCount.load(); }
 
+    std::string schedulerKey;
+
     uint64_t getLastDeviceDiffBytes() const { return lastDeviceDiffBytes.load(); }
 
     // Blocks until every pool thread finished (tests)

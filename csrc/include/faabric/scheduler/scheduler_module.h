@@ -232,7 +232,27 @@ class Scheduler
 
     // ---- Threads ----
     // Recently released executors per function (hints: entries may be stale)
-    std::mutex idleMx;
+    // (a spin lock: the critical section is one push / pop, and at the end of
+    // a 1024-way fan-out every pool thread passes through it at once - a
+    // sleeping mutex turns that into a convoy of futex hand-offs)
+    struct IdleLock
+    {
+        std::atomic_flag flag = ATOMIC_FLAG_INIT;
+
+        void lock()
+        {
+            for (int spins = 0; flag.test_and_set(std::memory_order_acquire); spins++) {
+                if (spins < 64) {
+                    __builtin_ia32_pause();
+                } else {
+                    std::this_thread::yield();
+                }
+            }
+        }
+
+        void unlock() { flag.clear(std::memory_order_release); }
+    };
+    IdleLock idleMx;
     std::unordered_map<std::string, std::vector<std::weak_ptr<faabric::executor::Executor>>> idleExecutors;
 
     faabric::snapshot::SnapshotRegistry& reg;

@@ -1472,6 +1472,11 @@ template<typename T>
 class Queue
 {
   public:
+    // Consumers that are not in a request/response exchange (an executor's
+    // pool thread waiting for its next function) go to sleep at once: with a
+    // thousand of them a brief yield-spin each is a scheduling storm
+    void setSpinBeforeSleep(bool v) { spinBeforeSleep = v; }
+
     void enqueue(T value)
     {
         {
@@ -1503,7 +1508,7 @@ class Queue
         // next item within microseconds: look for it briefly before paying
         // for a sleep + wake-up (the yield lets a producer that shares our
         // core run)
-        if (approxSize.load(std::memory_order_acquire) == 0) {
+        if (spinBeforeSleep && approxSize.load(std::memory_order_acquire) == 0) {
             auto start = std::chrono::steady_clock::now();
             for (int i = 0; approxSize.load(std::memory_order_acquire) == 0; i++) {
                 if ((i & 15) == 15) {
@@ -1578,6 +1583,7 @@ class Queue
   private:
     std::queue<T> mq;
     std::atomic<long> approxSize{ 0 };
+    bool spinBeforeSleep = true;
     std::condition_variable enqueueNotifier;
     std::condition_variable emptyNotifier;
     std::mutex mx;

@@ -101,6 +101,9 @@ Executor::Executor(faabric::Message& msg)
   , threadPoolThreads(threadPoolSize)
   , threadTaskQueues(threadPoolSize)
 {
+    for (auto& q : threadTaskQueues) {
+        q.setSpinBeforeSleep(false);
+    }
     faabric::util::SystemConfig& conf = faabric::util::getSystemConfig();
     // Unique id: host, function, counter
     id = conf.endpointHost + "_" + std::to_string(faabric::util::generateGid());
@@ -192,10 +195,13 @@ void Executor::claim()
 
 void Executor::releaseClaim()
 {
+    // (the key only depends on what the executor was bound to: built once)
+    if (schedulerKey.empty()) {
+        schedulerKey = faabric::scheduler::Scheduler::executorKeyFor(boundMessage);
+    }
     claimed.store(false);
     // Tell the scheduler so the next claim does not have to search for us
-    faabric::scheduler::getScheduler().notifyExecutorIdle(faabric::scheduler::Scheduler::executorKeyFor(boundMessage),
-                                                          weak_from_this());
+    faabric::scheduler::getScheduler().notifyExecutorIdle(schedulerKey, weak_from_this());
 }
 
 bool Executor::isExecuting()

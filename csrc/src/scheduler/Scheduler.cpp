@@ -129,7 +129,7 @@ void Scheduler::reset()
         executors.clear();
     }
     {
-        std::lock_guard<std::mutex> lk(idleMx);
+        std::lock_guard<IdleLock> lk(idleMx);
         idleExecutors.clear();
     }
     for (auto& e : toStop) {
@@ -178,7 +178,7 @@ void SchedulerReaperThread::doWork()
 
 void Scheduler::notifyExecutorIdle(const std::string& funcKey, std::weak_ptr<faabric::executor::Executor> executor)
 {
-    std::lock_guard<std::mutex> lk(idleMx);
+    std::lock_guard<IdleLock> lk(idleMx);
     idleExecutors[funcKey].push_back(std::move(executor));
 }
 
@@ -277,7 +277,7 @@ std::shared_ptr<faabric::executor::Executor> Scheduler::claimExecutorForKey(
     for (;;) {
         std::shared_ptr<faabric::executor::Executor> candidate;
         {
-            std::lock_guard<std::mutex> lk(idleMx);
+            std::lock_guard<IdleLock> lk(idleMx);
             auto it = idleExecutors.find(key);
             if (it == idleExecutors.end() || it->second.empty()) {
                 break;
