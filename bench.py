@@ -39,8 +39,8 @@ sys.path.insert(0, str(ROOT))
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refcpu", "mpi-host", "mpi-device", "mpi-symmetric", "mpi-symmetric-nb"])
     ap.add_argument("--mode", default="allreduce",
                     choices=["allreduce", "sweep", "alltoall", "snapshot", "planner", "threads", "pingpong", "hostcoll"])
