@@ -84,6 +84,15 @@ struct RankState
     uint64_t groupLaunchSeq = 0;
     uint64_t groupCompletedSeq = 0;
     void* groupCompletedStream = nullptr;
+    // This rank's communicator and first stream, looked up once: the per-call
+    // path of a burst must not take world-wide locks (8 rank threads issuing
+    // 214 calls each would serialise on them)
+    std::shared_ptr<faabric::device::Communicator> cachedComm;
+    void* cachedStream0 = nullptr;
+    int cachedCommRank = -1;
+    bool cachedCommValid = false;
+    uint64_t deferredCount = 0;
+    std::atomic<uint64_t>* deferredCounter = nullptr;
 
     void reset()
     {
@@ -101,6 +110,12 @@ struct RankState
         groupComm = nullptr;
         groupItems.clear();
         groupRequests.clear();
+        cachedComm = nullptr;
+        cachedStream0 = nullptr;
+        cachedCommRank = -1;
+        cachedCommValid = false;
+        deferredCount = 0;
+        deferredCounter = nullptr;
         nextRequestId = 1;
     }
 };
@@ -864,6 +879,10 @@ static void flushPendingGroup()
     if (tls.groupItems.empty()) {
         return;
     }
+    if (tls.deferredCounter != nullptr && tls.deferredCount > 0) {
+        tls.deferredCounter->fetch_add(tls.deferredCount);
+        tls.deferredCount = 0;
+    }
     auto comm = tls.groupComm;
     auto items = std::move(tls.groupItems);
     auto reqs = std::move(tls.groupRequests);
@@ -1221,11 +1240,24 @@ int MpiWorld::iAllReduce(int rank, uint8_t* send, uint8_t* recv, faabric_datatyp
     r.recvRank = rank;
     int fdt = fbDtypeFor(dt);
     int fop = fbOpFor(op);
-    auto comm = (bytes > 0 && fdt >= 0 && fop >= 0 && isDevicePointer(send)) ? getDeviceComm(rank) : nullptr;
+    if (!tls.cachedCommValid || tls.cachedCommRank != rank) {
+        tls.cachedComm = getDeviceComm(rank);
+        tls.cachedStream0 = tls.cachedComm != nullptr ? streamForRank(rank, 0) : nullptr;
+        tls.cachedCommRank = rank;
+        tls.cachedCommValid = true;
+    }
+    std::shared_ptr<faabric::device::Communicator> comm;
+    bool symmetric = false;
+    if (bytes > 0 && fdt >= 0 && fop >= 0 && tls.cachedComm != nullptr) {
+        // a buffer inside this rank's symmetric heap needs no driver query
+        symmetric = tls.cachedComm->inHeap(send, bytes) && tls.cachedComm->inHeap(recv, bytes);
+        if (symmetric || isDevicePointer(send)) {
+            comm = tls.cachedComm;
+        }
+    }
     if (comm != nullptr) {
         // Symmetric buffers may use any channel; others go through the single
         // staging area on channel 0
-        const bool symmetric = comm->inHeap(send, bytes) && comm->inHeap(recv, bytes);
         if (symmetric && ((((uintptr_t)send) | ((uintptr_t)recv)) & 15) == 0 && groupIallreduce) {
             // Deferred: the whole burst becomes ONE kernel at the next wait
             if (!tls.groupItems.empty() &&
@@ -1235,10 +1267,11 @@ int MpiWorld::iAllReduce(int rank, uint8_t* send, uint8_t* recv, faabric_datatyp
             tls.groupComm = comm;
             tls.groupDtype = fdt;
             tls.groupOp = fop;
-            tls.groupStream = streamForRank(rank, 0);
+            tls.groupStream = tls.cachedStream0;
             tls.groupItems.push_back({ send, recv, (size_t)count });
             tls.groupRequests.push_back(requestId);
-            deviceCollectives.fetch_add(1);
+            tls.deferredCount++; // added to the world's counter at the flush
+            tls.deferredCounter = &deviceCollectives;
             r.isDeviceCollective = true;
             r.deferred = true;
             r.stream = tls.groupStream;

@@ -31,9 +31,27 @@ thread_local MpiContext executingContext;
 thread_local bool mpiInitialised = false;
 thread_local bool mpiFinalised = false;
 
+// (looked up once per thread and world: every MPI call starts here, and eight
+// rank threads copying the same shared_ptr bounce its reference count around)
+namespace {
+thread_local int cachedWorldId = -1;
+thread_local MpiWorld* cachedWorld = nullptr;
+}
+
 MpiWorld& getExecutingWorld()
 {
-    return getMpiWorldRegistry().getWorld(executingContext.getWorldId());
+    int worldId = executingContext.getWorldId();
+    if (cachedWorld == nullptr || cachedWorldId != worldId) {
+        cachedWorld = &getMpiWorldRegistry().getWorld(worldId);
+        cachedWorldId = worldId;
+    }
+    return *cachedWorld;
+}
+
+void forgetExecutingWorld()
+{
+    cachedWorld = nullptr;
+    cachedWorldId = -1;
 }
 
 faabric::Message* getExecutingCall()
@@ -43,6 +61,10 @@ faabric::Message* getExecutingCall()
 
 int terminateMpi()
 {
+    struct Forget
+    {
+        ~Forget() { forgetExecutingWorld(); }
+    } forget;
     // Destroy the MPI world
     bool mustClear = getExecutingWorld().destroy();
     if (mustClear) {
@@ -142,6 +164,7 @@ extern "C"
 
 int MPI_Init(int* argc, char*** argv)
 {
+    forgetExecutingWorld(); // a pool thread runs many functions, one world each
     faabric::Message* call = getExecutingCall();
     // A function resuming after a migration / thaw re-enters an existing
     // world: even rank 0 joins, and nobody waits for it at a start-up barrier
