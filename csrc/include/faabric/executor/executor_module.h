@@ -179,6 +179,12 @@ class Executor : public std::enable_shared_from_this<Executor>
 
     std::string schedulerKey;
 
+    // Incremental device THREADS: the stamp of the main image this executor's
+    // memory and private base were last identical to (0 = never), and which
+    // image that was
+    uint32_t threadsSyncStamp = 0;
+    uint64_t threadsSyncImageUid = 0;
+
     uint64_t getLastDeviceDiffBytes() const { return lastDeviceDiffBytes.load(); }
 
     // Blocks until every pool thread finished (tests)

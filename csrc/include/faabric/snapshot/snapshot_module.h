@@ -134,6 +134,49 @@ class DeviceSnapshot
     // descriptor carries no IPC handle)
     static std::shared_ptr<DeviceSnapshot> fromDescriptor(const DeviceSnapshotDescriptor& desc);
 
+    // ---- incremental synchronisation (THREADS fork-join after the first) ----
+    // Every 4 KiB page of an image this process owns carries a stamp: the last
+    // fork (2k: the main thread's refresh) or join (2k+1: a host's merge) that
+    // changed it.  A copy that was identical to the image at stamp s is brought
+    // up to date by pulling the pages stamped later than s.
+    // nullptr when the image has no stamps (wrapped or mapped from elsewhere)
+    uint32_t* pageStamps();
+
+    // Starts fork k: returns 2k.  currentForkStamp() repeats it.
+    uint32_t beginFork();
+
+    uint32_t currentForkStamp() const { return 2 * forkCounter.load(); }
+
+    // Copies that synchronised before this stamp must be copied whole again
+    // (the image was rewritten by something that does not stamp pages)
+    uint32_t fullMutationStamp() const { return fullMutation.load(); }
+
+    // Distinguishes images that reuse an address
+    uint64_t uid() const { return uniqueId; }
+
+    // The image was (or may have been) changed without stamping pages
+    void markRewritten() { noteFullMutation(); }
+
+    // image := mem wherever they differ, stamping the changed pages with
+    // `stamp` (asynchronous on `stream`, which must belong to this image's GPU)
+    void syncPagesFrom(const uint8_t* mem, size_t n, uint32_t stamp, void* stream = nullptr);
+
+    // Pages stamped later than `since` are copied into dst1 (and dst2); runs on
+    // `onDevice`, the GPU that owns the destinations.  Asynchronous.
+    void pullChangedPages(uint8_t* dst1, uint8_t* dst2, uint32_t since, size_t n, int onDevice, void* stream = nullptr);
+
+    // Pages moved by the launches above since the counter was last read
+    // (synchronises `stream`)
+    uint64_t takePageCopyCount(int onDevice, void* stream = nullptr);
+
+    // diffAndPush into an image that keeps stamps: pages this launch changes
+    // there are stamped with `stamp`
+    void setPushStamps(uint32_t* stampsOfTarget, uint32_t stamp)
+    {
+        pushStamps = stampsOfTarget;
+        pushStamp = stamp;
+    }
+
     // How many fused diff+push launches this image has issued (tests, metrics)
     uint64_t getDiffPushCount() const { return diffPushCount; }
 
@@ -160,6 +203,19 @@ class DeviceSnapshot
 
     void* ipcMapped = nullptr;
     uint64_t diffPushCount = 0;
+
+    faabric::util::DeviceRegion stampsDev;
+    std::atomic<uint32_t> forkCounter{ 0 };
+    std::atomic<uint32_t> fullMutation{ 0 };
+    uint64_t uniqueId = 0;
+    uint32_t* pushStamps = nullptr;
+    uint32_t pushStamp = 0;
+    // per-GPU counters for the page kernels (they run where the copies live)
+    std::map<int, faabric::util::DeviceRegion> pageStatsDev;
+
+    uint64_t* pageStatsOn(int onDevice);
+
+    void noteFullMutation() { fullMutation.store(2 * forkCounter.load() + 1); }
 };
 
 }

@@ -251,11 +251,36 @@ struct SnapDiffArgs
     uint8_t* chunkFlags;       // optional: 128-byte chunks that produced a diff
     uint64_t* stats;           // [0]=diff bytes, [1]=pages with diffs
     int32_t updateBase;        // also fold the changes into the local base
+    // optional: one word per 4 KiB page of `dst`, set to `pageStamp` for every
+    // page this launch changed (peers find out what to re-pull at the next fork)
+    uint32_t* pageStampOut;
+    uint32_t pageStamp;
 };
 
 cudaError_t launchSnapshotDiffPush(const SnapDiffArgs& a,
                                    int blocks,
                                    cudaStream_t s);
+// dst page := src page wherever they differ; changed pages get `stamp`.
+// stats[0] += pages copied
+cudaError_t launchPageSync(const uint8_t* src,
+                           uint8_t* dst,
+                           uint32_t* pageStamps,
+                           uint32_t stamp,
+                           uint64_t size,
+                           uint64_t* stats,
+                           int blocks,
+                           cudaStream_t s);
+// Copies every page whose stamp is newer than `since` from src into dst1 (and
+// dst2 when not null).  stats[0] += pages copied
+cudaError_t launchPagePull(const uint8_t* src,
+                           uint8_t* dst1,
+                           uint8_t* dst2,
+                           const uint32_t* pageStamps,
+                           uint32_t since,
+                           uint64_t size,
+                           uint64_t* stats,
+                           int blocks,
+                           cudaStream_t s);
 cudaError_t launchDirtyScan(const uint8_t* mem,
                             const uint8_t* base,
                             uint64_t size,

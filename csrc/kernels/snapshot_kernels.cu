@@ -535,6 +535,9 @@ __global__ void __launch_bounds__(512, 2) snapshotDiffPushKernel(
             if (a.pageFlagsOut != nullptr) {
                 a.pageFlagsOut[page] = 1;
             }
+            if (a.pageStampOut != nullptr) {
+                a.pageStampOut[page] = a.pageStamp; // same value from every writer
+            }
         }
     }
 
@@ -579,6 +582,10 @@ __global__ void __launch_bounds__(512, 2) snapshotDiffPushKernel(
                 }
                 if (d) {
                     diffBytes += sz;
+                    if (a.pageStampOut != nullptr) {
+                        a.pageStampOut[off / PAGE] = a.pageStamp;
+                        a.pageStampOut[(off + sz - 1) / PAGE] = a.pageStamp;
+                    }
                 }
             }
         }
@@ -609,6 +616,134 @@ cudaError_t launchSnapshotDiffPush(const SnapDiffArgs& a,
                                    cudaStream_t s)
 {
     snapshotDiffPushKernel<<<blocks, 512, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------
+// Page-granular synchronisation of two images (incremental THREADS fork-join):
+// pageSync folds an executor's memory into the main image and stamps what
+// changed; pagePull brings a stale copy up to date from the stamps.  One warp
+// per 4 KiB page, 16-byte vectors, 8 per lane.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void copyPage(const uint8_t* src, uint8_t* dst1, uint8_t* dst2, uint64_t pBeg, uint64_t nBytes, int lane)
+{
+    const uint64_t nVec = nBytes >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + pBeg);
+    uint4* d4 = reinterpret_cast<uint4*>(dst1 + pBeg);
+    uint4* e4 = dst2 != nullptr ? reinterpret_cast<uint4*>(dst2 + pBeg) : nullptr;
+    for (uint64_t i = lane; i < nVec; i += 32) {
+        uint4 v = s4[i];
+        d4[i] = v;
+        if (e4 != nullptr) {
+            e4[i] = v;
+        }
+    }
+    for (uint64_t p = (nVec << 4) + lane; p < nBytes; p += 32) {
+        uint8_t b = src[pBeg + p];
+        dst1[pBeg + p] = b;
+        if (dst2 != nullptr) {
+            dst2[pBeg + p] = b;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512, 2) pageSyncKernel(const uint8_t* src,
+                                                         uint8_t* dst,
+                                                         uint32_t* pageStamps,
+                                                         uint32_t stamp,
+                                                         uint64_t size,
+                                                         uint64_t* stats)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warpId = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nWarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t nPages = (size + PAGE - 1) / PAGE;
+    uint32_t copied = 0;
+    for (uint64_t page = warpId; page < nPages; page += nWarps) {
+        const uint64_t pBeg = page * PAGE;
+        const uint64_t nBytes = min((uint64_t)PAGE, size - pBeg);
+        const uint64_t nVec = nBytes >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + pBeg);
+        const uint4* d4 = reinterpret_cast<const uint4*>(dst + pBeg);
+        bool differ = false;
+        for (uint64_t i = lane; i < nVec; i += 32) {
+            uint4 a = s4[i], b = d4[i];
+            differ |= (a.x != b.x) | (a.y != b.y) | (a.z != b.z) | (a.w != b.w);
+        }
+        for (uint64_t p = (nVec << 4) + lane; p < nBytes; p += 32) {
+            differ |= src[pBeg + p] != dst[pBeg + p];
+        }
+        if (__any_sync(0xffffffffu, differ)) {
+            copyPage(src, dst, nullptr, pBeg, nBytes, lane);
+            if (lane == 0) {
+                if (pageStamps != nullptr) {
+                    pageStamps[page] = stamp;
+                }
+                copied++;
+            }
+        }
+    }
+    if (lane == 0 && copied != 0 && stats != nullptr) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&stats[0]), (unsigned long long)copied);
+    }
+}
+
+__global__ void __launch_bounds__(512, 2) pagePullKernel(const uint8_t* src,
+                                                         uint8_t* dst1,
+                                                         uint8_t* dst2,
+                                                         const uint32_t* pageStamps,
+                                                         uint32_t since,
+                                                         uint64_t size,
+                                                         uint64_t* stats)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warpId = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nWarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t nPages = (size + PAGE - 1) / PAGE;
+    uint32_t copied = 0;
+    // each lane looks at one stamp of a group of 32 pages, the warp then copies
+    // the flagged ones one after the other
+    for (uint64_t group = warpId * 32; group < nPages; group += nWarps * 32) {
+        const uint64_t mine = group + lane;
+        const bool want = mine < nPages && pageStamps[mine] > since;
+        uint32_t mask = __ballot_sync(0xffffffffu, want);
+        while (mask != 0) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint64_t pBeg = (group + k) * PAGE;
+            copyPage(src, dst1, dst2, pBeg, min((uint64_t)PAGE, size - pBeg), lane);
+            copied++;
+        }
+    }
+    if (lane == 0 && copied != 0 && stats != nullptr) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&stats[0]), (unsigned long long)copied);
+    }
+}
+
+cudaError_t launchPageSync(const uint8_t* src,
+                           uint8_t* dst,
+                           uint32_t* pageStamps,
+                           uint32_t stamp,
+                           uint64_t size,
+                           uint64_t* stats,
+                           int blocks,
+                           cudaStream_t s)
+{
+    pageSyncKernel<<<blocks, 512, 0, s>>>(src, dst, pageStamps, stamp, size, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launchPagePull(const uint8_t* src,
+                           uint8_t* dst1,
+                           uint8_t* dst2,
+                           const uint32_t* pageStamps,
+                           uint32_t since,
+                           uint64_t size,
+                           uint64_t* stats,
+                           int blocks,
+                           cudaStream_t s)
+{
+    pagePullKernel<<<blocks, 512, 0, s>>>(src, dst1, dst2, pageStamps, since, size, stats);
     return cudaGetLastError();
 }
 

@@ -421,6 +421,16 @@ std::shared_ptr<faabric::snapshot::DeviceSnapshot> Executor::getMainThreadDevice
     return snap;
 }
 
+// FAABRIC_THREADS_INCREMENTAL=0: every fork copies the whole image again
+static bool incrementalDeviceThreads()
+{
+    static const bool on = []() {
+        const char* v = getenv("FAABRIC_THREADS_INCREMENTAL");
+        return v == nullptr || std::string(v) != "0";
+    }();
+    return on;
+}
+
 // Every host of a THREADS batch (the main one included) diffs against a PRIVATE
 // copy of what it started from: the main image is being written by the other
 // hosts' merge kernels while this host still runs.
@@ -430,18 +440,36 @@ void Executor::prepareDeviceThreads(const std::string& key, bool isMain)
     auto mainSnap = reg.getDeviceSnapshot(key);
     GpuGuard g(dv.device);
     auto stream = (cudaStream_t)computeStream;
-    if (!isMain) {
-        if (mainSnap->getSize() > dv.size) {
-            setMemorySize(mainSnap->getSize());
-            dv = getDeviceMemoryView();
-        }
-        mainSnap->restoreTo(dv.ptr, std::min(dv.size, mainSnap->getSize()), stream);
+    if (!isMain && mainSnap->getSize() > dv.size) {
+        setMemorySize(mainSnap->getSize());
+        dv = getDeviceMemoryView();
     }
     const size_t n = std::min(dv.size, mainSnap->getSize());
-    if (threadsBase == nullptr || threadsBase->getSize() != n || threadsBase->getDevice() != dv.device) {
-        threadsBase = std::make_shared<faabric::snapshot::DeviceSnapshot>(n, dv.device);
+    const bool baseFits = threadsBase != nullptr && threadsBase->getSize() == n && threadsBase->getDevice() == dv.device;
+    // After the first fork this host's memory and base equal the image as of
+    // their last synchronisation: only pages stamped since are copied
+    const bool incremental = incrementalDeviceThreads() && mainSnap->pageStamps() != nullptr && baseFits &&
+                             threadsSyncStamp != 0 && threadsSyncImageUid == mainSnap->uid() &&
+                             threadsSyncStamp >= mainSnap->fullMutationStamp();
+    const uint32_t forkStamp = mainSnap->currentForkStamp();
+    if (incremental) {
+        if (isMain) {
+            // the main thread's memory was just folded into the image
+            mainSnap->pullChangedPages(threadsBase->getDevicePtr(), nullptr, threadsSyncStamp, n, dv.device, stream);
+        } else {
+            mainSnap->pullChangedPages(dv.ptr, threadsBase->getDevicePtr(), threadsSyncStamp, n, dv.device, stream);
+        }
+    } else {
+        if (!isMain) {
+            mainSnap->restoreTo(dv.ptr, n, stream);
+        }
+        if (!baseFits) {
+            threadsBase = std::make_shared<faabric::snapshot::DeviceSnapshot>(n, dv.device);
+        }
+        cudaCheck(cudaMemcpyAsync(threadsBase->getDevicePtr(), dv.ptr, n, cudaMemcpyDeviceToDevice, stream), "thread base copy");
     }
-    cudaCheck(cudaMemcpyAsync(threadsBase->getDevicePtr(), dv.ptr, n, cudaMemcpyDeviceToDevice, stream), "thread base copy");
+    threadsSyncStamp = forkStamp;
+    threadsSyncImageUid = mainSnap->uid();
     threadsBase->clearMergeRegions();
     for (const auto& r : mainSnap->getMergeRegions()) {
         threadsBase->addMergeRegion(r.offset, r.length, r.dataType, r.operation);
@@ -458,7 +486,13 @@ uint64_t Executor::mergeDirtyRegionsOnDevice(const faabric::Message& msg)
     DeviceMemoryView dv = getDeviceMemoryView();
     GpuGuard g(dv.device);
     auto stream = (cudaStream_t)computeStream;
-    // scan + diff + typed merge + store into the (possibly remote) main image
+    // scan + diff + typed merge + store into the (possibly remote) main image;
+    // the pages changed there are stamped as "merged in this batch"
+    if (incrementalDeviceThreads() && threadsMain->pageStamps() != nullptr) {
+        threadsBase->setPushStamps(threadsMain->pageStamps(), threadsMain->currentForkStamp() + 1);
+    } else {
+        threadsBase->setPushStamps(nullptr, 0);
+    }
     threadsBase->diffAndPush(dv.ptr, dv.size, threadsMain->getDevicePtr(), nullptr, false, stream);
     auto stats = threadsBase->getLastStats(stream); // synchronises: the merge has landed
     deviceMergeCount.fetch_add(1);
@@ -594,12 +628,21 @@ std::vector<std::pair<uint32_t, int32_t>> Executor::executeThreads(
     if (!dv.empty()) {
         // ---- device-resident fork-join ----
         auto snap = getMainThreadDeviceSnapshot(msg, true);
+        const size_t nImage = std::min(dv.size, snap->getSize());
+        const bool incremental = incrementalDeviceThreads() && snap->pageStamps() != nullptr;
+        const uint32_t forkStamp = snap->beginFork();
         {
-            // The main thread is authoritative: bring the image up to date
+            // The main thread is authoritative: bring the image up to date.
+            // Incrementally: compare, copy the pages that differ and stamp them
+            // (two reads of the image's size, writes only where needed)
             GpuGuard g(dv.device);
             auto stream = (cudaStream_t)computeStream;
-            cudaCheck(cudaMemcpyAsync(snap->getDevicePtr(), dv.ptr, std::min(dv.size, snap->getSize()), cudaMemcpyDeviceToDevice, stream),
-                      "main image refresh");
+            if (incremental) {
+                snap->syncPagesFrom(dv.ptr, nImage, forkStamp, stream);
+            } else {
+                cudaCheck(cudaMemcpyAsync(snap->getDevicePtr(), dv.ptr, nImage, cudaMemcpyDeviceToDevice, stream), "main image refresh");
+                snap->markRewritten();
+            }
             cudaCheck(cudaStreamSynchronize(stream), "main image refresh sync");
         }
         snap->clearMergeRegions();
@@ -614,10 +657,22 @@ std::vector<std::pair<uint32_t, int32_t>> Executor::executeThreads(
         auto results = faabric::scheduler::getScheduler().awaitThreadResults(req);
         if (!decision.isSingleHost()) {
             // every host's merge kernel has completed before its result was
-            // published: the image now holds the merged state
+            // published: the image now holds the merged state.  Hosts served by
+            // another process cannot stamp the pages they merged
+            bool allHere = true;
+            for (const auto& h : decision.hosts) {
+                allHere = allHere && faabric::transport::MessageEndpointServer::localServerFor(h, FUNCTION_CALL_ASYNC_PORT, false) != nullptr;
+            }
             GpuGuard g(dv.device);
             auto stream = (cudaStream_t)computeStream;
-            snap->restoreTo(dv.ptr, std::min(dv.size, snap->getSize()), stream);
+            if (incremental && allHere) {
+                snap->pullChangedPages(dv.ptr, nullptr, forkStamp, nImage, dv.device, stream);
+            } else {
+                if (!allHere) {
+                    snap->markRewritten();
+                }
+                snap->restoreTo(dv.ptr, nImage, stream);
+            }
             cudaCheck(cudaStreamSynchronize(stream), "merged image restore");
         }
         return results;

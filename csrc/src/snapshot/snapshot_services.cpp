@@ -665,6 +665,8 @@ struct DeviceGuard
 };
 }
 
+static std::atomic<uint64_t> nextDeviceSnapshotUid{ 1 };
+
 DeviceSnapshot::DeviceSnapshot(size_t sizeIn, int deviceIn)
   : size(sizeIn)
   , device(deviceIn)
@@ -674,6 +676,11 @@ DeviceSnapshot::DeviceSnapshot(size_t sizeIn, int deviceIn)
     DeviceGuard g(device);
     DS_CUDA(cudaMemset(image, 0, size));
     statsDev = faabric::util::allocateDeviceMemory(64, device);
+    // one stamp per 4 KiB page
+    const size_t nPages = (size + 4095) / 4096;
+    stampsDev = faabric::util::allocateDeviceMemory(std::max<size_t>(1, nPages) * sizeof(uint32_t), device);
+    DS_CUDA(cudaMemset(stampsDev.ptr, 0, std::max<size_t>(1, nPages) * sizeof(uint32_t)));
+    uniqueId = nextDeviceSnapshotUid.fetch_add(1);
 }
 
 DeviceSnapshot::DeviceSnapshot(uint8_t* devicePtr, size_t sizeIn, int deviceIn)
@@ -682,6 +689,30 @@ DeviceSnapshot::DeviceSnapshot(uint8_t* devicePtr, size_t sizeIn, int deviceIn)
   , image(devicePtr)
 {
     statsDev = faabric::util::allocateDeviceMemory(64, device);
+    uniqueId = nextDeviceSnapshotUid.fetch_add(1);
+}
+
+uint32_t* DeviceSnapshot::pageStamps()
+{
+    return (uint32_t*)stampsDev.ptr;
+}
+
+uint32_t DeviceSnapshot::beginFork()
+{
+    return 2 * (forkCounter.fetch_add(1) + 1);
+}
+
+uint64_t* DeviceSnapshot::pageStatsOn(int onDevice)
+{
+    std::lock_guard<std::mutex> lk(mx);
+    auto it = pageStatsDev.find(onDevice);
+    if (it == pageStatsDev.end()) {
+        auto region = faabric::util::allocateDeviceMemory(64, onDevice);
+        DeviceGuard g(onDevice);
+        DS_CUDA(cudaMemset(region.ptr, 0, 64));
+        it = pageStatsDev.emplace(onDevice, std::move(region)).first;
+    }
+    return (uint64_t*)it->second.ptr;
 }
 
 DeviceSnapshot::~DeviceSnapshot()
@@ -745,6 +776,7 @@ void DeviceSnapshot::copyInData(std::span<const uint8_t> hostData, uint64_t offs
     }
     DeviceGuard g(device);
     DS_CUDA(cudaMemcpy(image + offset, hostData.data(), hostData.size(), cudaMemcpyHostToDevice));
+    noteFullMutation();
 }
 
 std::vector<uint8_t> DeviceSnapshot::getDataCopy(uint64_t offset, size_t n)
@@ -915,9 +947,49 @@ void DeviceSnapshot::diffAndPush(const uint8_t* mem,
     a.dirtyPages = dirtyPagesDev;
     a.stats = (uint64_t*)statsDev.ptr;
     a.updateBase = updateBase ? 1 : 0;
+    if (pushStamps != nullptr && mainImage != nullptr) {
+        ensurePeerAccessTo(device, pushStamps);
+        a.pageStampOut = pushStamps;
+        a.pageStamp = pushStamp;
+    }
     DS_CUDA(fb::launchSnapshotDiffPush(a, 296, (cudaStream_t)stream));
     diffPushCount++;
     globalDiffPushCount.fetch_add(1);
+}
+
+void DeviceSnapshot::syncPagesFrom(const uint8_t* mem, size_t n, uint32_t stamp, void* stream)
+{
+    if (n > size) {
+        throw std::runtime_error("Source memory larger than device snapshot");
+    }
+    DeviceGuard g(device);
+    ensurePeerAccessTo(device, mem);
+    DS_CUDA(fb::launchPageSync(mem, image, pageStamps(), stamp, n, pageStatsOn(device), 296, (cudaStream_t)stream));
+}
+
+void DeviceSnapshot::pullChangedPages(uint8_t* dst1, uint8_t* dst2, uint32_t since, size_t n, int onDevice, void* stream)
+{
+    if (n > size) {
+        throw std::runtime_error("Target memory larger than device snapshot");
+    }
+    if (pageStamps() == nullptr) {
+        throw std::runtime_error("This device snapshot keeps no page stamps");
+    }
+    DeviceGuard g(onDevice);
+    ensurePeerAccessTo(onDevice, image);
+    ensurePeerAccessTo(onDevice, pageStamps());
+    DS_CUDA(fb::launchPagePull(image, dst1, dst2, pageStamps(), since, n, pageStatsOn(onDevice), 296, (cudaStream_t)stream));
+}
+
+uint64_t DeviceSnapshot::takePageCopyCount(int onDevice, void* stream)
+{
+    uint64_t* dev = pageStatsOn(onDevice);
+    uint64_t host = 0;
+    DeviceGuard g(onDevice);
+    DS_CUDA(cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DS_CUDA(cudaMemsetAsync(dev, 0, sizeof(host), (cudaStream_t)stream));
+    DS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return host;
 }
 
 DeviceDiffStats DeviceSnapshot::getLastStats(void* stream)
@@ -934,6 +1006,7 @@ void DeviceSnapshot::applyDiffs(const std::vector<SnapshotDiff>& diffs, void* st
     if (diffs.empty()) {
         return;
     }
+    noteFullMutation();
     // The kernel applies the descriptors of one launch concurrently, the
     // reference applies a diff list in order (SnapshotData::applyDiffs).  Diffs
     // that touch the same bytes (several Sum diffs onto one scalar, a Bytewise

@@ -242,6 +242,106 @@ TEST_CASE("threads on device memory: restore is a device copy, the merge one fus
     f.awaitBatch(req);
 }
 
+TEST_CASE("threads on device memory: later fork-joins move only the pages stamped since the last one", "[gpu][threads]")
+{
+    if (!faabric::device::cudaAvailable()) {
+        SKIP_TEST("no CUDA device");
+    }
+    ClusterFixture f(0, 2, 2);
+    faabric::executor::setExecutorFactory(std::make_shared<DeviceTestFactory>());
+    const int nThreads = 3;
+    const int nRounds = 4;
+    std::atomic<int> staleReads{ 0 };
+    std::atomic<int> remoteThreads{ 0 };
+    registerTestFunction("demo", "devrounds", [&](auto* exec, int, int idx, auto req) {
+        auto& m = *req->mutable_messages(idx);
+        auto dv = exec->getDeviceMemoryView();
+        if (dv.empty()) {
+            return 9;
+        }
+        cudaSetDevice(dv.device);
+        if (req->type() == faabric::BatchExecuteRequest::THREADS) {
+            int t = m.appidx();
+            int round = atoi(m.inputdata().c_str());
+            if (m.executedhost() != m.mainhost()) {
+                remoteThreads++;
+            }
+            // what the main thread wrote just before this fork must be here,
+            // and so must what the OTHER hosts merged in the previous round
+            if (devRead<uint32_t>(dv.ptr + 4096 * 20) != (uint32_t)(round + 1) * 1000u) {
+                staleReads++;
+            }
+            if (round > 0) {
+                for (int o = 1; o <= nThreads; o++) {
+                    // (a thread sharing this host's memory may already have
+                    // written this round's value)
+                    uint32_t v = devRead<uint32_t>(dv.ptr + 4096 * (10 + o));
+                    if (v != (uint32_t)(round * 1000 + o) && v != (uint32_t)((round + 1) * 1000 + o)) {
+                        staleReads++;
+                    }
+                }
+            }
+            devWrite<uint8_t>(dv.ptr + 1024 + t, (uint8_t)(round * 16 + t));
+            devWrite<uint32_t>(dv.ptr + 4096 * (10 + t), (uint32_t)((round + 1) * 1000 + t));
+            static std::mutex sumMx;
+            std::lock_guard<std::mutex> lk(sumMx);
+            devWrite<int>(dv.ptr + 64, devRead<int>(dv.ptr + 64) + t + 1);
+            return t;
+        }
+        devWrite<int>(dv.ptr + 64, 100);
+        std::vector<faabric::util::SnapshotMergeRegion> regions = {
+            { 64, sizeof(int), SnapshotDataType::Int, SnapshotMergeOperation::Sum }
+        };
+        for (int round = 0; round < nRounds; round++) {
+            // the main thread changes one page between joins
+            devWrite<uint32_t>(dv.ptr + 4096 * 20, (uint32_t)(round + 1) * 1000u);
+            auto threads = faabric::util::batchExecFactory("demo", "devrounds", nThreads);
+            faabric::util::updateBatchExecAppId(threads, m.appid());
+            for (int i = 0; i < nThreads; i++) {
+                threads->mutable_messages(i)->set_appidx(i + 1);
+                threads->mutable_messages(i)->set_groupidx(i + 1);
+                threads->mutable_messages(i)->set_inputdata(std::to_string(round));
+            }
+            auto results = exec->executeThreads(threads, regions);
+            if ((int)results.size() != nThreads) {
+                return 1;
+            }
+            // the Sum word accumulates over the rounds, the private bytes and
+            // far pages hold this round's values
+            if (devRead<int>(dv.ptr + 64) != 100 + (round + 1) * 9) {
+                return 2;
+            }
+            for (int t = 1; t <= nThreads; t++) {
+                if (devRead<uint8_t>(dv.ptr + 1024 + t) != (uint8_t)(round * 16 + t) ||
+                    devRead<uint32_t>(dv.ptr + 4096 * (10 + t)) != (uint32_t)((round + 1) * 1000 + t)) {
+                    return 3;
+                }
+            }
+        }
+        m.set_outputdata(std::to_string(devRead<int>(dv.ptr + 64)));
+        return 0;
+    });
+    auto req = faabric::util::batchExecFactory("demo", "devrounds", 1);
+    f.plannerCli.callFunctions(req);
+    auto res = f.awaitResult(req->messages(0), 60000);
+    REQUIRE_EQ(res.returnvalue(), 0);
+    REQUIRE_EQ(res.outputdata(), std::to_string(100 + nRounds * 9));
+    REQUIRE_EQ(staleReads.load(), 0);
+    REQUIRE_EQ(remoteThreads.load(), 2 * nRounds);
+    // after the first fork the image keeps page stamps that moved on with every fork and join
+    std::string key = faabric::util::getMainThreadSnapshotKey(req->messages(0));
+    auto snap = faabric::snapshot::getSnapshotRegistry().getDeviceSnapshot(key);
+    REQUIRE(snap->pageStamps() != nullptr);
+    REQUIRE_EQ(snap->currentForkStamp(), (uint32_t)(2 * nRounds));
+    std::vector<uint32_t> stamps(32);
+    cudaMemcpy(stamps.data(), snap->pageStamps(), stamps.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    REQUIRE_EQ(stamps[20], (uint32_t)(2 * nRounds));         // the main thread's page: last fork
+    REQUIRE_EQ(stamps[11], (uint32_t)(2 * nRounds + 1));     // a thread's page: last join
+    REQUIRE_EQ(stamps[0], (uint32_t)(2 * nRounds + 1));      // the Sum word and the private bytes
+    REQUIRE_EQ(stamps[5], 0u);                               // never touched
+    f.awaitBatch(req);
+}
+
 // Child side of the test below (run as `faabric_tests --ipc-map-child <hex> <size>`):
 // maps the parent's image through the descriptor, checks a byte, leaves a mark
 int ipcMapChildMain(const char* hexHandle, const char* sizeStr)
