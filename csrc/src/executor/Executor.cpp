@@ -101,8 +101,14 @@ Executor::Executor(faabric::Message& msg)
   , threadPoolThreads(threadPoolSize)
   , threadTaskQueues(threadPoolSize)
 {
+    // FAABRIC_EXECUTOR_DEQUEUE_SPIN=0: idle pool threads sleep at once instead
+    // of looking for their next task for ~20 us first
+    static const bool dequeueSpin = []() {
+        const char* v = getenv("FAABRIC_EXECUTOR_DEQUEUE_SPIN");
+        return v == nullptr || std::string(v) != "0";
+    }();
     for (auto& q : threadTaskQueues) {
-        q.setSpinBeforeSleep(false);
+        q.setSpinBeforeSleep(dequeueSpin);
     }
     faabric::util::SystemConfig& conf = faabric::util::getSystemConfig();
     // Unique id: host, function, counter
