@@ -2,7 +2,7 @@
 # Final 1-GPU pass: the driver's own commands
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-echo "== python -m pytest tests/ -q -m gpu"; timeout 330 python -m pytest tests/ -q -m gpu > gpurun_out/final_pytest_gpu.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/final_pytest_gpu.log | cut -c1-300
+echo "== python -m pytest tests/ -q -m gpu"; timeout 400 python -m pytest tests/ -q -m gpu > gpurun_out/final_pytest_gpu.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/final_pytest_gpu.log | cut -c1-300
 echo "== smoke()"; timeout 90 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
 echo "== bench.py (default flags)"; timeout 200 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "rc=$?"; cut -c1-2400 gpurun_out/final_bench.json; tail -2 gpurun_out/final_bench.err
 echo "== bench.py --impl reference"; timeout 60 python bench.py --impl reference 2>/dev/null | tail -1 | cut -c1-300
