@@ -34,6 +34,8 @@ FAMILIES = {
     "chunkRunsKernel": r"chunkRunsKernel",
     "flagsOrKernel": r"flagsOrKernel",
     "statePushDirtyKernel": r"statePushDirtyKernel",
+    "pageSyncKernel": r"pageSyncKernel",
+    "pagePullKernel": r"pagePullKernel",
 }
 INTERESTING = re.compile(
     r"\b(LDG|STG|REDG|ATOMG|LDGMC|UBLKCP|UTMALDG|UTMASTG|SYNCS|MEMBAR|CCTL|ERRBAR|BAR|LDS|STS|LDGSTS|UTC\w*|LDTM|STTM|S2UR|CS2R|MATCH|VOTE)\b[\.\w]*"
