@@ -12,7 +12,7 @@ next to it against NVLink.  Device-timed with CUDA events, max over ranks.
 Other modes (each prints one JSON line and appends to --out):
   sweep     MpiWorld allreduce bus GB/s 1 KB..1 GB, ours (per algo) vs NCCL
   alltoall  all-to-all bus GB/s 1 KB..64 MB per rank, ours vs NCCL
-  snapshot  1 GB region diff+push at 1..50 % dirty (MB/s), vs CPU oracle rate
+  snapshot  1 GB region diff+push at 1..50 % dirty (MB/s), vs CPU oracle rate; plus the runtime-level fork-join
   planner   1024-function fan-out / fan-in through the native planner (us)
   threads   THREADS fork-join of a 1 GiB device function memory through the runtime (ms)
   pingpong  MPI ping-pong RTT, 2 ranks in one worker and in two (CPU)
@@ -48,6 +48,7 @@ def parse():
                     help="tuned = measure the algorithm policies in place and keep the fastest (allreduce mode)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--channels", type=int, default=8, help="lanes of --sync-mode lanes")
+    ap.add_argument("--no-runtime-arm", action="store_true", help="snapshot mode: skip the THREADS fork-join through the runtime")
     ap.add_argument("--no-mpi-api", action="store_true", help="skip the MPI C-API arm reported under 'mpi_api'")
     ap.add_argument("--sync-mode", default="grouped", choices=["grouped", "lanes"],
                     help="grouped = ONE fused kernel per step over all 214 tensors; lanes = one kernel per tensor")
@@ -641,6 +642,17 @@ def mode_snapshot(args, dist: Dist):
         "cpu_oracle": cpu,
         "note": "every rank pushes into rank 0's image over NVLink (rank 0 pushes locally)",
     }
+    # The same kernels where the runtime uses them: a THREADS fork-join through planner, scheduler,
+    # DeviceExecutor and SnapshotRegistry (one thread per virtual GPU host, 1 GiB function memory)
+    if dist.rank == 0 and not args.no_runtime_arm:
+        try:
+            from faabric_b200.runtime import threads_forkjoin_bench
+
+            fj = threads_forkjoin_bench("device", hosts=max(n, 2), iters=10, warmup=3)
+            out["runtime_forkjoin"] = {k: fj.get(k) for k in ("hosts", "gpus", "mem_bytes", "dirty_pct", "ms_median", "ms_min",
+                                                                "diff_push_kernels", "verified")}
+        except Exception as e:  # the kernel rows never depend on this arm
+            out["runtime_forkjoin"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     return out, {"_keep": (comm, group, main_img)}
 
 
