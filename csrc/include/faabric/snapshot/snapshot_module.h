@@ -127,6 +127,18 @@ class DeviceSnapshot
     // GPU dirty-page detection of `mem` against this image
     std::vector<char> getDirtyPages(const uint8_t* mem, size_t memSize);
 
+    // ---- delta codec on device images (util/delta.h command stream) ----
+    // Delta that turns this image into `mem` (device memory on this image's
+    // GPU, memSize <= size): the page compare and the XOR run on the GPU, only
+    // the changed pages cross PCIe.  Byte-identical to
+    // faabric::util::serializeDelta on host copies of the two buffers.
+    // Settings without 4 KiB pages go through host copies.
+    std::vector<uint8_t> serializeDelta(const faabric::util::DeltaSettings& cfg, const uint8_t* mem, size_t memSize);
+
+    // Applies a delta to this image in place (XOR / overwrite runs become one
+    // batch of device diffs)
+    void applyDelta(const std::vector<uint8_t>& delta, void* stream = nullptr);
+
     // ---- control-plane descriptor (cross-process mapping through CUDA IPC) ----
     DeviceSnapshotDescriptor describe();
 

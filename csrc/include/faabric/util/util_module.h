@@ -778,6 +778,23 @@ void applyDelta(const std::vector<uint8_t>& delta,
 // True if libzstd could be loaded at runtime
 bool deltaZstdAvailable();
 
+// ---- building blocks (used by DeviceSnapshot::serializeDelta / applyDelta,
+// where the page compare and the XOR run on the GPU) ----
+// A command stream under construction: TOTAL_SIZE first, then runs, then END
+void deltaBegin(std::vector<uint8_t>& cmds, uint32_t totalSize);
+
+// One run whose payload (`length` bytes: new bytes, or new ^ old when isXor)
+// has already been computed
+void deltaAppendRun(std::vector<uint8_t>& cmds, bool isXor, uint32_t offset, const uint8_t* payload, uint32_t length);
+
+// Appends END and applies the zstd wrapper the settings ask for
+std::vector<uint8_t> deltaFinish(const DeltaSettings& cfg, std::vector<uint8_t>&& cmds);
+
+// Walks a (possibly compressed) delta: onSize(total) and onRun(isXor, offset, payload, length)
+void deltaForEach(const std::vector<uint8_t>& delta,
+                  const std::function<void(uint32_t)>& onSize,
+                  const std::function<void(bool, uint32_t, const uint8_t*, uint32_t)>& onRun);
+
 }
 
 // ==========================================================================

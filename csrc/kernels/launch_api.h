@@ -281,6 +281,17 @@ cudaError_t launchPagePull(const uint8_t* src,
                            uint64_t* stats,
                            int blocks,
                            cudaStream_t s);
+// Delta encoding of a device image: gathers the listed 4 KiB pages into a
+// compact buffer, as new bytes (xorMode 0) or as new ^ old (xorMode 1)
+cudaError_t launchPageGather(const uint8_t* oldImg,
+                             const uint8_t* newMem,
+                             const uint32_t* pages,
+                             uint32_t nListed,
+                             uint64_t size,
+                             int xorMode,
+                             uint8_t* out,
+                             int blocks,
+                             cudaStream_t s);
 cudaError_t launchDirtyScan(const uint8_t* mem,
                             const uint8_t* base,
                             uint64_t size,

@@ -720,6 +720,61 @@ __global__ void __launch_bounds__(512, 2) pagePullKernel(const uint8_t* src,
     }
 }
 
+// out[k] = page pages[k] of newMem, XORed with the same page of oldImg when
+// xorMode: what the delta codec (util/delta.h) sends for a changed page
+__global__ void __launch_bounds__(512, 2) pageGatherKernel(const uint8_t* oldImg,
+                                                           const uint8_t* newMem,
+                                                           const uint32_t* pages,
+                                                           uint32_t nListed,
+                                                           uint64_t size,
+                                                           int xorMode,
+                                                           uint8_t* out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warpId = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nWarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t k = warpId; k < nListed; k += nWarps) {
+        const uint64_t pBeg = (uint64_t)pages[k] * PAGE;
+        if (pBeg >= size) {
+            continue;
+        }
+        const uint64_t nBytes = min((uint64_t)PAGE, size - pBeg);
+        const uint64_t nVec = nBytes >> 4;
+        const uint4* n4 = reinterpret_cast<const uint4*>(newMem + pBeg);
+        const uint4* o4 = reinterpret_cast<const uint4*>(oldImg + pBeg);
+        uint4* d4 = reinterpret_cast<uint4*>(out + k * PAGE);
+        for (uint64_t i = lane; i < nVec; i += 32) {
+            uint4 v = n4[i];
+            if (xorMode) {
+                uint4 o = o4[i];
+                v.x ^= o.x;
+                v.y ^= o.y;
+                v.z ^= o.z;
+                v.w ^= o.w;
+            }
+            d4[i] = v;
+        }
+        for (uint64_t p = (nVec << 4) + lane; p < nBytes; p += 32) {
+            uint8_t b = newMem[pBeg + p];
+            out[k * PAGE + p] = xorMode ? (uint8_t)(b ^ oldImg[pBeg + p]) : b;
+        }
+    }
+}
+
+cudaError_t launchPageGather(const uint8_t* oldImg,
+                             const uint8_t* newMem,
+                             const uint32_t* pages,
+                             uint32_t nListed,
+                             uint64_t size,
+                             int xorMode,
+                             uint8_t* out,
+                             int blocks,
+                             cudaStream_t s)
+{
+    pageGatherKernel<<<blocks, 512, 0, s>>>(oldImg, newMem, pages, nListed, size, xorMode, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launchPageSync(const uint8_t* src,
                            uint8_t* dst,
                            uint32_t* pageStamps,

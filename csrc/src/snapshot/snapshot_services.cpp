@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <deque>
 #include <map>
 #include <atomic>
 #include <cstring>
@@ -955,6 +956,80 @@ void DeviceSnapshot::diffAndPush(const uint8_t* mem,
     DS_CUDA(fb::launchSnapshotDiffPush(a, 296, (cudaStream_t)stream));
     diffPushCount++;
     globalDiffPushCount.fetch_add(1);
+}
+
+std::vector<uint8_t> DeviceSnapshot::serializeDelta(const faabric::util::DeltaSettings& cfg, const uint8_t* mem, size_t memSize)
+{
+    if (memSize > size || memSize > UINT32_MAX) {
+        throw std::runtime_error("Delta of a device image: new data must fit the image (and 4 GiB)");
+    }
+    if (!cfg.usePages || cfg.pageSize != 4096) {
+        // not the device's granularity: encode from host copies
+        std::vector<uint8_t> oldHost = getDataCopy(0, memSize);
+        std::vector<uint8_t> newHost(memSize);
+        DeviceGuard g(device);
+        DS_CUDA(cudaMemcpy(newHost.data(), mem, memSize, cudaMemcpyDeviceToHost));
+        return faabric::util::serializeDelta(cfg, oldHost.data(), oldHost.size(), newHost.data(), newHost.size());
+    }
+    // 1. which pages changed (compare kernel, one flag per page back to the host)
+    std::vector<char> dirty = getDirtyPages(mem, memSize);
+    std::vector<uint32_t> pages;
+    for (size_t p = 0; p < dirty.size(); p++) {
+        if (dirty[p]) {
+            pages.push_back((uint32_t)p);
+        }
+    }
+    std::vector<uint8_t> cmds;
+    faabric::util::deltaBegin(cmds, (uint32_t)memSize);
+    if (!pages.empty()) {
+        // 2. gather them (as new ^ old when the settings say so) into a compact buffer
+        DeviceGuard g(device);
+        auto listDev = faabric::util::allocateDeviceMemory(pages.size() * sizeof(uint32_t), device);
+        auto outDev = faabric::util::allocateDeviceMemory(pages.size() * 4096, device);
+        DS_CUDA(cudaMemcpy(listDev.ptr, pages.data(), pages.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        DS_CUDA(fb::launchPageGather(
+          image, mem, (const uint32_t*)listDev.ptr, (uint32_t)pages.size(), memSize, cfg.xorWithOld ? 1 : 0, outDev.ptr, 296, nullptr));
+        std::vector<uint8_t> compact(pages.size() * 4096);
+        DS_CUDA(cudaMemcpy(compact.data(), outDev.ptr, compact.size(), cudaMemcpyDeviceToHost));
+        // 3. runs of consecutive pages become one command each
+        size_t k = 0;
+        while (k < pages.size()) {
+            size_t e = k + 1;
+            while (e < pages.size() && pages[e] == pages[e - 1] + 1) {
+                e++;
+            }
+            const uint64_t off = (uint64_t)pages[k] * 4096;
+            const uint64_t len = std::min<uint64_t>((uint64_t)(e - k) * 4096, memSize - off);
+            faabric::util::deltaAppendRun(cmds, cfg.xorWithOld, (uint32_t)off, compact.data() + k * 4096, (uint32_t)len);
+            k = e;
+        }
+    }
+    return faabric::util::deltaFinish(cfg, std::move(cmds));
+}
+
+void DeviceSnapshot::applyDelta(const std::vector<uint8_t>& delta, void* stream)
+{
+    std::vector<SnapshotDiff> diffs;
+    // (payloads of a compressed delta only live inside the walk: keep copies)
+    std::deque<std::vector<uint8_t>> payloads;
+    faabric::util::deltaForEach(
+      delta,
+      [&](uint32_t total) {
+          if (total > size) {
+              throw std::runtime_error("Delta is larger than the device image");
+          }
+      },
+      [&](bool isXor, uint32_t offset, const uint8_t* payload, uint32_t length) {
+          if ((uint64_t)offset + length > size) {
+              throw std::runtime_error("Delta run beyond the end of the device image");
+          }
+          payloads.emplace_back(payload, payload + length);
+          diffs.emplace_back(SnapshotDataType::Raw,
+                             isXor ? SnapshotMergeOperation::XOR : SnapshotMergeOperation::Bytewise,
+                             offset,
+                             std::span<const uint8_t>(payloads.back().data(), length));
+      });
+    applyDiffs(diffs, stream);
 }
 
 void DeviceSnapshot::syncPagesFrom(const uint8_t* mem, size_t n, uint32_t stamp, void* stream)

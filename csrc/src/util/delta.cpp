@@ -172,6 +172,29 @@ std::vector<uint8_t> serializeDelta(const DeltaSettings& cfg,
     } else {
         emit(0, newDataLen);
     }
+    return deltaFinish(cfg, std::move(cmds));
+}
+
+void deltaBegin(std::vector<uint8_t>& cmds, uint32_t totalSize)
+{
+    cmds.push_back(DELTACMD_TOTAL_SIZE);
+    put<uint32_t>(cmds, totalSize);
+}
+
+void deltaAppendRun(std::vector<uint8_t>& cmds, bool isXor, uint32_t offset, const uint8_t* payload, uint32_t length)
+{
+    if (length == 0) {
+        return;
+    }
+    cmds.push_back(isXor ? DELTACMD_DELTA_XOR : DELTACMD_DELTA_OVERWRITE);
+    put<uint32_t>(cmds, offset);
+    put<uint32_t>(cmds, length);
+    cmds.insert(cmds.end(), payload, payload + length);
+}
+
+std::vector<uint8_t> deltaFinish(const DeltaSettings& cfg, std::vector<uint8_t>&& cmdsIn)
+{
+    std::vector<uint8_t> cmds = std::move(cmdsIn);
     cmds.push_back(DELTACMD_END);
 
     if (!cfg.useZstd || !zstd().ok) {
@@ -196,16 +219,16 @@ std::vector<uint8_t> serializeDelta(const DeltaSettings& cfg,
     return out;
 }
 
-void applyDelta(const std::vector<uint8_t>& delta,
-                std::function<void(uint32_t)> setDataSize,
-                std::function<uint8_t*()> getDataPointer)
+void deltaForEach(const std::vector<uint8_t>& delta,
+                  const std::function<void(uint32_t)>& onSize,
+                  const std::function<void(bool, uint32_t, const uint8_t*, uint32_t)>& onRun)
 {
     size_t pos = 0;
     while (pos < delta.size()) {
         uint8_t cmd = delta[pos++];
         switch (cmd) {
             case DELTACMD_TOTAL_SIZE: {
-                setDataSize(get<uint32_t>(delta, pos));
+                onSize(get<uint32_t>(delta, pos));
                 break;
             }
             case DELTACMD_ZSTD_COMPRESSED_COMMANDS: {
@@ -224,29 +247,17 @@ void applyDelta(const std::vector<uint8_t>& delta,
                     throw std::runtime_error("zstd decompression failed");
                 }
                 pos += compLen;
-                applyDelta(inner, setDataSize, getDataPointer);
+                deltaForEach(inner, onSize, onRun);
                 break;
             }
-            case DELTACMD_DELTA_OVERWRITE: {
-                uint32_t offset = get<uint32_t>(delta, pos);
-                uint32_t length = get<uint32_t>(delta, pos);
-                if (pos + length > delta.size()) {
-                    throw std::runtime_error("Delta stream truncated");
-                }
-                memcpy(getDataPointer() + offset, delta.data() + pos, length);
-                pos += length;
-                break;
-            }
+            case DELTACMD_DELTA_OVERWRITE:
             case DELTACMD_DELTA_XOR: {
                 uint32_t offset = get<uint32_t>(delta, pos);
                 uint32_t length = get<uint32_t>(delta, pos);
                 if (pos + length > delta.size()) {
                     throw std::runtime_error("Delta stream truncated");
                 }
-                uint8_t* dst = getDataPointer() + offset;
-                for (uint32_t i = 0; i < length; i++) {
-                    dst[i] ^= delta[pos + i];
-                }
+                onRun(cmd == DELTACMD_DELTA_XOR, offset, delta.data() + pos, length);
                 pos += length;
                 break;
             }
@@ -256,6 +267,25 @@ void applyDelta(const std::vector<uint8_t>& delta,
                 throw std::runtime_error("Invalid delta command");
         }
     }
+}
+
+void applyDelta(const std::vector<uint8_t>& delta,
+                std::function<void(uint32_t)> setDataSize,
+                std::function<uint8_t*()> getDataPointer)
+{
+    deltaForEach(
+      delta,
+      [&](uint32_t total) { setDataSize(total); },
+      [&](bool isXor, uint32_t offset, const uint8_t* payload, uint32_t length) {
+          uint8_t* dst = getDataPointer() + offset;
+          if (isXor) {
+              for (uint32_t i = 0; i < length; i++) {
+                  dst[i] ^= payload[i];
+              }
+          } else {
+              memcpy(dst, payload, length);
+          }
+      });
 }
 
 } // namespace faabric::util

@@ -463,3 +463,61 @@ TEST_CASE("device snapshot: overlapping diffs are applied in order, like the hos
     REQUIRE_EQ((int)got[1000], 0xee);
     REQUIRE_EQ((int)got[1040], 0x22);
 }
+
+TEST_CASE("device snapshot: delta encoding on the GPU is byte-identical to the host codec and applies in place", "[gpu][snapshot][delta]")
+{
+    if (!faabric::device::cudaAvailable()) {
+        SKIP_TEST("no CUDA device");
+    }
+    const size_t size = 64 * 4096 + 100; // a ragged last page
+    std::vector<uint8_t> oldHost(size), newHost;
+    for (size_t i = 0; i < size; i++) {
+        oldHost[i] = (uint8_t)(i * 7 + 3);
+    }
+    newHost = oldHost;
+    // a lone page, a run of three pages, single bytes at page edges, the ragged tail
+    for (size_t i = 5 * 4096 + 10; i < 5 * 4096 + 900; i++) {
+        newHost[i] ^= 0x5a;
+    }
+    for (size_t i = 20 * 4096; i < 23 * 4096; i++) {
+        newHost[i] = (uint8_t)(i % 251);
+    }
+    newHost[30 * 4096] ^= 1;
+    newHost[31 * 4096 - 1] ^= 2;
+    newHost[size - 1] ^= 0x80;
+
+    faabric::snapshot::DeviceSnapshot image(size, 0);
+    image.copyInData(oldHost, 0);
+    uint8_t* mem = nullptr;
+    cudaSetDevice(0);
+    REQUIRE(cudaMalloc(&mem, size) == cudaSuccess);
+    cudaMemcpy(mem, newHost.data(), size, cudaMemcpyHostToDevice);
+
+    for (const char* def : { "pages=4096;xor;", "pages=4096;", "pages=4096;xor;zstd=1;", "xor;" }) {
+        faabric::util::DeltaSettings cfg(def);
+        if (cfg.useZstd && !faabric::util::deltaZstdAvailable()) {
+            continue;
+        }
+        std::vector<uint8_t> onDevice = image.serializeDelta(cfg, mem, size);
+        std::vector<uint8_t> onHost = faabric::util::serializeDelta(cfg, oldHost.data(), size, newHost.data(), size);
+        REQUIRE(onDevice == onHost);
+        if (cfg.usePages && !cfg.useZstd) {
+            // only the changed pages travel: 1 + 3 + 2 + 1 pages and a few headers
+            REQUIRE(onDevice.size() < 8 * 4096);
+        }
+        // applying it to another copy of the old image gives the new bytes
+        faabric::snapshot::DeviceSnapshot other(size, 0);
+        other.copyInData(oldHost, 0);
+        other.applyDelta(onDevice);
+        REQUIRE(other.getDataCopy() == newHost);
+    }
+    // an unchanged image encodes to just the header and the end marker
+    faabric::util::DeltaSettings plain("pages=4096;xor;");
+    cudaMemcpy(mem, oldHost.data(), size, cudaMemcpyHostToDevice);
+    REQUIRE_EQ(image.serializeDelta(plain, mem, size).size(), 6u);
+    // a shorter new buffer is a valid target, a longer one is not
+    REQUIRE(image.serializeDelta(plain, mem, size - 4096) ==
+            faabric::util::serializeDelta(plain, oldHost.data(), size, oldHost.data(), size - 4096));
+    REQUIRE_THROWS(image.serializeDelta(plain, mem, size + 1));
+    cudaFree(mem);
+}

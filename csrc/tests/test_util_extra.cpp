@@ -615,3 +615,50 @@ TEST_CASE("cpu pinning: claims are exclusive, released and exhaustible", "[util]
     bindThreadToGpu(-1);
     bindThreadToGpu(0);
 }
+
+TEST_CASE("delta: the building blocks produce and walk the same stream as the one-shot codec", "[util][delta]")
+{
+    std::vector<uint8_t> oldData(3 * 4096, 7), newData(3 * 4096, 7);
+    for (int i = 4096; i < 4096 + 64; i++) {
+        newData[i] = (uint8_t)i;
+    }
+    for (const char* def : { "pages=4096;xor;", "pages=4096;", "pages=4096;xor;zstd=1;" }) {
+        faabric::util::DeltaSettings cfg(def);
+        if (cfg.useZstd && !faabric::util::deltaZstdAvailable()) {
+            continue;
+        }
+        auto whole = faabric::util::serializeDelta(cfg, oldData.data(), oldData.size(), newData.data(), newData.size());
+        // by hand: one run covering the changed page
+        std::vector<uint8_t> payload(newData.begin() + 4096, newData.begin() + 8192);
+        if (cfg.xorWithOld) {
+            for (size_t i = 0; i < payload.size(); i++) {
+                payload[i] ^= oldData[4096 + i];
+            }
+        }
+        std::vector<uint8_t> cmds;
+        faabric::util::deltaBegin(cmds, (uint32_t)newData.size());
+        faabric::util::deltaAppendRun(cmds, cfg.xorWithOld, 4096, payload.data(), (uint32_t)payload.size());
+        faabric::util::deltaAppendRun(cmds, cfg.xorWithOld, 0, payload.data(), 0); // empty runs are dropped
+        REQUIRE(faabric::util::deltaFinish(cfg, std::move(cmds)) == whole);
+        // walking it reports the size and exactly that run
+        uint32_t total = 0;
+        int runs = 0;
+        faabric::util::deltaForEach(
+          whole,
+          [&](uint32_t t) { total = t; },
+          [&](bool isXor, uint32_t offset, const uint8_t* p, uint32_t length) {
+              runs++;
+              REQUIRE_EQ(isXor, cfg.xorWithOld);
+              REQUIRE_EQ(offset, 4096u);
+              REQUIRE_EQ(length, 4096u);
+              REQUIRE(memcmp(p, payload.data(), length) == 0);
+          });
+        REQUIRE_EQ(total, (uint32_t)newData.size());
+        REQUIRE_EQ(runs, 1);
+    }
+    // truncated and unknown commands are refused
+    std::vector<uint8_t> bad = { faabric::util::DELTACMD_DELTA_XOR, 0, 0, 0, 0, 9, 0, 0, 0, 1 };
+    REQUIRE_THROWS(faabric::util::deltaForEach(bad, [](uint32_t) {}, [](bool, uint32_t, const uint8_t*, uint32_t) {}));
+    std::vector<uint8_t> unknown = { 0x77 };
+    REQUIRE_THROWS(faabric::util::deltaForEach(unknown, [](uint32_t) {}, [](bool, uint32_t, const uint8_t*, uint32_t) {}));
+}
