@@ -36,6 +36,7 @@ FAMILIES = {
     "statePushDirtyKernel": r"statePushDirtyKernel",
     "pageSyncKernel": r"pageSyncKernel",
     "pagePullKernel": r"pagePullKernel",
+    "pageGatherKernel": r"pageGatherKernel",
 }
 INTERESTING = re.compile(
     r"\b(LDG|STG|REDG|ATOMG|LDGMC|UBLKCP|UTMALDG|UTMASTG|SYNCS|MEMBAR|CCTL|ERRBAR|BAR|LDS|STS|LDGSTS|UTC\w*|LDTM|STTM|S2UR|CS2R|MATCH|VOTE)\b[\.\w]*"
