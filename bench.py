@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--channels", type=int, default=8, help="lanes of --sync-mode lanes")
     ap.add_argument("--no-runtime-arm", action="store_true", help="snapshot mode: skip the THREADS fork-join through the runtime")
+    ap.add_argument("--bind-numa", default="auto", choices=["auto", "on", "off"],
+                    help="e2e: restrict the process to the CPUs of the GPU's NUMA node before allocating the pinned buffers (auto: multi-GPU runs only)")
     ap.add_argument("--no-mpi-api", action="store_true", help="skip the MPI C-API arm reported under 'mpi_api'")
     ap.add_argument("--sync-mode", default="grouped", choices=["grouped", "lanes"],
                     help="grouped = ONE fused kernel per step over all 214 tensors; lanes = one kernel per tensor")
@@ -330,7 +332,7 @@ def mode_allreduce(args, dist: Dist):
         # ---- end to end through the public API:
         # pinned host -> H2D -> all-reduce -> D2H of the FULL result into pinned host memory
         from faabric_b200.utils import bind_process_near_gpu
-        numa_cpus = bind_process_near_gpu(dist.local) if dist.multi else []
+        numa_cpus = bind_process_near_gpu(dist.local) if (args.bind_numa == "on" or (args.bind_numa == "auto" and dist.multi)) else []
         host = torch.empty(sync.total_padded, dtype=torch.int32).pin_memory()
         host.copy_((torch.arange(sync.total_padded, dtype=torch.int32) % 1000) + dist.rank)
         out_host = torch.empty(sync.total_padded, dtype=torch.int32).pin_memory()

@@ -135,6 +135,13 @@ std::vector<MpiMessage> getMpiMockedMessages(int sendRank)
 void clearMpiMockedMessages()
 {
     std::lock_guard<std::mutex> lk(mockMx);
+    // the captured copies own their payloads
+    for (auto& [rank, msgs] : mockedMessages) {
+        for (auto& m : msgs) {
+            free(m.buffer);
+            m.buffer = nullptr;
+        }
+    }
     mockedMessages.clear();
 }
 
