@@ -351,10 +351,14 @@ void Redis::enqueueBytes(const std::string& queueName, const uint8_t* buffer, si
 std::vector<uint8_t> Redis::popFront(const std::string& queueName, int timeoutMs)
 {
     std::unique_lock<std::mutex> lk(mx);
-    bool ok = listCv.wait_for(lk, std::chrono::milliseconds(timeoutMs <= 0 ? 3600000 : timeoutMs), [&] {
+    auto ready = [&] {
         auto it = lists.find(queueName);
         return it != lists.end() && !it->second.empty();
-    });
+    };
+    // timeout 0 = do not block at all (the reference switches from BLPOP to
+    // LPOP: src/redis/Redis.cpp dequeueBase); negative = wait "forever"
+    bool ok = timeoutMs == 0 ? ready()
+                             : listCv.wait_for(lk, std::chrono::milliseconds(timeoutMs < 0 ? 3600000 : timeoutMs), ready);
     if (!ok) {
         throw RedisNoResponseException();
     }
