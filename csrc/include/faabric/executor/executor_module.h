@@ -107,6 +107,15 @@ class Executor : public std::enable_shared_from_this<Executor>
                       std::shared_ptr<faabric::BatchExecuteRequest> req,
                       std::function<void()> prelude = nullptr);
 
+    // Publishes the result of one thread of a THREADS batch: the diffs are
+    // queued on the main-thread snapshot when the main host is served here,
+    // pushed to it together with the result otherwise; then the message result
+    // goes to the planner (reference: src/executor/Executor.cpp:271-305)
+    void setThreadResult(faabric::Message& msg,
+                         int32_t returnValue,
+                         const std::string& key,
+                         const std::vector<faabric::util::SnapshotDiff>& diffs);
+
     // ---- hooks for subclasses ----
     virtual void reset(faabric::Message& msg);
 

@@ -723,6 +723,24 @@ std::vector<std::pair<uint32_t, int32_t>> Executor::executeThreads(
     return results;
 }
 
+void Executor::setThreadResult(faabric::Message& msg,
+                               int32_t returnValue,
+                               const std::string& key,
+                               const std::vector<faabric::util::SnapshotDiff>& diffs)
+{
+    if (mainHostIsHere(msg)) {
+        if (!diffs.empty()) {
+            // (the diffs point into executor memory, which outlives the merge)
+            SPDLOG_DEBUG("Queueing {} diffs for {} to snapshot {}", diffs.size(), faabric::util::funcToString(msg, false), key);
+            reg.getSnapshot(key)->queueDiffs(diffs);
+        }
+    } else {
+        // result and diffs travel to the main host together
+        faabric::snapshot::getSnapshotClient(msg.mainhost())->pushThreadResult(msg.appid(), msg.id(), returnValue, key, diffs);
+    }
+    faabric::planner::getPlannerClient().setMessageResult(std::make_shared<faabric::Message>(msg));
+}
+
 void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
 {
     SPDLOG_DEBUG("Thread pool thread {}:{} starting up", id, threadPoolIdx);
@@ -854,26 +872,18 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
         }
 
         msg.set_finishtimestamp(faabric::util::getGlobalClock().epochMillis());
-        if (isThreads) {
-            bool mainIsHere = mainHostIsHere(msg);
-            if (!diffs.empty() || isLastThreadInBatch) {
-                std::string key = faabric::util::getMainThreadSnapshotKey(msg);
-                if (mainIsHere) {
-                    if (!diffs.empty()) {
-                        reg.getSnapshot(key)->queueDiffs(diffs);
-                    }
-                } else if (deviceMerged) {
-                    // the bytes are already in the main image: control message only
-                    faabric::snapshot::getSnapshotClient(msg.mainhost())
-                      ->pushDeviceThreadResult(msg.appid(), msg.id(), returnValue, key, deviceDiffBytes);
-                } else if (!diffs.empty()) {
-                    faabric::snapshot::getSnapshotClient(msg.mainhost())
-                      ->pushThreadResult(msg.appid(), msg.id(), returnValue, key, diffs);
-                }
-            }
+        if (isThreads && deviceMerged && !mainHostIsHere(msg)) {
+            // the bytes are already in the main image: control message only
+            faabric::snapshot::getSnapshotClient(msg.mainhost())
+              ->pushDeviceThreadResult(msg.appid(), msg.id(), returnValue, faabric::util::getMainThreadSnapshotKey(msg), deviceDiffBytes);
+            faabric::planner::getPlannerClient().setMessageResult(std::make_shared<faabric::Message>(msg));
+        } else if (isThreads) {
+            // only the last thread of a host's batch carries the diffs
+            std::string key = (!diffs.empty() || isLastThreadInBatch) ? faabric::util::getMainThreadSnapshotKey(msg) : "";
+            setThreadResult(msg, returnValue, key, diffs);
+        } else {
+            faabric::planner::getPlannerClient().setMessageResult(std::make_shared<faabric::Message>(msg));
         }
-        auto result = std::make_shared<faabric::Message>(msg);
-        faabric::planner::getPlannerClient().setMessageResult(result);
     }
     // Thread-local caches die with the thread
     sch.resetThreadLocalCache();
