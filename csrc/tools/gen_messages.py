@@ -442,6 +442,13 @@ def gen_message(m, out, indent=""):
         else:
             w(f"    {CPP_TYPE[t]} {member} = 0;")
     w("};")
+    # protobuf's namespace-level spellings of nested enums and their values
+    # (Message_MessageType, Message_MessageType_EMPTY, ...): code written
+    # against the reference uses both forms
+    for en, vals in m.get("enums", []):
+        w(f"using {name}_{en} = {name}::{en};")
+        for vn, _ in vals:
+            w(f"inline constexpr {name}_{en} {name}_{en}_{vn} = {name}::{vn};")
     w()
 
 
