@@ -190,13 +190,13 @@ void PlannerEndpointHandler::onRequest(const HttpRequest& request, HttpResponse&
             try {
                 planner.setNextEvictedVm(ips);
             } catch (std::exception&) {
-                return reply(response, 400, "Next evicted VMs can only be set with the SPOT policy");
+                return reply(response, 400, "Next evicted VM must only be set in 'spot' policy");
             }
             return reply(response, 200, "Next evicted VM set");
         }
         default: {
             SPDLOG_ERROR("Unrecognised message type {}", (int)msg.type());
-            return reply(response, 400, "Unrecognised request");
+            return reply(response, 400, "Unrecognised message type");
         }
     }
 }
