@@ -240,6 +240,11 @@ SendMessageEndpoint::SendMessageEndpoint(const std::string& hostIn,
                                          int timeoutMsIn)
   : timeoutMs(timeoutMsIn)
 {
+    // (reference: MessageEndpoint's constructor refuses them too)
+    if (timeoutMsIn <= 0) {
+        SPDLOG_ERROR("Setting invalid timeout of {}", timeoutMsIn);
+        throw std::runtime_error("Setting invalid timeout");
+    }
     HostAddress a = parseHostAddress(hostIn);
     host = a.ip;
     port = portIn + a.portOffset;

@@ -131,14 +131,23 @@ class PortListener
 };
 
 // ---------------------------------------------------------------------------
+static int validTimeout(int timeoutMs)
+{
+    if (timeoutMs <= 0) {
+        SPDLOG_ERROR("Setting invalid timeout of {}", timeoutMs);
+        throw std::runtime_error("Setting invalid timeout");
+    }
+    return timeoutMs;
+}
+
 RecvMessageEndpoint::RecvMessageEndpoint(int portIn, int timeoutMsIn)
   : port(portIn)
-  , timeoutMs(timeoutMsIn)
+  , timeoutMs(validTimeout(timeoutMsIn))
   , listener(std::make_shared<PortListener>(portIn))
 {}
 
 RecvMessageEndpoint::RecvMessageEndpoint(const std::string& inprocLabel, int timeoutMsIn)
-  : timeoutMs(timeoutMsIn)
+  : timeoutMs(validTimeout(timeoutMsIn))
   , mailbox(getInprocMailbox(inprocLabel))
 {}
 
@@ -202,7 +211,7 @@ void SyncRecvMessageEndpoint::sendResponse(uint8_t header, const uint8_t* data, 
 // ---------------------------------------------------------------------------
 FanMessageEndpoint::FanMessageEndpoint(int portIn, int timeoutMsIn, bool isAsyncIn)
   : port(portIn)
-  , timeoutMs(timeoutMsIn)
+  , timeoutMs(validTimeout(timeoutMsIn))
   , isAsync(isAsyncIn)
   , listener(std::make_shared<PortListener>(portIn))
 {}
