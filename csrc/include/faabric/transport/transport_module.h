@@ -888,7 +888,6 @@ class PointToPointGroup
 
     int timeoutMs = DEFAULT_DISTRIBUTED_TIMEOUT_MS;
 
-    std::string mainHost;
     int appId = 0;
     int groupId = 0;
     int groupSize = 0;

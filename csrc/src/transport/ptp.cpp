@@ -234,8 +234,8 @@ PointToPointGroup::PointToPointGroup(int appIdIn, int groupIdIn, int groupSizeIn
   , groupId(groupIdIn)
   , groupSize(groupSizeIn)
 {
-    // The coordinator of every group is the host of idx 0
-    mainHost = getPointToPointBroker().getHostForReceiver(groupId, POINT_TO_POINT_MAIN_IDX);
+    // (the coordinator of a group is the host of idx 0: looked up when needed,
+    // a group may be registered before - or without - that mapping)
     localBarrier = faabric::util::Barrier::create(groupSize);
 }
 
