@@ -2154,6 +2154,24 @@ class SnapshotData
 } // namespace faabric::util
 
 // ==========================================================================
+// util/state.h
+// ==========================================================================
+// Naming of state values in the backing store and mask helpers
+// (reference: include/faabric/util/state.h, src/util/state.cpp)
+#define STATE_MASK_8 0b11111111
+#define STATE_MASK_32 0b11111111111111111111111111111111
+
+namespace faabric::util {
+
+// "<user>_<key>"; throws when either part is empty
+std::string keyForUser(const std::string& user, const std::string& key);
+
+// Sets the two 32-bit words of a mask that cover double number `idx`
+void maskDouble(unsigned int* maskArray, unsigned long idx);
+
+}
+
+// ==========================================================================
 // util/string_tools.h
 // ==========================================================================
 namespace faabric::util {

@@ -33,10 +33,7 @@ namespace faabric::state {
 
 static std::string keyFor(const std::string& user, const std::string& key)
 {
-    if (user.empty() || key.empty()) {
-        throw std::runtime_error("Creating key with empty user or key (" + user + "/" + key + ")");
-    }
-    return user + "_" + key;
+    return faabric::util::keyForUser(user, key);
 }
 
 // ---------------------------------------------------------------------------

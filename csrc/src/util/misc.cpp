@@ -445,4 +445,22 @@ bool isMockMode()
     return mockMode.load();
 }
 
+
+// ---- util/state.h ----
+std::string keyForUser(const std::string& user, const std::string& key)
+{
+    if (user.empty() || key.empty()) {
+        throw std::runtime_error("Cannot have empty user or key (" + user + "/" + key + ")");
+    }
+    return user + "_" + key;
+}
+
+void maskDouble(unsigned int* maskArray, unsigned long idx)
+{
+    // (an unsigned int is half a double)
+    unsigned long intIdx = 2 * idx;
+    maskArray[intIdx] |= STATE_MASK_32;
+    maskArray[intIdx + 1] |= STATE_MASK_32;
+}
+
 } // namespace faabric::util
