@@ -15,6 +15,9 @@
 #include <faabric/util/locks.h>
 #include <faabric/util/queue.h>
 
+#include <netinet/in.h>
+#include <sys/socket.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
@@ -215,6 +218,25 @@ void setRecvTimeoutMs(int fd, int timeoutMs);
 void setSendTimeoutMs(int fd, int timeoutMs);
 void setRecvBufferSize(int fd, size_t bufferSize);
 void setSendBufferSize(int fd, size_t bufferSize);
+
+// IPv4 socket address (reference: include/faabric/transport/tcp/Address.h)
+class Address
+{
+  public:
+    Address(const std::string& host, int port);
+
+    // any local interface
+    explicit Address(int port);
+
+    sockaddr* get() const { return (sockaddr*)&addr; }
+
+    int port() const;
+
+    std::string host() const;
+
+  private:
+    sockaddr_in addr;
+};
 
 class Socket
 {

@@ -203,6 +203,36 @@ void SendSocket::sendOne(const uint8_t* buffer, size_t bufferSize)
     }
 }
 
+Address::Address(const std::string& host, int port)
+{
+    memset(&addr, 0, sizeof(addr));
+    addr.sin_family = AF_INET;
+    addr.sin_port = htons((uint16_t)port);
+    if (::inet_pton(AF_INET, host.c_str(), &addr.sin_addr) != 1) {
+        throw std::runtime_error("Not an IPv4 address: " + host);
+    }
+}
+
+Address::Address(int port)
+{
+    memset(&addr, 0, sizeof(addr));
+    addr.sin_family = AF_INET;
+    addr.sin_port = htons((uint16_t)port);
+    addr.sin_addr.s_addr = htonl(INADDR_ANY);
+}
+
+int Address::port() const
+{
+    return ntohs(addr.sin_port);
+}
+
+std::string Address::host() const
+{
+    char buf[INET_ADDRSTRLEN] = { 0 };
+    ::inet_ntop(AF_INET, &addr.sin_addr, buf, sizeof(buf));
+    return buf;
+}
+
 RecvSocket::RecvSocket(int portIn, const std::string& hostIn)
   : host(hostIn)
   , port(portIn)

@@ -464,3 +464,9 @@ void maskDouble(unsigned int* maskArray, unsigned long idx)
 }
 
 } // namespace faabric::util
+
+// (reference: include/faabric/wasm/wasm.h declares it for the embedder)
+int helloFaabricWasm()
+{
+    return 0;
+}

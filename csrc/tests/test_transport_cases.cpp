@@ -368,3 +368,15 @@ TEST_CASE("transport case: a server keeps listening after its socket timeout pas
     REQUIRE_EQ(server.messageCount.load(), 2);
     server.stop();
 }
+
+TEST_CASE("transport case: socket addresses", "[transport][cases]")
+{
+    faabric::transport::tcp::Address a("127.0.0.2", 8123);
+    REQUIRE_EQ(a.port(), 8123);
+    REQUIRE_EQ(a.host(), std::string("127.0.0.2"));
+    REQUIRE_EQ(((sockaddr_in*)a.get())->sin_family, (sa_family_t)AF_INET);
+    faabric::transport::tcp::Address any(9000);
+    REQUIRE_EQ(any.port(), 9000);
+    REQUIRE_EQ(any.host(), std::string("0.0.0.0"));
+    REQUIRE_THROWS(faabric::transport::tcp::Address("not-an-ip", 1));
+}
