@@ -186,6 +186,9 @@ class Executor : public std::enable_shared_from_this<Executor>
 
     uint64_t getDeviceMergeCount() const { return deviceMergeCount.load(); }
 
+    // The message this executor was created for
+    faabric::Message& getBoundMessage() { return boundMessage; }
+
     std::string schedulerKey;
 
     // Incremental device THREADS: the stamp of the main image this executor's

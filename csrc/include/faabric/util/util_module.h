@@ -213,6 +213,9 @@ std::shared_ptr<faabric::BatchExecuteRequest> batchExecFactory(
 
 bool isBatchExecRequestValid(std::shared_ptr<faabric::BatchExecuteRequest> ber);
 
+// Results of a status that are final (migrated messages will report again)
+int getNumFinishedMessagesInBatch(std::shared_ptr<faabric::BatchExecuteRequestStatus> berStatus);
+
 void updateBatchExecAppId(std::shared_ptr<faabric::BatchExecuteRequest> ber,
                           int newAppId);
 
@@ -237,6 +240,9 @@ namespace faabric::util {
 
 std::vector<uint8_t> stringToBytes(const std::string& str);
 
+// The int stored in exactly sizeof(int) bytes
+int bytesToInt(const std::vector<uint8_t>& bytes);
+
 std::string bytesToString(const std::vector<uint8_t>& bytes);
 
 std::string formatByteArrayToIntString(const std::vector<uint8_t>& bytes);
@@ -254,6 +260,31 @@ int safeCopyToBuffer(const uint8_t* dataIn,
                      int bufferLen);
 
 std::string byteArrayToHexString(const uint8_t* data, int dataSize);
+
+// Zero-padded hex of an integer, two digits per byte of T
+template<typename T>
+std::string intToHexString(T i)
+{
+    static const char* digits = "0123456789abcdef";
+    std::string out(sizeof(T) * 2, '0');
+    auto v = (unsigned long long)i;
+    if constexpr (sizeof(T) < sizeof(unsigned long long)) {
+        v &= (1ull << (8 * sizeof(T))) - 1;
+    }
+    for (size_t k = 0; k < sizeof(T) * 2; k++) {
+        out[sizeof(T) * 2 - 1 - k] = digits[v & 0xf];
+        v >>= 4;
+    }
+    return out;
+}
+
+// Appends the object representation of `value`
+template<class T>
+void appendBytesOf(std::vector<uint8_t>& container, T value)
+{
+    const uint8_t* start = reinterpret_cast<const uint8_t*>(&value);
+    container.insert(container.end(), start, start + sizeof(T));
+}
 
 std::vector<uint8_t> hexStringToByteArray(const std::string& hexString);
 
@@ -718,6 +749,10 @@ namespace faabric::util {
 void setUpCrashHandler(int sig = -1);
 
 void printStackTrace(void* contextR = nullptr);
+
+// What the installed handler does: prints the back-trace, then (unless `sig`
+// is the test signal) re-raises with the default action
+void handleCrash(int sig);
 
 }
 
@@ -2193,6 +2228,24 @@ std::vector<std::string> splitString(const std::string& input, char delim);
 std::string trim(const std::string& input);
 
 std::string toLower(const std::string& input);
+
+// "[a, b, c]"
+template<class T>
+std::string vectorToString(std::vector<T> vec)
+{
+    std::string out = "[";
+    for (size_t i = 0; i < vec.size(); i++) {
+        if constexpr (std::is_arithmetic_v<T>) {
+            out += std::to_string(vec[i]);
+        } else {
+            out += vec[i];
+        }
+        if (i + 1 < vec.size()) {
+            out += ", ";
+        }
+    }
+    return out + "]";
+}
 
 }
 

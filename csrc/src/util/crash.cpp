@@ -35,6 +35,11 @@ static void crashHandler(int sig, siginfo_t* info, void*) noexcept
     }
 }
 
+void handleCrash(int sig)
+{
+    crashHandler(sig, nullptr, nullptr);
+}
+
 static void installHandler(int s)
 {
     struct sigaction sa{};

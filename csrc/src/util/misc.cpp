@@ -446,6 +446,28 @@ bool isMockMode()
 }
 
 
+// ---- util/bytes.h, util/batch.h additions ----
+int bytesToInt(const std::vector<uint8_t>& bytes)
+{
+    if (bytes.size() != sizeof(int)) {
+        throw std::runtime_error("bytesToInt needs exactly sizeof(int) bytes");
+    }
+    int v;
+    memcpy(&v, bytes.data(), sizeof(int));
+    return v;
+}
+
+int getNumFinishedMessagesInBatch(std::shared_ptr<faabric::BatchExecuteRequestStatus> berStatus)
+{
+    int n = 0;
+    for (const auto& m : berStatus->messageresults()) {
+        if (m.returnvalue() != MIGRATED_FUNCTION_RETURN_VALUE) {
+            n++;
+        }
+    }
+    return n;
+}
+
 // ---- util/state.h ----
 std::string keyForUser(const std::string& user, const std::string& key)
 {

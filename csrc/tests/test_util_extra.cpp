@@ -662,3 +662,26 @@ TEST_CASE("delta: the building blocks produce and walk the same stream as the on
     std::vector<uint8_t> unknown = { 0x77 };
     REQUIRE_THROWS(faabric::util::deltaForEach(unknown, [](uint32_t) {}, [](bool, uint32_t, const uint8_t*, uint32_t) {}));
 }
+
+TEST_CASE("bytes, strings and batch helpers under the reference's names", "[util]")
+{
+    std::vector<uint8_t> four;
+    faabric::util::appendBytesOf<int>(four, 0x01020304);
+    REQUIRE_EQ(four.size(), sizeof(int));
+    REQUIRE_EQ(faabric::util::bytesToInt(four), 0x01020304);
+    faabric::util::appendBytesOf<uint8_t>(four, 9);
+    REQUIRE_EQ(four.size(), 5u);
+    REQUIRE_THROWS(faabric::util::bytesToInt(four));
+    REQUIRE_EQ(faabric::util::intToHexString<uint8_t>(0x0f), std::string("0f"));
+    REQUIRE_EQ(faabric::util::intToHexString<uint16_t>(0xabc), std::string("0abc"));
+    REQUIRE_EQ(faabric::util::intToHexString<uint32_t>(255), std::string("000000ff"));
+    REQUIRE_EQ(faabric::util::intToHexString<int>(-1), std::string("ffffffff"));
+    REQUIRE_EQ(faabric::util::vectorToString<int>({ 1, 2, 3 }), std::string("[1, 2, 3]"));
+    REQUIRE_EQ(faabric::util::vectorToString<std::string>({ "a", "bc" }), std::string("[a, bc]"));
+    REQUIRE_EQ(faabric::util::vectorToString<int>({}), std::string("[]"));
+    auto status = faabric::util::batchExecStatusFactory(7);
+    for (int rv : { 0, 1, MIGRATED_FUNCTION_RETURN_VALUE, 0 }) {
+        status->add_messageresults()->set_returnvalue(rv);
+    }
+    REQUIRE_EQ(faabric::util::getNumFinishedMessagesInBatch(status), 3);
+}
