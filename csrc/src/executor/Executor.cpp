@@ -262,7 +262,13 @@ static bool mainHostIsHere(const faabric::Message& msg)
 }
 
 // ---- hooks (defaults) ----
-void Executor::reset(faabric::Message& msg) {}
+void Executor::reset(faabric::Message& msg)
+{
+    // (reference: src/executor/Executor.cpp reset() - the chained calls of the
+    // function that just finished are forgotten)
+    std::lock_guard<std::mutex> lk(chainedMx);
+    chainedMessages.clear();
+}
 
 DeviceMemoryView Executor::getDeviceMemoryView()
 {

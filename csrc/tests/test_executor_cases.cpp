@@ -473,3 +473,120 @@ TEST_CASE("executor case: tasks can be handed to an executor by hand", "[executo
     }
     REQUIRE(rvs == (std::set<int>{ 100, 101, 102 }));
 }
+
+TEST_CASE("executor case: the time since the last execution restarts with every execution", "[executor][cases]")
+{
+    ClusterFixture f(5);
+    auto req = faabric::util::batchExecFactory("foo", "bar", 1);
+    faabric::Message msg = req->messages(0);
+    req->mutable_messages(0)->set_executedhost(f.conf.endpointHost);
+    faabric::HostResources res;
+    res.set_slots(5);
+    res.set_usedslots(5);
+    f.sch.setThisHostResources(res);
+    f.sch.addHostToGlobalSet();
+    auto exec = std::make_shared<TestExecutor>(*req->mutable_messages(0));
+    long a = exec->getMillisSinceLastExec();
+    std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    long b = exec->getMillisSinceLastExec();
+    REQUIRE(b > a);
+    REQUIRE(b - a > 90);
+    exec->claim();
+    exec->executeTasks({ 0 }, req);
+    REQUIRE(exec->getMillisSinceLastExec() < b);
+    f.awaitResult(msg, 2000);
+    exec->shutdown();
+}
+
+TEST_CASE("executor case: chained messages are kept until the executor is reset", "[executor][cases]")
+{
+    ClusterFixture f(2);
+    auto req = faabric::util::batchExecFactory("hello", "world", 1);
+    auto& first = *req->mutable_messages(0);
+    auto exec = std::make_shared<TestExecutor>(first);
+    REQUIRE(exec->getChainedMessageIds().empty());
+    faabric::Message chained = faabric::util::messageFactory("hello", "chained");
+    chained.set_inputdata("payload");
+    exec->addChainedMessage(chained);
+    REQUIRE(exec->getChainedMessageIds() == (std::set<unsigned int>{ (unsigned int)chained.id() }));
+    const faabric::Message& kept = exec->getChainedMessage(chained.id());
+    REQUIRE_EQ(kept.id(), chained.id());
+    REQUIRE_EQ(kept.function(), std::string("chained"));
+    REQUIRE_EQ(kept.inputdata(), std::string("payload"));
+    REQUIRE_THROWS(exec->getChainedMessage(chained.id() + 1));
+    exec->reset(first);
+    REQUIRE(exec->getChainedMessageIds().empty());
+    exec->shutdown();
+}
+
+TEST_CASE("executor case: executors idle for longer than the bound timeout are reaped, busy ones are not", "[executor][cases]")
+{
+    ClusterFixture f(4);
+    f.conf.boundTimeout = 200;
+    auto release = std::make_shared<std::atomic<bool>>(false);
+    registerTestFunction("reap", "busy", [release](auto*, int, int, auto) {
+        while (!release->load()) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        }
+        return 0;
+    });
+    auto idle = faabric::util::batchExecFactory("reap", "idle", 2);
+    auto busy = faabric::util::batchExecFactory("reap", "busy", 1);
+    f.plannerCli.callFunctions(idle);
+    f.awaitBatch(idle);
+    f.plannerCli.callFunctions(busy);
+    REQUIRE_EQ(f.sch.getFunctionExecutorCount(idle->messages(0)), 2);
+    REQUIRE_EQ(f.sch.getFunctionExecutorCount(busy->messages(0)), 1);
+    // nothing is stale yet
+    REQUIRE_EQ(f.sch.reapStaleExecutors(), 0);
+    std::this_thread::sleep_for(std::chrono::milliseconds(400));
+    REQUIRE_EQ(f.sch.reapStaleExecutors(), 2);
+    REQUIRE_EQ(f.sch.getFunctionExecutorCount(idle->messages(0)), 0);
+    REQUIRE_EQ(f.sch.getFunctionExecutorCount(busy->messages(0)), 1);
+    release->store(true);
+    f.awaitBatch(busy);
+    f.conf.reset();
+}
+
+TEST_CASE("executor case: threads forked by a function that was itself chained", "[executor][cases]")
+{
+    ClusterFixture f(8);
+    std::atomic<int> threadsRun{ 0 };
+    registerTestFunction("chain", "leaf-threads", [&](auto* exec, int, int idx, auto req) {
+        auto& m = *req->mutable_messages(idx);
+        if (req->type() == faabric::BatchExecuteRequest::THREADS) {
+            threadsRun++;
+            return m.appidx();
+        }
+        // the chained function forks three threads and adds up what they return
+        auto threads = faabric::util::batchExecFactory("chain", "leaf-threads", 3);
+        faabric::util::updateBatchExecAppId(threads, m.appid());
+        for (int i = 0; i < 3; i++) {
+            threads->mutable_messages(i)->set_appidx(i + 1);
+            threads->mutable_messages(i)->set_groupidx(i + 1);
+        }
+        threads->set_singlehosthint(true);
+        int sum = 0;
+        for (auto& [id, rv] : exec->executeThreads(threads, {})) {
+            sum += rv;
+        }
+        m.set_outputdata(std::to_string(sum));
+        return 0;
+    });
+    registerTestFunction("chain", "root", [&](auto* exec, int, int idx, auto req) {
+        auto& m = *req->mutable_messages(idx);
+        // (a chained call is an app of its own; only threads join their parent's)
+        auto chained = faabric::util::batchExecFactory("chain", "leaf-threads", 1);
+        exec->addChainedMessage(chained->messages(0));
+        faabric::planner::getPlannerClient().callFunctions(chained);
+        auto res = faabric::planner::getPlannerClient().getMessageResult(chained->messages(0), 5000);
+        m.set_outputdata("threads said " + res.outputdata());
+        return res.returnvalue();
+    });
+    auto req = faabric::util::batchExecFactory("chain", "root", 1);
+    f.plannerCli.callFunctions(req);
+    auto res = f.awaitResult(req->messages(0), 10000);
+    REQUIRE_EQ(res.returnvalue(), 0);
+    REQUIRE_EQ(res.outputdata(), std::string("threads said 6"));
+    REQUIRE_EQ(threadsRun.load(), 3);
+}
