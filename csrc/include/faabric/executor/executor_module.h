@@ -254,6 +254,8 @@ class Executor : public std::enable_shared_from_this<Executor>
 
     void prepareDeviceThreads(const std::string& key, bool isMain);
 
+    void stopPoolThreads();
+
     void threadPoolThread(std::stop_token st, int threadPoolIdx);
 };
 

@@ -142,8 +142,12 @@ Executor::~Executor()
 {
     if (!_isShutdown) {
         SPDLOG_DEBUG("Destructing executor {} without shutting down first", id);
-        shutdown();
     }
+    // (also when it was shut down before: a batch dispatched concurrently with
+    // the shutdown may have started a pool thread afterwards, and a thread
+    // that was never poisoned only notices its stop token after a whole
+    // bound timeout)
+    stopPoolThreads();
     if (computeStream != nullptr) {
         cudaStreamDestroy((cudaStream_t)computeStream);
         cudaGetLastError();
@@ -157,6 +161,11 @@ void Executor::shutdown()
     if (_isShutdown.exchange(true)) {
         return;
     }
+    stopPoolThreads();
+}
+
+void Executor::stopPoolThreads()
+{
     // Poison every started pool thread, then join
     std::vector<std::shared_ptr<std::jthread>> toJoin;
     {

@@ -522,10 +522,17 @@ TEST_CASE("executor case: chained messages are kept until the executor is reset"
 TEST_CASE("executor case: executors idle for longer than the bound timeout are reaped, busy ones are not", "[executor][cases]")
 {
     ClusterFixture f(4);
-    f.conf.boundTimeout = 200;
+    f.conf.boundTimeout = 1500;
     auto release = std::make_shared<std::atomic<bool>>(false);
+    // (whatever an assertion below does, the busy function must be let go
+    // before the fixture tears the scheduler down)
+    struct Release
+    {
+        std::shared_ptr<std::atomic<bool>> flag;
+        ~Release() { flag->store(true); }
+    } letGo{ release };
     registerTestFunction("reap", "busy", [release](auto*, int, int, auto) {
-        while (!release->load()) {
+        for (int waited = 0; !release->load() && waited < 10000; waited += 2) {
             std::this_thread::sleep_for(std::chrono::milliseconds(2));
         }
         return 0;
@@ -535,11 +542,15 @@ TEST_CASE("executor case: executors idle for longer than the bound timeout are r
     f.plannerCli.callFunctions(idle);
     f.awaitBatch(idle);
     f.plannerCli.callFunctions(busy);
+    // (dispatch to the host is asynchronous: wait for the executor to appear)
+    for (int i = 0; i < 400 && f.sch.getFunctionExecutorCount(busy->messages(0)) < 1; i++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
     REQUIRE_EQ(f.sch.getFunctionExecutorCount(idle->messages(0)), 2);
     REQUIRE_EQ(f.sch.getFunctionExecutorCount(busy->messages(0)), 1);
     // nothing is stale yet
     REQUIRE_EQ(f.sch.reapStaleExecutors(), 0);
-    std::this_thread::sleep_for(std::chrono::milliseconds(400));
+    std::this_thread::sleep_for(std::chrono::milliseconds(2000));
     REQUIRE_EQ(f.sch.reapStaleExecutors(), 2);
     REQUIRE_EQ(f.sch.getFunctionExecutorCount(idle->messages(0)), 0);
     REQUIRE_EQ(f.sch.getFunctionExecutorCount(busy->messages(0)), 1);

@@ -139,7 +139,7 @@ TEST_CASE("planner case: the scheduling decision of a registered app", "[planner
     auto req = faabric::util::batchExecFactory("foo", "bar", 4);
     auto holdUntil = std::make_shared<std::atomic<bool>>(false);
     registerTestFunction("foo", "bar", [holdUntil](auto*, int, int, auto) {
-        while (!holdUntil->load()) {
+        for (int waited = 0; !holdUntil->load() && waited < 10000; waited += 1) {
             std::this_thread::sleep_for(std::chrono::milliseconds(1));
         }
         return 0;

@@ -272,7 +272,7 @@ TEST_CASE("endpoint case: flushing the scheduling state forgets in-flight apps",
     EndpointFixture f;
     auto release = std::make_shared<std::atomic<bool>>(false);
     registerTestFunction("foo", "hold", [release](auto*, int, int, auto) {
-        while (!release->load()) {
+        for (int waited = 0; !release->load() && waited < 10000; waited += 1) {
             std::this_thread::sleep_for(std::chrono::milliseconds(1));
         }
         return 0;
@@ -298,7 +298,7 @@ TEST_CASE("endpoint case: in-flight apps before, during and after a batch, and t
     REQUIRE_EQ(r.second, faabric::util::messageToJson(expected));
     auto release = std::make_shared<std::atomic<bool>>(false);
     registerTestFunction("foo", "bar5", [release](auto*, int, int, auto) {
-        while (!release->load()) {
+        for (int waited = 0; !release->load() && waited < 10000; waited += 1) {
             std::this_thread::sleep_for(std::chrono::milliseconds(1));
         }
         return 0;
