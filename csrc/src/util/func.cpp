@@ -57,6 +57,10 @@ unsigned int setMessageId(faabric::Message& msg)
     if (msg.appid() == 0) {
         msg.set_appid((int32_t)generateGid());
     }
+    // (reference: src/util/func.cpp:102-106 - a message without a timestamp gets one)
+    if (msg.starttimestamp() <= 0) {
+        msg.set_starttimestamp(getGlobalClock().epochMillis());
+    }
     msg.set_resultkey(resultKeyFromMessageId(id));
     msg.set_statuskey(statusKeyFromMessageId(id));
     return id;
