@@ -34,6 +34,7 @@
 #include <unistd.h>
 #include <unordered_map>
 #include <utility>
+#include <unordered_set>
 #include <vector>
 
 // ==========================================================================
@@ -1949,6 +1950,9 @@ namespace faabric::util {
 std::string randomString(int len);
 
 std::string randomStringFromSet(int len, const std::string& charSet);
+
+// A uniformly chosen member of the set ("" for an empty one)
+std::string randomStringFromSet(const std::unordered_set<std::string>& s);
 
 int randomInteger(int iStart, int iEnd);
 

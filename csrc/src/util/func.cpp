@@ -152,9 +152,11 @@ std::shared_ptr<faabric::BatchExecuteRequest> batchExecFactory(
 bool isBatchExecRequestValid(std::shared_ptr<faabric::BatchExecuteRequest> ber)
 {
     if (ber == nullptr) {
+        SPDLOG_ERROR("Invalid BER: null");
         return false;
     }
-    if (ber->messages_size() <= 0) {
+    // never initialised: no messages and no app id
+    if (ber->messages_size() <= 0 && ber->appid() == 0) {
         SPDLOG_ERROR("Invalid BER: zero messages");
         return false;
     }
@@ -162,10 +164,12 @@ bool isBatchExecRequestValid(std::shared_ptr<faabric::BatchExecuteRequest> ber)
         SPDLOG_ERROR("Invalid BER: empty user or function");
         return false;
     }
+    // Every message shares the request's user and app id.  Function names may
+    // differ (a request may carry calls chained by name) but not be empty
+    // (reference: src/util/batch.cpp:58-78)
     for (int i = 0; i < ber->messages_size(); i++) {
         const auto& m = ber->messages(i);
-        if (m.user() != ber->user() || m.function() != ber->function() ||
-            m.appid() != ber->appid()) {
+        if (m.user() != ber->user() || m.function().empty() || m.appid() != ber->appid()) {
             SPDLOG_ERROR("Invalid BER: message {} inconsistent with request", i);
             return false;
         }

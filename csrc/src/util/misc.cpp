@@ -446,6 +446,16 @@ bool isMockMode()
 }
 
 
+std::string randomStringFromSet(const std::unordered_set<std::string>& s)
+{
+    if (s.empty()) {
+        return "";
+    }
+    auto it = s.begin();
+    std::advance(it, randomInteger(0, (int)s.size() - 1));
+    return *it;
+}
+
 // ---- util/bytes.h, util/batch.h additions ----
 int bytesToInt(const std::vector<uint8_t>& bytes)
 {

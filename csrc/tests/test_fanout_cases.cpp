@@ -62,29 +62,12 @@ TEST_CASE("fan-out case: every function of a wide batch runs exactly once, each 
     REQUIRE_EQ((int)executorsSeen.size(), n);
 }
 
-TEST_CASE("fan-out case: a request whose messages name another function is rejected", "[planner][executor][fanout]")
+TEST_CASE("fan-out case: a request may mix functions (chaining by name); each runs in an executor of its function",
+          "[planner][executor][fanout]")
 {
-    // (this is what lets the scheduler build the executor key once per batch:
-    // every message of a request shares user and function)
+    // (the scheduler builds the executor key once per run of equal messages:
+    // the cached key must follow when the function changes)
     ClusterFixture f(16);
-    std::atomic<int> ran{ 0 };
-    registerTestFunction("demo", "alpha", [&](auto*, int, int, auto) {
-        ran++;
-        return 0;
-    });
-    registerTestFunction("demo", "beta", [&](auto*, int, int, auto) {
-        ran++;
-        return 0;
-    });
-    auto req = faabric::util::batchExecFactory("demo", "alpha", 8);
-    for (int i = 0; i < 8; i += 2) {
-        req->mutable_messages(i)->set_function("beta");
-    }
-    REQUIRE(!faabric::util::isBatchExecRequestValid(req));
-    REQUIRE_THROWS(f.plannerCli.callFunctions(req));
-    REQUIRE_EQ(ran.load(), 0);
-    REQUIRE_EQ(f.planner.getInFlightReqs().size(), 0u);
-    // the same messages as two consistent requests run in executors per function
     std::mutex mx;
     std::map<std::string, std::set<faabric::executor::Executor*>> executorsOf;
     auto body = [&](auto* exec, int, int idx, auto r) {
@@ -94,17 +77,27 @@ TEST_CASE("fan-out case: a request whose messages name another function is rejec
     };
     registerTestFunction("demo", "alpha", body);
     registerTestFunction("demo", "beta", body);
-    auto a = faabric::util::batchExecFactory("demo", "alpha", 4);
-    auto b = faabric::util::batchExecFactory("demo", "beta", 4);
-    f.plannerCli.callFunctions(a);
-    f.plannerCli.callFunctions(b);
-    f.awaitBatch(a);
-    f.awaitBatch(b);
+    auto req = faabric::util::batchExecFactory("demo", "alpha", 8);
+    for (int i = 0; i < 8; i += 2) {
+        req->mutable_messages(i)->set_function("beta"); // alternate
+    }
+    REQUIRE(faabric::util::isBatchExecRequestValid(req));
+    f.plannerCli.callFunctions(req);
+    auto status = f.awaitBatch(req);
+    REQUIRE_EQ(status->messageresults_size(), 8);
     REQUIRE_EQ(executorsOf["alpha"].size(), 4u);
     REQUIRE_EQ(executorsOf["beta"].size(), 4u);
     for (auto* e : executorsOf["alpha"]) {
         REQUIRE(executorsOf["beta"].count(e) == 0);
     }
+    // what is NOT allowed: another user, another app, an empty function
+    auto otherUser = faabric::util::batchExecFactory("demo", "alpha", 2);
+    otherUser->mutable_messages(1)->set_user("somebody");
+    REQUIRE(!faabric::util::isBatchExecRequestValid(otherUser));
+    auto noFunction = faabric::util::batchExecFactory("demo", "alpha", 2);
+    noFunction->mutable_messages(1)->set_function("");
+    REQUIRE(!faabric::util::isBatchExecRequestValid(noFunction));
+    REQUIRE_THROWS(f.plannerCli.callFunctions(noFunction));
 }
 
 TEST_CASE("fan-out case: results submitted concurrently are all recorded, in one piece", "[planner][fanout]")

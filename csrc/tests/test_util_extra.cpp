@@ -200,10 +200,18 @@ TEST_CASE("batch helpers: validity, ids and status objects", "[util]")
         REQUIRE_EQ(m.user(), std::string("demo"));
     }
     REQUIRE(!isBatchExecRequestValid(nullptr));
-    // a message that disagrees with the request invalidates it
+    // a message for another user invalidates the request; another (non-empty)
+    // function name does not: requests may carry calls chained by name
+    // (reference: src/util/batch.cpp:58-78)
+    auto chainedByName = batchExecFactory("demo", "echo", 2);
+    chainedByName->mutable_messages(1)->set_function("other");
+    REQUIRE(isBatchExecRequestValid(chainedByName));
     auto broken = batchExecFactory("demo", "echo", 2);
-    broken->mutable_messages(1)->set_function("other");
+    broken->mutable_messages(1)->set_user("somebody-else");
     REQUIRE(!isBatchExecRequestValid(broken));
+    auto noFunction = batchExecFactory("demo", "echo", 2);
+    noFunction->mutable_messages(0)->set_function("");
+    REQUIRE(!isBatchExecRequestValid(noFunction));
     auto wrongApp = batchExecFactory("demo", "echo", 2);
     wrongApp->mutable_messages(0)->set_appid(wrongApp->appid() + 1);
     REQUIRE(!isBatchExecRequestValid(wrongApp));
