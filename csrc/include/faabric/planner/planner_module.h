@@ -412,7 +412,11 @@ class PlannerClient final : public faabric::transport::MessageEndpointClient
     void setMessageResult(std::shared_ptr<faabric::Message> msg);
 
     // Called by the FunctionCallServer when the planner notifies a result
-    void setMessageResultLocally(std::shared_ptr<faabric::Message> msg);
+    // onlyIfAwaited: deliver only to a wait that is already registered (the
+    // planner's notifications, which are always answers to one)
+    void setMessageResultLocally(std::shared_ptr<faabric::Message> msg, bool onlyIfAwaited = false);
+    // Drops a locally delivered result nobody is going to wait for
+    void forgetMessageResult(uint32_t msgId);
 
     faabric::Message getMessageResult(int appId, int msgId, int timeoutMs);
 

@@ -188,9 +188,14 @@ void PlannerClient::setMessageResult(std::shared_ptr<faabric::Message> msg)
     asyncSend(PlannerCalls::SetMessageResult, msg.get());
 }
 
-void PlannerClient::setMessageResultLocally(std::shared_ptr<faabric::Message> msg)
+void PlannerClient::setMessageResultLocally(std::shared_ptr<faabric::Message> msg, bool onlyIfAwaited)
 {
     std::lock_guard<std::mutex> lk(sharedCacheMx);
+    if (onlyIfAwaited && sharedCache.plannerResults.find((uint32_t)msg->id()) == sharedCache.plannerResults.end()) {
+        // The waiter the planner is answering has gone (timed out, or served
+        // by a result pushed to it directly): nothing to keep
+        return;
+    }
     // May arrive before anyone waits: the promise holds it until then
     auto& promise = sharedCache.plannerResults[(uint32_t)msg->id()];
     try {
@@ -198,6 +203,12 @@ void PlannerClient::setMessageResultLocally(std::shared_ptr<faabric::Message> ms
     } catch (const std::future_error&) {
         SPDLOG_DEBUG("Result for message {} delivered twice", msg->id());
     }
+}
+
+void PlannerClient::forgetMessageResult(uint32_t msgId)
+{
+    std::lock_guard<std::mutex> lk(sharedCacheMx);
+    sharedCache.plannerResults.erase(msgId);
 }
 
 faabric::Message PlannerClient::getMessageResult(int appId, int msgId, int timeoutMs)

@@ -222,7 +222,7 @@ void FunctionCallServer::recvSetMessageResult(std::span<const uint8_t> buffer)
     if (!msg->ParseFromArray(buffer.data(), (int)buffer.size())) {
         throw std::runtime_error("Could not parse message result");
     }
-    faabric::planner::getPlannerClient().setMessageResultLocally(msg);
+    faabric::planner::getPlannerClient().setMessageResultLocally(msg, true);
 }
 
 } // namespace faabric::scheduler

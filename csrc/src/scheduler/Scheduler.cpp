@@ -458,6 +458,14 @@ void Scheduler::setThreadResultLocally(uint32_t appId,
     } catch (const std::future_error&) {
         SPDLOG_WARN("Thread result for {} set twice", msgId);
     }
+    // Somebody may already be blocked on the planner for this thread: the
+    // pushed result resolves that wait too (reference:
+    // src/scheduler/Scheduler.cpp setThreadResultLocally does the same)
+    auto asMessage = std::make_shared<faabric::Message>();
+    asMessage->set_appid((int)appId);
+    asMessage->set_id((int)msgId);
+    asMessage->set_returnvalue(returnValue);
+    faabric::planner::getPlannerClient().setMessageResultLocally(asMessage);
 }
 
 std::vector<std::pair<uint32_t, int32_t>> Scheduler::awaitThreadResults(
@@ -481,6 +489,7 @@ std::vector<std::pair<uint32_t, int32_t>> Scheduler::awaitThreadResults(
         }
         if (local && fut.wait_for(std::chrono::milliseconds(0)) == std::future_status::ready) {
             results.emplace_back(msgId, fut.get());
+            faabric::planner::getPlannerClient().forgetMessageResult(msgId);
             continue;
         }
         faabric::Message res = faabric::planner::getPlannerClient().getMessageResult(

@@ -598,11 +598,14 @@ TEST_CASE("cpu pinning: claims are exclusive, released and exhaustible", "[util]
             while (getNumFreeCpus() > 0) {
                 pins.push_back(pinThreadToFreeCpu(pthread_self()));
             }
+            // (outside test mode: in test mode an extra pin shares CPU 0)
+            setTestMode(false);
             try {
                 pinThreadToFreeCpu(pthread_self());
             } catch (const std::runtime_error&) {
                 exhaustedThrew = true;
             }
+            setTestMode(true);
         });
         rest.join();
         REQUIRE(exhaustedThrew.load());
