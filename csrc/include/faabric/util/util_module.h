@@ -536,11 +536,29 @@ class ConcurrentMap
         return inserted;
     }
 
+    // True if the key was new, false if an existing value was replaced
     template<typename V>
-    void insertOrAssign(const Key& key, V&& value)
+    bool insertOrAssign(const Key& key, V&& value)
     {
         FullLock lock(mx);
-        map.insert_or_assign(key, std::forward<V>(value));
+        return map.insert_or_assign(key, std::forward<V>(value)).second;
+    }
+
+    // Inserts a (key, value) pair unless the key is taken; true if inserted
+    template<typename P>
+    bool insert(P&& pair)
+    {
+        FullLock lock(mx);
+        return map.insert(std::forward<P>(pair)).second;
+    }
+
+    void swap(ConcurrentMap<Key, Value>& other)
+    {
+        if (this == &other) {
+            return;
+        }
+        std::scoped_lock lock(mx, other.mx);
+        map.swap(other.map);
     }
 
     bool erase(const Key& key)

@@ -11,6 +11,7 @@
 #include <fcntl.h>
 #include <linux/userfaultfd.h>
 #include <mutex>
+#include <unordered_map>
 #include <poll.h>
 #include <signal.h>
 #include <stdexcept>
@@ -499,6 +500,13 @@ struct UffdDirtyTracker::Impl
     std::span<uint8_t> tracked;
     // The event thread marks pages in the record the control calls reset
     std::mutex recordMx;
+    // Features the kernel granted (see openUffd)
+    bool wpUnpopulated = false;
+    bool threadIds = false;
+    // Faults carry the id of the faulting thread: a thread that asked for
+    // thread-local tracking gets its own record (the counterpart of the
+    // reference's per-thread SIGBUS bookkeeping, src/util/dirty.cpp:626-700)
+    std::unordered_map<uint32_t, std::shared_ptr<TrackingRecord>> perThread;
 
     void loop()
     {
@@ -522,8 +530,18 @@ struct UffdDirtyTracker::Impl
             void* addr = (void*)(uintptr_t)msg.arg.pagefault.address;
             {
                 std::lock_guard<std::mutex> lk(recordMx);
-                if (TrackingRecord* rec = globalRecords.find(addr)) {
-                    rec->mark(addr);
+                bool attributed = false;
+                if (threadIds) {
+                    auto it = perThread.find((uint32_t)msg.arg.pagefault.feat.ptid);
+                    if (it != perThread.end() && it->second->contains(addr)) {
+                        it->second->mark(addr);
+                        attributed = true;
+                    }
+                }
+                if (!attributed) {
+                    if (TrackingRecord* rec = globalRecords.find(addr)) {
+                        rec->mark(addr);
+                    }
                 }
             }
             // Drop write protection on the page and wake the faulting thread
@@ -536,21 +554,47 @@ struct UffdDirtyTracker::Impl
     }
 };
 
-static int openUffd()
+// Opens a userfaultfd with write-protect faults, asking for the optional
+// features too: protection of pages that are not populated yet (6.4+; without
+// it the tracker pre-faults the region), of shared / file-backed memory
+// (5.19+) and thread ids in fault messages
+static int openUffd(bool* wpUnpopulated = nullptr, bool* threadIds = nullptr)
 {
-    int fd = (int)::syscall(SYS_userfaultfd, O_CLOEXEC | O_NONBLOCK);
-    if (fd < 0) {
-        return -1;
-    }
-    uffdio_api api;
-    memset(&api, 0, sizeof(api));
-    api.api = UFFD_API;
-    api.features = UFFD_FEATURE_PAGEFAULT_FLAG_WP;
-    if (::ioctl(fd, UFFDIO_API, &api) != 0) {
+    const uint64_t base = UFFD_FEATURE_PAGEFAULT_FLAG_WP;
+    const uint64_t wishes[] = {
+        base | UFFD_FEATURE_THREAD_ID | UFFD_FEATURE_WP_UNPOPULATED | UFFD_FEATURE_WP_HUGETLBFS_SHMEM,
+        base | UFFD_FEATURE_THREAD_ID | UFFD_FEATURE_WP_UNPOPULATED,
+        base | UFFD_FEATURE_THREAD_ID,
+        base
+    };
+    // FAABRIC_UFFD_FEATURES=basic behaves like an old kernel (tests)
+    const char* limit = ::getenv("FAABRIC_UFFD_FEATURES");
+    const bool basicOnly = limit != nullptr && std::string(limit) == "basic";
+    for (uint64_t features : wishes) {
+        if (basicOnly && features != base) {
+            continue;
+        }
+        int fd = (int)::syscall(SYS_userfaultfd, O_CLOEXEC | O_NONBLOCK);
+        if (fd < 0) {
+            return -1;
+        }
+        uffdio_api api;
+        memset(&api, 0, sizeof(api));
+        api.api = UFFD_API;
+        api.features = features;
+        if (::ioctl(fd, UFFDIO_API, &api) == 0) {
+            if (wpUnpopulated != nullptr) {
+                *wpUnpopulated = (features & UFFD_FEATURE_WP_UNPOPULATED) != 0;
+            }
+            if (threadIds != nullptr) {
+                *threadIds = (features & UFFD_FEATURE_THREAD_ID) != 0;
+            }
+            return fd;
+        }
+        // (a failed handshake leaves the descriptor unusable)
         ::close(fd);
-        return -1;
     }
-    return fd;
+    return -1;
 }
 
 bool UffdDirtyTracker::isSupported()
@@ -585,7 +629,7 @@ UffdDirtyTracker::UffdDirtyTracker(const std::string& modeIn)
   : mode(modeIn)
   , impl(std::make_unique<Impl>())
 {
-    impl->uffd = openUffd();
+    impl->uffd = openUffd(&impl->wpUnpopulated, &impl->threadIds);
     if (impl->uffd < 0) {
         SPDLOG_ERROR("userfaultfd unavailable: {}", strerror(errno));
         throw std::runtime_error("userfaultfd unavailable");
@@ -617,6 +661,7 @@ void UffdDirtyTracker::clearAll()
     std::lock_guard<std::mutex> lk(impl->recordMx);
     globalRecords.clear();
     threadRecord.clear();
+    impl->perThread.clear();
 }
 
 void UffdDirtyTracker::startTracking(std::span<uint8_t> region)
@@ -638,6 +683,16 @@ void UffdDirtyTracker::startTracking(std::span<uint8_t> region)
     if (::ioctl(impl->uffd, UFFDIO_REGISTER, &reg) != 0) {
         SPDLOG_ERROR("uffd register failed: {}", strerror(errno));
         throw std::runtime_error("uffd register failed");
+    }
+    if (!impl->wpUnpopulated) {
+        // Protection only sticks to pages that have a page-table entry: map
+        // the untouched ones (read-only zero pages, nothing is allocated)
+        if (::madvise(region.data(), len, MADV_POPULATE_READ) != 0) {
+            volatile uint8_t sink = 0;
+            for (size_t off = 0; off < len; off += HOST_PAGE_SIZE) {
+                sink = sink + region.data()[off];
+            }
+        }
     }
     uffdio_writeprotect wp;
     wp.range.start = (uintptr_t)region.data();
@@ -666,20 +721,49 @@ std::vector<char> UffdDirtyTracker::getDirtyPages(std::span<uint8_t> region)
     return globalRecords.snapshot(region);
 }
 
-void UffdDirtyTracker::startThreadLocalTracking(std::span<uint8_t> region) {}
+// (this thread's record, kept readable after tracking stops)
+static thread_local std::shared_ptr<TrackingRecord> uffdThreadRecord;
 
-void UffdDirtyTracker::stopThreadLocalTracking(std::span<uint8_t> region) {}
+void UffdDirtyTracker::startThreadLocalTracking(std::span<uint8_t> region)
+{
+    if (!impl->threadIds || region.empty() || region.data() == nullptr) {
+        return;
+    }
+    auto rec = std::make_shared<TrackingRecord>();
+    rec->reset(region);
+    uffdThreadRecord = rec;
+    std::lock_guard<std::mutex> lk(impl->recordMx);
+    impl->perThread[(uint32_t)::syscall(SYS_gettid)] = std::move(rec);
+}
+
+void UffdDirtyTracker::stopThreadLocalTracking(std::span<uint8_t> region)
+{
+    if (!impl->threadIds) {
+        return;
+    }
+    // (a write returns only after the event thread has recorded its fault, so
+    // the record is complete here)
+    std::lock_guard<std::mutex> lk(impl->recordMx);
+    impl->perThread.erase((uint32_t)::syscall(SYS_gettid));
+}
 
 std::vector<char> UffdDirtyTracker::getThreadLocalDirtyPages(
   std::span<uint8_t> region)
 {
-    // Faults are drained by the event thread: attribution is global
-    return std::vector<char>(getRequiredHostPages(region.size()), 0);
+    const size_t want = getRequiredHostPages(region.size());
+    if (uffdThreadRecord != nullptr && uffdThreadRecord->regionBase == region.data()) {
+        return uffdThreadRecord->snapshot(want);
+    }
+    // Without thread ids in fault messages attribution is global
+    return std::vector<char>(want, 0);
 }
 
 std::vector<char> UffdDirtyTracker::getBothDirtyPages(std::span<uint8_t> region)
 {
-    return getDirtyPages(region);
+    std::vector<char> g = getDirtyPages(region);
+    std::vector<char> t = getThreadLocalDirtyPages(region);
+    mergeDirtyPages(g, t);
+    return g;
 }
 
 // ---------------------------------------------------------------------------
