@@ -599,7 +599,11 @@ void MessageEndpointServerHandler::start(int timeoutMs)
                         if (c < 0) {
                             break;
                         }
-                        tcp::setNoDelay(c);
+                        try {
+                            tcp::setNoDelay(c);
+                        } catch (const std::exception&) {
+                            // (a peer that is already gone: the read reports it)
+                        }
                         epoll_event cev;
                         memset(&cev, 0, sizeof(cev));
                         cev.events = EPOLLIN;

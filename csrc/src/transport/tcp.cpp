@@ -23,11 +23,31 @@
 
 namespace faabric::transport::tcp {
 
-static void setOpt(int fd, int level, int name, int value, const char* what)
+// Options throw when they cannot be applied (reference:
+// src/transport/tcp/SocketOptions.cpp does for every one of them).  The two
+// latency hints may be refused by policy in a sandbox (no CAP_NET_ADMIN, a
+// socket family without them): that alone is only logged.
+static void setOpt(int fd, int level, int name, int value, const char* what, bool hint = false)
 {
     if (::setsockopt(fd, level, name, &value, sizeof(value)) != 0) {
-        SPDLOG_WARN("setsockopt {} failed on fd {}: {}", what, fd, strerror(errno));
+        int err = errno;
+        if (hint && (err == EPERM || err == ENOPROTOOPT || err == EOPNOTSUPP)) {
+            SPDLOG_DEBUG("setsockopt {} not applied on fd {}: {}", what, fd, strerror(err));
+            return;
+        }
+        SPDLOG_ERROR("setsockopt {} failed on fd {}: {}", what, fd, strerror(err));
+        throw std::runtime_error(std::string("Error setting socket option: ") + what);
     }
+}
+
+static int getFlags(int fd, const char* why)
+{
+    int flags = ::fcntl(fd, F_GETFL, 0);
+    if (flags < 0) {
+        SPDLOG_ERROR("fcntl(F_GETFL) failed on fd {}: {}", fd, strerror(errno));
+        throw std::runtime_error(std::string("Error ") + why);
+    }
+    return flags;
 }
 
 void setReuseAddr(int fd)
@@ -42,48 +62,51 @@ void setNoDelay(int fd)
 
 void setQuickAck(int fd)
 {
-    setOpt(fd, IPPROTO_TCP, TCP_QUICKACK, 1, "TCP_QUICKACK");
+    setOpt(fd, IPPROTO_TCP, TCP_QUICKACK, 1, "TCP_QUICKACK", true);
 }
 
 void setBusyPolling(int fd)
 {
     // Microseconds to busy poll in the kernel before sleeping
-    setOpt(fd, SOL_SOCKET, SO_BUSY_POLL, 10000, "SO_BUSY_POLL");
+    setOpt(fd, SOL_SOCKET, SO_BUSY_POLL, 10000, "SO_BUSY_POLL", true);
 }
 
 void setNonBlocking(int fd)
 {
-    int flags = ::fcntl(fd, F_GETFL, 0);
+    int flags = getFlags(fd, "setting socket as non-blocking");
     ::fcntl(fd, F_SETFL, flags | O_NONBLOCK);
 }
 
 void setBlocking(int fd)
 {
-    int flags = ::fcntl(fd, F_GETFL, 0);
+    int flags = getFlags(fd, "setting socket as blocking");
     ::fcntl(fd, F_SETFL, flags & ~O_NONBLOCK);
 }
 
 bool isNonBlocking(int fd)
 {
-    return (::fcntl(fd, F_GETFL, 0) & O_NONBLOCK) != 0;
+    return (getFlags(fd, "checking if socket is blocking") & O_NONBLOCK) != 0;
 }
 
-static void setTimeout(int fd, int name, int timeoutMs)
+static void setTimeout(int fd, int name, int timeoutMs, const char* what)
 {
     timeval tv;
     tv.tv_sec = timeoutMs / 1000;
     tv.tv_usec = (timeoutMs % 1000) * 1000;
-    ::setsockopt(fd, SOL_SOCKET, name, &tv, sizeof(tv));
+    if (::setsockopt(fd, SOL_SOCKET, name, &tv, sizeof(tv)) != 0) {
+        SPDLOG_ERROR("setsockopt {} failed on fd {}: {}", what, fd, strerror(errno));
+        throw std::runtime_error(std::string("Error setting ") + what);
+    }
 }
 
 void setRecvTimeoutMs(int fd, int timeoutMs)
 {
-    setTimeout(fd, SO_RCVTIMEO, timeoutMs);
+    setTimeout(fd, SO_RCVTIMEO, timeoutMs, "recv timeout");
 }
 
 void setSendTimeoutMs(int fd, int timeoutMs)
 {
-    setTimeout(fd, SO_SNDTIMEO, timeoutMs);
+    setTimeout(fd, SO_SNDTIMEO, timeoutMs, "send timeout");
 }
 
 void setRecvBufferSize(int fd, size_t bufferSize)
@@ -307,8 +330,14 @@ void RecvSocket::recvOne(int conn, uint8_t* buffer, size_t bufferSize)
                 continue;
             }
             if (errno == EAGAIN || errno == EWOULDBLOCK) {
-                CPU_RELAX();
-                continue;
+                // A non-blocking socket is polled; on a blocking one this is
+                // its receive timeout expiring
+                if ((::fcntl(conn, F_GETFL, 0) & O_NONBLOCK) != 0) {
+                    CPU_RELAX();
+                    continue;
+                }
+                SPDLOG_ERROR("TCP recv on fd {} timed out", conn);
+                throw std::runtime_error("TCP receive timed out");
             }
             SPDLOG_ERROR("TCP recv failed: {}", strerror(errno));
             throw std::runtime_error("Error receiving TCP message");

@@ -143,6 +143,7 @@ TEST_CASE("ptp case: a scheduling decision sets the local mappings and sends the
 {
     PtpCase f;
     faabric::util::setMockMode(true);
+    clearSentMessages();
     const int appId = 1, groupId = 113;
     faabric::batch_scheduler::SchedulingDecision d(appId, groupId);
     d.addMessage(f.thisHost, 101, 0, 0);

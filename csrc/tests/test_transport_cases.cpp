@@ -380,3 +380,125 @@ TEST_CASE("transport case: socket addresses", "[transport][cases]")
     REQUIRE_EQ(any.host(), std::string("0.0.0.0"));
     REQUIRE_THROWS(faabric::transport::tcp::Address("not-an-ip", 1));
 }
+
+// ---- raw TCP sockets (reference: tests/test/transport/test_tcp_sockets.cpp) ----
+#include <faabric/transport/tcp/RecvSocket.h>
+#include <faabric/transport/tcp/SendSocket.h>
+#include <faabric/transport/tcp/SocketOptions.h>
+
+#include <fcntl.h>
+
+namespace {
+const int RAW_PORT = 9977;
+
+// fd numbers are reused quickly: a closed one is recognised by fcntl failing
+bool isClosed(int fd)
+{
+    return ::fcntl(fd, F_GETFD) == -1 && errno == EBADF;
+}
+
+void rawSendRecv(const std::vector<int>& msg, bool sendNothing)
+{
+    namespace tcp = faabric::transport::tcp;
+    tcp::RecvSocket dst(RAW_PORT);
+    auto done = faabric::util::Latch::create(2);
+    std::thread sender([&] {
+        tcp::SendSocket src("127.0.0.1", RAW_PORT);
+        src.dial();
+        if (!sendNothing) {
+            src.sendOne(BYTES_CONST(msg.data()), sizeof(int) * msg.size());
+        }
+        done->wait();
+    });
+    dst.listen();
+    int conn = dst.accept();
+    std::vector<int> actual(msg.size());
+    if (sendNothing) {
+        tcp::setRecvTimeoutMs(conn, 200);
+        REQUIRE_THROWS(dst.recvOne(conn, BYTES(actual.data()), sizeof(int) * actual.size()));
+    } else {
+        tcp::setRecvBufferSize(conn, SocketBufferSizeBytes);
+        dst.recvOne(conn, BYTES(actual.data()), sizeof(int) * actual.size());
+        REQUIRE(actual == msg);
+    }
+    done->wait();
+    sender.join();
+}
+}
+
+TEST_CASE("tcp case: an accepted connection is closed with its receiving socket", "[transport][tcp][cases]")
+{
+    namespace tcp = faabric::transport::tcp;
+    int conn = -1;
+    {
+        tcp::RecvSocket dst(RAW_PORT);
+        std::thread sender([&] {
+            tcp::SendSocket src("127.0.0.1", RAW_PORT);
+            src.dial();
+        });
+        dst.listen();
+        conn = dst.accept();
+        REQUIRE(conn >= 0);
+        REQUIRE(!isClosed(conn));
+        sender.join();
+    }
+    REQUIRE(isClosed(conn));
+}
+
+TEST_CASE("tcp case: every socket option applies to an open connection and throws on a closed one", "[transport][tcp][cases]")
+{
+    namespace tcp = faabric::transport::tcp;
+    auto done = faabric::util::Latch::create(2);
+    int conn = -1;
+    {
+        tcp::RecvSocket dst(RAW_PORT);
+        std::thread sender([&] {
+            tcp::SendSocket src("127.0.0.1", RAW_PORT);
+            src.dial();
+            done->wait();
+        });
+        dst.listen();
+        conn = dst.accept();
+        tcp::setReuseAddr(conn);
+        tcp::setNoDelay(conn);
+        tcp::setQuickAck(conn);
+        tcp::setQuickAck(conn);
+        tcp::setBusyPolling(conn);
+        tcp::setNonBlocking(conn);
+        REQUIRE(tcp::isNonBlocking(conn));
+        tcp::setBlocking(conn);
+        tcp::setRecvTimeoutMs(conn, 5000);
+        tcp::setSendTimeoutMs(conn, 5000);
+        tcp::setRecvBufferSize(conn, SocketBufferSizeBytes);
+        tcp::setSendBufferSize(conn, SocketBufferSizeBytes);
+        REQUIRE(!tcp::isNonBlocking(conn));
+        done->wait();
+        sender.join();
+    }
+    REQUIRE(isClosed(conn));
+    REQUIRE_THROWS(tcp::setReuseAddr(conn));
+    REQUIRE_THROWS(tcp::setNoDelay(conn));
+    REQUIRE_THROWS(tcp::setQuickAck(conn));
+    REQUIRE_THROWS(tcp::setBusyPolling(conn));
+    REQUIRE_THROWS(tcp::setNonBlocking(conn));
+    REQUIRE_THROWS(tcp::setBlocking(conn));
+    REQUIRE_THROWS(tcp::setRecvTimeoutMs(conn, 5000));
+    REQUIRE_THROWS(tcp::setSendTimeoutMs(conn, 5000));
+    REQUIRE_THROWS(tcp::setRecvBufferSize(conn, SocketBufferSizeBytes));
+    REQUIRE_THROWS(tcp::setSendBufferSize(conn, SocketBufferSizeBytes));
+}
+
+TEST_CASE("tcp case: one small message over raw sockets", "[transport][tcp][cases]")
+{
+    rawSendRecv(std::vector<int>(3, 2), false);
+}
+
+TEST_CASE("tcp case: one large message over raw sockets", "[transport][tcp][cases]")
+{
+    rawSendRecv(std::vector<int>(300, 200), false);
+}
+
+TEST_CASE("tcp case: receiving times out when nothing is sent", "[transport][tcp][cases]")
+{
+    rawSendRecv(std::vector<int>(3, 2), true);
+}
