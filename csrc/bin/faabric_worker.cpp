@@ -203,6 +203,70 @@ static void registerFunctions()
         return 0;
     };
 
+    // Repeated fork-join with two Sum reductions (one sharing a page with a
+    // per-thread array) across whatever hosts the threads land on; checks that
+    // snapshots stay in step over many rounds
+    // (reference dist test "Check repeated reduction",
+    // tests/dist/scheduler/functions.cpp:201-360)
+    functions()["demo/reduction"] = [](faabric::Message& msg) {
+        auto ctx = ExecutorContext::get();
+        auto* exec = ctx->getExecutor();
+        auto mem = exec->getMemoryView();
+        const size_t page = faabric::util::HOST_PAGE_SIZE;
+        int32_t* reductionA = (int32_t*)(mem.data() + page);
+        int32_t* reductionB = (int32_t*)(mem.data() + 2 * page);
+        int32_t* array = (int32_t*)(mem.data() + page + 10 * sizeof(int32_t));
+        const int nThreads = 4;
+        if (ctx->getBatchRequest()->type() == faabric::BatchExecuteRequest::THREADS) {
+            int idx = msg.appidx();
+            // threads sharing an executor's memory take turns
+            auto group = faabric::transport::PointToPointGroup::getGroup(msg.groupid());
+            group->localLock();
+            *reductionA += 10;
+            *reductionB += 20;
+            array[idx] = idx * 30;
+            group->localUnlock();
+            msg.set_outputdata("thread " + std::to_string(idx) + " on " + faabric::scheduler::getScheduler().getThisHost());
+            return 0;
+        }
+        const int nRepeats = msg.inputdata().empty() ? 20 : std::stoi(msg.inputdata());
+        for (int r = 0; r < nRepeats; r++) {
+            auto threads = faabric::util::batchExecFactory(msg.user(), msg.function(), nThreads);
+            faabric::util::updateBatchExecAppId(threads, msg.appid());
+            for (int i = 0; i < nThreads; i++) {
+                threads->mutable_messages(i)->set_appidx(i);
+                threads->mutable_messages(i)->set_groupidx(i);
+            }
+            std::vector<faabric::util::SnapshotMergeRegion> regions = {
+                { (uint32_t)page, sizeof(int32_t), faabric::util::SnapshotDataType::Int, faabric::util::SnapshotMergeOperation::Sum },
+                { (uint32_t)(2 * page), sizeof(int32_t), faabric::util::SnapshotDataType::Int, faabric::util::SnapshotMergeOperation::Sum }
+            };
+            auto results = exec->executeThreads(threads, regions);
+            for (auto& [id, rv] : results) {
+                if (rv != 0) {
+                    msg.set_outputdata("round " + std::to_string(r) + ": thread " + std::to_string(id) + " returned " + std::to_string(rv));
+                    return 1;
+                }
+            }
+            int expectedA = (r + 1) * nThreads * 10, expectedB = (r + 1) * nThreads * 20;
+            if (*reductionA != expectedA || *reductionB != expectedB) {
+                msg.set_outputdata("round " + std::to_string(r) + ": reductions " + std::to_string(*reductionA) + " / " +
+                                   std::to_string(*reductionB) + ", expected " + std::to_string(expectedA) + " / " +
+                                   std::to_string(expectedB));
+                return 1;
+            }
+            for (int i = 0; i < nThreads; i++) {
+                if (array[i] != i * 30) {
+                    msg.set_outputdata("round " + std::to_string(r) + ": array[" + std::to_string(i) + "] = " + std::to_string(array[i]));
+                    return 1;
+                }
+            }
+        }
+        msg.set_outputdata("reduced " + std::to_string(nRepeats) + " rounds to " + std::to_string(*reductionA) + " / " +
+                           std::to_string(*reductionB));
+        return 0;
+    };
+
     mpiFunction("helloworld", [](int rank, int size, faabric::Message& msg) {
         char name[MPI_MAX_PROCESSOR_NAME];
         int len = 0;

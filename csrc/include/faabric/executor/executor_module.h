@@ -47,6 +47,8 @@ class ExecutorTask
     // Run by the pool thread before the task itself: the scheduler uses it to
     // spread the launch of a wide batch over the threads it has already woken
     std::function<void()> prelude;
+    // False for a thread that had to share an already busy pool thread
+    bool ownsPoolThread = true;
 };
 
 }
@@ -225,7 +227,9 @@ class Executor : public std::enable_shared_from_this<Executor>
 
     std::atomic<int> threadBatchCounter = 0;
 
-    faabric::util::TimePoint lastExec;
+    // (steady-clock nanoseconds; written by pool threads, read by the reaper)
+    std::atomic<int64_t> lastExecNs{ 0 };
+    void touchLastExec();
 
     // ---- Application threads ----
     std::shared_mutex threadExecutionMutex;
@@ -237,6 +241,10 @@ class Executor : public std::enable_shared_from_this<Executor>
     std::mutex threadsMutex;
     std::vector<std::shared_ptr<std::jthread>> threadPoolThreads;
     std::set<int> availablePoolThreads;
+    // Pool threads running a function (which may block on its own threads):
+    // never shared with thread tasks when the pool is oversubscribed
+    std::set<int> functionPoolThreads;
+    int overloadCursor = 0;
 
     std::vector<faabric::util::Queue<ExecutorTask>> threadTaskQueues;
 

@@ -77,10 +77,11 @@ class FaabricEndpoint
 
     void stop();
 
-    int getPort() const { return port; }
+    int getPort() const { return port.load(); }
 
   private:
-    int port;
+    // (read by other threads while start() is binding an ephemeral port)
+    std::atomic<int> port;
     int threadCount;
     std::shared_ptr<HttpRequestHandler> requestHandler;
     struct Impl;
@@ -415,8 +416,6 @@ class PlannerClient final : public faabric::transport::MessageEndpointClient
     // onlyIfAwaited: deliver only to a wait that is already registered (the
     // planner's notifications, which are always answers to one)
     void setMessageResultLocally(std::shared_ptr<faabric::Message> msg, bool onlyIfAwaited = false);
-    // Drops a locally delivered result nobody is going to wait for
-    void forgetMessageResult(uint32_t msgId);
 
     faabric::Message getMessageResult(int appId, int msgId, int timeoutMs);
 

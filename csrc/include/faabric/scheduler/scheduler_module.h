@@ -277,8 +277,6 @@ class Scheduler
 
     faabric::snapshot::SnapshotRegistry& reg;
 
-    std::unordered_map<uint32_t, std::promise<int32_t>> threadResults;
-    std::unordered_map<uint32_t, std::shared_future<int32_t>> threadFutures;
     std::unordered_map<uint32_t, faabric::transport::Message>
       threadResultMessages;
     std::mutex threadResultsMx;

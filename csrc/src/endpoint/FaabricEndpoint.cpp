@@ -235,11 +235,11 @@ void FaabricEndpoint::start(EndpointMode mode)
     sockaddr_in addr{};
     addr.sin_family = AF_INET;
     addr.sin_addr.s_addr = htonl(INADDR_ANY);
-    addr.sin_port = htons((uint16_t)port);
+    addr.sin_port = htons((uint16_t)port.load());
     if (::bind(fd, (sockaddr*)&addr, sizeof(addr)) != 0 || ::listen(fd, 1024) != 0) {
         ::close(fd);
         impl->running = false;
-        throw std::runtime_error("Endpoint could not bind to port " + std::to_string(port) + ": " + strerror(errno));
+        throw std::runtime_error("Endpoint could not bind to port " + std::to_string(port.load()) + ": " + strerror(errno));
     }
     if (port == 0) {
         socklen_t len = sizeof(addr);
@@ -247,7 +247,7 @@ void FaabricEndpoint::start(EndpointMode mode)
         port = ntohs(addr.sin_port);
     }
     impl->listenFd = fd;
-    SPDLOG_INFO("Starting HTTP endpoint on {}, {} threads", port, threadCount);
+    SPDLOG_INFO("Starting HTTP endpoint on {}, {} threads", port.load(), threadCount);
 
     Impl* im = impl.get();
     auto handler = requestHandler;
@@ -313,7 +313,7 @@ void FaabricEndpoint::stop()
     if (!impl || !impl->running.exchange(false)) {
         return;
     }
-    SPDLOG_DEBUG("Shutting down endpoint on {}", port);
+    SPDLOG_DEBUG("Shutting down endpoint on {}", port.load());
     if (impl->acceptor.joinable()) {
         impl->acceptor.join();
     }

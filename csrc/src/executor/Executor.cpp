@@ -113,7 +113,7 @@ Executor::Executor(faabric::Message& msg)
     faabric::util::SystemConfig& conf = faabric::util::getSystemConfig();
     // Unique id: host, function, counter
     id = conf.endpointHost + "_" + std::to_string(faabric::util::generateGid());
-    lastExec = faabric::util::getGlobalClock().now();
+    touchLastExec();
     for (uint32_t i = 0; i < threadPoolSize; i++) {
         availablePoolThreads.insert((int)i);
     }
@@ -224,10 +224,21 @@ bool Executor::isExecuting()
     return claimed.load();
 }
 
+static int64_t steadyNowNs()
+{
+    return (int64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             faabric::util::getGlobalClock().now().time_since_epoch())
+      .count();
+}
+
+void Executor::touchLastExec()
+{
+    lastExecNs.store(steadyNowNs(), std::memory_order_relaxed);
+}
+
 long Executor::getMillisSinceLastExec()
 {
-    auto now = faabric::util::getGlobalClock().now();
-    return faabric::util::getGlobalClock().timeDiff(now, lastExec);
+    return (long)((steadyNowNs() - lastExecNs.load(std::memory_order_relaxed)) / 1000000);
 }
 
 namespace {
@@ -559,7 +570,7 @@ void Executor::executeTasks(std::vector<int> msgIdxs,
                             std::function<void()> prelude)
 {
     const int nMessages = (int)msgIdxs.size();
-    lastExec = faabric::util::getGlobalClock().now();
+    touchLastExec();
     faabric::Message& first = *req->mutable_messages(msgIdxs.at(0));
     const bool isThreads = req->type() == faabric::BatchExecuteRequest::THREADS;
     const bool isSingleHost = req->singlehost();
@@ -600,21 +611,39 @@ void Executor::executeTasks(std::vector<int> msgIdxs,
     }
 
     for (int msgIdx : msgIdxs) {
-        const faabric::Message& msg = req->messages(msgIdx);
-        int poolIdx;
-        if (isThreads) {
-            // Threads with the same app idx always share a pool thread
-            poolIdx = msg.appidx() % (int)threadPoolSize;
-        } else {
+        int poolIdx = -1;
+        bool ownsPoolThread = true;
+        {
+            // Functions and threads alike take a free pool thread (reference:
+            // src/executor/Executor.cpp:182-203).  A thread must never queue
+            // behind the function that forked it - that function is waiting
+            // for it - so when the pool is oversubscribed (more threads than
+            // cores) threads double up on pool threads that run threads only.
             std::lock_guard<std::mutex> lk(threadsMutex);
-            if (availablePoolThreads.empty()) {
+            if (!availablePoolThreads.empty()) {
+                poolIdx = *availablePoolThreads.begin();
+                availablePoolThreads.erase(availablePoolThreads.begin());
+            } else if (isThreads) {
+                ownsPoolThread = false;
+                for (size_t k = 0; k < threadPoolSize; k++) {
+                    int candidate = (int)((overloadCursor + k) % threadPoolSize);
+                    if (functionPoolThreads.count(candidate) == 0) {
+                        poolIdx = candidate;
+                        overloadCursor = candidate + 1;
+                        break;
+                    }
+                }
+            }
+            if (poolIdx < 0) {
                 SPDLOG_ERROR("No available thread pool threads (size: {})", threadPoolSize);
                 throw std::runtime_error("No available thread pool threads!");
             }
-            poolIdx = *availablePoolThreads.begin();
-            availablePoolThreads.erase(availablePoolThreads.begin());
+            if (!isThreads) {
+                functionPoolThreads.insert(poolIdx);
+            }
         }
         ExecutorTask task(msgIdx, req);
+        task.ownsPoolThread = ownsPoolThread;
         if (prelude) {
             task.prelude = std::move(prelude);
             prelude = nullptr;
@@ -761,13 +790,14 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
     SPDLOG_DEBUG("Thread pool thread {}:{} starting up", id, threadPoolIdx);
     auto& sch = faabric::scheduler::getScheduler();
     faabric::transport::PointToPointBroker& broker = faabric::transport::getPointToPointBroker();
-    const auto& conf = faabric::util::getSystemConfig();
+    // (read once: tests reset the configuration while pool threads idle)
+    const int boundTimeout = faabric::util::getSystemConfig().boundTimeout;
     faabric::util::bindThreadToGpu(gpuIdx);
 
     while (!st.stop_requested()) {
         ExecutorTask task;
         try {
-            task = threadTaskQueues[threadPoolIdx].dequeue(conf.boundTimeout);
+            task = threadTaskQueues[threadPoolIdx].dequeue(boundTimeout);
         } catch (const faabric::util::QueueTimeoutException&) {
             // Nothing to do for a while: keep waiting, the reaper decides
             // when the whole executor goes away
@@ -877,13 +907,14 @@ void Executor::threadPoolThread(std::stop_token st, int threadPoolIdx)
                     SPDLOG_ERROR("Error resetting executor {}: {}", id, ex.what());
                 }
             }
-            lastExec = faabric::util::getGlobalClock().now();
+            touchLastExec();
             currentAppId.store(0);
             releaseClaim();
         }
-        if (!isThreads) {
+        if (task.ownsPoolThread) {
             std::lock_guard<std::mutex> lk(threadsMutex);
             availablePoolThreads.insert(threadPoolIdx);
+            functionPoolThreads.erase(threadPoolIdx);
         }
 
         msg.set_finishtimestamp(faabric::util::getGlobalClock().epochMillis());

@@ -205,12 +205,6 @@ void PlannerClient::setMessageResultLocally(std::shared_ptr<faabric::Message> ms
     }
 }
 
-void PlannerClient::forgetMessageResult(uint32_t msgId)
-{
-    std::lock_guard<std::mutex> lk(sharedCacheMx);
-    sharedCache.plannerResults.erase(msgId);
-}
-
 faabric::Message PlannerClient::getMessageResult(int appId, int msgId, int timeoutMs)
 {
     auto msgPtr = std::make_shared<faabric::Message>();
@@ -249,7 +243,17 @@ faabric::Message PlannerClient::doGetMessageResult(std::shared_ptr<faabric::Mess
             // instead of sharing the future
         }
     }
-    syncSend(PlannerCalls::GetMessageResult, msgPtr.get(), &resp);
+    if (plannerIsInProcess(host)) {
+        // (no RPC to ourselves: fork-joins ask once per thread)
+        auto direct = faabric::planner::getPlanner().getMessageResult(msgPtr);
+        if (direct != nullptr) {
+            resp = *direct;
+        } else {
+            resp.set_type(faabric::Message::EMPTY);
+        }
+    } else {
+        syncSend(PlannerCalls::GetMessageResult, msgPtr.get(), &resp);
+    }
     bool ready = resp.id() == msgId && (resp.type() != faabric::Message::EMPTY);
     if (ready) {
         std::lock_guard<std::mutex> lk(sharedCacheMx);

@@ -116,7 +116,10 @@ void FunctionCallClient::executeFunctions(std::shared_ptr<faabric::BatchExecuteR
     if (!faabric::util::FaultInjector::get().armed()) {
         if (auto* local = faabric::transport::MessageEndpointServer::localServerFor(host, FUNCTION_CALL_ASYNC_PORT, false)) {
             // Same process (a worker serving this - possibly virtual - host):
-            // hand the request object to the server's workers as it is
+            // hand the request object to the server's workers as it is.  The
+            // executing side stamps and fills its messages, so the caller
+            // must not touch the request afterwards (over TCP it would have
+            // been serialised; the planner dispatches copies of its own)
             std::string target = host;
             local->getAsyncHandler()->deliverLocalTask([req, target] {
                 auto& sch = faabric::scheduler::getScheduler();
@@ -140,6 +143,13 @@ void FunctionCallClient::setMessageResult(std::shared_ptr<faabric::Message> msg)
     if (faabric::util::isMockMode()) {
         std::lock_guard<std::mutex> lk(mockMutex);
         messageResults.emplace_back(host, msg);
+        return;
+    }
+    if (!faabric::util::FaultInjector::get().armed() &&
+        faabric::transport::MessageEndpointServer::localServerFor(host, FUNCTION_CALL_ASYNC_PORT, false) != nullptr) {
+        // The waiter lives in this process: fulfil its promise here (a mutex
+        // and a wake-up; nothing to serialise, no worker thread in between)
+        faabric::planner::getPlannerClient().setMessageResultLocally(msg, true);
         return;
     }
     asyncSend(FunctionCalls::SetMessageResult, msg.get());

@@ -137,8 +137,6 @@ void Scheduler::reset()
     }
     {
         std::lock_guard<std::mutex> lk(threadResultsMx);
-        threadResults.clear();
-        threadFutures.clear();
         threadResultMessages.clear();
     }
     {
@@ -443,29 +441,15 @@ void Scheduler::setThreadResultLocally(uint32_t appId,
                                        int32_t returnValue,
                                        faabric::transport::Message& message)
 {
-    std::lock_guard<std::mutex> lk(threadResultsMx);
     // Diffs attached to the result point into the transport message: keep it
-    // (a borrowed in-process view must first take a copy)
+    // (a borrowed in-process view must first take a copy).  The result itself
+    // reaches whoever awaits the thread through the planner, never from here:
+    // the planner releases the thread's slot before it answers, so a function
+    // that forks again right after the join finds its slots free
+    // (reference: src/scheduler/Scheduler.cpp:395-421)
+    std::lock_guard<std::mutex> lk(threadResultsMx);
     message.ensureOwned();
     threadResultMessages.insert_or_assign(msgId, std::move(message));
-    auto it = threadResults.find(msgId);
-    if (it == threadResults.end()) {
-        it = threadResults.emplace(msgId, std::promise<int32_t>()).first;
-        threadFutures.emplace(msgId, it->second.get_future().share());
-    }
-    try {
-        it->second.set_value(returnValue);
-    } catch (const std::future_error&) {
-        SPDLOG_WARN("Thread result for {} set twice", msgId);
-    }
-    // Somebody may already be blocked on the planner for this thread: the
-    // pushed result resolves that wait too (reference:
-    // src/scheduler/Scheduler.cpp setThreadResultLocally does the same)
-    auto asMessage = std::make_shared<faabric::Message>();
-    asMessage->set_appid((int)appId);
-    asMessage->set_id((int)msgId);
-    asMessage->set_returnvalue(returnValue);
-    faabric::planner::getPlannerClient().setMessageResultLocally(asMessage);
 }
 
 std::vector<std::pair<uint32_t, int32_t>> Scheduler::awaitThreadResults(
@@ -476,22 +460,6 @@ std::vector<std::pair<uint32_t, int32_t>> Scheduler::awaitThreadResults(
     results.reserve(req->messages_size());
     for (int i = 0; i < req->messages_size(); i++) {
         uint32_t msgId = (uint32_t)req->messages(i).id();
-        // Prefer a result that was pushed to us directly (remote threads)
-        std::shared_future<int32_t> fut;
-        bool local = false;
-        {
-            std::lock_guard<std::mutex> lk(threadResultsMx);
-            auto it = threadFutures.find(msgId);
-            if (it != threadFutures.end()) {
-                fut = it->second;
-                local = true;
-            }
-        }
-        if (local && fut.wait_for(std::chrono::milliseconds(0)) == std::future_status::ready) {
-            results.emplace_back(msgId, fut.get());
-            faabric::planner::getPlannerClient().forgetMessageResult(msgId);
-            continue;
-        }
         faabric::Message res = faabric::planner::getPlannerClient().getMessageResult(
           req->appid(), (int)msgId, timeoutMs);
         results.emplace_back(msgId, res.returnvalue());

@@ -77,8 +77,11 @@ TEST_CASE("scheduler case: a batch sent through the function call client runs ev
     res.set_usedslots(nCalls);
     f.sch.setThisHostResources(res);
     f.sch.addHostToGlobalSet();
+    // (a request handed to a host in this process is not copied: from here on
+    // it belongs to the executing side)
+    std::vector<faabric::Message> sent(req->messages().begin(), req->messages().end());
     faabric::scheduler::getFunctionCallClient(f.conf.endpointHost)->executeFunctions(req);
-    for (const auto& m : req->messages()) {
+    for (const auto& m : sent) {
         REQUIRE_EQ(f.awaitResult(m, 5000).returnvalue(), 0);
     }
     REQUIRE_EQ((int)f.sch.getRecordedMessages().size(), nCalls);

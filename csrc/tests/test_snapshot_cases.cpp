@@ -178,7 +178,7 @@ TEST_CASE("snapshot case: integer max diffs, with and without a change", "[snaps
     mergeOpCase(SnapshotMergeOperation::Max, 20, 10, 20);
 }
 
-TEST_CASE("snapshot case: a thread result resolves whoever awaits that thread, with or without diffs", "[snapshot][cases]")
+TEST_CASE("snapshot case: pushed thread results queue their diffs, the planner resolves whoever awaits the threads", "[snapshot][cases]")
 {
     SnapCase f;
     auto reqA = faabric::util::batchExecFactory("demo", "thr", 2);
@@ -196,6 +196,20 @@ TEST_CASE("snapshot case: a thread result resolves whoever awaits that thread, w
     });
     f.cli.pushThreadResult(reqA->appid(), idA, 333, "", {});
     f.cli.pushThreadResult(reqA->appid(), idB, 444, key, diffs);
+    // the pushed results carry the diffs; the return values travel through the
+    // planner (which must see the slots of the threads as used)
+    faabric::HostResources res;
+    res.set_slots(2);
+    res.set_usedslots(2);
+    f.sch.setThisHostResources(res);
+    for (auto [id, rv] : { std::pair<uint32_t, int>{ idA, 333 }, std::pair<uint32_t, int>{ idB, 444 } }) {
+        auto result = std::make_shared<faabric::Message>();
+        result->set_appid(reqA->appid());
+        result->set_id((int)id);
+        result->set_returnvalue(rv);
+        result->set_executedhost(f.conf.endpointHost);
+        f.plannerCli.setMessageResult(result);
+    }
     waiter.join();
     REQUIRE_EQ(gotA.load(), 333);
     REQUIRE_EQ(gotB.load(), 444);

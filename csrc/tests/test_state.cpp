@@ -392,13 +392,24 @@ TEST_CASE("snapshots: push, update, thread results, delete over RPC", "[snapshot
     REQUIRE_EQ(faabric::util::unalignedRead<int>(received->getDataPtr(64)), 0x01010101 + 5);
     REQUIRE_EQ(received->getMergeRegions().size(), 0u);
 
-    // Thread results queue their diffs and resolve the waiting future
+    // Thread results queue their diffs; the return value reaches the waiter
+    // through the planner
     auto threadReq = faabric::util::batchExecFactory("demo", "thr", 1);
     uint32_t msgId = threadReq->messages(0).id();
     std::vector<faabric::util::SnapshotDiff> threadDiffs;
     threadDiffs.emplace_back(faabric::util::SnapshotDataType::Raw, faabric::util::SnapshotMergeOperation::Bytewise, 2000, bytes);
     cli.pushThreadResult(threadReq->appid(), msgId, 42, "snapA", threadDiffs);
     REQUIRE_EQ(received->getQueuedDiffsCount(), 1u);
+    {
+        faabric::HostResources res;
+        res.set_slots(2);
+        res.set_usedslots(1);
+        f.sch.setThisHostResources(res);
+        auto viaPlanner = std::make_shared<faabric::Message>(threadReq->messages(0));
+        viaPlanner->set_returnvalue(42);
+        viaPlanner->set_executedhost(f.conf.endpointHost);
+        f.plannerCli.setMessageResult(viaPlanner);
+    }
     auto results = f.sch.awaitThreadResults(threadReq, 2000);
     REQUIRE_EQ(results.size(), 1u);
     REQUIRE_EQ(results[0].first, msgId);

@@ -346,6 +346,21 @@ def test_threads_fork_join_across_workers(tmp_path):
         assert thread_hosts == set(c.worker_hosts()), res
 
 
+def test_repeated_reduction_across_workers(tmp_path):
+    """The reference's "repeated reduction" dist test: 20 rounds of a 4-thread
+    fork-join spanning two worker processes, two Sum-merged counters (one on the
+    page the threads also write an array to) checked after every round."""
+    with LocalCluster(n_workers=2, slots_per_worker=3, log_dir=tmp_path) as c:
+        st = c.client.invoke("demo", "reduction", input_data="20", timeout=120)
+        res = st["messageResults"]
+        main = [m for m in res if m.get("output_data", "").startswith(("reduced", "round"))]
+        assert len(main) == 1, res
+        assert main[0]["output_data"] == "reduced 20 rounds to 800 / 1600", main[0]
+        assert main[0].get("returnValue", 0) == 0
+        thread_hosts = {m["output_data"].split()[-1] for m in res if m.get("output_data", "").startswith("thread")}
+        assert thread_hosts == set(c.worker_hosts()), res
+
+
 def test_exec_graph_and_policy(cluster):
     batch = cluster.client.make_batch("demo", "echo", input_data="g", record_exec_graph=True)
     cluster.client.execute_batch(batch)
