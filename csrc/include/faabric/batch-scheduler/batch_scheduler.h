@@ -27,6 +27,41 @@
 
 namespace faabric::batch_scheduler {
 
+// Legacy placement hints and migration strategies: the planner's policies
+// (bin-pack / compact / spot) replaced them, the names stay for embedders that
+// still pass them around (reference: include/faabric/batch-scheduler/
+// SchedulingDecision.h:9-56)
+enum SchedulingTopologyHint
+{
+    NONE,
+    CACHED,
+    FORCE_LOCAL,
+    NEVER_ALONE,
+    UNDERFULL,
+};
+
+const std::unordered_map<std::string, SchedulingTopologyHint> strToTopologyHint = {
+    { "NONE", SchedulingTopologyHint::NONE },
+    { "CACHED", SchedulingTopologyHint::CACHED },
+    { "FORCE_LOCAL", SchedulingTopologyHint::FORCE_LOCAL },
+    { "NEVER_ALONE", SchedulingTopologyHint::NEVER_ALONE },
+    { "UNDERFULL", SchedulingTopologyHint::UNDERFULL },
+};
+
+const std::unordered_map<SchedulingTopologyHint, std::string> topologyHintToStr = {
+    { SchedulingTopologyHint::NONE, "NONE" },
+    { SchedulingTopologyHint::CACHED, "CACHED" },
+    { SchedulingTopologyHint::FORCE_LOCAL, "FORCE_LOCAL" },
+    { SchedulingTopologyHint::NEVER_ALONE, "NEVER_ALONE" },
+    { SchedulingTopologyHint::UNDERFULL, "UNDERFULL" },
+};
+
+enum MigrationStrategy
+{
+    BIN_PACK,
+    EMPTY_HOSTS
+};
+
 class SchedulingDecision
 {
   public:

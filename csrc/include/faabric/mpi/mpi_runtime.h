@@ -106,6 +106,8 @@ void parseMpiMsg(const std::vector<uint8_t>& bytes, MpiMessage* msg);
 
 
 // Exec-graph detail keys (reference: include/faabric/mpi/MpiWorld.h:13-18)
+// (how many counters a plain send adds to a recording message)
+#define NUM_MPI_EXEC_GRAPH_DETAILS 2
 #define MPI_MSG_COUNT_PREFIX "mpi-msgcount-torank"
 #define MPI_MSGTYPE_COUNT_PREFIX "mpi-msgtype-torank"
 

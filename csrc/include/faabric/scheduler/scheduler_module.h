@@ -209,6 +209,10 @@ class Scheduler
       int overwriteNewGroupId = 0);
 
     // Idle-executor reaping, returns how many were reaped
+    // Deletes a snapshot on every other host registered with the planner
+    // (declared by the reference, include/faabric/scheduler/Scheduler.h:51)
+    void broadcastSnapshotDelete(const faabric::Message& msg, const std::string& snapshotKey);
+
     int reapStaleExecutors();
 
     // Called by an executor when it becomes claimable again

@@ -274,6 +274,10 @@ class StateKeyValueException : public faabric::util::FaabricException
     {}
 };
 
+// Remote lock acquisition: time per attempt and attempts before giving up
+constexpr int REMOTE_LOCK_TIMEOUT_SECS(1);
+constexpr int REMOTE_LOCK_MAX_RETRIES(100);
+
 class StateKeyValue
 {
   public:

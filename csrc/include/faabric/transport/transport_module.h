@@ -1100,17 +1100,20 @@ class PointToPointServer final : public MessageEndpointServer
 // Well-known ports (reference: include/faabric/transport/common.h:9-29).  With
 // one worker process per GPU on a box, FAABRIC_PORT_OFFSET shifts the whole
 // block so workers do not collide.
-#define DEFAULT_STATE_HOST "0.0.0.0"
+#ifndef ANY_HOST
+#define ANY_HOST "0.0.0.0"
+#endif
+#define DEFAULT_STATE_HOST ANY_HOST
 #define STATE_ASYNC_PORT 8003
 #define STATE_SYNC_PORT 8004
 #define STATE_INPROC_LABEL "state"
 
-#define DEFAULT_FUNCTION_CALL_HOST "0.0.0.0"
+#define DEFAULT_FUNCTION_CALL_HOST ANY_HOST
 #define FUNCTION_CALL_ASYNC_PORT 8005
 #define FUNCTION_CALL_SYNC_PORT 8006
 #define FUNCTION_INPROC_LABEL "function"
 
-#define DEFAULT_SNAPSHOT_HOST "0.0.0.0"
+#define DEFAULT_SNAPSHOT_HOST ANY_HOST
 #define SNAPSHOT_ASYNC_PORT 8007
 #define SNAPSHOT_SYNC_PORT 8008
 #define SNAPSHOT_INPROC_LABEL "snapshot"

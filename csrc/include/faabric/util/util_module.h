@@ -135,6 +135,8 @@ void incrementCounter(faabric::Message& msg, const std::string& key, int valueTo
 namespace faabric::util {
 
 // Runs doWork() every `intervalSeconds` on its own thread until stop()
+#define DEFAULT_BACKGROUND_INTERVAL_SECONDS 30
+
 class PeriodicBackgroundThread
 {
   public:
@@ -1373,6 +1375,10 @@ void logFmt(LogLevel level, std::string_view f, const Args&... args)
 #define BYTES(arr) reinterpret_cast<uint8_t*>(arr)
 #define BYTES_CONST(arr) reinterpret_cast<const uint8_t*>(arr)
 #define UNUSED(x) (void)(x)
+
+#ifndef SLEEP_MS
+#define SLEEP_MS(ms) usleep((ms) * 1000)
+#endif
 
 // Symbol visibility helper for the few things looked up by dlsym / ctypes
 #define FAABRIC_EXPORT __attribute__((visibility("default")))

@@ -261,6 +261,20 @@ MpiWorld::MpiWorld()
 
 MpiWorld::~MpiWorld()
 {
+    // Messages nobody received own their payloads
+    for (auto& q : localQueues) {
+        if (q == nullptr) {
+            continue;
+        }
+        while (q->size() > 0) {
+            MpiMessage m{};
+            m.buffer = nullptr;
+            q->dequeueIfPresent(&m);
+            if (m.buffer != nullptr) {
+                free(m.buffer);
+            }
+        }
+    }
     for (void* s : deviceStreams) {
         if (s != nullptr) {
             cudaStreamDestroy((cudaStream_t)s);

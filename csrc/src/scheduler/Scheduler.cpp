@@ -3,6 +3,7 @@
 #include <faabric/executor/ExecutorFactory.h>
 #include <faabric/scheduler/FunctionCallClient.h>
 #include <faabric/scheduler/Scheduler.h>
+#include <faabric/snapshot/SnapshotClient.h>
 #include <faabric/transport/common.h>
 #include <faabric/util/batch.h>
 #include <faabric/util/environment.h>
@@ -430,6 +431,16 @@ void Scheduler::executeBatch(std::shared_ptr<faabric::BatchExecuteRequest> req)
         m->set_returnvalue(1);
         m->set_outputdata("Failed to claim executor: " + failure);
         faabric::planner::getPlannerClient().setMessageResult(m);
+    }
+}
+
+void Scheduler::broadcastSnapshotDelete(const faabric::Message& msg, const std::string& snapshotKey)
+{
+    for (const auto& host : faabric::planner::getPlannerClient().getAvailableHosts()) {
+        if (host.ip() == thisHost || host.ip() == msg.mainhost()) {
+            continue;
+        }
+        faabric::snapshot::getSnapshotClient(host.ip())->deleteSnapshot(snapshotKey);
     }
 }
 

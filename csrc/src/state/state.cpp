@@ -25,8 +25,6 @@
 
 #define ONES_BITMASK 0b11111111
 #define ZERO_BITMASK 0b00000000
-#define REMOTE_LOCK_TIMEOUT_SECS 1
-#define REMOTE_LOCK_MAX_RETRIES 10
 #define MAIN_KEY_PREFIX "main_"
 
 namespace faabric::state {
@@ -594,7 +592,7 @@ uint32_t StateKeyValue::waitOnRedisRemoteLock(const std::string& redisKey)
     while (lockId == 0) {
         std::this_thread::sleep_for(std::chrono::milliseconds(1));
         lockId = redis.acquireLock(redisKey, REMOTE_LOCK_TIMEOUT_SECS);
-        if (++retries >= REMOTE_LOCK_MAX_RETRIES * 1000) {
+        if (++retries >= REMOTE_LOCK_MAX_RETRIES * 100) {
             SPDLOG_ERROR("Timed out waiting for lock on {}", redisKey);
             break;
         }

@@ -261,8 +261,8 @@ TEST_CASE("executor: claims, chained messages and pool limits", "[executor]")
     REQUIRE_EQ(exec->getMemoryView().size(), before + faabric::util::HOST_PAGE_SIZE);
     REQUIRE(exec->getMaxMemorySize() >= exec->getMemoryView().size());
 
-    // More concurrent functions than pool threads cannot be placed (threads
-    // of one app share pool threads by app idx instead)
+    // More concurrent functions than pool threads cannot be placed (only
+    // threads may double up, on pool threads that run threads)
     int pool = faabric::util::getUsableCores();
     std::atomic<bool> release{ false };
     std::atomic<int> held{ 0 };

@@ -5,6 +5,8 @@
 
 #include <faabric/scheduler/FunctionCallClient.h>
 #include <faabric/scheduler/FunctionCallServer.h>
+#include <faabric/mpi/MpiWorld.h>
+#include <faabric/util/PeriodicBackgroundThread.h>
 #include <faabric/snapshot/SnapshotClient.h>
 #include <faabric/state/State.h>
 #include <faabric/transport/PointToPointBroker.h>
@@ -311,4 +313,44 @@ TEST_CASE("scheduler case: a transport message cached with a thread result outli
     }
     REQUIRE_EQ(f.sch.getCachedMessageCount(), 1u);
     REQUIRE(data[0] == 1 && data[1] == 2 && data[2] == 3);
+}
+
+TEST_CASE("scheduler case: a snapshot deletion is broadcast to every other host", "[scheduler][cases]")
+{
+    ClusterFixture f(2);
+    faabric::util::setMockMode(true);
+    faabric::snapshot::clearMockSnapshotRequests();
+    for (const char* ip : { "10.0.0.7", "10.0.0.8" }) {
+        auto res = std::make_shared<faabric::HostResources>();
+        res->set_slots(1);
+        f.sch.addHostToGlobalSet(ip, res);
+    }
+    auto msg = faabric::util::messageFactory("demo", "echo");
+    msg.set_mainhost(f.conf.endpointHost);
+    f.sch.broadcastSnapshotDelete(msg, "some-snapshot");
+    auto deletes = faabric::snapshot::getSnapshotDeletes();
+    REQUIRE_EQ(deletes.size(), 2u);
+    std::set<std::string> hosts;
+    for (auto& [host, key] : deletes) {
+        hosts.insert(host);
+        REQUIRE_EQ(key, std::string("some-snapshot"));
+    }
+    REQUIRE(hosts == (std::set<std::string>{ "10.0.0.7", "10.0.0.8" }));
+    faabric::snapshot::clearMockSnapshotRequests();
+    faabric::util::setMockMode(false);
+    f.planner.reset();
+}
+
+TEST_CASE("scheduler case: legacy topology hints keep their names", "[batch-scheduler][cases]")
+{
+    using namespace faabric::batch_scheduler;
+    REQUIRE_EQ(strToTopologyHint.size(), 5u);
+    for (const auto& [name, hint] : strToTopologyHint) {
+        REQUIRE_EQ(topologyHintToStr.at(hint), name);
+    }
+    REQUIRE(strToTopologyHint.at("NEVER_ALONE") == SchedulingTopologyHint::NEVER_ALONE);
+    REQUIRE((int)MigrationStrategy::BIN_PACK != (int)MigrationStrategy::EMPTY_HOSTS);
+    REQUIRE_EQ(std::string(DEFAULT_STATE_HOST), std::string(ANY_HOST));
+    REQUIRE_EQ(DEFAULT_BACKGROUND_INTERVAL_SECONDS, 30);
+    REQUIRE_EQ(NUM_MPI_EXEC_GRAPH_DETAILS, 2);
 }
