@@ -473,6 +473,12 @@ std::vector<std::pair<uint32_t, int32_t>> Scheduler::awaitThreadResults(
         uint32_t msgId = (uint32_t)req->messages(i).id();
         faabric::Message res = faabric::planner::getPlannerClient().getMessageResult(
           req->appid(), (int)msgId, timeoutMs);
+        if (res.type() == faabric::Message::EMPTY && res.id() != (int)msgId) {
+            // Nothing came back in time: the join must not look like a success
+            SPDLOG_ERROR("Timed out after {} ms waiting for thread {} of app {}", timeoutMs, msgId, req->appid());
+            results.emplace_back(msgId, 1);
+            continue;
+        }
         results.emplace_back(msgId, res.returnvalue());
     }
     return results;

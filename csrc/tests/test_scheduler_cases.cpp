@@ -354,3 +354,24 @@ TEST_CASE("scheduler case: legacy topology hints keep their names", "[batch-sche
     REQUIRE_EQ(DEFAULT_BACKGROUND_INTERVAL_SECONDS, 30);
     REQUIRE_EQ(NUM_MPI_EXEC_GRAPH_DETAILS, 2);
 }
+
+TEST_CASE("scheduler case: a join that times out reports the missing thread as failed", "[scheduler][cases]")
+{
+    ClusterFixture f(2);
+    auto req = faabric::util::batchExecFactory("demo", "never-runs", 2);
+    // one thread's result arrives, the other never does
+    faabric::HostResources res;
+    res.set_slots(2);
+    res.set_usedslots(1);
+    f.sch.setThisHostResources(res);
+    auto done = std::make_shared<faabric::Message>(req->messages(0));
+    done->set_returnvalue(0);
+    done->set_executedhost(f.conf.endpointHost);
+    f.plannerCli.setMessageResult(done);
+    auto results = f.sch.awaitThreadResults(req, 300);
+    REQUIRE_EQ(results.size(), 2u);
+    REQUIRE_EQ(results[0].first, (uint32_t)req->messages(0).id());
+    REQUIRE_EQ(results[0].second, 0);
+    REQUIRE_EQ(results[1].first, (uint32_t)req->messages(1).id());
+    REQUIRE(results[1].second != 0);
+}
