@@ -334,3 +334,154 @@ TEST_CASE("decision cache", "[batch-scheduler]")
     REQUIRE(cache.getCachedDecision(ber2) == nullptr);
     cache.clear();
 }
+
+// ---- one case per case / section of the reference's decision suite ----
+// (reference: tests/test/batch-scheduler/test_scheduling_decisions.cpp)
+namespace {
+void buildDecisionCase(std::string hostA, std::string hostB, std::string hostC, bool expectSingleHost)
+{
+    const int appId = 123, groupId = 345;
+    auto req = faabric::util::batchExecFactory("foo", "bar", 3);
+    SchedulingDecision decision(appId, groupId);
+    faabric::Message msgA = req->messages(0), msgB = req->messages(1), msgC = req->messages(2);
+    decision.addMessage(hostB, msgA);
+    decision.addMessage(hostA, msgB);
+    decision.addMessage(hostC, msgC);
+    REQUIRE_EQ(decision.appId, (decltype(decision.appId))appId);
+    REQUIRE_EQ(decision.groupId, groupId);
+    REQUIRE_EQ(decision.nFunctions, 3);
+    REQUIRE(decision.messageIds == (decltype(decision.messageIds){ msgA.id(), msgB.id(), msgC.id() }));
+    REQUIRE(decision.hosts == (Hosts{ hostB, hostA, hostC }));
+    REQUIRE(decision.uniqueHosts() == (std::set<std::string>{ hostA, hostB, hostC }));
+    REQUIRE(decision.appIdxs == (decltype(decision.appIdxs){ msgA.appidx(), msgB.appidx(), msgC.appidx() }));
+    REQUIRE_EQ(decision.isSingleHost(), expectSingleHost);
+    auto copy = decision;
+    REQUIRE(copy == decision);
+    copy.groupId = 1338;
+    REQUIRE(copy != decision);
+    decision.print();
+}
+}
+
+TEST_CASE("decision case: built over three hosts", "[batch-scheduler][cases]")
+{
+    buildDecisionCase("hostA", "hostB", "hostC", false);
+}
+
+TEST_CASE("decision case: built on one remote host only", "[batch-scheduler][cases]")
+{
+    buildDecisionCase("hostA", "hostA", "hostA", true);
+}
+
+TEST_CASE("decision case: built on this host only", "[batch-scheduler][cases]")
+{
+    std::string here = faabric::util::getSystemConfig().endpointHost;
+    buildDecisionCase(here, here, here, true);
+}
+
+TEST_CASE("decision case: from point-to-point mappings", "[batch-scheduler][cases]")
+{
+    faabric::PointToPointMappings mappings;
+    mappings.set_appid(123);
+    mappings.set_groupid(345);
+    auto* a = mappings.add_mappings();
+    a->set_host("foobar");
+    a->set_messageid(222);
+    a->set_appidx(2);
+    a->set_groupidx(22);
+    auto* b = mappings.add_mappings();
+    b->set_host("bazbaz");
+    b->set_messageid(333);
+    b->set_appidx(3);
+    b->set_groupidx(33);
+    auto actual = SchedulingDecision::fromPointToPointMappings(mappings);
+    REQUIRE_EQ(actual.appId, (decltype(actual.appId))123);
+    REQUIRE_EQ(actual.nFunctions, 2);
+    REQUIRE(actual.appIdxs == (decltype(actual.appIdxs){ 2, 3 }));
+    REQUIRE(actual.groupIdxs == (decltype(actual.groupIdxs){ 22, 33 }));
+    REQUIRE(actual.messageIds == (decltype(actual.messageIds){ 222, 333 }));
+    REQUIRE(actual.hosts == (Hosts{ "foobar", "bazbaz" }));
+}
+
+TEST_CASE("decision case: removing messages one by one until it is empty", "[batch-scheduler][cases]")
+{
+    auto req = faabric::util::batchExecFactory("foo", "bar", 3);
+    SchedulingDecision decision(req->appid(), req->groupid());
+    decision.addMessage("foo", req->messages(0));
+    decision.addMessage("bar", req->messages(1));
+    decision.addMessage("baz", req->messages(2));
+    decision.removeMessage(req->messages(1).id());
+    REQUIRE_EQ(decision.nFunctions, 2);
+    REQUIRE_EQ(decision.hosts.size(), 2u);
+    REQUIRE_EQ(decision.messageIds.size(), 2u);
+    REQUIRE_EQ(decision.appIdxs.size(), 2u);
+    REQUIRE_EQ(decision.groupIdxs.size(), 2u);
+    REQUIRE_EQ(decision.mpiPorts.size(), 2u);
+    REQUIRE_THROWS(decision.removeMessage(req->messages(1).id()));
+    decision.removeMessage(req->messages(0).id());
+    decision.removeMessage(req->messages(2).id());
+    REQUIRE_EQ(decision.nFunctions, 0);
+    REQUIRE(decision.hosts.empty());
+    REQUIRE(decision.messageIds.empty());
+    REQUIRE(decision.appIdxs.empty());
+    REQUIRE(decision.groupIdxs.empty());
+}
+
+TEST_CASE("decision cache case: a cached decision comes back with its hosts and group, until cleared", "[batch-scheduler][cases]")
+{
+    auto& cache = getSchedulingDecisionCache();
+    cache.clear();
+    auto req = faabric::util::batchExecFactory("foo", "bar", 5);
+    Hosts hosts = { "alpha", "alpha", "beta", "gamma", "alpha" };
+    SchedulingDecision decision(123, 345);
+    for (size_t i = 0; i < hosts.size(); i++) {
+        decision.addMessage(hosts[i], req->messages((int)i));
+    }
+    REQUIRE(cache.getCachedDecision(req) == nullptr);
+    cache.addCachedDecision(req, decision);
+    auto actual = cache.getCachedDecision(req);
+    REQUIRE(actual != nullptr);
+    REQUIRE(actual->getHosts() == hosts);
+    REQUIRE_EQ(actual->getGroupId(), 345);
+    cache.clear();
+    REQUIRE(cache.getCachedDecision(req) == nullptr);
+}
+
+TEST_CASE("decision cache case: a decision with the wrong number of hosts is refused", "[batch-scheduler][cases]")
+{
+    auto& cache = getSchedulingDecisionCache();
+    cache.clear();
+    auto req = faabric::util::batchExecFactory("foo", "bar", 3);
+    SchedulingDecision decision(123, 345);
+    decision.addMessage("alpha", req->messages(0));
+    decision.addMessage("alpha", req->messages(1));
+    REQUIRE_THROWS(cache.addCachedDecision(req, decision));
+    cache.clear();
+}
+
+TEST_CASE("decision cache case: two sizes of one function are cached side by side", "[batch-scheduler][cases]")
+{
+    auto& cache = getSchedulingDecisionCache();
+    cache.clear();
+    auto reqA = faabric::util::batchExecFactory("foo", "bar", 3);
+    auto reqB = faabric::util::batchExecFactory("foo", "bar", 5);
+    Hosts hostsA = { "alpha", "alpha", "beta" };
+    Hosts hostsB = { "alpha", "alpha", "beta", "gamma", "gamma" };
+    SchedulingDecision decisionA(123, 345), decisionB(456, 789);
+    for (size_t i = 0; i < hostsA.size(); i++) {
+        decisionA.addMessage(hostsA[i], reqA->messages((int)i));
+    }
+    for (size_t i = 0; i < hostsB.size(); i++) {
+        decisionB.addMessage(hostsB[i], reqB->messages((int)i));
+    }
+    cache.addCachedDecision(reqA, decisionA);
+    cache.addCachedDecision(reqB, decisionB);
+    auto actualA = cache.getCachedDecision(reqA);
+    auto actualB = cache.getCachedDecision(reqB);
+    REQUIRE(actualA != nullptr && actualB != nullptr);
+    REQUIRE(actualA->getHosts() == hostsA);
+    REQUIRE_EQ(actualA->getGroupId(), 345);
+    REQUIRE(actualB->getHosts() == hostsB);
+    REQUIRE_EQ(actualB->getGroupId(), 789);
+    cache.clear();
+}

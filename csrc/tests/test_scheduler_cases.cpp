@@ -274,6 +274,7 @@ TEST_CASE("scheduler case: point-to-point mappings of a decision are set here an
 {
     ClusterFixture f(2);
     faabric::util::setMockMode(true);
+    faabric::transport::clearSentMessages();
     const std::string thisHost = f.conf.endpointHost;
     const std::string otherHost = "10.0.0.1"; // (sorts after this host: ties go to the larger address)
     auto other = std::make_shared<faabric::HostResources>();
