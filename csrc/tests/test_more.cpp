@@ -502,3 +502,48 @@ TEST_CASE("device: tuning file parses, serialises and applies", "[device][config
     }
     REQUIRE(CommTuning::parse("").empty());
 }
+
+// The reference's runner case, section by section
+// (reference: tests/test/runner/test_main.cpp:29-72)
+namespace {
+void mainRunnerCase(bool makeCalls)
+{
+    faabric::planner::PlannerServer plannerServer;
+    plannerServer.start();
+    faabric::planner::getPlanner().reset();
+    {
+        faabric::runner::FaabricMain m(std::make_shared<TestExecutorFactory>());
+        m.startBackground();
+        if (makeCalls) {
+            auto req = faabric::util::batchExecFactory("demo", "echo", 4);
+            // (waiter and executors share an address space: keep ids, not the request)
+            const int appId = req->appid();
+            std::vector<int> msgIds;
+            for (int i = 0; i < 4; i++) {
+                req->mutable_messages(i)->set_inputdata("call " + std::to_string(req->messages(i).id()));
+                msgIds.push_back(req->messages(i).id());
+            }
+            faabric::planner::getPlannerClient().callFunctions(req);
+            for (int id : msgIds) {
+                auto res = faabric::planner::getPlannerClient().getMessageResult(appId, id, 5000);
+                REQUIRE_EQ(res.returnvalue(), 0);
+                REQUIRE_EQ(res.outputdata(), "call " + std::to_string(id));
+            }
+        }
+        m.shutdown();
+    }
+    faabric::planner::getPlanner().reset();
+    plannerServer.stop();
+    faabric::scheduler::getScheduler().reset();
+}
+}
+
+TEST_CASE("runner case: started in the background and shut down without work", "[runner][cases]")
+{
+    mainRunnerCase(false);
+}
+
+TEST_CASE("runner case: four calls through the planner come back from the worker", "[runner][cases]")
+{
+    mainRunnerCase(true);
+}
