@@ -506,6 +506,74 @@ static void registerFunctions()
         return 0;
     });
 
+    // Rank 0 hands every rank a number and waits for each to answer
+    // (reference dist test "MPI checks", tests/dist/mpi/examples/mpi_checks.cpp)
+    mpiFunction("checks", [](int rank, int size, faabric::Message&) {
+        EXPECT(rank >= 0 && size > 1);
+        if (rank == 0) {
+            for (int r = 1; r < size; r++) {
+                int sent = -100 - r;
+                MPI_Send(&sent, 1, MPI_INT, r, 0, MPI_COMM_WORLD);
+            }
+            int responses = 0;
+            for (int r = 1; r < size; r++) {
+                int got = -1;
+                MPI_Recv(&got, 1, MPI_INT, r, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+                EXPECT(got == r);
+                responses++;
+            }
+            EXPECT(responses == size - 1);
+        } else {
+            int got = 0;
+            MPI_Recv(&got, 1, MPI_INT, 0, 0, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+            EXPECT(got == -100 - rank);
+            MPI_Send(&rank, 1, MPI_INT, 0, 0, MPI_COMM_WORLD);
+        }
+        return 0;
+    });
+
+    // One plain send from rank 0 to rank 1 (reference: mpi_send.cpp)
+    mpiFunction("send", [](int rank, int size, faabric::Message&) {
+        if (rank == 0) {
+            int v = 123;
+            MPI_Send(&v, 1, MPI_INT, 1, 0, MPI_COMM_WORLD);
+        } else if (rank == 1) {
+            int v = 0;
+            MPI_Status st{};
+            MPI_Recv(&v, 1, MPI_INT, 0, 0, MPI_COMM_WORLD, &st);
+            EXPECT(v == 123 && st.MPI_SOURCE == 0);
+        }
+        return 0;
+    });
+
+    // Barriers and all-to-alls, a long pause with nothing in flight, then the
+    // same again: connections and queues must survive sitting idle
+    // (reference: mpi_alltoall_sleep.cpp; the pause is 1 s here, 5 s there)
+    mpiFunction("alltoall-sleep", [](int rank, int size, faabric::Message&) {
+        std::vector<int> out(size), in(size);
+        auto round = [&](int i) {
+            MPI_Barrier(MPI_COMM_WORLD);
+            for (int r = 0; r < size; r++) {
+                out[r] = i * 1000 + rank * 10 + r;
+            }
+            MPI_Alltoall(out.data(), 1, MPI_INT, in.data(), 1, MPI_INT, MPI_COMM_WORLD);
+            for (int r = 0; r < size; r++) {
+                if (in[r] != i * 1000 + r * 10 + rank) {
+                    return false;
+                }
+            }
+            return true;
+        };
+        for (int i = 0; i < 500; i++) {
+            EXPECT(round(i));
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(1000));
+        for (int i = 0; i < 500; i++) {
+            EXPECT(round(i));
+        }
+        return 0;
+    });
+
     mpiFunction("sync-async", [](int rank, int size, faabric::Message&) {
         // every rank in turn sends to all: blocking first, then non-blocking
         for (int sender = 0; sender < size; sender++) {

@@ -92,6 +92,9 @@ MPI_FUNCTIONS = [
     "alltoall-many",
     "sync-async",
     "typesize",
+    "checks",
+    "send",
+    "alltoall-sleep",
 ]
 
 
