@@ -1913,6 +1913,15 @@ class SpinLockQueue
 
     bool tryDequeue(T& out) { return ring.tryPop(out); }
 
+    // Same name as the blocking queues' non-blocking take
+    void dequeueIfPresent(T* res)
+    {
+        T v;
+        if (ring.tryPop(v)) {
+            *res = std::move(v);
+        }
+    }
+
     long size() { return (long)ring.sizeApprox(); }
 
     void drain()
